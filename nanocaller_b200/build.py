@@ -1,0 +1,79 @@
+"""In-tree native builds (no pip, no JIT cache): the built .so files sit next to the sources so
+they travel to the GPU box with the repo snapshot.
+
+  libnanocaller_b200.so   nvcc, sm_100a only: CUDA kernels + the C-ABI (include/nanocaller_b200.h)
+  libnc_synth.so          g++: synthetic world generator (test / bench infrastructure)
+
+`python -m nanocaller_b200.build` builds everything that is stale.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB_CUDA = os.path.join(HERE, "libnanocaller_b200.so")
+LIB_SYNTH = os.path.join(HERE, "libnc_synth.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-O3,-fno-strict-aliasing", "-shared",
+]
+CUDA_SOURCES = ["nc_api.cu"]
+CUDA_DEPS_EXT = (".cu", ".cuh", ".h", ".hpp")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print("+", " ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+    if verbose and (r.stdout or r.stderr):
+        print(r.stdout + r.stderr, flush=True)
+
+
+def build_synth(force=False, verbose=False):
+    src = os.path.join(CSRC, "synth.cpp")
+    if force or _stale(LIB_SYNTH, [src]):
+        _run(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", LIB_SYNTH, src], verbose)
+    return LIB_SYNTH
+
+
+def cuda_deps():
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(CUDA_DEPS_EXT)]
+    deps.append(os.path.join(ROOT, "include", "nanocaller_b200.h"))
+    return deps
+
+
+def build_cuda(force=False, verbose=False, extra=()):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        if os.path.exists(LIB_CUDA):
+            return LIB_CUDA  # prebuilt library travelled with the snapshot
+        raise RuntimeError("nvcc not found and no prebuilt libnanocaller_b200.so")
+    if force or _stale(LIB_CUDA, cuda_deps()):
+        srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
+        cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-I", os.path.join(ROOT, "include"), "-I", CSRC,
+                                                   "-o", LIB_CUDA] + srcs + ["-lcudart"]
+        _run(cmd, verbose)
+    return LIB_CUDA
+
+
+def build_all(force=False, verbose=False):
+    build_synth(force, verbose)
+    build_cuda(force, verbose)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose=True)
