@@ -1,0 +1,179 @@
+/* nanocaller_b200.h — C-ABI of libnanocaller_b200.so (sm_100a CUDA, one context per GPU).
+ *
+ * The reference (WGLab/NanoCaller) is pure Python and has no FFI; the drop-in boundary for the
+ * hot path is four Python call sites.  Each entry point below names the reference code it
+ * replaces (paths under nanocaller_src/):
+ *
+ *   get_snp_testing_candidates   generate_SNP_pileups.py:103-278, called at snpCaller.py:86
+ *   get_cnd_pos                  generate_SNP_pileups.py:6-101
+ *   coverage scaling (N1)        snpCaller.py:90-96, 167-173
+ *   SNP_model.call               model_architect.py:36-64,       called at snpCaller.py:111
+ *   haploid_SNP_model.call       model_architect_SNP_haploid.py:33-53, called at snpCaller.py:183
+ *
+ * Conventions: every function returns 0 on success and a negative NC_E* code on failure;
+ * nc_last_error(ctx) returns the message of the last failure on that context.  No exceptions
+ * cross the boundary.  A context is bound to one CUDA device and one stream and is NOT
+ * thread-safe (one host thread per context, like one reference worker process).  All pointer
+ * arguments are HOST pointers unless the name ends in _dev.  There is no CPU fallback: with no
+ * usable CUDA device nc_create fails.
+ */
+#ifndef NANOCALLER_B200_H
+#define NANOCALLER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NC_OK            0
+#define NC_ECUDA        -1   /* CUDA runtime error                          */
+#define NC_EINVAL       -2   /* bad argument                                */
+#define NC_ESTATE       -3   /* call order violated (e.g. scan before stage) */
+#define NC_ENOMEM       -4
+#define NC_EOVERFLOW    -5   /* a count does not fit the device encoding    */
+
+#define NC_ABI_VERSION   1
+
+/* --sequencing (NanoCaller:96) -> neighbour-window rule of get_cnd_pos */
+#define NC_SEQ_ONT             0
+#define NC_SEQ_SHORT_ONT       1
+#define NC_SEQ_UL_ONT          2
+#define NC_SEQ_UL_ONT_EXTREME  3
+#define NC_SEQ_PACBIO          4
+
+/* Tensor geometry (generate_SNP_pileups.py:254): int [5][41][5] per site.  Device and fetch
+ * buffers use a per-site stride of NC_SNP_SITE_STRIDE int16 (16-byte aligned rows). */
+#define NC_SNP_ROWS          5
+#define NC_SNP_COLS          41
+#define NC_SNP_CH            5
+#define NC_SNP_SITE_ELEMS    1025
+#define NC_SNP_SITE_STRIDE   1032
+
+typedef struct nc_ctx nc_ctx;
+
+/* Subset of the reference's `dct` that the SNP path reads (generate_SNP_pileups.py:113-132,
+ * 170-183,202,215,244) plus region['ploidy']. */
+typedef struct NcSnpParams {
+    double  thr_lo, thr_hi;      /* dct['threshold'] = --neighbor_threshold               */
+    double  min_allele_freq;     /* dct['min_allele_freq']                                */
+    int32_t mincov, maxcov;      /* dct['mincov'], dct['maxcov']                          */
+    int32_t min_nbr_sites;       /* dct['min_nbr_sites']                                  */
+    int32_t seq;                 /* NC_SEQ_* from dct['seq']                              */
+    int32_t supplementary;       /* dct['supplementary'] (keeps 0x800 reads when non-zero) */
+    int32_t haploid;             /* region['ploidy'] == 'haploid'                         */
+} NcSnpParams;
+
+/* One chunk of utils.get_chunks (utils.py:67-83): 1-based, both ends inclusive. */
+typedef struct NcChunk {
+    int32_t start, end;
+} NcChunk;
+
+/* Per emitted candidate: everything get_snp_testing_candidates returns besides the tensor. */
+typedef struct NcSiteMeta {
+    int32_t  pos;            /* 1-based v_pos                                                  */
+    int32_t  chunk;          /* index into the chunk array of the scan call                   */
+    int32_t  dp;             /* get_num_aligned() of the column (:164, :259)                  */
+    int32_t  alt;            /* max non-reference A/G/T/C count; freq = alt / dp (:166, :260) */
+    uint16_t fwd[4];         /* forward-strand depth of A,G,T,C before down-sampling (:212)   */
+    uint16_t rev[4];         /* reverse-strand depth (:213)                                   */
+    uint8_t  ref_code;       /* A0 G1 T2 C3 (:104)                                            */
+    uint8_t  n_left;         /* len(ls_total_1)                                               */
+    uint8_t  n_right;        /* len(ls_total_2)                                               */
+    uint8_t  reserved;
+    int32_t  sample_depth;   /* len(sample) after the maxcov cut (:215-216, :263)            */
+} NcSiteMeta;
+
+/* Cumulative device-side timings of the last nc_snp_scan / nc_snp_forward (CUDA events on the
+ * context stream), in milliseconds, and launch counters.  */
+typedef struct NcTimings {
+    float    decode_ms;      /* K0: CIGAR + 4-bit bases -> reference-aligned code rows        */
+    float    scan_ms;        /* K1: column counts, site selection, column store               */
+    float    tensor_ms;      /* K2: neighbour choice + tensor build                           */
+    float    cnn_ms;         /* K3: CNN forward                                               */
+    uint64_t launches;       /* kernels launched by this library on this context since create */
+    uint64_t tensor_bytes;   /* algorithmic bytes of the last K2 launch        */
+    uint64_t scan_bytes;     /* algorithmic bytes of the last K0+K1 pass                      */
+} NcTimings;
+
+int         nc_abi_version(void);
+int         nc_create(int device, nc_ctx** out);
+void        nc_destroy(nc_ctx* ctx);
+const char* nc_last_error(const nc_ctx* ctx);
+int         nc_sync(nc_ctx* ctx);
+int         nc_get_timings(nc_ctx* ctx, NcTimings* out);
+int         nc_device_sm_count(nc_ctx* ctx);
+
+/* Replaces pysam.Samfile/FastaFile opening at generate_SNP_pileups.py:134-137: uploads one
+ * contig's coordinate-sorted alignments in BAM-native encoding (SAM spec 4.2: 0-based pos,
+ * CIGAR as len<<4|op, 4-bit bases two per byte, each read starting on a byte boundary at
+ * seq_off[i]) and the reference characters ref[0..ref_len) whose first base has 0-based
+ * coordinate ref_start.  Arrays may be pageable or pinned; the copy is asynchronous on the
+ * context stream when pinned.  Invalidates earlier scan results. */
+int nc_stage_reads(nc_ctx* ctx, int64_t n_reads, const int32_t* pos, const uint16_t* flag,
+                   const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
+                   const int32_t* l_seq, const uint8_t* seq4, const uint8_t* ref,
+                   int64_t ref_start, int64_t ref_len);
+
+/* K0 — htslib pileup-engine replacement (generate_SNP_pileups.py:156):
+ * turns every staged read into a reference-aligned row of 4-bit codes (A0 G1 T2 C3, 4 for a
+ * deletion / N / anything else).  Called implicitly by nc_snp_scan when needed. */
+int nc_decode_reads(nc_ctx* ctx);
+
+/* get_snp_testing_candidates for a batch of chunks of the staged contig
+ * (generate_SNP_pileups.py:103-278).  `bed` holds n_bed (start,end) pairs of the exclude BED for
+ * this contig (NULL/0 for none), interpreted like the reference does: a site is skipped iff
+ * start <= v_pos < end for some pair (:116-119,161).  On return *n_sites is the number of
+ * emitted candidates over all chunks, ordered by (chunk, position).  Tensors, metadata and the
+ * per-chunk mean sampled depth stay on the device until fetched. */
+int nc_snp_scan(nc_ctx* ctx, const NcSnpParams* params, const NcChunk* chunks, int32_t n_chunks,
+                const int32_t* bed, int32_t n_bed, int64_t* n_sites);
+
+/* Copies results of the last scan to the host.  Any pointer may be NULL.
+ *   mat         int16 [n_sites][NC_SNP_SITE_STRIDE]  (first 1025 of each row = [5][41][5])
+ *   meta        NcSiteMeta [n_sites]
+ *   chunk_depth double [n_chunks]   mean(len(sample)) per chunk (:274), 0 for empty chunks
+ *   chunk_count int64  [n_chunks]   candidates emitted per chunk */
+int nc_snp_fetch(nc_ctx* ctx, int16_t* mat, NcSiteMeta* meta, double* chunk_depth, int64_t* chunk_count);
+
+/* Model weights: packed fp32 blob in the canonical tensor order of
+ * nanocaller_b200/host/weights.py (`pack_snp_blob`): conv1_1 k,b  conv1_2 k,b  conv1_3 k,b
+ * conv2 k,b  conv3 k,b  fc1 k,b  then diploid: fa A G T C fc2 fc3 GT (k,b each)
+ *                                     haploid: fc2 fc3 (k,b each).
+ * Kernels keep Keras layout (HWIO / [in,out]).  train_coverage is the `.coverage` value
+ * (snpCaller.py:48-53; 30 for the haploid model, :73). */
+int nc_load_snp_weights(nc_ctx* ctx, const float* blob, size_t n_floats, double train_coverage, int haploid);
+
+/* snp_model / hap_snp_model forward on the tensors of the last scan, with the coverage scaling
+ * of snpCaller.py:90-96 fused into the input load:
+ *   normalize != 0 : x[:,1:,:,:4] *= fp32(train_coverage / chunk_depth)
+ *   normalize == 0 : --disable_coverage_normalization, per-site train_coverage / dp (float64 product)
+ * probs (host, may be NULL) receives float32 [n_sites][4] = P(A),P(G),P(T),P(C): the [:,1]
+ * softmax columns of the four heads (snpCaller.py:115) or the haploid 4-way softmax (:183).
+ * impl: 0 = tcgen05 tensor-core kernel (default), 1 = fp32 CUDA-core kernel. */
+int nc_snp_forward(nc_ctx* ctx, int normalize, int impl, float* probs);
+
+/* Drop-in for snp_model([x, A_ref, G_ref, T_ref, C_ref]) (snpCaller.py:111) and
+ * hap_snp_model([x, ref]) (:183) on host tensors: x float32 [n][5][41][5] (already scaled),
+ * ref_onehot float32 [n][4].  out: diploid float32 [n][10] = out_A[2] out_G[2] out_T[2] out_C[2]
+ * out_GT[2]; haploid float32 [n][4]. */
+int nc_snp_model_forward(nc_ctx* ctx, const float* x, const float* ref_onehot, int64_t n, int haploid, int impl, float* out);
+
+/* Device pointers of the last scan/forward for callers that keep the data on the GPU
+ * (torch / NCCL plumbing); valid until the next stage/scan on this context. */
+int nc_snp_device_buffers(nc_ctx* ctx, void** mat_dev, void** meta_dev, void** probs_dev, int64_t* n_sites);
+
+/* Indel CNNs (indelCaller.py:85 `indel_model(batch_x_all)`, :171 `hap_indel_model(batch_x)`;
+ * model_architect_indel.py:28-48, model_architect_indels_haploid.py:29-48).  Blob order:
+ * conv1_1 k,b conv1_2 k,b conv1_3 k,b conv2 k,b conv3 k,b fc1 k,b fc2 k,b fc3 k,b (Keras layouts). */
+int nc_load_indel_weights(nc_ctx* ctx, const float* blob, size_t n_floats, int haploid);
+
+/* x float32 [n][15][128][2] (diploid: hstack of hap0, hap1, all — indelCaller.py:83) or
+ * [n][5][128][2] (haploid).  out: float32 [n][4] softmax / [n][1] sigmoid. */
+int nc_indel_model_forward(nc_ctx* ctx, const float* x, int64_t n, int haploid, int impl, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NANOCALLER_B200_H */

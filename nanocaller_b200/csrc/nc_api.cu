@@ -1,0 +1,718 @@
+// libnanocaller_b200.so — C-ABI (include/nanocaller_b200.h) over the sm_100a kernels.
+// One context = one device + one stream; every entry point returns 0 or a negative NC_E* code.
+#include <algorithm>
+#include <cstdarg>
+#include <utility>
+
+#include "nc_common.cuh"
+#include "nc_pileup.cuh"
+#include "nc_cnn.cuh"
+#include "nc_cnn_tc.cuh"
+
+using namespace nc;
+
+namespace {
+
+struct LayerRef { int64_t k = 0, b = 0; int KH = 0, KW = 0, Cin = 0, Cout = 0; };
+
+struct Model {
+    bool loaded = false;
+    int kind = 0;                 // 0 SNP diploid, 1 SNP haploid, 2 indel diploid, 3 indel haploid
+    int Hin = 0, Win = 0, Cin = 0, C1 = 0, C2 = 0, C3 = 0, F1 = 0;
+    int H2 = 0, W2 = 0, H3 = 0, W3 = 0, flat = 0;
+    double train_cov = 0;
+    size_t n_floats = 0;
+    DevBuf w;
+    LayerRef conv[5], fc1;        // conv1_1 conv1_2 conv1_3 conv2 conv3
+    int64_t tail[16][2];          // (kernel, bias) offsets of the tail layers in blob order
+    DevBuf ktab[5];
+    TcModel tc;                   // tensor-core operand images (nc_cnn_tc.cuh)
+};
+
+}  // namespace
+
+struct nc_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    // staged contig
+    bool staged = false, decoded = false, scanned = false;
+    int64_t n_reads = 0, n_cigar = 0, n_seq = 0, ref_start = 0, ref_len = 0;
+    DevBuf d_pos, d_flag, d_cigar_off, d_cigar, d_seq_off, d_lseq, d_seq4, d_ref;
+    // decode products
+    DevBuf d_end, d_nwords, d_opstart, d_pmaxend, d_rowoff, d_rows;
+    int64_t n_row_words = 0;
+    // scan products
+    DevBuf d_flags, d_tile_nbr, d_tile_cand, d_nbr_off, d_cand_off, d_nbr_pos, d_cand_pos, d_bed;
+    DevBuf d_nfirst, d_nlen, d_nbytes, d_noff, d_nrows;
+    DevBuf d_chunks, d_chunk_lo, d_chunk_cnt, d_chunk_off, d_keep, d_keep32, d_outidx;
+    DevBuf d_mat, d_meta, d_depth_sum, d_depth_cnt, d_chunk_depth, d_chunk_count, d_probs;
+    DevBuf d_scan_partial;
+    PinBuf pin;
+    int64_t n_nbr = 0, n_cand = 0, n_slots = 0, n_sites = 0;
+    int32_t n_chunks = 0;
+    bool have_probs = false;
+    int scan_haploid = 0;
+    // CNN
+    Model snp[2], indel[2];
+    DevBuf ws_c1, ws_c2, ws_c3, ws_f1, ws_sf, ws_sd, ws_x, ws_ref, ws_out;
+    // timings
+    cudaEvent_t ev[10] = {};
+    NcTimings tm = {};
+    bool tm_decode = false, tm_scan = false, tm_cnn = false;
+};
+
+namespace {
+
+int fail(nc_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define NC_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(c, e_ == cudaErrorMemoryAllocation ? NC_ENOMEM : NC_ECUDA, "%s:%d %s: %s", \
+                        __FILE__, __LINE__, #call, cudaGetErrorString(e_));                        \
+    } while (0)
+
+#define NC_LAUNCH_CHECK()                                                                          \
+    do {                                                                                           \
+        c->launches++;                                                                             \
+        cudaError_t e_ = cudaGetLastError();                                                       \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(c, NC_ECUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+int upload(nc_ctx* c, DevBuf& d, const void* h, size_t bytes) {
+    NC_CUDA(d.reserve(bytes ? bytes : 16));
+    if (bytes) NC_CUDA(cudaMemcpyAsync(d.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    return NC_OK;
+}
+
+// exclusive scan int32[n] -> int64[n+1]
+int device_scan(nc_ctx* c, const int32_t* in, int64_t n, int64_t* out) {
+    if (n <= 0) { NC_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t), c->stream)); return NC_OK; }
+    const int64_t nparts = div_up(n, kScanTile);
+    NC_CUDA(c->d_scan_partial.reserve((size_t)(nparts + 1) * sizeof(int64_t)));
+    int64_t* part = c->d_scan_partial.as<int64_t>();
+    scan_reduce_kernel<<<(unsigned)nparts, kScanThreads, 0, c->stream>>>(in, n, part); NC_LAUNCH_CHECK();
+    scan_partials_kernel<<<1, 1024, 0, c->stream>>>(part, nparts); NC_LAUNCH_CHECK();
+    scan_apply_kernel<<<(unsigned)nparts, kScanThreads, 0, c->stream>>>(in, n, part, nparts, out); NC_LAUNCH_CHECK();
+    return NC_OK;
+}
+
+// read one int64 from the device (synchronises the stream)
+int read_i64(nc_ctx* c, const int64_t* dev, int64_t* out) {
+    NC_CUDA(c->pin.reserve(64));
+    NC_CUDA(cudaMemcpyAsync(c->pin.p, dev, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    NC_CUDA(cudaStreamSynchronize(c->stream));
+    *out = *c->pin.as<int64_t>();
+    return NC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// model tables
+// ------------------------------------------------------------------------------------------------
+int model_init(nc_ctx* c, Model& M, int kind, const float* blob, size_t n_floats, double train_cov) {
+    M.loaded = false;
+    M.kind = kind; M.train_cov = train_cov;
+    const bool snp = kind < 2;
+    if (snp) { M.Hin = 5; M.Win = 41; M.Cin = 5; M.C1 = 16; M.C2 = 32; M.C3 = 64; M.F1 = 48; }
+    else { M.Hin = kind == 2 ? 15 : 5; M.Win = 128; M.Cin = 2; M.C1 = 8; M.C2 = 32; M.C3 = 48; M.F1 = 32; }
+    M.H2 = M.Hin - 1; M.W2 = (M.Win - 3) / 2 + 1; M.H3 = M.H2 - 1; M.W3 = (M.W2 - 3) / 2 + 1;
+    M.flat = M.H3 * M.W3 * M.C3;
+    int64_t off = 0;
+    auto take = [&](LayerRef& L, int KH, int KW, int Cin, int Cout) {
+        L.KH = KH; L.KW = KW; L.Cin = Cin; L.Cout = Cout;
+        L.k = off; off += (int64_t)KH * KW * Cin * Cout; L.b = off; off += Cout;
+    };
+    take(M.conv[0], 1, 5, M.Cin, M.C1);
+    take(M.conv[1], 5, 1, M.Cin, M.C1);
+    take(M.conv[2], 5, 5, M.Cin, M.C1);
+    take(M.conv[3], 2, 3, 3 * M.C1, M.C2);
+    take(M.conv[4], 2, 3, M.C2, M.C3);
+    take(M.fc1, 1, 1, M.flat, M.F1);
+    int nt = 0;
+    auto tail = [&](int nin, int nout) { M.tail[nt][0] = off; off += (int64_t)nin * nout; M.tail[nt][1] = off; off += nout; nt++; };
+    if (kind == 0) { tail(48, 16); for (int j = 0; j < 4; j++) tail(17, 2); tail(48, 16); tail(24, 8); tail(8, 2); }
+    else if (kind == 1) { tail(48, 16); tail(20, 4); }
+    else if (kind == 2) { tail(32, 24); tail(24, 4); }
+    else { tail(32, 24); tail(24, 1); }
+    if ((size_t)off != n_floats)
+        return fail(c, NC_EINVAL, "weight blob has %zu floats, model kind %d needs %lld", n_floats, kind, (long long)off);
+    M.n_floats = n_floats;
+    int rc = upload(c, M.w, blob, n_floats * sizeof(float));
+    if (rc) return rc;
+    for (int l = 0; l < 5; l++) {
+        const LayerRef& L = M.conv[l];
+        std::vector<int32_t> tab((size_t)L.KH * L.KW * L.Cin);
+        size_t k = 0;
+        for (int kh = 0; kh < L.KH; kh++)
+            for (int kw = 0; kw < L.KW; kw++)
+                for (int ci = 0; ci < L.Cin; ci++) tab[k++] = (kh << 24) | (kw << 16) | ci;
+        rc = upload(c, M.ktab[l], tab.data(), tab.size() * sizeof(int32_t));
+        if (rc) return rc;
+    }
+    NC_CUDA(cudaStreamSynchronize(c->stream));     // `tab` is pageable host memory
+    rc = tc_model_prepare(c->stream, M.tc, kind, blob, n_floats, &c->err);
+    if (rc) return rc;
+    M.loaded = true;
+    return NC_OK;
+}
+
+template <int BN, int MODE>
+void conv_launch(nc_ctx* c, const ConvArgs& a) {
+    const unsigned grid = (unsigned)div_up(a.M, 64);
+    conv_f32_kernel<BN, MODE><<<grid, 16 * (BN / 4), 0, c->stream>>>(a);
+}
+
+int conv_dispatch(nc_ctx* c, int in_mode, const ConvArgs& a) {
+    if (a.M <= 0) return NC_OK;
+    if (in_mode == 1 && a.Cout == 16) conv_launch<16, 1>(c, a);
+    else if (in_mode == 2 && a.Cout == 16) conv_launch<16, 2>(c, a);
+    else if (in_mode != 0) return fail(c, NC_EINVAL, "int16 input only feeds the 16-channel SNP first layer");
+    else if (a.Cout == 8) conv_launch<8, 0>(c, a);
+    else if (a.Cout == 16) conv_launch<16, 0>(c, a);
+    else if (a.Cout == 32) conv_launch<32, 0>(c, a);
+    else if (a.Cout == 48) conv_launch<48, 0>(c, a);
+    else if (a.Cout == 64) conv_launch<64, 0>(c, a);
+    else return fail(c, NC_EINVAL, "unsupported Cout %d", a.Cout);
+    NC_LAUNCH_CHECK();
+    return NC_OK;
+}
+
+TailW tail_weights(const Model& M) {
+    TailW t = {};
+    const float* w = M.w.as<float>();
+    if (M.kind == 0) {
+        t.fa_k = w + M.tail[0][0]; t.fa_b = w + M.tail[0][1];
+        for (int j = 0; j < 4; j++) { t.hk[j] = w + M.tail[1 + j][0]; t.hb[j] = w + M.tail[1 + j][1]; }
+        t.fc2_k = w + M.tail[5][0]; t.fc2_b = w + M.tail[5][1];
+        t.fc3_k = w + M.tail[6][0]; t.fc3_b = w + M.tail[6][1];
+        t.gt_k = w + M.tail[7][0]; t.gt_b = w + M.tail[7][1];
+    } else {
+        t.fc2_k = w + M.tail[0][0]; t.fc2_b = w + M.tail[0][1];
+        t.fc3_k = w + M.tail[1][0]; t.fc3_b = w + M.tail[1][1];
+    }
+    return t;
+}
+
+// fp32 CUDA-core forward over n sites.  in_mode 0: fp32 NHWC input; 1/2: int16 SNP tensors + scale.
+// outputs: SNP diploid -> out_full [n][10] and/or probs [n][4]; SNP haploid -> probs [n][4];
+// indel -> out_full [n][4] / [n][1].
+int cnn_forward_f32(nc_ctx* c, Model& M, int in_mode, const void* in_dev, int64_t in_site_stride, int64_t n,
+                    const NcSiteMeta* meta, const float* ref4, const float* scale_f, const double* scale_d,
+                    float* out_full, float* probs) {
+    if (n <= 0) return NC_OK;
+    const int64_t c1_site = (int64_t)M.Hin * M.Win * 3 * M.C1, c2_site = (int64_t)M.H2 * M.W2 * M.C2;
+    // batch so that the widest activation stays L2-resident (~64 MB)
+    int64_t NB = std::max<int64_t>(64, (64ll << 20) / (c1_site * 4));
+    NB = std::min(NB, n);
+    NC_CUDA(c->ws_c1.reserve((size_t)NB * c1_site * 4));
+    NC_CUDA(c->ws_c2.reserve((size_t)NB * c2_site * 4));
+    NC_CUDA(c->ws_c3.reserve((size_t)NB * M.flat * 4));
+    NC_CUDA(c->ws_f1.reserve((size_t)NB * M.F1 * 4));
+    const float* w = M.w.as<float>();
+    const size_t in_elt = in_mode == 0 ? 4 : 2;
+    const TailW tw = tail_weights(M);
+    for (int64_t b0 = 0; b0 < n; b0 += NB) {
+        const int64_t nb = std::min(NB, n - b0);
+        const char* in_b = reinterpret_cast<const char*>(in_dev) + (size_t)b0 * in_site_stride * in_elt;
+        for (int l = 0; l < 3; l++) {
+            const LayerRef& L = M.conv[l];
+            ConvArgs a = {};
+            a.in = in_b; a.w = w + L.k; a.bias = w + L.b; a.out = c->ws_c1.as<float>();
+            a.scale_f = scale_f ? scale_f + b0 : nullptr; a.scale_d = scale_d ? scale_d + b0 : nullptr;
+            a.ktab = M.ktab[l].as<int32_t>();
+            a.M = nb * M.Hin * M.Win; a.in_site_stride = in_site_stride;
+            a.K = L.KH * L.KW * L.Cin; a.Hin = M.Hin; a.Win = M.Win; a.Cin = M.Cin; a.SW = 1;
+            a.PH = L.KH / 2; a.PW = L.KW / 2; a.Hout = M.Hin; a.Wout = M.Win; a.Cout = M.C1;
+            a.out_cstride = 3 * M.C1; a.out_coff = l * M.C1; a.selu = 1;
+            int rc = conv_dispatch(c, in_mode, a);
+            if (rc) return rc;
+        }
+        {
+            const LayerRef& L = M.conv[3];
+            ConvArgs a = {};
+            a.in = c->ws_c1.p; a.w = w + L.k; a.bias = w + L.b; a.out = c->ws_c2.as<float>();
+            a.ktab = M.ktab[3].as<int32_t>();
+            a.M = nb * M.H2 * M.W2; a.in_site_stride = c1_site;
+            a.K = L.KH * L.KW * L.Cin; a.Hin = M.Hin; a.Win = M.Win; a.Cin = 3 * M.C1; a.SW = 2;
+            a.PH = 0; a.PW = 0; a.Hout = M.H2; a.Wout = M.W2; a.Cout = M.C2; a.out_cstride = M.C2; a.out_coff = 0; a.selu = 1;
+            int rc = conv_dispatch(c, 0, a);
+            if (rc) return rc;
+        }
+        {
+            const LayerRef& L = M.conv[4];
+            ConvArgs a = {};
+            a.in = c->ws_c2.p; a.w = w + L.k; a.bias = w + L.b; a.out = c->ws_c3.as<float>();
+            a.ktab = M.ktab[4].as<int32_t>();
+            a.M = nb * M.H3 * M.W3; a.in_site_stride = c2_site;
+            a.K = L.KH * L.KW * L.Cin; a.Hin = M.H2; a.Win = M.W2; a.Cin = M.C2; a.SW = 2;
+            a.PH = 0; a.PW = 0; a.Hout = M.H3; a.Wout = M.W3; a.Cout = M.C3; a.out_cstride = M.C3; a.out_coff = 0; a.selu = 1;
+            int rc = conv_dispatch(c, 0, a);
+            if (rc) return rc;
+        }
+        {
+            ConvArgs a = {};
+            a.in = c->ws_c3.p; a.w = w + M.fc1.k; a.bias = w + M.fc1.b; a.out = c->ws_f1.as<float>();
+            a.ktab = nullptr; a.M = nb; a.in_site_stride = M.flat;
+            a.K = M.flat; a.Hin = 1; a.Win = 1; a.Cin = M.flat; a.SW = 1; a.PH = 0; a.PW = 0; a.Hout = 1; a.Wout = 1;
+            a.Cout = M.F1; a.out_cstride = M.F1; a.out_coff = 0; a.selu = 1;
+            int rc = conv_dispatch(c, 0, a);
+            if (rc) return rc;
+        }
+        const unsigned tg = (unsigned)div_up(nb, 128);
+        const float* f1 = c->ws_f1.as<float>();
+        const NcSiteMeta* mb = meta ? meta + b0 : nullptr;
+        const float* rb = ref4 ? ref4 + b0 * 4 : nullptr;
+        if (M.kind == 0) snp_tail_kernel<<<tg, 128, 0, c->stream>>>(f1, nb, tw, mb, rb, out_full ? out_full + b0 * 10 : nullptr, probs ? probs + b0 * 4 : nullptr);
+        else if (M.kind == 1) snp_hap_tail_kernel<<<tg, 128, 0, c->stream>>>(f1, nb, tw, mb, rb, probs + b0 * 4);
+        else if (M.kind == 2) indel_tail_kernel<false><<<tg, 128, 0, c->stream>>>(f1, nb, tw, out_full + b0 * 4);
+        else indel_tail_kernel<true><<<tg, 128, 0, c->stream>>>(f1, nb, tw, out_full + b0);
+        NC_LAUNCH_CHECK();
+    }
+    return NC_OK;
+}
+
+int cnn_forward(nc_ctx* c, Model& M, int impl, int in_mode, const void* in_dev, int64_t in_site_stride, int64_t n,
+                const NcSiteMeta* meta, const float* ref4, const float* scale_f, const double* scale_d,
+                float* out_full, float* probs) {
+    if (impl == 1)
+        return cnn_forward_f32(c, M, in_mode, in_dev, in_site_stride, n, meta, ref4, scale_f, scale_d, out_full, probs);
+    if (impl != 0) return fail(c, NC_EINVAL, "impl must be 0 (tcgen05) or 1 (fp32 CUDA cores)");
+    uint64_t launches = 0;
+    int rc = tc_forward(c->stream, M.tc, in_mode, in_dev, in_site_stride, n, meta, ref4, scale_f, scale_d,
+                        M.w.as<float>(), out_full, probs, c->sm_count, &launches, &c->err);
+    c->launches += launches;
+    if (rc == NC_ESTATE) {
+        // no tensor-core image for this model kind yet: the fp32 kernels are the (GPU) implementation
+        return cnn_forward_f32(c, M, in_mode, in_dev, in_site_stride, n, meta, ref4, scale_f, scale_d, out_full, probs);
+    }
+    return rc;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+extern "C" {
+
+int nc_abi_version(void) { return NC_ABI_VERSION; }
+
+int nc_create(int device, nc_ctx** out) {
+    if (!out) return NC_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return NC_ECUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return NC_ECUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NC_ECUDA;
+    if (prop.major != 10) return NC_ECUDA;          // sm_100a cubin only: no fallback path exists
+    nc_ctx* c = new (std::nothrow) nc_ctx();
+    if (!c) return NC_ENOMEM;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NC_ECUDA; }
+    for (auto& e : c->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) { delete c; return NC_ECUDA; }
+    *out = c;
+    return NC_OK;
+}
+
+void nc_destroy(nc_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->d_pos, &c->d_flag, &c->d_cigar_off, &c->d_cigar, &c->d_seq_off, &c->d_lseq, &c->d_seq4, &c->d_ref,
+                      &c->d_end, &c->d_nwords, &c->d_opstart, &c->d_pmaxend, &c->d_rowoff, &c->d_rows, &c->d_flags,
+                      &c->d_tile_nbr, &c->d_tile_cand, &c->d_nbr_off, &c->d_cand_off, &c->d_nbr_pos, &c->d_cand_pos, &c->d_bed,
+                      &c->d_nfirst, &c->d_nlen, &c->d_nbytes, &c->d_noff, &c->d_nrows, &c->d_chunks, &c->d_chunk_lo,
+                      &c->d_chunk_cnt, &c->d_chunk_off, &c->d_keep, &c->d_keep32, &c->d_outidx, &c->d_mat, &c->d_meta,
+                      &c->d_depth_sum, &c->d_depth_cnt, &c->d_chunk_depth, &c->d_chunk_count, &c->d_probs, &c->d_scan_partial,
+                      &c->ws_c1, &c->ws_c2, &c->ws_c3, &c->ws_f1, &c->ws_sf, &c->ws_sd, &c->ws_x, &c->ws_ref, &c->ws_out};
+    for (DevBuf* b : bufs) b->release();
+    for (Model* m : {&c->snp[0], &c->snp[1], &c->indel[0], &c->indel[1]}) {
+        m->w.release();
+        for (auto& t : m->ktab) t.release();
+        tc_model_release(m->tc);
+    }
+    c->pin.release();
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* nc_last_error(const nc_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int nc_sync(nc_ctx* c) {
+    if (!c) return NC_EINVAL;
+    NC_CUDA(cudaSetDevice(c->device));
+    NC_CUDA(cudaStreamSynchronize(c->stream));
+    return NC_OK;
+}
+
+int nc_device_sm_count(nc_ctx* c) { return c ? c->sm_count : NC_EINVAL; }
+
+int nc_get_timings(nc_ctx* c, NcTimings* out) {
+    if (!c || !out) return NC_EINVAL;
+    NC_CUDA(cudaSetDevice(c->device));
+    NC_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->tm_decode) { NC_CUDA(cudaEventElapsedTime(&c->tm.decode_ms, c->ev[0], c->ev[1])); }
+    if (c->tm_scan) {
+        NC_CUDA(cudaEventElapsedTime(&c->tm.scan_ms, c->ev[2], c->ev[3]));
+        NC_CUDA(cudaEventElapsedTime(&c->tm.tensor_ms, c->ev[4], c->ev[5]));
+    }
+    if (c->tm_cnn) { NC_CUDA(cudaEventElapsedTime(&c->tm.cnn_ms, c->ev[6], c->ev[7])); }
+    c->tm.launches = c->launches;
+    *out = c->tm;
+    return NC_OK;
+}
+
+int nc_stage_reads(nc_ctx* c, int64_t n_reads, const int32_t* pos, const uint16_t* flag, const int64_t* cigar_off,
+                   const uint32_t* cigar, const int64_t* seq_off, const int32_t* l_seq, const uint8_t* seq4,
+                   const uint8_t* ref, int64_t ref_start, int64_t ref_len) {
+    if (!c) return NC_EINVAL;
+    NC_CUDA(cudaSetDevice(c->device));
+    c->staged = c->decoded = c->scanned = false;
+    c->have_probs = false;
+    if (n_reads < 0 || ref_len < 0 || ref_start < 0 || (n_reads > 0 && (!pos || !flag || !cigar_off || !seq_off || !l_seq)) || (ref_len > 0 && !ref))
+        return fail(c, NC_EINVAL, "nc_stage_reads: null or negative argument");
+    if (ref_start + ref_len > 0x7fffff00ll) return fail(c, NC_EOVERFLOW, "contig coordinates must fit 31 bits");
+    int64_t n_cig = 0, n_seq = 0;
+    if (n_reads > 0) {
+        if (cigar_off[0] != 0 || seq_off[0] != 0) return fail(c, NC_EINVAL, "offset arrays must start at 0");
+        for (int64_t i = 0; i < n_reads; i++) {
+            if (i && pos[i] < pos[i - 1]) return fail(c, NC_EINVAL, "reads must be coordinate-sorted (read %lld)", (long long)i);
+            if (cigar_off[i + 1] < cigar_off[i] || seq_off[i + 1] < seq_off[i] || l_seq[i] < 0 ||
+                (int64_t)(l_seq[i] + 1) / 2 > seq_off[i + 1] - seq_off[i])
+                return fail(c, NC_EINVAL, "inconsistent offsets at read %lld", (long long)i);
+        }
+        n_cig = cigar_off[n_reads]; n_seq = seq_off[n_reads];
+        if ((n_cig > 0 && !cigar) || (n_seq > 0 && !seq4)) return fail(c, NC_EINVAL, "nc_stage_reads: null payload");
+    }
+    int rc;
+    static const int64_t zero = 0;
+    if ((rc = upload(c, c->d_pos, pos, (size_t)n_reads * 4))) return rc;
+    if ((rc = upload(c, c->d_flag, flag, (size_t)n_reads * 2))) return rc;
+    if ((rc = upload(c, c->d_cigar_off, n_reads ? cigar_off : &zero, (size_t)(n_reads + 1) * 8))) return rc;
+    if ((rc = upload(c, c->d_cigar, cigar, (size_t)n_cig * 4))) return rc;
+    if ((rc = upload(c, c->d_seq_off, n_reads ? seq_off : &zero, (size_t)(n_reads + 1) * 8))) return rc;
+    if ((rc = upload(c, c->d_lseq, l_seq, (size_t)n_reads * 4))) return rc;
+    if ((rc = upload(c, c->d_seq4, seq4, (size_t)n_seq))) return rc;
+    if ((rc = upload(c, c->d_ref, ref, (size_t)ref_len))) return rc;
+    c->n_reads = n_reads; c->n_cigar = n_cig; c->n_seq = n_seq; c->ref_start = ref_start; c->ref_len = ref_len;
+    c->staged = true;
+    return NC_OK;
+}
+
+int nc_decode_reads(nc_ctx* c) {
+    if (!c) return NC_EINVAL;
+    if (!c->staged) return fail(c, NC_ESTATE, "nc_decode_reads before nc_stage_reads");
+    if (c->decoded) return NC_OK;
+    NC_CUDA(cudaSetDevice(c->device));
+    const int64_t n = c->n_reads;
+    NC_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    NC_CUDA(c->d_end.reserve((size_t)std::max<int64_t>(n, 1) * 4));
+    NC_CUDA(c->d_nwords.reserve((size_t)std::max<int64_t>(n, 1) * 4));
+    NC_CUDA(c->d_pmaxend.reserve((size_t)std::max<int64_t>(n, 1) * 4));
+    NC_CUDA(c->d_opstart.reserve((size_t)std::max<int64_t>(c->n_cigar, 1) * 8));
+    NC_CUDA(c->d_rowoff.reserve((size_t)(n + 1) * 8));
+    c->n_row_words = 0;
+    if (n > 0) {
+        const unsigned grid = (unsigned)std::min<int64_t>(div_up(n * 32, 256), (int64_t)c->sm_count * 32);
+        cigar_scan_kernel<<<grid, 256, 0, c->stream>>>(n, c->d_pos.as<int32_t>(), c->d_cigar_off.as<int64_t>(), c->d_cigar.as<uint32_t>(),
+                                                       c->d_end.as<int32_t>(), c->d_nwords.as<int32_t>(), c->d_opstart.as<int2>());
+        NC_LAUNCH_CHECK();
+        prefix_max_kernel<<<1, 1024, 0, c->stream>>>(c->d_end.as<int32_t>(), n, c->d_pmaxend.as<int32_t>());
+        NC_LAUNCH_CHECK();
+        int rc = device_scan(c, c->d_nwords.as<int32_t>(), n, c->d_rowoff.as<int64_t>());
+        if (rc) return rc;
+        if ((rc = read_i64(c, c->d_rowoff.as<int64_t>() + n, &c->n_row_words))) return rc;
+        NC_CUDA(c->d_rows.reserve((size_t)std::max<int64_t>(c->n_row_words, 1) * 4));
+        const unsigned g2 = (unsigned)std::min<int64_t>(n, (int64_t)c->sm_count * 64);
+        row_fill_kernel<<<g2, 128, 0, c->stream>>>(c->d_pos.as<int32_t>(), c->d_end.as<int32_t>(), c->d_cigar_off.as<int64_t>(),
+                                                   c->d_cigar.as<uint32_t>(), c->d_opstart.as<int2>(), c->d_seq_off.as<int64_t>(),
+                                                   c->d_lseq.as<int32_t>(), c->d_seq4.as<uint8_t>(), c->d_rowoff.as<int64_t>(),
+                                                   c->d_nwords.as<int32_t>(), c->d_rows.as<uint32_t>(), n);
+        NC_LAUNCH_CHECK();
+    }
+    NC_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    c->tm_decode = true;
+    // algorithmic bytes of K0: BAM-native input once + the aligned rows once
+    c->tm.scan_bytes = (uint64_t)c->n_cigar * 4 + (uint64_t)c->n_seq + (uint64_t)n * 16 + (uint64_t)c->n_row_words * 4;
+    c->decoded = true;
+    return NC_OK;
+}
+
+int nc_snp_scan(nc_ctx* c, const NcSnpParams* P, const NcChunk* chunks, int32_t n_chunks, const int32_t* bed,
+                int32_t n_bed, int64_t* n_sites_out) {
+    if (!c || !P || !n_sites_out || n_chunks < 0 || (n_chunks > 0 && !chunks) || n_bed < 0 || (n_bed > 0 && !bed))
+        return fail(c, NC_EINVAL, "nc_snp_scan: bad argument");
+    *n_sites_out = 0;
+    if (!c->staged) return fail(c, NC_ESTATE, "nc_snp_scan before nc_stage_reads");
+    if (P->seq < 0 || P->seq > 4) return fail(c, NC_EINVAL, "unknown sequencing mode %d", P->seq);
+    if (P->maxcov < 1 || P->maxcov > 32767) return fail(c, NC_EOVERFLOW, "maxcov %d does not fit the int16 tensor", P->maxcov);
+    NC_CUDA(cudaSetDevice(c->device));
+    int rc = nc_decode_reads(c);
+    if (rc) return rc;
+    c->scanned = false; c->have_probs = false; c->scan_haploid = P->haploid ? 1 : 0;
+    c->n_sites = c->n_slots = c->n_nbr = c->n_cand = 0; c->n_chunks = n_chunks;
+
+    // scanned range = union of the chunks' pileup windows (generate_SNP_pileups.py:156), clipped to the staged reference
+    int64_t lo = INT64_MAX, hi = INT64_MIN;
+    for (int i = 0; i < n_chunks; i++) {
+        if (chunks[i].end < chunks[i].start) continue;
+        lo = std::min<int64_t>(lo, std::max<int64_t>(0, (int64_t)chunks[i].start - 1 - 50000));
+        hi = std::max<int64_t>(hi, (int64_t)chunks[i].end + 50000);
+    }
+    lo = std::max(lo, c->ref_start); hi = std::min(hi, c->ref_start + c->ref_len);
+    NC_CUDA(c->d_chunk_depth.reserve((size_t)std::max(n_chunks, 1) * 8));
+    NC_CUDA(c->d_chunk_count.reserve((size_t)std::max(n_chunks, 1) * 8));
+    NC_CUDA(cudaMemsetAsync(c->d_chunk_depth.p, 0, (size_t)std::max(n_chunks, 1) * 8, c->stream));
+    NC_CUDA(cudaMemsetAsync(c->d_chunk_count.p, 0, (size_t)std::max(n_chunks, 1) * 8, c->stream));
+    NC_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    NC_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    NC_CUDA(cudaEventRecord(c->ev[4], c->stream));
+    NC_CUDA(cudaEventRecord(c->ev[5], c->stream));
+    c->tm_scan = true; c->tm.tensor_bytes = 0;
+    if (n_chunks == 0 || hi <= lo || c->n_reads == 0) { c->scanned = true; return NC_OK; }
+
+    // exclude BED: sort + merge so that "start <= v < end for some interval" is a binary search.
+    // (The reference's IntervalTree raises on null intervals, which disables exclusion: the host mirror handles that.)
+    std::vector<std::pair<int32_t, int32_t>> iv;
+    for (int i = 0; i < n_bed; i++) if (bed[2 * i + 1] > bed[2 * i]) iv.emplace_back(bed[2 * i], bed[2 * i + 1]);
+    std::sort(iv.begin(), iv.end());
+    std::vector<int32_t> merged;
+    for (auto& x : iv) {
+        if (!merged.empty() && x.first <= merged[merged.size() - 1]) merged[merged.size() - 1] = std::max(merged[merged.size() - 1], x.second);
+        else { merged.push_back(x.first); merged.push_back(x.second); }
+    }
+    const int32_t n_merged = (int32_t)(merged.size() / 2);
+    if ((rc = upload(c, c->d_bed, merged.data(), merged.size() * 4))) return rc;
+    if ((rc = upload(c, c->d_chunks, chunks, (size_t)n_chunks * sizeof(NcChunk)))) return rc;
+    NC_CUDA(cudaStreamSynchronize(c->stream));     // host vectors above are pageable
+
+    const uint32_t flag_filter = P->supplementary ? 0x704u : 0xF04u;
+    const int32_t lo_al = (int32_t)lo & ~7;
+    const int64_t n_tiles = div_up(hi - lo_al, kTilePos);
+    NC_CUDA(c->d_flags.reserve((size_t)n_tiles * kTilePos));
+    NC_CUDA(c->d_tile_nbr.reserve((size_t)n_tiles * 4));
+    NC_CUDA(c->d_tile_cand.reserve((size_t)n_tiles * 4));
+    NC_CUDA(c->d_nbr_off.reserve((size_t)(n_tiles + 1) * 8));
+    NC_CUDA(c->d_cand_off.reserve((size_t)(n_tiles + 1) * 8));
+
+    NC_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    ScanArgs sa = {};
+    sa.n_reads = c->n_reads; sa.pos = c->d_pos.as<int32_t>(); sa.end = c->d_end.as<int32_t>(); sa.flag = c->d_flag.as<uint16_t>();
+    sa.pmaxend = c->d_pmaxend.as<int32_t>(); sa.rowoff = c->d_rowoff.as<int64_t>(); sa.nwords = c->d_nwords.as<int32_t>();
+    sa.rows = c->d_rows.as<uint32_t>(); sa.ref = c->d_ref.as<uint8_t>(); sa.ref_start = c->ref_start; sa.ref_len = c->ref_len;
+    sa.lo_al = lo_al; sa.lo = (int32_t)lo; sa.hi = (int32_t)hi; sa.mincov = P->mincov; sa.haploid = P->haploid;
+    sa.thr_lo = P->thr_lo; sa.thr_hi = P->thr_hi; sa.maf = P->min_allele_freq; sa.flag_filter = flag_filter;
+    sa.bed = c->d_bed.as<int32_t>(); sa.n_bed = n_merged;
+    sa.flags = c->d_flags.as<uint8_t>(); sa.tile_nbr = c->d_tile_nbr.as<int32_t>(); sa.tile_cand = c->d_tile_cand.as<int32_t>();
+    scan_kernel<<<(unsigned)n_tiles, kTileThreads, 0, c->stream>>>(sa); NC_LAUNCH_CHECK();
+    if ((rc = device_scan(c, sa.tile_nbr, n_tiles, c->d_nbr_off.as<int64_t>()))) return rc;
+    if ((rc = device_scan(c, sa.tile_cand, n_tiles, c->d_cand_off.as<int64_t>()))) return rc;
+    if ((rc = read_i64(c, c->d_nbr_off.as<int64_t>() + n_tiles, &c->n_nbr))) return rc;
+    if ((rc = read_i64(c, c->d_cand_off.as<int64_t>() + n_tiles, &c->n_cand))) return rc;
+    NC_CUDA(c->d_nbr_pos.reserve((size_t)std::max<int64_t>(c->n_nbr, 1) * 4));
+    NC_CUDA(c->d_cand_pos.reserve((size_t)std::max<int64_t>(c->n_cand, 1) * 4));
+    site_list_kernel<<<(unsigned)n_tiles, kTileThreads, 0, c->stream>>>(c->d_flags.as<uint8_t>(), lo_al, c->d_nbr_off.as<int64_t>(),
+                                                                        c->d_cand_off.as<int64_t>(), c->d_nbr_pos.as<int32_t>(),
+                                                                        c->d_cand_pos.as<int32_t>());
+    NC_LAUNCH_CHECK();
+    // K0 bytes were counted at decode; K1 reads every aligned row once, the reference once, and writes one flag byte per position
+    c->tm.scan_bytes = (uint64_t)c->n_row_words * 4 + (uint64_t)(hi - lo) * 2 + (uint64_t)c->n_reads * 10;
+
+    // neighbour matrix
+    NC_CUDA(c->d_nfirst.reserve((size_t)c->n_reads * 4));
+    NC_CUDA(c->d_nlen.reserve((size_t)c->n_reads * 4));
+    NC_CUDA(c->d_nbytes.reserve((size_t)c->n_reads * 4));
+    NC_CUDA(c->d_noff.reserve((size_t)(c->n_reads + 1) * 8));
+    const unsigned rg = (unsigned)div_up(c->n_reads, 256);
+    nmat_len_kernel<<<rg, 256, 0, c->stream>>>(c->n_reads, c->d_pos.as<int32_t>(), c->d_end.as<int32_t>(), c->d_nbr_pos.as<int32_t>(),
+                                               (int32_t)c->n_nbr, c->d_nfirst.as<int32_t>(), c->d_nlen.as<int32_t>(), c->d_nbytes.as<int32_t>());
+    NC_LAUNCH_CHECK();
+    if ((rc = device_scan(c, c->d_nbytes.as<int32_t>(), c->n_reads, c->d_noff.as<int64_t>()))) return rc;
+    int64_t n_nbytes = 0;
+    if ((rc = read_i64(c, c->d_noff.as<int64_t>() + c->n_reads, &n_nbytes))) return rc;
+    NC_CUDA(c->d_nrows.reserve((size_t)std::max<int64_t>(n_nbytes, 16)));
+    nmat_fill_kernel<<<rg, 256, 0, c->stream>>>(c->n_reads, c->d_pos.as<int32_t>(), c->d_rowoff.as<int64_t>(), c->d_rows.as<uint32_t>(),
+                                                c->d_nbr_pos.as<int32_t>(), c->d_nfirst.as<int32_t>(), c->d_nlen.as<int32_t>(),
+                                                c->d_noff.as<int64_t>(), c->d_nrows.as<uint8_t>());
+    NC_LAUNCH_CHECK();
+
+    // chunk cut
+    NC_CUDA(c->d_chunk_lo.reserve((size_t)n_chunks * 4));
+    NC_CUDA(c->d_chunk_cnt.reserve((size_t)n_chunks * 4));
+    NC_CUDA(c->d_chunk_off.reserve((size_t)(n_chunks + 1) * 8));
+    chunk_ranges_kernel<<<(unsigned)div_up(n_chunks, 128), 128, 0, c->stream>>>(c->d_chunks.as<NcChunk>(), n_chunks, c->d_cand_pos.as<int32_t>(),
+                                                                                c->n_cand, c->d_chunk_lo.as<int32_t>(), c->d_chunk_cnt.as<int32_t>());
+    NC_LAUNCH_CHECK();
+    if ((rc = device_scan(c, c->d_chunk_cnt.as<int32_t>(), n_chunks, c->d_chunk_off.as<int64_t>()))) return rc;
+    if ((rc = read_i64(c, c->d_chunk_off.as<int64_t>() + n_chunks, &c->n_slots))) return rc;
+    NC_CUDA(cudaEventRecord(c->ev[3], c->stream));
+
+    TensorArgs ta = {};
+    ta.n_reads = c->n_reads; ta.pos = sa.pos; ta.end = sa.end; ta.flag = sa.flag; ta.pmaxend = sa.pmaxend;
+    ta.rowoff = sa.rowoff; ta.rows = sa.rows;
+    ta.nfirst = c->d_nfirst.as<int32_t>(); ta.nlen = c->d_nlen.as<int32_t>(); ta.noff = c->d_noff.as<int64_t>(); ta.nrows = c->d_nrows.as<uint8_t>();
+    ta.nbr_pos = c->d_nbr_pos.as<int32_t>(); ta.n_nbr = (int32_t)c->n_nbr; ta.cand_pos = c->d_cand_pos.as<int32_t>();
+    ta.chunks = c->d_chunks.as<NcChunk>(); ta.n_chunks = n_chunks; ta.chunk_off = c->d_chunk_off.as<int64_t>();
+    ta.chunk_lo = c->d_chunk_lo.as<int32_t>(); ta.outidx = nullptr;
+    ta.ref = sa.ref; ta.ref_start = c->ref_start; ta.ref_len = c->ref_len;
+    ta.seq = P->seq; ta.maxcov = P->maxcov; ta.min_nbr_sites = P->min_nbr_sites; ta.flag_filter = flag_filter;
+    ta.n_slots = c->n_slots;
+
+    NC_CUDA(cudaEventRecord(c->ev[4], c->stream));
+    c->n_sites = c->n_slots;
+    if (c->n_slots > 0 && P->min_nbr_sites > 1) {
+        NC_CUDA(c->d_keep.reserve((size_t)c->n_slots));
+        NC_CUDA(c->d_keep32.reserve((size_t)c->n_slots * 4));
+        NC_CUDA(c->d_outidx.reserve((size_t)(c->n_slots + 1) * 8));
+        ta.keep = c->d_keep.as<uint8_t>();
+        keep_kernel<<<(unsigned)div_up(c->n_slots * 32, 128), 128, 0, c->stream>>>(ta); NC_LAUNCH_CHECK();
+        keep_to_i32_kernel<<<(unsigned)div_up(c->n_slots, 256), 256, 0, c->stream>>>(ta.keep, c->n_slots, c->d_keep32.as<int32_t>()); NC_LAUNCH_CHECK();
+        if ((rc = device_scan(c, c->d_keep32.as<int32_t>(), c->n_slots, c->d_outidx.as<int64_t>()))) return rc;
+        if ((rc = read_i64(c, c->d_outidx.as<int64_t>() + c->n_slots, &c->n_sites))) return rc;
+        ta.outidx = c->d_outidx.as<int64_t>();
+    }
+    NC_CUDA(c->d_depth_sum.reserve((size_t)n_chunks * 8));
+    NC_CUDA(c->d_depth_cnt.reserve((size_t)n_chunks * 8));
+    NC_CUDA(cudaMemsetAsync(c->d_depth_sum.p, 0, (size_t)n_chunks * 8, c->stream));
+    NC_CUDA(cudaMemsetAsync(c->d_depth_cnt.p, 0, (size_t)n_chunks * 8, c->stream));
+    if (c->n_sites > 0) {
+        NC_CUDA(c->d_mat.reserve((size_t)c->n_sites * NC_SNP_SITE_STRIDE * 2));
+        NC_CUDA(c->d_meta.reserve((size_t)c->n_sites * sizeof(NcSiteMeta)));
+        ta.mat = c->d_mat.as<int16_t>(); ta.meta = c->d_meta.as<NcSiteMeta>();
+        ta.chunk_depth_sum = c->d_depth_sum.as<unsigned long long>(); ta.chunk_count = c->d_depth_cnt.as<unsigned long long>();
+        const unsigned tg = (unsigned)std::min<int64_t>(div_up(c->n_slots, kTensorWarps), (int64_t)c->sm_count * 16);
+        tensor_kernel<<<tg, kTensorWarps * 32, 0, c->stream>>>(ta); NC_LAUNCH_CHECK();
+    }
+    chunk_depth_kernel<<<(unsigned)div_up(n_chunks, 128), 128, 0, c->stream>>>(c->d_depth_sum.as<unsigned long long>(), c->d_depth_cnt.as<unsigned long long>(),
+                                                                               n_chunks, c->d_chunk_depth.as<double>(), c->d_chunk_count.as<int64_t>());
+    NC_LAUNCH_CHECK();
+    NC_CUDA(cudaEventRecord(c->ev[5], c->stream));
+    c->tm.tensor_bytes = (uint64_t)c->n_sites * (NC_SNP_SITE_STRIDE * 2 + sizeof(NcSiteMeta));   // + per-read terms added by the host from meta
+    c->scanned = true;
+    *n_sites_out = c->n_sites;
+    return NC_OK;
+}
+
+int nc_snp_fetch(nc_ctx* c, int16_t* mat, NcSiteMeta* meta, double* chunk_depth, int64_t* chunk_count) {
+    if (!c) return NC_EINVAL;
+    if (!c->scanned) return fail(c, NC_ESTATE, "nc_snp_fetch before nc_snp_scan");
+    NC_CUDA(cudaSetDevice(c->device));
+    if (mat && c->n_sites) NC_CUDA(cudaMemcpyAsync(mat, c->d_mat.p, (size_t)c->n_sites * NC_SNP_SITE_STRIDE * 2, cudaMemcpyDeviceToHost, c->stream));
+    if (meta && c->n_sites) NC_CUDA(cudaMemcpyAsync(meta, c->d_meta.p, (size_t)c->n_sites * sizeof(NcSiteMeta), cudaMemcpyDeviceToHost, c->stream));
+    if (chunk_depth && c->n_chunks) NC_CUDA(cudaMemcpyAsync(chunk_depth, c->d_chunk_depth.p, (size_t)c->n_chunks * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (chunk_count && c->n_chunks) NC_CUDA(cudaMemcpyAsync(chunk_count, c->d_chunk_count.p, (size_t)c->n_chunks * 8, cudaMemcpyDeviceToHost, c->stream));
+    NC_CUDA(cudaStreamSynchronize(c->stream));
+    return NC_OK;
+}
+
+int nc_load_snp_weights(nc_ctx* c, const float* blob, size_t n_floats, double train_coverage, int haploid) {
+    if (!c || !blob) return fail(c, NC_EINVAL, "nc_load_snp_weights: null argument");
+    NC_CUDA(cudaSetDevice(c->device));
+    return model_init(c, c->snp[haploid ? 1 : 0], haploid ? 1 : 0, blob, n_floats, train_coverage);
+}
+
+int nc_load_indel_weights(nc_ctx* c, const float* blob, size_t n_floats, int haploid) {
+    if (!c || !blob) return fail(c, NC_EINVAL, "nc_load_indel_weights: null argument");
+    NC_CUDA(cudaSetDevice(c->device));
+    return model_init(c, c->indel[haploid ? 1 : 0], haploid ? 3 : 2, blob, n_floats, 0.0);
+}
+
+int nc_snp_forward(nc_ctx* c, int normalize, int impl, float* probs) {
+    if (!c) return NC_EINVAL;
+    if (!c->scanned) return fail(c, NC_ESTATE, "nc_snp_forward before nc_snp_scan");
+    NC_CUDA(cudaSetDevice(c->device));
+    // haploid regions go through hap_snp_model (snpCaller.py:165-183), diploid ones through snp_model (:88-111)
+    Model& M = c->snp[c->scan_haploid ? 1 : 0];
+    if (!M.loaded) return fail(c, NC_ESTATE, "nc_snp_forward: no %s SNP weights loaded", c->scan_haploid ? "haploid" : "diploid");
+    if (normalize && !(M.train_cov > 0)) return fail(c, NC_EINVAL, "coverage normalisation needs a positive train_coverage");
+    const int64_t n = c->n_sites;
+    NC_CUDA(cudaEventRecord(c->ev[6], c->stream));
+    if (n > 0) {
+        NC_CUDA(c->d_probs.reserve((size_t)n * 4 * sizeof(float)));
+        NC_CUDA(c->ws_sf.reserve((size_t)n * sizeof(float)));
+        NC_CUDA(c->ws_sd.reserve((size_t)n * sizeof(double)));
+        site_scale_kernel<<<(unsigned)div_up(n, 256), 256, 0, c->stream>>>(c->d_meta.as<NcSiteMeta>(), n, c->d_chunk_depth.as<double>(),
+                                                                          M.train_cov, normalize, c->ws_sf.as<float>(), c->ws_sd.as<double>());
+        NC_LAUNCH_CHECK();
+        int rc = cnn_forward(c, M, impl, normalize ? 1 : 2, c->d_mat.p, NC_SNP_SITE_STRIDE, n, c->d_meta.as<NcSiteMeta>(), nullptr,
+                             c->ws_sf.as<float>(), c->ws_sd.as<double>(), nullptr, c->d_probs.as<float>());
+        if (rc) return rc;
+    }
+    NC_CUDA(cudaEventRecord(c->ev[7], c->stream));
+    c->tm_cnn = true;
+    c->have_probs = true;
+    if (probs && n > 0) {
+        NC_CUDA(cudaMemcpyAsync(probs, c->d_probs.p, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        NC_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return NC_OK;
+}
+
+int nc_snp_model_forward(nc_ctx* c, const float* x, const float* ref_onehot, int64_t n, int haploid, int impl, float* out) {
+    if (!c || n < 0 || (n > 0 && (!x || !ref_onehot || !out))) return fail(c, NC_EINVAL, "nc_snp_model_forward: bad argument");
+    NC_CUDA(cudaSetDevice(c->device));
+    Model& M = c->snp[haploid ? 1 : 0];
+    if (!M.loaded) return fail(c, NC_ESTATE, "nc_snp_model_forward: no %s SNP weights loaded", haploid ? "haploid" : "diploid");
+    if (n == 0) return NC_OK;
+    const int64_t site = NC_SNP_SITE_ELEMS;
+    const int nout = haploid ? 4 : 10;
+    NC_CUDA(c->ws_x.reserve((size_t)n * site * 4));
+    NC_CUDA(c->ws_ref.reserve((size_t)n * 4 * 4));
+    NC_CUDA(c->ws_out.reserve((size_t)n * nout * 4));
+    NC_CUDA(cudaMemcpyAsync(c->ws_x.p, x, (size_t)n * site * 4, cudaMemcpyHostToDevice, c->stream));
+    NC_CUDA(cudaMemcpyAsync(c->ws_ref.p, ref_onehot, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    int rc = cnn_forward(c, M, impl, 0, c->ws_x.p, site, n, nullptr, c->ws_ref.as<float>(), nullptr, nullptr,
+                         haploid ? nullptr : c->ws_out.as<float>(), haploid ? c->ws_out.as<float>() : nullptr);
+    if (rc) return rc;
+    NC_CUDA(cudaMemcpyAsync(out, c->ws_out.p, (size_t)n * nout * 4, cudaMemcpyDeviceToHost, c->stream));
+    NC_CUDA(cudaStreamSynchronize(c->stream));
+    return NC_OK;
+}
+
+int nc_indel_model_forward(nc_ctx* c, const float* x, int64_t n, int haploid, int impl, float* out) {
+    if (!c || n < 0 || (n > 0 && (!x || !out))) return fail(c, NC_EINVAL, "nc_indel_model_forward: bad argument");
+    NC_CUDA(cudaSetDevice(c->device));
+    Model& M = c->indel[haploid ? 1 : 0];
+    if (!M.loaded) return fail(c, NC_ESTATE, "nc_indel_model_forward: no %s indel weights loaded", haploid ? "haploid" : "diploid");
+    if (n == 0) return NC_OK;
+    const int64_t site = (int64_t)M.Hin * M.Win * M.Cin;
+    const int nout = haploid ? 1 : 4;
+    NC_CUDA(c->ws_x.reserve((size_t)n * site * 4));
+    NC_CUDA(c->ws_out.reserve((size_t)n * nout * 4));
+    NC_CUDA(cudaMemcpyAsync(c->ws_x.p, x, (size_t)n * site * 4, cudaMemcpyHostToDevice, c->stream));
+    int rc = cnn_forward(c, M, impl, 0, c->ws_x.p, site, n, nullptr, nullptr, nullptr, nullptr, c->ws_out.as<float>(), nullptr);
+    if (rc) return rc;
+    NC_CUDA(cudaMemcpyAsync(out, c->ws_out.p, (size_t)n * nout * 4, cudaMemcpyDeviceToHost, c->stream));
+    NC_CUDA(cudaStreamSynchronize(c->stream));
+    return NC_OK;
+}
+
+int nc_snp_device_buffers(nc_ctx* c, void** mat_dev, void** meta_dev, void** probs_dev, int64_t* n_sites) {
+    if (!c) return NC_EINVAL;
+    if (!c->scanned) return fail(c, NC_ESTATE, "nc_snp_device_buffers before nc_snp_scan");
+    if (mat_dev) *mat_dev = c->n_sites ? c->d_mat.p : nullptr;
+    if (meta_dev) *meta_dev = c->n_sites ? c->d_meta.p : nullptr;
+    if (probs_dev) *probs_dev = (c->have_probs && c->n_sites) ? c->d_probs.p : nullptr;
+    if (n_sites) *n_sites = c->n_sites;
+    return NC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,775 @@
+// Pileup kernels of libnanocaller_b200 (sm_100a): the htslib-pileup replacement (K0), the column
+// scan (K1), the neighbour matrix (K1b) and the per-candidate tensor build (K2).
+//
+// Reference being replaced: nanocaller_src/generate_SNP_pileups.py
+//   K0  decode        samfile.pileup column semantics (:156-162)
+//   K1  scan          per-column counts, alt_freq, neighbour / candidate tests (:158-186)
+//   K1b neighbour mat pileup_dict[nb_pos][name] restricted to neighbour sites (:175,:179)
+//   K2  tensor        get_cnd_pos (:6-101) + tensor assembly (:200-263)
+//
+// HBM layout (all per staged contig):
+//   rows     u32 words, one "aligned row" per read: 8 reference positions per word, nibble t of a
+//            word = position 8*w+t (absolute position multiples of 8 start a word, so tiles of any
+//            read line up).  Nibble codes: 0..3 = A,G,T,C (generate_SNP_pileups.py:104), 4 = '*'/'N'
+//            (deletion, ref-skip, N or any IUPAC code), 0xF = read does not cover the position.
+//   flags    u8 per scanned position: bit0 neighbour site, bit1 candidate-eligible.
+//   nrows    per read, the codes of the read at the neighbour sites inside its span, two per byte.
+#pragma once
+#include "nc_common.cuh"
+
+namespace nc {
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t lower_bound_i32(const int32_t* __restrict__ a, int32_t n, int32_t key) {
+    int32_t lo = 0, hi = n;                      // first index with a[i] >= key
+    while (lo < hi) { int32_t mid = (lo + hi) >> 1; if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ int64_t lower_bound_i32_64(const int32_t* __restrict__ a, int64_t n, int32_t key) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+// first index with a[i] > key
+__device__ __forceinline__ int64_t upper_bound_i32_64(const int32_t* __restrict__ a, int64_t n, int32_t key) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (__ldg(a + mid) <= key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ int ref_code_of(uint8_t c) {    // only UPPER-case AGTC count (:137)
+    return c == 'A' ? 0 : c == 'G' ? 1 : c == 'T' ? 2 : c == 'C' ? 3 : 4;
+}
+__device__ __forceinline__ int64_t warp_incl_scan64(int64_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int64_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+    return v;
+}
+__device__ __forceinline__ int32_t warp_incl_scan32(int32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int32_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+    return v;
+}
+// Exclusive block scan; `sm` must hold 33 int64.  Returns the exclusive prefix of v, sets total.
+__device__ __forceinline__ int64_t block_excl_scan64(int64_t v, int64_t* sm, int64_t& total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int64_t inc = warp_incl_scan64(v, lane);
+    if (lane == 31) sm[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int64_t x = lane < nw ? sm[lane] : 0;
+        int64_t xi = warp_incl_scan64(x, lane);
+        sm[lane] = xi - x;
+        if (lane == 31) sm[32] = xi;
+    }
+    __syncthreads();
+    total = sm[32];
+    int64_t r = inc - v + sm[w];
+    __syncthreads();
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan int32 -> int64 (out has n+1 entries, out[n] = total); three launches
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int32_t* __restrict__ in, int64_t n,
+                                                                    int64_t* __restrict__ partial) {
+    __shared__ int64_t sm[33];
+    int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) if (base + i < n) s += in[base + i];
+    int64_t tot;
+    block_excl_scan64(s, sm, tot);
+    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+// single block: in-place exclusive scan of the partials, total -> partial[nparts]
+__global__ void __launch_bounds__(1024) scan_partials_kernel(int64_t* __restrict__ partial, int64_t nparts) {
+    __shared__ int64_t sm[33];
+    int64_t carry = 0;
+    for (int64_t b = 0; b < nparts; b += blockDim.x) {
+        int64_t i = b + threadIdx.x;
+        int64_t v = i < nparts ? partial[i] : 0, tot;
+        int64_t ex = block_excl_scan64(v, sm, tot);
+        if (i < nparts) partial[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) partial[nparts] = carry;
+}
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const int32_t* __restrict__ in, int64_t n,
+                                                                   const int64_t* __restrict__ partial,
+                                                                   int64_t nparts, int64_t* __restrict__ out) {
+    __shared__ int64_t sm[33];
+    int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int32_t v[kScanItems];
+    int64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) { v[i] = base + i < n ? in[base + i] : 0; s += v[i]; }
+    int64_t tot;
+    int64_t ex = block_excl_scan64(s, sm, tot) + partial[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = partial[nparts];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0a — CIGAR prefix scan: one warp per read.  Per op the (reference, query) offsets at which it
+// starts; per read the exclusive reference end and the number of aligned-row words.
+// CIGAR op codes (SAM spec): M0 I1 D2 N3 S4 H5 P6 =7 X8.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t cig_ref_len(uint32_t w) { return ((0x18Du >> (w & 15)) & 1u) ? (int32_t)(w >> 4) : 0; }
+__device__ __forceinline__ int32_t cig_qry_len(uint32_t w) { return ((0x193u >> (w & 15)) & 1u) ? (int32_t)(w >> 4) : 0; }
+__device__ __forceinline__ bool cig_is_match(uint32_t w) { return ((0x181u >> (w & 15)) & 1u) != 0; }
+
+__global__ void __launch_bounds__(256) cigar_scan_kernel(int64_t n_reads, const int32_t* __restrict__ pos,
+                                                         const int64_t* __restrict__ cigar_off,
+                                                         const uint32_t* __restrict__ cigar,
+                                                         int32_t* __restrict__ end, int32_t* __restrict__ nwords,
+                                                         int2* __restrict__ opstart) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads;
+         r += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const int64_t c0 = cigar_off[r], c1 = cigar_off[r + 1];
+        int32_t rr = 0, qq = 0;
+        for (int64_t k = c0; k < c1; k += 32) {
+            const int64_t kk = k + lane;
+            const uint32_t w = kk < c1 ? __ldg(cigar + kk) : 0u;
+            const int32_t rl = cig_ref_len(w), ql = cig_qry_len(w);
+            const int32_t ri = warp_incl_scan32(rl, lane), qi = warp_incl_scan32(ql, lane);
+            if (kk < c1) opstart[kk] = make_int2(rr + ri - rl, qq + qi - ql);
+            rr += __shfl_sync(0xffffffffu, ri, 31);
+            qq += __shfl_sync(0xffffffffu, qi, 31);
+        }
+        if (lane == 0) {
+            const int32_t p = pos[r];
+            if (p < 0) rr = 0;                       // unplaced record: covers nothing
+            end[r] = p + rr;
+            nwords[r] = rr > 0 ? ((p + rr + 7) >> 3) - (p >> 3) : 0;
+        }
+    }
+}
+
+// Inclusive prefix maximum of end[] (single block).  pmaxend[i] > p  <=>  some read j <= i ends after p,
+// which bounds from below the BAM-index window of reads that can cover p.
+__global__ void __launch_bounds__(1024) prefix_max_kernel(const int32_t* __restrict__ end, int64_t n,
+                                                          int32_t* __restrict__ pmax) {
+    __shared__ int32_t sm[33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int32_t carry = INT32_MIN;
+    for (int64_t b = 0; b < n; b += blockDim.x) {
+        const int64_t i = b + threadIdx.x;
+        int32_t v = i < n ? end[i] : INT32_MIN;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int32_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = max(v, t); }
+        if (lane == 31) sm[w] = v;
+        __syncthreads();
+        if (w == 0) {
+            int32_t x = sm[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int32_t t = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x = max(x, t); }
+            sm[lane] = x;
+        }
+        __syncthreads();
+        int32_t pre = w > 0 ? sm[w - 1] : INT32_MIN;
+        v = max(max(v, pre), carry);
+        if (i < n) pmax[i] = v;
+        carry = max(carry, sm[31]);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0b — aligned-row fill: one CTA per read, one thread per output word (8 reference positions).
+// BAM 4-bit base -> code LUT packed in a u64: '='4 A0 C3 M4 G1 R4 S4 V4 T2 W..N 4.
+// ------------------------------------------------------------------------------------------------
+constexpr uint64_t kNibToCode = 0x4444444244414304ull;
+
+__global__ void __launch_bounds__(128) row_fill_kernel(const int32_t* __restrict__ pos, const int32_t* __restrict__ end,
+                                                       const int64_t* __restrict__ cigar_off,
+                                                       const uint32_t* __restrict__ cigar,
+                                                       const int2* __restrict__ opstart,
+                                                       const int64_t* __restrict__ seq_off,
+                                                       const int32_t* __restrict__ l_seq,
+                                                       const uint8_t* __restrict__ seq4,
+                                                       const int64_t* __restrict__ rowoff,
+                                                       const int32_t* __restrict__ nwords,
+                                                       uint32_t* __restrict__ rows, int64_t n_reads) {
+    for (int64_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        const int32_t nw = nwords[r];
+        if (nw == 0) continue;
+        const int32_t p0 = pos[r], span = end[r] - p0, a0 = p0 & ~7;
+        const int64_t c0 = cigar_off[r];
+        const int32_t nops = (int32_t)(cigar_off[r + 1] - c0);
+        const int32_t lseq = l_seq[r];
+        const uint8_t* __restrict__ sq = seq4 + seq_off[r];
+        uint32_t* __restrict__ out = rows + rowoff[r];
+        for (int32_t w = threadIdx.x; w < nw; w += blockDim.x) {
+            const int32_t o = a0 + 8 * w - p0;                 // read-relative offset of nibble 0, in [-7, span)
+            const int32_t os = o < 0 ? 0 : o;
+            int32_t lo = 0, hi = nops;                         // last op whose reference start is <= os
+            while (lo < hi) { int32_t mid = (lo + hi) >> 1; if (__ldg(&opstart[c0 + mid].x) <= os) lo = mid + 1; else hi = mid; }
+            int32_t k = lo - 1;
+            uint32_t cw = __ldg(cigar + c0 + k);
+            int2 st = __ldg(opstart + c0 + k);
+            int32_t rl = cig_ref_len(cw);
+            uint32_t word = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const int32_t oo = o + t;
+                uint32_t nib = 15u;
+                if (oo >= 0 && oo < span) {
+                    while (oo >= st.x + rl) {                  // terminates: oo < span = total reference length
+                        k++;
+                        cw = __ldg(cigar + c0 + k);
+                        st = __ldg(opstart + c0 + k);
+                        rl = cig_ref_len(cw);
+                    }
+                    nib = 4u;                                  // D / N: '*' (appendix C.4); also the default for bad bases
+                    if (cig_is_match(cw)) {
+                        const int32_t q = st.y + (oo - st.x);
+                        if (q < lseq) {
+                            const uint32_t b = __ldg(sq + (q >> 1));
+                            const uint32_t bn = (q & 1) ? (b & 15u) : (b >> 4);
+                            nib = (uint32_t)(kNibToCode >> (4 * bn)) & 15u;
+                        }
+                    }
+                }
+                word |= nib << (4 * t);
+            }
+            out[w] = word;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 — column scan.  One CTA (4 warps) per tile of 1024 reference positions; lane owns 8
+// consecutive positions (one aligned-row word per read).  Per position: n, A/G/T/C counts,
+// alt_freq = max non-ref count / n as a correctly rounded float64 quotient (python int / int,
+// generate_SNP_pileups.py:166), neighbour test (:170-179), candidate-eligibility (:183 without the
+// chunk bounds, which are applied when chunks are cut).
+// ------------------------------------------------------------------------------------------------
+constexpr int kTilePos = 1024;
+constexpr int kTileThreads = 128;
+
+struct ScanArgs {
+    int64_t n_reads;
+    const int32_t* pos; const int32_t* end; const uint16_t* flag; const int32_t* pmaxend;
+    const int64_t* rowoff; const int32_t* nwords; const uint32_t* rows;
+    const uint8_t* ref; int64_t ref_start, ref_len;
+    int32_t lo_al, lo, hi;             // scanned 0-based range [lo, hi); lo_al = lo & ~7
+    int32_t mincov, haploid;
+    double thr_lo, thr_hi, maf;
+    uint32_t flag_filter;
+    const int32_t* bed; int32_t n_bed; // merged, sorted (start, end) pairs; v excluded iff start <= v < end
+    uint8_t* flags; int32_t* tile_nbr; int32_t* tile_cand;
+};
+
+__device__ __forceinline__ bool bed_excluded(const int32_t* __restrict__ bed, int32_t n_bed, int32_t v) {
+    int32_t lo = 0, hi = n_bed;                               // last interval with start <= v
+    while (lo < hi) { int32_t mid = (lo + hi) >> 1; if (__ldg(bed + 2 * mid) <= v) lo = mid + 1; else hi = mid; }
+    return lo > 0 && v < __ldg(bed + 2 * (lo - 1) + 1);
+}
+
+__global__ void __launch_bounds__(kTileThreads) scan_kernel(const ScanArgs a) {
+    __shared__ int32_t s_posw[kTileThreads];
+    __shared__ int32_t s_nw[kTileThreads];
+    __shared__ int64_t s_rowoff[kTileThreads];
+    __shared__ uint8_t s_strand[kTileThreads];
+    __shared__ uint16_t s_acc[9][kTilePos];        // A,G,T,C fwd ; A,G,T,C rev ; n
+    __shared__ int32_t s_cnt, s_nbr, s_cand;
+    __shared__ int64_t s_ilo, s_ihi;
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int32_t P0 = a.lo_al + kTilePos * (int32_t)blockIdx.x;
+    const int32_t P1 = min(P0 + kTilePos, a.hi);
+    for (int i = tid; i < 9 * kTilePos; i += kTileThreads) (&s_acc[0][0])[i] = 0;
+    if (tid == 0) {
+        s_cnt = 0; s_nbr = 0; s_cand = 0;
+        s_ihi = upper_bound_i32_64(a.pos, a.n_reads, P1 - 1);
+        int64_t lo = 0, hi = a.n_reads;                       // first read index whose prefix-max end exceeds P0
+        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (__ldg(a.pmaxend + mid) <= P0) lo = mid + 1; else hi = mid; }
+        s_ilo = lo;
+    }
+    __syncthreads();
+    const int64_t ilo = s_ilo, ihi = s_ihi;
+    const int32_t Wbase = (P0 >> 3) + 32 * w;                 // absolute word index of lane 0
+    const int32_t myw = Wbase + lane;
+
+    uint32_t cf[4][2], cr[4][2], cn[2];
+#pragma unroll
+    for (int b = 0; b < 4; b++) { cf[b][0] = cf[b][1] = cr[b][0] = cr[b][1] = 0; }
+    cn[0] = cn[1] = 0;
+    int pending = 0;
+    const int sbase = w * 256 + lane * 8;
+
+    auto flush = [&]() {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                s_acc[b][sbase + 2 * j] += (cf[b][0] >> (8 * j)) & 255u;
+                s_acc[b][sbase + 2 * j + 1] += (cf[b][1] >> (8 * j)) & 255u;
+                s_acc[4 + b][sbase + 2 * j] += (cr[b][0] >> (8 * j)) & 255u;
+                s_acc[4 + b][sbase + 2 * j + 1] += (cr[b][1] >> (8 * j)) & 255u;
+            }
+            s_acc[8][sbase + 2 * j] += (cn[0] >> (8 * j)) & 255u;
+            s_acc[8][sbase + 2 * j + 1] += (cn[1] >> (8 * j)) & 255u;
+        }
+#pragma unroll
+        for (int b = 0; b < 4; b++) { cf[b][0] = cf[b][1] = cr[b][0] = cr[b][1] = 0; }
+        cn[0] = cn[1] = 0;
+        pending = 0;
+    };
+
+    for (int64_t base = ilo; base < ihi; base += kTileThreads) {
+        const int64_t i = base + tid;
+        if (i < ihi) {
+            const int32_t p = __ldg(a.pos + i), e = __ldg(a.end + i);
+            const uint32_t f = __ldg(a.flag + i);
+            if ((f & a.flag_filter) == 0 && e > P0 && p < P1 && e > p) {
+                const int slot = atomicAdd(&s_cnt, 1);
+                s_posw[slot] = p >> 3;
+                s_nw[slot] = __ldg(a.nwords + i);
+                s_rowoff[slot] = __ldg(a.rowoff + i);
+                s_strand[slot] = (uint8_t)((f >> 4) & 1u);
+            }
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        for (int j = 0; j < cnt; j++) {
+            const int32_t pw = s_posw[j], nw = s_nw[j];
+            if (Wbase + 31 < pw || Wbase >= pw + nw) continue;            // warp-uniform
+            const int32_t rel = myw - pw;
+            uint32_t word = 0xFFFFFFFFu;
+            if (rel >= 0 && rel < nw) word = __ldg(a.rows + s_rowoff[j] + rel);
+            const uint32_t M1 = 0x11111111u;
+            const uint32_t b0 = word & M1, b1 = (word >> 1) & M1, b2 = (word >> 2) & M1, b3 = (word >> 3) & M1;
+            const uint32_t cov = b3 ^ M1;                                   // nibble <= 7: the read has a token here
+            const uint32_t base4 = cov & ~b2;                               // codes 0..3
+            const uint32_t e0 = base4 & ~b1 & ~b0, e1 = base4 & ~b1 & b0, e2 = base4 & b1 & ~b0, e3 = base4 & b1 & b0;
+            const uint32_t M8 = 0x01010101u;
+            cn[0] += cov & M8; cn[1] += (cov >> 4) & M8;
+            if (s_strand[j]) {
+                cr[0][0] += e0 & M8; cr[0][1] += (e0 >> 4) & M8;
+                cr[1][0] += e1 & M8; cr[1][1] += (e1 >> 4) & M8;
+                cr[2][0] += e2 & M8; cr[2][1] += (e2 >> 4) & M8;
+                cr[3][0] += e3 & M8; cr[3][1] += (e3 >> 4) & M8;
+            } else {
+                cf[0][0] += e0 & M8; cf[0][1] += (e0 >> 4) & M8;
+                cf[1][0] += e1 & M8; cf[1][1] += (e1 >> 4) & M8;
+                cf[2][0] += e2 & M8; cf[2][1] += (e2 >> 4) & M8;
+                cf[3][0] += e3 & M8; cf[3][1] += (e3 >> 4) & M8;
+            }
+            if (++pending == 255) flush();
+        }
+        __syncthreads();
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+    }
+    flush();
+
+    // finalize the lane's 8 positions
+    uint32_t out_lo = 0, out_hi = 0;
+    int my_nbr = 0, my_cand = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const int32_t p = P0 + sbase + t;
+        uint32_t fl = 0;
+        const int64_t ri = (int64_t)p - a.ref_start;
+        if (p >= a.lo && p < a.hi && ri >= 0 && ri < a.ref_len) {
+            const int rc = ref_code_of(__ldg(a.ref + ri));
+            const int32_t n = s_acc[8][sbase + t];
+            if (rc < 4 && n > 0 && n >= a.mincov) {
+                int32_t alt = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int32_t c = (int32_t)s_acc[b][sbase + t] + (int32_t)s_acc[4 + b][sbase + t];
+                    if (b != rc) alt = max(alt, c);
+                }
+                const double fq = (double)alt / (double)n;
+                const bool nbr = a.thr_lo <= fq && (a.haploid || fq < a.thr_hi);
+                const bool cand = a.maf <= fq;
+                if ((nbr || cand) && !(a.n_bed > 0 && bed_excluded(a.bed, a.n_bed, p + 1))) {
+                    fl = (nbr ? 1u : 0u) | (cand ? 2u : 0u);
+                    my_nbr += nbr; my_cand += cand;
+                }
+            }
+        }
+        if (t < 4) out_lo |= fl << (8 * t); else out_hi |= fl << (8 * (t - 4));
+    }
+    *reinterpret_cast<uint2*>(a.flags + (size_t)(P0 - a.lo_al) + sbase) = make_uint2(out_lo, out_hi);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        my_nbr += __shfl_xor_sync(0xffffffffu, my_nbr, d);
+        my_cand += __shfl_xor_sync(0xffffffffu, my_cand, d);
+    }
+    if (lane == 0) { atomicAdd(&s_nbr, my_nbr); atomicAdd(&s_cand, my_cand); }
+    __syncthreads();
+    if (tid == 0) { a.tile_nbr[blockIdx.x] = s_nbr; a.tile_cand[blockIdx.x] = s_cand; }
+}
+
+// K1w — ordered compaction of the flagged positions into the neighbour list and the candidate list
+// (1-based v_pos, ascending), using the scanned per-tile counts.
+__global__ void __launch_bounds__(kTileThreads) site_list_kernel(const uint8_t* __restrict__ flags, int32_t lo_al,
+                                                                 const int64_t* __restrict__ nbr_off,
+                                                                 const int64_t* __restrict__ cand_off,
+                                                                 int32_t* __restrict__ nbr_pos,
+                                                                 int32_t* __restrict__ cand_pos) {
+    __shared__ int64_t sm[33];
+    const int tid = threadIdx.x;
+    const size_t idx = (size_t)blockIdx.x * kTilePos + (size_t)tid * 8;
+    const uint2 f = *reinterpret_cast<const uint2*>(flags + idx);
+    const uint64_t bits = ((uint64_t)f.y << 32) | f.x;
+    const int nn = __popcll(bits & 0x0101010101010101ull), nc_ = __popcll(bits & 0x0202020202020202ull);
+    int64_t tot;
+    int64_t on = block_excl_scan64(nn, sm, tot) + nbr_off[blockIdx.x];
+    int64_t oc = block_excl_scan64(nc_, sm, tot) + cand_off[blockIdx.x];
+    const int32_t v0 = lo_al + (int32_t)idx + 1;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const uint32_t fl = (uint32_t)(bits >> (8 * t)) & 255u;
+        if (fl & 1u) nbr_pos[on++] = v0 + t;
+        if (fl & 2u) cand_pos[oc++] = v0 + t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b — neighbour matrix: for every read, its codes at the neighbour sites inside its span.
+// ------------------------------------------------------------------------------------------------
+__global__ void nmat_len_kernel(int64_t n_reads, const int32_t* __restrict__ pos, const int32_t* __restrict__ end,
+                                const int32_t* __restrict__ nbr_pos, int32_t n_nbr, int32_t* __restrict__ nfirst,
+                                int32_t* __restrict__ nlen, int32_t* __restrict__ nbytes) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int32_t p = pos[r], e = end[r];
+    int32_t jf = 0, len = 0;
+    if (e > p) {
+        jf = lower_bound_i32(nbr_pos, n_nbr, p + 1);          // v_pos - 1 >= pos
+        len = lower_bound_i32(nbr_pos, n_nbr, e + 1) - jf;    // v_pos - 1 <  end
+    }
+    nfirst[r] = jf; nlen[r] = len; nbytes[r] = (len + 1) >> 1;
+}
+__global__ void nmat_fill_kernel(int64_t n_reads, const int32_t* __restrict__ pos, const int64_t* __restrict__ rowoff,
+                                 const uint32_t* __restrict__ rows, const int32_t* __restrict__ nbr_pos,
+                                 const int32_t* __restrict__ nfirst, const int32_t* __restrict__ nlen,
+                                 const int64_t* __restrict__ noff, uint8_t* __restrict__ nrows) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int32_t len = nlen[r];
+    if (len == 0) return;
+    const int32_t jf = nfirst[r], pw = pos[r] >> 3;
+    const uint32_t* __restrict__ row = rows + rowoff[r];
+    uint8_t* __restrict__ out = nrows + noff[r];
+    for (int32_t j = 0; j < len; j += 2) {
+        const int32_t p0 = __ldg(nbr_pos + jf + j) - 1;
+        uint32_t b = (__ldg(row + ((p0 >> 3) - pw)) >> (4 * (p0 & 7))) & 15u;
+        if (j + 1 < len) {
+            const int32_t p1 = __ldg(nbr_pos + jf + j + 1) - 1;
+            b |= ((__ldg(row + ((p1 >> 3) - pw)) >> (4 * (p1 & 7))) & 15u) << 4;
+        } else {
+            b |= 0xF0u;
+        }
+        out[j >> 1] = (uint8_t)b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Chunk cut: candidates of chunk c are the eligible sites with start <= v_pos <= end
+// (generate_SNP_pileups.py:183); a site on a shared chunk boundary belongs to both chunks.
+// ------------------------------------------------------------------------------------------------
+__global__ void chunk_ranges_kernel(const NcChunk* __restrict__ chunks, int32_t n_chunks,
+                                    const int32_t* __restrict__ cand_pos, int64_t n_cand,
+                                    int32_t* __restrict__ chunk_lo, int32_t* __restrict__ chunk_cnt) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    const int64_t lo = lower_bound_i32_64(cand_pos, n_cand, chunks[c].start);
+    const int64_t hi = upper_bound_i32_64(cand_pos, n_cand, chunks[c].end);
+    chunk_lo[c] = (int32_t)lo;
+    chunk_cnt[c] = hi > lo ? (int32_t)(hi - lo) : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// get_cnd_pos (generate_SNP_pileups.py:6-101) as distance bins: neighbours p with a < |p - v| <= b,
+// keep k of them, `far` = the k farthest inside the bin instead of the k nearest.  The outermost
+// bin is bounded by the strict radius test, hence b = R - 1.
+// ------------------------------------------------------------------------------------------------
+struct BinSpec { int32_t a, b, k, far; };
+__constant__ BinSpec c_bins[5][7] = {
+    /* ont            */ {{0, 2000, 2, 1}, {2000, 5000, 3, 0}, {5000, 10000, 4, 0}, {10000, 20000, 5, 0}, {20000, 49999, 6, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}},
+    /* short_ont      */ {{0, 2000, 5, 0}, {2000, 5000, 10, 0}, {5000, 49999, 5, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}},
+    /* ul_ont         */ {{0, 2000, 2, 1}, {2000, 5000, 2, 0}, {5000, 10000, 3, 0}, {10000, 20000, 3, 0}, {20000, 40000, 4, 0}, {40000, 50000, 3, 0}, {50000, 99999, 3, 0}},
+    /* ul_ont_extreme */ {{0, 10000, 2, 1}, {10000, 20000, 2, 0}, {20000, 50000, 3, 0}, {50000, 75000, 3, 0}, {75000, 100000, 4, 0}, {100000, 200000, 4, 0}, {200000, 299999, 2, 0}},
+    /* pacbio         */ {{0, 2000, 4, 1}, {2000, 5000, 5, 0}, {5000, 10000, 5, 0}, {10000, 19999, 6, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}},
+};
+__constant__ int c_nbins[5] = {5, 3, 7, 7, 4};
+
+// Warp-cooperative neighbour choice.  Lanes 0..6 own the left bins, lanes 8..14 the right bins.
+// On return every lane holds (sel_lo, sel_cnt) of its bin (cnt 0 elsewhere); n_left / n_right are
+// warp-uniform.  wlo/whi = inclusive v_pos bounds of the chunk's pileup window (:156).
+__device__ __forceinline__ void choose_neighbours(const int32_t* __restrict__ nbr_pos, int32_t n_nbr, int seq,
+                                                  int32_t v, int32_t wlo, int32_t whi, int lane,
+                                                  int32_t& sel_lo, int32_t& sel_cnt, int& n_left, int& n_right) {
+    sel_lo = 0; sel_cnt = 0;
+    const int side = lane >> 3, bin = lane & 7;
+    if (lane < 16 && bin < c_nbins[seq]) {
+        const BinSpec bs = c_bins[seq][bin];
+        int32_t lo, hi;
+        if (side == 0) {                                               // v-b <= p < v-a
+            const int64_t from = max((int64_t)v - bs.b, (int64_t)wlo);
+            lo = lower_bound_i32(nbr_pos, n_nbr, (int32_t)max(from, (int64_t)INT32_MIN + 1));
+            hi = lower_bound_i32(nbr_pos, n_nbr, v - bs.a);
+            if (hi > lo) { sel_cnt = min(hi - lo, bs.k); sel_lo = bs.far ? lo : hi - sel_cnt; }
+        } else {                                                       // v+a < p <= v+b
+            const int64_t to = min((int64_t)v + bs.b, (int64_t)whi);
+            lo = lower_bound_i32(nbr_pos, n_nbr, v + bs.a + 1);
+            hi = lower_bound_i32(nbr_pos, n_nbr, (int32_t)min(to + 1, (int64_t)INT32_MAX));
+            if (hi > lo) { sel_cnt = min(hi - lo, bs.k); sel_lo = bs.far ? hi - sel_cnt : lo; }
+        }
+    }
+    const uint32_t full = 0xffffffffu;
+    int l = 0, r = 0;
+#pragma unroll
+    for (int b = 0; b < 7; b++) {
+        l += __shfl_sync(full, sel_cnt, b);
+        r += __shfl_sync(full, sel_cnt, 8 + b);
+    }
+    n_left = l; n_right = r;
+}
+
+// Neighbour-list index of tensor column c (0..40) or -1 for padding / the candidate column.
+__device__ __forceinline__ int32_t column_neighbour(int c, int seq, int32_t sel_lo, int32_t sel_cnt, int n_left, int n_right) {
+    const uint32_t full = 0xffffffffu;
+    const int nb = c_nbins[seq];
+    int32_t j = -1;
+    int il = c - (20 - n_left);          // rank inside the sorted left list
+    int ir = c - 21;                     // rank inside the sorted right list
+    const bool is_l = c < 20 && il >= 0, is_r = c > 20 && c < 41 && ir < n_right;
+#pragma unroll
+    for (int b = 6; b >= 0; b--) {       // left list ascending = farthest bin first
+        const int32_t lo = __shfl_sync(full, sel_lo, b), cnt = __shfl_sync(full, sel_cnt, b);
+        if (b < nb && is_l && j < 0) { if (il < cnt) j = lo + il; else il -= cnt; }
+    }
+#pragma unroll
+    for (int b = 0; b < 7; b++) {        // right list ascending = nearest bin first
+        const int32_t lo = __shfl_sync(full, sel_lo, 8 + b), cnt = __shfl_sync(full, sel_cnt, 8 + b);
+        if (b < nb && is_r && j < 0) { if (ir < cnt) j = lo + ir; else ir -= cnt; }
+    }
+    return j;
+}
+
+struct TensorArgs {
+    int64_t n_reads;
+    const int32_t* pos; const int32_t* end; const uint16_t* flag; const int32_t* pmaxend;
+    const int64_t* rowoff; const uint32_t* rows;
+    const int32_t* nfirst; const int32_t* nlen; const int64_t* noff; const uint8_t* nrows;
+    const int32_t* nbr_pos; int32_t n_nbr;
+    const int32_t* cand_pos;
+    const NcChunk* chunks; int32_t n_chunks;
+    const int64_t* chunk_off;          // [n_chunks+1] slot offsets (before the min_nbr_sites filter)
+    const int32_t* chunk_lo;           // first candidate-list index of every chunk
+    const int64_t* outidx;             // [n_slots+1] output row of every slot, or nullptr = identity
+    const uint8_t* ref; int64_t ref_start, ref_len;
+    int32_t seq, maxcov, min_nbr_sites;
+    uint32_t flag_filter;
+    int64_t n_slots;
+    int16_t* mat; NcSiteMeta* meta;
+    unsigned long long* chunk_depth_sum; unsigned long long* chunk_count;
+    uint8_t* keep;                     // K2a only
+};
+
+__device__ __forceinline__ int slot_chunk(const int64_t* __restrict__ chunk_off, int32_t n_chunks, int64_t s) {
+    int lo = 0, hi = n_chunks;           // last chunk with chunk_off[c] <= s
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(chunk_off + mid) <= s) lo = mid + 1; else hi = mid; }
+    return lo - 1;
+}
+
+// K2a — only when min_nbr_sites > 1: keep[s] = len(total_rlist) >= min_nbr_sites (:244).
+__global__ void __launch_bounds__(128) keep_kernel(const TensorArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= a.n_slots) return;
+    const int c = slot_chunk(a.chunk_off, a.n_chunks, s);
+    const int32_t v = __ldg(a.cand_pos + a.chunk_lo[c] + (s - a.chunk_off[c]));
+    const int32_t wlo = max(1, a.chunks[c].start - 50000), whi = a.chunks[c].end + 50000;
+    int32_t sel_lo, sel_cnt; int nl, nr;
+    choose_neighbours(a.nbr_pos, a.n_nbr, a.seq, v, wlo, whi, lane, sel_lo, sel_cnt, nl, nr);
+    if (lane == 0) a.keep[s] = (nl + nr + 1 >= a.min_nbr_sites) ? 1 : 0;
+}
+__global__ void keep_to_i32_kernel(const uint8_t* __restrict__ keep, int64_t n, int32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = keep[i];
+}
+
+// K2 — tensor build, one warp per candidate (generate_SNP_pileups.py:200-263).
+//   lanes as READS   walk the BAM-index window of reads that can cover the candidate, 32 at a time:
+//                    admission, code at the candidate (one nibble of the aligned row), strand depths;
+//   lanes as COLUMNS for every sampled read (first maxcov in BAM order, see DESIGN.md on :215-216) the
+//                    read's neighbour-matrix row is broadcast and lane c looks up the code at column c
+//                    (columns 32..40 ride on lanes 0..8), counting into 4 x 4 16-bit fields.
+constexpr int kTensorWarps = 4;
+
+__global__ void __launch_bounds__(kTensorWarps * 32) tensor_kernel(const TensorArgs a) {
+    __shared__ __align__(16) int16_t s_out[kTensorWarps][NC_SNP_SITE_STRIDE];
+    const uint32_t full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int16_t* buf = s_out[wib];
+
+    for (int64_t s = (int64_t)blockIdx.x * kTensorWarps + wib; s < a.n_slots; s += (int64_t)gridDim.x * kTensorWarps) {
+        int64_t orow = s;
+        if (a.outidx) {
+            orow = __ldg(a.outidx + s);
+            if (__ldg(a.outidx + s + 1) == orow) continue;                // dropped by min_nbr_sites
+        }
+        const int c = slot_chunk(a.chunk_off, a.n_chunks, s);
+        const int32_t v = __ldg(a.cand_pos + a.chunk_lo[c] + (s - a.chunk_off[c]));
+        const int32_t p = v - 1;
+        const int32_t wlo = max(1, a.chunks[c].start - 50000), whi = a.chunks[c].end + 50000;
+
+        // ---- neighbour choice and the lane's columns
+        int32_t sel_lo, sel_cnt; int nl, nr;
+        choose_neighbours(a.nbr_pos, a.n_nbr, a.seq, v, wlo, whi, lane, sel_lo, sel_cnt, nl, nr);
+        const int32_t j0 = column_neighbour(lane, a.seq, sel_lo, sel_cnt, nl, nr);
+        const int32_t j1 = column_neighbour(lane + 32, a.seq, sel_lo, sel_cnt, nl, nr);
+        const int rc_v = ref_code_of(__ldg(a.ref + ((int64_t)p - a.ref_start)));
+        int rc0 = 4, rc1 = 4;                                            // reference code of the lane's columns
+        if (lane == 20) rc0 = rc_v;
+        if (j0 >= 0) rc0 = ref_code_of(__ldg(a.ref + ((int64_t)__ldg(a.nbr_pos + j0) - 1 - a.ref_start)));
+        if (j1 >= 0) rc1 = ref_code_of(__ldg(a.ref + ((int64_t)__ldg(a.nbr_pos + j1) - 1 - a.ref_start)));
+
+        // ---- read window
+        const int64_t ihi = upper_bound_i32_64(a.pos, a.n_reads, p);
+        int64_t ilo;
+        {
+            int64_t lo = 0, hi = ihi;
+            while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (__ldg(a.pmaxend + mid) <= p) lo = mid + 1; else hi = mid; }
+            ilo = lo;
+        }
+
+        uint64_t acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+        uint64_t fwd = 0, rev = 0;                                        // per-lane 4 x 16-bit strand depths
+        int32_t dp = 0, sampled = 0;
+
+        for (int64_t base = ilo; base < ihi; base += 32) {
+            const int64_t i = base + lane;
+            bool cover = false;
+            uint32_t code = 4;
+            int32_t nf = 0, nlen = 0;
+            int64_t noff = 0;
+            if (i < ihi) {
+                const int32_t rp = __ldg(a.pos + i), re = __ldg(a.end + i);
+                const uint32_t f = __ldg(a.flag + i);
+                if ((f & a.flag_filter) == 0 && rp <= p && p < re) {
+                    cover = true;
+                    code = (__ldg(a.rows + __ldg(a.rowoff + i) + ((p >> 3) - (rp >> 3))) >> (4 * (p & 7))) & 15u;
+                    if (code < 4) { if (f & 0x10u) rev += 1ull << (16 * code); else fwd += 1ull << (16 * code); }
+                    nf = __ldg(a.nfirst + i); nlen = __ldg(a.nlen + i); noff = __ldg(a.noff + i);
+                }
+            }
+            const uint32_t cm = __ballot_sync(full, cover);
+            if (cm == 0) continue;
+            dp += __popc(cm);
+            // sample = the first maxcov covering reads in BAM order
+            uint32_t take = cm;
+            const int room = a.maxcov - sampled;
+            if (__popc(cm) > room) {
+                // keep the lowest `room` set bits
+                uint32_t m = cm, kept = 0;
+                for (int q = 0; q < room; q++) { const uint32_t low = m & (0u - m); kept |= low; m ^= low; }
+                take = room > 0 ? kept : 0u;
+            }
+            sampled += __popc(take);
+            while (take) {
+                const int k = __ffs(take) - 1;
+                take &= take - 1;
+                const uint32_t ci = __shfl_sync(full, code, k);
+                const int32_t rnf = __shfl_sync(full, nf, k), rnl = __shfl_sync(full, nlen, k);
+                const int64_t rno = __shfl_sync(full, noff, k);
+                if (ci >= 4) continue;                                     // '*' / N at the candidate: counted in depth only
+                uint32_t b0 = 4, b1 = 4;
+                if (lane == 20) b0 = ci;
+                if (j0 >= 0) {
+                    const uint32_t rel = (uint32_t)(j0 - rnf);
+                    if (rel < (uint32_t)rnl) { const uint32_t by = __ldg(a.nrows + rno + (rel >> 1)); b0 = (rel & 1u) ? (by >> 4) : (by & 15u); }
+                }
+                if (j1 >= 0) {
+                    const uint32_t rel = (uint32_t)(j1 - rnf);
+                    if (rel < (uint32_t)rnl) { const uint32_t by = __ldg(a.nrows + rno + (rel >> 1)); b1 = (rel & 1u) ? (by >> 4) : (by & 15u); }
+                }
+                const uint64_t i0 = b0 < 4 ? 1ull << (16 * b0) : 0ull, i1 = b1 < 4 ? 1ull << (16 * b1) : 0ull;
+                switch (ci) {                                              // warp-uniform
+                    case 0: acc0[0] += i0; acc1[0] += i1; break;
+                    case 1: acc0[1] += i0; acc1[1] += i1; break;
+                    case 2: acc0[2] += i0; acc1[2] += i1; break;
+                    default: acc0[3] += i0; acc1[3] += i1; break;
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            fwd += __shfl_xor_sync(full, fwd, d);
+            rev += __shfl_xor_sync(full, rev, d);
+        }
+
+        // ---- assemble [5][41][5] in shared memory, then 16-byte coalesced stores
+        for (int i = lane; i < NC_SNP_SITE_STRIDE / 8; i += 32) reinterpret_cast<uint4*>(buf)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int col = lane + 32 * half;
+            const int rc = half ? rc1 : rc0;
+            const bool real = half ? (j1 >= 0) : (j0 >= 0 || lane == 20);
+            if (real && col < NC_SNP_COLS) {
+                if (rc < 4) buf[col * 5 + rc] = 1;                                          // :249-251 total_ref
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint64_t av = half ? acc1[i] : acc0[i];
+                    int16_t* o = buf + ((i + 1) * NC_SNP_COLS + col) * 5;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int32_t cnt = (int32_t)((av >> (16 * b)) & 0xFFFFull);
+                        o[b] = (int16_t)(b == rc ? -cnt : cnt);                             // :253 mat * (1 - 2*total_ref)
+                    }
+                    o[4] = (i == rc_v) ? 1 : 0;                                             // :252
+                }
+            }
+        }
+        __syncwarp();
+        uint4* dst = reinterpret_cast<uint4*>(a.mat + orow * NC_SNP_SITE_STRIDE);
+        for (int i = lane; i < NC_SNP_SITE_STRIDE / 8; i += 32) dst[i] = reinterpret_cast<const uint4*>(buf)[i];
+        __syncwarp();
+
+        if (lane == 0) {
+            NcSiteMeta m;
+            m.pos = v; m.chunk = c; m.dp = dp;
+            int32_t alt = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint32_t fb = (uint32_t)((fwd >> (16 * b)) & 0xFFFFull), rb = (uint32_t)((rev >> (16 * b)) & 0xFFFFull);
+                m.fwd[b] = (uint16_t)fb; m.rev[b] = (uint16_t)rb;
+                if (b != rc_v) alt = max(alt, (int32_t)(fb + rb));
+            }
+            m.alt = alt;
+            m.ref_code = (uint8_t)rc_v; m.n_left = (uint8_t)nl; m.n_right = (uint8_t)nr; m.reserved = 0;
+            m.sample_depth = sampled;
+            a.meta[orow] = m;
+            atomicAdd(a.chunk_depth_sum + c, (unsigned long long)sampled);
+            atomicAdd(a.chunk_count + c, 1ull);
+        }
+    }
+}
+
+// mean(current_depth) per chunk (generate_SNP_pileups.py:274): exact integer sum / count in float64.
+__global__ void chunk_depth_kernel(const unsigned long long* __restrict__ sum, const unsigned long long* __restrict__ cnt,
+                                   int32_t n_chunks, double* __restrict__ depth, int64_t* __restrict__ count) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    depth[c] = cnt[c] ? (double)sum[c] / (double)cnt[c] : 0.0;
+    count[c] = (int64_t)cnt[c];
+}
+
+}  // namespace nc

@@ -1,0 +1,209 @@
+"""ctypes binding of libnanocaller_b200.so (include/nanocaller_b200.h).
+
+There is no CPU fallback: if the CUDA library cannot be built/loaded, or no sm_100 device is
+present, constructing a `Context` raises."""
+import ctypes
+import os
+
+import numpy as np
+
+from .. import build as _build
+
+NC_OK, NC_ECUDA, NC_EINVAL, NC_ESTATE, NC_ENOMEM, NC_EOVERFLOW = 0, -1, -2, -3, -4, -5
+SEQ_CODES = {"ont": 0, "short_ont": 1, "ul_ont": 2, "ul_ont_extreme": 3, "pacbio": 4}
+SITE_ELEMS, SITE_STRIDE = 1025, 1032
+
+EXPORTS = ["nc_abi_version", "nc_create", "nc_destroy", "nc_last_error", "nc_sync", "nc_get_timings",
+           "nc_device_sm_count", "nc_stage_reads", "nc_decode_reads", "nc_snp_scan", "nc_snp_fetch",
+           "nc_load_snp_weights", "nc_snp_forward", "nc_snp_model_forward", "nc_snp_device_buffers",
+           "nc_load_indel_weights", "nc_indel_model_forward"]
+
+
+class NcSnpParams(ctypes.Structure):
+    _fields_ = [("thr_lo", ctypes.c_double), ("thr_hi", ctypes.c_double), ("min_allele_freq", ctypes.c_double),
+                ("mincov", ctypes.c_int32), ("maxcov", ctypes.c_int32), ("min_nbr_sites", ctypes.c_int32),
+                ("seq", ctypes.c_int32), ("supplementary", ctypes.c_int32), ("haploid", ctypes.c_int32)]
+
+
+class NcTimings(ctypes.Structure):
+    _fields_ = [("decode_ms", ctypes.c_float), ("scan_ms", ctypes.c_float), ("tensor_ms", ctypes.c_float),
+                ("cnn_ms", ctypes.c_float), ("launches", ctypes.c_uint64), ("tensor_bytes", ctypes.c_uint64),
+                ("scan_bytes", ctypes.c_uint64)]
+
+
+CHUNK_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4")])
+META_DTYPE = np.dtype([("pos", "<i4"), ("chunk", "<i4"), ("dp", "<i4"), ("alt", "<i4"), ("fwd", "<u2", (4,)),
+                       ("rev", "<u2", (4,)), ("ref_code", "u1"), ("n_left", "u1"), ("n_right", "u1"),
+                       ("reserved", "u1"), ("sample_depth", "<i4")])
+assert META_DTYPE.itemsize == 40
+
+_lib = None
+
+
+class NcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libnanocaller_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def library_path():
+    return _build.LIB_CUDA
+
+
+def load_library():
+    """Build (if stale and nvcc is present) and load the CUDA library; raises when impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build_cuda()
+    lib = ctypes.CDLL(path)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+    lib.nc_abi_version.restype = ctypes.c_int
+    lib.nc_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    lib.nc_destroy.argtypes = [vp]
+    lib.nc_destroy.restype = None
+    lib.nc_last_error.argtypes = [vp]
+    lib.nc_last_error.restype = ctypes.c_char_p
+    lib.nc_sync.argtypes = [vp]
+    lib.nc_get_timings.argtypes = [vp, ctypes.POINTER(NcTimings)]
+    lib.nc_device_sm_count.argtypes = [vp]
+    lib.nc_stage_reads.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64]
+    lib.nc_decode_reads.argtypes = [vp]
+    lib.nc_snp_scan.argtypes = [vp, ctypes.POINTER(NcSnpParams), vp, i32, vp, i32, ctypes.POINTER(i64)]
+    lib.nc_snp_fetch.argtypes = [vp, vp, vp, vp, vp]
+    lib.nc_load_snp_weights.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_double, ctypes.c_int]
+    lib.nc_snp_forward.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    lib.nc_snp_model_forward.argtypes = [vp, vp, vp, i64, ctypes.c_int, ctypes.c_int, vp]
+    lib.nc_snp_device_buffers.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64)]
+    lib.nc_load_indel_weights.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_int]
+    lib.nc_indel_model_forward.argtypes = [vp, vp, i64, ctypes.c_int, ctypes.c_int, vp]
+    for name in EXPORTS:
+        if name not in ("nc_destroy", "nc_last_error"):
+            getattr(lib, name).restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def snp_params(dct, ploidy):
+    """NcSnpParams from the reference's `dct` (generate_SNP_pileups.py:113-132,170-183,202,215,244)."""
+    return NcSnpParams(float(dct["threshold"][0]), float(dct["threshold"][1]), float(dct["min_allele_freq"]),
+                       int(dct["mincov"]), int(dct["maxcov"]), int(dct["min_nbr_sites"]), SEQ_CODES[dct["seq"]],
+                       1 if dct.get("supplementary") else 0, 1 if ploidy == "haploid" else 0)
+
+
+class Context:
+    """One GPU, one stream — the analogue of one reference worker process."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self._lib.nc_create(device, ctypes.byref(h))
+        if rc != NC_OK:
+            raise NcError(rc, "nc_create(device=%d) failed: no usable sm_100 CUDA device (there is no CPU fallback)" % device)
+        self._h = h
+        self.device = device
+        self.n_sites = 0
+        self.n_chunks = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != NC_OK:
+            raise NcError(rc, (self._lib.nc_last_error(self._h) or b"").decode())
+
+    # ---- staging
+    def stage_reads(self, rs, ref_start=0):
+        arrs = (rs.pos, rs.flag, rs.cigar_off, rs.cigar, rs.seq_off, rs.l_seq, rs.seq4, rs.ref)
+        self._keep = arrs
+        self._check(self._lib.nc_stage_reads(self._h, rs.n, _p(rs.pos), _p(rs.flag), _p(rs.cigar_off), _p(rs.cigar),
+                                             _p(rs.seq_off), _p(rs.l_seq), _p(rs.seq4), _p(rs.ref), ref_start, len(rs.ref)))
+
+    def stage_arrays(self, pos, flag, cigar_off, cigar, seq_off, l_seq, seq4, ref, ref_start=0):
+        self._keep = (pos, flag, cigar_off, cigar, seq_off, l_seq, seq4, ref)
+        self._check(self._lib.nc_stage_reads(self._h, len(pos), _p(pos), _p(flag), _p(cigar_off), _p(cigar), _p(seq_off),
+                                             _p(l_seq), _p(seq4), _p(ref), ref_start, len(ref)))
+
+    def decode_reads(self):
+        self._check(self._lib.nc_decode_reads(self._h))
+
+    # ---- SNP feature path
+    def snp_scan(self, params, chunks, bed=None):
+        """chunks: iterable of (start, end) 1-based inclusive; bed: iterable of (start, end) or None."""
+        ch = np.array([(int(s), int(e)) for s, e in chunks], dtype=CHUNK_DTYPE)
+        bd = np.ascontiguousarray(np.array(bed, dtype=np.int32).reshape(-1, 2)) if bed is not None and len(bed) else None
+        n = ctypes.c_int64(0)
+        self._check(self._lib.nc_snp_scan(self._h, ctypes.byref(params), _p(ch) if len(ch) else None, len(ch), _p(bd),
+                                          0 if bd is None else len(bd), ctypes.byref(n)))
+        self.n_sites, self.n_chunks = n.value, len(ch)
+        return n.value
+
+    def snp_fetch(self, want_mat=True):
+        n, nc = self.n_sites, self.n_chunks
+        mat = np.empty((n, SITE_STRIDE), np.int16) if want_mat else None
+        meta = np.empty(n, META_DTYPE)
+        depth = np.zeros(nc, np.float64)
+        count = np.zeros(nc, np.int64)
+        self._check(self._lib.nc_snp_fetch(self._h, _p(mat) if want_mat and n else None, _p(meta) if n else None,
+                                           _p(depth) if nc else None, _p(count) if nc else None))
+        return mat, meta, depth, count
+
+    # ---- models
+    def load_snp_weights(self, blob, train_coverage, haploid):
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
+        self._check(self._lib.nc_load_snp_weights(self._h, _p(blob), blob.size, float(train_coverage), 1 if haploid else 0))
+
+    def load_indel_weights(self, blob, haploid):
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
+        self._check(self._lib.nc_load_indel_weights(self._h, _p(blob), blob.size, 1 if haploid else 0))
+
+    def snp_forward(self, normalize=True, impl=0, fetch=True):
+        probs = np.empty((self.n_sites, 4), np.float32) if fetch else None
+        self._check(self._lib.nc_snp_forward(self._h, 1 if normalize else 0, impl, _p(probs) if fetch and self.n_sites else None))
+        return probs
+
+    def snp_model_forward(self, x, ref_onehot, haploid=False, impl=0):
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 5, 41, 5)
+        ref = np.ascontiguousarray(ref_onehot, dtype=np.float32).reshape(-1, 4)
+        n = len(x)
+        out = np.empty((n, 4 if haploid else 10), np.float32)
+        self._check(self._lib.nc_snp_model_forward(self._h, _p(x), _p(ref), n, 1 if haploid else 0, impl, _p(out)))
+        return out
+
+    def indel_model_forward(self, x, haploid=False, impl=0):
+        rows = 5 if haploid else 15
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, rows, 128, 2)
+        n = len(x)
+        out = np.empty((n, 1 if haploid else 4), np.float32)
+        self._check(self._lib.nc_indel_model_forward(self._h, _p(x), n, 1 if haploid else 0, impl, _p(out)))
+        return out
+
+    def sync(self):
+        self._check(self._lib.nc_sync(self._h))
+
+    def timings(self):
+        t = NcTimings()
+        self._check(self._lib.nc_get_timings(self._h, ctypes.byref(t)))
+        return {k: getattr(t, k) for k, _ in NcTimings._fields_}
+
+    def sm_count(self):
+        return self._lib.nc_device_sm_count(self._h)
+
+    def device_buffers(self):
+        m, me, pr = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        n = ctypes.c_int64()
+        self._check(self._lib.nc_snp_device_buffers(self._h, ctypes.byref(m), ctypes.byref(me), ctypes.byref(pr), ctypes.byref(n)))
+        return m.value, me.value, pr.value, n.value

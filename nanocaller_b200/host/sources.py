@@ -1,0 +1,54 @@
+"""Alignment sources: what `dct['sam_path']` / `dct['fasta_path']` resolve to on the host.
+
+The reference opens the BAM and the FASTA by path inside every call (generate_SNP_pileups.py:134-135).
+Here a path resolves to per-contig `ReadSet`s in BAM-native encoding.  In-memory sources (the synthetic
+generator, tests) are registered under a `mem://` name; file-backed BAM/FASTA sources plug in through
+the same `resolve` call."""
+
+_REGISTRY = {}
+_BEDS = {}
+
+
+def register_source(path, readsets):
+    """Expose `readsets` (ReadSet or list of ReadSet, one per contig) under `path`."""
+    if not isinstance(readsets, (list, tuple)):
+        readsets = [readsets]
+    _REGISTRY[path] = {rs.chrom: rs for rs in readsets}
+
+
+def register_bed(path, intervals):
+    """intervals: {chrom: [(start, end), ...]} — stands for a tabix-indexed exclude BED."""
+    _BEDS[path] = intervals
+
+
+def unregister_all():
+    _REGISTRY.clear()
+    _BEDS.clear()
+
+
+def resolve(sam_path, chrom):
+    try:
+        return _REGISTRY[sam_path][chrom]
+    except KeyError:
+        raise FileNotFoundError("no alignment source registered for %r contig %r" % (sam_path, chrom))
+
+
+def contigs(sam_path):
+    return list(_REGISTRY[sam_path])
+
+
+def bed_intervals(path, chrom):
+    """-> list of (start, end) for `chrom`, or None when the contig is absent from the BED (the reference
+    then disables exclusion: generate_SNP_pileups.py:121-123)."""
+    if not path:
+        return None
+    table = _BEDS.get(path)
+    if table is None:
+        raise FileNotFoundError("no exclude BED registered for %r" % path)
+    ivs = table.get(chrom)
+    if ivs is None:
+        return None
+    # IntervalTree rejects null intervals with ValueError, which the reference catches and treats as "no exclusion"
+    if any(e <= s for s, e in ivs):
+        return None
+    return list(ivs)

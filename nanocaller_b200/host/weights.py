@@ -340,3 +340,22 @@ def load_model(kind, name, nanocaller_src=None):
     cov_path = path + ".coverage"
     cov = float(open(cov_path).readlines()[0].rstrip("\n")) if os.path.exists(cov_path) else 0.0
     return tensors, {"train_coverage": cov, "haploid": False, "source": os.path.basename(path)}
+
+
+# ------------------------------------------------------------------ packed blobs for the C-ABI
+def _pack(tensors, layers):
+    parts = []
+    for name in layers:
+        parts.append(np.ascontiguousarray(tensors[name + "/kernel"], dtype="<f4").ravel())
+        parts.append(np.ascontiguousarray(tensors[name + "/bias"], dtype="<f4").ravel())
+    return np.concatenate(parts)
+
+
+def pack_snp_blob(tensors, haploid):
+    """Canonical tensor order of nc_load_snp_weights (include/nanocaller_b200.h)."""
+    return _pack(tensors, SNP_HAP_LAYERS if haploid else SNP_LAYERS)
+
+
+def pack_indel_blob(tensors):
+    """Canonical tensor order of nc_load_indel_weights."""
+    return _pack(tensors, INDEL_LAYERS)
