@@ -291,15 +291,23 @@ int cnn_forward(nc_ctx* c, Model& M, int impl, int in_mode, const void* in_dev, 
     if (impl == 1)
         return cnn_forward_f32(c, M, in_mode, in_dev, in_site_stride, n, meta, ref4, scale_f, scale_d, out_full, probs);
     if (impl != 0) return fail(c, NC_EINVAL, "impl must be 0 (tcgen05) or 1 (fp32 CUDA cores)");
-    uint64_t launches = 0;
-    int rc = tc_forward(c->stream, M.tc, in_mode, in_dev, in_site_stride, n, meta, ref4, scale_f, scale_d,
-                        M.w.as<float>(), out_full, probs, c->sm_count, &launches, &c->err);
-    c->launches += launches;
-    if (rc == NC_ESTATE) {
-        // no tensor-core image for this model kind yet: the fp32 kernels are the (GPU) implementation
+    if (!M.tc.ready)    // no tensor-core image for this model kind (indel models): the fp32 kernels are the GPU implementation
         return cnn_forward_f32(c, M, in_mode, in_dev, in_site_stride, n, meta, ref4, scale_f, scale_d, out_full, probs);
-    }
+    uint64_t launches = 0;
+    int rc = tc_forward_ex(c->stream, M.tc, in_mode, in_dev, in_site_stride, n, meta, ref4, scale_f, scale_d, tail_weights(M),
+                           out_full, probs, c->sm_count, &launches, &c->err, 0);
+    c->launches += launches;
     return rc;
+}
+
+// mbarrier waits in the tensor-core kernels are bounded; a timeout raises this flag instead of hanging the device
+int tc_check(nc_ctx* c, Model& M) {
+    if (!M.tc.ready) return NC_OK;
+    NC_CUDA(c->pin.reserve(64));
+    NC_CUDA(cudaMemcpyAsync(c->pin.p, M.tc.err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    NC_CUDA(cudaStreamSynchronize(c->stream));
+    if (*c->pin.as<int>() != 0) return fail(c, NC_ECUDA, "tensor-core CNN kernel: mbarrier wait timed out");
+    return NC_OK;
 }
 
 }  // namespace
@@ -662,6 +670,7 @@ int nc_snp_forward(nc_ctx* c, int normalize, int impl, float* probs) {
     if (probs && n > 0) {
         NC_CUDA(cudaMemcpyAsync(probs, c->d_probs.p, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
         NC_CUDA(cudaStreamSynchronize(c->stream));
+        if (impl == 0) return tc_check(c, M);
     }
     return NC_OK;
 }
@@ -684,7 +693,7 @@ int nc_snp_model_forward(nc_ctx* c, const float* x, const float* ref_onehot, int
     if (rc) return rc;
     NC_CUDA(cudaMemcpyAsync(out, c->ws_out.p, (size_t)n * nout * 4, cudaMemcpyDeviceToHost, c->stream));
     NC_CUDA(cudaStreamSynchronize(c->stream));
-    return NC_OK;
+    return impl == 0 ? tc_check(c, M) : NC_OK;
 }
 
 int nc_indel_model_forward(nc_ctx* c, const float* x, int64_t n, int haploid, int impl, float* out) {
@@ -713,6 +722,55 @@ int nc_snp_device_buffers(nc_ctx* c, void** mat_dev, void** meta_dev, void** pro
     if (probs_dev) *probs_dev = (c->have_probs && c->n_sites) ? c->d_probs.p : nullptr;
     if (n_sites) *n_sites = c->n_sites;
     return NC_OK;
+}
+
+// ---- development probes (not part of the public header) -------------------------------------------------
+int nc_debug_umma(nc_ctx* c, const void* a_img, int a_bytes, const void* b_img, int b_bytes, const void* prog, int n_ops,
+                  int N, int ncols, float* out) {
+    if (!c || !a_img || !b_img || !prog || !out || a_bytes % 16 || b_bytes % 16 || ncols % 16 || ncols > 64) return fail(c, NC_EINVAL, "nc_debug_umma: bad argument");
+    NC_CUDA(cudaSetDevice(c->device));
+    DevBuf da, db, dp, dout, derr;
+    int rc = NC_OK;
+    do {
+        if ((rc = upload(c, da, a_img, a_bytes)) || (rc = upload(c, db, b_img, b_bytes)) || (rc = upload(c, dp, prog, (size_t)n_ops * sizeof(MmaOp)))) break;
+        if (dout.reserve((size_t)128 * ncols * 4) != cudaSuccess || derr.reserve(16) != cudaSuccess) { rc = NC_ENOMEM; break; }
+        cudaMemsetAsync(derr.p, 0, 16, c->stream);
+        const int smem = a_bytes + b_bytes;
+        if (cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { rc = fail(c, NC_ECUDA, "probe smem"); break; }
+        umma_probe_kernel<<<1, 128, smem, c->stream>>>(da.as<uint8_t>(), a_bytes, db.as<uint8_t>(), b_bytes, dp.as<MmaOp>(), n_ops, N, ncols,
+                                                      dout.as<float>(), derr.as<int>());
+        c->launches++;
+        int herr = 0;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout.p, (size_t)128 * ncols * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&herr, derr.p, 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { rc = fail(c, NC_ECUDA, "nc_debug_umma: %s", cudaGetErrorString(e)); break; }
+        if (herr) rc = fail(c, NC_ECUDA, "nc_debug_umma: mbarrier wait timed out");
+    } while (0);
+    da.release(); db.release(); dp.release(); dout.release(); derr.release();
+    return rc;
+}
+
+// Runs the tensor-core trunk up to `stage` (1: after conv2, 2: after conv3) on fp32 inputs and returns the raw
+// fp16 hi/lo activation image (layouts documented in nc_cnn_tc.cuh) for layer-by-layer parity tests.
+int nc_debug_tc_trunk(nc_ctx* c, const float* x, int64_t n, int haploid, int stage, void* raw, size_t raw_bytes) {
+    if (!c || !x || !raw || n <= 0 || (stage != 1 && stage != 2)) return fail(c, NC_EINVAL, "nc_debug_tc_trunk: bad argument");
+    NC_CUDA(cudaSetDevice(c->device));
+    Model& M = c->snp[haploid ? 1 : 0];
+    if (!M.loaded || !M.tc.ready) return fail(c, NC_ESTATE, "nc_debug_tc_trunk: no tensor-core SNP model loaded");
+    NC_CUDA(c->ws_x.reserve((size_t)n * NC_SNP_SITE_ELEMS * 4));
+    NC_CUDA(cudaMemcpyAsync(c->ws_x.p, x, (size_t)n * NC_SNP_SITE_ELEMS * 4, cudaMemcpyHostToDevice, c->stream));
+    uint64_t launches = 0;
+    int rc = tc_forward_ex(c->stream, M.tc, 0, c->ws_x.p, NC_SNP_SITE_ELEMS, n, nullptr, nullptr, nullptr, nullptr, tail_weights(M),
+                           nullptr, nullptr, c->sm_count, &launches, &c->err, stage);
+    c->launches += launches;
+    if (rc) return rc;
+    const size_t have = stage == 1 ? (size_t)n * tcg::C2_SITE_BYTES : (size_t)((n + 127) / 128) * tcg::C3_TILE_BYTES;
+    if (raw_bytes < have) return fail(c, NC_EINVAL, "nc_debug_tc_trunk: output buffer too small (%zu < %zu)", raw_bytes, have);
+    NC_CUDA(cudaMemcpyAsync(raw, stage == 1 ? M.tc.c2.p : M.tc.c3.p, have, cudaMemcpyDeviceToHost, c->stream));
+    NC_CUDA(cudaStreamSynchronize(c->stream));
+    return tc_check(c, M);
 }
 
 }  // extern "C"

@@ -1,16 +1,785 @@
-// tcgen05 tensor-core CNN path (impl = 0) — placeholder interface; see nc_cnn_tc.cuh history.
+// CNN forward on the 5th-generation tensor cores (impl = 0): tcgen05.mma kind::f16 with fp32
+// accumulation in TMEM, for SNP_model / haploid_SNP_model (model_architect.py:36-64,
+// model_architect_SNP_haploid.py:33-53).
+//
+// Precision.  Single-pass bf16/fp16/tf32 operands miss the 1e-4 probability tolerance by 10-100x
+// (measured).  Every operand is therefore split x = hi + lo with hi = fp16(x),
+// lo = fp16(x - hi) (22 mantissa bits) and every product is three MMAs: hi*hi + lo*hi + hi*lo.
+//
+// Convolutions as tap-decomposed implicit GEMMs.  Activations live in shared memory as "planes"
+// [k-group of 8 channels][pixel row][8 x fp16 = 16 B]: the canonical K-major no-swizzle UMMA layout
+// with SBO = 128 B, so GEMM row r of a core matrix group is simply 16 B further.  A convolution
+// tap is then nothing but a different start address (row shift), the two 8-wide K groups of one
+// K=16 MMA are addressed through LBO (another plane, or another tap of the same plane), and no
+// im2col copy is ever materialised.  Stride-2 layers read from planes split by column parity.
+//
+//   TA  conv1_{1,2,3} + conv2   one warpgroup per site, two warpgroups per CTA, weights resident in smem
+//   TB  conv3                   three sites per 128-row tile
+//   TC  fc1 + heads             128 sites per tile, K streamed position by position (double buffered)
 #pragma once
+#include <cuda_fp16.h>
+
 #include "nc_common.cuh"
+#include "nc_cnn.cuh"
 
 namespace nc {
 
-struct TcModel { bool ready = false; };
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-inline int tc_model_prepare(cudaStream_t, TcModel& T, int, const float*, size_t, std::string*) { T.ready = false; return NC_OK; }
-inline void tc_model_release(TcModel&) {}
-inline int tc_forward(cudaStream_t, TcModel& T, int, const void*, int64_t, int64_t, const NcSiteMeta*, const float*, const float*,
-                      const double*, const float*, float*, float*, int, uint64_t*, std::string*) {
-    return NC_ESTATE;
+// K-major, no swizzle, version 1 (Blackwell) shared-memory matrix descriptor.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D fp32, A/B fp16, both K-major, dense.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// Bounded wait: a protocol bug must not hang the GPU box.  Returns false on timeout.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 24); spin++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, float* r) {
+    uint32_t v[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(addr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) r[i] = __uint_as_float(v[i]);
+}
+__device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" :: "r"(wg + 1) : "memory"); }
+
+// SELU with the fast exponential (ex2.approx): abs error ~1e-7 on the negative branch.
+__device__ __forceinline__ float selu_fast(float x) {
+    const float scale = 1.0507009873554805f, sa = 1.0507009873554805f * 1.6732632423543772f;
+    return x > 0.f ? scale * x : sa * (__expf(x) - 1.f);
+}
+// x -> (hi, lo) fp16 pair with hi + lo ~= x to 22 bits; saturates instead of overflowing to inf.
+__device__ __forceinline__ void split16(float x, __half& hi, __half& lo) {
+    x = fminf(fmaxf(x, -65000.f), 65000.f);
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+// 8 consecutive channels -> one 16-byte hi word and one 16-byte lo word
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    __half h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) split16(v[i], h[i], l[i]);
+    hi = *reinterpret_cast<uint4*>(h);
+    lo = *reinterpret_cast<uint4*>(l);
+}
+
+// One MMA of a layer's "program": where its A rows start, how its two K groups are spaced, which
+// B tile it multiplies and which accumulator columns it adds into.
+struct MmaOp { uint32_t a_off, a_lbo, b_off, misc; };     // misc: bits 0-9 D column, bit 15 accumulate
+constexpr uint32_t kOpAcc = 1u << 15;
+
+__device__ __forceinline__ void issue_program(const MmaOp* prog, int n_ops, uint32_t a_base, uint32_t w_base, uint32_t b_lbo,
+                                              uint32_t d_base, uint32_t idesc) {
+    for (int i = 0; i < n_ops; i++) {
+        const MmaOp op = prog[i];
+        umma_f16(d_base + (op.misc & 0x3FFu), make_sdesc(a_base + op.a_off, op.a_lbo, 128u),
+                 make_sdesc(w_base + op.b_off, b_lbo, 128u), idesc, (op.misc & kOpAcc) ? 1u : 0u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry of the SNP trunk
+// ------------------------------------------------------------------------------------------------
+namespace tcg {
+constexpr int WP = 45;                         // padded input width (41 + 2*2)
+constexpr int IN_ROWS = 416;                   // 9*45 = 405 padded pixels + slack for junk rows
+constexpr int IN_PLANE = IN_ROWS * 16;         // bytes of one input plane (8 channels of fp16 per pixel)
+constexpr int C1_PITCH = 21;                   // columns per parity plane of c1 (even: 21 real, odd: 20 real + 1 junk)
+constexpr int C1_ROWS = 5 * C1_PITCH;          // 105
+constexpr int C1_PLANE = C1_ROWS * 16;         // 1680 B per (part, parity, k-group)
+constexpr int C1_BYTES = 2 * 2 * 6 * C1_PLANE + 1024;
+constexpr int TILE1_START = 97;                // second conv1 tile covers output rows 97..224
+constexpr int C2_PITCH = 10;
+constexpr int C2_SITE_ROWS = 4 * C2_PITCH;     // 40 rows per site and parity
+constexpr int C2_CHUNK = C2_SITE_ROWS * 16;    // 640 B per (part, parity, k-group)
+constexpr int C2_SITE_BYTES = 2 * 2 * 4 * C2_CHUNK;   // 10240 B per site in HBM
+constexpr int C2_PLANE = 3 * C2_CHUNK;         // three sites stacked: 1920 B
+constexpr int C2_SMEM = 2 * 2 * 4 * C2_PLANE + 512;
+constexpr int FC_KG = 27 * 8;                  // 216 k-groups of fc1 (27 positions x 64 channels)
+constexpr int C3_TILE_BYTES = 2 * FC_KG * 128 * 16;   // 884736 B per 128-site tile in HBM
+constexpr int TA_WBYTES = (35 + 19) * 512 + 54 * 0;   // conv1 tiles; conv2 tiles follow
+constexpr int W1_BYTES = (35 + 19) * 512;      // 27648
+constexpr int W2_BYTES = 36 * 1024;            // 6 taps x 3 K-chunks x (hi, lo) tiles of [32 x 16]
+constexpr int W3_BYTES = 24 * 2048;            // 6 taps x 2 K-chunks x (hi, lo) tiles of [64 x 16]
+constexpr int WF_POS_BYTES = 8 * 1536;         // per position: 4 K-chunks x (hi, lo) tiles of [48 x 16]
+constexpr int N_OPS1 = 54, N_OPS2 = 54, N_OPS3 = 36, N_OPSF = 12;
+}  // namespace tcg
+
+struct TAParams {
+    const void* in; int in_mode; int64_t in_site_stride;
+    const float* scale_f; const double* scale_d;
+    int64_t n_sites;
+    const uint8_t* wimg;                      // W1 tiles then W2 tiles
+    const MmaOp* prog1; const MmaOp* prog2;
+    const float* bias1; const float* bias2;
+    uint8_t* c2_out;
+    int* err;
+};
+
+constexpr int TA_SMEM_W = tcg::W1_BYTES + tcg::W2_BYTES;                           // 64512
+constexpr int TA_SMEM_WG = 2 * tcg::IN_PLANE + tcg::C1_BYTES;                      // 13312 + 41344
+constexpr int TA_SMEM_MISC = (tcg::N_OPS1 + tcg::N_OPS2) * 16 + 80 * 4 + 64;
+constexpr int TA_SMEM = TA_SMEM_W + 2 * TA_SMEM_WG + TA_SMEM_MISC + 128;
+
+__global__ void __launch_bounds__(256, 1) tc_trunk_a_kernel(const TAParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_w = smem;
+    uint8_t* s_wg0 = smem + TA_SMEM_W;
+    MmaOp* s_prog = reinterpret_cast<MmaOp*>(smem + TA_SMEM_W + 2 * TA_SMEM_WG);
+    float* s_bias = reinterpret_cast<float*>(s_prog + tcg::N_OPS1 + tcg::N_OPS2);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 80);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+
+    const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = tid >> 5, lane = tid & 31;
+    uint8_t* s_in = s_wg0 + wg * TA_SMEM_WG;               // hi plane, then lo plane
+    uint8_t* s_c1 = s_in + 2 * tcg::IN_PLANE;
+
+    // one-time setup: weights, programs, biases, zeroed activations, barriers, TMEM
+    for (int i = tid; i < TA_SMEM_W / 16; i += 256) reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(P.wimg) + i);
+    for (int i = tid; i < tcg::N_OPS1; i += 256) s_prog[i] = P.prog1[i];
+    for (int i = tid; i < tcg::N_OPS2; i += 256) s_prog[tcg::N_OPS1 + i] = P.prog2[i];
+    if (tid < 48) s_bias[tid] = P.bias1[tid];
+    if (tid >= 64 && tid < 96) s_bias[48 + tid - 64] = P.bias2[tid - 64];
+    for (int i = tid; i < 2 * TA_SMEM_WG / 16; i += 256) reinterpret_cast<uint4*>(s_wg0)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(s_tmem, 256);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem + (uint32_t)wg * 128u;                       // this warpgroup's 128 columns
+    const uint32_t tmem_lane = tmem + ((uint32_t)(warp & 3) << 21);            // lane quarter of this warp (lane << 16)
+    const uint32_t a_in = smem_u32(s_in), a_c1 = smem_u32(s_c1), a_w = smem_u32(s_w);
+    const uint32_t idesc1 = make_idesc_f16(128, 16), idesc2 = make_idesc_f16(128, 32);
+    uint32_t phase = 0;
+    bool ok = true;
+
+    for (int64_t site = (int64_t)blockIdx.x * 2 + wg; site < P.n_sites; site += (int64_t)gridDim.x * 2) {
+        // ---- input: [5][41][5] -> padded planes (pixel row = (h+2)*45 + (w+2)), channels 5..7 stay zero
+        for (int px = t; px < 205; px += 128) {
+            const int h = px / 41, w = px - h * 41;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (P.in_mode == 0) {
+                const float* src = reinterpret_cast<const float*>(P.in) + site * P.in_site_stride + px * 5;
+#pragma unroll
+                for (int c = 0; c < 5; c++) v[c] = __ldg(src + c);
+            } else {
+                const int16_t* src = reinterpret_cast<const int16_t*>(P.in) + site * P.in_site_stride + px * 5;
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    const int16_t raw = __ldg(src + c);
+                    float x = (float)raw;
+                    if (h > 0 && c < 4) {
+                        if (P.in_mode == 1) x = __fmul_rn(x, __ldg(P.scale_f + site));
+                        else x = (float)((double)raw * __ldg(P.scale_d + site));
+                    }
+                    v[c] = x;
+                }
+            }
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            const int row = (h + 2) * tcg::WP + w + 2;
+            *reinterpret_cast<uint4*>(s_in + row * 16) = hi;
+            *reinterpret_cast<uint4*>(s_in + tcg::IN_PLANE + row * 16) = lo;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        wg_barrier(wg);
+        // ---- conv1: two 128-row tiles, three branches -> 48 accumulator columns per tile
+        if (t == 0) {
+            tc_fence_after();
+            issue_program(s_prog, tcg::N_OPS1, a_in, a_w, 16 * 16, tmem, idesc1);
+            issue_program(s_prog, tcg::N_OPS1, a_in + tcg::TILE1_START * 16, a_w, 16 * 16, tmem + 48, idesc1);
+            umma_commit(&s_bar[wg]);
+        }
+        ok = mbar_wait(&s_bar[wg], phase) && ok; phase ^= 1;
+        tc_fence_after();
+        // ---- epilogue 1: bias + SELU + split -> c1 planes [part][parity][k-group][h*21 + w/2]
+#pragma unroll 1
+        for (int j = 0; j < 2; j++) {
+            const int m = (j ? tcg::TILE1_START : 0) + t;
+            const int h = m / tcg::WP, w = m - h * tcg::WP;
+            const bool valid = m < 225 && w < 41 && (j == 0 || m >= 128);
+            const int row = h * tcg::C1_PITCH + (w >> 1), par = w & 1;
+#pragma unroll 1
+            for (int cb = 0; cb < 3; cb++) {
+                float acc[16];
+                tmem_ld16(tmem_lane + j * 48 + cb * 16, acc);
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) acc[i] = selu_fast(acc[i] + s_bias[cb * 16 + i]);
+#pragma unroll
+                    for (int g = 0; g < 2; g++) {
+                        uint4 hi, lo;
+                        split8(acc + 8 * g, hi, lo);
+                        const int kg = cb * 2 + g;
+                        *reinterpret_cast<uint4*>(s_c1 + ((0 * 2 + par) * 6 + kg) * tcg::C1_PLANE + row * 16) = hi;
+                        *reinterpret_cast<uint4*>(s_c1 + ((1 * 2 + par) * 6 + kg) * tcg::C1_PLANE + row * 16) = lo;
+                    }
+                }
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        wg_barrier(wg);
+        // ---- conv2: one tile (rows h2*21 + w2), 6 taps x 3 K-chunks x 3 split terms
+        if (t == 0) {
+            tc_fence_after();
+            issue_program(s_prog + tcg::N_OPS1, tcg::N_OPS2, a_c1, a_w + tcg::W1_BYTES, 32 * 16, tmem + 96, idesc2);
+            umma_commit(&s_bar[wg]);
+        }
+        ok = mbar_wait(&s_bar[wg], phase) && ok; phase ^= 1;
+        tc_fence_after();
+        // ---- epilogue 2: bias + SELU + split -> HBM c2 [site][part][parity][k-group][h2*10 + w2/2][8]
+        {
+            const int m = t, h2 = m / tcg::C1_PITCH, w2 = m - h2 * tcg::C1_PITCH;
+            const bool valid = m < 84 && w2 < 20;
+            uint8_t* dst = P.c2_out + site * tcg::C2_SITE_BYTES + (h2 * tcg::C2_PITCH + (w2 >> 1)) * 16;
+            const int par = w2 & 1;
+#pragma unroll 1
+            for (int cb = 0; cb < 2; cb++) {
+                float acc[16];
+                tmem_ld16(tmem_lane + 96 + cb * 16, acc);
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) acc[i] = selu_fast(acc[i] + s_bias[48 + cb * 16 + i]);
+#pragma unroll
+                    for (int g = 0; g < 2; g++) {
+                        uint4 hi, lo;
+                        split8(acc + 8 * g, hi, lo);
+                        const int kg = cb * 2 + g;
+                        *reinterpret_cast<uint4*>(dst + ((0 * 2 + par) * 4 + kg) * tcg::C2_CHUNK) = hi;
+                        *reinterpret_cast<uint4*>(dst + ((1 * 2 + par) * 4 + kg) * tcg::C2_CHUNK) = lo;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        wg_barrier(wg);              // TMEM and c1 planes are free for the next site
+    }
+    if (!ok && t == 0) atomicExch(P.err, 1);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(*s_tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TB — conv3, three sites per tile
+// ------------------------------------------------------------------------------------------------
+struct TBParams {
+    const uint8_t* c2; int64_t n_sites;
+    const uint8_t* wimg; const MmaOp* prog; const float* bias;
+    uint8_t* c3_out; int* err;
+};
+constexpr int TB_SMEM_MISC = tcg::N_OPS3 * 16 + 64 * 4 + 64;
+constexpr int TB_SMEM = tcg::W3_BYTES + 2 * tcg::C2_SMEM + TB_SMEM_MISC + 128;
+
+__global__ void __launch_bounds__(256, 1) tc_trunk_b_kernel(const TBParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_w = smem;
+    MmaOp* s_prog = reinterpret_cast<MmaOp*>(smem + tcg::W3_BYTES + 2 * tcg::C2_SMEM);
+    float* s_bias = reinterpret_cast<float*>(s_prog + tcg::N_OPS3);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 64);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+    const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = tid >> 5;
+    uint8_t* s_c2 = smem + tcg::W3_BYTES + wg * tcg::C2_SMEM;
+
+    for (int i = tid; i < tcg::W3_BYTES / 16; i += 256) reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(P.wimg) + i);
+    for (int i = tid; i < tcg::N_OPS3; i += 256) s_prog[i] = P.prog[i];
+    if (tid < 64) s_bias[tid] = P.bias[tid];
+    for (int i = tid; i < 2 * tcg::C2_SMEM / 16; i += 256) reinterpret_cast<uint4*>(smem + tcg::W3_BYTES)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(s_tmem, 128);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem + (uint32_t)wg * 64u;
+    const uint32_t tmem_lane = tmem + ((uint32_t)(warp & 3) << 21);
+    const uint32_t a_c2 = smem_u32(s_c2), a_w = smem_u32(s_w);
+    const uint32_t idesc = make_idesc_f16(128, 64);
+    uint32_t phase = 0;
+    bool ok = true;
+    const int64_t n_groups = (P.n_sites + 2) / 3;
+
+    for (int64_t grp = (int64_t)blockIdx.x * 2 + wg; grp < n_groups; grp += (int64_t)gridDim.x * 2) {
+        const int64_t s0 = grp * 3;
+        // ---- load: per site 16 chunks of 640 B -> plane (part, parity, kg) + s*640
+        for (int i = t; i < 3 * 16 * 40; i += 128) {
+            const int s = i / 640, r = i - s * 640, ch = r / 40, q = r - ch * 40;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (s0 + s < P.n_sites) v = __ldg(reinterpret_cast<const uint4*>(P.c2 + (s0 + s) * tcg::C2_SITE_BYTES + ch * tcg::C2_CHUNK) + q);
+            *reinterpret_cast<uint4*>(s_c2 + ch * tcg::C2_PLANE + s * tcg::C2_CHUNK + q * 16) = v;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        wg_barrier(wg);
+        if (t == 0) {
+            tc_fence_after();
+            issue_program(s_prog, tcg::N_OPS3, a_c2, a_w, 64 * 16, tmem, idesc);
+            umma_commit(&s_bar[wg]);
+        }
+        ok = mbar_wait(&s_bar[wg], phase) && ok; phase ^= 1;
+        tc_fence_after();
+        // ---- epilogue: row m = s*40 + h3*10 + w3 -> HBM c3 [tile][part][pos*8 + g][site % 128][8]
+        {
+            const int s = t / 40, r = t - s * 40, h3 = r / 10, w3 = r - h3 * 10;
+            const int64_t site = s0 + s;
+            const bool valid = s < 3 && h3 < 3 && w3 < 9 && site < P.n_sites;
+            const int pos = h3 * 9 + w3;
+            uint8_t* dst = P.c3_out + (site >> 7) * (int64_t)tcg::C3_TILE_BYTES + (int64_t)(pos * 8) * 2048 + (site & 127) * 16;
+#pragma unroll 1
+            for (int cb = 0; cb < 4; cb++) {
+                float acc[16];
+                tmem_ld16(tmem_lane + cb * 16, acc);
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) acc[i] = selu_fast(acc[i] + s_bias[cb * 16 + i]);
+#pragma unroll
+                    for (int g = 0; g < 2; g++) {
+                        uint4 hi, lo;
+                        split8(acc + 8 * g, hi, lo);
+                        const int kg = cb * 2 + g;
+                        *reinterpret_cast<uint4*>(dst + (int64_t)kg * 2048) = hi;
+                        *reinterpret_cast<uint4*>(dst + (int64_t)tcg::FC_KG * 2048 + (int64_t)kg * 2048) = lo;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        wg_barrier(wg);
+    }
+    if (!ok && t == 0) atomicExch(P.err, 1);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(*s_tmem, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TC — fc1 (K = 1728 streamed by position, two smem stages) + heads, 128 sites per CTA
+// ------------------------------------------------------------------------------------------------
+struct TCParams {
+    const uint8_t* c3; int64_t n_sites;
+    const uint8_t* wimg;            // [27 positions][8 tiles of 1536 B]
+    const MmaOp* prog;              // 12 ops, offsets relative to a stage
+    const float* bias;              // fc1 bias (48)
+    TailW tail; int haploid;
+    const NcSiteMeta* meta; const float* ref4;
+    float* out10; float* probs4;
+    int* err;
+};
+constexpr int TC_STAGE_A = 2 * 8 * 2048;                    // 32768: [part][kg 8][128 rows][16 B]
+constexpr int TC_STAGE = TC_STAGE_A + tcg::WF_POS_BYTES;    // + 12288 of weights
+constexpr int TC_SMEM = 2 * TC_STAGE + tcg::N_OPSF * 16 + 48 * 4 + 64 + 128;
+
+__device__ __forceinline__ void snp_tail_row(const float* x, int64_t s, const TCParams& P) {
+    const TailW& w = P.tail;
+    float ref[4];
+    if (P.ref4) { for (int j = 0; j < 4; j++) ref[j] = P.ref4[s * 4 + j]; }
+    else { const int rc = P.meta[s].ref_code; for (int j = 0; j < 4; j++) ref[j] = (j == rc) ? 1.f : 0.f; }
+    if (P.haploid) {
+        float in[20], z[4];
+        dense_t<48, 16>(x, w.fc2_k, w.fc2_b, in, true);
+        for (int j = 0; j < 4; j++) in[16 + j] = ref[j];
+        dense_t<20, 4>(in, w.fc3_k, w.fc3_b, z, true);
+        softmax_t<4>(z);
+        for (int j = 0; j < 4; j++) P.probs4[s * 4 + j] = z[j];
+        return;
+    }
+    float fa[17], fc3in[24];
+    dense_t<48, 16>(x, w.fa_k, w.fa_b, fa, true);
+    if (P.out10) dense_t<48, 16>(x, w.fc2_k, w.fc2_b, fc3in, true);
+    for (int j = 0; j < 4; j++) {
+        float z[2];
+        fa[16] = ref[j];
+        dense_t<17, 2>(fa, w.hk[j], w.hb[j], z, false);
+        softmax_t<2>(z);
+        fc3in[16 + 2 * j] = z[0]; fc3in[17 + 2 * j] = z[1];
+        if (P.out10) { P.out10[s * 10 + 2 * j] = z[0]; P.out10[s * 10 + 2 * j + 1] = z[1]; }
+        if (P.probs4) P.probs4[s * 4 + j] = z[1];
+    }
+    if (P.out10) {
+        float fc3[8], gt[2];
+        dense_t<24, 8>(fc3in, w.fc3_k, w.fc3_b, fc3, true);
+        dense_t<8, 2>(fc3, w.gt_k, w.gt_b, gt, false);
+        softmax_t<2>(gt);
+        P.out10[s * 10 + 8] = gt[0]; P.out10[s * 10 + 9] = gt[1];
+    }
+}
+
+__global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    MmaOp* s_prog = reinterpret_cast<MmaOp*>(smem + 2 * TC_STAGE);
+    float* s_bias = reinterpret_cast<float*>(s_prog + tcg::N_OPSF);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 48);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+    const int t = threadIdx.x, warp = t >> 5;
+    const int64_t tile = blockIdx.x;
+
+    if (t < tcg::N_OPSF) s_prog[t] = P.prog[t];
+    if (t < 48) s_bias[t] = P.bias[t];
+    if (t == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(s_tmem, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t tmem_lane = tmem + ((uint32_t)(warp & 3) << 21);
+    const uint32_t idesc = make_idesc_f16(128, 48);
+    const uint8_t* a_src = P.c3 + tile * (int64_t)tcg::C3_TILE_BYTES;
+    bool ok = true;
+
+    auto load_stage = [&](int pos) {
+        uint8_t* st = smem + (pos & 1) * TC_STAGE;
+        // A: per part 8 k-groups x 2048 B contiguous in HBM at k-group pos*8
+        for (int i = t; i < TC_STAGE_A / 16; i += 128) {
+            const int part = i >> 10, r = i & 1023;
+            reinterpret_cast<uint4*>(st)[i] = __ldg(reinterpret_cast<const uint4*>(a_src + ((int64_t)part * tcg::FC_KG + pos * 8) * 2048) + r);
+        }
+        const uint4* wsrc = reinterpret_cast<const uint4*>(P.wimg + (int64_t)pos * tcg::WF_POS_BYTES);
+        for (int i = t; i < tcg::WF_POS_BYTES / 16; i += 128) reinterpret_cast<uint4*>(st + TC_STAGE_A)[i] = __ldg(wsrc + i);
+    };
+
+    load_stage(0);
+    for (int pos = 0; pos < 27; pos++) {
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (t == 0) {
+            tc_fence_after();
+            const uint32_t sb = smem_u32(smem + (pos & 1) * TC_STAGE);
+            for (int i = 0; i < tcg::N_OPSF; i++) {
+                const MmaOp op = s_prog[i];
+                umma_f16(tmem, make_sdesc(sb + op.a_off, op.a_lbo, 128u), make_sdesc(sb + TC_STAGE_A + op.b_off, 48 * 16, 128u), idesc,
+                         (pos > 0 || (op.misc & kOpAcc)) ? 1u : 0u);
+            }
+            umma_commit(&s_bar[pos & 1]);
+        }
+        if (pos + 1 < 27) {
+            if (pos >= 1) ok = mbar_wait(&s_bar[(pos + 1) & 1], ((pos - 1) >> 1) & 1) && ok;   // MMAs of pos-1 released that stage
+            load_stage(pos + 1);
+        }
+    }
+    ok = mbar_wait(&s_bar[0], 1) && ok;          // pos 26: 14th completion of stage 0 -> parity 1
+    ok = mbar_wait(&s_bar[1], 0) && ok;          // pos 25: 13th completion of stage 1 -> parity 0
+    tc_fence_after();
+    {
+        float x[48];
+#pragma unroll
+        for (int cb = 0; cb < 3; cb++) tmem_ld16(tmem_lane + cb * 16, x + cb * 16);
+        const int64_t s = tile * 128 + t;
+        if (s < P.n_sites) {
+#pragma unroll
+            for (int i = 0; i < 48; i++) x[i] = selu_fast(x[i] + s_bias[i]);
+            snp_tail_row(x, s, P);
+        }
+    }
+    if (!ok && t == 0) atomicExch(P.err, 1);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic single-tile UMMA probe (tests/test_cuda_umma.py): runs a program on caller-supplied A
+// planes and B tiles and returns the fp32 accumulator block — pins the descriptor semantics the
+// layer programs rely on (row shifts through the start address, K groups through LBO).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(const uint8_t* a_img, int a_bytes, const uint8_t* b_img, int b_bytes,
+                                                            const MmaOp* prog, int n_ops, int N, int ncols, float* out, int* err) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int i = t; i < a_bytes / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(a_img)[i];
+    for (int i = t; i < b_bytes / 16; i += 128) reinterpret_cast<uint4*>(smem + a_bytes)[i] = reinterpret_cast<const uint4*>(b_img)[i];
+    if (t == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(&tmem_slot, 64);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (t == 0) {
+        issue_program(prog, n_ops, smem_u32(smem), smem_u32(smem + a_bytes), (uint32_t)N * 16u, tmem, make_idesc_f16(128, N));
+        umma_commit(&bar);
+    }
+    const bool ok = mbar_wait(&bar, 0);
+    tc_fence_after();
+    for (int cb = 0; cb < ncols / 16; cb++) {
+        float acc[16];
+        tmem_ld16(tmem + ((uint32_t)(warp & 3) << 21) + cb * 16, acc);
+        for (int i = 0; i < 16; i++) out[t * ncols + cb * 16 + i] = acc[i];
+    }
+    if (!ok && t == 0) atomicExch(err, 1);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: weight images, programs, launch
+// ------------------------------------------------------------------------------------------------
+struct TcModel {
+    bool ready = false;
+    int kind = 0;
+    DevBuf wimg_a, wimg_b, wimg_c, prog, bias;   // prog: ops1 | ops2 | ops3 | opsF ; bias: b1(48) b2(32) b3(64) bf(48)
+    DevBuf c2, c3, err;
+    int64_t tail_off[16][2];
+};
+
+inline void tc_model_release(TcModel& T) {
+    for (DevBuf* b : {&T.wimg_a, &T.wimg_b, &T.wimg_c, &T.prog, &T.bias, &T.c2, &T.c3, &T.err}) b->release();
+    T.ready = false;
+}
+
+namespace tcdetail {
+inline void put_split(std::vector<uint8_t>& hi_img, std::vector<uint8_t>& lo_img, size_t byte_off, float w) {
+    const __half h = __float2half_rn(w);
+    const __half l = __float2half_rn(w - __half2float(h));
+    memcpy(hi_img.data() + byte_off, &h, 2);
+    memcpy(lo_img.data() + byte_off, &l, 2);
+}
+// B tile [N rows][K = 16] in the K-major blocked layout: element (kslot, n) at ((kslot/8)*N + n)*16 + (kslot%8)*2
+inline size_t btile_off(int N, int kslot, int n) { return ((size_t)(kslot >> 3) * N + n) * 16 + (size_t)(kslot & 7) * 2; }
+}  // namespace tcdetail
+
+// Builds the tensor-core operand images for an SNP model (kind 0 / 1).  Other kinds: not prepared
+// (the fp32 kernels serve them), T.ready stays false.
+inline int tc_model_prepare(cudaStream_t stream, TcModel& T, int kind, const float* blob, size_t n_floats, std::string* err) {
+    using namespace tcg;
+    using namespace tcdetail;
+    T.ready = false; T.kind = kind;
+    if (kind > 1) return NC_OK;
+    (void)n_floats;
+    // blob offsets (canonical order, see model_init)
+    const float* w11 = blob; const float* b11 = w11 + 400;
+    const float* w12 = b11 + 16; const float* b12 = w12 + 400;
+    const float* w13 = b12 + 16; const float* b13 = w13 + 2000;
+    const float* w2 = b13 + 16; const float* b2 = w2 + 9216;
+    const float* w3 = b2 + 32; const float* b3 = w3 + 12288;
+    const float* wf = b3 + 64; const float* bf = wf + 82944;
+
+    std::vector<MmaOp> ops;
+    // ---------------- conv1: three branches, taps in ascending shift order
+    struct Tap { int shift; const float* w; };      // w -> [ci 5][co 16] slice of the HWIO kernel
+    std::vector<uint8_t> img_hi(35 * 512, 0), img_lo(19 * 512, 0);
+    std::vector<uint8_t> dummy(35 * 512, 0);
+    int hi_tiles = 0, lo_tiles = 0;
+    for (int br = 0; br < 3; br++) {
+        std::vector<Tap> taps;
+        if (br == 0) for (int kw = 0; kw < 5; kw++) taps.push_back({2 * WP + kw, w11 + (size_t)kw * 5 * 16});
+        if (br == 1) for (int kh = 0; kh < 5; kh++) taps.push_back({kh * WP + 2, w12 + (size_t)kh * 5 * 16});
+        if (br == 2) for (int kh = 0; kh < 5; kh++) for (int kw = 0; kw < 5; kw++) taps.push_back({kh * WP + kw, w13 + (size_t)(kh * 5 + kw) * 5 * 16});
+        bool first = true;
+        // (a_hi | a_lo) x (w_hi ; w_hi)
+        for (const Tap& tp : taps) {
+            const size_t base = (size_t)hi_tiles * 512;
+            for (int ci = 0; ci < 5; ci++)
+                for (int n = 0; n < 16; n++) {
+                    const float w = tp.w[ci * 16 + n];
+                    put_split(img_hi, dummy, base + btile_off(16, ci, n), w);
+                    put_split(img_hi, dummy, base + btile_off(16, 8 + ci, n), w);
+                }
+            ops.push_back({(uint32_t)(tp.shift * 16), (uint32_t)IN_PLANE, (uint32_t)(hi_tiles * 512), (uint32_t)(br * 16) | (first ? 0u : kOpAcc)});
+            first = false; hi_tiles++;
+        }
+        // (a_hi tap t | a_hi tap t') x (w_lo t ; w_lo t')
+        for (size_t i = 0; i < taps.size(); i += 2) {
+            const size_t base = (size_t)lo_tiles * 512;
+            const bool pair = i + 1 < taps.size();
+            for (int half = 0; half < (pair ? 2 : 1); half++)
+                for (int ci = 0; ci < 5; ci++)
+                    for (int n = 0; n < 16; n++) {
+                        const float w = taps[i + half].w[ci * 16 + n];
+                        const __half h = __float2half_rn(w);
+                        const __half l = __float2half_rn(w - __half2float(h));
+                        memcpy(img_lo.data() + base + btile_off(16, 8 * half + ci, n), &l, 2);
+                    }
+            const uint32_t lbo = pair ? (uint32_t)((taps[i + 1].shift - taps[i].shift) * 16) : 16u;
+            ops.push_back({(uint32_t)(taps[i].shift * 16), lbo, (uint32_t)(35 * 512 + lo_tiles * 512), (uint32_t)(br * 16) | kOpAcc});
+            lo_tiles++;
+        }
+    }
+    if ((int)ops.size() != N_OPS1 || hi_tiles != 35 || lo_tiles != 19) { if (err) *err = "conv1 program size mismatch"; return NC_EINVAL; }
+    // ---------------- conv2: [kh 2][kw 3][ci 48][co 32]
+    std::vector<uint8_t> w2_hi(18 * 1024, 0), w2_lo(18 * 1024, 0);
+    {
+        int tile = 0; bool first = true;
+        for (int kh = 0; kh < 2; kh++)
+            for (int kw = 0; kw < 3; kw++)
+                for (int c = 0; c < 3; c++) {
+                    for (int s = 0; s < 16; s++)
+                        for (int n = 0; n < 32; n++)
+                            put_split(w2_hi, w2_lo, (size_t)tile * 1024 + btile_off(32, s, n), w2[((size_t)(kh * 3 + kw) * 48 + 16 * c + s) * 32 + n]);
+                    const int par = kw & 1, shift = kh * C1_PITCH + (kw >> 1);
+                    const uint32_t a_hi = (uint32_t)(((0 * 2 + par) * 6 + 2 * c) * C1_PLANE + shift * 16);
+                    const uint32_t a_lo = (uint32_t)(((1 * 2 + par) * 6 + 2 * c) * C1_PLANE + shift * 16);
+                    ops.push_back({a_hi, (uint32_t)C1_PLANE, (uint32_t)(tile * 1024), 0u | (first ? 0u : kOpAcc)});
+                    ops.push_back({a_lo, (uint32_t)C1_PLANE, (uint32_t)(tile * 1024), kOpAcc});
+                    ops.push_back({a_hi, (uint32_t)C1_PLANE, (uint32_t)(18 * 1024 + tile * 1024), kOpAcc});
+                    first = false; tile++;
+                }
+    }
+    // ---------------- conv3: [kh 2][kw 3][ci 32][co 64]
+    std::vector<uint8_t> w3_hi(12 * 2048, 0), w3_lo(12 * 2048, 0);
+    {
+        int tile = 0; bool first = true;
+        for (int kh = 0; kh < 2; kh++)
+            for (int kw = 0; kw < 3; kw++)
+                for (int c = 0; c < 2; c++) {
+                    for (int s = 0; s < 16; s++)
+                        for (int n = 0; n < 64; n++)
+                            put_split(w3_hi, w3_lo, (size_t)tile * 2048 + btile_off(64, s, n), w3[((size_t)(kh * 3 + kw) * 32 + 16 * c + s) * 64 + n]);
+                    const int par = kw & 1, shift = kh * C2_PITCH + (kw >> 1);
+                    const uint32_t a_hi = (uint32_t)(((0 * 2 + par) * 4 + 2 * c) * C2_PLANE + shift * 16);
+                    const uint32_t a_lo = (uint32_t)(((1 * 2 + par) * 4 + 2 * c) * C2_PLANE + shift * 16);
+                    ops.push_back({a_hi, (uint32_t)C2_PLANE, (uint32_t)(tile * 2048), 0u | (first ? 0u : kOpAcc)});
+                    ops.push_back({a_lo, (uint32_t)C2_PLANE, (uint32_t)(tile * 2048), kOpAcc});
+                    ops.push_back({a_hi, (uint32_t)C2_PLANE, (uint32_t)(12 * 2048 + tile * 2048), kOpAcc});
+                    first = false; tile++;
+                }
+    }
+    // ---------------- fc1: [k = pos*64 + ch][n 48]; per position 4 K-chunks, tiles hi0..3 then lo0..3
+    std::vector<uint8_t> wf_img((size_t)27 * WF_POS_BYTES, 0);
+    {
+        std::vector<uint8_t> thi(1536), tlo(1536);
+        for (int pos = 0; pos < 27; pos++)
+            for (int c = 0; c < 4; c++) {
+                std::fill(thi.begin(), thi.end(), 0); std::fill(tlo.begin(), tlo.end(), 0);
+                for (int s = 0; s < 16; s++)
+                    for (int n = 0; n < 48; n++)
+                        put_split(thi, tlo, btile_off(48, s, n), wf[((size_t)pos * 64 + 16 * c + s) * 48 + n]);
+                memcpy(wf_img.data() + (size_t)pos * WF_POS_BYTES + (size_t)c * 1536, thi.data(), 1536);
+                memcpy(wf_img.data() + (size_t)pos * WF_POS_BYTES + (size_t)(4 + c) * 1536, tlo.data(), 1536);
+            }
+        for (int c = 0; c < 4; c++) {
+            const uint32_t a_hi = (uint32_t)((0 * 8 + 2 * c) * 2048), a_lo = (uint32_t)((1 * 8 + 2 * c) * 2048);
+            ops.push_back({a_hi, 2048u, (uint32_t)(c * 1536), c == 0 ? 0u : kOpAcc});
+            ops.push_back({a_lo, 2048u, (uint32_t)(c * 1536), kOpAcc});
+            ops.push_back({a_hi, 2048u, (uint32_t)((4 + c) * 1536), kOpAcc});
+        }
+    }
+    if ((int)ops.size() != N_OPS1 + N_OPS2 + N_OPS3 + N_OPSF) { if (err) *err = "program size mismatch"; return NC_EINVAL; }
+
+    std::vector<uint8_t> img_a;
+    img_a.insert(img_a.end(), img_hi.begin(), img_hi.end());
+    img_a.insert(img_a.end(), img_lo.begin(), img_lo.end());
+    img_a.insert(img_a.end(), w2_hi.begin(), w2_hi.end());
+    img_a.insert(img_a.end(), w2_lo.begin(), w2_lo.end());
+    std::vector<uint8_t> img_b;
+    img_b.insert(img_b.end(), w3_hi.begin(), w3_hi.end());
+    img_b.insert(img_b.end(), w3_lo.begin(), w3_lo.end());
+    std::vector<float> bias;
+    bias.insert(bias.end(), b11, b11 + 16); bias.insert(bias.end(), b12, b12 + 16); bias.insert(bias.end(), b13, b13 + 16);
+    bias.insert(bias.end(), b2, b2 + 32); bias.insert(bias.end(), b3, b3 + 64); bias.insert(bias.end(), bf, bf + 48);
+
+    auto up = [&](DevBuf& d, const void* h, size_t bytes) -> cudaError_t {
+        cudaError_t e = d.reserve(bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync(d.p, h, bytes, cudaMemcpyHostToDevice, stream);
+    };
+    cudaError_t e;
+    if ((e = up(T.wimg_a, img_a.data(), img_a.size())) != cudaSuccess || (e = up(T.wimg_b, img_b.data(), img_b.size())) != cudaSuccess ||
+        (e = up(T.wimg_c, wf_img.data(), wf_img.size())) != cudaSuccess || (e = up(T.prog, ops.data(), ops.size() * sizeof(MmaOp))) != cudaSuccess ||
+        (e = up(T.bias, bias.data(), bias.size() * 4)) != cudaSuccess || (e = T.err.reserve(16)) != cudaSuccess ||
+        (e = cudaMemsetAsync(T.err.p, 0, 16, stream)) != cudaSuccess || (e = cudaStreamSynchronize(stream)) != cudaSuccess) {
+        if (err) *err = std::string("tc_model_prepare: ") + cudaGetErrorString(e);
+        return NC_ECUDA;
+    }
+    if (img_a.size() != (size_t)TA_SMEM_W) { if (err) *err = "TA weight image size mismatch"; return NC_EINVAL; }
+    T.ready = true;
+    return NC_OK;
+}
+
+// Runs TA -> TB -> TC over n sites.  `blob` = device pointer of the fp32 weight blob (tails).
+// stop_after: 0 = full forward, 1 = after TA, 2 = after TB (debug entry points).
+inline int tc_forward_ex(cudaStream_t stream, TcModel& T, int in_mode, const void* in_dev, int64_t in_site_stride, int64_t n,
+                         const NcSiteMeta* meta, const float* ref4, const float* scale_f, const double* scale_d, const TailW& tw,
+                         float* out_full, float* probs, int sm_count, uint64_t* launches, std::string* err, int stop_after) {
+    using namespace tcg;
+    if (!T.ready) return NC_ESTATE;
+    if (n <= 0) return NC_OK;
+    auto cuda_fail = [&](cudaError_t e, const char* what) { if (err) *err = std::string(what) + ": " + cudaGetErrorString(e); return NC_ECUDA; };
+    cudaError_t e;
+    const int64_t n_tiles = (n + 127) / 128;
+    if ((e = T.c2.reserve((size_t)n * C2_SITE_BYTES)) != cudaSuccess) return cuda_fail(e, "c2 alloc");
+    if ((e = T.c3.reserve((size_t)n_tiles * C3_TILE_BYTES)) != cudaSuccess) return cuda_fail(e, "c3 alloc");
+    static bool attr_set = false;
+    if (!attr_set) {
+        if ((e = cudaFuncSetAttribute(tc_trunk_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM)) != cudaSuccess) return cuda_fail(e, "TA smem attr");
+        if ((e = cudaFuncSetAttribute(tc_trunk_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM)) != cudaSuccess) return cuda_fail(e, "TB smem attr");
+        if ((e = cudaFuncSetAttribute(tc_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)) != cudaSuccess) return cuda_fail(e, "TC smem attr");
+        attr_set = true;
+    }
+    const MmaOp* prog = T.prog.as<MmaOp>();
+    const float* bias = T.bias.as<float>();
+    TAParams pa = {};
+    pa.in = in_dev; pa.in_mode = in_mode; pa.in_site_stride = in_site_stride; pa.scale_f = scale_f; pa.scale_d = scale_d; pa.n_sites = n;
+    pa.wimg = T.wimg_a.as<uint8_t>(); pa.prog1 = prog; pa.prog2 = prog + N_OPS1; pa.bias1 = bias; pa.bias2 = bias + 48;
+    pa.c2_out = T.c2.as<uint8_t>(); pa.err = T.err.as<int>();
+    const unsigned ga = (unsigned)std::min<int64_t>((n + 1) / 2, sm_count);
+    tc_trunk_a_kernel<<<ga, 256, TA_SMEM, stream>>>(pa);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "TA launch");
+    (*launches)++;
+    if (stop_after == 1) return NC_OK;
+    TBParams pb = {};
+    pb.c2 = T.c2.as<uint8_t>(); pb.n_sites = n; pb.wimg = T.wimg_b.as<uint8_t>(); pb.prog = prog + N_OPS1 + N_OPS2; pb.bias = bias + 80;
+    pb.c3_out = T.c3.as<uint8_t>(); pb.err = T.err.as<int>();
+    const int64_t n_groups = (n + 2) / 3;
+    const unsigned gb = (unsigned)std::min<int64_t>((n_groups + 1) / 2, sm_count);
+    tc_trunk_b_kernel<<<gb, 256, TB_SMEM, stream>>>(pb);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "TB launch");
+    (*launches)++;
+    if (stop_after == 2) return NC_OK;
+    TCParams pc = {};
+    pc.c3 = T.c3.as<uint8_t>(); pc.n_sites = n; pc.wimg = T.wimg_c.as<uint8_t>(); pc.prog = prog + N_OPS1 + N_OPS2 + N_OPS3; pc.bias = bias + 144;
+    pc.tail = tw; pc.haploid = T.kind == 1; pc.meta = meta; pc.ref4 = ref4; pc.out10 = out_full; pc.probs4 = probs; pc.err = T.err.as<int>();
+    if (pc.haploid && !pc.probs4) pc.probs4 = out_full;
+    tc_fc_kernel<<<(unsigned)n_tiles, 128, TC_SMEM, stream>>>(pc);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "TC launch");
+    (*launches)++;
+    return NC_OK;
 }
 
 }  // namespace nc
