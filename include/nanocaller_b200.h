@@ -105,6 +105,13 @@ int         nc_sync(nc_ctx* ctx);
 int         nc_get_timings(nc_ctx* ctx, NcTimings* out);
 int         nc_device_sm_count(nc_ctx* ctx);
 
+/* Measurement helpers (bench.py): CUDA events on the context stream — the only stream this library
+ * launches on — in slots 0..3, and a switch that drops the decoded aligned rows so the next scan runs
+ * K0 again on the already staged (HBM-resident) reads. */
+int         nc_event_record(nc_ctx* ctx, int slot);
+int         nc_event_elapsed_ms(nc_ctx* ctx, int slot_start, int slot_end, float* ms);   /* synchronises */
+int         nc_invalidate_decode(nc_ctx* ctx);
+
 /* Replaces pysam.Samfile/FastaFile opening at generate_SNP_pileups.py:134-137: uploads one
  * contig's coordinate-sorted alignments in BAM-native encoding (SAM spec 4.2: 0-based pos,
  * CIGAR as len<<4|op, 4-bit bases two per byte, each read starting on a byte boundary at
@@ -153,6 +160,9 @@ int nc_load_snp_weights(nc_ctx* ctx, const float* blob, size_t n_floats, double 
  * softmax columns of the four heads (snpCaller.py:115) or the haploid 4-way softmax (:183).
  * impl: 0 = tcgen05 tensor-core kernel (default), 1 = fp32 CUDA-core kernel. */
 int nc_snp_forward(nc_ctx* ctx, int normalize, int impl, float* probs);
+
+/* Copies the probabilities of the last nc_snp_forward to the host: float32 [n_sites][4]. */
+int nc_snp_fetch_probs(nc_ctx* ctx, float* probs);
 
 /* Drop-in for snp_model([x, A_ref, G_ref, T_ref, C_ref]) (snpCaller.py:111) and
  * hap_snp_model([x, ref]) (:183) on host tensors: x float32 [n][5][41][5] (already scaled),

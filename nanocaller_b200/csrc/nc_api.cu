@@ -60,7 +60,7 @@ struct nc_ctx {
     Model snp[2], indel[2];
     DevBuf ws_c1, ws_c2, ws_c3, ws_f1, ws_sf, ws_sd, ws_x, ws_ref, ws_out;
     // timings
-    cudaEvent_t ev[10] = {};
+    cudaEvent_t ev[12] = {};     // 0-7 phase timings, 8-11 user slots (nc_event_record)
     NcTimings tm = {};
     bool tm_decode = false, tm_scan = false, tm_cnn = false;
 };
@@ -388,6 +388,27 @@ int nc_get_timings(nc_ctx* c, NcTimings* out) {
     return NC_OK;
 }
 
+int nc_event_record(nc_ctx* c, int slot) {
+    if (!c || slot < 0 || slot > 3) return fail(c, NC_EINVAL, "nc_event_record: slot must be 0..3");
+    NC_CUDA(cudaSetDevice(c->device));
+    NC_CUDA(cudaEventRecord(c->ev[8 + slot], c->stream));
+    return NC_OK;
+}
+
+int nc_event_elapsed_ms(nc_ctx* c, int a, int b, float* ms) {
+    if (!c || !ms || a < 0 || a > 3 || b < 0 || b > 3) return fail(c, NC_EINVAL, "nc_event_elapsed_ms: bad argument");
+    NC_CUDA(cudaSetDevice(c->device));
+    NC_CUDA(cudaEventSynchronize(c->ev[8 + b]));
+    NC_CUDA(cudaEventElapsedTime(ms, c->ev[8 + a], c->ev[8 + b]));
+    return NC_OK;
+}
+
+int nc_invalidate_decode(nc_ctx* c) {
+    if (!c) return NC_EINVAL;
+    c->decoded = false; c->scanned = false; c->have_probs = false;
+    return NC_OK;
+}
+
 int nc_stage_reads(nc_ctx* c, int64_t n_reads, const int32_t* pos, const uint16_t* flag, const int64_t* cigar_off,
                    const uint32_t* cigar, const int64_t* seq_off, const int32_t* l_seq, const uint8_t* seq4,
                    const uint8_t* ref, int64_t ref_start, int64_t ref_len) {
@@ -673,6 +694,15 @@ int nc_snp_forward(nc_ctx* c, int normalize, int impl, float* probs) {
         if (impl == 0) return tc_check(c, M);
     }
     return NC_OK;
+}
+
+int nc_snp_fetch_probs(nc_ctx* c, float* probs) {
+    if (!c || !probs) return fail(c, NC_EINVAL, "nc_snp_fetch_probs: null argument");
+    if (!c->scanned || !c->have_probs) return fail(c, NC_ESTATE, "nc_snp_fetch_probs before nc_snp_forward");
+    NC_CUDA(cudaSetDevice(c->device));
+    if (c->n_sites) NC_CUDA(cudaMemcpyAsync(probs, c->d_probs.p, (size_t)c->n_sites * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    NC_CUDA(cudaStreamSynchronize(c->stream));
+    return tc_check(c, c->snp[c->scan_haploid ? 1 : 0]);
 }
 
 int nc_snp_model_forward(nc_ctx* c, const float* x, const float* ref_onehot, int64_t n, int haploid, int impl, float* out) {

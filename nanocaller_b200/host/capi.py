@@ -14,8 +14,8 @@ SEQ_CODES = {"ont": 0, "short_ont": 1, "ul_ont": 2, "ul_ont_extreme": 3, "pacbio
 SITE_ELEMS, SITE_STRIDE = 1025, 1032
 
 EXPORTS = ["nc_abi_version", "nc_create", "nc_destroy", "nc_last_error", "nc_sync", "nc_get_timings",
-           "nc_device_sm_count", "nc_stage_reads", "nc_decode_reads", "nc_snp_scan", "nc_snp_fetch",
-           "nc_load_snp_weights", "nc_snp_forward", "nc_snp_model_forward", "nc_snp_device_buffers",
+           "nc_device_sm_count", "nc_event_record", "nc_event_elapsed_ms", "nc_invalidate_decode", "nc_stage_reads", "nc_decode_reads", "nc_snp_scan", "nc_snp_fetch",
+           "nc_load_snp_weights", "nc_snp_forward", "nc_snp_fetch_probs", "nc_snp_model_forward", "nc_snp_device_buffers",
            "nc_load_indel_weights", "nc_indel_model_forward"]
 
 
@@ -67,12 +67,16 @@ def load_library():
     lib.nc_sync.argtypes = [vp]
     lib.nc_get_timings.argtypes = [vp, ctypes.POINTER(NcTimings)]
     lib.nc_device_sm_count.argtypes = [vp]
+    lib.nc_event_record.argtypes = [vp, ctypes.c_int]
+    lib.nc_event_elapsed_ms.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+    lib.nc_invalidate_decode.argtypes = [vp]
     lib.nc_stage_reads.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64]
     lib.nc_decode_reads.argtypes = [vp]
     lib.nc_snp_scan.argtypes = [vp, ctypes.POINTER(NcSnpParams), vp, i32, vp, i32, ctypes.POINTER(i64)]
     lib.nc_snp_fetch.argtypes = [vp, vp, vp, vp, vp]
     lib.nc_load_snp_weights.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_double, ctypes.c_int]
     lib.nc_snp_forward.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    lib.nc_snp_fetch_probs.argtypes = [vp, vp]
     lib.nc_snp_model_forward.argtypes = [vp, vp, vp, i64, ctypes.c_int, ctypes.c_int, vp]
     lib.nc_snp_device_buffers.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64)]
     lib.nc_load_indel_weights.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_int]
@@ -175,6 +179,15 @@ class Context:
         self._check(self._lib.nc_snp_forward(self._h, 1 if normalize else 0, impl, _p(probs) if fetch and self.n_sites else None))
         return probs
 
+    def fetch_calls(self, probs, meta):
+        """Per-site call records of the last scan + forward into caller-owned (e.g. pinned) arrays:
+        probs float32 [n_sites,4], meta META_DTYPE-sized rows [n_sites]."""
+        if self.n_sites == 0:
+            return
+        assert probs.nbytes >= self.n_sites * 16 and meta.nbytes >= self.n_sites * META_DTYPE.itemsize
+        self._check(self._lib.nc_snp_fetch(self._h, None, _p(meta), None, None))
+        self._check(self._lib.nc_snp_fetch_probs(self._h, _p(probs)))
+
     def snp_model_forward(self, x, ref_onehot, haploid=False, impl=0):
         x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 5, 41, 5)
         ref = np.ascontiguousarray(ref_onehot, dtype=np.float32).reshape(-1, 4)
@@ -198,6 +211,17 @@ class Context:
         t = NcTimings()
         self._check(self._lib.nc_get_timings(self._h, ctypes.byref(t)))
         return {k: getattr(t, k) for k, _ in NcTimings._fields_}
+
+    def event_record(self, slot):
+        self._check(self._lib.nc_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = ctypes.c_float()
+        self._check(self._lib.nc_event_elapsed_ms(self._h, a, b, ctypes.byref(ms)))
+        return ms.value
+
+    def invalidate_decode(self):
+        self._check(self._lib.nc_invalidate_decode(self._h))
 
     def sm_count(self):
         return self._lib.nc_device_sm_count(self._h)
