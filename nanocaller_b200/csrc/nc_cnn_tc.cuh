@@ -81,6 +81,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, float* r) {
 #pragma unroll
     for (int i = 0; i < 16; i++) r[i] = __uint_as_float(v[i]);
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t addr, float* r) {
+    uint32_t v[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(addr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) r[i] = __uint_as_float(v[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xFFFFFFFF;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" :: "r"(wg + 1) : "memory"); }
 
 // SELU with the fast exponential (ex2.approx): abs error ~1e-7 on the negative branch.
@@ -103,6 +118,29 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     lo = *reinterpret_cast<uint4*>(l);
 }
 
+// Branch-free SELU: sa*(exp(min(x,0)) - 1) + scale*max(x,0)  (6 instructions, exact 0 contribution for x > 0).
+__device__ __forceinline__ float selu_bf(float x) {
+    const float scale = 1.0507009873554805f, sa = 1.0507009873554805f * 1.6732632423543772f;
+    return fmaf(sa, __expf(fminf(x, 0.f)), -sa) + scale * fmaxf(x, 0.f);
+}
+// two values -> packed (hi, hi) and (lo, lo) fp16 pairs; upper clamp keeps hi finite (SELU bounds the lower side)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    a = fminf(a, 65000.f); b = fminf(b, 65000.f);
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// 8 accumulator values + bias -> SELU -> hi / lo 16-byte words
+__device__ __forceinline__ void act_split8(const float* acc, const float* bias, uint4& hi, uint4& lo) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias), b1 = *reinterpret_cast<const float4*>(bias + 4);
+    split2(selu_bf(acc[0] + b0.x), selu_bf(acc[1] + b0.y), hi.x, lo.x);
+    split2(selu_bf(acc[2] + b0.z), selu_bf(acc[3] + b0.w), hi.y, lo.y);
+    split2(selu_bf(acc[4] + b1.x), selu_bf(acc[5] + b1.y), hi.z, lo.z);
+    split2(selu_bf(acc[6] + b1.z), selu_bf(acc[7] + b1.w), hi.w, lo.w);
+}
+
 // One MMA of a layer's "program": where its A rows start, how its two K groups are spaced, which
 // B tile it multiplies and which accumulator columns it adds into.
 struct MmaOp { uint32_t a_off, a_lbo, b_off, misc; };     // misc: bits 0-9 D column, bit 15 accumulate
@@ -114,6 +152,29 @@ __device__ __forceinline__ void issue_program(const MmaOp* prog, int n_ops, uint
         const MmaOp op = prog[i];
         umma_f16(d_base + (op.misc & 0x3FFu), make_sdesc(a_base + op.a_off, op.a_lbo, 128u),
                  make_sdesc(w_base + op.b_off, b_lbo, 128u), idesc, (op.misc & kOpAcc) ? 1u : 0u);
+    }
+}
+
+// Programs in constant memory: the operand offsets depend only on the layer geometry, not on the weights.
+// a_lo = (A byte offset >> 4) | ((LBO bytes >> 4) << 16), b_off16 = B tile byte offset >> 4, misc as in MmaOp.
+struct COp { uint32_t a_lo, b_off16, misc; };
+__constant__ COp c_prog1[54];
+__constant__ COp c_prog2[54];
+__constant__ COp c_prog3[36];
+__constant__ COp c_progF[12];
+constexpr uint64_t kDescHi = 0x4008ull << 32;        // SBO = 128 B, descriptor version 1
+
+// Issued by one whole (converged) warp: address arithmetic stays warp-uniform, only the MMA itself is
+// predicated on the elected lane.  a_base16 = A region smem address >> 4; b_base_lo = (B region >> 4) | (B LBO >> 4) << 16.
+template <int N_OPS>
+__device__ __forceinline__ void issue_cprog(const COp* prog, uint32_t a_base16, uint32_t b_base_lo, uint32_t d_base, uint32_t idesc,
+                                            bool leader, bool force_acc) {
+#pragma unroll 6
+    for (int i = 0; i < N_OPS; i++) {
+        const COp op = prog[i];
+        if (leader)
+            umma_f16(d_base + (op.misc & 0x3FFu), kDescHi | (uint64_t)(op.a_lo + a_base16), kDescHi | (uint64_t)(op.b_off16 + b_base_lo), idesc,
+                     (force_acc || (op.misc & kOpAcc)) ? 1u : 0u);
     }
 }
 
@@ -150,87 +211,119 @@ struct TAParams {
     const float* scale_f; const double* scale_d;
     int64_t n_sites;
     const uint8_t* wimg;                      // W1 tiles then W2 tiles
-    const MmaOp* prog1; const MmaOp* prog2;
     const float* bias1; const float* bias2;
     uint8_t* c2_out;
     int* err;
 };
 
+constexpr int TA_WGS = 3;
+constexpr int TA_THREADS = TA_WGS * 128;
 constexpr int TA_SMEM_W = tcg::W1_BYTES + tcg::W2_BYTES;                           // 64512
 constexpr int TA_SMEM_WG = 2 * tcg::IN_PLANE + tcg::C1_BYTES;                      // 13312 + 41344
-constexpr int TA_SMEM_MISC = (tcg::N_OPS1 + tcg::N_OPS2) * 16 + 80 * 4 + 64;
-constexpr int TA_SMEM = TA_SMEM_W + 2 * TA_SMEM_WG + TA_SMEM_MISC + 128;
+constexpr int TA_SMEM_MISC = 80 * 4 + 64;
+constexpr int TA_SMEM = TA_SMEM_W + TA_WGS * TA_SMEM_WG + TA_SMEM_MISC + 64;
 
-__global__ void __launch_bounds__(256, 1) tc_trunk_a_kernel(const TAParams P) {
+// one pixel (5 channels) of the network input as fp32, coverage scaling applied (snpCaller.py:90-96)
+__device__ __forceinline__ void ta_load_pixel(const TAParams& P, int64_t site, int px, float* v) {
+    const int h = px / 41;
+    if (P.in_mode == 0) {
+        const float* src = reinterpret_cast<const float*>(P.in) + site * P.in_site_stride + px * 5;
+#pragma unroll
+        for (int c = 0; c < 5; c++) v[c] = __ldg(src + c);
+    } else {
+        const int16_t* src = reinterpret_cast<const int16_t*>(P.in) + site * P.in_site_stride + px * 5;
+        int16_t raw[5];
+#pragma unroll
+        for (int c = 0; c < 5; c++) raw[c] = __ldg(src + c);
+        if (P.in_mode == 1) {
+            const float sc = h > 0 ? __ldg(P.scale_f + site) : 1.f;
+#pragma unroll
+            for (int c = 0; c < 5; c++) v[c] = c < 4 ? __fmul_rn((float)raw[c], sc) : (float)raw[c];
+        } else {
+            const double sc = __ldg(P.scale_d + site);
+#pragma unroll
+            for (int c = 0; c < 5; c++) v[c] = (h > 0 && c < 4) ? (float)((double)raw[c] * sc) : (float)raw[c];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_w = smem;
     uint8_t* s_wg0 = smem + TA_SMEM_W;
-    MmaOp* s_prog = reinterpret_cast<MmaOp*>(smem + TA_SMEM_W + 2 * TA_SMEM_WG);
-    float* s_bias = reinterpret_cast<float*>(s_prog + tcg::N_OPS1 + tcg::N_OPS2);
+    float* s_bias = reinterpret_cast<float*>(smem + TA_SMEM_W + TA_WGS * TA_SMEM_WG);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 80);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
 
-    const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = tid >> 5;
     uint8_t* s_in = s_wg0 + wg * TA_SMEM_WG;               // hi plane, then lo plane
     uint8_t* s_c1 = s_in + 2 * tcg::IN_PLANE;
 
-    // one-time setup: weights, programs, biases, zeroed activations, barriers, TMEM
-    for (int i = tid; i < TA_SMEM_W / 16; i += 256) reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(P.wimg) + i);
-    for (int i = tid; i < tcg::N_OPS1; i += 256) s_prog[i] = P.prog1[i];
-    for (int i = tid; i < tcg::N_OPS2; i += 256) s_prog[tcg::N_OPS1 + i] = P.prog2[i];
+    for (int i = tid; i < TA_SMEM_W / 16; i += TA_THREADS) reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(P.wimg) + i);
     if (tid < 48) s_bias[tid] = P.bias1[tid];
     if (tid >= 64 && tid < 96) s_bias[48 + tid - 64] = P.bias2[tid - 64];
-    for (int i = tid; i < 2 * TA_SMEM_WG / 16; i += 256) reinterpret_cast<uint4*>(s_wg0)[i] = make_uint4(0, 0, 0, 0);
-    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    if (warp == 0) tmem_alloc(s_tmem, 256);
+    for (int i = tid; i < TA_WGS * TA_SMEM_WG / 16; i += TA_THREADS) reinterpret_cast<uint4*>(s_wg0)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        for (int i = 0; i < TA_WGS; i++) mbar_init(&s_bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(s_tmem, 512);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem + (uint32_t)wg * 128u;                       // this warpgroup's 128 columns
-    const uint32_t tmem_lane = tmem + ((uint32_t)(warp & 3) << 21);            // lane quarter of this warp (lane << 16)
-    const uint32_t a_in = smem_u32(s_in), a_c1 = smem_u32(s_c1), a_w = smem_u32(s_w);
+    const uint32_t tmem_lane = tmem + ((uint32_t)(warp & 3) << 21);            // lane quarter of this warp
+    const uint32_t in16 = smem_u32(s_in) >> 4, c116 = smem_u32(s_c1) >> 4, w16 = smem_u32(s_w) >> 4;
     const uint32_t idesc1 = make_idesc_f16(128, 16), idesc2 = make_idesc_f16(128, 32);
+    const bool issuer_warp = (warp & 3) == 0;
     uint32_t phase = 0;
     bool ok = true;
 
-    for (int64_t site = (int64_t)blockIdx.x * 2 + wg; site < P.n_sites; site += (int64_t)gridDim.x * 2) {
-        // ---- input: [5][41][5] -> padded planes (pixel row = (h+2)*45 + (w+2)), channels 5..7 stay zero
-        for (int px = t; px < 205; px += 128) {
-            const int h = px / 41, w = px - h * 41;
-            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (P.in_mode == 0) {
-                const float* src = reinterpret_cast<const float*>(P.in) + site * P.in_site_stride + px * 5;
+    const int64_t stride = (int64_t)gridDim.x * TA_WGS;
+    int64_t site = (int64_t)blockIdx.x * TA_WGS + wg;
+    float pv[2][5];
+    const int px1 = t + 128;
+    if (site < P.n_sites) {
+        ta_load_pixel(P, site, t, pv[0]);
+        if (px1 < 205) ta_load_pixel(P, site, px1, pv[1]);
+    }
+    for (; site < P.n_sites; site += stride) {
+        // ---- input: prefetched pixels -> padded planes (pixel row = (h+2)*45 + (w+2)), channels 5..7 stay zero
 #pragma unroll
-                for (int c = 0; c < 5; c++) v[c] = __ldg(src + c);
-            } else {
-                const int16_t* src = reinterpret_cast<const int16_t*>(P.in) + site * P.in_site_stride + px * 5;
-#pragma unroll
-                for (int c = 0; c < 5; c++) {
-                    const int16_t raw = __ldg(src + c);
-                    float x = (float)raw;
-                    if (h > 0 && c < 4) {
-                        if (P.in_mode == 1) x = __fmul_rn(x, __ldg(P.scale_f + site));
-                        else x = (float)((double)raw * __ldg(P.scale_d + site));
-                    }
-                    v[c] = x;
-                }
+        for (int k = 0; k < 2; k++) {
+            const int px = t + 128 * k;
+            if (px < 205) {
+                const int h = px / 41, w = px - h * 41;
+                uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+                split2(fmaxf(pv[k][0], -65000.f), fmaxf(pv[k][1], -65000.f), hi.x, lo.x);
+                split2(fmaxf(pv[k][2], -65000.f), fmaxf(pv[k][3], -65000.f), hi.y, lo.y);
+                split2(fmaxf(pv[k][4], -65000.f), 0.f, hi.z, lo.z);
+                const int row = (h + 2) * tcg::WP + w + 2;
+                *reinterpret_cast<uint4*>(s_in + row * 16) = hi;
+                *reinterpret_cast<uint4*>(s_in + tcg::IN_PLANE + row * 16) = lo;
             }
-            uint4 hi, lo;
-            split8(v, hi, lo);
-            const int row = (h + 2) * tcg::WP + w + 2;
-            *reinterpret_cast<uint4*>(s_in + row * 16) = hi;
-            *reinterpret_cast<uint4*>(s_in + tcg::IN_PLANE + row * 16) = lo;
         }
         fence_async_smem();
         tc_fence_before();
         wg_barrier(wg);
         // ---- conv1: two 128-row tiles, three branches -> 48 accumulator columns per tile
-        if (t == 0) {
+        if (issuer_warp) {
             tc_fence_after();
-            issue_program(s_prog, tcg::N_OPS1, a_in, a_w, 16 * 16, tmem, idesc1);
-            issue_program(s_prog, tcg::N_OPS1, a_in + tcg::TILE1_START * 16, a_w, 16 * 16, tmem + 48, idesc1);
-            umma_commit(&s_bar[wg]);
+            const bool leader = elect_one();
+            const uint32_t blo = w16 | ((16u * 16u >> 4) << 16);
+            issue_cprog<tcg::N_OPS1>(c_prog1, in16, blo, tmem, idesc1, leader, false);
+            issue_cprog<tcg::N_OPS1>(c_prog1, in16 + tcg::TILE1_START, blo, tmem + 48, idesc1, leader, false);
+            if (leader) umma_commit(&s_bar[wg]);
+            __syncwarp();
+        }
+        // ---- prefetch the next site's pixels while the tensor core works
+        {
+            const int64_t nxt = site + stride;
+            if (nxt < P.n_sites) {
+                ta_load_pixel(P, nxt, t, pv[0]);
+                if (px1 < 205) ta_load_pixel(P, nxt, px1, pv[1]);
+            }
         }
         ok = mbar_wait(&s_bar[wg], phase) && ok; phase ^= 1;
         tc_fence_after();
@@ -240,22 +333,19 @@ __global__ void __launch_bounds__(256, 1) tc_trunk_a_kernel(const TAParams P) {
             const int m = (j ? tcg::TILE1_START : 0) + t;
             const int h = m / tcg::WP, w = m - h * tcg::WP;
             const bool valid = m < 225 && w < 41 && (j == 0 || m >= 128);
-            const int row = h * tcg::C1_PITCH + (w >> 1), par = w & 1;
-#pragma unroll 1
-            for (int cb = 0; cb < 3; cb++) {
-                float acc[16];
-                tmem_ld16(tmem_lane + j * 48 + cb * 16, acc);
-                if (valid) {
+            float acc[48];
+            tmem_ld16_nowait(tmem_lane + j * 48, acc);
+            tmem_ld16_nowait(tmem_lane + j * 48 + 16, acc + 16);
+            tmem_ld16_nowait(tmem_lane + j * 48 + 32, acc + 32);
+            tmem_ld_wait();
+            if (valid) {
+                uint8_t* dst = s_c1 + ((w & 1) * 6) * tcg::C1_PLANE + (h * tcg::C1_PITCH + (w >> 1)) * 16;
 #pragma unroll
-                    for (int i = 0; i < 16; i++) acc[i] = selu_fast(acc[i] + s_bias[cb * 16 + i]);
-#pragma unroll
-                    for (int g = 0; g < 2; g++) {
-                        uint4 hi, lo;
-                        split8(acc + 8 * g, hi, lo);
-                        const int kg = cb * 2 + g;
-                        *reinterpret_cast<uint4*>(s_c1 + ((0 * 2 + par) * 6 + kg) * tcg::C1_PLANE + row * 16) = hi;
-                        *reinterpret_cast<uint4*>(s_c1 + ((1 * 2 + par) * 6 + kg) * tcg::C1_PLANE + row * 16) = lo;
-                    }
+                for (int kg = 0; kg < 6; kg++) {
+                    uint4 hi, lo;
+                    act_split8(acc + 8 * kg, s_bias + 8 * kg, hi, lo);
+                    *reinterpret_cast<uint4*>(dst + kg * tcg::C1_PLANE) = hi;
+                    *reinterpret_cast<uint4*>(dst + (12 + kg) * tcg::C1_PLANE) = lo;
                 }
             }
         }
@@ -263,10 +353,12 @@ __global__ void __launch_bounds__(256, 1) tc_trunk_a_kernel(const TAParams P) {
         tc_fence_before();
         wg_barrier(wg);
         // ---- conv2: one tile (rows h2*21 + w2), 6 taps x 3 K-chunks x 3 split terms
-        if (t == 0) {
+        if (issuer_warp) {
             tc_fence_after();
-            issue_program(s_prog + tcg::N_OPS1, tcg::N_OPS2, a_c1, a_w + tcg::W1_BYTES, 32 * 16, tmem + 96, idesc2);
-            umma_commit(&s_bar[wg]);
+            const bool leader = elect_one();
+            issue_cprog<tcg::N_OPS2>(c_prog2, c116, (w16 + (tcg::W1_BYTES >> 4)) | ((32u * 16u >> 4) << 16), tmem + 96, idesc2, leader, false);
+            if (leader) umma_commit(&s_bar[wg]);
+            __syncwarp();
         }
         ok = mbar_wait(&s_bar[wg], phase) && ok; phase ^= 1;
         tc_fence_after();
@@ -274,23 +366,18 @@ __global__ void __launch_bounds__(256, 1) tc_trunk_a_kernel(const TAParams P) {
         {
             const int m = t, h2 = m / tcg::C1_PITCH, w2 = m - h2 * tcg::C1_PITCH;
             const bool valid = m < 84 && w2 < 20;
-            uint8_t* dst = P.c2_out + site * tcg::C2_SITE_BYTES + (h2 * tcg::C2_PITCH + (w2 >> 1)) * 16;
-            const int par = w2 & 1;
-#pragma unroll 1
-            for (int cb = 0; cb < 2; cb++) {
-                float acc[16];
-                tmem_ld16(tmem_lane + 96 + cb * 16, acc);
-                if (valid) {
+            float acc[32];
+            tmem_ld16_nowait(tmem_lane + 96, acc);
+            tmem_ld16_nowait(tmem_lane + 112, acc + 16);
+            tmem_ld_wait();
+            if (valid) {
+                uint8_t* dst = P.c2_out + site * tcg::C2_SITE_BYTES + ((w2 & 1) * 4) * tcg::C2_CHUNK + (h2 * tcg::C2_PITCH + (w2 >> 1)) * 16;
 #pragma unroll
-                    for (int i = 0; i < 16; i++) acc[i] = selu_fast(acc[i] + s_bias[48 + cb * 16 + i]);
-#pragma unroll
-                    for (int g = 0; g < 2; g++) {
-                        uint4 hi, lo;
-                        split8(acc + 8 * g, hi, lo);
-                        const int kg = cb * 2 + g;
-                        *reinterpret_cast<uint4*>(dst + ((0 * 2 + par) * 4 + kg) * tcg::C2_CHUNK) = hi;
-                        *reinterpret_cast<uint4*>(dst + ((1 * 2 + par) * 4 + kg) * tcg::C2_CHUNK) = lo;
-                    }
+                for (int kg = 0; kg < 4; kg++) {
+                    uint4 hi, lo;
+                    act_split8(acc + 8 * kg, s_bias + 48 + 8 * kg, hi, lo);
+                    *reinterpret_cast<uint4*>(dst + kg * tcg::C2_CHUNK) = hi;
+                    *reinterpret_cast<uint4*>(dst + (8 + kg) * tcg::C2_CHUNK) = lo;
                 }
             }
         }
@@ -300,7 +387,7 @@ __global__ void __launch_bounds__(256, 1) tc_trunk_a_kernel(const TAParams P) {
     if (!ok && t == 0) atomicExch(P.err, 1);
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(*s_tmem, 256);
+    if (warp == 0) tmem_dealloc(*s_tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -308,43 +395,48 @@ __global__ void __launch_bounds__(256, 1) tc_trunk_a_kernel(const TAParams P) {
 // ------------------------------------------------------------------------------------------------
 struct TBParams {
     const uint8_t* c2; int64_t n_sites;
-    const uint8_t* wimg; const MmaOp* prog; const float* bias;
+    const uint8_t* wimg; const float* bias;
     uint8_t* c3_out; int* err;
 };
-constexpr int TB_SMEM_MISC = tcg::N_OPS3 * 16 + 64 * 4 + 64;
-constexpr int TB_SMEM = tcg::W3_BYTES + 2 * tcg::C2_SMEM + TB_SMEM_MISC + 128;
+constexpr int TB_WGS = 3;
+constexpr int TB_THREADS = TB_WGS * 128;
+constexpr int TB_SMEM_MISC = 64 * 4 + 64;
+constexpr int TB_SMEM = tcg::W3_BYTES + TB_WGS * tcg::C2_SMEM + TB_SMEM_MISC + 64;
 
-__global__ void __launch_bounds__(256, 1) tc_trunk_b_kernel(const TBParams P) {
+__global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_w = smem;
-    MmaOp* s_prog = reinterpret_cast<MmaOp*>(smem + tcg::W3_BYTES + 2 * tcg::C2_SMEM);
-    float* s_bias = reinterpret_cast<float*>(s_prog + tcg::N_OPS3);
+    float* s_bias = reinterpret_cast<float*>(smem + tcg::W3_BYTES + TB_WGS * tcg::C2_SMEM);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 64);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
     const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = tid >> 5;
     uint8_t* s_c2 = smem + tcg::W3_BYTES + wg * tcg::C2_SMEM;
 
-    for (int i = tid; i < tcg::W3_BYTES / 16; i += 256) reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(P.wimg) + i);
-    for (int i = tid; i < tcg::N_OPS3; i += 256) s_prog[i] = P.prog[i];
+    for (int i = tid; i < tcg::W3_BYTES / 16; i += TB_THREADS) reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(P.wimg) + i);
     if (tid < 64) s_bias[tid] = P.bias[tid];
-    for (int i = tid; i < 2 * tcg::C2_SMEM / 16; i += 256) reinterpret_cast<uint4*>(smem + tcg::W3_BYTES)[i] = make_uint4(0, 0, 0, 0);
-    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    if (warp == 0) tmem_alloc(s_tmem, 128);
+    for (int i = tid; i < TB_WGS * tcg::C2_SMEM / 16; i += TB_THREADS) reinterpret_cast<uint4*>(smem + tcg::W3_BYTES)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        for (int i = 0; i < TB_WGS; i++) mbar_init(&s_bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(s_tmem, 256);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem + (uint32_t)wg * 64u;
     const uint32_t tmem_lane = tmem + ((uint32_t)(warp & 3) << 21);
-    const uint32_t a_c2 = smem_u32(s_c2), a_w = smem_u32(s_w);
+    const uint32_t c216 = smem_u32(s_c2) >> 4, w16 = smem_u32(s_w) >> 4;
     const uint32_t idesc = make_idesc_f16(128, 64);
+    const bool issuer_warp = (warp & 3) == 0;
     uint32_t phase = 0;
     bool ok = true;
     const int64_t n_groups = (P.n_sites + 2) / 3;
 
-    for (int64_t grp = (int64_t)blockIdx.x * 2 + wg; grp < n_groups; grp += (int64_t)gridDim.x * 2) {
+    for (int64_t grp = (int64_t)blockIdx.x * TB_WGS + wg; grp < n_groups; grp += (int64_t)gridDim.x * TB_WGS) {
         const int64_t s0 = grp * 3;
         // ---- load: per site 16 chunks of 640 B -> plane (part, parity, kg) + s*640
+#pragma unroll 5
         for (int i = t; i < 3 * 16 * 40; i += 128) {
             const int s = i / 640, r = i - s * 640, ch = r / 40, q = r - ch * 40;
             uint4 v = make_uint4(0, 0, 0, 0);
@@ -354,10 +446,12 @@ __global__ void __launch_bounds__(256, 1) tc_trunk_b_kernel(const TBParams P) {
         fence_async_smem();
         tc_fence_before();
         wg_barrier(wg);
-        if (t == 0) {
+        if (issuer_warp) {
             tc_fence_after();
-            issue_program(s_prog, tcg::N_OPS3, a_c2, a_w, 64 * 16, tmem, idesc);
-            umma_commit(&s_bar[wg]);
+            const bool leader = elect_one();
+            issue_cprog<tcg::N_OPS3>(c_prog3, c216, w16 | ((64u * 16u >> 4) << 16), tmem, idesc, leader, false);
+            if (leader) umma_commit(&s_bar[wg]);
+            __syncwarp();
         }
         ok = mbar_wait(&s_bar[wg], phase) && ok; phase ^= 1;
         tc_fence_after();
@@ -369,19 +463,19 @@ __global__ void __launch_bounds__(256, 1) tc_trunk_b_kernel(const TBParams P) {
             const int pos = h3 * 9 + w3;
             uint8_t* dst = P.c3_out + (site >> 7) * (int64_t)tcg::C3_TILE_BYTES + (int64_t)(pos * 8) * 2048 + (site & 127) * 16;
 #pragma unroll 1
-            for (int cb = 0; cb < 4; cb++) {
-                float acc[16];
-                tmem_ld16(tmem_lane + cb * 16, acc);
+            for (int half = 0; half < 2; half++) {
+                float acc[32];
+                tmem_ld16_nowait(tmem_lane + half * 32, acc);
+                tmem_ld16_nowait(tmem_lane + half * 32 + 16, acc + 16);
+                tmem_ld_wait();
                 if (valid) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) acc[i] = selu_fast(acc[i] + s_bias[cb * 16 + i]);
-#pragma unroll
-                    for (int g = 0; g < 2; g++) {
+                    for (int g = 0; g < 4; g++) {
                         uint4 hi, lo;
-                        split8(acc + 8 * g, hi, lo);
-                        const int kg = cb * 2 + g;
+                        const int kg = half * 4 + g;
+                        act_split8(acc + 8 * g, s_bias + 8 * kg, hi, lo);
                         *reinterpret_cast<uint4*>(dst + (int64_t)kg * 2048) = hi;
-                        *reinterpret_cast<uint4*>(dst + (int64_t)tcg::FC_KG * 2048 + (int64_t)kg * 2048) = lo;
+                        *reinterpret_cast<uint4*>(dst + (int64_t)(tcg::FC_KG + kg) * 2048) = lo;
                     }
                 }
             }
@@ -392,7 +486,7 @@ __global__ void __launch_bounds__(256, 1) tc_trunk_b_kernel(const TBParams P) {
     if (!ok && t == 0) atomicExch(P.err, 1);
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(*s_tmem, 128);
+    if (warp == 0) tmem_dealloc(*s_tmem, 256);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -401,7 +495,6 @@ __global__ void __launch_bounds__(256, 1) tc_trunk_b_kernel(const TBParams P) {
 struct TCParams {
     const uint8_t* c3; int64_t n_sites;
     const uint8_t* wimg;            // [27 positions][8 tiles of 1536 B]
-    const MmaOp* prog;              // 12 ops, offsets relative to a stage
     const float* bias;              // fc1 bias (48)
     TailW tail; int haploid;
     const NcSiteMeta* meta; const float* ref4;
@@ -410,7 +503,7 @@ struct TCParams {
 };
 constexpr int TC_STAGE_A = 2 * 8 * 2048;                    // 32768: [part][kg 8][128 rows][16 B]
 constexpr int TC_STAGE = TC_STAGE_A + tcg::WF_POS_BYTES;    // + 12288 of weights
-constexpr int TC_SMEM = 2 * TC_STAGE + tcg::N_OPSF * 16 + 48 * 4 + 64 + 128;
+constexpr int TC_SMEM = 2 * TC_STAGE + 48 * 4 + 64 + 64;
 
 __device__ __forceinline__ void snp_tail_row(const float* x, int64_t s, const TCParams& P) {
     const TailW& w = P.tail;
@@ -449,14 +542,12 @@ __device__ __forceinline__ void snp_tail_row(const float* x, int64_t s, const TC
 
 __global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    MmaOp* s_prog = reinterpret_cast<MmaOp*>(smem + 2 * TC_STAGE);
-    float* s_bias = reinterpret_cast<float*>(s_prog + tcg::N_OPSF);
+    float* s_bias = reinterpret_cast<float*>(smem + 2 * TC_STAGE);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 48);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
     const int t = threadIdx.x, warp = t >> 5;
     const int64_t tile = blockIdx.x;
 
-    if (t < tcg::N_OPSF) s_prog[t] = P.prog[t];
     if (t < 48) s_bias[t] = P.bias[t];
     if (t == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) tmem_alloc(s_tmem, 64);
@@ -472,11 +563,13 @@ __global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
     auto load_stage = [&](int pos) {
         uint8_t* st = smem + (pos & 1) * TC_STAGE;
         // A: per part 8 k-groups x 2048 B contiguous in HBM at k-group pos*8
+#pragma unroll 4
         for (int i = t; i < TC_STAGE_A / 16; i += 128) {
             const int part = i >> 10, r = i & 1023;
             reinterpret_cast<uint4*>(st)[i] = __ldg(reinterpret_cast<const uint4*>(a_src + ((int64_t)part * tcg::FC_KG + pos * 8) * 2048) + r);
         }
         const uint4* wsrc = reinterpret_cast<const uint4*>(P.wimg + (int64_t)pos * tcg::WF_POS_BYTES);
+#pragma unroll 3
         for (int i = t; i < tcg::WF_POS_BYTES / 16; i += 128) reinterpret_cast<uint4*>(st + TC_STAGE_A)[i] = __ldg(wsrc + i);
     };
 
@@ -485,15 +578,13 @@ __global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (t == 0) {
+        if (warp == 0) {
             tc_fence_after();
-            const uint32_t sb = smem_u32(smem + (pos & 1) * TC_STAGE);
-            for (int i = 0; i < tcg::N_OPSF; i++) {
-                const MmaOp op = s_prog[i];
-                umma_f16(tmem, make_sdesc(sb + op.a_off, op.a_lbo, 128u), make_sdesc(sb + TC_STAGE_A + op.b_off, 48 * 16, 128u), idesc,
-                         (pos > 0 || (op.misc & kOpAcc)) ? 1u : 0u);
-            }
-            umma_commit(&s_bar[pos & 1]);
+            const bool leader = elect_one();
+            const uint32_t sb16 = smem_u32(smem + (pos & 1) * TC_STAGE) >> 4;
+            issue_cprog<tcg::N_OPSF>(c_progF, sb16, (sb16 + (TC_STAGE_A >> 4)) | ((48u * 16u >> 4) << 16), tmem, idesc, leader, pos > 0);
+            if (leader) umma_commit(&s_bar[pos & 1]);
+            __syncwarp();
         }
         if (pos + 1 < 27) {
             if (pos >= 1) ok = mbar_wait(&s_bar[(pos + 1) & 1], ((pos - 1) >> 1) & 1) && ok;   // MMAs of pos-1 released that stage
@@ -505,12 +596,14 @@ __global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
     tc_fence_after();
     {
         float x[48];
-#pragma unroll
-        for (int cb = 0; cb < 3; cb++) tmem_ld16(tmem_lane + cb * 16, x + cb * 16);
+        tmem_ld16_nowait(tmem_lane, x);
+        tmem_ld16_nowait(tmem_lane + 16, x + 16);
+        tmem_ld16_nowait(tmem_lane + 32, x + 32);
+        tmem_ld_wait();
         const int64_t s = tile * 128 + t;
         if (s < P.n_sites) {
 #pragma unroll
-            for (int i = 0; i < 48; i++) x[i] = selu_fast(x[i] + s_bias[i]);
+            for (int i = 0; i < 48; i++) x[i] = selu_bf(x[i] + s_bias[i]);
             snp_tail_row(x, s, P);
         }
     }
@@ -728,6 +821,18 @@ inline int tc_model_prepare(cudaStream_t stream, TcModel& T, int kind, const flo
         return NC_ECUDA;
     }
     if (img_a.size() != (size_t)TA_SMEM_W) { if (err) *err = "TA weight image size mismatch"; return NC_EINVAL; }
+    {   // programs -> constant memory (geometry only: identical for every SNP model)
+        std::vector<COp> cp(ops.size());
+        for (size_t i = 0; i < ops.size(); i++) cp[i] = {(ops[i].a_off >> 4) | ((ops[i].a_lbo >> 4) << 16), ops[i].b_off >> 4, ops[i].misc};
+        if ((e = cudaMemcpyToSymbolAsync(c_prog1, cp.data(), N_OPS1 * sizeof(COp), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
+            (e = cudaMemcpyToSymbolAsync(c_prog2, cp.data() + N_OPS1, N_OPS2 * sizeof(COp), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
+            (e = cudaMemcpyToSymbolAsync(c_prog3, cp.data() + N_OPS1 + N_OPS2, N_OPS3 * sizeof(COp), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
+            (e = cudaMemcpyToSymbolAsync(c_progF, cp.data() + N_OPS1 + N_OPS2 + N_OPS3, N_OPSF * sizeof(COp), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(stream)) != cudaSuccess) {
+            if (err) *err = std::string("tc_model_prepare (programs): ") + cudaGetErrorString(e);
+            return NC_ECUDA;
+        }
+    }
     T.ready = true;
     return NC_OK;
 }
@@ -752,28 +857,27 @@ inline int tc_forward_ex(cudaStream_t stream, TcModel& T, int in_mode, const voi
         if ((e = cudaFuncSetAttribute(tc_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)) != cudaSuccess) return cuda_fail(e, "TC smem attr");
         attr_set = true;
     }
-    const MmaOp* prog = T.prog.as<MmaOp>();
     const float* bias = T.bias.as<float>();
     TAParams pa = {};
     pa.in = in_dev; pa.in_mode = in_mode; pa.in_site_stride = in_site_stride; pa.scale_f = scale_f; pa.scale_d = scale_d; pa.n_sites = n;
-    pa.wimg = T.wimg_a.as<uint8_t>(); pa.prog1 = prog; pa.prog2 = prog + N_OPS1; pa.bias1 = bias; pa.bias2 = bias + 48;
+    pa.wimg = T.wimg_a.as<uint8_t>(); pa.bias1 = bias; pa.bias2 = bias + 48;
     pa.c2_out = T.c2.as<uint8_t>(); pa.err = T.err.as<int>();
-    const unsigned ga = (unsigned)std::min<int64_t>((n + 1) / 2, sm_count);
-    tc_trunk_a_kernel<<<ga, 256, TA_SMEM, stream>>>(pa);
+    const unsigned ga = (unsigned)std::min<int64_t>((n + TA_WGS - 1) / TA_WGS, sm_count);
+    tc_trunk_a_kernel<<<ga, TA_THREADS, TA_SMEM, stream>>>(pa);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "TA launch");
     (*launches)++;
     if (stop_after == 1) return NC_OK;
     TBParams pb = {};
-    pb.c2 = T.c2.as<uint8_t>(); pb.n_sites = n; pb.wimg = T.wimg_b.as<uint8_t>(); pb.prog = prog + N_OPS1 + N_OPS2; pb.bias = bias + 80;
+    pb.c2 = T.c2.as<uint8_t>(); pb.n_sites = n; pb.wimg = T.wimg_b.as<uint8_t>(); pb.bias = bias + 80;
     pb.c3_out = T.c3.as<uint8_t>(); pb.err = T.err.as<int>();
     const int64_t n_groups = (n + 2) / 3;
-    const unsigned gb = (unsigned)std::min<int64_t>((n_groups + 1) / 2, sm_count);
-    tc_trunk_b_kernel<<<gb, 256, TB_SMEM, stream>>>(pb);
+    const unsigned gb = (unsigned)std::min<int64_t>((n_groups + TB_WGS - 1) / TB_WGS, sm_count);
+    tc_trunk_b_kernel<<<gb, TB_THREADS, TB_SMEM, stream>>>(pb);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "TB launch");
     (*launches)++;
     if (stop_after == 2) return NC_OK;
     TCParams pc = {};
-    pc.c3 = T.c3.as<uint8_t>(); pc.n_sites = n; pc.wimg = T.wimg_c.as<uint8_t>(); pc.prog = prog + N_OPS1 + N_OPS2 + N_OPS3; pc.bias = bias + 144;
+    pc.c3 = T.c3.as<uint8_t>(); pc.n_sites = n; pc.wimg = T.wimg_c.as<uint8_t>(); pc.bias = bias + 144;
     pc.tail = tw; pc.haploid = T.kind == 1; pc.meta = meta; pc.ref4 = ref4; pc.out10 = out_full; pc.probs4 = probs; pc.err = T.err.as<int>();
     if (pc.haploid && !pc.probs4) pc.probs4 = out_full;
     tc_fc_kernel<<<(unsigned)n_tiles, 128, TC_SMEM, stream>>>(pc);
