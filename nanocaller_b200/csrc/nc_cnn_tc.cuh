@@ -155,29 +155,6 @@ __device__ __forceinline__ void issue_program(const MmaOp* prog, int n_ops, uint
     }
 }
 
-// Programs in constant memory: the operand offsets depend only on the layer geometry, not on the weights.
-// a_lo = (A byte offset >> 4) | ((LBO bytes >> 4) << 16), b_off16 = B tile byte offset >> 4, misc as in MmaOp.
-struct COp { uint32_t a_lo, b_off16, misc; };
-__constant__ COp c_prog1[54];
-__constant__ COp c_prog2[54];
-__constant__ COp c_prog3[36];
-__constant__ COp c_progF[12];
-constexpr uint64_t kDescHi = 0x4008ull << 32;        // SBO = 128 B, descriptor version 1
-
-// Issued by one whole (converged) warp: address arithmetic stays warp-uniform, only the MMA itself is
-// predicated on the elected lane.  a_base16 = A region smem address >> 4; b_base_lo = (B region >> 4) | (B LBO >> 4) << 16.
-template <int N_OPS>
-__device__ __forceinline__ void issue_cprog(const COp* prog, uint32_t a_base16, uint32_t b_base_lo, uint32_t d_base, uint32_t idesc,
-                                            bool leader, bool force_acc) {
-#pragma unroll 6
-    for (int i = 0; i < N_OPS; i++) {
-        const COp op = prog[i];
-        if (leader)
-            umma_f16(d_base + (op.misc & 0x3FFu), kDescHi | (uint64_t)(op.a_lo + a_base16), kDescHi | (uint64_t)(op.b_off16 + b_base_lo), idesc,
-                     (force_acc || (op.misc & kOpAcc)) ? 1u : 0u);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // geometry of the SNP trunk
 // ------------------------------------------------------------------------------------------------
@@ -206,6 +183,65 @@ constexpr int WF_POS_BYTES = 8 * 1536;         // per position: 4 K-chunks x (hi
 constexpr int N_OPS1 = 54, N_OPS2 = 54, N_OPS3 = 36, N_OPSF = 12;
 }  // namespace tcg
 
+// ---- compile-time MMA programs -----------------------------------------------------------------
+// The operand offsets depend only on the layer geometry, so every descriptor is (runtime smem base) +
+// (compile-time constant): after unrolling, one MMA costs a handful of integer instructions.  All
+// offsets below are in 16-byte units (the descriptor granularity).  B tile order = tc_model_prepare.
+__device__ __forceinline__ uint64_t sdesc16(uint32_t lo) { return (0x4008ull << 32) | (uint64_t)lo; }   // SBO 128 B, version 1
+
+template <int BR> __device__ __forceinline__ constexpr int conv1_shift(int t) {
+    return BR == 0 ? 2 * tcg::WP + t : BR == 1 ? t * tcg::WP + 2 : (t / 5) * tcg::WP + (t % 5);
+}
+// one branch of conv1 on one tile: (a_hi | a_lo) x (w_hi ; w_hi) per tap, then (a_hi tap | a_hi tap') x (w_lo ; w_lo') per tap pair
+template <int BR>
+__device__ __forceinline__ void issue_conv1_branch(uint32_t in16, uint32_t w16, uint32_t d, uint32_t idesc) {
+    constexpr int NT = BR == 2 ? 25 : 5, HI0 = BR == 0 ? 0 : BR == 1 ? 5 : 10, LO0 = BR == 0 ? 35 : BR == 1 ? 38 : 41;
+    const uint32_t blo = w16 | (16u << 16);
+#pragma unroll
+    for (int t = 0; t < NT; t++)
+        umma_f16(d + BR * 16, sdesc16(in16 + conv1_shift<BR>(t) + ((uint32_t)(tcg::IN_PLANE / 16) << 16)), sdesc16(blo + (HI0 + t) * 32), idesc, t > 0 ? 1u : 0u);
+#pragma unroll
+    for (int p = 0; p < (NT + 1) / 2; p++) {
+        const int s0 = conv1_shift<BR>(2 * p);
+        const int lbo = (2 * p + 1 < NT) ? conv1_shift<BR>(2 * p + 1) - s0 : 1;
+        umma_f16(d + BR * 16, sdesc16(in16 + s0 + ((uint32_t)lbo << 16)), sdesc16(blo + (LO0 + p) * 32), idesc, 1u);
+    }
+}
+// taps [T0, T1) of conv2 (tap = kh*3 + kw) into accumulator d
+template <int T0, int T1>
+__device__ __forceinline__ void issue_conv2_taps(uint32_t c116, uint32_t w16, uint32_t d, uint32_t idesc) {
+    const uint32_t bhi = (w16 + tcg::W1_BYTES / 16) | (32u << 16), blo = bhi + 18 * 64;
+#pragma unroll
+    for (int tap = T0; tap < T1; tap++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const int kh = tap / 3, kw = tap % 3, par = kw & 1, shift = kh * tcg::C1_PITCH + (kw >> 1);
+            const uint32_t a_hi = c116 + (par * 6 + 2 * c) * tcg::C1_ROWS + shift + ((uint32_t)tcg::C1_ROWS << 16);
+            const uint32_t a_lo = a_hi + 12 * tcg::C1_ROWS;
+            const int idx = tap * 3 + c;
+            umma_f16(d, sdesc16(a_hi), sdesc16(bhi + idx * 64), idesc, (tap > T0 || c > 0) ? 1u : 0u);
+            umma_f16(d, sdesc16(a_lo), sdesc16(bhi + idx * 64), idesc, 1u);
+            umma_f16(d, sdesc16(a_hi), sdesc16(blo + idx * 64), idesc, 1u);
+        }
+}
+template <int T0, int T1>
+__device__ __forceinline__ void issue_conv3_taps(uint32_t c216, uint32_t w16, uint32_t d, uint32_t idesc) {
+    constexpr int PL = tcg::C2_PLANE / 16;          // 120
+    const uint32_t bhi = w16 | (64u << 16), blo = bhi + 12 * 128;
+#pragma unroll
+    for (int tap = T0; tap < T1; tap++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int kh = tap / 3, kw = tap % 3, par = kw & 1, shift = kh * tcg::C2_PITCH + (kw >> 1);
+            const uint32_t a_hi = c216 + (par * 4 + 2 * c) * PL + shift + ((uint32_t)PL << 16);
+            const uint32_t a_lo = a_hi + 8 * PL;
+            const int idx = tap * 2 + c;
+            umma_f16(d, sdesc16(a_hi), sdesc16(bhi + idx * 128), idesc, (tap > T0 || c > 0) ? 1u : 0u);
+            umma_f16(d, sdesc16(a_lo), sdesc16(bhi + idx * 128), idesc, 1u);
+            umma_f16(d, sdesc16(a_hi), sdesc16(blo + idx * 128), idesc, 1u);
+        }
+}
+
 struct TAParams {
     const void* in; int in_mode; int64_t in_site_stride;
     const float* scale_f; const double* scale_d;
@@ -222,29 +258,18 @@ constexpr int TA_SMEM_W = tcg::W1_BYTES + tcg::W2_BYTES;                        
 constexpr int TA_SMEM_WG = 2 * tcg::IN_PLANE + tcg::C1_BYTES;                      // 13312 + 41344
 constexpr int TA_SMEM_MISC = 80 * 4 + 64;
 constexpr int TA_SMEM = TA_SMEM_W + TA_WGS * TA_SMEM_WG + TA_SMEM_MISC + 64;
+constexpr int TA_TMEM_WG = 160;                                                    // conv1 2 x 48 + conv2 2 partial x 32
 
-// one pixel (5 channels) of the network input as fp32, coverage scaling applied (snpCaller.py:90-96)
-__device__ __forceinline__ void ta_load_pixel(const TAParams& P, int64_t site, int px, float* v) {
-    const int h = px / 41;
-    if (P.in_mode == 0) {
-        const float* src = reinterpret_cast<const float*>(P.in) + site * P.in_site_stride + px * 5;
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// fp32 debug / drop-in input path: one pixel (5 channels) straight from global memory
+__device__ __forceinline__ void ta_load_pixel_f32(const TAParams& P, int64_t site, int px, float* v) {
+    const float* src = reinterpret_cast<const float*>(P.in) + site * P.in_site_stride + px * 5;
 #pragma unroll
-        for (int c = 0; c < 5; c++) v[c] = __ldg(src + c);
-    } else {
-        const int16_t* src = reinterpret_cast<const int16_t*>(P.in) + site * P.in_site_stride + px * 5;
-        int16_t raw[5];
-#pragma unroll
-        for (int c = 0; c < 5; c++) raw[c] = __ldg(src + c);
-        if (P.in_mode == 1) {
-            const float sc = h > 0 ? __ldg(P.scale_f + site) : 1.f;
-#pragma unroll
-            for (int c = 0; c < 5; c++) v[c] = c < 4 ? __fmul_rn((float)raw[c], sc) : (float)raw[c];
-        } else {
-            const double sc = __ldg(P.scale_d + site);
-#pragma unroll
-            for (int c = 0; c < 5; c++) v[c] = (h > 0 && c < 4) ? (float)((double)raw[c] * sc) : (float)raw[c];
-        }
-    }
+    for (int c = 0; c < 5; c++) v[c] = __ldg(src + c);
 }
 
 __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParams P) {
@@ -252,19 +277,20 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
     uint8_t* s_w = smem;
     uint8_t* s_wg0 = smem + TA_SMEM_W;
     float* s_bias = reinterpret_cast<float*>(smem + TA_SMEM_W + TA_WGS * TA_SMEM_WG);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 80);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 80);                     // [wg][2]: conv1 (4 arrivals), conv2 (2 arrivals)
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * TA_WGS);
 
-    const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = tid >> 5;
+    const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = tid >> 5, wq = warp & 3;
     uint8_t* s_in = s_wg0 + wg * TA_SMEM_WG;               // hi plane, then lo plane
     uint8_t* s_c1 = s_in + 2 * tcg::IN_PLANE;
+    uint8_t* s_raw = s_c1;                                 // the raw int16 site image is staged where c1 will be written later
 
     for (int i = tid; i < TA_SMEM_W / 16; i += TA_THREADS) reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(P.wimg) + i);
     if (tid < 48) s_bias[tid] = P.bias1[tid];
     if (tid >= 64 && tid < 96) s_bias[48 + tid - 64] = P.bias2[tid - 64];
     for (int i = tid; i < TA_WGS * TA_SMEM_WG / 16; i += TA_THREADS) reinterpret_cast<uint4*>(s_wg0)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
-        for (int i = 0; i < TA_WGS; i++) mbar_init(&s_bar[i], 1);
+        for (int i = 0; i < TA_WGS; i++) { mbar_init(&s_bar[2 * i], 4); mbar_init(&s_bar[2 * i + 1], 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(s_tmem, 512);
@@ -272,33 +298,58 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *s_tmem + (uint32_t)wg * 128u;                       // this warpgroup's 128 columns
-    const uint32_t tmem_lane = tmem + ((uint32_t)(warp & 3) << 21);            // lane quarter of this warp
+    const uint32_t tmem = *s_tmem + (uint32_t)wg * TA_TMEM_WG;
+    const uint32_t tmem_lane = tmem + ((uint32_t)wq << 21);                    // lane quarter of this warp
     const uint32_t in16 = smem_u32(s_in) >> 4, c116 = smem_u32(s_c1) >> 4, w16 = smem_u32(s_w) >> 4;
     const uint32_t idesc1 = make_idesc_f16(128, 16), idesc2 = make_idesc_f16(128, 32);
-    const bool issuer_warp = (warp & 3) == 0;
+    uint64_t* bar1 = &s_bar[2 * wg];
+    uint64_t* bar2 = &s_bar[2 * wg + 1];
     uint32_t phase = 0;
     bool ok = true;
 
     const int64_t stride = (int64_t)gridDim.x * TA_WGS;
     int64_t site = (int64_t)blockIdx.x * TA_WGS + wg;
-    float pv[2][5];
-    const int px1 = t + 128;
-    if (site < P.n_sites) {
-        ta_load_pixel(P, site, t, pv[0]);
-        if (px1 < 205) ta_load_pixel(P, site, px1, pv[1]);
-    }
+    const bool raw_mode = P.in_mode != 0;
+    uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = make_uint4(0, 0, 0, 0);
+    auto prefetch = [&](int64_t sidx) {          // 2064 B of int16 -> registers, 16 B per thread (+1 chunk on thread 0)
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(P.in) + sidx * P.in_site_stride * 2);
+        pre0 = __ldg(src + t);
+        if (t == 0) pre1 = __ldg(src + 128);
+    };
+    if (raw_mode && site < P.n_sites) prefetch(site);
+
     for (; site < P.n_sites; site += stride) {
-        // ---- input: prefetched pixels -> padded planes (pixel row = (h+2)*45 + (w+2)), channels 5..7 stay zero
+        // ---- input -> padded planes (pixel row = (h+2)*45 + (w+2)), channels 5..7 stay zero
+        float sc_f = 1.f; double sc_d = 1.0;
+        if (P.in_mode == 1) sc_f = __ldg(P.scale_f + site);
+        if (P.in_mode == 2) sc_d = __ldg(P.scale_d + site);
+        if (raw_mode) {
+            *reinterpret_cast<uint4*>(s_raw + t * 16) = pre0;
+            if (t == 0) *reinterpret_cast<uint4*>(s_raw + 2048) = pre1;
+            wg_barrier(wg);
+        }
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             const int px = t + 128 * k;
             if (px < 205) {
                 const int h = px / 41, w = px - h * 41;
+                float v[5];
+                if (!raw_mode) {
+                    ta_load_pixel_f32(P, site, px, v);
+                } else {
+                    const int16_t* rp = reinterpret_cast<const int16_t*>(s_raw) + px * 5;
+#pragma unroll
+                    for (int c = 0; c < 5; c++) {
+                        const int16_t raw = rp[c];
+                        float x = (float)raw;
+                        if (h > 0 && c < 4) x = P.in_mode == 1 ? __fmul_rn(x, sc_f) : (float)((double)raw * sc_d);
+                        v[c] = x;
+                    }
+                }
                 uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-                split2(fmaxf(pv[k][0], -65000.f), fmaxf(pv[k][1], -65000.f), hi.x, lo.x);
-                split2(fmaxf(pv[k][2], -65000.f), fmaxf(pv[k][3], -65000.f), hi.y, lo.y);
-                split2(fmaxf(pv[k][4], -65000.f), 0.f, hi.z, lo.z);
+                split2(fmaxf(v[0], -65000.f), fmaxf(v[1], -65000.f), hi.x, lo.x);
+                split2(fmaxf(v[2], -65000.f), fmaxf(v[3], -65000.f), hi.y, lo.y);
+                split2(fmaxf(v[4], -65000.f), 0.f, hi.z, lo.z);
                 const int row = (h + 2) * tcg::WP + w + 2;
                 *reinterpret_cast<uint4*>(s_in + row * 16) = hi;
                 *reinterpret_cast<uint4*>(s_in + tcg::IN_PLANE + row * 16) = lo;
@@ -307,25 +358,22 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
         fence_async_smem();
         tc_fence_before();
         wg_barrier(wg);
-        // ---- conv1: two 128-row tiles, three branches -> 48 accumulator columns per tile
-        if (issuer_warp) {
+        // ---- conv1: two 128-row tiles x three branches, issued by the four warps in parallel
+        //      (independent accumulators: warp 0/1 = 5x5 branch of tile 0/1, warp 2/3 = 1x5 and 5x1 branches of tile 0/1)
+        if (elect_one()) {
             tc_fence_after();
-            const bool leader = elect_one();
-            const uint32_t blo = w16 | ((16u * 16u >> 4) << 16);
-            issue_cprog<tcg::N_OPS1>(c_prog1, in16, blo, tmem, idesc1, leader, false);
-            issue_cprog<tcg::N_OPS1>(c_prog1, in16 + tcg::TILE1_START, blo, tmem + 48, idesc1, leader, false);
-            if (leader) umma_commit(&s_bar[wg]);
-            __syncwarp();
-        }
-        // ---- prefetch the next site's pixels while the tensor core works
-        {
-            const int64_t nxt = site + stride;
-            if (nxt < P.n_sites) {
-                ta_load_pixel(P, nxt, t, pv[0]);
-                if (px1 < 205) ta_load_pixel(P, nxt, px1, pv[1]);
+            const uint32_t a16 = in16 + ((wq & 1) ? tcg::TILE1_START : 0), d = tmem + ((wq & 1) ? 48 : 0);
+            if (wq < 2) {
+                issue_conv1_branch<2>(a16, w16, d, idesc1);
+            } else {
+                issue_conv1_branch<0>(a16, w16, d, idesc1);
+                issue_conv1_branch<1>(a16, w16, d, idesc1);
             }
+            umma_commit(bar1);
         }
-        ok = mbar_wait(&s_bar[wg], phase) && ok; phase ^= 1;
+        __syncwarp();
+        if (raw_mode && site + stride < P.n_sites) prefetch(site + stride);     // in flight while the tensor core and the epilogues run
+        ok = mbar_wait(bar1, phase) && ok;
         tc_fence_after();
         // ---- epilogue 1: bias + SELU + split -> c1 planes [part][parity][k-group][h*21 + w/2]
 #pragma unroll 1
@@ -352,25 +400,30 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
         fence_async_smem();
         tc_fence_before();
         wg_barrier(wg);
-        // ---- conv2: one tile (rows h2*21 + w2), 6 taps x 3 K-chunks x 3 split terms
-        if (issuer_warp) {
+        // ---- conv2: one tile (rows h2*21 + w2); taps 0-2 and 3-5 accumulate into two partial accumulators
+        if (wq < 2 && elect_one()) {
             tc_fence_after();
-            const bool leader = elect_one();
-            issue_cprog<tcg::N_OPS2>(c_prog2, c116, (w16 + (tcg::W1_BYTES >> 4)) | ((32u * 16u >> 4) << 16), tmem + 96, idesc2, leader, false);
-            if (leader) umma_commit(&s_bar[wg]);
-            __syncwarp();
+            if (wq == 0) issue_conv2_taps<0, 3>(c116, w16, tmem + 96, idesc2);
+            else issue_conv2_taps<3, 6>(c116, w16, tmem + 128, idesc2);
+            umma_commit(bar2);
         }
-        ok = mbar_wait(&s_bar[wg], phase) && ok; phase ^= 1;
+        __syncwarp();
+        ok = mbar_wait(bar2, phase) && ok;
+        phase ^= 1;
         tc_fence_after();
-        // ---- epilogue 2: bias + SELU + split -> HBM c2 [site][part][parity][k-group][h2*10 + w2/2][8]
+        // ---- epilogue 2: partial sums + bias + SELU + split -> HBM c2 [site][part][parity][k-group][h2*10 + w2/2][8]
         {
             const int m = t, h2 = m / tcg::C1_PITCH, w2 = m - h2 * tcg::C1_PITCH;
             const bool valid = m < 84 && w2 < 20;
-            float acc[32];
+            float acc[32], acc2[32];
             tmem_ld16_nowait(tmem_lane + 96, acc);
             tmem_ld16_nowait(tmem_lane + 112, acc + 16);
+            tmem_ld16_nowait(tmem_lane + 128, acc2);
+            tmem_ld16_nowait(tmem_lane + 144, acc2 + 16);
             tmem_ld_wait();
             if (valid) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) acc[i] += acc2[i];
                 uint8_t* dst = P.c2_out + site * tcg::C2_SITE_BYTES + ((w2 & 1) * 4) * tcg::C2_CHUNK + (h2 * tcg::C2_PITCH + (w2 >> 1)) * 16;
 #pragma unroll
                 for (int kg = 0; kg < 4; kg++) {
@@ -409,26 +462,25 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
     float* s_bias = reinterpret_cast<float*>(smem + tcg::W3_BYTES + TB_WGS * tcg::C2_SMEM);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 64);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
-    const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = tid >> 5;
+    const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = tid >> 5, wq = warp & 3;
     uint8_t* s_c2 = smem + tcg::W3_BYTES + wg * tcg::C2_SMEM;
 
     for (int i = tid; i < tcg::W3_BYTES / 16; i += TB_THREADS) reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(P.wimg) + i);
     if (tid < 64) s_bias[tid] = P.bias[tid];
     for (int i = tid; i < TB_WGS * tcg::C2_SMEM / 16; i += TB_THREADS) reinterpret_cast<uint4*>(smem + tcg::W3_BYTES)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
-        for (int i = 0; i < TB_WGS; i++) mbar_init(&s_bar[i], 1);
+        for (int i = 0; i < TB_WGS; i++) mbar_init(&s_bar[i], 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(s_tmem, 256);
+    if (warp == 0) tmem_alloc(s_tmem, 512);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *s_tmem + (uint32_t)wg * 64u;
-    const uint32_t tmem_lane = tmem + ((uint32_t)(warp & 3) << 21);
+    const uint32_t tmem = *s_tmem + (uint32_t)wg * 128u;          // two partial accumulators of 64 columns
+    const uint32_t tmem_lane = tmem + ((uint32_t)wq << 21);
     const uint32_t c216 = smem_u32(s_c2) >> 4, w16 = smem_u32(s_w) >> 4;
     const uint32_t idesc = make_idesc_f16(128, 64);
-    const bool issuer_warp = (warp & 3) == 0;
     uint32_t phase = 0;
     bool ok = true;
     const int64_t n_groups = (P.n_sites + 2) / 3;
@@ -446,13 +498,13 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
         fence_async_smem();
         tc_fence_before();
         wg_barrier(wg);
-        if (issuer_warp) {
+        if (wq < 2 && elect_one()) {
             tc_fence_after();
-            const bool leader = elect_one();
-            issue_cprog<tcg::N_OPS3>(c_prog3, c216, w16 | ((64u * 16u >> 4) << 16), tmem, idesc, leader, false);
-            if (leader) umma_commit(&s_bar[wg]);
-            __syncwarp();
+            if (wq == 0) issue_conv3_taps<0, 3>(c216, w16, tmem, idesc);
+            else issue_conv3_taps<3, 6>(c216, w16, tmem + 64, idesc);
+            umma_commit(&s_bar[wg]);
         }
+        __syncwarp();
         ok = mbar_wait(&s_bar[wg], phase) && ok; phase ^= 1;
         tc_fence_after();
         // ---- epilogue: row m = s*40 + h3*10 + w3 -> HBM c3 [tile][part][pos*8 + g][site % 128][8]
@@ -464,11 +516,15 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
             uint8_t* dst = P.c3_out + (site >> 7) * (int64_t)tcg::C3_TILE_BYTES + (int64_t)(pos * 8) * 2048 + (site & 127) * 16;
 #pragma unroll 1
             for (int half = 0; half < 2; half++) {
-                float acc[32];
+                float acc[32], acc2[32];
                 tmem_ld16_nowait(tmem_lane + half * 32, acc);
                 tmem_ld16_nowait(tmem_lane + half * 32 + 16, acc + 16);
+                tmem_ld16_nowait(tmem_lane + 64 + half * 32, acc2);
+                tmem_ld16_nowait(tmem_lane + 64 + half * 32 + 16, acc2 + 16);
                 tmem_ld_wait();
                 if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) acc[i] += acc2[i];
 #pragma unroll
                     for (int g = 0; g < 4; g++) {
                         uint4 hi, lo;
@@ -486,7 +542,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
     if (!ok && t == 0) atomicExch(P.err, 1);
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(*s_tmem, 256);
+    if (warp == 0) tmem_dealloc(*s_tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -578,14 +634,20 @@ __global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (warp == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
-            const bool leader = elect_one();
             const uint32_t sb16 = smem_u32(smem + (pos & 1) * TC_STAGE) >> 4;
-            issue_cprog<tcg::N_OPSF>(c_progF, sb16, (sb16 + (TC_STAGE_A >> 4)) | ((48u * 16u >> 4) << 16), tmem, idesc, leader, pos > 0);
-            if (leader) umma_commit(&s_bar[pos & 1]);
-            __syncwarp();
+            const uint32_t bhi = (sb16 + TC_STAGE_A / 16) | (48u << 16);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t a_hi = sb16 + (2 * c) * 128 + (128u << 16), a_lo = a_hi + 8 * 128;
+                umma_f16(tmem, sdesc16(a_hi), sdesc16(bhi + c * 96), idesc, (pos > 0 || c > 0) ? 1u : 0u);
+                umma_f16(tmem, sdesc16(a_lo), sdesc16(bhi + c * 96), idesc, 1u);
+                umma_f16(tmem, sdesc16(a_hi), sdesc16(bhi + (4 + c) * 96), idesc, 1u);
+            }
+            umma_commit(&s_bar[pos & 1]);
         }
+        __syncwarp();
         if (pos + 1 < 27) {
             if (pos >= 1) ok = mbar_wait(&s_bar[(pos + 1) & 1], ((pos - 1) >> 1) & 1) && ok;   // MMAs of pos-1 released that stage
             load_stage(pos + 1);
@@ -821,18 +883,6 @@ inline int tc_model_prepare(cudaStream_t stream, TcModel& T, int kind, const flo
         return NC_ECUDA;
     }
     if (img_a.size() != (size_t)TA_SMEM_W) { if (err) *err = "TA weight image size mismatch"; return NC_EINVAL; }
-    {   // programs -> constant memory (geometry only: identical for every SNP model)
-        std::vector<COp> cp(ops.size());
-        for (size_t i = 0; i < ops.size(); i++) cp[i] = {(ops[i].a_off >> 4) | ((ops[i].a_lbo >> 4) << 16), ops[i].b_off >> 4, ops[i].misc};
-        if ((e = cudaMemcpyToSymbolAsync(c_prog1, cp.data(), N_OPS1 * sizeof(COp), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
-            (e = cudaMemcpyToSymbolAsync(c_prog2, cp.data() + N_OPS1, N_OPS2 * sizeof(COp), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
-            (e = cudaMemcpyToSymbolAsync(c_prog3, cp.data() + N_OPS1 + N_OPS2, N_OPS3 * sizeof(COp), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
-            (e = cudaMemcpyToSymbolAsync(c_progF, cp.data() + N_OPS1 + N_OPS2 + N_OPS3, N_OPSF * sizeof(COp), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
-            (e = cudaStreamSynchronize(stream)) != cudaSuccess) {
-            if (err) *err = std::string("tc_model_prepare (programs): ") + cudaGetErrorString(e);
-            return NC_ECUDA;
-        }
-    }
     T.ready = true;
     return NC_OK;
 }
