@@ -333,3 +333,10 @@ class TabixFile:
         if reference not in self._b:
             raise ValueError("could not create iterator for region '%s'" % reference)
         return [_BedRow((reference, str(s), str(e))) for s, e in self._b[reference]]
+
+
+class VariantFile:
+    """Imported (never used) by generate_indel_pileups.py:4."""
+
+    def __init__(self, *a, **kw):
+        raise NotImplementedError("shim pysam: VariantFile is not used on the hot path")
