@@ -183,6 +183,51 @@ int nc_load_indel_weights(nc_ctx* ctx, const float* blob, size_t n_floats, int h
  * [n][5][128][2] (haploid).  out: float32 [n][4] softmax / [n][1] sigmoid. */
 int nc_indel_model_forward(nc_ctx* ctx, const float* x, int64_t n, int haploid, int impl, float* out);
 
+/* ---- indel feature path (diploid): generate_indel_pileups.get_indel_testing_candidates (generate_indel_pileups.py:129-370,
+ * called at indelCaller.py:69).  MUSCLE (:30) and parasail (:79) are external; the alignment used instead is this
+ * library's own star alignment / affine NW, specified in oracle/star_msa.py and DESIGN.md. ---- */
+#define NC_INDEL_CNS_MAX 544
+
+typedef struct NcIndelParams {
+    double  ins_t, del_t;            /* dct['ins_t'], dct['del_t']                                  */
+    int32_t mincov, maxcov;
+    int32_t win_size, small_win_size;
+    int32_t window_after;            /* 160, or 260 for dct['seq'] == 'pacbio' (:136-139)           */
+    int32_t supplementary;
+} NcIndelParams;
+
+typedef struct NcIndelVariant { int32_t key, type, chunk; } NcIndelVariant;   /* variants[key] = type (:268,:274) */
+
+typedef struct NcIndelSiteMeta {
+    int32_t pos, chunk, type, phase, ref_len;
+    int32_t n[3];                    /* reads used per group: HP1, HP2, all                         */
+    int32_t cns_len[3];
+    int32_t ok[3];                   /* msa() flag per group (:48)                                  */
+} NcIndelSiteMeta;
+
+/* HP / PS tags of the staged reads (hp: 0 untagged, 1, 2), read by generate_indel_pileups.py:180-188. */
+int nc_stage_tags(nc_ctx* ctx, const int8_t* hp, const int32_t* ps);
+
+/* Pass 1 (:213-275) over a batch of chunks: *n_variants = number of (key, type, chunk) triples, unordered. */
+int nc_indel_scan(nc_ctx* ctx, const NcIndelParams* params, const NcChunk* chunks, int32_t n_chunks, const int32_t* bed,
+                  int32_t n_bed, int64_t* n_variants);
+int nc_indel_fetch_variants(nc_ctx* ctx, NcIndelVariant* out);
+
+/* Pass 2 + msa (:306-348, :12-73) for key positions given in (chunk, key) order (the host applies the dict semantics of
+ * `variants`).  Results stay on the device until fetched:
+ *   meta     NcIndelSiteMeta [n_sites]
+ *   tensors  float32 [n_sites][3][5][128][2]  (group 0 HP1, 1 HP2, 2 all; zero when !ok)
+ *   cns      uint8 [n_sites][3][NC_INDEL_CNS_MAX] consensus codes A0 G1 T2 C3 */
+int nc_indel_build(nc_ctx* ctx, const NcIndelParams* params, const NcChunk* chunks, int32_t n_chunks,
+                   const NcIndelVariant* sites, int64_t n_sites);
+int nc_indel_fetch(nc_ctx* ctx, NcIndelSiteMeta* meta, float* tensors, uint8_t* cns);
+
+/* Host-side global affine alignment with traceback, replaces parasail.nw_trace(query, ref, open, extend, matrix)
+ * (generate_indel_pileups.py:79): codes A0 G1 T2 C3; cigar_out receives (len << 4 | op) words, op '='7 'X'8 'I'1 'D'2.
+ * Returns the number of words, or a negative NC_E* code (NC_EOVERFLOW if cap is too small). */
+int nc_nw_trace(const uint8_t* query, int32_t n, const uint8_t* ref, int32_t m, int32_t gap_open, int32_t gap_extend,
+                int32_t match, int32_t mismatch, uint32_t* cigar_out, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@
 #include "nc_pileup.cuh"
 #include "nc_cnn.cuh"
 #include "nc_cnn_tc.cuh"
+#include "nc_indel.cuh"
 
 using namespace nc;
 
@@ -56,6 +57,12 @@ struct nc_ctx {
     int32_t n_chunks = 0;
     bool have_probs = false;
     int scan_haploid = 0;
+    // indel path
+    bool tags_staged = false, indel_scanned = false, indel_built = false;
+    DevBuf d_hp, d_ps, d_idepth, d_em, d_grank, d_empos, d_ichunks, d_nem1, d_rankoff, d_diff, d_uscan, d_hit, d_variants, d_icount;
+    DevBuf d_isites, d_site_m, d_site_cnt, d_site_off, d_eread, d_eqpn, d_eslice, d_eacode, d_einslen, d_einsfirst, d_en, d_itensors, d_icns, d_imeta;
+    int64_t n_variants = 0, n_isites = 0, indel_R = 0;
+    int32_t indel_lo_al = 0;
     // CNN
     Model snp[2], indel[2];
     DevBuf ws_c1, ws_c2, ws_c3, ws_f1, ws_sf, ws_sd, ws_x, ws_ref, ws_out;
@@ -349,6 +356,9 @@ void nc_destroy(nc_ctx* c) {
                       &c->d_nfirst, &c->d_nlen, &c->d_nbytes, &c->d_noff, &c->d_nrows, &c->d_chunks, &c->d_chunk_lo,
                       &c->d_chunk_cnt, &c->d_chunk_off, &c->d_keep, &c->d_keep32, &c->d_outidx, &c->d_mat, &c->d_meta,
                       &c->d_depth_sum, &c->d_depth_cnt, &c->d_chunk_depth, &c->d_chunk_count, &c->d_probs, &c->d_scan_partial,
+                      &c->d_hp, &c->d_ps, &c->d_idepth, &c->d_em, &c->d_grank, &c->d_empos, &c->d_ichunks, &c->d_nem1, &c->d_rankoff, &c->d_diff,
+                      &c->d_uscan, &c->d_hit, &c->d_variants, &c->d_icount, &c->d_isites, &c->d_site_m, &c->d_site_cnt, &c->d_site_off, &c->d_eread,
+                      &c->d_eqpn, &c->d_eslice, &c->d_eacode, &c->d_einslen, &c->d_einsfirst, &c->d_en, &c->d_itensors, &c->d_icns, &c->d_imeta,
                       &c->ws_c1, &c->ws_c2, &c->ws_c3, &c->ws_f1, &c->ws_sf, &c->ws_sd, &c->ws_x, &c->ws_ref, &c->ws_out};
     for (DevBuf* b : bufs) b->release();
     for (Model* m : {&c->snp[0], &c->snp[1], &c->indel[0], &c->indel[1]}) {
@@ -415,7 +425,7 @@ int nc_stage_reads(nc_ctx* c, int64_t n_reads, const int32_t* pos, const uint16_
     if (!c) return NC_EINVAL;
     NC_CUDA(cudaSetDevice(c->device));
     c->staged = c->decoded = c->scanned = false;
-    c->have_probs = false;
+    c->have_probs = false; c->tags_staged = c->indel_scanned = c->indel_built = false;
     if (n_reads < 0 || ref_len < 0 || ref_start < 0 || (n_reads > 0 && (!pos || !flag || !cigar_off || !seq_off || !l_seq)) || (ref_len > 0 && !ref))
         return fail(c, NC_EINVAL, "nc_stage_reads: null or negative argument");
     if (ref_start + ref_len > 0x7fffff00ll) return fail(c, NC_EOVERFLOW, "contig coordinates must fit 31 bits");
@@ -752,6 +762,244 @@ int nc_snp_device_buffers(nc_ctx* c, void** mat_dev, void** meta_dev, void** pro
     if (probs_dev) *probs_dev = (c->have_probs && c->n_sites) ? c->d_probs.p : nullptr;
     if (n_sites) *n_sites = c->n_sites;
     return NC_OK;
+}
+
+// ---- indel feature path ------------------------------------------------------------------------------------
+int nc_stage_tags(nc_ctx* c, const int8_t* hp, const int32_t* ps) {
+    if (!c) return NC_EINVAL;
+    if (!c->staged) return fail(c, NC_ESTATE, "nc_stage_tags before nc_stage_reads");
+    if (c->n_reads > 0 && (!hp || !ps)) return fail(c, NC_EINVAL, "nc_stage_tags: null argument");
+    NC_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = upload(c, c->d_hp, hp, (size_t)c->n_reads))) return rc;
+    if ((rc = upload(c, c->d_ps, ps, (size_t)c->n_reads * 4))) return rc;
+    c->tags_staged = true; c->indel_scanned = c->indel_built = false;
+    return NC_OK;
+}
+
+int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int32_t n_chunks, const int32_t* bed, int32_t n_bed,
+                  int64_t* n_variants) {
+    if (!c || !P || !n_variants || n_chunks < 0 || (n_chunks > 0 && !chunks) || n_bed < 0 || (n_bed > 0 && !bed))
+        return fail(c, NC_EINVAL, "nc_indel_scan: bad argument");
+    *n_variants = 0;
+    if (!c->staged || !c->tags_staged) return fail(c, NC_ESTATE, "nc_indel_scan needs nc_stage_reads and nc_stage_tags");
+    if (P->win_size < 1 || P->small_win_size < 1 || P->win_size > 190) return fail(c, NC_EINVAL, "win_size must be in 1..190");
+    NC_CUDA(cudaSetDevice(c->device));
+    int rc = nc_decode_reads(c);
+    if (rc) return rc;
+    c->indel_scanned = c->indel_built = false; c->n_variants = 0;
+    for (int i = 0; i + 1 < n_chunks; i++)
+        if (chunks[i + 1].start < chunks[i].start) return fail(c, NC_EINVAL, "indel chunks must be sorted by start");
+    int64_t lo = INT64_MAX, hi = INT64_MIN;
+    for (int i = 0; i < n_chunks; i++) {
+        if (chunks[i].end < chunks[i].start) continue;
+        lo = std::min<int64_t>(lo, std::max<int64_t>(0, (int64_t)chunks[i].start - 1));
+        hi = std::max<int64_t>(hi, (int64_t)chunks[i].end);
+    }
+    lo = std::max(lo, c->ref_start); hi = std::min(hi, c->ref_start + c->ref_len);
+    if (n_chunks == 0 || hi <= lo || c->n_reads == 0) { c->indel_scanned = true; return NC_OK; }
+
+    std::vector<std::pair<int32_t, int32_t>> iv;
+    for (int i = 0; i < n_bed; i++) if (bed[2 * i + 1] > bed[2 * i]) iv.emplace_back(bed[2 * i], bed[2 * i + 1]);
+    std::sort(iv.begin(), iv.end());
+    std::vector<int32_t> merged;
+    for (auto& x : iv) {
+        if (!merged.empty() && x.first <= merged[merged.size() - 1]) merged[merged.size() - 1] = std::max(merged[merged.size() - 1], x.second);
+        else { merged.push_back(x.first); merged.push_back(x.second); }
+    }
+    const int32_t n_merged = (int32_t)(merged.size() / 2);
+    if ((rc = upload(c, c->d_bed, merged.data(), merged.size() * 4))) return rc;
+    if ((rc = upload(c, c->d_chunks, chunks, (size_t)n_chunks * sizeof(NcChunk)))) return rc;
+    NC_CUDA(cudaStreamSynchronize(c->stream));
+
+    const uint32_t flag_filter = P->supplementary ? 0x704u : 0xF04u;
+    const int32_t lo_al = (int32_t)lo & ~7;
+    const int64_t n_tiles = div_up(hi - lo_al, kTilePos), n_al = n_tiles * kTilePos;
+    c->indel_lo_al = lo_al;
+    NC_CUDA(c->d_idepth.reserve((size_t)3 * n_al * 2));
+    NC_CUDA(c->d_em.reserve((size_t)n_al * 4));
+    NC_CUDA(c->d_grank.reserve((size_t)(n_al + 1) * 8));
+    DepthArgs da = {};
+    da.n_reads = c->n_reads; da.pos = c->d_pos.as<int32_t>(); da.end = c->d_end.as<int32_t>(); da.flag = c->d_flag.as<uint16_t>();
+    da.hp = c->d_hp.as<int8_t>(); da.pmaxend = c->d_pmaxend.as<int32_t>(); da.rowoff = c->d_rowoff.as<int64_t>();
+    da.nwords = c->d_nwords.as<int32_t>(); da.rows = c->d_rows.as<uint32_t>(); da.lo_al = lo_al; da.lo = (int32_t)lo; da.hi = (int32_t)hi;
+    da.flag_filter = flag_filter; da.depth = c->d_idepth.as<uint16_t>(); da.n_al = n_al;
+    indel_depth_kernel<<<(unsigned)n_tiles, kTileThreads, 0, c->stream>>>(da); NC_LAUNCH_CHECK();
+    indel_emitted_kernel<<<(unsigned)div_up(n_al, 256), 256, 0, c->stream>>>(c->d_idepth.as<uint16_t>() + 2 * n_al, n_al, lo_al, c->d_bed.as<int32_t>(),
+                                                                           n_merged, c->d_em.as<int32_t>());
+    NC_LAUNCH_CHECK();
+    if ((rc = device_scan(c, c->d_em.as<int32_t>(), n_al, c->d_grank.as<int64_t>()))) return rc;
+    int64_t n_em_total = 0;
+    if ((rc = read_i64(c, c->d_grank.as<int64_t>() + n_al, &n_em_total))) return rc;
+    NC_CUDA(c->d_empos.reserve((size_t)std::max<int64_t>(n_em_total, 1) * 4));
+    indel_empos_kernel<<<(unsigned)div_up(n_al, 256), 256, 0, c->stream>>>(c->d_em.as<int32_t>(), c->d_grank.as<int64_t>(), n_al, lo_al, c->d_empos.as<int32_t>());
+    NC_LAUNCH_CHECK();
+    NC_CUDA(c->d_ichunks.reserve((size_t)n_chunks * sizeof(IndelChunk)));
+    NC_CUDA(c->d_nem1.reserve((size_t)n_chunks * 4));
+    NC_CUDA(c->d_rankoff.reserve((size_t)(n_chunks + 1) * 8));
+    indel_chunk_kernel<<<(unsigned)div_up(n_chunks, 128), 128, 0, c->stream>>>(c->d_chunks.as<NcChunk>(), n_chunks, lo_al, (int32_t)lo, (int32_t)hi,
+                                                                               c->d_grank.as<int64_t>(), c->d_ichunks.as<IndelChunk>(), c->d_nem1.as<int32_t>());
+    NC_LAUNCH_CHECK();
+    if ((rc = device_scan(c, c->d_nem1.as<int32_t>(), n_chunks, c->d_rankoff.as<int64_t>()))) return rc;
+    int64_t R = 0;
+    if ((rc = read_i64(c, c->d_rankoff.as<int64_t>() + n_chunks, &R))) return rc;
+    c->indel_R = R;
+    indel_chunk_off_kernel<<<(unsigned)div_up(n_chunks, 128), 128, 0, c->stream>>>(c->d_ichunks.as<IndelChunk>(), n_chunks, c->d_rankoff.as<int64_t>());
+    NC_LAUNCH_CHECK();
+    NC_CUDA(c->d_diff.reserve((size_t)8 * R * 4));
+    NC_CUDA(cudaMemsetAsync(c->d_diff.p, 0, (size_t)8 * R * 4, c->stream));
+    EventArgs ea = {};
+    ea.n_reads = c->n_reads; ea.pos = da.pos; ea.end = da.end; ea.flag = da.flag; ea.hp = da.hp; ea.cigar_off = c->d_cigar_off.as<int64_t>();
+    ea.cigar = c->d_cigar.as<uint32_t>(); ea.chunks = c->d_ichunks.as<IndelChunk>(); ea.n_chunks = n_chunks; ea.em = c->d_em.as<int32_t>();
+    ea.grank = c->d_grank.as<int64_t>(); ea.lo_al = lo_al; ea.flag_filter = flag_filter; ea.win = P->win_size; ea.small_win = P->small_win_size;
+    ea.diff = c->d_diff.as<int32_t>(); ea.R = R;
+    indel_events_kernel<<<(unsigned)div_up(c->n_reads, 128), 128, 0, c->stream>>>(ea); NC_LAUNCH_CHECK();
+    NC_CUDA(c->d_uscan.reserve((size_t)8 * (R + 1) * 8));
+    for (int k = 0; k < 8; k++)
+        if ((rc = device_scan(c, c->d_diff.as<int32_t>() + (int64_t)k * R, R, c->d_uscan.as<int64_t>() + (int64_t)k * (R + 1)))) return rc;
+    NC_CUDA(c->d_hit.reserve((size_t)R));
+    NC_CUDA(c->d_icount.reserve(64));
+    NC_CUDA(cudaMemsetAsync(c->d_icount.p, 0, 64, c->stream));
+    DecideArgs dd = {};
+    dd.chunks = c->d_ichunks.as<IndelChunk>(); dd.n_chunks = n_chunks; dd.R = R; dd.uscan = c->d_uscan.as<int64_t>(); dd.em_pos = c->d_empos.as<int32_t>();
+    dd.depth = c->d_idepth.as<uint16_t>(); dd.n_al = n_al; dd.lo_al = lo_al; dd.mincov = P->mincov; dd.ins_t = P->ins_t; dd.del_t = P->del_t;
+    dd.hit = c->d_hit.as<uint8_t>(); dd.n_hits = c->d_icount.as<unsigned long long>();
+    indel_decide_kernel<<<(unsigned)div_up(R, 256), 256, 0, c->stream>>>(dd); NC_LAUNCH_CHECK();
+    int64_t n_hits = 0;
+    if ((rc = read_i64(c, c->d_icount.as<int64_t>(), &n_hits))) return rc;
+    NC_CUDA(c->d_variants.reserve((size_t)std::max<int64_t>(n_hits, 1) * sizeof(NcIndelVariant)));
+    indel_greedy_kernel<<<(unsigned)div_up((int64_t)n_chunks * 32, 128), 128, 0, c->stream>>>(c->d_ichunks.as<IndelChunk>(), n_chunks, c->d_hit.as<uint8_t>(),
+                                                                                            c->d_empos.as<int32_t>(), P->win_size, c->d_variants.as<NcIndelVariant>(),
+                                                                                            c->d_icount.as<unsigned long long>() + 1);
+    NC_LAUNCH_CHECK();
+    if ((rc = read_i64(c, c->d_icount.as<int64_t>() + 1, &c->n_variants))) return rc;
+    c->indel_scanned = true;
+    *n_variants = c->n_variants;
+    return NC_OK;
+}
+
+int nc_indel_fetch_variants(nc_ctx* c, NcIndelVariant* out) {
+    if (!c) return NC_EINVAL;
+    if (!c->indel_scanned) return fail(c, NC_ESTATE, "nc_indel_fetch_variants before nc_indel_scan");
+    NC_CUDA(cudaSetDevice(c->device));
+    if (c->n_variants > 0) {
+        if (!out) return fail(c, NC_EINVAL, "nc_indel_fetch_variants: null output");
+        NC_CUDA(cudaMemcpyAsync(out, c->d_variants.p, (size_t)c->n_variants * sizeof(NcIndelVariant), cudaMemcpyDeviceToHost, c->stream));
+    }
+    NC_CUDA(cudaStreamSynchronize(c->stream));
+    return NC_OK;
+}
+
+int nc_indel_build(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int32_t n_chunks, const NcIndelVariant* sites, int64_t n_sites) {
+    if (!c || !P || n_sites < 0 || (n_sites > 0 && (!sites || !chunks)) || n_chunks < 0) return fail(c, NC_EINVAL, "nc_indel_build: bad argument");
+    if (!c->staged || !c->tags_staged) return fail(c, NC_ESTATE, "nc_indel_build needs nc_stage_reads and nc_stage_tags");
+    if (P->window_after < 1 || P->window_after > 260) return fail(c, NC_EINVAL, "window_after must be <= 260");
+    NC_CUDA(cudaSetDevice(c->device));
+    int rc = nc_decode_reads(c);
+    if (rc) return rc;
+    c->indel_built = false; c->n_isites = n_sites;
+    if (n_sites == 0) { c->indel_built = true; return NC_OK; }
+    for (int64_t i = 0; i < n_sites; i++)
+        if (sites[i].chunk < 0 || sites[i].chunk >= n_chunks) return fail(c, NC_EINVAL, "site %lld names chunk %d of %d", (long long)i, sites[i].chunk, n_chunks);
+    if ((rc = upload(c, c->d_chunks, chunks, (size_t)n_chunks * sizeof(NcChunk)))) return rc;
+    if ((rc = upload(c, c->d_isites, sites, (size_t)n_sites * sizeof(NcIndelVariant)))) return rc;
+    NC_CUDA(c->d_site_m.reserve((size_t)n_sites * 4));
+    NC_CUDA(c->d_site_cnt.reserve((size_t)n_sites * 4));
+    NC_CUDA(c->d_site_off.reserve((size_t)(n_sites + 1) * 8));
+    SiteArgs sa = {};
+    sa.n_reads = c->n_reads; sa.pos = c->d_pos.as<int32_t>(); sa.end = c->d_end.as<int32_t>(); sa.flag = c->d_flag.as<uint16_t>();
+    sa.hp = c->d_hp.as<int8_t>(); sa.ps = c->d_ps.as<int32_t>(); sa.pmaxend = c->d_pmaxend.as<int32_t>();
+    sa.cigar_off = c->d_cigar_off.as<int64_t>(); sa.cigar = c->d_cigar.as<uint32_t>(); sa.opstart = c->d_opstart.as<int2>();
+    sa.seq_off = c->d_seq_off.as<int64_t>(); sa.l_seq = c->d_lseq.as<int32_t>(); sa.seq4 = c->d_seq4.as<uint8_t>();
+    sa.ref = c->d_ref.as<uint8_t>(); sa.ref_start = c->ref_start; sa.ref_len = c->ref_len; sa.contig_len = (int32_t)(c->ref_start + c->ref_len);
+    sa.sites = c->d_isites.as<NcIndelVariant>(); sa.n_sites = n_sites; sa.chunks = c->d_chunks.as<NcChunk>();
+    sa.flag_filter = P->supplementary ? 0x704u : 0xF04u; sa.wa = P->window_after; sa.win = P->win_size; sa.mincov = P->mincov; sa.maxcov = P->maxcov;
+    sa.site_m = c->d_site_m.as<int32_t>(); sa.site_cnt = c->d_site_cnt.as<int32_t>(); sa.site_off = c->d_site_off.as<int64_t>();
+    sa.nmax = 264; sa.mmax = 264; sa.cmax = NC_INDEL_CNS_MAX;
+    const unsigned sg = (unsigned)div_up(n_sites * 32, 128);
+    indel_site_reads_kernel<false><<<sg, 128, 0, c->stream>>>(sa); NC_LAUNCH_CHECK();
+    if ((rc = device_scan(c, sa.site_cnt, n_sites, c->d_site_off.as<int64_t>()))) return rc;
+    int64_t n_entries = 0;
+    if ((rc = read_i64(c, c->d_site_off.as<int64_t>() + n_sites, &n_entries))) return rc;
+    const size_t ne = (size_t)std::max<int64_t>(n_entries, 1);
+    NC_CUDA(c->d_eread.reserve(ne * 4)); NC_CUDA(c->d_eqpn.reserve(ne * 4)); NC_CUDA(c->d_en.reserve(ne * 4));
+    NC_CUDA(c->d_eslice.reserve(ne * sa.nmax)); NC_CUDA(c->d_eacode.reserve(ne * sa.mmax));
+    NC_CUDA(c->d_einslen.reserve(ne * (sa.mmax + 1) * 2)); NC_CUDA(c->d_einsfirst.reserve(ne * (sa.mmax + 1) * 2));
+    NC_CUDA(c->d_itensors.reserve((size_t)n_sites * 3 * 1280 * 4));
+    NC_CUDA(c->d_icns.reserve((size_t)n_sites * 3 * NC_INDEL_CNS_MAX));
+    NC_CUDA(c->d_imeta.reserve((size_t)n_sites * sizeof(NcIndelSiteMeta)));
+    sa.e_read = c->d_eread.as<int32_t>(); sa.e_qpn = c->d_eqpn.as<int32_t>(); sa.e_n = c->d_en.as<int32_t>();
+    sa.e_slice = c->d_eslice.as<uint8_t>(); sa.e_acode = c->d_eacode.as<uint8_t>(); sa.e_inslen = c->d_einslen.as<uint16_t>();
+    sa.e_insfirst = c->d_einsfirst.as<uint16_t>(); sa.tensors = c->d_itensors.as<float>(); sa.cns = c->d_icns.as<uint8_t>();
+    sa.meta = c->d_imeta.as<NcIndelSiteMeta>();
+    indel_site_reads_kernel<true><<<sg, 128, 0, c->stream>>>(sa); NC_LAUNCH_CHECK();
+    if (n_entries > 0) {
+        const int smem = kAlignWarps * kRowsMax * 32 * 4;
+        static bool attr = false;
+        if (!attr) { NC_CUDA(cudaFuncSetAttribute(indel_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+        const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_entries, kAlignWarps), (int64_t)c->sm_count * 12);
+        indel_align_kernel<<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries); NC_LAUNCH_CHECK();
+    }
+    indel_msa_kernel<<<(unsigned)n_sites, 96, 0, c->stream>>>(sa); NC_LAUNCH_CHECK();
+    c->indel_built = true;
+    return NC_OK;
+}
+
+int nc_indel_fetch(nc_ctx* c, NcIndelSiteMeta* meta, float* tensors, uint8_t* cns) {
+    if (!c) return NC_EINVAL;
+    if (!c->indel_built) return fail(c, NC_ESTATE, "nc_indel_fetch before nc_indel_build");
+    NC_CUDA(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->n_isites;
+    if (n) {
+        if (meta) NC_CUDA(cudaMemcpyAsync(meta, c->d_imeta.p, n * sizeof(NcIndelSiteMeta), cudaMemcpyDeviceToHost, c->stream));
+        if (tensors) NC_CUDA(cudaMemcpyAsync(tensors, c->d_itensors.p, n * 3 * 1280 * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (cns) NC_CUDA(cudaMemcpyAsync(cns, c->d_icns.p, n * 3 * NC_INDEL_CNS_MAX, cudaMemcpyDeviceToHost, c->stream));
+    }
+    NC_CUDA(cudaStreamSynchronize(c->stream));
+    return NC_OK;
+}
+
+// Global affine-gap alignment with traceback on the host (the reference calls parasail, a CPU library, here too).
+// Same recurrences and tie rules as oracle/star_msa.nw_trace: H ties DIAG > F ('I') > E ('D'); E/F ties prefer extension.
+int nc_nw_trace(const uint8_t* q, int32_t n, const uint8_t* r, int32_t m, int32_t go, int32_t ge, int32_t match, int32_t mismatch,
+                uint32_t* out, int32_t cap) {
+    if (n < 0 || m < 0 || (n > 0 && !q) || (m > 0 && !r) || !out || cap < 1) return NC_EINVAL;
+    const int64_t NEG = -(1ll << 40);
+    const size_t W = (size_t)m + 1;
+    std::vector<int64_t> H((size_t)(n + 1) * W, NEG), E((size_t)(n + 1) * W, NEG), F((size_t)(n + 1) * W, NEG);
+    H[0] = 0;
+    for (int j = 1; j <= m; j++) { E[j] = -go - (int64_t)ge * (j - 1); H[j] = E[j]; }
+    for (int i = 1; i <= n; i++) { F[i * W] = -go - (int64_t)ge * (i - 1); H[i * W] = F[i * W]; }
+    for (int i = 1; i <= n; i++)
+        for (int j = 1; j <= m; j++) {
+            const int64_t s = q[i - 1] == r[j - 1] ? match : mismatch;
+            const int64_t f = std::max(F[(i - 1) * W + j] - ge, H[(i - 1) * W + j] - go);
+            const int64_t e = std::max(E[i * W + j - 1] - ge, H[i * W + j - 1] - go);
+            F[i * W + j] = f; E[i * W + j] = e;
+            H[i * W + j] = std::max(H[(i - 1) * W + j - 1] + s, std::max(f, e));
+        }
+    std::vector<uint8_t> ops;
+    int i = n, j = m, state = 0;     // 0 H, 1 F, 2 E
+    while (i > 0 || j > 0) {
+        if (state == 0) {
+            if (i > 0 && j > 0 && H[i * W + j] == H[(i - 1) * W + j - 1] + (q[i - 1] == r[j - 1] ? match : mismatch)) {
+                ops.push_back(q[i - 1] == r[j - 1] ? 7 : 8); i--; j--;
+            } else if (i > 0 && H[i * W + j] == F[i * W + j]) state = 1;
+            else state = 2;
+        } else if (state == 1) {
+            ops.push_back(1);
+            if (i > 1 && F[i * W + j] == F[(i - 1) * W + j] - ge) i--; else { i--; state = 0; }
+        } else {
+            ops.push_back(2);
+            if (j > 1 && E[i * W + j] == E[i * W + j - 1] - ge) j--; else { j--; state = 0; }
+        }
+    }
+    int32_t nw = 0;
+    for (size_t k = ops.size(); k-- > 0;) {
+        if (nw > 0 && (out[nw - 1] & 15u) == ops[k]) out[nw - 1] += 16u;
+        else { if (nw >= cap) return NC_EOVERFLOW; out[nw++] = (1u << 4) | ops[k]; }
+    }
+    return nw;
 }
 
 // ---- development probes (not part of the public header) -------------------------------------------------

@@ -1,0 +1,592 @@
+// Indel feature path (diploid): candidate scan, read slices, star alignment, [5][128][2] tensors, consensus.
+//
+// Reference being replaced: nanocaller_src/generate_indel_pileups.py
+//   I1 scan      per-haplotype indel-event windows over the pileup columns, thresholds, `prev` suppression (:213-275)
+//   I2 slices    query_sequence[query_position_or_next : +160|260] per read at a key position (:306-338)
+//   I3 msa       MUSCLE is an external binary (:30); this library aligns every slice to the reference window with its
+//                own, fully specified star alignment (oracle/star_msa.py states it) and builds the column-frequency
+//                tensors and the consensus exactly as `msa` does (:54-71)
+// The impute_indel_phase branch (:278-304) is not built.
+#pragma once
+#include "nc_common.cuh"
+#include "nc_pileup.cuh"
+
+namespace nc {
+
+struct IndelChunk { int32_t lo, hi; int64_t grank_lo; int64_t rank_off; int32_t n_em; int32_t pad; };   // 0-based [lo, hi)
+
+// ------------------------------------------------------------------------------------------------
+// I1.1 per-position read depth of haplotype 1, haplotype 2 and all admitted reads (aligned rows, like K1)
+// ------------------------------------------------------------------------------------------------
+struct DepthArgs {
+    int64_t n_reads;
+    const int32_t* pos; const int32_t* end; const uint16_t* flag; const int8_t* hp; const int32_t* pmaxend;
+    const int64_t* rowoff; const int32_t* nwords; const uint32_t* rows;
+    int32_t lo_al, lo, hi; uint32_t flag_filter;
+    uint16_t* depth;           // [3][n_al]
+    int64_t n_al;
+};
+
+__global__ void __launch_bounds__(kTileThreads) indel_depth_kernel(const DepthArgs a) {
+    __shared__ int32_t s_posw[kTileThreads];
+    __shared__ int32_t s_nw[kTileThreads];
+    __shared__ int64_t s_rowoff[kTileThreads];
+    __shared__ int8_t s_hp[kTileThreads];
+    __shared__ uint16_t s_acc[3][kTilePos];
+    __shared__ int32_t s_cnt;
+    __shared__ int64_t s_ilo, s_ihi;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int32_t P0 = a.lo_al + kTilePos * (int32_t)blockIdx.x;
+    const int32_t P1 = min(P0 + kTilePos, a.hi);
+    for (int i = tid; i < 3 * kTilePos; i += kTileThreads) (&s_acc[0][0])[i] = 0;
+    if (tid == 0) {
+        s_cnt = 0;
+        s_ihi = upper_bound_i32_64(a.pos, a.n_reads, P1 - 1);
+        int64_t lo = 0, hi = a.n_reads;
+        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (__ldg(a.pmaxend + mid) <= P0) lo = mid + 1; else hi = mid; }
+        s_ilo = lo;
+    }
+    __syncthreads();
+    const int64_t ilo = s_ilo, ihi = s_ihi;
+    const int32_t Wbase = (P0 >> 3) + 32 * w, myw = Wbase + lane;
+    uint32_t c[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    int pending = 0;
+    const int sbase = w * 256 + lane * 8;
+    auto flush = [&]() {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                s_acc[k][sbase + 2 * j] += (c[k][0] >> (8 * j)) & 255u;
+                s_acc[k][sbase + 2 * j + 1] += (c[k][1] >> (8 * j)) & 255u;
+            }
+#pragma unroll
+        for (int k = 0; k < 3; k++) c[k][0] = c[k][1] = 0;
+        pending = 0;
+    };
+    for (int64_t base = ilo; base < ihi; base += kTileThreads) {
+        const int64_t i = base + tid;
+        if (i < ihi) {
+            const int32_t p = __ldg(a.pos + i), e = __ldg(a.end + i);
+            const uint32_t f = __ldg(a.flag + i);
+            if ((f & a.flag_filter) == 0 && e > P0 && p < P1 && e > p) {
+                const int slot = atomicAdd(&s_cnt, 1);
+                s_posw[slot] = p >> 3; s_nw[slot] = __ldg(a.nwords + i); s_rowoff[slot] = __ldg(a.rowoff + i); s_hp[slot] = __ldg(a.hp + i);
+            }
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        for (int j = 0; j < cnt; j++) {
+            const int32_t pw = s_posw[j], nw = s_nw[j];
+            if (Wbase + 31 < pw || Wbase >= pw + nw) continue;
+            const int32_t rel = myw - pw;
+            uint32_t word = 0xFFFFFFFFu;
+            if (rel >= 0 && rel < nw) word = __ldg(a.rows + s_rowoff[j] + rel);
+            const uint32_t cov = ((word >> 3) & 0x11111111u) ^ 0x11111111u;
+            const uint32_t e0 = cov & 0x01010101u, e1 = (cov >> 4) & 0x01010101u;
+            c[2][0] += e0; c[2][1] += e1;
+            const int h = s_hp[j];
+            if (h == 1) { c[0][0] += e0; c[0][1] += e1; }
+            else if (h == 2) { c[1][0] += e0; c[1][1] += e1; }
+            if (++pending == 255) flush();
+        }
+        __syncthreads();
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+    }
+    flush();
+    const size_t o = (size_t)(P0 - a.lo_al) + sbase;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        uint16_t v[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) v[t] = (P0 + sbase + t >= a.lo && P0 + sbase + t < a.hi) ? s_acc[k][sbase + t] : (uint16_t)0;
+        *reinterpret_cast<uint4*>(a.depth + (size_t)k * a.n_al + o) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
+// emitted[p] = the pileup yields a column (depth > 0) that is not excluded (:218)
+__global__ void indel_emitted_kernel(const uint16_t* __restrict__ depth_all, int64_t n, int32_t lo_al, const int32_t* __restrict__ bed,
+                                     int32_t n_bed, int32_t* __restrict__ em) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int e = depth_all[i] > 0;
+    if (e && n_bed > 0 && bed_excluded(bed, n_bed, lo_al + (int32_t)i + 1)) e = 0;
+    em[i] = e;
+}
+// global rank -> position of the emitted column
+__global__ void indel_empos_kernel(const int32_t* __restrict__ em, const int64_t* __restrict__ grank, int64_t n, int32_t lo_al,
+                                   int32_t* __restrict__ em_pos) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && em[i]) em_pos[grank[i]] = lo_al + (int32_t)i;
+}
+__global__ void indel_chunk_kernel(const NcChunk* __restrict__ chunks, int32_t n_chunks, int32_t lo_al, int32_t ref_lo, int32_t ref_hi,
+                                   const int64_t* __restrict__ grank, IndelChunk* __restrict__ out, int32_t* __restrict__ n_em1) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    IndelChunk ic;
+    ic.lo = max(max(0, chunks[c].start - 1), ref_lo);
+    ic.hi = max(ic.lo, min(chunks[c].end, ref_hi));
+    ic.grank_lo = grank[ic.lo - lo_al];
+    ic.n_em = (int32_t)(grank[ic.hi - lo_al] - ic.grank_lo);
+    ic.rank_off = 0; ic.pad = 0;
+    out[c] = ic;
+    n_em1[c] = ic.n_em + 1;
+}
+__global__ void indel_chunk_off_kernel(IndelChunk* __restrict__ ch, int32_t n_chunks, const int64_t* __restrict__ off) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_chunks) ch[c].rank_off = off[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// I1.2 indel events of every haplotagged read -> difference arrays of the window unions.
+// A read with a qualifying event at emitted column rank r is a member of the union of the last `win` columns at
+// ranks r .. r+win-1; overlapping intervals of one read are merged so it is counted once (a set union).
+// kinds: key = hap*4 + {0 del 2<L<=50, 1 del L<=10, 2 ins 2<L<=50, 3 ins L<=10}.
+// ------------------------------------------------------------------------------------------------
+struct EventArgs {
+    int64_t n_reads;
+    const int32_t* pos; const int32_t* end; const uint16_t* flag; const int8_t* hp;
+    const int64_t* cigar_off; const uint32_t* cigar;
+    const IndelChunk* chunks; int32_t n_chunks;
+    const int32_t* em; const int64_t* grank; int32_t lo_al;
+    uint32_t flag_filter; int32_t win, small_win;
+    int32_t* diff; int64_t R;          // [8][R]
+};
+
+__global__ void indel_events_kernel(const EventArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_reads) return;
+    const int h = a.hp[r] - 1;
+    if (h < 0 || h > 1 || (a.flag[r] & a.flag_filter) != 0) return;
+    const int32_t rp = a.pos[r], re = a.end[r];
+    if (re <= rp) return;
+    // chunks overlapping [rp, re): chunk los are ascending
+    int c0;
+    { int lo = 0, hi = a.n_chunks; while (lo < hi) { int mid = (lo + hi) >> 1; if (a.chunks[mid].hi <= rp) lo = mid + 1; else hi = mid; } c0 = lo; }
+    const int64_t k0 = a.cigar_off[r], k1 = a.cigar_off[r + 1];
+    for (int c = c0; c < a.n_chunks && a.chunks[c].lo < re; c++) {
+        const IndelChunk ch = a.chunks[c];
+        int32_t ca[4] = {-1, -1, -1, -1}, cb[4] = {0, 0, 0, 0};
+        int32_t* dbase = a.diff + (int64_t)(h * 4) * a.R + ch.rank_off;
+        auto add = [&](int kind, int32_t rk) {
+            const int32_t win = (kind & 1) ? a.small_win : a.win;
+            const int32_t b = min(ch.n_em, rk + win);
+            if (ca[kind] < 0) { ca[kind] = rk; cb[kind] = b; }
+            else if (rk <= cb[kind]) { cb[kind] = max(cb[kind], b); }
+            else {
+                atomicAdd(dbase + (int64_t)kind * a.R + ca[kind], 1); atomicAdd(dbase + (int64_t)kind * a.R + cb[kind], -1);
+                ca[kind] = rk; cb[kind] = b;
+            }
+        };
+        int32_t x = rp;
+        for (int64_t k = k0; k < k1; k++) {
+            const uint32_t cw = __ldg(a.cigar + k);
+            const int32_t rl = cig_ref_len(cw);
+            if (rl == 0) continue;
+            const int32_t plast = x + rl - 1;
+            x += rl;
+            if (k + 1 >= k1 || plast < ch.lo || plast >= ch.hi) { if (plast >= ch.hi) break; continue; }
+            const uint32_t op = cw & 15u, op2 = __ldg(a.cigar + k + 1) & 15u;
+            int32_t tot = 0; bool is_del = false;
+            if (op2 == 2u && op != 2u) {
+                is_del = true;
+                tot = (int32_t)(__ldg(a.cigar + k + 1) >> 4);
+                for (int64_t j = k + 2; j < k1; j++) {
+                    const uint32_t w2 = __ldg(a.cigar + j), o2 = w2 & 15u;
+                    if (o2 == 2u) tot += (int32_t)(w2 >> 4);
+                    else if (o2 == 1u || o2 == 4u || o2 == 0u || o2 == 7u || o2 == 8u) break;
+                }
+            } else if (op2 == 1u || (op2 == 6u && k + 2 < k1)) {
+                for (int64_t j = k + 1; j < k1; j++) {
+                    const uint32_t w2 = __ldg(a.cigar + j), o2 = w2 & 15u;
+                    if (o2 == 1u) tot += (int32_t)(w2 >> 4);
+                    else if (o2 != 6u) break;
+                }
+            }
+            if (tot == 0) continue;
+            const int64_t pi = (int64_t)plast - a.lo_al;
+            if (!__ldg(a.em + pi)) continue;
+            const int32_t rk = (int32_t)(__ldg(a.grank + pi) - ch.grank_lo);
+            const int base = is_del ? 0 : 2;
+            if (tot > 2 && tot <= 50) add(base, rk);
+            if (tot <= 10) add(base + 1, rk);
+        }
+#pragma unroll
+        for (int kind = 0; kind < 4; kind++)
+            if (ca[kind] >= 0) { atomicAdd(dbase + (int64_t)kind * a.R + ca[kind], 1); atomicAdd(dbase + (int64_t)kind * a.R + cb[kind], -1); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// I1.3 threshold tests per emitted column (:252-275): hit = 1 large-window condition, 2 small-window condition
+// ------------------------------------------------------------------------------------------------
+struct DecideArgs {
+    const IndelChunk* chunks; int32_t n_chunks; int64_t R;
+    const int64_t* uscan;      // [8][R+1] exclusive scans of diff
+    const int32_t* em_pos; const uint16_t* depth; int64_t n_al; int32_t lo_al;
+    int32_t mincov; double ins_t, del_t;
+    uint8_t* hit; unsigned long long* n_hits;
+};
+__global__ void indel_decide_kernel(const DecideArgs a) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.R) return;
+    int c;
+    { int lo = 0, hi = a.n_chunks; while (lo < hi) { int mid = (lo + hi) >> 1; if (a.chunks[mid].rank_off <= g) lo = mid + 1; else hi = mid; } c = lo - 1; }
+    const IndelChunk ch = a.chunks[c];
+    const int32_t r = (int32_t)(g - ch.rank_off);
+    uint8_t hit = 0;
+    if (r < ch.n_em) {
+        const int32_t p = a.em_pos[ch.grank_lo + r];
+        const int64_t pi = (int64_t)p - a.lo_al;
+        const int32_t l0 = a.depth[pi], l1 = a.depth[a.n_al + pi];
+        if (l0 >= a.mincov && l1 >= a.mincov) {
+            double f[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int32_t l = k < 4 ? l0 : l1;
+                f[k] = l > 0 ? (double)a.uscan[(int64_t)k * (a.R + 1) + g + 1] / (double)l : 0.0;
+            }
+            if (fmax(f[0], f[4]) >= a.del_t || fmax(f[2], f[6]) >= a.ins_t) hit = 1;
+            else if (fmax(f[1], f[5]) >= a.del_t || fmax(f[3], f[7]) >= a.ins_t || (f[1] + f[3]) >= 0.9 || (f[5] + f[7]) >= 0.9) hit = 2;
+        }
+    }
+    a.hit[g] = hit;
+    if (hit) atomicAdd(a.n_hits, 1ull);
+}
+
+// I1.4 greedy pass with `prev` (:249,267,273): one warp per chunk walks its columns in order.
+__global__ void indel_greedy_kernel(const IndelChunk* __restrict__ chunks, int32_t n_chunks, const uint8_t* __restrict__ hit,
+                                    const int32_t* __restrict__ em_pos, int32_t win, NcIndelVariant* __restrict__ out,
+                                    unsigned long long* __restrict__ n_out) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= n_chunks) return;
+    const IndelChunk ch = chunks[c];
+    int32_t prev = 0;
+    for (int32_t r0 = 0; r0 < ch.n_em; r0 += 32) {
+        const int32_t r = r0 + lane;
+        int h = 0; int32_t v = 0;
+        if (r < ch.n_em) { h = hit[ch.rank_off + r]; v = em_pos[ch.grank_lo + r] + 1; }
+        uint32_t m = __ballot_sync(0xffffffffu, h != 0);
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const int hl = __shfl_sync(0xffffffffu, h, l);
+            const int32_t vl = __shfl_sync(0xffffffffu, v, l);
+            if (vl <= prev) continue;
+            const int32_t back = hl == 1 ? win : 10;
+            prev = vl + back;
+            if (lane == 0) {
+                const unsigned long long slot = atomicAdd(n_out, 1ull);
+                NcIndelVariant nv; nv.key = max(1, vl - back); nv.type = hl - 1; nv.chunk = c;
+                out[slot] = nv;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// I2 / I3 — per key position: covering reads, slices, alignment, tensors
+// ------------------------------------------------------------------------------------------------
+struct SiteArgs {
+    int64_t n_reads;
+    const int32_t* pos; const int32_t* end; const uint16_t* flag; const int8_t* hp; const int32_t* ps; const int32_t* pmaxend;
+    const int64_t* cigar_off; const uint32_t* cigar; const int2* opstart;
+    const int64_t* seq_off; const int32_t* l_seq; const uint8_t* seq4;
+    const uint8_t* ref; int64_t ref_start, ref_len; int32_t contig_len;
+    const NcIndelVariant* sites; int64_t n_sites;
+    const NcChunk* chunks;
+    uint32_t flag_filter; int32_t wa, win, mincov, maxcov;
+    int32_t* site_m;           // reference window length per site (0 = skipped)
+    int32_t* site_cnt;         // covering reads per site
+    const int64_t* site_off;   // [n_sites+1] entry offsets
+    int32_t* e_read; int32_t* e_qpn;
+    // alignment outputs, stride per entry
+    uint8_t* e_slice; uint8_t* e_acode; uint16_t* e_inslen; uint16_t* e_insfirst; int32_t* e_n;
+    int32_t nmax, mmax;
+    // msa outputs
+    float* tensors;            // [n_sites][3][5][128][2]
+    uint8_t* cns;              // [n_sites][3][cmax]
+    int32_t cmax;
+    NcIndelSiteMeta* meta;
+};
+
+// window of BAM indices of reads that can cover p
+__device__ __forceinline__ void read_window(const int32_t* pos, const int32_t* pmaxend, int64_t n, int32_t p, int64_t& ilo, int64_t& ihi) {
+    ihi = upper_bound_i32_64(pos, n, p);
+    int64_t lo = 0, hi = ihi;
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (__ldg(pmaxend + mid) <= p) lo = mid + 1; else hi = mid; }
+    ilo = lo;
+}
+
+// pass A (count) / pass B (fill): warp per site
+template <bool FILL>
+__global__ void __launch_bounds__(128) indel_site_reads_kernel(const SiteArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= a.n_sites) return;
+    const NcIndelVariant sv = a.sites[s];
+    const int32_t v = sv.key, p = v - 1;
+    const NcChunk ck = a.chunks[sv.chunk];
+    // pass-2 pileup range (:306) and reference window (:325-328)
+    const int32_t plo = max(0, ck.start - 10 - a.win), phi = min(ck.end, a.contig_len);
+    int32_t m = min(a.contig_len, v + a.wa + 1) - v;
+    bool okref = p >= plo && p < phi && m > 0 && (int64_t)p >= a.ref_start && (int64_t)(p + m) <= a.ref_start + a.ref_len;
+    if (okref) {
+        bool bad = false;
+        for (int j = lane; j < m; j += 32) { const uint8_t ch = __ldg(a.ref + ((int64_t)p + j - a.ref_start)); bad |= ref_code_of(ch) > 3; }
+        okref = !__any_sync(0xffffffffu, bad);
+    }
+    int64_t ilo = 0, ihi = 0;
+    if (okref) read_window(a.pos, a.pmaxend, a.n_reads, p, ilo, ihi);
+    int32_t cnt = 0;
+    const int64_t off = FILL ? a.site_off[s] : 0;
+    for (int64_t base = ilo; base < ihi; base += 32) {
+        const int64_t i = base + lane;
+        bool cover = false;
+        if (i < ihi) {
+            const int32_t rp = __ldg(a.pos + i), re = __ldg(a.end + i);
+            cover = (__ldg(a.flag + i) & a.flag_filter) == 0 && rp <= p && p < re;
+        }
+        const uint32_t cm = __ballot_sync(0xffffffffu, cover);
+        if (FILL && cover) {
+            const int64_t e = off + cnt + __popc(cm & ((1u << lane) - 1u));
+            a.e_read[e] = (int32_t)i;
+            // query_position_or_next (appendix C.4): op containing p
+            const int64_t c0 = a.cigar_off[i];
+            const int32_t nops = (int32_t)(a.cigar_off[i + 1] - c0), os = p - __ldg(a.pos + i);
+            int32_t lo = 0, hi = nops;
+            while (lo < hi) { int32_t mid = (lo + hi) >> 1; if (__ldg(&a.opstart[c0 + mid].x) <= os) lo = mid + 1; else hi = mid; }
+            const int32_t k = lo - 1;
+            const int2 st = __ldg(a.opstart + c0 + k);
+            a.e_qpn[e] = cig_is_match(__ldg(a.cigar + c0 + k)) ? st.y + (os - st.x) : st.y;
+        }
+        cnt += __popc(cm);
+    }
+    if (!FILL && lane == 0) { a.site_cnt[s] = okref ? cnt : 0; a.site_m[s] = (okref && cnt > 0) ? m : 0; }
+}
+
+// Star alignment step 1: global linear-gap NW of one read slice against the reference window, one warp per entry.
+// match +2, mismatch -4, gap -3; direction DIAG if the diagonal attains the max, else UP (read base unaligned), else LEFT.
+// Lane l owns reference columns [l*CW, (l+1)*CW); rows are processed as a skewed wavefront (lane l works on row t-l).
+constexpr int kAlignWarps = 2;
+constexpr int kCW = 9;                      // 32 * 9 = 288 >= 261 reference columns
+constexpr int kRowsMax = 264;
+
+__global__ void __launch_bounds__(kAlignWarps * 32) indel_align_kernel(const SiteArgs a, int64_t n_entries) {
+    extern __shared__ uint32_t s_dir_all[];                      // per warp [kRowsMax][32] direction words (2 bits per column)
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t* s_dir = s_dir_all + (size_t)wib * kRowsMax * 32;
+    const uint32_t full = 0xffffffffu;
+    for (int64_t e = (int64_t)blockIdx.x * kAlignWarps + wib; e < n_entries; e += (int64_t)gridDim.x * kAlignWarps) {
+        int64_t s;
+        { int64_t lo = 0, hi = a.n_sites; while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (__ldg(a.site_off + mid) <= e) lo = mid + 1; else hi = mid; } s = lo - 1; }
+        const int32_t m = a.site_m[s];
+        const int32_t v = a.sites[s].key, p = v - 1;
+        const int64_t ri = a.e_read[e];
+        const int32_t q0 = a.e_qpn[e], lseq = __ldg(a.l_seq + ri);
+        const int32_t n = max(0, min(a.wa, lseq - q0));
+        const uint8_t* sq = a.seq4 + __ldg(a.seq_off + ri);
+        uint8_t* o_slice = a.e_slice + e * a.nmax;
+        uint8_t* o_ac = a.e_acode + e * a.mmax;
+        uint16_t* o_il = a.e_inslen + e * (a.mmax + 1);
+        uint16_t* o_if = a.e_insfirst + e * (a.mmax + 1);
+        // slice codes -> global (also read back as the DP's read sequence)
+        for (int i = lane; i < n; i += 32) {
+            const int32_t q = q0 + i;
+            const uint32_t b = __ldg(sq + (q >> 1));
+            const uint32_t bn = (q & 1) ? (b & 15u) : (b >> 4);
+            o_slice[i] = (uint8_t)((kNibToCode >> (4 * bn)) & 15u);
+        }
+        for (int j = lane; j <= m; j += 32) { o_il[j] = 0; o_if[j] = 0; }
+        __syncwarp();
+        // reference codes of the lane's strip
+        int refc[kCW];
+#pragma unroll
+        for (int k = 0; k < kCW; k++) {
+            const int j = lane * kCW + k;         // 0-based reference column
+            refc[k] = j < m ? ref_code_of(__ldg(a.ref + ((int64_t)p + j - a.ref_start))) : 7;
+        }
+        // H of the previous row for the strip: hp[k] = H[i-1][j0+k+1], hleft = H[i-1][j0] (column left of the strip)
+        int32_t hp[kCW];
+#pragma unroll
+        for (int k = 0; k < kCW; k++) hp[k] = -3 * (lane * kCW + k + 1);
+        int32_t h_left_prev = -3 * (lane * kCW);              // H[i-1][j0]
+        int32_t last_out = 0;                                   // H[i][last column of strip] of the row finished in the previous step
+        for (int t = 1; t <= n + 31; t++) {
+            // value of the left neighbour's strip end for the row this lane works on now: lane-1 finished row i at step t-1
+            const int32_t from_left = __shfl_up_sync(full, last_out, 1);
+            const int i = t - lane;
+            if (i >= 1 && i <= n) {
+                const int rb = o_slice[i - 1];
+                const int32_t h_left_cur = lane == 0 ? -3 * i : from_left;        // H[i][j0]
+                int32_t diag_in = h_left_prev, left = h_left_cur;
+                uint32_t dw = 0;
+#pragma unroll
+                for (int k = 0; k < kCW; k++) {
+                    const int32_t sc = (refc[k] == rb && rb < 4) ? 2 : -4;
+                    const int32_t dg = diag_in + sc, up = hp[k] - 3, lf = left - 3;
+                    const int32_t best = max(dg, max(up, lf));
+                    const uint32_t d = best == dg ? 0u : (best == up ? 1u : 2u);
+                    dw |= d << (2 * k);
+                    diag_in = hp[k];
+                    hp[k] = best;
+                    left = best;
+                }
+                s_dir[i * 32 + lane] = dw;
+                h_left_prev = h_left_cur;
+                last_out = left;
+            }
+        }
+        __syncwarp();
+        // traceback (lane 0) from (n, m)
+        if (lane == 0) {
+            int i = n, j = m;
+            while (i > 0 || j > 0) {
+                uint32_t d;
+                if (i == 0) d = 2u; else if (j == 0) d = 1u;
+                else d = (s_dir[i * 32 + (j - 1) / kCW] >> (2 * ((j - 1) % kCW))) & 3u;
+                if (d == 0u) { o_ac[j - 1] = o_slice[i - 1]; i--; j--; }
+                else if (d == 1u) { o_il[j]++; o_if[j] = (uint16_t)(i - 1); i--; }
+                else { o_ac[j - 1] = 5; j--; }
+            }
+            a.e_n[e] = n;
+        }
+        __syncwarp();
+    }
+}
+
+// Star alignment step 2 + `msa` tensor assembly (:54-71): one warp per (site, group); group 0 = HP1, 1 = HP2, 2 = all reads.
+__global__ void __launch_bounds__(96) indel_msa_kernel(const SiteArgs a) {
+    __shared__ uint16_t s_width[3][kRowsMax + 8];
+    __shared__ uint16_t s_col[3][kRowsMax + 8];
+    __shared__ uint8_t s_cns[3][2 * kRowsMax + 32];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int64_t s = blockIdx.x;
+    const uint32_t full = 0xffffffffu;
+    const int32_t m = a.site_m[s];
+    float* T = a.tensors + ((s * 3 + g) * 5) * 256;
+    for (int i = lane; i < 5 * 256; i += 32) T[i] = 0.f;
+    __syncwarp();
+    int32_t n_g = 0, first_read = -1;
+    const int64_t e0 = a.site_off[s];
+    const int32_t cnt = m > 0 ? a.site_cnt[s] : 0;
+    const int32_t mincov = g == 2 ? a.mincov : 2;
+    // membership: first maxcov reads of the group in pileup order (deterministic rule for the unseeded random.sample, :19)
+    auto member = [&](int32_t k) -> bool {
+        const int h = __ldg(a.hp + a.e_read[e0 + k]);
+        return g == 2 || h == g + 1;
+    };
+    // n_g and the first member
+    for (int32_t k0 = 0; k0 < cnt; k0 += 32) {
+        const int32_t k = k0 + lane;
+        const bool mem = k < cnt && member(k);
+        const uint32_t bm = __ballot_sync(full, mem);
+        if (first_read < 0 && bm) first_read = a.e_read[e0 + k0 + __ffs(bm) - 1];
+        n_g += __popc(bm);
+    }
+    const int32_t n_use = min(n_g, a.maxcov);
+    const bool ok = m > 0 && n_use >= mincov;
+    uint16_t* width = s_width[g];
+    uint16_t* col = s_col[g];
+    int32_t L = 0, cl = 0;
+    if (ok) {
+        // widths of the insertion blocks
+        for (int j = lane; j <= m; j += 32) width[j] = 0;
+        __syncwarp();
+        int32_t seen = 0;
+        for (int32_t k = 0; k < cnt && seen < n_use; k++) {
+            if (!member(k)) continue;                      // warp-uniform
+            seen++;
+            const uint16_t* il = a.e_inslen + (e0 + k) * (a.mmax + 1);
+            for (int j = lane; j <= m; j += 32) { const uint16_t w = il[j]; if (w > width[j]) width[j] = w; }
+        }
+        __syncwarp();
+        // column of reference base j = j + sum_{j' <= j} width[j']
+        int32_t carry = 0;
+        for (int j0 = 0; j0 <= m; j0 += 32) {
+            const int j = j0 + lane;
+            const int32_t w = j <= m ? width[j] : 0;
+            const int32_t inc = warp_incl_scan32(w, lane);
+            if (j <= m) col[j] = (uint16_t)(j + carry + inc);
+            carry += __shfl_sync(full, inc, 31);
+        }
+        __syncwarp();
+        L = m + carry;
+        const float nf = (float)n_use;
+        uint8_t* cns_sym = s_cns[g];
+        for (int i = lane; i < L; i += 32) cns_sym[i] = 4;
+        __syncwarp();
+        // match columns: lane-parallel over reference bases
+        for (int j = lane; j < m; j += 32) {
+            int32_t c[5] = {0, 0, 0, 0, 0};
+            int32_t seen2 = 0;
+            for (int32_t k = 0; k < cnt && seen2 < n_use; k++) {
+                if (!member(k)) continue;
+                seen2++;
+                const uint8_t code = a.e_acode[(e0 + k) * a.mmax + j];
+                c[code < 4 ? code : 4]++;
+            }
+            const int rc = ref_code_of(__ldg(a.ref + ((int64_t)(a.sites[s].key - 1) + j - a.ref_start)));
+            const int cc = col[j];
+            float best = -1.f; int bi = 0;
+#pragma unroll
+            for (int b = 0; b < 5; b++) {
+                const float f = (float)c[b] / nf;
+                const float tf = b == 4 ? f - 0.01f : f;
+                if (tf > best) { best = tf; bi = b; }
+                if (cc < 128) { T[(b * 128 + cc) * 2] = f - (b == rc ? 1.f : 0.f); T[(b * 128 + cc) * 2 + 1] = b == rc ? 1.f : 0.f; }
+            }
+            cns_sym[cc] = (uint8_t)bi;
+        }
+        // insertion columns: slot j (before reference base j, or after the last one for j = m), k-th inserted base
+        for (int j = 0; j <= m; j++) {
+            const int w = width[j];
+            if (w == 0) continue;                          // warp-uniform (shared memory)
+            const int cstart = (j < m ? col[j] : L) - w;
+            for (int kk = lane; kk < w; kk += 32) {
+                int32_t c[5] = {0, 0, 0, 0, 0};
+                int32_t seen2 = 0;
+                for (int32_t k = 0; k < cnt && seen2 < n_use; k++) {
+                    if (!member(k)) continue;
+                    seen2++;
+                    const int64_t e = e0 + k;
+                    const uint16_t il = a.e_inslen[e * (a.mmax + 1) + j];
+                    int code = 4;
+                    if (kk < il) { code = a.e_slice[e * a.nmax + a.e_insfirst[e * (a.mmax + 1) + j] + kk]; if (code > 3) code = 4; }
+                    c[code]++;
+                }
+                const int cc = cstart + kk;
+                float best = -1.f; int bi = 0;
+#pragma unroll
+                for (int b = 0; b < 5; b++) {
+                    const float f = (float)c[b] / nf;
+                    const float tf = b == 4 ? f - 0.01f : f;
+                    if (tf > best) { best = tf; bi = b; }
+                    if (cc < 128) { T[(b * 128 + cc) * 2] = f - (b == 4 ? 1.f : 0.f); T[(b * 128 + cc) * 2 + 1] = b == 4 ? 1.f : 0.f; }
+                }
+                cns_sym[cc] = (uint8_t)bi;
+            }
+        }
+        __syncwarp();
+        // consensus = column argmax without gaps (:63-64), ordered compaction
+        uint8_t* out = a.cns + (s * 3 + g) * a.cmax;
+        for (int i0 = 0; i0 < L; i0 += 32) {
+            const int i = i0 + lane;
+            const int sy = i < L ? cns_sym[i] : 4;
+            const uint32_t bm = __ballot_sync(full, sy < 4);
+            if (sy < 4) { const int o = cl + __popc(bm & ((1u << lane) - 1u)); if (o < a.cmax) out[o] = (uint8_t)sy; }
+            cl += __popc(bm);
+        }
+    }
+    if (lane == 0) {
+        NcIndelSiteMeta* mt = a.meta + s;
+        mt->n[g] = ok ? n_use : 0;
+        mt->cns_len[g] = ok ? min(cl, a.cmax) : 0;
+        mt->ok[g] = ok ? 1 : 0;
+        if (g == 0) { mt->pos = a.sites[s].key; mt->chunk = a.sites[s].chunk; mt->type = a.sites[s].type; mt->ref_len = m;
+                      mt->phase = (ok && first_read >= 0) ? __ldg(a.ps + first_read) : 0; }
+    }
+}
+
+}  // namespace nc

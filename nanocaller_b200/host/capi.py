@@ -16,7 +16,8 @@ SITE_ELEMS, SITE_STRIDE = 1025, 1032
 EXPORTS = ["nc_abi_version", "nc_create", "nc_destroy", "nc_last_error", "nc_sync", "nc_get_timings",
            "nc_device_sm_count", "nc_event_record", "nc_event_elapsed_ms", "nc_invalidate_decode", "nc_stage_reads", "nc_decode_reads", "nc_snp_scan", "nc_snp_fetch",
            "nc_load_snp_weights", "nc_snp_forward", "nc_snp_fetch_probs", "nc_snp_model_forward", "nc_snp_device_buffers",
-           "nc_load_indel_weights", "nc_indel_model_forward"]
+           "nc_load_indel_weights", "nc_indel_model_forward", "nc_stage_tags", "nc_indel_scan", "nc_indel_fetch_variants",
+           "nc_indel_build", "nc_indel_fetch", "nc_nw_trace"]
 
 
 class NcSnpParams(ctypes.Structure):
@@ -31,6 +32,16 @@ class NcTimings(ctypes.Structure):
                 ("scan_bytes", ctypes.c_uint64)]
 
 
+class NcIndelParams(ctypes.Structure):
+    _fields_ = [("ins_t", ctypes.c_double), ("del_t", ctypes.c_double), ("mincov", ctypes.c_int32), ("maxcov", ctypes.c_int32),
+                ("win_size", ctypes.c_int32), ("small_win_size", ctypes.c_int32), ("window_after", ctypes.c_int32),
+                ("supplementary", ctypes.c_int32)]
+
+
+VARIANT_DTYPE = np.dtype([("key", "<i4"), ("type", "<i4"), ("chunk", "<i4")])
+INDEL_META_DTYPE = np.dtype([("pos", "<i4"), ("chunk", "<i4"), ("type", "<i4"), ("phase", "<i4"), ("ref_len", "<i4"),
+                             ("n", "<i4", (3,)), ("cns_len", "<i4", (3,)), ("ok", "<i4", (3,))])
+INDEL_CNS_MAX = 544
 CHUNK_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4")])
 META_DTYPE = np.dtype([("pos", "<i4"), ("chunk", "<i4"), ("dp", "<i4"), ("alt", "<i4"), ("fwd", "<u2", (4,)),
                        ("rev", "<u2", (4,)), ("ref_code", "u1"), ("n_left", "u1"), ("n_right", "u1"),
@@ -81,6 +92,12 @@ def load_library():
     lib.nc_snp_device_buffers.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64)]
     lib.nc_load_indel_weights.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_int]
     lib.nc_indel_model_forward.argtypes = [vp, vp, i64, ctypes.c_int, ctypes.c_int, vp]
+    lib.nc_stage_tags.argtypes = [vp, vp, vp]
+    lib.nc_indel_scan.argtypes = [vp, ctypes.POINTER(NcIndelParams), vp, i32, vp, i32, ctypes.POINTER(i64)]
+    lib.nc_indel_fetch_variants.argtypes = [vp, vp]
+    lib.nc_indel_build.argtypes = [vp, ctypes.POINTER(NcIndelParams), vp, i32, vp, i64]
+    lib.nc_indel_fetch.argtypes = [vp, vp, vp, vp]
+    lib.nc_nw_trace.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp, i32]
     for name in EXPORTS:
         if name not in ("nc_destroy", "nc_last_error"):
             getattr(lib, name).restype = ctypes.c_int
@@ -97,6 +114,24 @@ def snp_params(dct, ploidy):
     return NcSnpParams(float(dct["threshold"][0]), float(dct["threshold"][1]), float(dct["min_allele_freq"]),
                        int(dct["mincov"]), int(dct["maxcov"]), int(dct["min_nbr_sites"]), SEQ_CODES[dct["seq"]],
                        1 if dct.get("supplementary") else 0, 1 if ploidy == "haploid" else 0)
+
+
+def indel_params(dct):
+    """NcIndelParams from the reference's `dct` (generate_indel_pileups.py:136-157)."""
+    return NcIndelParams(float(dct["ins_t"]), float(dct["del_t"]), int(dct["mincov"]), int(dct["maxcov"]), int(dct["win_size"]),
+                         int(dct["small_win_size"]), 260 if dct["seq"] == "pacbio" else 160, 1 if dct.get("supplementary") else 0)
+
+
+def nw_trace(query_codes, ref_codes, gap_open=9, gap_extend=1, match=20, mismatch=-10):
+    """Host-side affine alignment of the library (replaces parasail.nw_trace): -> list of (op code, length), ops '='7 'X'8 'I'1 'D'2."""
+    lib = load_library()
+    q = np.ascontiguousarray(query_codes, np.uint8)
+    r = np.ascontiguousarray(ref_codes, np.uint8)
+    out = np.empty(len(q) + len(r) + 2, np.uint32)
+    n = lib.nc_nw_trace(_p(q) if len(q) else None, len(q), _p(r) if len(r) else None, len(r), gap_open, gap_extend, match, mismatch, _p(out), len(out))
+    if n < 0:
+        raise NcError(n, "nc_nw_trace failed")
+    return [(int(w & 15), int(w >> 4)) for w in out[:n]]
 
 
 class Context:
@@ -140,6 +175,34 @@ class Context:
         self._keep = (pos, flag, cigar_off, cigar, seq_off, l_seq, seq4, ref)
         self._check(self._lib.nc_stage_reads(self._h, len(pos), _p(pos), _p(flag), _p(cigar_off), _p(cigar), _p(seq_off),
                                              _p(l_seq), _p(seq4), _p(ref), ref_start, len(ref)))
+
+    def stage_tags(self, hp, ps):
+        hp = np.ascontiguousarray(hp, np.int8)
+        ps = np.ascontiguousarray(ps, np.int32)
+        self._keep_tags = (hp, ps)
+        self._check(self._lib.nc_stage_tags(self._h, _p(hp), _p(ps)))
+
+    # ---- indel feature path
+    def indel_scan(self, params, chunks, bed=None):
+        ch = np.array([(int(s), int(e)) for s, e in chunks], dtype=CHUNK_DTYPE)
+        bd = np.ascontiguousarray(np.array(bed, dtype=np.int32).reshape(-1, 2)) if bed is not None and len(bed) else None
+        n = ctypes.c_int64(0)
+        self._check(self._lib.nc_indel_scan(self._h, ctypes.byref(params), _p(ch) if len(ch) else None, len(ch), _p(bd),
+                                            0 if bd is None else len(bd), ctypes.byref(n)))
+        out = np.empty(n.value, VARIANT_DTYPE)
+        self._check(self._lib.nc_indel_fetch_variants(self._h, _p(out) if n.value else None))
+        return out
+
+    def indel_build(self, params, chunks, sites):
+        ch = np.array([(int(s), int(e)) for s, e in chunks], dtype=CHUNK_DTYPE)
+        sites = np.ascontiguousarray(sites, VARIANT_DTYPE)
+        n = len(sites)
+        self._check(self._lib.nc_indel_build(self._h, ctypes.byref(params), _p(ch) if len(ch) else None, len(ch), _p(sites) if n else None, n))
+        meta = np.empty(n, INDEL_META_DTYPE)
+        tensors = np.empty((n, 3, 5, 128, 2), np.float32)
+        cns = np.empty((n, 3, INDEL_CNS_MAX), np.uint8)
+        self._check(self._lib.nc_indel_fetch(self._h, _p(meta) if n else None, _p(tensors) if n else None, _p(cns) if n else None))
+        return meta, tensors, cns
 
     def decode_reads(self):
         self._check(self._lib.nc_decode_reads(self._h))

@@ -1,0 +1,61 @@
+"""GPU parity of the indel feature path through the C-ABI against fixtures produced by the UNMODIFIED reference
+generate_indel_pileups.py (run over the stand-in muscle / parasail, see tests/golden/make_golden_indel.py):
+candidate positions, the three float tensors bit for bit, allele strings and phase sets; then the indel CNN on them."""
+import json
+
+import numpy as np
+import pytest
+
+from tests.test_indel_oracle_golden import CASES, load_indel_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(got, g, ci, tag):
+    pos, x0, x1, x2, alleles, phase = got
+    want_pos = g["c%d_pos" % ci]
+    assert list(pos) == list(want_pos), (tag, list(pos)[:10], list(want_pos)[:10])
+    if len(want_pos) == 0:
+        return
+    for k, x in (("x0", x0), ("x1", x1), ("x2", x2)):
+        w = g["c%d_%s" % (ci, k)].astype(np.float64)
+        bad = np.nonzero((np.asarray(x) != w).reshape(len(w), -1).any(1))[0]
+        assert len(bad) == 0, "%s %s: %d/%d tensors differ, first site %d" % (tag, k, len(bad), len(w), bad[0])
+    assert json.loads(json.dumps(alleles)) == json.loads(str(g["c%d_alleles" % ci])), tag
+    assert list(phase) == json.loads(str(g["c%d_phase" % ci])), tag
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_drop_in_matches_reference_golden(name):
+    from nanocaller_b200.host import indel_pileups, sources
+    rs, dct, chunks, g = load_indel_case(name)
+    sources.unregister_all()
+    sources.register_source("mem://bam", rs)
+    d = dict(dct, fasta_path="mem://bam")
+    for ci, chunk in enumerate(chunks):
+        got = indel_pileups.get_indel_testing_candidates(d, dict(chunk, sam_path="mem://bam"))
+        _check(got, g, ci, (name, ci))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_batched_chunks_match_reference_golden(name):
+    from nanocaller_b200.host import indel_pileups, snp_pileups
+    rs, dct, chunks, g = load_indel_case(name)
+    res = indel_pileups.candidates_for_chunks(snp_pileups.context(0), rs, dct, chunks)
+    for ci in range(len(chunks)):
+        _check(res[ci], g, ci, (name, ci, "batched"))
+
+
+def test_indel_cnn_on_device_tensors():
+    """hstack of the three tensors -> Indel_model (indelCaller.py:83-85) vs the fp32 oracle."""
+    from nanocaller_b200.host import indel_pileups, snp_pileups, weights as W
+    from oracle import cnn_oracle
+    rs, dct, chunks, g = load_indel_case("indel_ont")
+    ctx = snp_pileups.context(0)
+    pos, x0, x1, x2, alleles, phase = indel_pileups.candidates_for_chunks(ctx, rs, dct, chunks)[0]
+    x = np.hstack([x0, x1, x2]).astype(np.float32)
+    tensors, _ = W.load_model("indel", "ONT-HG002")
+    ctx.load_indel_weights(W.pack_indel_blob(tensors), False)
+    got = ctx.indel_model_forward(x, haploid=False, impl=1)
+    want = cnn_oracle.indel_model(tensors, x)
+    assert np.abs(got - want).max() < 1e-4
