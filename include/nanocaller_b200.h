@@ -194,6 +194,8 @@ typedef struct NcIndelParams {
     int32_t win_size, small_win_size;
     int32_t window_after;            /* 160, or 260 for dct['seq'] == 'pacbio' (:136-139)           */
     int32_t supplementary;
+    int32_t haploid;                 /* generate_indel_pileups_haploid.py: one window set / one MSA over all reads */
+    int32_t reserved;
 } NcIndelParams;
 
 typedef struct NcIndelVariant { int32_t key, type, chunk; } NcIndelVariant;   /* variants[key] = type (:268,:274) */

@@ -782,7 +782,13 @@ int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int3
     if (!c || !P || !n_variants || n_chunks < 0 || (n_chunks > 0 && !chunks) || n_bed < 0 || (n_bed > 0 && !bed))
         return fail(c, NC_EINVAL, "nc_indel_scan: bad argument");
     *n_variants = 0;
-    if (!c->staged || !c->tags_staged) return fail(c, NC_ESTATE, "nc_indel_scan needs nc_stage_reads and nc_stage_tags");
+    if (!c->staged || (!c->tags_staged && !P->haploid)) return fail(c, NC_ESTATE, "nc_indel_scan needs nc_stage_reads and nc_stage_tags");
+    if (!c->tags_staged) {        // haploid caller never looks at HP / PS: stage neutral tags
+        std::vector<int8_t> z8((size_t)c->n_reads, 0); std::vector<int32_t> z32((size_t)c->n_reads, 0);
+        int rc0 = nc_stage_tags(c, z8.data(), z32.data());
+        if (rc0) return rc0;
+        NC_CUDA(cudaStreamSynchronize(c->stream));
+    }
     if (P->win_size < 1 || P->small_win_size < 1 || P->win_size > 190) return fail(c, NC_EINVAL, "win_size must be in 1..190");
     NC_CUDA(cudaSetDevice(c->device));
     int rc = nc_decode_reads(c);
@@ -851,7 +857,7 @@ int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int3
     EventArgs ea = {};
     ea.n_reads = c->n_reads; ea.pos = da.pos; ea.end = da.end; ea.flag = da.flag; ea.hp = da.hp; ea.cigar_off = c->d_cigar_off.as<int64_t>();
     ea.cigar = c->d_cigar.as<uint32_t>(); ea.chunks = c->d_ichunks.as<IndelChunk>(); ea.n_chunks = n_chunks; ea.em = c->d_em.as<int32_t>();
-    ea.grank = c->d_grank.as<int64_t>(); ea.lo_al = lo_al; ea.flag_filter = flag_filter; ea.win = P->win_size; ea.small_win = P->small_win_size;
+    ea.grank = c->d_grank.as<int64_t>(); ea.lo_al = lo_al; ea.flag_filter = flag_filter; ea.win = P->win_size; ea.small_win = P->small_win_size; ea.haploid = P->haploid;
     ea.diff = c->d_diff.as<int32_t>(); ea.R = R;
     indel_events_kernel<<<(unsigned)div_up(c->n_reads, 128), 128, 0, c->stream>>>(ea); NC_LAUNCH_CHECK();
     NC_CUDA(c->d_uscan.reserve((size_t)8 * (R + 1) * 8));
@@ -862,7 +868,7 @@ int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int3
     NC_CUDA(cudaMemsetAsync(c->d_icount.p, 0, 64, c->stream));
     DecideArgs dd = {};
     dd.chunks = c->d_ichunks.as<IndelChunk>(); dd.n_chunks = n_chunks; dd.R = R; dd.uscan = c->d_uscan.as<int64_t>(); dd.em_pos = c->d_empos.as<int32_t>();
-    dd.depth = c->d_idepth.as<uint16_t>(); dd.n_al = n_al; dd.lo_al = lo_al; dd.mincov = P->mincov; dd.ins_t = P->ins_t; dd.del_t = P->del_t;
+    dd.depth = c->d_idepth.as<uint16_t>(); dd.n_al = n_al; dd.lo_al = lo_al; dd.mincov = P->mincov; dd.haploid = P->haploid; dd.ins_t = P->ins_t; dd.del_t = P->del_t;
     dd.hit = c->d_hit.as<uint8_t>(); dd.n_hits = c->d_icount.as<unsigned long long>();
     indel_decide_kernel<<<(unsigned)div_up(R, 256), 256, 0, c->stream>>>(dd); NC_LAUNCH_CHECK();
     int64_t n_hits = 0;

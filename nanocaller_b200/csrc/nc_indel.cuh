@@ -150,14 +150,14 @@ struct EventArgs {
     const int64_t* cigar_off; const uint32_t* cigar;
     const IndelChunk* chunks; int32_t n_chunks;
     const int32_t* em; const int64_t* grank; int32_t lo_al;
-    uint32_t flag_filter; int32_t win, small_win;
+    uint32_t flag_filter; int32_t win, small_win, haploid;
     int32_t* diff; int64_t R;          // [8][R]
 };
 
 __global__ void indel_events_kernel(const EventArgs a) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.n_reads) return;
-    const int h = a.hp[r] - 1;
+    const int h = a.haploid ? 0 : a.hp[r] - 1;           // haploid caller: one window set over all reads
     if (h < 0 || h > 1 || (a.flag[r] & a.flag_filter) != 0) return;
     const int32_t rp = a.pos[r], re = a.end[r];
     if (re <= rp) return;
@@ -225,7 +225,7 @@ struct DecideArgs {
     const IndelChunk* chunks; int32_t n_chunks; int64_t R;
     const int64_t* uscan;      // [8][R+1] exclusive scans of diff
     const int32_t* em_pos; const uint16_t* depth; int64_t n_al; int32_t lo_al;
-    int32_t mincov; double ins_t, del_t;
+    int32_t mincov, haploid; double ins_t, del_t;
     uint8_t* hit; unsigned long long* n_hits;
 };
 __global__ void indel_decide_kernel(const DecideArgs a) {
@@ -239,8 +239,16 @@ __global__ void indel_decide_kernel(const DecideArgs a) {
     if (r < ch.n_em) {
         const int32_t p = a.em_pos[ch.grank_lo + r];
         const int64_t pi = (int64_t)p - a.lo_al;
-        const int32_t l0 = a.depth[pi], l1 = a.depth[a.n_al + pi];
-        if (l0 >= a.mincov && l1 >= a.mincov) {
+        const int32_t l0 = a.haploid ? a.depth[2 * a.n_al + pi] : a.depth[pi], l1 = a.haploid ? l0 : a.depth[a.n_al + pi];
+        if (a.haploid) {
+            if (l0 >= a.mincov) {                      // generate_indel_pileups_haploid.py:224-241
+                double f[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) f[k] = l0 > 0 ? (double)a.uscan[(int64_t)k * (a.R + 1) + g + 1] / (double)l0 : 0.0;
+                if (f[0] >= a.del_t || f[2] >= a.ins_t) hit = 1;
+                else if (f[1] >= a.del_t || f[3] >= a.ins_t || (f[1] + f[3]) >= 0.9) hit = 2;
+            }
+        } else if (l0 >= a.mincov && l1 >= a.mincov) {
             double f[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) {

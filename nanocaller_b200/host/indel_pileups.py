@@ -74,13 +74,14 @@ def order_variants(variants):
     return np.array(out, dtype=capi.VARIANT_DTYPE) if out else np.zeros(0, capi.VARIANT_DTYPE)
 
 
-def candidates_for_chunks(ctx, rs, dct, chunks, bed=None):
-    """Scan + build for a list of chunk dicts of one contig; -> per-chunk reference-shaped tuples."""
-    if dct.get("impute_indel_phase"):
+def candidates_for_chunks(ctx, rs, dct, chunks, bed=None, haploid=False):
+    """Scan + build for a list of chunk dicts of one contig; -> per-chunk reference-shaped tuples
+    (diploid: 6-tuple of generate_indel_pileups.py:370; haploid: 3-tuple of generate_indel_pileups_haploid.py:277)."""
+    if dct.get("impute_indel_phase") and not haploid:
         raise NotImplementedError("impute_indel_phase (generate_indel_pileups.py:278-304) is not built")
     snp_pileups.stage(ctx, rs)
     ctx.stage_tags(rs.hp, rs.ps)
-    P = capi.indel_params(dct)
+    P = capi.indel_params(dct, haploid)
     ch = [(c["start"], c["end"]) for c in chunks]
     variants = ctx.indel_scan(P, ch, bed)
     # hits of one chunk are produced in column order by one warp; keep that order when applying the dict semantics
@@ -89,9 +90,10 @@ def candidates_for_chunks(ctx, rs, dct, chunks, bed=None):
     max_range = {0: max(10, int(dct["win_size"])), 1: 10}
     res = []
     for ci in range(len(chunks)):
-        sel = np.nonzero((meta["chunk"] == ci) & (meta["ok"].min(1) > 0))[0]
+        okmask = meta["ok"][:, 2] > 0 if haploid else meta["ok"].min(1) > 0
+        sel = np.nonzero((meta["chunk"] == ci) & okmask)[0]
         if len(sel) == 0:
-            res.append(([], [], [], [], [], []))                        # generate_indel_pileups.py:363-364
+            res.append(([], [], []) if haploid else ([], [], [], [], [], []))       # generate_indel_pileups.py:363-364
             continue
         pos = [int(p) for p in meta["pos"][sel]]
         alleles, phase = [], []
@@ -102,14 +104,14 @@ def candidates_for_chunks(ctx, rs, dct, chunks, bed=None):
             ref_seq = ref_b.tobytes().decode()
             rc = _REF_CODE[ref_b]
             trip = []
-            for g in range(3):
+            for g in ((2,) if haploid else range(3)):
                 codes = cns[s, g, :meta["cns_len"][s, g]]
                 alt = BASES[codes].tobytes().decode()
                 trip.append(allele_prediction(alt, ref_seq, max_range[int(meta["type"][s])], codes, rc))
-            alleles.append(trip)
+            alleles.append(trip[0] if haploid else trip)
             phase.append(int(meta["phase"][s]))
         x = tensors[sel].astype(np.float64)                                  # float32 values in a float64 container (:69-71)
-        res.append((pos, x[:, 0], x[:, 1], x[:, 2], alleles, phase))
+        res.append((pos, x[:, 2], alleles) if haploid else (pos, x[:, 0], x[:, 1], x[:, 2], alleles, phase))
     return res
 
 
@@ -119,3 +121,11 @@ def get_indel_testing_candidates(dct, chunk, device=0):
     rs = sources.resolve(chunk["sam_path"], chunk["chrom"])
     bed = sources.bed_intervals(dct.get("exclude_bed"), chunk["chrom"])
     return candidates_for_chunks(ctx, rs, dct, [chunk], bed)[0]
+
+
+def get_indel_testing_candidates_haploid(dct, chunk, device=0):
+    """Drop-in for generate_indel_pileups_haploid.get_indel_testing_candidates_haploid (indelCaller.py:159): 3-tuple."""
+    ctx = snp_pileups.context(device)
+    rs = sources.resolve(chunk["sam_path"], chunk["chrom"])
+    bed = sources.bed_intervals(dct.get("exclude_bed"), chunk["chrom"])
+    return candidates_for_chunks(ctx, rs, dct, [chunk], bed, haploid=True)[0]

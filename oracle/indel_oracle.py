@@ -138,8 +138,9 @@ def allele_prediction(alt, ref_seq, max_range):
     return ref_seq[:ref_out_len], alt[:alt_out_len]
 
 
-def scan_variants(rs, dct, chunk, bed_intervals=None):
-    """Pass 1 (generate_indel_pileups.py:213-275): -> dict {key v_pos: type 0 | 1}."""
+def scan_variants(rs, dct, chunk, bed_intervals=None, haploid=False):
+    """Pass 1 (generate_indel_pileups.py:213-275; haploid: generate_indel_pileups_haploid.py:199-241):
+    -> dict {key v_pos: type 0 | 1}."""
     start, end = chunk["start"], chunk["end"]
     W, SW = dct["win_size"], dct["small_win_size"]
     mincov, ins_t, del_t = dct["mincov"], dct["ins_t"], dct["del_t"]
@@ -154,7 +155,7 @@ def scan_variants(rs, dct, chunk, bed_intervals=None):
     for i in adm:
         a, b = max(lo, int(rs.pos[i])) - lo, min(hi, int(rs.ref_end[i])) - lo
         depth[2, a] += 1; depth[2, b] -= 1
-        h = int(rs.hp[i]) - 1
+        h = 0 if haploid else int(rs.hp[i]) - 1
         if h in (0, 1):
             depth[h, a] += 1; depth[h, b] -= 1
             for p0, L in read_events(rs, int(i)):
@@ -205,7 +206,16 @@ def scan_variants(rs, dct, chunk, bed_intervals=None):
         if v_pos <= prev:
             continue
         l0, l1 = int(depth[0, c]), int(depth[1, c])
-        if l0 >= mincov and l1 >= mincov:
+        if haploid:
+            if l0 >= mincov:
+                f = lambda key: union[key, r] / l0 if l0 > 0 else 0
+                if f(0) >= del_t or f(2) >= ins_t:
+                    prev = v_pos + W
+                    variants[max(1, v_pos - W)] = 0
+                elif f(1) >= del_t or f(3) >= ins_t or (f(1) + f(3)) >= 0.9:
+                    prev = v_pos + 10
+                    variants[max(1, v_pos - 10)] = 1
+        elif l0 >= mincov and l1 >= mincov:
             f = lambda key, l: union[key, r] / l if l > 0 else 0
             del0, dels0, ins0, inss0 = f(0, l0), f(1, l0), f(2, l0), f(3, l0)
             del1, dels1, ins1, inss1 = f(4, l1), f(5, l1), f(6, l1), f(7, l1)
@@ -274,3 +284,23 @@ def get_indel_testing_candidates(rs, dct, chunk, bed_intervals=None):
     if not pos:
         return pos, X0, X1, X2, alleles, phase
     return pos, np.array(X0), np.array(X1), np.array(X2), alleles, phase
+
+
+def get_indel_testing_candidates_haploid(rs, dct, chunk, bed_intervals=None):
+    """generate_indel_pileups_haploid.py:129-277 -> (pos, x_total, alleles)."""
+    W = dct["win_size"]
+    max_range = {0: max(10, W), 1: 10}
+    variants = scan_variants(rs, dct, chunk, bed_intervals, haploid=True)
+    pos, X, alleles = [], [], []
+    for v_pos in sorted(variants):
+        ss = site_slices(rs, dct, chunk, v_pos)
+        if ss is None:
+            continue
+        ref, reads = ss
+        ft, dt, at, rt = msa_tensor([s for _, _, s in reads], ref, dct["mincov"], dct["maxcov"])
+        if ft:
+            pos.append(v_pos); X.append(dt)
+            alleles.append(allele_prediction(at, rt, max_range[variants[v_pos]]))
+    if not pos:
+        return pos, X, alleles
+    return pos, np.array(X), alleles

@@ -20,6 +20,9 @@ INDEL_CASES = {
     "indel_sub": (lambda: _world(chrom="chr2", preset="ont", contig_len=50_000, seed=42, coverage=24.0, indel_every=900, indel_maxlen=45,
                                  het_every=700, hom_every=0, sys_per_10k=20, clip_prob=0.3),
                   {"win_size": 20, "small_win_size": 2}, [("chr2", 10_001, 40_000, "diploid")], 2, 100000),
+    "indel_haploid": (lambda: _world(chrom="chrX", preset="ont", contig_len=40_000, seed=43, coverage=30.0, indel_every=1200, indel_maxlen=20,
+                                     het_every=0, hom_every=0, sys_per_10k=0, ploidy=1),
+                      {"del_t": 0.5}, [("chrX", 1, 40_000, "haploid")], 1, 100000),
 }
 
 

@@ -22,6 +22,7 @@ os.environ["PATH"] = os.path.join(ROOT, "oracle", "shim", "bin") + os.pathsep + 
 
 import pysam  # the shim  # noqa: E402
 from nanocaller_src.generate_indel_pileups import get_indel_testing_candidates  # noqa: E402  (reference, unchanged)
+from nanocaller_src.generate_indel_pileups_haploid import get_indel_testing_candidates_haploid  # noqa: E402  (reference, unchanged)
 from nanocaller_src.utils import get_chunks  # noqa: E402
 from tests.golden.indel_cases import INDEL_CASES, indel_case_inputs  # noqa: E402
 
@@ -36,7 +37,12 @@ def run_case(name):
     for ci, chunk in enumerate(chunks):
         t = time.time()
         ch = dict(chunk, sam_path="mem://bam")
-        pos, x0, x1, x2, alleles, phase = get_indel_testing_candidates(d, ch)
+        if chunk["ploidy"] == "haploid":
+            pos, x2, alleles = get_indel_testing_candidates_haploid(d, ch)
+            x0 = x1 = x2
+            phase = []
+        else:
+            pos, x0, x1, x2, alleles, phase = get_indel_testing_candidates(d, ch)
         n = len(pos)
         print("  %s chunk %d %s: %d candidates (%.1fs)" % (name, ci, chunk, n, time.time() - t), flush=True)
         out["c%d_pos" % ci] = np.asarray(pos, np.int64)

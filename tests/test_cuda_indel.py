@@ -33,7 +33,11 @@ def test_drop_in_matches_reference_golden(name):
     sources.register_source("mem://bam", rs)
     d = dict(dct, fasta_path="mem://bam")
     for ci, chunk in enumerate(chunks):
-        got = indel_pileups.get_indel_testing_candidates(d, dict(chunk, sam_path="mem://bam"))
+        if chunk["ploidy"] == "haploid":
+            pos, x, alleles = indel_pileups.get_indel_testing_candidates_haploid(d, dict(chunk, sam_path="mem://bam"))
+            got = (pos, x, x, x, alleles, [])
+        else:
+            got = indel_pileups.get_indel_testing_candidates(d, dict(chunk, sam_path="mem://bam"))
         _check(got, g, ci, (name, ci))
 
 
@@ -41,9 +45,11 @@ def test_drop_in_matches_reference_golden(name):
 def test_batched_chunks_match_reference_golden(name):
     from nanocaller_b200.host import indel_pileups, snp_pileups
     rs, dct, chunks, g = load_indel_case(name)
-    res = indel_pileups.candidates_for_chunks(snp_pileups.context(0), rs, dct, chunks)
+    hap = chunks[0]["ploidy"] == "haploid"
+    res = indel_pileups.candidates_for_chunks(snp_pileups.context(0), rs, dct, chunks, haploid=hap)
     for ci in range(len(chunks)):
-        _check(res[ci], g, ci, (name, ci, "batched"))
+        got = res[ci] if not hap else (res[ci][0], res[ci][1], res[ci][1], res[ci][1], res[ci][2], [])
+        _check(got, g, ci, (name, ci, "batched"))
 
 
 def test_indel_cnn_on_device_tensors():
@@ -59,3 +65,24 @@ def test_indel_cnn_on_device_tensors():
     got = ctx.indel_model_forward(x, haploid=False, impl=1)
     want = cnn_oracle.indel_model(tensors, x)
     assert np.abs(got - want).max() < 1e-4
+
+
+def test_call_chunk_records_match_oracle_pipeline():
+    """indel_run equivalent for one chunk: GPU scan/build/CNN + host records vs oracle tensors -> fp32 CNN -> restated records."""
+    from nanocaller_b200.host import indel_caller, sources, weights as W
+    from oracle import cnn_oracle, indel_caller_oracle, indel_oracle
+    rs, dct, chunks, g = load_indel_case("indel_ont")
+    sources.unregister_all()
+    sources.register_source("mem://bam", rs)
+    tensors, _ = W.load_model("indel", "ONT-HG002")
+    chunk = dict(chunks[0], sam_path="mem://bam")
+    got = indel_caller.call_chunk(dict(dct, fasta_path="mem://bam"), chunk, tensors)
+    pos, x0, x1, x2, alleles, phase = indel_oracle.get_indel_testing_candidates(rs, dct, chunks[0])
+    probs = cnn_oracle.indel_model(tensors, np.hstack([x0, x1, x2]).astype(np.float32))
+    want = indel_caller_oracle.diploid_records(chunks[0]["chrom"], pos, probs, alleles, phase)
+    assert len(got) == len(want) > 0
+    for a, b in zip(got, want):
+        fa, fb = a.split("\t"), b.split("\t")
+        assert fa[:5] == fb[:5] and fa[6:9] == fb[6:9], (a, b)
+        assert abs(float(fa[5]) - float(fb[5])) < 0.02
+        assert fa[9].split(":")[0] == fb[9].split(":")[0]
