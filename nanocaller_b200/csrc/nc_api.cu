@@ -481,7 +481,7 @@ int nc_decode_reads(nc_ctx* c) {
         if ((rc = read_i64(c, c->d_rowoff.as<int64_t>() + n, &c->n_row_words))) return rc;
         NC_CUDA(c->d_rows.reserve((size_t)std::max<int64_t>(c->n_row_words, 1) * 4));
         const unsigned g2 = (unsigned)std::min<int64_t>(n, (int64_t)c->sm_count * 64);
-        row_fill_kernel<<<g2, 128, 0, c->stream>>>(c->d_pos.as<int32_t>(), c->d_end.as<int32_t>(), c->d_cigar_off.as<int64_t>(),
+        row_fill_kernel<<<g2, kFillThreads, 0, c->stream>>>(c->d_pos.as<int32_t>(), c->d_end.as<int32_t>(), c->d_cigar_off.as<int64_t>(),
                                                    c->d_cigar.as<uint32_t>(), c->d_opstart.as<int2>(), c->d_seq_off.as<int64_t>(),
                                                    c->d_lseq.as<int32_t>(), c->d_seq4.as<uint8_t>(), c->d_rowoff.as<int64_t>(),
                                                    c->d_nwords.as<int32_t>(), c->d_rows.as<uint32_t>(), n);
@@ -1050,7 +1050,7 @@ int nc_debug_tc_trunk(nc_ctx* c, const float* x, int64_t n, int haploid, int sta
                            nullptr, nullptr, c->sm_count, &launches, &c->err, stage);
     c->launches += launches;
     if (rc) return rc;
-    const size_t have = stage == 1 ? (size_t)n * tcg::C2_SITE_BYTES : (size_t)((n + 127) / 128) * tcg::C3_TILE_BYTES;
+    const size_t have = stage == 1 ? (size_t)((n + 2) / 3) * tcg::C2_GROUP_BYTES : (size_t)((n + 127) / 128) * tcg::C3_TILE_BYTES;
     if (raw_bytes < have) return fail(c, NC_EINVAL, "nc_debug_tc_trunk: output buffer too small (%zu < %zu)", raw_bytes, have);
     NC_CUDA(cudaMemcpyAsync(raw, stage == 1 ? M.tc.c2.p : M.tc.c3.p, have, cudaMemcpyDeviceToHost, c->stream));
     NC_CUDA(cudaStreamSynchronize(c->stream));

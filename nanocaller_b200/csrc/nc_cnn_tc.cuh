@@ -96,6 +96,14 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xFFFFFFFF;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" :: "r"(wg + 1) : "memory"); }
 
 // SELU with the fast exponential (ex2.approx): abs error ~1e-7 on the negative branch.
@@ -171,6 +179,7 @@ constexpr int C2_PITCH = 10;
 constexpr int C2_SITE_ROWS = 4 * C2_PITCH;     // 40 rows per site and parity
 constexpr int C2_CHUNK = C2_SITE_ROWS * 16;    // 640 B per (part, parity, k-group)
 constexpr int C2_SITE_BYTES = 2 * 2 * 4 * C2_CHUNK;   // 10240 B per site in HBM
+constexpr int C2_GROUP_BYTES = 3 * C2_SITE_BYTES;      // 30720 B: three sites stored as the exact smem image of TB ([plane 16][site 3][40 rows][16 B])
 constexpr int C2_PLANE = 3 * C2_CHUNK;         // three sites stacked: 1920 B
 constexpr int C2_SMEM = 2 * 2 * 4 * C2_PLANE + 512;
 constexpr int FC_KG = 27 * 8;                  // 216 k-groups of fc1 (27 positions x 64 channels)
@@ -424,13 +433,13 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
             if (valid) {
 #pragma unroll
                 for (int i = 0; i < 32; i++) acc[i] += acc2[i];
-                uint8_t* dst = P.c2_out + site * tcg::C2_SITE_BYTES + ((w2 & 1) * 4) * tcg::C2_CHUNK + (h2 * tcg::C2_PITCH + (w2 >> 1)) * 16;
+                uint8_t* dst = P.c2_out + (site / 3) * tcg::C2_GROUP_BYTES + (int)(site % 3) * tcg::C2_CHUNK + ((w2 & 1) * 4) * tcg::C2_PLANE + (h2 * tcg::C2_PITCH + (w2 >> 1)) * 16;
 #pragma unroll
                 for (int kg = 0; kg < 4; kg++) {
                     uint4 hi, lo;
                     act_split8(acc + 8 * kg, s_bias + 48 + 8 * kg, hi, lo);
-                    *reinterpret_cast<uint4*>(dst + kg * tcg::C2_CHUNK) = hi;
-                    *reinterpret_cast<uint4*>(dst + (8 + kg) * tcg::C2_CHUNK) = lo;
+                    *reinterpret_cast<uint4*>(dst + kg * tcg::C2_PLANE) = hi;
+                    *reinterpret_cast<uint4*>(dst + (8 + kg) * tcg::C2_PLANE) = lo;
                 }
             }
         }
@@ -453,7 +462,7 @@ struct TBParams {
 };
 constexpr int TB_WGS = 3;
 constexpr int TB_THREADS = TB_WGS * 128;
-constexpr int TB_SMEM_MISC = 64 * 4 + 64;
+constexpr int TB_SMEM_MISC = 64 * 4 + 96;
 constexpr int TB_SMEM = tcg::W3_BYTES + TB_WGS * tcg::C2_SMEM + TB_SMEM_MISC + 64;
 
 __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParams P) {
@@ -461,7 +470,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
     uint8_t* s_w = smem;
     float* s_bias = reinterpret_cast<float*>(smem + tcg::W3_BYTES + TB_WGS * tcg::C2_SMEM);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 64);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
+    uint64_t* s_full = s_bar + 4;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
     const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = tid >> 5, wq = warp & 3;
     uint8_t* s_c2 = smem + tcg::W3_BYTES + wg * tcg::C2_SMEM;
 
@@ -469,7 +479,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
     if (tid < 64) s_bias[tid] = P.bias[tid];
     for (int i = tid; i < TB_WGS * tcg::C2_SMEM / 16; i += TB_THREADS) reinterpret_cast<uint4*>(smem + tcg::W3_BYTES)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
-        for (int i = 0; i < TB_WGS; i++) mbar_init(&s_bar[i], 2);
+        for (int i = 0; i < TB_WGS; i++) { mbar_init(&s_bar[i], 2); mbar_init(&s_full[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(s_tmem, 512);
@@ -481,21 +491,20 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
     const uint32_t tmem_lane = tmem + ((uint32_t)wq << 21);
     const uint32_t c216 = smem_u32(s_c2) >> 4, w16 = smem_u32(s_w) >> 4;
     const uint32_t idesc = make_idesc_f16(128, 64);
-    uint32_t phase = 0;
+    uint32_t phase = 0, lphase = 0;
     bool ok = true;
     const int64_t n_groups = (P.n_sites + 2) / 3;
+    const int64_t gstride = (int64_t)gridDim.x * TB_WGS;
+    int64_t grp = (int64_t)blockIdx.x * TB_WGS + wg;
+    if (t == 0 && grp < n_groups) {
+        mbar_expect_tx(&s_full[wg], tcg::C2_GROUP_BYTES);
+        bulk_g2s(s_c2, P.c2 + grp * tcg::C2_GROUP_BYTES, tcg::C2_GROUP_BYTES, &s_full[wg]);
+    }
 
-    for (int64_t grp = (int64_t)blockIdx.x * TB_WGS + wg; grp < n_groups; grp += (int64_t)gridDim.x * TB_WGS) {
+    for (; grp < n_groups; grp += gstride) {
         const int64_t s0 = grp * 3;
-        // ---- load: per site 16 chunks of 640 B -> plane (part, parity, kg) + s*640
-#pragma unroll 5
-        for (int i = t; i < 3 * 16 * 40; i += 128) {
-            const int s = i / 640, r = i - s * 640, ch = r / 40, q = r - ch * 40;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (s0 + s < P.n_sites) v = __ldg(reinterpret_cast<const uint4*>(P.c2 + (s0 + s) * tcg::C2_SITE_BYTES + ch * tcg::C2_CHUNK) + q);
-            *reinterpret_cast<uint4*>(s_c2 + ch * tcg::C2_PLANE + s * tcg::C2_CHUNK + q * 16) = v;
-        }
-        fence_async_smem();
+        // ---- the group's c2 image (30,720 B, already in plane layout) arrives by one TMA bulk copy
+        ok = mbar_wait(&s_full[wg], lphase) && ok; lphase ^= 1;
         tc_fence_before();
         wg_barrier(wg);
         if (wq < 2 && elect_one()) {
@@ -507,6 +516,11 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
         __syncwarp();
         ok = mbar_wait(&s_bar[wg], phase) && ok; phase ^= 1;
         tc_fence_after();
+        // the MMAs have consumed the smem image: the next group's copy overlaps the epilogue
+        if (t == 0 && grp + gstride < n_groups) {
+            mbar_expect_tx(&s_full[wg], tcg::C2_GROUP_BYTES);
+            bulk_g2s(s_c2, P.c2 + (grp + gstride) * tcg::C2_GROUP_BYTES, tcg::C2_GROUP_BYTES, &s_full[wg]);
+        }
         // ---- epilogue: row m = s*40 + h3*10 + w3 -> HBM c3 [tile][part][pos*8 + g][site % 128][8]
         {
             const int s = t / 40, r = t - s * 40, h3 = r / 10, w3 = r - h3 * 10;
@@ -559,7 +573,7 @@ struct TCParams {
 };
 constexpr int TC_STAGE_A = 2 * 8 * 2048;                    // 32768: [part][kg 8][128 rows][16 B]
 constexpr int TC_STAGE = TC_STAGE_A + tcg::WF_POS_BYTES;    // + 12288 of weights
-constexpr int TC_SMEM = 2 * TC_STAGE + 48 * 4 + 64 + 64;
+constexpr int TC_SMEM = 2 * TC_STAGE + 48 * 4 + 96 + 64;
 
 __device__ __forceinline__ void snp_tail_row(const float* x, int64_t s, const TCParams& P) {
     const TailW& w = P.tail;
@@ -599,13 +613,18 @@ __device__ __forceinline__ void snp_tail_row(const float* x, int64_t s, const TC
 __global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     float* s_bias = reinterpret_cast<float*>(smem + 2 * TC_STAGE);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 48);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_bias + 48);      // [2] TMA bytes landed
+    uint64_t* s_empty = s_full + 2;                                    // [2] MMAs that read the stage have completed
+    uint64_t* s_done = s_empty + 2;                                    // every MMA of the tile has completed
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_done + 1);
     const int t = threadIdx.x, warp = t >> 5;
     const int64_t tile = blockIdx.x;
 
     if (t < 48) s_bias[t] = P.bias[t];
-    if (t == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (t == 0) {
+        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(&s_empty[0], 1); mbar_init(&s_empty[1], 1); mbar_init(s_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (warp == 0) tmem_alloc(s_tmem, 64);
     tc_fence_before();
     __syncthreads();
@@ -616,45 +635,45 @@ __global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
     const uint8_t* a_src = P.c3 + tile * (int64_t)tcg::C3_TILE_BYTES;
     bool ok = true;
 
-    auto load_stage = [&](int pos) {
-        uint8_t* st = smem + (pos & 1) * TC_STAGE;
-        // A: per part 8 k-groups x 2048 B contiguous in HBM at k-group pos*8
-#pragma unroll 4
-        for (int i = t; i < TC_STAGE_A / 16; i += 128) {
-            const int part = i >> 10, r = i & 1023;
-            reinterpret_cast<uint4*>(st)[i] = __ldg(reinterpret_cast<const uint4*>(a_src + ((int64_t)part * tcg::FC_KG + pos * 8) * 2048) + r);
-        }
-        const uint4* wsrc = reinterpret_cast<const uint4*>(P.wimg + (int64_t)pos * tcg::WF_POS_BYTES);
-#pragma unroll 3
-        for (int i = t; i < tcg::WF_POS_BYTES / 16; i += 128) reinterpret_cast<uint4*>(st + TC_STAGE_A)[i] = __ldg(wsrc + i);
-    };
-
-    load_stage(0);
-    for (int pos = 0; pos < 27; pos++) {
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (warp == 0 && elect_one()) {
-            tc_fence_after();
-            const uint32_t sb16 = smem_u32(smem + (pos & 1) * TC_STAGE) >> 4;
-            const uint32_t bhi = (sb16 + TC_STAGE_A / 16) | (48u << 16);
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const uint32_t a_hi = sb16 + (2 * c) * 128 + (128u << 16), a_lo = a_hi + 8 * 128;
-                umma_f16(tmem, sdesc16(a_hi), sdesc16(bhi + c * 96), idesc, (pos > 0 || c > 0) ? 1u : 0u);
-                umma_f16(tmem, sdesc16(a_lo), sdesc16(bhi + c * 96), idesc, 1u);
-                umma_f16(tmem, sdesc16(a_hi), sdesc16(bhi + (4 + c) * 96), idesc, 1u);
+    if (warp == 0) {
+        // ===== TMA producer: per position two 16 KB slabs of activations (hi, lo) and 12 KB of weights
+        if (elect_one()) {
+            for (int pos = 0; pos < 27; pos++) {
+                const int st = pos & 1;
+                if (pos >= 2) ok = mbar_wait(&s_empty[st], ((pos >> 1) - 1) & 1) && ok;
+                uint8_t* dst = smem + st * TC_STAGE;
+                mbar_expect_tx(&s_full[st], TC_STAGE);
+                bulk_g2s(dst, a_src + (int64_t)(pos * 8) * 2048, 16384, &s_full[st]);
+                bulk_g2s(dst + 16384, a_src + ((int64_t)tcg::FC_KG + pos * 8) * 2048, 16384, &s_full[st]);
+                bulk_g2s(dst + TC_STAGE_A, P.wimg + (int64_t)pos * tcg::WF_POS_BYTES, tcg::WF_POS_BYTES, &s_full[st]);
             }
-            umma_commit(&s_bar[pos & 1]);
         }
         __syncwarp();
-        if (pos + 1 < 27) {
-            if (pos >= 1) ok = mbar_wait(&s_bar[(pos + 1) & 1], ((pos - 1) >> 1) & 1) && ok;   // MMAs of pos-1 released that stage
-            load_stage(pos + 1);
+    } else if (warp == 1) {
+        // ===== MMA issuer
+        if (elect_one()) {
+            for (int pos = 0; pos < 27; pos++) {
+                const int st = pos & 1;
+                ok = mbar_wait(&s_full[st], (pos >> 1) & 1) && ok;
+                tc_fence_after();
+                const uint32_t sb16 = smem_u32(smem + st * TC_STAGE) >> 4;
+                const uint32_t bhi = (sb16 + TC_STAGE_A / 16) | (48u << 16);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint32_t a_hi = sb16 + (2 * c) * 128 + (128u << 16), a_lo = a_hi + 8 * 128;
+                    umma_f16(tmem, sdesc16(a_hi), sdesc16(bhi + c * 96), idesc, (pos > 0 || c > 0) ? 1u : 0u);
+                    umma_f16(tmem, sdesc16(a_lo), sdesc16(bhi + c * 96), idesc, 1u);
+                    umma_f16(tmem, sdesc16(a_hi), sdesc16(bhi + (4 + c) * 96), idesc, 1u);
+                }
+                umma_commit(&s_empty[st]);
+            }
+            umma_commit(s_done);
         }
+        __syncwarp();
     }
-    ok = mbar_wait(&s_bar[0], 1) && ok;          // pos 26: 14th completion of stage 0 -> parity 1
-    ok = mbar_wait(&s_bar[1], 0) && ok;          // pos 25: 13th completion of stage 1 -> parity 0
+    // ===== epilogue (all four warps).  A dedicated barrier: warps 2 and 3 get here before the first MMA, and a parity-1
+    // wait on a fresh mbarrier passes immediately.
+    ok = mbar_wait(s_done, 0) && ok;
     tc_fence_after();
     {
         float x[48];
@@ -669,7 +688,7 @@ __global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
             snp_tail_row(x, s, P);
         }
     }
-    if (!ok && t == 0) atomicExch(P.err, 1);
+    if (!ok) atomicExch(P.err, 1);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 64);
@@ -898,7 +917,7 @@ inline int tc_forward_ex(cudaStream_t stream, TcModel& T, int in_mode, const voi
     auto cuda_fail = [&](cudaError_t e, const char* what) { if (err) *err = std::string(what) + ": " + cudaGetErrorString(e); return NC_ECUDA; };
     cudaError_t e;
     const int64_t n_tiles = (n + 127) / 128;
-    if ((e = T.c2.reserve((size_t)n * C2_SITE_BYTES)) != cudaSuccess) return cuda_fail(e, "c2 alloc");
+    if ((e = T.c2.reserve((size_t)((n + 2) / 3) * C2_GROUP_BYTES)) != cudaSuccess) return cuda_fail(e, "c2 alloc");
     if ((e = T.c3.reserve((size_t)n_tiles * C3_TILE_BYTES)) != cudaSuccess) return cuda_fail(e, "c3 alloc");
     static bool attr_set = false;
     if (!attr_set) {

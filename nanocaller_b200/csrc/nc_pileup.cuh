@@ -189,7 +189,13 @@ __global__ void __launch_bounds__(1024) prefix_max_kernel(const int32_t* __restr
 // ------------------------------------------------------------------------------------------------
 constexpr uint64_t kNibToCode = 0x4444444244414304ull;
 
-__global__ void __launch_bounds__(128) row_fill_kernel(const int32_t* __restrict__ pos, const int32_t* __restrict__ end,
+// One CTA per read, one thread per output word.  Threads first build, in shared memory, a coarse index (the op
+// containing every 256th position: one full binary search per 32 words), then every thread narrows its own search to
+// the ops between two index entries, walks its 8 positions, and fetches the 8 bases with independent loads.
+constexpr int kFillThreads = 128;
+constexpr int kFillIdx = 512;            // coarse index entries kept in shared memory (reads up to 131 kb; longer: global search)
+
+__global__ void __launch_bounds__(kFillThreads) row_fill_kernel(const int32_t* __restrict__ pos, const int32_t* __restrict__ end,
                                                        const int64_t* __restrict__ cigar_off,
                                                        const uint32_t* __restrict__ cigar,
                                                        const int2* __restrict__ opstart,
@@ -199,6 +205,7 @@ __global__ void __launch_bounds__(128) row_fill_kernel(const int32_t* __restrict
                                                        const int64_t* __restrict__ rowoff,
                                                        const int32_t* __restrict__ nwords,
                                                        uint32_t* __restrict__ rows, int64_t n_reads) {
+    __shared__ int32_t s_idx[kFillIdx + 1];
     for (int64_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
         const int32_t nw = nwords[r];
         if (nw == 0) continue;
@@ -208,20 +215,33 @@ __global__ void __launch_bounds__(128) row_fill_kernel(const int32_t* __restrict
         const int32_t lseq = l_seq[r];
         const uint8_t* __restrict__ sq = seq4 + seq_off[r];
         uint32_t* __restrict__ out = rows + rowoff[r];
-        for (int32_t w = threadIdx.x; w < nw; w += blockDim.x) {
+        const int32_t nblk = min((nw + 31) >> 5, kFillIdx);
+        __syncthreads();                                        // previous read's index no longer in use
+        for (int32_t b = threadIdx.x; b <= nblk; b += kFillThreads) {
+            // last op whose reference start is <= offset of word 32*b (upper bound for b == nblk: last op)
+            const int32_t os = min(max(a0 + 256 * b - p0, 0), span);
+            int32_t lo = 0, hi = nops;
+            while (lo < hi) { int32_t mid = (lo + hi) >> 1; if (__ldg(&opstart[c0 + mid].x) <= os) lo = mid + 1; else hi = mid; }
+            s_idx[b] = lo - 1;
+        }
+        __syncthreads();
+        for (int32_t w = threadIdx.x; w < nw; w += kFillThreads) {
             const int32_t o = a0 + 8 * w - p0;                 // read-relative offset of nibble 0, in [-7, span)
             const int32_t os = o < 0 ? 0 : o;
-            int32_t lo = 0, hi = nops;                         // last op whose reference start is <= os
+            const int32_t b = w >> 5;
+            int32_t lo, hi;                                    // search window: ops between two coarse index entries
+            if (b < nblk) { lo = s_idx[b]; hi = min(s_idx[b + 1] + 1, nops); } else { lo = s_idx[nblk]; hi = nops; }
+            lo = max(lo, 0);
             while (lo < hi) { int32_t mid = (lo + hi) >> 1; if (__ldg(&opstart[c0 + mid].x) <= os) lo = mid + 1; else hi = mid; }
             int32_t k = lo - 1;
             uint32_t cw = __ldg(cigar + c0 + k);
             int2 st = __ldg(opstart + c0 + k);
             int32_t rl = cig_ref_len(cw);
-            uint32_t word = 0;
+            int32_t qi[8];                                     // query index per position; -1: '*' (D / N / bad base), -2: not covered
 #pragma unroll
             for (int t = 0; t < 8; t++) {
                 const int32_t oo = o + t;
-                uint32_t nib = 15u;
+                qi[t] = -2;
                 if (oo >= 0 && oo < span) {
                     while (oo >= st.x + rl) {                  // terminates: oo < span = total reference length
                         k++;
@@ -229,15 +249,20 @@ __global__ void __launch_bounds__(128) row_fill_kernel(const int32_t* __restrict
                         st = __ldg(opstart + c0 + k);
                         rl = cig_ref_len(cw);
                     }
-                    nib = 4u;                                  // D / N: '*' (appendix C.4); also the default for bad bases
-                    if (cig_is_match(cw)) {
-                        const int32_t q = st.y + (oo - st.x);
-                        if (q < lseq) {
-                            const uint32_t b = __ldg(sq + (q >> 1));
-                            const uint32_t bn = (q & 1) ? (b & 15u) : (b >> 4);
-                            nib = (uint32_t)(kNibToCode >> (4 * bn)) & 15u;
-                        }
-                    }
+                    const int32_t q = st.y + (oo - st.x);
+                    qi[t] = (cig_is_match(cw) && q < lseq) ? q : -1;
+                }
+            }
+            uint32_t bb[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) bb[t] = qi[t] >= 0 ? (uint32_t)__ldg(sq + (qi[t] >> 1)) : 0u;
+            uint32_t word = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                uint32_t nib = qi[t] == -2 ? 15u : 4u;
+                if (qi[t] >= 0) {
+                    const uint32_t bn = (qi[t] & 1) ? (bb[t] & 15u) : (bb[t] >> 4);
+                    nib = (uint32_t)(kNibToCode >> (4 * bn)) & 15u;
                 }
                 word |= nib << (4 * t);
             }

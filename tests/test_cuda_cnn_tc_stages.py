@@ -50,7 +50,9 @@ def test_trunk_stages_match_oracle():
     x = snp_oracle.scale_counts(w0["mat"][:n], meta["train_coverage"], coverage=float(w0["depth"]))
     want_c2, want_c3 = _oracle_acts(tensors, x)
 
-    raw = _trunk(x, n, 1, n * 10240).view(np.float16).reshape(n, 2, 2, 4, 40, 8).astype(np.float32)
+    groups = (n + 2) // 3                                       # c2 in HBM = TB's smem image: [group][part][parity][kg][site % 3][40 rows][8]
+    raw = _trunk(x, n, 1, groups * 30720).view(np.float16).reshape(groups, 2, 2, 4, 3, 40, 8).astype(np.float32)
+    raw = np.transpose(raw, (0, 4, 1, 2, 3, 5, 6)).reshape(groups * 3, 2, 2, 4, 40, 8)[:n]
     v = raw[:, 0] + raw[:, 1]                                   # [n, parity, kg, row, 8]
     got_c2 = np.zeros((n, 4, 20, 32), np.float32)
     for h in range(4):
