@@ -1,0 +1,194 @@
+"""BAM / BGZF / FASTA readers and writers producing the BAM-native arrays the device stager consumes
+(replaces pysam.Samfile / FastaFile opening at generate_SNP_pileups.py:134-137).
+
+Pure host code (zlib only): BGZF is a series of gzip members, BAM records are parsed into one `ReadSet` per contig with
+CIGAR words and 4-bit bases copied verbatim (they already are the staging format), HP / PS integer tags extracted for
+the indel path.  The writer exists so tests and the synthetic generator can produce real files."""
+import gzip
+import os
+import struct
+import zlib
+
+import numpy as np
+
+from .readset import ReadSet
+
+_BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def bgzf_compress(data, level=4):
+    """bytes -> BGZF stream (64 KiB blocks with the BC extra field, plus the EOF marker)."""
+    out = []
+    for off in range(0, len(data), 0xff00):
+        chunk = data[off:off + 0xff00]
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        body = co.compress(chunk) + co.flush()
+        bsize = len(body) + 25
+        out.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize) + body +
+                   struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+    out.append(_BGZF_EOF)
+    return b"".join(out)
+
+
+def bgzf_decompress(path):
+    with gzip.open(path, "rb") as f:          # gzip handles concatenated members
+        return f.read()
+
+
+def write_bam(path, readsets, header_text=None):
+    """Write coordinate-sorted ReadSets (one per contig) as a BAM file.  qual is written as 0xff (absent)."""
+    text = header_text or ("@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % (rs.chrom, rs.contig_len) for rs in readsets))
+    parts = [b"BAM\x01", struct.pack("<i", len(text)), text.encode(), struct.pack("<i", len(readsets))]
+    for rs in readsets:
+        nm = rs.chrom.encode() + b"\0"
+        parts += [struct.pack("<i", len(nm)), nm, struct.pack("<i", rs.contig_len)]
+    for rid, rs in enumerate(readsets):
+        ends = rs.ref_end
+        for i in range(rs.n):
+            name = rs.qname(i).encode() + b"\0"
+            cig = rs.cigar[rs.cigar_off[i]:rs.cigar_off[i + 1]]
+            seq = rs.seq4[rs.seq_off[i]:rs.seq_off[i + 1]]
+            l_seq = int(rs.l_seq[i])
+            aux = b""
+            if rs.hp[i] > 0:
+                aux = b"HPC" + struct.pack("<B", int(rs.hp[i])) + b"PSi" + struct.pack("<i", int(rs.ps[i]))
+            pos = int(rs.pos[i])
+            bin_ = _reg2bin(pos, max(pos + 1, int(ends[i])))
+            core = struct.pack("<iiBBHHHiiii", rid, pos, len(name), 60, bin_, len(cig), int(rs.flag[i]), l_seq, -1, -1, 0)
+            body = core + name + cig.astype("<u4").tobytes() + seq.tobytes()[:(l_seq + 1) // 2] + b"\xff" * l_seq + aux
+            parts.append(struct.pack("<i", len(body)) + body)
+    with open(path, "wb") as f:
+        f.write(bgzf_compress(b"".join(parts)))
+
+
+def _reg2bin(beg, end):
+    end -= 1
+    for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        if beg >> shift == end >> shift:
+            return base + (beg >> shift)
+    return 0
+
+
+_AUX_FIXED = {ord("A"): 1, ord("c"): 1, ord("C"): 1, ord("s"): 2, ord("S"): 2, ord("i"): 4, ord("I"): 4, ord("f"): 4}
+_AUX_FMT = {ord("c"): "<b", ord("C"): "<B", ord("s"): "<h", ord("S"): "<H", ord("i"): "<i", ord("I"): "<I"}
+
+
+def _aux_ints(buf, off, end, want=(b"HP", b"PS")):
+    """Integer values of the wanted aux tags of one record."""
+    out = {}
+    while off + 3 <= end:
+        tag, typ = bytes(buf[off:off + 2]), buf[off + 2]
+        off += 3
+        if typ in _AUX_FIXED:
+            if tag in want and typ in _AUX_FMT:
+                out[tag] = struct.unpack_from(_AUX_FMT[typ], buf, off)[0]
+            off += _AUX_FIXED[typ]
+        elif typ in (ord("Z"), ord("H")):
+            off = buf.index(b"\0", off) + 1
+        elif typ == ord("B"):
+            sub = buf[off]
+            n = struct.unpack_from("<i", buf, off + 1)[0]
+            off += 5 + n * _AUX_FIXED.get(sub, 1)
+        else:
+            break
+    return out
+
+
+def read_bam(path, fasta=None, contigs=None):
+    """-> (list of ReadSet in header order, header text).  `fasta`: {contig: uint8 array}; contigs without a reference
+    get an all-'N' reference.  Unmapped records (refID < 0) are dropped.  Records must be coordinate-sorted."""
+    buf = bgzf_decompress(path)
+    if buf[:4] != b"BAM\x01":
+        raise ValueError("%s: not a BAM file" % path)
+    l_text = struct.unpack_from("<i", buf, 4)[0]
+    text = buf[8:8 + l_text].decode(errors="replace")
+    off = 8 + l_text
+    n_ref = struct.unpack_from("<i", buf, off)[0]
+    off += 4
+    refs = []
+    for _ in range(n_ref):
+        ln = struct.unpack_from("<i", buf, off)[0]
+        name = buf[off + 4:off + 4 + ln - 1].decode()
+        lref = struct.unpack_from("<i", buf, off + 4 + ln)[0]
+        refs.append((name, lref))
+        off += 8 + ln
+    per = [dict(pos=[], flag=[], lseq=[], cig=[], seq=[], hp=[], ps=[], qn=[]) for _ in refs]
+    n = len(buf)
+    mv = memoryview(buf)
+    while off + 4 <= n:
+        bs = struct.unpack_from("<i", buf, off)[0]
+        rec = off + 4
+        rid, pos, l_name, _mq, _bin, n_cig, flag, l_seq = struct.unpack_from("<iiBBHHHi", buf, rec)
+        off = rec + bs
+        if rid < 0 or (contigs is not None and refs[rid][0] not in contigs):
+            continue
+        p = rec + 32
+        qn = bytes(mv[p:p + l_name - 1]).decode()
+        p += l_name
+        cig = np.frombuffer(buf, "<u4", n_cig, p)
+        p += 4 * n_cig
+        nb = (l_seq + 1) // 2
+        seq = np.frombuffer(buf, np.uint8, nb, p)
+        p += nb + l_seq
+        tags = _aux_ints(buf, p, off)
+        d = per[rid]
+        d["pos"].append(pos); d["flag"].append(flag); d["lseq"].append(l_seq); d["cig"].append(cig); d["seq"].append(seq)
+        d["hp"].append(tags.get(b"HP", 0)); d["ps"].append(tags.get(b"PS", 0)); d["qn"].append(qn)
+    out = []
+    for (name, lref), d in zip(refs, per):
+        if contigs is not None and name not in contigs:
+            continue
+        cl = np.array([len(c) for c in d["cig"]], np.int64)
+        sl = np.array([len(s) for s in d["seq"]], np.int64)
+        cig_off = np.concatenate([[0], np.cumsum(cl)]).astype(np.int64)
+        seq_off = np.concatenate([[0], np.cumsum(sl)]).astype(np.int64)
+        cigar = np.concatenate(d["cig"]) if d["cig"] else np.zeros(0, np.uint32)
+        seq4 = np.concatenate(d["seq"]) if d["seq"] else np.zeros(0, np.uint8)
+        ref = fasta.get(name) if fasta else None
+        if ref is None:
+            ref = np.full(lref, ord("N"), np.uint8)
+        out.append(ReadSet(name, ref, d["pos"], d["flag"], cig_off, cigar, seq_off, d["lseq"], seq4, d["hp"], d["ps"], d["qn"]))
+    return out, text
+
+
+def read_fasta(path):
+    """-> {contig: uint8 array of the sequence bytes, case preserved} (plain or gzip/BGZF-compressed FASTA)."""
+    opener = gzip.open if open(path, "rb").read(2) == b"\x1f\x8b" else open
+    out, name, chunks = {}, None, []
+    with opener(path, "rb") as f:
+        for line in f:
+            if line.startswith(b">"):
+                if name is not None:
+                    out[name] = np.frombuffer(b"".join(chunks), np.uint8).copy()
+                name, chunks = line[1:].split()[0].decode(), []
+            else:
+                chunks.append(line.strip())
+    if name is not None:
+        out[name] = np.frombuffer(b"".join(chunks), np.uint8).copy()
+    return out
+
+
+def write_fasta(path, readsets, width=60):
+    with open(path, "wb") as f:
+        for rs in readsets:
+            f.write(b">" + rs.chrom.encode() + b"\n")
+            b = rs.ref.tobytes()
+            for i in range(0, len(b), width):
+                f.write(b[i:i + width] + b"\n")
+    with open(path + ".fai", "w") as f:
+        off = 0
+        for rs in readsets:
+            off += len(rs.chrom) + 2
+            f.write("%s\t%d\t%d\t%d\t%d\n" % (rs.chrom, rs.contig_len, off, width, width + 1))
+            off += rs.contig_len + (rs.contig_len + width - 1) // width
+
+
+def open_alignment(sam_path, fasta_path):
+    """Parse `sam_path` (BAM) and `fasta_path` once and register the contigs as an alignment source."""
+    from . import sources
+    if not os.path.exists(sam_path):
+        raise FileNotFoundError(sam_path)
+    fasta = read_fasta(fasta_path) if fasta_path and os.path.exists(fasta_path) else None
+    readsets, _ = read_bam(sam_path, fasta)
+    sources.register_source(sam_path, readsets)
+    return readsets

@@ -26,7 +26,20 @@ def unregister_all():
     _BEDS.clear()
 
 
+_FASTA_FOR = {}
+
+
+def attach_fasta(sam_path, fasta_path):
+    """Remember which FASTA goes with a BAM path (the reference passes both in `dct`)."""
+    _FASTA_FOR[sam_path] = fasta_path
+
+
 def resolve(sam_path, chrom):
+    if sam_path not in _REGISTRY:
+        import os
+        if os.path.exists(sam_path):               # a real BAM on disk: parse once, keep per-contig arrays
+            from . import bamio
+            bamio.open_alignment(sam_path, _FASTA_FOR.get(sam_path))
     try:
         return _REGISTRY[sam_path][chrom]
     except KeyError:

@@ -1,0 +1,57 @@
+"""VCF assembly: header lines of snpCaller.call_manager (snpCaller.py:259-276) and
+indelCaller.call_manager (indelCaller.py:373-383), coordinate sort (what `bcftools sort` does to the concatenated
+per-process files), PASS filter (`bcftools view -f PASS`, snpCaller.py:285) and BGZF output.  No CSI/tabix index is
+written (not on the measured path)."""
+from .bamio import bgzf_compress
+
+SNP_HEADER = (
+    '##fileformat=VCFv4.2\n'
+    '##FILTER=<ID=PASS,Description="All filters passed">\n'
+    '##FILTER=<ID=LOW,Description="All alleles have probability less than 50%.">\n'
+    '##FILTER=<ID=REF,Description="Homozygous Reference. Only reference allele has greater than 50% probability. All alternative alleles having probability less than 50%.">\n'
+    '{contigs}'
+    '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">\n'
+    '##FORMAT=<ID=DP,Number=1,Type=Integer,Description="Depth">\n'
+    '##FORMAT=<ID=AD,Number=R,Type=Integer,Description="Allelic depths for the ref and alt alleles in the order listed">\n'
+    '##FORMAT=<ID=ADF,Number=R,Type=Integer,Description="Allelic depths on forward strand for the ref and alt alleles in the order listed">\n'
+    '##FORMAT=<ID=ADR,Number=R,Type=Integer,Description="Allelic depths on reverse strand for the ref and alt alleles in the order listed">\n'
+    '##FORMAT=<ID=VF,Number=A,Type=Float,Description="Alternative allele frequency in the order listed">\n'
+    '##INFO=<ID=PR,Number=4,Type=Float,Description="Probability of presence of alleles A, C, G and T, in the given order. Probability of each base is out of 1, independent of each other.">\n'
+    '##INFO=<ID=FQ,Number=1,Type=Float,Description="Maximum frequency of non-reference base.">\n'
+    '#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t{sample}\n')
+
+INDEL_HEADER = (
+    '##fileformat=VCFv4.2\n'
+    '##FILTER=<ID=PASS,Description="All filters passed">\n'
+    '{contigs}'
+    '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">\n'
+    '##FORMAT=<ID=GQ,Number=1,Type=Float,Description="Genotype Probability">\n'
+    '##FORMAT=<ID=PS,Number=1,Type=Integer,Description="Phase set identifier">\n'
+    '#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t{sample}\n')
+
+
+def header(kind, contigs, sample="SAMPLE"):
+    """`contigs` in the order to print (the reference iterates a Python set for SNPs — order unspecified)."""
+    tmpl = SNP_HEADER if kind == "snps" else INDEL_HEADER
+    return tmpl.format(contigs="".join("##contig=<ID=%s>\n" % c for c in contigs), sample=sample)
+
+
+def sort_records(lines, contigs):
+    """Stable coordinate sort by (contig order, POS): duplicates from shared chunk boundaries are both kept, like bcftools sort."""
+    rank = {c: i for i, c in enumerate(contigs)}
+
+    def key(ln):
+        f = ln.split("\t", 2)
+        return rank.get(f[0], len(rank)), int(f[1])
+    return sorted(lines, key=key)
+
+
+def pass_only(lines):
+    return [ln for ln in lines if ln.split("\t", 7)[6] == "PASS"]
+
+
+def write_vcf(path, kind, contigs, lines, sample="SAMPLE"):
+    """Write header + sorted records; BGZF-compressed when the path ends in .gz."""
+    data = (header(kind, contigs, sample) + "".join(sort_records(lines, contigs))).encode()
+    with open(path, "wb") as f:
+        f.write(bgzf_compress(data) if path.endswith(".gz") else data)

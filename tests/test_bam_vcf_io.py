@@ -1,0 +1,55 @@
+"""CPU: BAM/BGZF/FASTA round trip into the staging arrays, and VCF header / sort / PASS filter / BGZF output."""
+import gzip
+import os
+
+import numpy as np
+
+from nanocaller_b200.host import bamio, sources, vcfio
+from nanocaller_b200.synth import make_world
+from tests.golden.cases import _handmade
+
+
+def _same(a, b):
+    for k in ("pos", "flag", "cigar_off", "cigar", "seq_off", "l_seq", "seq4", "hp", "ps", "ref"):
+        np.testing.assert_array_equal(getattr(a, k), getattr(b, k), err_msg=k)
+
+
+def test_bam_fasta_round_trip(tmp_path):
+    rs1 = make_world(chrom="chrA", preset="ont", contig_len=30_000, seed=3, coverage=8.0, indel_every=900, indel_maxlen=9,
+                     junk_frac=0.05, untagged_frac=0.2).reads
+    rs2 = _handmade()
+    bam, fa = str(tmp_path / "x.bam"), str(tmp_path / "x.fa")
+    bamio.write_bam(bam, [rs1, rs2])
+    bamio.write_fasta(fa, [rs1, rs2])
+    raw = open(bam, "rb").read()
+    assert raw[:4] == b"\x1f\x8b\x08\x04" and raw.endswith(bamio._BGZF_EOF)
+    got, text = bamio.read_bam(bam, bamio.read_fasta(fa))
+    assert [g.chrom for g in got] == ["chrA", "tiny"] and "@SQ\tSN:chrA" in text
+    # the handmade set has no tags for junk twins etc.; ps is only defined where hp > 0
+    for a, b in zip(got, [rs1, rs2]):
+        b2 = b
+        b2.ps = np.where(b.hp > 0, b.ps, 0).astype(np.int32)
+        _same(a, b2)
+    # path-based resolution used by the drop-in functions
+    sources.unregister_all()
+    sources.attach_fasta(bam, fa)
+    r = sources.resolve(bam, "tiny")
+    assert r.n == rs2.n and r.checksum() == got[1].checksum()
+
+
+def test_vcf_writer(tmp_path):
+    lines = ["chr2\t50\t.\tA\tG\t10.000\tPASS\tPR=0.1000,0.1000,0.9000,0.1000;FQ=0.5000\tGT:DP:VF:AD:ADF:ADR\t1/1:9:0.5:1,2:1,1:0,1\n",
+             "chr1\t70\t.\tC\t.\t3.000\tREF\tPR=0.1000,0.9000,0.1000,0.1000;FQ=0.2000\tGT:DP:VF:AD:ADF:ADR\t./.:9:.:.:.:.\n",
+             "chr1\t20\t.\tT\tA\t30.000\tPASS\tPR=0.9000,0.1000,0.1000,0.6000;FQ=0.4000\tGT:DP:VF:AD:ADF:ADR\t0/1:9:0.4:5,4:2,2:3,2\n",
+             "chr1\t20\t.\tT\tA\t31.000\tPASS\tPR=0.9000,0.1000,0.1000,0.6000;FQ=0.4000\tGT:DP:VF:AD:ADF:ADR\t0/1:9:0.4:5,4:2,2:3,2\n"]
+    s = vcfio.sort_records(lines, ["chr1", "chr2"])
+    assert [x.split("\t")[:2] for x in s] == [["chr1", "20"], ["chr1", "20"], ["chr1", "70"], ["chr2", "50"]]
+    assert s[0].split("\t")[5] == "30.000"                           # stable: boundary duplicates keep their order
+    assert len(vcfio.pass_only(s)) == 3
+    p = str(tmp_path / "o.vcf.gz")
+    vcfio.write_vcf(p, "snps", ["chr1", "chr2"], lines, sample="S1")
+    txt = gzip.open(p, "rt").read()
+    assert txt.startswith("##fileformat=VCFv4.2\n") and "##contig=<ID=chr1>\n##contig=<ID=chr2>\n" in txt
+    assert txt.splitlines()[-5].endswith("FORMAT\tS1") and txt.endswith(s[-1])
+    h = vcfio.header("indels", ["chr1"])
+    assert "ID=GQ" in h and "ID=PS" in h and "LOW" not in h
