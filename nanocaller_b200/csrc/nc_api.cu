@@ -1011,7 +1011,7 @@ int nc_nw_trace(const uint8_t* q, int32_t n, const uint8_t* r, int32_t m, int32_
 // ---- development probes (not part of the public header) -------------------------------------------------
 int nc_debug_umma(nc_ctx* c, const void* a_img, int a_bytes, const void* b_img, int b_bytes, const void* prog, int n_ops,
                   int N, int ncols, float* out) {
-    if (!c || !a_img || !b_img || !prog || !out || a_bytes % 16 || b_bytes % 16 || ncols % 16 || ncols > 64) return fail(c, NC_EINVAL, "nc_debug_umma: bad argument");
+    if (!c || !a_img || !b_img || !prog || !out || a_bytes % 16 || b_bytes % 16 || ncols % 16 || ncols > 128) return fail(c, NC_EINVAL, "nc_debug_umma: bad argument");
     NC_CUDA(cudaSetDevice(c->device));
     DevBuf da, db, dp, dout, derr;
     int rc = NC_OK;

@@ -19,6 +19,8 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <utility>
+
 #include "nc_common.cuh"
 #include "nc_cnn.cuh"
 
@@ -151,15 +153,18 @@ __device__ __forceinline__ void act_split8(const float* acc, const float* bias, 
 
 // One MMA of a layer's "program": where its A rows start, how its two K groups are spaced, which
 // B tile it multiplies and which accumulator columns it adds into.
-struct MmaOp { uint32_t a_off, a_lbo, b_off, misc; };     // misc: bits 0-9 D column, bit 15 accumulate
+struct MmaOp { uint32_t a_off, a_lbo, b_off, misc; };     // misc: bits 0-9 D column, bit 14 B LBO = 0, bit 15 accumulate, bits 16-23 N/8 override
 constexpr uint32_t kOpAcc = 1u << 15;
+constexpr uint32_t kOpBLbo0 = 1u << 14;
 
 __device__ __forceinline__ void issue_program(const MmaOp* prog, int n_ops, uint32_t a_base, uint32_t w_base, uint32_t b_lbo,
                                               uint32_t d_base, uint32_t idesc) {
     for (int i = 0; i < n_ops; i++) {
         const MmaOp op = prog[i];
+        const uint32_t n8 = (op.misc >> 16) & 0xFFu;
+        const uint32_t id = n8 ? ((idesc & ~(0x3Fu << 17)) | (n8 << 17)) : idesc;
         umma_f16(d_base + (op.misc & 0x3FFu), make_sdesc(a_base + op.a_off, op.a_lbo, 128u),
-                 make_sdesc(w_base + op.b_off, b_lbo, 128u), idesc, (op.misc & kOpAcc) ? 1u : 0u);
+                 make_sdesc(w_base + op.b_off, (op.misc & kOpBLbo0) ? 0u : b_lbo, 128u), id, (op.misc & kOpAcc) ? 1u : 0u);
     }
 }
 
@@ -184,71 +189,80 @@ constexpr int C2_PLANE = 3 * C2_CHUNK;         // three sites stacked: 1920 B
 constexpr int C2_SMEM = 2 * 2 * 4 * C2_PLANE + 512;
 constexpr int FC_KG = 27 * 8;                  // 216 k-groups of fc1 (27 positions x 64 channels)
 constexpr int C3_TILE_BYTES = 2 * FC_KG * 128 * 16;   // 884736 B per 128-site tile in HBM
-constexpr int TA_WBYTES = (35 + 19) * 512 + 54 * 0;   // conv1 tiles; conv2 tiles follow
-constexpr int W1_BYTES = (35 + 19) * 512;      // 27648
-constexpr int W2_BYTES = 36 * 1024;            // 6 taps x 3 K-chunks x (hi, lo) tiles of [32 x 16]
-constexpr int W3_BYTES = 24 * 2048;            // 6 taps x 2 K-chunks x (hi, lo) tiles of [64 x 16]
-constexpr int WF_POS_BYTES = 8 * 1536;         // per position: 4 K-chunks x (hi, lo) tiles of [48 x 16]
-constexpr int N_OPS1 = 54, N_OPS2 = 54, N_OPS3 = 36, N_OPSF = 12;
+
+// What one MMA costs (measured, tools/umma_rate.cu): M = 128, K = 16, operands in shared memory, any N <= 128:
+// 32 + N/4 cycles, i.e. (A bytes + B bytes) / 128 B per clock -- the tensor pipe is never the limit here, the operand
+// reads are.  So the layer programs minimise the number of A reads: the hi/lo weight halves sit side by side in one
+// wider B tile ([w_hi | w_lo] rows), and conv1 merges its three branches into one tile per 5x5 tap.
+//
+// conv1: per 5x5 tap (kh, kw) one MMA  (a_hi | a_lo) x B  with B's LBO = 0 (both K groups read the same weight
+// group), giving (a_hi + a_lo) w_hi and (a_hi + a_lo) w_lo in adjacent accumulator columns.  Accumulator columns
+//   [0,16) 1x5 hi  [16,32) 1x5 lo  [32,48) 5x5 hi  [48,64) 5x5 lo  [64,80) 5x1 hi  [80,96) 5x1 lo
+// and the 1x5 / 5x1 branches only have taps on the cross kh == 2 / kw == 2:
+//   centre  N = 96 at column 0     row taps (kh == 2)  N = 64 at column 0
+//   column taps (kw == 2)  N = 64 at column 32          the other 16 taps  N = 32 at column 32
+__host__ __device__ constexpr int c1_tap_n(int t) { return t == 12 ? 96 : (t / 5 == 2 || t % 5 == 2) ? 64 : 32; }
+__host__ __device__ constexpr int c1_tap_dcol(int t) { return t / 5 == 2 ? 0 : 32; }
+__host__ __device__ constexpr int c1_tap_off16(int t) { int o = 0; for (int i = 0; i < t; i++) o += c1_tap_n(i); return o; }   // 16-byte units
+constexpr int W1_BYTES = c1_tap_off16(25) * 16;            // 17920: one 16-byte row (8 input-channel slots) per accumulator column
+constexpr int W2_TILE = 2 * 64 * 16;                        // conv2 per (tap, 16-channel chunk): [k-group 2][w_hi 32 | w_lo 32 rows][16 B]
+constexpr int W2_BYTES = 18 * W2_TILE;                      // 36864
+constexpr int W3_TILE = 2 * 128 * 16;                       // conv3 per (tap, chunk): [k-group 2][w_hi 64 | w_lo 64 rows][16 B]
+constexpr int W3_BYTES = 12 * W3_TILE;                      // 49152
+constexpr int WF_TILE = 2 * 96 * 16;                        // fc1 per (position, chunk): [k-group 2][w_hi 48 | w_lo 48 rows][16 B]
+constexpr int WF_POS_BYTES = 4 * WF_TILE;                   // 12288
 }  // namespace tcg
 
 // ---- compile-time MMA programs -----------------------------------------------------------------
 // The operand offsets depend only on the layer geometry, so every descriptor is (runtime smem base) +
-// (compile-time constant): after unrolling, one MMA costs a handful of integer instructions.  All
-// offsets below are in 16-byte units (the descriptor granularity).  B tile order = tc_model_prepare.
+// (compile-time constant): one MMA costs a handful of integer instructions in the one issuing thread.
+// All offsets below are in 16-byte units (the descriptor granularity).  B tile order = tc_model_prepare.
 __device__ __forceinline__ uint64_t sdesc16(uint32_t lo) { return (0x4008ull << 32) | (uint64_t)lo; }   // SBO 128 B, version 1
 
-template <int BR> __device__ __forceinline__ constexpr int conv1_shift(int t) {
-    return BR == 0 ? 2 * tcg::WP + t : BR == 1 ? t * tcg::WP + 2 : (t / 5) * tcg::WP + (t % 5);
+template <int T>
+__device__ __forceinline__ void issue_conv1_tap(uint32_t a16, uint32_t w16, uint32_t d, uint32_t acc) {
+    constexpr int shift = (T / 5) * tcg::WP + (T % 5);
+    constexpr uint32_t idesc = make_idesc_f16(128, tcg::c1_tap_n(T));
+    umma_f16(d + tcg::c1_tap_dcol(T), sdesc16(a16 + shift + ((uint32_t)(tcg::IN_PLANE / 16) << 16)),
+             sdesc16(w16 + tcg::c1_tap_off16(T)), idesc, acc);                       // B: LBO = 0
 }
-// one branch of conv1 on one tile: (a_hi | a_lo) x (w_hi ; w_hi) per tap, then (a_hi tap | a_hi tap') x (w_lo ; w_lo') per tap pair
-template <int BR>
-__device__ __forceinline__ void issue_conv1_branch(uint32_t in16, uint32_t w16, uint32_t d, uint32_t idesc) {
-    constexpr int NT = BR == 2 ? 25 : 5, HI0 = BR == 0 ? 0 : BR == 1 ? 5 : 10, LO0 = BR == 0 ? 35 : BR == 1 ? 38 : 41;
-    const uint32_t blo = w16 | (16u << 16);
-#pragma unroll
-    for (int t = 0; t < NT; t++)
-        umma_f16(d + BR * 16, sdesc16(in16 + conv1_shift<BR>(t) + ((uint32_t)(tcg::IN_PLANE / 16) << 16)), sdesc16(blo + (HI0 + t) * 32), idesc, t > 0 ? 1u : 0u);
-#pragma unroll
-    for (int p = 0; p < (NT + 1) / 2; p++) {
-        const int s0 = conv1_shift<BR>(2 * p);
-        const int lbo = (2 * p + 1 < NT) ? conv1_shift<BR>(2 * p + 1) - s0 : 1;
-        umma_f16(d + BR * 16, sdesc16(in16 + s0 + ((uint32_t)lbo << 16)), sdesc16(blo + (LO0 + p) * 32), idesc, 1u);
-    }
+template <int... I>
+__device__ __forceinline__ void issue_conv1_seq(uint32_t a16, uint32_t w16, uint32_t d, std::integer_sequence<int, I...>) {
+    issue_conv1_tap<12>(a16, w16, d, 0u);                                            // the centre tap covers all 96 columns: it initialises
+    (issue_conv1_tap<(I < 12 ? I : I + 1)>(a16, w16, d, 1u), ...);
 }
-// taps [T0, T1) of conv2 (tap = kh*3 + kw) into accumulator d
-template <int T0, int T1>
-__device__ __forceinline__ void issue_conv2_taps(uint32_t c116, uint32_t w16, uint32_t d, uint32_t idesc) {
-    const uint32_t bhi = (w16 + tcg::W1_BYTES / 16) | (32u << 16), blo = bhi + 18 * 64;
-#pragma unroll
-    for (int tap = T0; tap < T1; tap++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const int kh = tap / 3, kw = tap % 3, par = kw & 1, shift = kh * tcg::C1_PITCH + (kw >> 1);
-            const uint32_t a_hi = c116 + (par * 6 + 2 * c) * tcg::C1_ROWS + shift + ((uint32_t)tcg::C1_ROWS << 16);
-            const uint32_t a_lo = a_hi + 12 * tcg::C1_ROWS;
-            const int idx = tap * 3 + c;
-            umma_f16(d, sdesc16(a_hi), sdesc16(bhi + idx * 64), idesc, (tap > T0 || c > 0) ? 1u : 0u);
-            umma_f16(d, sdesc16(a_lo), sdesc16(bhi + idx * 64), idesc, 1u);
-            umma_f16(d, sdesc16(a_hi), sdesc16(blo + idx * 64), idesc, 1u);
-        }
+// one 128-row tile of conv1 (all three branches): 25 MMAs
+__device__ __forceinline__ void issue_conv1_tile(uint32_t a16, uint32_t w16, uint32_t d) {
+    issue_conv1_seq(a16, w16, d, std::make_integer_sequence<int, 24>{});
 }
-template <int T0, int T1>
-__device__ __forceinline__ void issue_conv3_taps(uint32_t c216, uint32_t w16, uint32_t d, uint32_t idesc) {
+// conv2 (tap = kh*3 + kw, three 16-channel chunks per tap): a_hi x [w_hi | w_lo] (N = 64) + a_lo x w_hi (N = 32)
+template <int IDX>
+__device__ __forceinline__ void issue_conv2_step(uint32_t c116, uint32_t w16, uint32_t d) {
+    constexpr int tap = IDX / 3, c = IDX % 3, kh = tap / 3, kw = tap % 3, par = kw & 1, shift = kh * tcg::C1_PITCH + (kw >> 1);
+    const uint32_t a_hi = c116 + (par * 6 + 2 * c) * tcg::C1_ROWS + shift + ((uint32_t)tcg::C1_ROWS << 16);
+    const uint32_t a_lo = a_hi + 12 * tcg::C1_ROWS;
+    const uint32_t b = (w16 + (tcg::W1_BYTES + IDX * tcg::W2_TILE) / 16) | (64u << 16);
+    umma_f16(d, sdesc16(a_hi), sdesc16(b), make_idesc_f16(128, 64), IDX > 0 ? 1u : 0u);
+    umma_f16(d, sdesc16(a_lo), sdesc16(b), make_idesc_f16(128, 32), 1u);
+}
+template <int... I>
+__device__ __forceinline__ void issue_conv2_seq(uint32_t c116, uint32_t w16, uint32_t d, std::integer_sequence<int, I...>) {
+    (issue_conv2_step<I>(c116, w16, d), ...);
+}
+// conv3 (tap = kh*3 + kw, two chunks per tap): a_hi x [w_hi | w_lo] (N = 128) + a_lo x w_hi (N = 64)
+template <int IDX>
+__device__ __forceinline__ void issue_conv3_step(uint32_t c216, uint32_t w16, uint32_t d) {
     constexpr int PL = tcg::C2_PLANE / 16;          // 120
-    const uint32_t bhi = w16 | (64u << 16), blo = bhi + 12 * 128;
-#pragma unroll
-    for (int tap = T0; tap < T1; tap++)
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-            const int kh = tap / 3, kw = tap % 3, par = kw & 1, shift = kh * tcg::C2_PITCH + (kw >> 1);
-            const uint32_t a_hi = c216 + (par * 4 + 2 * c) * PL + shift + ((uint32_t)PL << 16);
-            const uint32_t a_lo = a_hi + 8 * PL;
-            const int idx = tap * 2 + c;
-            umma_f16(d, sdesc16(a_hi), sdesc16(bhi + idx * 128), idesc, (tap > T0 || c > 0) ? 1u : 0u);
-            umma_f16(d, sdesc16(a_lo), sdesc16(bhi + idx * 128), idesc, 1u);
-            umma_f16(d, sdesc16(a_hi), sdesc16(blo + idx * 128), idesc, 1u);
-        }
+    constexpr int tap = IDX / 2, c = IDX % 2, kh = tap / 3, kw = tap % 3, par = kw & 1, shift = kh * tcg::C2_PITCH + (kw >> 1);
+    const uint32_t a_hi = c216 + (par * 4 + 2 * c) * PL + shift + ((uint32_t)PL << 16);
+    const uint32_t a_lo = a_hi + 8 * PL;
+    const uint32_t b = (w16 + IDX * (tcg::W3_TILE / 16)) | (128u << 16);
+    umma_f16(d, sdesc16(a_hi), sdesc16(b), make_idesc_f16(128, 128), IDX > 0 ? 1u : 0u);
+    umma_f16(d, sdesc16(a_lo), sdesc16(b), make_idesc_f16(128, 64), 1u);
+}
+template <int... I>
+__device__ __forceinline__ void issue_conv3_seq(uint32_t c216, uint32_t w16, uint32_t d, std::integer_sequence<int, I...>) {
+    (issue_conv3_step<I>(c216, w16, d), ...);
 }
 
 struct TAParams {
@@ -263,11 +277,13 @@ struct TAParams {
 
 constexpr int TA_WGS = 3;
 constexpr int TA_THREADS = TA_WGS * 128;
-constexpr int TA_SMEM_W = tcg::W1_BYTES + tcg::W2_BYTES;                           // 64512
-constexpr int TA_SMEM_WG = 2 * tcg::IN_PLANE + tcg::C1_BYTES;                      // 13312 + 41344
+constexpr int TA_SMEM_W = tcg::W1_BYTES + tcg::W2_BYTES;                           // 54784
+constexpr int TA_RAW_BYTES = 2176;                                                 // staging of one int16 site image (2064 B)
+constexpr int TA_SMEM_WG = 2 * tcg::IN_PLANE + tcg::C1_BYTES + TA_RAW_BYTES;       // 13312 + 41344 + 2176
 constexpr int TA_SMEM_MISC = 80 * 4 + 64;
 constexpr int TA_SMEM = TA_SMEM_W + TA_WGS * TA_SMEM_WG + TA_SMEM_MISC + 64;
-constexpr int TA_TMEM_WG = 160;                                                    // conv1 2 x 48 + conv2 2 partial x 32
+constexpr int TA_TMEM_WG = 160;                                                    // conv1 96 (both tiles, one after the other) + conv2 64
+static_assert(TA_SMEM <= 232448, "TA shared memory exceeds the 227 KB per-CTA limit");
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -280,26 +296,42 @@ __device__ __forceinline__ void ta_load_pixel_f32(const TAParams& P, int64_t sit
 #pragma unroll
     for (int c = 0; c < 5; c++) v[c] = __ldg(src + c);
 }
+// 32 accumulator columns [w_hi part 16 | w_lo part 16] -> 16 sums
+__device__ __forceinline__ void tmem_ld_pair16(uint32_t addr, float* v) {
+    float a[16], b[16];
+    tmem_ld16_nowait(addr, a);
+    tmem_ld16_nowait(addr + 16, b);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = a[i] + b[i];
+}
 
+// TA: conv1_{1,2,3} + conv2.  148 persistent CTAs x 3 warpgroups, one site per warpgroup at a time.  Per site a warpgroup
+// runs three MMA phases on its own accumulator columns (conv1 rows 0..127, conv1 rows 97..224, conv2), all issued by one
+// elected thread and tracked by one mbarrier; the CUDA-core work is arranged so that most of it runs while this
+// warpgroup's own MMAs are in flight (and the other two warpgroups keep the operand pipe busy the rest of the time):
+//   conv1 tile 0 in flight : previous site's conv2 epilogue (bias, SELU, fp16 split, HBM stores)
+//   conv1 tile 1 in flight : tile 0 epilogue (bias, SELU, split -> c1 planes in shared memory)
+//   conv2 in flight        : next site's int16 tensor -> scaled fp16 hi/lo input planes
 __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_w = smem;
     uint8_t* s_wg0 = smem + TA_SMEM_W;
     float* s_bias = reinterpret_cast<float*>(smem + TA_SMEM_W + TA_WGS * TA_SMEM_WG);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 80);                     // [wg][2]: conv1 (4 arrivals), conv2 (2 arrivals)
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * TA_WGS);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 80);                     // [wg]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
 
     const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = tid >> 5, wq = warp & 3;
     uint8_t* s_in = s_wg0 + wg * TA_SMEM_WG;               // hi plane, then lo plane
     uint8_t* s_c1 = s_in + 2 * tcg::IN_PLANE;
-    uint8_t* s_raw = s_c1;                                 // the raw int16 site image is staged where c1 will be written later
+    uint8_t* s_raw = s_c1 + tcg::C1_BYTES;
 
     for (int i = tid; i < TA_SMEM_W / 16; i += TA_THREADS) reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(P.wimg) + i);
     if (tid < 48) s_bias[tid] = P.bias1[tid];
     if (tid >= 64 && tid < 96) s_bias[48 + tid - 64] = P.bias2[tid - 64];
     for (int i = tid; i < TA_WGS * TA_SMEM_WG / 16; i += TA_THREADS) reinterpret_cast<uint4*>(s_wg0)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
-        for (int i = 0; i < TA_WGS; i++) { mbar_init(&s_bar[2 * i], 4); mbar_init(&s_bar[2 * i + 1], 2); }
+        for (int i = 0; i < TA_WGS; i++) mbar_init(&s_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(s_tmem, 512);
@@ -310,9 +342,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
     const uint32_t tmem = *s_tmem + (uint32_t)wg * TA_TMEM_WG;
     const uint32_t tmem_lane = tmem + ((uint32_t)wq << 21);                    // lane quarter of this warp
     const uint32_t in16 = smem_u32(s_in) >> 4, c116 = smem_u32(s_c1) >> 4, w16 = smem_u32(s_w) >> 4;
-    const uint32_t idesc1 = make_idesc_f16(128, 16), idesc2 = make_idesc_f16(128, 32);
-    uint64_t* bar1 = &s_bar[2 * wg];
-    uint64_t* bar2 = &s_bar[2 * wg + 1];
+    uint64_t* bar = &s_bar[wg];
     uint32_t phase = 0;
     bool ok = true;
 
@@ -325,13 +355,11 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
         pre0 = __ldg(src + t);
         if (t == 0) pre1 = __ldg(src + 128);
     };
-    if (raw_mode && site < P.n_sites) prefetch(site);
-
-    for (; site < P.n_sites; site += stride) {
-        // ---- input -> padded planes (pixel row = (h+2)*45 + (w+2)), channels 5..7 stay zero
+    // site image (registers) -> padded fp16 hi / lo planes (pixel row = (h+2)*45 + (w+2)); channels 5..7 stay zero
+    auto convert = [&](int64_t sidx) {
         float sc_f = 1.f; double sc_d = 1.0;
-        if (P.in_mode == 1) sc_f = __ldg(P.scale_f + site);
-        if (P.in_mode == 2) sc_d = __ldg(P.scale_d + site);
+        if (P.in_mode == 1) sc_f = __ldg(P.scale_f + sidx);
+        if (P.in_mode == 2) sc_d = __ldg(P.scale_d + sidx);
         if (raw_mode) {
             *reinterpret_cast<uint4*>(s_raw + t * 16) = pre0;
             if (t == 0) *reinterpret_cast<uint4*>(s_raw + 2048) = pre1;
@@ -344,7 +372,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
                 const int h = px / 41, w = px - h * 41;
                 float v[5];
                 if (!raw_mode) {
-                    ta_load_pixel_f32(P, site, px, v);
+                    ta_load_pixel_f32(P, sidx, px, v);
                 } else {
                     const int16_t* rp = reinterpret_cast<const int16_t*>(s_raw) + px * 5;
 #pragma unroll
@@ -364,88 +392,117 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
                 *reinterpret_cast<uint4*>(s_in + tcg::IN_PLANE + row * 16) = lo;
             }
         }
-        fence_async_smem();
-        tc_fence_before();
-        wg_barrier(wg);
-        // ---- conv1: two 128-row tiles x three branches, issued by the four warps in parallel
-        //      (independent accumulators: warp 0/1 = 5x5 branch of tile 0/1, warp 2/3 = 1x5 and 5x1 branches of tile 0/1)
-        if (elect_one()) {
-            tc_fence_after();
-            const uint32_t a16 = in16 + ((wq & 1) ? tcg::TILE1_START : 0), d = tmem + ((wq & 1) ? 48 : 0);
-            if (wq < 2) {
-                issue_conv1_branch<2>(a16, w16, d, idesc1);
-            } else {
-                issue_conv1_branch<0>(a16, w16, d, idesc1);
-                issue_conv1_branch<1>(a16, w16, d, idesc1);
-            }
-            umma_commit(bar1);
-        }
-        __syncwarp();
-        if (raw_mode && site + stride < P.n_sites) prefetch(site + stride);     // in flight while the tensor core and the epilogues run
-        ok = mbar_wait(bar1, phase) && ok;
-        tc_fence_after();
-        // ---- epilogue 1: bias + SELU + split -> c1 planes [part][parity][k-group][h*21 + w/2]
-#pragma unroll 1
-        for (int j = 0; j < 2; j++) {
-            const int m = (j ? tcg::TILE1_START : 0) + t;
-            const int h = m / tcg::WP, w = m - h * tcg::WP;
-            const bool valid = m < 225 && w < 41 && (j == 0 || m >= 128);
-            float acc[48];
-            tmem_ld16_nowait(tmem_lane + j * 48, acc);
-            tmem_ld16_nowait(tmem_lane + j * 48 + 16, acc + 16);
-            tmem_ld16_nowait(tmem_lane + j * 48 + 32, acc + 32);
-            tmem_ld_wait();
-            if (valid) {
-                uint8_t* dst = s_c1 + ((w & 1) * 6) * tcg::C1_PLANE + (h * tcg::C1_PITCH + (w >> 1)) * 16;
+        if (raw_mode) wg_barrier(wg);            // s_raw is free for the next image
+    };
+    // conv1 epilogue of one tile: bias + SELU + split -> c1 planes [part][parity][k-group][h*21 + w/2]
+    auto store_c1 = [&](int j, const float* v) {
+        const int m = (j ? tcg::TILE1_START : 0) + t;
+        const int h = m / tcg::WP, w = m - h * tcg::WP;
+        const bool valid = m < 225 && w < 41 && (j == 0 || m >= 128);
+        if (valid) {
+            uint8_t* dst = s_c1 + ((w & 1) * 6) * tcg::C1_PLANE + (h * tcg::C1_PITCH + (w >> 1)) * 16;
 #pragma unroll
-                for (int kg = 0; kg < 6; kg++) {
-                    uint4 hi, lo;
-                    act_split8(acc + 8 * kg, s_bias + 8 * kg, hi, lo);
-                    *reinterpret_cast<uint4*>(dst + kg * tcg::C1_PLANE) = hi;
-                    *reinterpret_cast<uint4*>(dst + (12 + kg) * tcg::C1_PLANE) = lo;
-                }
+            for (int kg = 0; kg < 6; kg++) {
+                uint4 hi, lo;
+                act_split8(v + 8 * kg, s_bias + 8 * kg, hi, lo);
+                *reinterpret_cast<uint4*>(dst + kg * tcg::C1_PLANE) = hi;
+                *reinterpret_cast<uint4*>(dst + (12 + kg) * tcg::C1_PLANE) = lo;
             }
         }
-        fence_async_smem();
-        tc_fence_before();
-        wg_barrier(wg);
-        // ---- conv2: one tile (rows h2*21 + w2); taps 0-2 and 3-5 accumulate into two partial accumulators
-        if (wq < 2 && elect_one()) {
-            tc_fence_after();
-            if (wq == 0) issue_conv2_taps<0, 3>(c116, w16, tmem + 96, idesc2);
-            else issue_conv2_taps<3, 6>(c116, w16, tmem + 128, idesc2);
-            umma_commit(bar2);
-        }
-        __syncwarp();
-        ok = mbar_wait(bar2, phase) && ok;
-        phase ^= 1;
-        tc_fence_after();
-        // ---- epilogue 2: partial sums + bias + SELU + split -> HBM c2 [site][part][parity][k-group][h2*10 + w2/2][8]
-        {
-            const int m = t, h2 = m / tcg::C1_PITCH, w2 = m - h2 * tcg::C1_PITCH;
-            const bool valid = m < 84 && w2 < 20;
-            float acc[32], acc2[32];
-            tmem_ld16_nowait(tmem_lane + 96, acc);
-            tmem_ld16_nowait(tmem_lane + 112, acc + 16);
-            tmem_ld16_nowait(tmem_lane + 128, acc2);
-            tmem_ld16_nowait(tmem_lane + 144, acc2 + 16);
-            tmem_ld_wait();
-            if (valid) {
+    };
+    // accumulator columns -> 48 channel values in c1 order [1x5 | 5x1 | 5x5]
+    auto load_c1 = [&](float* v) {
+        tmem_ld_pair16(tmem_lane + 0, v);
+        tmem_ld_pair16(tmem_lane + 64, v + 16);
+        tmem_ld_pair16(tmem_lane + 32, v + 32);
+    };
+    // conv2 epilogue: bias + SELU + split -> HBM c2 [group][part][parity][k-group][site % 3][h2*10 + w2/2][8]
+    auto store_c2 = [&](int64_t sidx, const float* acc) {
+        const int m = t, h2 = m / tcg::C1_PITCH, w2 = m - h2 * tcg::C1_PITCH;
+        if (m < 84 && w2 < 20) {
+            uint8_t* dst = P.c2_out + (sidx / 3) * tcg::C2_GROUP_BYTES + (int)(sidx % 3) * tcg::C2_CHUNK + ((w2 & 1) * 4) * tcg::C2_PLANE + (h2 * tcg::C2_PITCH + (w2 >> 1)) * 16;
 #pragma unroll
-                for (int i = 0; i < 32; i++) acc[i] += acc2[i];
-                uint8_t* dst = P.c2_out + (site / 3) * tcg::C2_GROUP_BYTES + (int)(site % 3) * tcg::C2_CHUNK + ((w2 & 1) * 4) * tcg::C2_PLANE + (h2 * tcg::C2_PITCH + (w2 >> 1)) * 16;
-#pragma unroll
-                for (int kg = 0; kg < 4; kg++) {
-                    uint4 hi, lo;
-                    act_split8(acc + 8 * kg, s_bias + 48 + 8 * kg, hi, lo);
-                    *reinterpret_cast<uint4*>(dst + kg * tcg::C2_PLANE) = hi;
-                    *reinterpret_cast<uint4*>(dst + (8 + kg) * tcg::C2_PLANE) = lo;
-                }
+            for (int kg = 0; kg < 4; kg++) {
+                uint4 hi, lo;
+                act_split8(acc + 8 * kg, s_bias + 48 + 8 * kg, hi, lo);
+                *reinterpret_cast<uint4*>(dst + kg * tcg::C2_PLANE) = hi;
+                *reinterpret_cast<uint4*>(dst + (8 + kg) * tcg::C2_PLANE) = lo;
             }
         }
-        tc_fence_before();
-        wg_barrier(wg);              // TMEM and c1 planes are free for the next site
+    };
+
+    if (site < P.n_sites) {
+        if (raw_mode) prefetch(site);
+        convert(site);
+        if (raw_mode && site + stride < P.n_sites) prefetch(site + stride);
     }
+    fence_async_smem();
+    tc_fence_before();
+    wg_barrier(wg);
+
+    float acc2[32];
+    int64_t prev = -1;
+    for (; site < P.n_sites; site += stride) {
+        // ---- conv1, rows 0..127
+        if (wq == 0 && elect_one()) {
+            tc_fence_after();
+            issue_conv1_tile(in16, w16, tmem);
+            umma_commit(bar);
+        }
+        __syncwarp();
+        if (prev >= 0) store_c2(prev, acc2);                          // overlaps the MMAs just issued
+        ok = mbar_wait(bar, phase) && ok; phase ^= 1;
+        tc_fence_after();
+        float v[48];
+        load_c1(v);
+        tc_fence_before();
+        wg_barrier(wg);                                               // every warp has read its accumulator rows
+        // ---- conv1, rows 97..224 (same accumulator columns)
+        if (wq == 0 && elect_one()) {
+            tc_fence_after();
+            issue_conv1_tile(in16 + tcg::TILE1_START, w16, tmem);
+            umma_commit(bar);
+        }
+        __syncwarp();
+        store_c1(0, v);                                               // overlaps tile 1
+        ok = mbar_wait(bar, phase) && ok; phase ^= 1;
+        tc_fence_after();
+        load_c1(v);
+        store_c1(1, v);
+        fence_async_smem();
+        tc_fence_before();
+        wg_barrier(wg);                                               // c1 complete; input planes and conv1 columns free
+        // ---- conv2: one tile (rows h2*21 + w2)
+        if (wq == 0 && elect_one()) {
+            tc_fence_after();
+            issue_conv2_seq(c116, w16, tmem + 96, std::make_integer_sequence<int, 18>{});
+            umma_commit(bar);
+        }
+        __syncwarp();
+        const int64_t next = site + stride;
+        if (next < P.n_sites) {                                       // overlaps conv2
+            convert(next);
+            if (raw_mode && next + stride < P.n_sites) prefetch(next + stride);
+        }
+        ok = mbar_wait(bar, phase) && ok; phase ^= 1;
+        tc_fence_after();
+        {
+            // columns 96..127 = (a_hi + a_lo) w_hi, 128..159 = a_hi w_lo
+            float lo_part[32];
+            tmem_ld16_nowait(tmem_lane + 96, acc2);
+            tmem_ld16_nowait(tmem_lane + 112, acc2 + 16);
+            tmem_ld16_nowait(tmem_lane + 128, lo_part);
+            tmem_ld16_nowait(tmem_lane + 144, lo_part + 16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i++) acc2[i] += lo_part[i];
+        }
+        prev = site;
+        fence_async_smem();
+        tc_fence_before();
+        wg_barrier(wg);                                               // next site's planes visible; conv2 columns and c1 free
+    }
+    if (prev >= 0) store_c2(prev, acc2);
     if (!ok && t == 0) atomicExch(P.err, 1);
     tc_fence_before();
     __syncthreads();
@@ -479,7 +536,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
     if (tid < 64) s_bias[tid] = P.bias[tid];
     for (int i = tid; i < TB_WGS * tcg::C2_SMEM / 16; i += TB_THREADS) reinterpret_cast<uint4*>(smem + tcg::W3_BYTES)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
-        for (int i = 0; i < TB_WGS; i++) { mbar_init(&s_bar[i], 2); mbar_init(&s_full[i], 1); }
+        for (int i = 0; i < TB_WGS; i++) { mbar_init(&s_bar[i], 1); mbar_init(&s_full[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(s_tmem, 512);
@@ -487,10 +544,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *s_tmem + (uint32_t)wg * 128u;          // two partial accumulators of 64 columns
+    const uint32_t tmem = *s_tmem + (uint32_t)wg * 128u;          // columns [0,64) = (a_hi + a_lo) w_hi, [64,128) = a_hi w_lo
     const uint32_t tmem_lane = tmem + ((uint32_t)wq << 21);
     const uint32_t c216 = smem_u32(s_c2) >> 4, w16 = smem_u32(s_w) >> 4;
-    const uint32_t idesc = make_idesc_f16(128, 64);
     uint32_t phase = 0, lphase = 0;
     bool ok = true;
     const int64_t n_groups = (P.n_sites + 2) / 3;
@@ -507,10 +563,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
         ok = mbar_wait(&s_full[wg], lphase) && ok; lphase ^= 1;
         tc_fence_before();
         wg_barrier(wg);
-        if (wq < 2 && elect_one()) {
+        if (wq == 0 && elect_one()) {
             tc_fence_after();
-            if (wq == 0) issue_conv3_taps<0, 3>(c216, w16, tmem, idesc);
-            else issue_conv3_taps<3, 6>(c216, w16, tmem + 64, idesc);
+            issue_conv3_seq(c216, w16, tmem, std::make_integer_sequence<int, 12>{});
             umma_commit(&s_bar[wg]);
         }
         __syncwarp();
@@ -625,13 +680,12 @@ __global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
         mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(&s_empty[0], 1); mbar_init(&s_empty[1], 1); mbar_init(s_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(s_tmem, 64);
+    if (warp == 0) tmem_alloc(s_tmem, 128);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *s_tmem;
+    const uint32_t tmem = *s_tmem;                                     // columns [0,48) = (a_hi + a_lo) w_hi, [48,96) = a_hi w_lo
     const uint32_t tmem_lane = tmem + ((uint32_t)(warp & 3) << 21);
-    const uint32_t idesc = make_idesc_f16(128, 48);
     const uint8_t* a_src = P.c3 + tile * (int64_t)tcg::C3_TILE_BYTES;
     bool ok = true;
 
@@ -657,13 +711,12 @@ __global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
                 ok = mbar_wait(&s_full[st], (pos >> 1) & 1) && ok;
                 tc_fence_after();
                 const uint32_t sb16 = smem_u32(smem + st * TC_STAGE) >> 4;
-                const uint32_t bhi = (sb16 + TC_STAGE_A / 16) | (48u << 16);
+                const uint32_t b0 = (sb16 + TC_STAGE_A / 16) | (96u << 16);
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     const uint32_t a_hi = sb16 + (2 * c) * 128 + (128u << 16), a_lo = a_hi + 8 * 128;
-                    umma_f16(tmem, sdesc16(a_hi), sdesc16(bhi + c * 96), idesc, (pos > 0 || c > 0) ? 1u : 0u);
-                    umma_f16(tmem, sdesc16(a_lo), sdesc16(bhi + c * 96), idesc, 1u);
-                    umma_f16(tmem, sdesc16(a_hi), sdesc16(bhi + (4 + c) * 96), idesc, 1u);
+                    umma_f16(tmem, sdesc16(a_hi), sdesc16(b0 + c * (tcg::WF_TILE / 16)), make_idesc_f16(128, 96), (pos > 0 || c > 0) ? 1u : 0u);
+                    umma_f16(tmem, sdesc16(a_lo), sdesc16(b0 + c * (tcg::WF_TILE / 16)), make_idesc_f16(128, 48), 1u);
                 }
                 umma_commit(&s_empty[st]);
             }
@@ -676,22 +729,25 @@ __global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
     ok = mbar_wait(s_done, 0) && ok;
     tc_fence_after();
     {
-        float x[48];
+        float x[48], xl[48];
         tmem_ld16_nowait(tmem_lane, x);
         tmem_ld16_nowait(tmem_lane + 16, x + 16);
         tmem_ld16_nowait(tmem_lane + 32, x + 32);
+        tmem_ld16_nowait(tmem_lane + 48, xl);
+        tmem_ld16_nowait(tmem_lane + 64, xl + 16);
+        tmem_ld16_nowait(tmem_lane + 80, xl + 32);
         tmem_ld_wait();
         const int64_t s = tile * 128 + t;
         if (s < P.n_sites) {
 #pragma unroll
-            for (int i = 0; i < 48; i++) x[i] = selu_bf(x[i] + s_bias[i]);
+            for (int i = 0; i < 48; i++) x[i] = selu_bf(x[i] + xl[i] + s_bias[i]);
             snp_tail_row(x, s, P);
         }
     }
     if (!ok) atomicExch(P.err, 1);
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 64);
+    if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -708,7 +764,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const uint8_t* a_img
     for (int i = t; i < a_bytes / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(a_img)[i];
     for (int i = t; i < b_bytes / 16; i += 128) reinterpret_cast<uint4*>(smem + a_bytes)[i] = reinterpret_cast<const uint4*>(b_img)[i];
     if (t == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    if (warp == 0) tmem_alloc(&tmem_slot, 64);
+    if (warp == 0) tmem_alloc(&tmem_slot, 128);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -728,7 +784,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const uint8_t* a_img
     if (!ok && t == 0) atomicExch(err, 1);
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 64);
+    if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -737,13 +793,13 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const uint8_t* a_img
 struct TcModel {
     bool ready = false;
     int kind = 0;
-    DevBuf wimg_a, wimg_b, wimg_c, prog, bias;   // prog: ops1 | ops2 | ops3 | opsF ; bias: b1(48) b2(32) b3(64) bf(48)
+    DevBuf wimg_a, wimg_b, wimg_c, bias;         // bias: b1(48) b2(32) b3(64) bf(48)
     DevBuf c2, c3, err;
     int64_t tail_off[16][2];
 };
 
 inline void tc_model_release(TcModel& T) {
-    for (DevBuf* b : {&T.wimg_a, &T.wimg_b, &T.wimg_c, &T.prog, &T.bias, &T.c2, &T.c3, &T.err}) b->release();
+    for (DevBuf* b : {&T.wimg_a, &T.wimg_b, &T.wimg_c, &T.bias, &T.c2, &T.c3, &T.err}) b->release();
     T.ready = false;
 }
 
@@ -774,116 +830,62 @@ inline int tc_model_prepare(cudaStream_t stream, TcModel& T, int kind, const flo
     const float* w3 = b2 + 32; const float* b3 = w3 + 12288;
     const float* wf = b3 + 64; const float* bf = wf + 82944;
 
-    std::vector<MmaOp> ops;
-    // ---------------- conv1: three branches, taps in ascending shift order
-    struct Tap { int shift; const float* w; };      // w -> [ci 5][co 16] slice of the HWIO kernel
-    std::vector<uint8_t> img_hi(35 * 512, 0), img_lo(19 * 512, 0);
-    std::vector<uint8_t> dummy(35 * 512, 0);
-    int hi_tiles = 0, lo_tiles = 0;
-    for (int br = 0; br < 3; br++) {
-        std::vector<Tap> taps;
-        if (br == 0) for (int kw = 0; kw < 5; kw++) taps.push_back({2 * WP + kw, w11 + (size_t)kw * 5 * 16});
-        if (br == 1) for (int kh = 0; kh < 5; kh++) taps.push_back({kh * WP + 2, w12 + (size_t)kh * 5 * 16});
-        if (br == 2) for (int kh = 0; kh < 5; kh++) for (int kw = 0; kw < 5; kw++) taps.push_back({kh * WP + kw, w13 + (size_t)(kh * 5 + kw) * 5 * 16});
-        bool first = true;
-        // (a_hi | a_lo) x (w_hi ; w_hi)
-        for (const Tap& tp : taps) {
-            const size_t base = (size_t)hi_tiles * 512;
-            for (int ci = 0; ci < 5; ci++)
-                for (int n = 0; n < 16; n++) {
-                    const float w = tp.w[ci * 16 + n];
-                    put_split(img_hi, dummy, base + btile_off(16, ci, n), w);
-                    put_split(img_hi, dummy, base + btile_off(16, 8 + ci, n), w);
-                }
-            ops.push_back({(uint32_t)(tp.shift * 16), (uint32_t)IN_PLANE, (uint32_t)(hi_tiles * 512), (uint32_t)(br * 16) | (first ? 0u : kOpAcc)});
-            first = false; hi_tiles++;
+    // 8 input-channel slots of one accumulator column: fp16 hi (part 0) or lo (part 1) of w[ci] for ci < n_ci
+    auto put_row = [](std::vector<uint8_t>& img, size_t row_byte_off, const float* w, int ci_stride, int n_ci, int part) {
+        for (int ci = 0; ci < n_ci; ci++) {
+            const float x = w[(size_t)ci * ci_stride];
+            const __half h = __float2half_rn(x);
+            const __half l = __float2half_rn(x - __half2float(h));
+            memcpy(img.data() + row_byte_off + (size_t)ci * 2, part ? &l : &h, 2);
         }
-        // (a_hi tap t | a_hi tap t') x (w_lo t ; w_lo t')
-        for (size_t i = 0; i < taps.size(); i += 2) {
-            const size_t base = (size_t)lo_tiles * 512;
-            const bool pair = i + 1 < taps.size();
-            for (int half = 0; half < (pair ? 2 : 1); half++)
-                for (int ci = 0; ci < 5; ci++)
-                    for (int n = 0; n < 16; n++) {
-                        const float w = taps[i + half].w[ci * 16 + n];
-                        const __half h = __float2half_rn(w);
-                        const __half l = __float2half_rn(w - __half2float(h));
-                        memcpy(img_lo.data() + base + btile_off(16, 8 * half + ci, n), &l, 2);
-                    }
-            const uint32_t lbo = pair ? (uint32_t)((taps[i + 1].shift - taps[i].shift) * 16) : 16u;
-            ops.push_back({(uint32_t)(taps[i].shift * 16), lbo, (uint32_t)(35 * 512 + lo_tiles * 512), (uint32_t)(br * 16) | kOpAcc});
-            lo_tiles++;
-        }
+    };
+    // ---------------- conv1: one tile per 5x5 tap, rows = accumulator columns (see tcg), one K group (B LBO = 0)
+    std::vector<uint8_t> w1_img(W1_BYTES, 0);
+    for (int t = 0; t < 25; t++) {
+        const int kh = t / 5, kw = t % 5;
+        const size_t base = (size_t)c1_tap_off16(t) * 16;
+        int row = 0;
+        auto put_branch = [&](const float* wtap) {            // wtap -> [ci 5][co 16]; 16 hi rows then 16 lo rows
+            for (int part = 0; part < 2; part++)
+                for (int n = 0; n < 16; n++) put_row(w1_img, base + (size_t)(row++) * 16, wtap + n, 16, 5, part);
+        };
+        if (kh == 2) put_branch(w11 + (size_t)kw * 5 * 16);                 // 1x5 branch: columns 0..31
+        put_branch(w13 + (size_t)t * 5 * 16);                               // 5x5 branch
+        if (kw == 2) put_branch(w12 + (size_t)kh * 5 * 16);                 // 5x1 branch: columns 64..95 (32..63 of a column-tap tile)
+        if (row != c1_tap_n(t)) { if (err) *err = "conv1 tile size mismatch"; return NC_EINVAL; }
     }
-    if ((int)ops.size() != N_OPS1 || hi_tiles != 35 || lo_tiles != 19) { if (err) *err = "conv1 program size mismatch"; return NC_EINVAL; }
-    // ---------------- conv2: [kh 2][kw 3][ci 48][co 32]
-    std::vector<uint8_t> w2_hi(18 * 1024, 0), w2_lo(18 * 1024, 0);
-    {
-        int tile = 0; bool first = true;
-        for (int kh = 0; kh < 2; kh++)
-            for (int kw = 0; kw < 3; kw++)
-                for (int c = 0; c < 3; c++) {
-                    for (int s = 0; s < 16; s++)
-                        for (int n = 0; n < 32; n++)
-                            put_split(w2_hi, w2_lo, (size_t)tile * 1024 + btile_off(32, s, n), w2[((size_t)(kh * 3 + kw) * 48 + 16 * c + s) * 32 + n]);
-                    const int par = kw & 1, shift = kh * C1_PITCH + (kw >> 1);
-                    const uint32_t a_hi = (uint32_t)(((0 * 2 + par) * 6 + 2 * c) * C1_PLANE + shift * 16);
-                    const uint32_t a_lo = (uint32_t)(((1 * 2 + par) * 6 + 2 * c) * C1_PLANE + shift * 16);
-                    ops.push_back({a_hi, (uint32_t)C1_PLANE, (uint32_t)(tile * 1024), 0u | (first ? 0u : kOpAcc)});
-                    ops.push_back({a_lo, (uint32_t)C1_PLANE, (uint32_t)(tile * 1024), kOpAcc});
-                    ops.push_back({a_hi, (uint32_t)C1_PLANE, (uint32_t)(18 * 1024 + tile * 1024), kOpAcc});
-                    first = false; tile++;
-                }
-    }
-    // ---------------- conv3: [kh 2][kw 3][ci 32][co 64]
-    std::vector<uint8_t> w3_hi(12 * 2048, 0), w3_lo(12 * 2048, 0);
-    {
-        int tile = 0; bool first = true;
-        for (int kh = 0; kh < 2; kh++)
-            for (int kw = 0; kw < 3; kw++)
-                for (int c = 0; c < 2; c++) {
-                    for (int s = 0; s < 16; s++)
-                        for (int n = 0; n < 64; n++)
-                            put_split(w3_hi, w3_lo, (size_t)tile * 2048 + btile_off(64, s, n), w3[((size_t)(kh * 3 + kw) * 32 + 16 * c + s) * 64 + n]);
-                    const int par = kw & 1, shift = kh * C2_PITCH + (kw >> 1);
-                    const uint32_t a_hi = (uint32_t)(((0 * 2 + par) * 4 + 2 * c) * C2_PLANE + shift * 16);
-                    const uint32_t a_lo = (uint32_t)(((1 * 2 + par) * 4 + 2 * c) * C2_PLANE + shift * 16);
-                    ops.push_back({a_hi, (uint32_t)C2_PLANE, (uint32_t)(tile * 2048), 0u | (first ? 0u : kOpAcc)});
-                    ops.push_back({a_lo, (uint32_t)C2_PLANE, (uint32_t)(tile * 2048), kOpAcc});
-                    ops.push_back({a_hi, (uint32_t)C2_PLANE, (uint32_t)(12 * 2048 + tile * 2048), kOpAcc});
-                    first = false; tile++;
-                }
-    }
-    // ---------------- fc1: [k = pos*64 + ch][n 48]; per position 4 K-chunks, tiles hi0..3 then lo0..3
+    // ---------------- conv2: [kh 2][kw 3][ci 48][co 32]; per (tap, chunk) [k-group 2][w_hi 32 | w_lo 32][8 slots]
+    std::vector<uint8_t> w2_img(W2_BYTES, 0);
+    for (int tap = 0; tap < 6; tap++)
+        for (int c = 0; c < 3; c++)
+            for (int kg = 0; kg < 2; kg++)
+                for (int part = 0; part < 2; part++)
+                    for (int n = 0; n < 32; n++)
+                        put_row(w2_img, (size_t)(tap * 3 + c) * W2_TILE + ((size_t)kg * 64 + part * 32 + n) * 16,
+                                w2 + ((size_t)tap * 48 + 16 * c + 8 * kg) * 32 + n, 32, 8, part);
+    // ---------------- conv3: [kh 2][kw 3][ci 32][co 64]; per (tap, chunk) [k-group 2][w_hi 64 | w_lo 64][8 slots]
+    std::vector<uint8_t> w3_img(W3_BYTES, 0);
+    for (int tap = 0; tap < 6; tap++)
+        for (int c = 0; c < 2; c++)
+            for (int kg = 0; kg < 2; kg++)
+                for (int part = 0; part < 2; part++)
+                    for (int n = 0; n < 64; n++)
+                        put_row(w3_img, (size_t)(tap * 2 + c) * W3_TILE + ((size_t)kg * 128 + part * 64 + n) * 16,
+                                w3 + ((size_t)tap * 32 + 16 * c + 8 * kg) * 64 + n, 64, 8, part);
+    // ---------------- fc1: [k = pos*64 + ch][n 48]; per (position, chunk) [k-group 2][w_hi 48 | w_lo 48][8 slots]
     std::vector<uint8_t> wf_img((size_t)27 * WF_POS_BYTES, 0);
-    {
-        std::vector<uint8_t> thi(1536), tlo(1536);
-        for (int pos = 0; pos < 27; pos++)
-            for (int c = 0; c < 4; c++) {
-                std::fill(thi.begin(), thi.end(), 0); std::fill(tlo.begin(), tlo.end(), 0);
-                for (int s = 0; s < 16; s++)
+    for (int pos = 0; pos < 27; pos++)
+        for (int c = 0; c < 4; c++)
+            for (int kg = 0; kg < 2; kg++)
+                for (int part = 0; part < 2; part++)
                     for (int n = 0; n < 48; n++)
-                        put_split(thi, tlo, btile_off(48, s, n), wf[((size_t)pos * 64 + 16 * c + s) * 48 + n]);
-                memcpy(wf_img.data() + (size_t)pos * WF_POS_BYTES + (size_t)c * 1536, thi.data(), 1536);
-                memcpy(wf_img.data() + (size_t)pos * WF_POS_BYTES + (size_t)(4 + c) * 1536, tlo.data(), 1536);
-            }
-        for (int c = 0; c < 4; c++) {
-            const uint32_t a_hi = (uint32_t)((0 * 8 + 2 * c) * 2048), a_lo = (uint32_t)((1 * 8 + 2 * c) * 2048);
-            ops.push_back({a_hi, 2048u, (uint32_t)(c * 1536), c == 0 ? 0u : kOpAcc});
-            ops.push_back({a_lo, 2048u, (uint32_t)(c * 1536), kOpAcc});
-            ops.push_back({a_hi, 2048u, (uint32_t)((4 + c) * 1536), kOpAcc});
-        }
-    }
-    if ((int)ops.size() != N_OPS1 + N_OPS2 + N_OPS3 + N_OPSF) { if (err) *err = "program size mismatch"; return NC_EINVAL; }
+                        put_row(wf_img, (size_t)pos * WF_POS_BYTES + (size_t)c * WF_TILE + ((size_t)kg * 96 + part * 48 + n) * 16,
+                                wf + ((size_t)pos * 64 + 16 * c + 8 * kg) * 48 + n, 48, 8, part);
 
     std::vector<uint8_t> img_a;
-    img_a.insert(img_a.end(), img_hi.begin(), img_hi.end());
-    img_a.insert(img_a.end(), img_lo.begin(), img_lo.end());
-    img_a.insert(img_a.end(), w2_hi.begin(), w2_hi.end());
-    img_a.insert(img_a.end(), w2_lo.begin(), w2_lo.end());
-    std::vector<uint8_t> img_b;
-    img_b.insert(img_b.end(), w3_hi.begin(), w3_hi.end());
-    img_b.insert(img_b.end(), w3_lo.begin(), w3_lo.end());
+    img_a.insert(img_a.end(), w1_img.begin(), w1_img.end());
+    img_a.insert(img_a.end(), w2_img.begin(), w2_img.end());
+    const std::vector<uint8_t>& img_b = w3_img;
     std::vector<float> bias;
     bias.insert(bias.end(), b11, b11 + 16); bias.insert(bias.end(), b12, b12 + 16); bias.insert(bias.end(), b13, b13 + 16);
     bias.insert(bias.end(), b2, b2 + 32); bias.insert(bias.end(), b3, b3 + 64); bias.insert(bias.end(), bf, bf + 48);
@@ -895,7 +897,7 @@ inline int tc_model_prepare(cudaStream_t stream, TcModel& T, int kind, const flo
     };
     cudaError_t e;
     if ((e = up(T.wimg_a, img_a.data(), img_a.size())) != cudaSuccess || (e = up(T.wimg_b, img_b.data(), img_b.size())) != cudaSuccess ||
-        (e = up(T.wimg_c, wf_img.data(), wf_img.size())) != cudaSuccess || (e = up(T.prog, ops.data(), ops.size() * sizeof(MmaOp))) != cudaSuccess ||
+        (e = up(T.wimg_c, wf_img.data(), wf_img.size())) != cudaSuccess ||
         (e = up(T.bias, bias.data(), bias.size() * 4)) != cudaSuccess || (e = T.err.reserve(16)) != cudaSuccess ||
         (e = cudaMemsetAsync(T.err.p, 0, 16, stream)) != cudaSuccess || (e = cudaStreamSynchronize(stream)) != cudaSuccess) {
         if (err) *err = std::string("tc_model_prepare: ") + cudaGetErrorString(e);

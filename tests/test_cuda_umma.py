@@ -85,3 +85,62 @@ def test_n48_tile():
     out = _probe(A, B, [(0, 128 * 16, 0, 0)], 48, 48)
     Am = np.concatenate([A[0], A[1]], 1).astype(np.float32)
     np.testing.assert_array_equal(out, Am @ Bd)
+
+
+BLBO0 = 1 << 14
+
+
+def test_b_lbo_zero_reads_one_k_group_twice():
+    """LBO = 0 on the B descriptor: both K groups of the MMA read the same 8-wide weight group, so
+    (a_hi | a_lo) x (w ; w) = (a_hi + a_lo) w needs the weights only once in shared memory (conv1 of the SNP trunk)."""
+    rng = np.random.RandomState(5)
+    rows = 140
+    A = _planes(rng, 2, rows)
+    for N in (32, 64, 96):
+        B = (rng.randint(-8, 9, (1, N, 8)) / 8.0).astype(np.float16)           # one K group: [n][8]
+        Bd = B[0].astype(np.float32).T                                         # [8][N]
+        out = _probe(A, B, [(4 * 16, rows * 16, 0, BLBO0)], N, 96 if N > 64 else 64)[:, :N]
+        Am = (A[0, 4:132].astype(np.float32) + A[1, 4:132].astype(np.float32))
+        np.testing.assert_array_equal(out, Am @ Bd)
+
+
+def test_mixed_n_accumulation_into_overlapping_columns():
+    """MMAs of different N accumulate into overlapping accumulator column ranges in issue order
+    (conv1: centre tap N = 96 first, then N = 64 / N = 32 taps into sub-ranges)."""
+    rng = np.random.RandomState(6)
+    rows = 200
+    A = _planes(rng, 2, rows)
+    B96 = (rng.randint(-8, 9, (1, 96, 8)) / 8.0).astype(np.float16)
+    B64 = (rng.randint(-8, 9, (1, 64, 8)) / 8.0).astype(np.float16)
+    B32 = (rng.randint(-8, 9, (1, 32, 8)) / 8.0).astype(np.float16)
+    Bimg = np.concatenate([B96.ravel(), B64.ravel(), B32.ravel()])
+
+    def n8(n):
+        return (n // 8) << 16
+    ops = [(0, rows * 16, 0, BLBO0 | n8(96)),
+           (7 * 16, rows * 16, 96 * 16, BLBO0 | ACC | n8(64) | 32),           # columns 32..95
+           (50 * 16, rows * 16, (96 + 64) * 16, BLBO0 | ACC | n8(32) | 32),   # columns 32..63
+           (9 * 16, rows * 16, 96 * 16, BLBO0 | ACC | n8(64) | 0)]            # columns 0..63
+    out = _probe(A, Bimg, ops, 96, 96)
+
+    def am(shift):
+        return A[0, shift:shift + 128].astype(np.float32) + A[1, shift:shift + 128].astype(np.float32)
+    want = am(0) @ B96[0].astype(np.float32).T
+    want[:, 32:96] += am(7) @ B64[0].astype(np.float32).T
+    want[:, 32:64] += am(50) @ B32[0].astype(np.float32).T
+    want[:, 0:64] += am(9) @ B64[0].astype(np.float32).T
+    np.testing.assert_array_equal(out, want)
+
+
+def test_n_override_reads_a_prefix_of_a_wider_tile():
+    """conv2 / conv3: a_hi x [w_hi | w_lo] is one N = 2C MMA, a_lo x w_hi an N = C MMA on the same tile (same LBO)."""
+    rng = np.random.RandomState(7)
+    A = _planes(rng, 4, 128)
+    B, Bd = _btile(rng, 64)
+    ops = [(0, 128 * 16, 0, 0), (2 * 128 * 16, 128 * 16, 0, ACC | ((32 // 8) << 16))]
+    out = _probe(A, B, ops, 64, 64)
+    A01 = np.concatenate([A[0], A[1]], 1).astype(np.float32)
+    A23 = np.concatenate([A[2], A[3]], 1).astype(np.float32)
+    want = A01 @ Bd
+    want[:, :32] += A23 @ Bd[:, :32]
+    np.testing.assert_array_equal(out, want)
