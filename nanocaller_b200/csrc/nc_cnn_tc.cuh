@@ -107,48 +107,44 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
                  :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" :: "r"(wg + 1) : "memory"); }
+// the four warps of an epilogue warpgroup plus its MMA issuer warp
+__device__ __forceinline__ void wg_issuer_barrier(int wg) { asm volatile("bar.sync %0, 160;" :: "r"(wg + 4) : "memory"); }
 
-// SELU with the fast exponential (ex2.approx): abs error ~1e-7 on the negative branch.
-__device__ __forceinline__ float selu_fast(float x) {
-    const float scale = 1.0507009873554805f, sa = 1.0507009873554805f * 1.6732632423543772f;
-    return x > 0.f ? scale * x : sa * (__expf(x) - 1.f);
+// ---- epilogue arithmetic.  The CUDA-core epilogues (bias, SELU, fp16 hi/lo split of ~130 values per thread and site)
+// are what bounds TA once the MMA programs are folded, so every instruction counts:
+//   * exp through ex2.approx.ftz (no denormal range fix-up: -3 instructions per value), log2(e) folded into an FMA
+//     on the raw accumulator (bl = bias * log2 e is precomputed);
+//   * hi = x with the low 13 mantissa bits cleared (one LOP3; exactly representable in fp16), lo = fp16(x - hi): 21+
+//     significant bits like the round-to-nearest split, without converting hi back to fp32;
+//   * cvt.rn.satfinite packs two values per instruction and keeps hi finite without separate clamps.
+__device__ __forceinline__ float ex2_ftz(float x) { float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x)); return e; }
+// SELU(acc + bias): sa*(exp(min(z,0)) - 1) + scale*max(z,0), branch-free, exact 0 from the exponential branch for z > 0
+__device__ __forceinline__ float selu_acc(float acc, float bias, float bl) {
+    const float scale = 1.0507009873554805f, sa = 1.0507009873554805f * 1.6732632423543772f, l2e = 1.4426950408889634f;
+    const float e = ex2_ftz(fminf(fmaf(acc, l2e, bl), 0.f));
+    return fmaf(scale, fmaxf(acc + bias, 0.f), fmaf(sa, e, -sa));
 }
-// x -> (hi, lo) fp16 pair with hi + lo ~= x to 22 bits; saturates instead of overflowing to inf.
-__device__ __forceinline__ void split16(float x, __half& hi, __half& lo) {
-    x = fminf(fmaxf(x, -65000.f), 65000.f);
-    hi = __float2half_rn(x);
-    lo = __float2half_rn(x - __half2float(hi));
+__device__ __forceinline__ float selu_bf(float x) { return selu_acc(x, 0.f, 0.f); }
+// (a -> low half, b -> high half), saturating to the largest finite fp16
+__device__ __forceinline__ uint32_t pack_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
-// 8 consecutive channels -> one 16-byte hi word and one 16-byte lo word
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-    __half h[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) split16(v[i], h[i], l[i]);
-    hi = *reinterpret_cast<uint4*>(h);
-    lo = *reinterpret_cast<uint4*>(l);
-}
-
-// Branch-free SELU: sa*(exp(min(x,0)) - 1) + scale*max(x,0)  (6 instructions, exact 0 contribution for x > 0).
-__device__ __forceinline__ float selu_bf(float x) {
-    const float scale = 1.0507009873554805f, sa = 1.0507009873554805f * 1.6732632423543772f;
-    return fmaf(sa, __expf(fminf(x, 0.f)), -sa) + scale * fmaxf(x, 0.f);
-}
-// two values -> packed (hi, hi) and (lo, lo) fp16 pairs; upper clamp keeps hi finite (SELU bounds the lower side)
+// two values -> packed (hi, hi) and (lo, lo) fp16 pairs
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    a = fminf(a, 65000.f); b = fminf(b, 65000.f);
-    const __half2 h = __floats2half2_rn(a, b);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
+    const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+    hi = pack_sat(ah, bh);
+    lo = pack_sat(a - ah, b - bh);
 }
-// 8 accumulator values + bias -> SELU -> hi / lo 16-byte words
-__device__ __forceinline__ void act_split8(const float* acc, const float* bias, uint4& hi, uint4& lo) {
+// 8 accumulator values -> bias + SELU -> hi / lo 16-byte words.  bias2 = [bias | bias * log2 e] rows of 8 floats: bias2[0..7], bias2[n_bias..]
+__device__ __forceinline__ void act_split8(const float* acc, const float* bias, const float* bl, uint4& hi, uint4& lo) {
     const float4 b0 = *reinterpret_cast<const float4*>(bias), b1 = *reinterpret_cast<const float4*>(bias + 4);
-    split2(selu_bf(acc[0] + b0.x), selu_bf(acc[1] + b0.y), hi.x, lo.x);
-    split2(selu_bf(acc[2] + b0.z), selu_bf(acc[3] + b0.w), hi.y, lo.y);
-    split2(selu_bf(acc[4] + b1.x), selu_bf(acc[5] + b1.y), hi.z, lo.z);
-    split2(selu_bf(acc[6] + b1.z), selu_bf(acc[7] + b1.w), hi.w, lo.w);
+    const float4 l0 = *reinterpret_cast<const float4*>(bl), l1 = *reinterpret_cast<const float4*>(bl + 4);
+    split2(selu_acc(acc[0], b0.x, l0.x), selu_acc(acc[1], b0.y, l0.y), hi.x, lo.x);
+    split2(selu_acc(acc[2], b0.z, l0.z), selu_acc(acc[3], b0.w, l0.w), hi.y, lo.y);
+    split2(selu_acc(acc[4], b1.x, l1.x), selu_acc(acc[5], b1.y, l1.y), hi.z, lo.z);
+    split2(selu_acc(acc[6], b1.z, l1.z), selu_acc(acc[7], b1.w, l1.w), hi.w, lo.w);
 }
 
 // One MMA of a layer's "program": where its A rows start, how its two K groups are spaced, which
@@ -276,11 +272,11 @@ struct TAParams {
 };
 
 constexpr int TA_WGS = 3;
-constexpr int TA_THREADS = TA_WGS * 128;
+constexpr int TA_THREADS = TA_WGS * 128 + 128;                                     // three epilogue warpgroups + one warpgroup of MMA issuer warps (one per epilogue warpgroup)
 constexpr int TA_SMEM_W = tcg::W1_BYTES + tcg::W2_BYTES;                           // 54784
 constexpr int TA_RAW_BYTES = 2176;                                                 // staging of one int16 site image (2064 B)
 constexpr int TA_SMEM_WG = 2 * tcg::IN_PLANE + tcg::C1_BYTES + TA_RAW_BYTES;       // 13312 + 41344 + 2176
-constexpr int TA_SMEM_MISC = 80 * 4 + 64;
+constexpr int TA_SMEM_MISC = 160 * 4 + 64;                                         // bias[80], bias * log2e [80], mbarriers, TMEM slot
 constexpr int TA_SMEM = TA_SMEM_W + TA_WGS * TA_SMEM_WG + TA_SMEM_MISC + 64;
 constexpr int TA_TMEM_WG = 160;                                                    // conv1 96 (both tiles, one after the other) + conv2 64
 static_assert(TA_SMEM <= 232448, "TA shared memory exceeds the 227 KB per-CTA limit");
@@ -306,10 +302,12 @@ __device__ __forceinline__ void tmem_ld_pair16(uint32_t addr, float* v) {
     for (int i = 0; i < 16; i++) v[i] = a[i] + b[i];
 }
 
-// TA: conv1_{1,2,3} + conv2.  148 persistent CTAs x 3 warpgroups, one site per warpgroup at a time.  Per site a warpgroup
-// runs three MMA phases on its own accumulator columns (conv1 rows 0..127, conv1 rows 97..224, conv2), all issued by one
-// elected thread and tracked by one mbarrier; the CUDA-core work is arranged so that most of it runs while this
-// warpgroup's own MMAs are in flight (and the other two warpgroups keep the operand pipe busy the rest of the time):
+// TA: conv1_{1,2,3} + conv2.  148 persistent CTAs x 3 epilogue warpgroups, one site per warpgroup at a time, plus one
+// MMA issuer warp per warpgroup (tcgen05.mma blocks its issuing thread while the MMA queue is full, so a warp that also
+// has epilogue work must not issue).  Per site a warpgroup runs three MMA phases on its own accumulator columns (conv1
+// rows 0..127, conv1 rows 97..224, conv2), handed to the issuer through a 160-thread named barrier and tracked by one
+// mbarrier; the CUDA-core work is arranged so that most of it runs while this warpgroup's own MMAs are in flight (and
+// the other two warpgroups keep the operand pipe busy the rest of the time):
 //   conv1 tile 0 in flight : previous site's conv2 epilogue (bias, SELU, fp16 split, HBM stores)
 //   conv1 tile 1 in flight : tile 0 epilogue (bias, SELU, split -> c1 planes in shared memory)
 //   conv2 in flight        : next site's int16 tensor -> scaled fp16 hi/lo input planes
@@ -318,7 +316,8 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
     uint8_t* s_w = smem;
     uint8_t* s_wg0 = smem + TA_SMEM_W;
     float* s_bias = reinterpret_cast<float*>(smem + TA_SMEM_W + TA_WGS * TA_SMEM_WG);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 80);                     // [wg]
+    float* s_bl = s_bias + 80;                                                      // bias * log2(e)
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bl + 80);                       // [wg]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
 
     const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = tid >> 5, wq = warp & 3;
@@ -327,8 +326,8 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
     uint8_t* s_raw = s_c1 + tcg::C1_BYTES;
 
     for (int i = tid; i < TA_SMEM_W / 16; i += TA_THREADS) reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(P.wimg) + i);
-    if (tid < 48) s_bias[tid] = P.bias1[tid];
-    if (tid >= 64 && tid < 96) s_bias[48 + tid - 64] = P.bias2[tid - 64];
+    if (tid < 48) { const float b = P.bias1[tid]; s_bias[tid] = b; s_bl[tid] = b * 1.4426950408889634f; }
+    if (tid >= 64 && tid < 96) { const float b = P.bias2[tid - 64]; s_bias[48 + tid - 64] = b; s_bl[48 + tid - 64] = b * 1.4426950408889634f; }
     for (int i = tid; i < TA_WGS * TA_SMEM_WG / 16; i += TA_THREADS) reinterpret_cast<uint4*>(s_wg0)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         for (int i = 0; i < TA_WGS; i++) mbar_init(&s_bar[i], 1);
@@ -339,27 +338,50 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    const int64_t stride = (int64_t)gridDim.x * TA_WGS;
+    if (wg == TA_WGS) {
+        // ===== MMA issuer warps: warp wq serves epilogue warpgroup wq
+        if (wq < TA_WGS) {
+            const int ewg = wq;
+            const uint32_t tmem = *s_tmem + (uint32_t)ewg * TA_TMEM_WG;
+            const uint32_t in16 = smem_u32(s_wg0 + ewg * TA_SMEM_WG) >> 4, c116 = in16 + 2 * tcg::IN_PLANE / 16, w16 = smem_u32(s_w) >> 4;
+            uint64_t* bar = &s_bar[ewg];
+            for (int64_t site = (int64_t)blockIdx.x * TA_WGS + ewg; site < P.n_sites; site += stride) {
+                wg_issuer_barrier(ewg);                                   // input planes of `site` ready, conv1 columns free
+                if (elect_one()) { tc_fence_after(); issue_conv1_tile(in16, w16, tmem); umma_commit(bar); }
+                __syncwarp();
+                wg_issuer_barrier(ewg);                                   // tile 0 accumulators read
+                if (elect_one()) { tc_fence_after(); issue_conv1_tile(in16 + tcg::TILE1_START, w16, tmem); umma_commit(bar); }
+                __syncwarp();
+                wg_issuer_barrier(ewg);                                   // c1 complete
+                if (elect_one()) { tc_fence_after(); issue_conv2_seq(c116, w16, tmem + 96, std::make_integer_sequence<int, 18>{}); umma_commit(bar); }
+                __syncwarp();
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        return;
+    }
     const uint32_t tmem = *s_tmem + (uint32_t)wg * TA_TMEM_WG;
     const uint32_t tmem_lane = tmem + ((uint32_t)wq << 21);                    // lane quarter of this warp
-    const uint32_t in16 = smem_u32(s_in) >> 4, c116 = smem_u32(s_c1) >> 4, w16 = smem_u32(s_w) >> 4;
     uint64_t* bar = &s_bar[wg];
     uint32_t phase = 0;
     bool ok = true;
 
-    const int64_t stride = (int64_t)gridDim.x * TA_WGS;
     int64_t site = (int64_t)blockIdx.x * TA_WGS + wg;
     const bool raw_mode = P.in_mode != 0;
     uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = make_uint4(0, 0, 0, 0);
-    auto prefetch = [&](int64_t sidx) {          // 2064 B of int16 -> registers, 16 B per thread (+1 chunk on thread 0)
+    float pre_sf = 1.f; double pre_sd = 1.0;
+    auto prefetch = [&](int64_t sidx) {          // 2064 B of int16 -> registers, 16 B per thread (+1 chunk on thread 0), and the site's scale
         const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(P.in) + sidx * P.in_site_stride * 2);
         pre0 = __ldg(src + t);
         if (t == 0) pre1 = __ldg(src + 128);
+        if (P.in_mode == 1) pre_sf = __ldg(P.scale_f + sidx);
+        if (P.in_mode == 2) pre_sd = __ldg(P.scale_d + sidx);
     };
     // site image (registers) -> padded fp16 hi / lo planes (pixel row = (h+2)*45 + (w+2)); channels 5..7 stay zero
     auto convert = [&](int64_t sidx) {
-        float sc_f = 1.f; double sc_d = 1.0;
-        if (P.in_mode == 1) sc_f = __ldg(P.scale_f + sidx);
-        if (P.in_mode == 2) sc_d = __ldg(P.scale_d + sidx);
+        const float sc_f = pre_sf; const double sc_d = pre_sd;
         if (raw_mode) {
             *reinterpret_cast<uint4*>(s_raw + t * 16) = pre0;
             if (t == 0) *reinterpret_cast<uint4*>(s_raw + 2048) = pre1;
@@ -378,15 +400,15 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
 #pragma unroll
                     for (int c = 0; c < 5; c++) {
                         const int16_t raw = rp[c];
-                        float x = (float)raw;
+                        float x = __int_as_float(0x4B400000 + (int)raw) - 12582912.f;      // exact int16 -> fp32 without the conversion pipe
                         if (h > 0 && c < 4) x = P.in_mode == 1 ? __fmul_rn(x, sc_f) : (float)((double)raw * sc_d);
                         v[c] = x;
                     }
                 }
                 uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-                split2(fmaxf(v[0], -65000.f), fmaxf(v[1], -65000.f), hi.x, lo.x);
-                split2(fmaxf(v[2], -65000.f), fmaxf(v[3], -65000.f), hi.y, lo.y);
-                split2(fmaxf(v[4], -65000.f), 0.f, hi.z, lo.z);
+                split2(v[0], v[1], hi.x, lo.x);
+                split2(v[2], v[3], hi.y, lo.y);
+                split2(v[4], 0.f, hi.z, lo.z);
                 const int row = (h + 2) * tcg::WP + w + 2;
                 *reinterpret_cast<uint4*>(s_in + row * 16) = hi;
                 *reinterpret_cast<uint4*>(s_in + tcg::IN_PLANE + row * 16) = lo;
@@ -404,7 +426,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
 #pragma unroll
             for (int kg = 0; kg < 6; kg++) {
                 uint4 hi, lo;
-                act_split8(v + 8 * kg, s_bias + 8 * kg, hi, lo);
+                act_split8(v + 8 * kg, s_bias + 8 * kg, s_bl + 8 * kg, hi, lo);
                 *reinterpret_cast<uint4*>(dst + kg * tcg::C1_PLANE) = hi;
                 *reinterpret_cast<uint4*>(dst + (12 + kg) * tcg::C1_PLANE) = lo;
             }
@@ -420,11 +442,12 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
     auto store_c2 = [&](int64_t sidx, const float* acc) {
         const int m = t, h2 = m / tcg::C1_PITCH, w2 = m - h2 * tcg::C1_PITCH;
         if (m < 84 && w2 < 20) {
-            uint8_t* dst = P.c2_out + (sidx / 3) * tcg::C2_GROUP_BYTES + (int)(sidx % 3) * tcg::C2_CHUNK + ((w2 & 1) * 4) * tcg::C2_PLANE + (h2 * tcg::C2_PITCH + (w2 >> 1)) * 16;
+            const uint32_t grp = (uint32_t)sidx / 3u, sub = (uint32_t)sidx - 3u * grp;       // site counts stay below 2^31
+            uint8_t* dst = P.c2_out + (int64_t)grp * tcg::C2_GROUP_BYTES + sub * tcg::C2_CHUNK + ((w2 & 1) * 4) * tcg::C2_PLANE + (h2 * tcg::C2_PITCH + (w2 >> 1)) * 16;
 #pragma unroll
             for (int kg = 0; kg < 4; kg++) {
                 uint4 hi, lo;
-                act_split8(acc + 8 * kg, s_bias + 48 + 8 * kg, hi, lo);
+                act_split8(acc + 8 * kg, s_bias + 48 + 8 * kg, s_bl + 48 + 8 * kg, hi, lo);
                 *reinterpret_cast<uint4*>(dst + kg * tcg::C2_PLANE) = hi;
                 *reinterpret_cast<uint4*>(dst + (8 + kg) * tcg::C2_PLANE) = lo;
             }
@@ -436,56 +459,55 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
         convert(site);
         if (raw_mode && site + stride < P.n_sites) prefetch(site + stride);
     }
-    fence_async_smem();
-    tc_fence_before();
-    wg_barrier(wg);
 
+#ifdef NC_TA_PROFILE      // development aid: cycles per phase of the site loop, printed by (block 0, warpgroup 0, threads 0 and 64)
+    uint32_t prof[13], prof_last = (uint32_t)clock(), prof_n = 0;
+    for (int i = 0; i < 13; i++) prof[i] = 0;
+#define NC_TA_MARK(i) { const uint32_t now_ = (uint32_t)clock(); prof[i] += now_ - prof_last; prof_last = now_; if (i == 12) prof_n++; }
+#else
+#define NC_TA_MARK(i)
+#endif
     float acc2[32];
     int64_t prev = -1;
     for (; site < P.n_sites; site += stride) {
-        // ---- conv1, rows 0..127
-        if (wq == 0 && elect_one()) {
-            tc_fence_after();
-            issue_conv1_tile(in16, w16, tmem);
-            umma_commit(bar);
-        }
-        __syncwarp();
+        NC_TA_MARK(0);
+        // ---- conv1, rows 0..127: this site's input planes are written, the previous site's accumulators are in registers
+        fence_async_smem();
+        tc_fence_before();
+        wg_issuer_barrier(wg);
+        NC_TA_MARK(1);
         if (prev >= 0) store_c2(prev, acc2);                          // overlaps the MMAs just issued
+        NC_TA_MARK(2);
         ok = mbar_wait(bar, phase) && ok; phase ^= 1;
         tc_fence_after();
+        NC_TA_MARK(3);
         float v[48];
         load_c1(v);
         tc_fence_before();
-        wg_barrier(wg);                                               // every warp has read its accumulator rows
-        // ---- conv1, rows 97..224 (same accumulator columns)
-        if (wq == 0 && elect_one()) {
-            tc_fence_after();
-            issue_conv1_tile(in16 + tcg::TILE1_START, w16, tmem);
-            umma_commit(bar);
-        }
-        __syncwarp();
+        wg_issuer_barrier(wg);                                        // every warp has read its accumulator rows: conv1 rows 97..224 may start
+        NC_TA_MARK(4);
+        NC_TA_MARK(5);
         store_c1(0, v);                                               // overlaps tile 1
+        NC_TA_MARK(6);
         ok = mbar_wait(bar, phase) && ok; phase ^= 1;
         tc_fence_after();
+        NC_TA_MARK(7);
         load_c1(v);
         store_c1(1, v);
         fence_async_smem();
         tc_fence_before();
-        wg_barrier(wg);                                               // c1 complete; input planes and conv1 columns free
-        // ---- conv2: one tile (rows h2*21 + w2)
-        if (wq == 0 && elect_one()) {
-            tc_fence_after();
-            issue_conv2_seq(c116, w16, tmem + 96, std::make_integer_sequence<int, 18>{});
-            umma_commit(bar);
-        }
-        __syncwarp();
+        wg_issuer_barrier(wg);                                        // c1 complete: conv2 may start; input planes and conv1 columns are free
+        NC_TA_MARK(8);
+        NC_TA_MARK(9);
         const int64_t next = site + stride;
         if (next < P.n_sites) {                                       // overlaps conv2
             convert(next);
             if (raw_mode && next + stride < P.n_sites) prefetch(next + stride);
         }
+        NC_TA_MARK(10);
         ok = mbar_wait(bar, phase) && ok; phase ^= 1;
         tc_fence_after();
+        NC_TA_MARK(11);
         {
             // columns 96..127 = (a_hi + a_lo) w_hi, 128..159 = a_hi w_lo
             float lo_part[32];
@@ -498,11 +520,17 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
             for (int i = 0; i < 32; i++) acc2[i] += lo_part[i];
         }
         prev = site;
-        fence_async_smem();
-        tc_fence_before();
-        wg_barrier(wg);                                               // next site's planes visible; conv2 columns and c1 free
+        NC_TA_MARK(12);
     }
     if (prev >= 0) store_c2(prev, acc2);
+#ifdef NC_TA_PROFILE
+    if (blockIdx.x == 0 && wg == 0 && (t == 0 || t == 64) && prof_n > 0) {
+        printf("TA profile t=%d sites=%u cycles/site:", t, prof_n);
+        for (int i = 0; i < 13; i++) printf(" [%d]%u", i, prof[i] / prof_n);
+        printf("\n");
+    }
+#endif
+#undef NC_TA_MARK
     if (!ok && t == 0) atomicExch(P.err, 1);
     tc_fence_before();
     __syncthreads();
@@ -519,21 +547,22 @@ struct TBParams {
 };
 constexpr int TB_WGS = 3;
 constexpr int TB_THREADS = TB_WGS * 128;
-constexpr int TB_SMEM_MISC = 64 * 4 + 96;
+constexpr int TB_SMEM_MISC = 128 * 4 + 96;
 constexpr int TB_SMEM = tcg::W3_BYTES + TB_WGS * tcg::C2_SMEM + TB_SMEM_MISC + 64;
 
 __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_w = smem;
     float* s_bias = reinterpret_cast<float*>(smem + tcg::W3_BYTES + TB_WGS * tcg::C2_SMEM);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 64);
+    float* s_bl = s_bias + 64;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bl + 64);
     uint64_t* s_full = s_bar + 4;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
     const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = tid >> 5, wq = warp & 3;
     uint8_t* s_c2 = smem + tcg::W3_BYTES + wg * tcg::C2_SMEM;
 
     for (int i = tid; i < tcg::W3_BYTES / 16; i += TB_THREADS) reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(P.wimg) + i);
-    if (tid < 64) s_bias[tid] = P.bias[tid];
+    if (tid < 64) { const float b = P.bias[tid]; s_bias[tid] = b; s_bl[tid] = b * 1.4426950408889634f; }
     for (int i = tid; i < TB_WGS * tcg::C2_SMEM / 16; i += TB_THREADS) reinterpret_cast<uint4*>(smem + tcg::W3_BYTES)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         for (int i = 0; i < TB_WGS; i++) { mbar_init(&s_bar[i], 1); mbar_init(&s_full[i], 1); }
@@ -598,7 +627,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
                     for (int g = 0; g < 4; g++) {
                         uint4 hi, lo;
                         const int kg = half * 4 + g;
-                        act_split8(acc + 8 * g, s_bias + 8 * kg, hi, lo);
+                        act_split8(acc + 8 * g, s_bias + 8 * kg, s_bl + 8 * kg, hi, lo);
                         *reinterpret_cast<uint4*>(dst + (int64_t)kg * 2048) = hi;
                         *reinterpret_cast<uint4*>(dst + (int64_t)(tcg::FC_KG + kg) * 2048) = lo;
                     }
