@@ -184,16 +184,83 @@ __global__ void __launch_bounds__(1024) prefix_max_kernel(const int32_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// K0b — aligned-row fill: one CTA per read, one thread per output word (8 reference positions).
-// BAM 4-bit base -> code LUT packed in a u64: '='4 A0 C3 M4 G1 R4 S4 V4 T2 W..N 4.
+// K0b — aligned-row fill: one CTA per read (reads handed out dynamically, long reads dominate), one
+// thread per output word (8 reference positions), a warp per block of 32 words (256 positions).
+//   1. one linear pass over the read's ops records, per 256-position block, the op containing the
+//      block's first position (shared memory);
+//   2. a warp stages the ops of its block in shared memory (typically ~16), every lane finds the op
+//      of its word by binary search there and walks the <= few segments of its 8 positions;
+//   3. a match segment is a run of consecutive query bases: two aligned 32-bit loads of the packed
+//      4-bit sequence, nibble swap (BAM stores the first base of a byte in the high nibble), funnel
+//      shift to the run's first base, and the BAM-code -> tensor-code map on all 8 nibbles at once.
+// BAM 4-bit base codes: '='0 A1 C2 M3 G4 R5 S6 V7 T8 W9 Y10 H11 K12 D13 B14 N15 -> A0 G1 T2 C3, all else 4.
 // ------------------------------------------------------------------------------------------------
-constexpr uint64_t kNibToCode = 0x4444444244414304ull;
-
-// One CTA per read, one thread per output word.  Threads first build, in shared memory, a coarse index (the op
-// containing every 256th position: one full binary search per 32 words), then every thread narrows its own search to
-// the ops between two index entries, walks its 8 positions, and fetches the 8 bases with independent loads.
+constexpr uint64_t kNibToCode = 0x4444444244414304ull;   // the same map as a 16-entry nibble table (scalar users)
 constexpr int kFillThreads = 128;
-constexpr int kFillIdx = 512;            // coarse index entries kept in shared memory (reads up to 131 kb; longer: global search)
+constexpr int kFillWarps = kFillThreads / 32;
+constexpr int kFillIdx = 1024;           // blocks indexed in shared memory (reads up to 262 kb; longer reads: global search)
+constexpr int kFillOps = 96;             // ops staged per block (more: global search for that block)
+
+// 8 BAM base codes (one per nibble) -> 8 tensor codes
+__device__ __forceinline__ uint32_t bam_codes_to_tensor_codes(uint32_t n) {
+    const uint32_t M1 = 0x11111111u;
+    const uint32_t b0 = n & M1, b1 = (n >> 1) & M1, b2 = (n >> 2) & M1, b3 = (n >> 3) & M1;
+    const uint32_t isA = b0 & ~(b1 | b2 | b3), isC = b1 & ~(b0 | b2 | b3), isG = b2 & ~(b0 | b1 | b3), isT = b3 & ~(b0 | b1 | b2);
+    return (isC | isG) | ((isC | isT) << 1) | (((isA | isC | isG | isT) ^ M1) << 2);
+}
+__device__ __forceinline__ uint32_t swap_nibbles(uint32_t w) { return ((w & 0x0F0F0F0Fu) << 4) | ((w >> 4) & 0x0F0F0F0Fu); }
+// tensor codes of the 8 query bases starting at absolute nibble index Q of the packed sequence array
+__device__ __forceinline__ uint32_t fetch_codes8(const uint32_t* __restrict__ seq32, int64_t Q) {
+    const uint32_t lo = swap_nibbles(__ldg(seq32 + (Q >> 3))), hi = swap_nibbles(__ldg(seq32 + (Q >> 3) + 1));
+    return bam_codes_to_tensor_codes(__funnelshift_r(lo, hi, 4 * (int)(Q & 7)));
+}
+__device__ __forceinline__ uint32_t nib_mask(int n) { return n >= 8 ? 0xFFFFFFFFu : ((1u << (4 * n)) - 1u); }   // n low nibbles
+
+struct OpsShared {                        // ops of one block staged in shared memory
+    const int32_t* x; const int32_t* y; const uint32_t* w;
+    __device__ __forceinline__ int32_t ox(int j) const { return x[j]; }
+    __device__ __forceinline__ int32_t oy(int j) const { return y[j]; }
+    __device__ __forceinline__ uint32_t ow(int j) const { return w[j]; }
+};
+struct OpsGlobal {                        // straight from global memory (very long reads, very dense blocks)
+    const int2* st; const uint32_t* w;
+    __device__ __forceinline__ int32_t ox(int j) const { return __ldg(&st[j].x); }
+    __device__ __forceinline__ int32_t oy(int j) const { return __ldg(&st[j].y); }
+    __device__ __forceinline__ uint32_t ow(int j) const { return __ldg(w + j); }
+};
+
+// One output word: read-relative offset o of nibble 0 (in [-7, span)), ops [0, n) with ops.ox(0) <= max(o, 0).
+template <class Ops>
+__device__ __forceinline__ uint32_t fill_word(const Ops& ops, int n, int32_t o, int32_t span, int32_t lseq,
+                                              const uint32_t* __restrict__ seq32, int64_t q_base) {
+    uint32_t word = 0xFFFFFFFFu;                                    // 0xF = not covered
+    int t = o < 0 ? -o : 0;
+    int32_t oo = o + t;
+    if (oo >= span) return word;
+    int lo = 0, hi = n;                                             // last op whose reference start is <= oo
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ops.ox(mid) <= oo) lo = mid + 1; else hi = mid; }
+    int j = lo - 1;
+    uint32_t cw = ops.ow(j);
+    int32_t x = ops.ox(j), rl = cig_ref_len(cw);
+    const int32_t stop = min(o + 8, span);
+    while (oo < stop) {
+        while (oo >= x + rl) { j++; cw = ops.ow(j); x = ops.ox(j); rl = cig_ref_len(cw); }      // terminates: oo < span = total reference length
+        const int L = min(x + rl, stop) - oo;                      // 1..8 positions under this op
+        uint32_t vals = 0x44444444u;                                // '*': deletion, ref-skip, base beyond l_seq
+        if (cig_is_match(cw)) {
+            const int32_t q = ops.oy(j) + (oo - x);
+            const int Lv = min(L, lseq - q);                        // bases that exist
+            if (Lv > 0) {
+                const uint32_t m = nib_mask(Lv);
+                vals = (fetch_codes8(seq32, q_base + q) & m) | (vals & ~m);
+            }
+        }
+        const uint32_t m = nib_mask(L) << (4 * t);
+        word = (word & ~m) | ((vals << (4 * t)) & m);
+        t += L; oo += L;
+    }
+    return word;
+}
 
 __global__ void __launch_bounds__(kFillThreads) row_fill_kernel(const int32_t* __restrict__ pos, const int32_t* __restrict__ end,
                                                        const int64_t* __restrict__ cigar_off,
@@ -204,69 +271,62 @@ __global__ void __launch_bounds__(kFillThreads) row_fill_kernel(const int32_t* _
                                                        const uint8_t* __restrict__ seq4,
                                                        const int64_t* __restrict__ rowoff,
                                                        const int32_t* __restrict__ nwords,
-                                                       uint32_t* __restrict__ rows, int64_t n_reads) {
+                                                       uint32_t* __restrict__ rows, int64_t n_reads,
+                                                       unsigned long long* __restrict__ next_read) {
     __shared__ int32_t s_idx[kFillIdx + 1];
-    for (int64_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+    __shared__ int32_t s_ox[kFillWarps][kFillOps], s_oy[kFillWarps][kFillOps];
+    __shared__ uint32_t s_ow[kFillWarps][kFillOps];
+    __shared__ long long s_read;
+    const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+    const uint32_t* __restrict__ seq32 = reinterpret_cast<const uint32_t*>(seq4);
+    for (;;) {
+        __syncthreads();                                        // previous read's index and s_read no longer in use
+        if (tid == 0) s_read = (long long)atomicAdd(next_read, 1ull);
+        __syncthreads();
+        const int64_t r = s_read;
+        if (r >= n_reads) return;
         const int32_t nw = nwords[r];
         if (nw == 0) continue;
-        const int32_t p0 = pos[r], span = end[r] - p0, a0 = p0 & ~7;
+        const int32_t p0 = pos[r], span = end[r] - p0, d = p0 & 7;
         const int64_t c0 = cigar_off[r];
         const int32_t nops = (int32_t)(cigar_off[r + 1] - c0);
         const int32_t lseq = l_seq[r];
-        const uint8_t* __restrict__ sq = seq4 + seq_off[r];
+        const int64_t q_base = 2 * seq_off[r];                  // absolute nibble index of the read's first base
         uint32_t* __restrict__ out = rows + rowoff[r];
-        const int32_t nblk = min((nw + 31) >> 5, kFillIdx);
-        __syncthreads();                                        // previous read's index no longer in use
-        for (int32_t b = threadIdx.x; b <= nblk; b += kFillThreads) {
-            // last op whose reference start is <= offset of word 32*b (upper bound for b == nblk: last op)
-            const int32_t os = min(max(a0 + 256 * b - p0, 0), span);
-            int32_t lo = 0, hi = nops;
-            while (lo < hi) { int32_t mid = (lo + hi) >> 1; if (__ldg(&opstart[c0 + mid].x) <= os) lo = mid + 1; else hi = mid; }
-            s_idx[b] = lo - 1;
+        const int32_t nblk = (nw + 31) >> 5;
+        const OpsGlobal gops = {opstart + c0, cigar + c0};
+        if (nblk > kFillIdx) {                                  // longer than the shared index: every word searches all ops
+            for (int32_t w = tid; w < nw; w += kFillThreads) out[w] = fill_word(gops, nops, 8 * w - d, span, lseq, seq32, q_base);
+            continue;
+        }
+        // ---- 1. per block b, the op containing its first position max(256 b - d, 0)
+        for (int32_t k = tid; k < nops; k += kFillThreads) {
+            const int32_t rl = cig_ref_len(__ldg(cigar + c0 + k));
+            if (rl == 0) continue;
+            const int32_t x = __ldg(&opstart[c0 + k].x);
+            const int32_t b_lo = x == 0 ? 0 : (x + d + 255) >> 8, b_hi = min((x + rl - 1 + d) >> 8, nblk - 1);
+            for (int32_t b = b_lo; b <= b_hi; b++) s_idx[b] = k;
         }
         __syncthreads();
-        for (int32_t w = threadIdx.x; w < nw; w += kFillThreads) {
-            const int32_t o = a0 + 8 * w - p0;                 // read-relative offset of nibble 0, in [-7, span)
-            const int32_t os = o < 0 ? 0 : o;
-            const int32_t b = w >> 5;
-            int32_t lo, hi;                                    // search window: ops between two coarse index entries
-            if (b < nblk) { lo = s_idx[b]; hi = min(s_idx[b + 1] + 1, nops); } else { lo = s_idx[nblk]; hi = nops; }
-            lo = max(lo, 0);
-            while (lo < hi) { int32_t mid = (lo + hi) >> 1; if (__ldg(&opstart[c0 + mid].x) <= os) lo = mid + 1; else hi = mid; }
-            int32_t k = lo - 1;
-            uint32_t cw = __ldg(cigar + c0 + k);
-            int2 st = __ldg(opstart + c0 + k);
-            int32_t rl = cig_ref_len(cw);
-            int32_t qi[8];                                     // query index per position; -1: '*' (D / N / bad base), -2: not covered
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                const int32_t oo = o + t;
-                qi[t] = -2;
-                if (oo >= 0 && oo < span) {
-                    while (oo >= st.x + rl) {                  // terminates: oo < span = total reference length
-                        k++;
-                        cw = __ldg(cigar + c0 + k);
-                        st = __ldg(opstart + c0 + k);
-                        rl = cig_ref_len(cw);
-                    }
-                    const int32_t q = st.y + (oo - st.x);
-                    qi[t] = (cig_is_match(cw) && q < lseq) ? q : -1;
-                }
-            }
-            uint32_t bb[8];
-#pragma unroll
-            for (int t = 0; t < 8; t++) bb[t] = qi[t] >= 0 ? (uint32_t)__ldg(sq + (qi[t] >> 1)) : 0u;
+        // ---- 2. a warp per block
+        for (int32_t b = wi; b < nblk; b += kFillWarps) {
+            const int32_t k0 = s_idx[b], k1 = b + 1 < nblk ? s_idx[b + 1] : nops - 1;
+            const int32_t n = k1 - k0 + 1, w = 32 * b + lane;
             uint32_t word = 0;
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                uint32_t nib = qi[t] == -2 ? 15u : 4u;
-                if (qi[t] >= 0) {
-                    const uint32_t bn = (qi[t] & 1) ? (bb[t] & 15u) : (bb[t] >> 4);
-                    nib = (uint32_t)(kNibToCode >> (4 * bn)) & 15u;
+            if (n <= kFillOps) {
+                __syncwarp();
+                for (int32_t j = lane; j < n; j += 32) {
+                    const int2 st = __ldg(opstart + c0 + k0 + j);
+                    s_ox[wi][j] = st.x; s_oy[wi][j] = st.y; s_ow[wi][j] = __ldg(cigar + c0 + k0 + j);
                 }
-                word |= nib << (4 * t);
+                __syncwarp();
+                const OpsShared sops = {s_ox[wi], s_oy[wi], s_ow[wi]};
+                if (w < nw) word = fill_word(sops, n, 8 * w - d, span, lseq, seq32, q_base);
+            } else {
+                const OpsGlobal bops = {opstart + c0 + k0, cigar + c0 + k0};
+                if (w < nw) word = fill_word(bops, n, 8 * w - d, span, lseq, seq32, q_base);
             }
-            out[w] = word;
+            if (w < nw) out[w] = word;
         }
     }
 }
