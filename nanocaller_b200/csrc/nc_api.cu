@@ -42,7 +42,7 @@ struct nc_ctx {
     // staged contig
     bool staged = false, decoded = false, scanned = false;
     int64_t n_reads = 0, n_cigar = 0, n_seq = 0, ref_start = 0, ref_len = 0;
-    DevBuf d_pos, d_flag, d_cigar_off, d_cigar, d_seq_off, d_lseq, d_seq4, d_ref, d_fill_counter;
+    DevBuf d_pos, d_flag, d_cigar_off, d_cigar, d_seq_off, d_lseq, d_seq4, d_ref, d_fill_counter, d_seqc;
     // decode products
     DevBuf d_end, d_nwords, d_opstart, d_pmaxend, d_rowoff, d_rows;
     int64_t n_row_words = 0;
@@ -350,7 +350,7 @@ void nc_destroy(nc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->d_pos, &c->d_flag, &c->d_cigar_off, &c->d_cigar, &c->d_seq_off, &c->d_lseq, &c->d_seq4, &c->d_ref, &c->d_fill_counter,
+    DevBuf* bufs[] = {&c->d_pos, &c->d_flag, &c->d_cigar_off, &c->d_cigar, &c->d_seq_off, &c->d_lseq, &c->d_seq4, &c->d_ref, &c->d_fill_counter, &c->d_seqc,
                       &c->d_end, &c->d_nwords, &c->d_opstart, &c->d_pmaxend, &c->d_rowoff, &c->d_rows, &c->d_flags,
                       &c->d_tile_nbr, &c->d_tile_cand, &c->d_nbr_off, &c->d_cand_off, &c->d_nbr_pos, &c->d_cand_pos, &c->d_bed,
                       &c->d_nfirst, &c->d_nlen, &c->d_nbytes, &c->d_noff, &c->d_nrows, &c->d_chunks, &c->d_chunk_lo,
@@ -482,10 +482,17 @@ int nc_decode_reads(nc_ctx* c) {
         NC_CUDA(c->d_rows.reserve((size_t)std::max<int64_t>(c->n_row_words, 1) * 4));
         NC_CUDA(c->d_fill_counter.reserve(8));
         NC_CUDA(cudaMemsetAsync(c->d_fill_counter.p, 0, 8, c->stream));
+        const int64_t n_vec = div_up(c->n_seq, 16);
+        NC_CUDA(c->d_seqc.reserve((size_t)n_vec * 16 + 64));
+        if (n_vec > 0) {
+            seq_codes_kernel<<<(unsigned)std::min<int64_t>(div_up(n_vec, 256), (int64_t)c->sm_count * 16), 256, 0, c->stream>>>(
+                c->d_seq4.as<uint4>(), n_vec, c->d_seqc.as<uint4>());
+            NC_LAUNCH_CHECK();
+        }
         const unsigned g2 = (unsigned)std::min<int64_t>(n, (int64_t)c->sm_count * 12);      // persistent CTAs, reads handed out dynamically
         row_fill_kernel<<<g2, kFillThreads, 0, c->stream>>>(c->d_pos.as<int32_t>(), c->d_end.as<int32_t>(), c->d_cigar_off.as<int64_t>(),
                                                    c->d_cigar.as<uint32_t>(), c->d_opstart.as<int2>(), c->d_seq_off.as<int64_t>(),
-                                                   c->d_lseq.as<int32_t>(), c->d_seq4.as<uint8_t>(), c->d_rowoff.as<int64_t>(),
+                                                   c->d_lseq.as<int32_t>(), c->d_seqc.as<uint32_t>(), c->d_rowoff.as<int64_t>(),
                                                    c->d_nwords.as<int32_t>(), c->d_rows.as<uint32_t>(), n,
                                                    c->d_fill_counter.as<unsigned long long>());
         NC_LAUNCH_CHECK();

@@ -184,22 +184,12 @@ __global__ void __launch_bounds__(1024) prefix_max_kernel(const int32_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// K0b — aligned-row fill: one CTA per read (reads handed out dynamically, long reads dominate), one
-// thread per output word (8 reference positions), a warp per block of 32 words (256 positions).
-//   1. one linear pass over the read's ops records, per 256-position block, the op containing the
-//      block's first position (shared memory);
-//   2. a warp stages the ops of its block in shared memory (typically ~16), every lane finds the op
-//      of its word by binary search there and walks the <= few segments of its 8 positions;
-//   3. a match segment is a run of consecutive query bases: two aligned 32-bit loads of the packed
-//      4-bit sequence, nibble swap (BAM stores the first base of a byte in the high nibble), funnel
-//      shift to the run's first base, and the BAM-code -> tensor-code map on all 8 nibbles at once.
-// BAM 4-bit base codes: '='0 A1 C2 M3 G4 R5 S6 V7 T8 W9 Y10 H11 K12 D13 B14 N15 -> A0 G1 T2 C3, all else 4.
+// K0c — query codes: the packed BAM sequence (4 bits per base, first base of a byte in the HIGH
+// nibble, codes '='0 A1 C2 M3 G4 R5 S6 V7 T8 W9 Y10 H11 K12 D13 B14 N15) -> tensor codes
+// (A0 G1 T2 C3, all else 4) with base i in nibble i & 7 of word i >> 3.  One streaming pass at HBM
+// speed; afterwards a run of aligned bases is a funnel shift of two words.
 // ------------------------------------------------------------------------------------------------
 constexpr uint64_t kNibToCode = 0x4444444244414304ull;   // the same map as a 16-entry nibble table (scalar users)
-constexpr int kFillThreads = 128;
-constexpr int kFillWarps = kFillThreads / 32;
-constexpr int kFillIdx = 1024;           // blocks indexed in shared memory (reads up to 262 kb; longer reads: global search)
-constexpr int kFillOps = 96;             // ops staged per block (more: global search for that block)
 
 // 8 BAM base codes (one per nibble) -> 8 tensor codes
 __device__ __forceinline__ uint32_t bam_codes_to_tensor_codes(uint32_t n) {
@@ -209,51 +199,60 @@ __device__ __forceinline__ uint32_t bam_codes_to_tensor_codes(uint32_t n) {
     return (isC | isG) | ((isC | isT) << 1) | (((isA | isC | isG | isT) ^ M1) << 2);
 }
 __device__ __forceinline__ uint32_t swap_nibbles(uint32_t w) { return ((w & 0x0F0F0F0Fu) << 4) | ((w >> 4) & 0x0F0F0F0Fu); }
-// tensor codes of the 8 query bases starting at absolute nibble index Q of the packed sequence array
-__device__ __forceinline__ uint32_t fetch_codes8(const uint32_t* __restrict__ seq32, int64_t Q) {
-    const uint32_t lo = swap_nibbles(__ldg(seq32 + (Q >> 3))), hi = swap_nibbles(__ldg(seq32 + (Q >> 3) + 1));
-    return bam_codes_to_tensor_codes(__funnelshift_r(lo, hi, 4 * (int)(Q & 7)));
+
+__global__ void __launch_bounds__(256) seq_codes_kernel(const uint4* __restrict__ seq4, int64_t n_vec, uint4* __restrict__ codes) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 v = __ldg(seq4 + i);
+        v.x = bam_codes_to_tensor_codes(swap_nibbles(v.x)); v.y = bam_codes_to_tensor_codes(swap_nibbles(v.y));
+        v.z = bam_codes_to_tensor_codes(swap_nibbles(v.z)); v.w = bam_codes_to_tensor_codes(swap_nibbles(v.w));
+        codes[i] = v;
+    }
 }
+
+// ------------------------------------------------------------------------------------------------
+// K0b — aligned-row fill: one CTA per read (reads handed out dynamically, long reads dominate), a
+// warp per block of 32 output words (256 reference positions).
+//   1. one linear pass over the read's ops records, per block, the op containing the block's first
+//      position (shared memory);
+//   2. the warp stages the block's ops (typically ~24 for ONT), counts for every reference-consuming
+//      op the words it touches, scans the counts and writes one entry per (op, word) SEGMENT;
+//   3. lanes take segments, not words (a word has 1..8 segments; lanes-as-words ran at 30 % lane
+//      occupancy): a match segment is a funnel shift of two words of query codes, a deletion is a
+//      constant; the partial word is AND-ed into the block's 32 words in shared memory (0xF = not
+//      covered is the identity), and the block is stored with one coalesced 128-byte write.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFillThreads = 128;
+constexpr int kFillWarps = kFillThreads / 32;
+constexpr int kFillIdx = 1024;           // blocks indexed in shared memory (reads up to 262 kb; longer reads: per-word global search)
+constexpr int kFillOps = 96;             // ops staged per block (more: per-word global search for that block)
+
 __device__ __forceinline__ uint32_t nib_mask(int n) { return n >= 8 ? 0xFFFFFFFFu : ((1u << (4 * n)) - 1u); }   // n low nibbles
+// tensor codes of the 8 query bases starting at absolute base index Q
+__device__ __forceinline__ uint32_t fetch_codes8(const uint32_t* __restrict__ codes, int64_t Q) {
+    return __funnelshift_r(__ldg(codes + (Q >> 3)), __ldg(codes + (Q >> 3) + 1), 4 * (int)(Q & 7));
+}
 
-struct OpsShared {                        // ops of one block staged in shared memory
-    const int32_t* x; const int32_t* y; const uint32_t* w;
-    __device__ __forceinline__ int32_t ox(int j) const { return x[j]; }
-    __device__ __forceinline__ int32_t oy(int j) const { return y[j]; }
-    __device__ __forceinline__ uint32_t ow(int j) const { return w[j]; }
-};
-struct OpsGlobal {                        // straight from global memory (very long reads, very dense blocks)
-    const int2* st; const uint32_t* w;
-    __device__ __forceinline__ int32_t ox(int j) const { return __ldg(&st[j].x); }
-    __device__ __forceinline__ int32_t oy(int j) const { return __ldg(&st[j].y); }
-    __device__ __forceinline__ uint32_t ow(int j) const { return __ldg(w + j); }
-};
-
-// One output word: read-relative offset o of nibble 0 (in [-7, span)), ops [0, n) with ops.ox(0) <= max(o, 0).
-template <class Ops>
-__device__ __forceinline__ uint32_t fill_word(const Ops& ops, int n, int32_t o, int32_t span, int32_t lseq,
-                                              const uint32_t* __restrict__ seq32, int64_t q_base) {
+// Fallback, one thread per word: read-relative offset o of nibble 0 (in [-7, span)), ops [0, n) in global memory.
+__device__ __forceinline__ uint32_t fill_word_global(const int2* __restrict__ st, const uint32_t* __restrict__ cig, int n, int32_t o,
+                                                     int32_t span, int32_t lseq, const uint32_t* __restrict__ codes, int64_t q_base) {
     uint32_t word = 0xFFFFFFFFu;                                    // 0xF = not covered
     int t = o < 0 ? -o : 0;
     int32_t oo = o + t;
     if (oo >= span) return word;
     int lo = 0, hi = n;                                             // last op whose reference start is <= oo
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ops.ox(mid) <= oo) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(&st[mid].x) <= oo) lo = mid + 1; else hi = mid; }
     int j = lo - 1;
-    uint32_t cw = ops.ow(j);
-    int32_t x = ops.ox(j), rl = cig_ref_len(cw);
+    uint32_t cw = __ldg(cig + j);
+    int32_t x = __ldg(&st[j].x), rl = cig_ref_len(cw);
     const int32_t stop = min(o + 8, span);
     while (oo < stop) {
-        while (oo >= x + rl) { j++; cw = ops.ow(j); x = ops.ox(j); rl = cig_ref_len(cw); }      // terminates: oo < span = total reference length
+        while (oo >= x + rl) { j++; cw = __ldg(cig + j); x = __ldg(&st[j].x); rl = cig_ref_len(cw); }   // terminates: oo < span
         const int L = min(x + rl, stop) - oo;                      // 1..8 positions under this op
         uint32_t vals = 0x44444444u;                                // '*': deletion, ref-skip, base beyond l_seq
         if (cig_is_match(cw)) {
-            const int32_t q = ops.oy(j) + (oo - x);
+            const int32_t q = __ldg(&st[j].y) + (oo - x);
             const int Lv = min(L, lseq - q);                        // bases that exist
-            if (Lv > 0) {
-                const uint32_t m = nib_mask(Lv);
-                vals = (fetch_codes8(seq32, q_base + q) & m) | (vals & ~m);
-            }
+            if (Lv > 0) { const uint32_t m = nib_mask(Lv); vals = (fetch_codes8(codes, q_base + q) & m) | (vals & ~m); }
         }
         const uint32_t m = nib_mask(L) << (4 * t);
         word = (word & ~m) | ((vals << (4 * t)) & m);
@@ -268,17 +267,21 @@ __global__ void __launch_bounds__(kFillThreads) row_fill_kernel(const int32_t* _
                                                        const int2* __restrict__ opstart,
                                                        const int64_t* __restrict__ seq_off,
                                                        const int32_t* __restrict__ l_seq,
-                                                       const uint8_t* __restrict__ seq4,
+                                                       const uint32_t* __restrict__ codes,
                                                        const int64_t* __restrict__ rowoff,
                                                        const int32_t* __restrict__ nwords,
                                                        uint32_t* __restrict__ rows, int64_t n_reads,
                                                        unsigned long long* __restrict__ next_read) {
     __shared__ int32_t s_idx[kFillIdx + 1];
-    __shared__ int32_t s_ox[kFillWarps][kFillOps], s_oy[kFillWarps][kFillOps];
-    __shared__ uint32_t s_ow[kFillWarps][kFillOps];
+    __shared__ int32_t s_x[kFillWarps][kFillOps];            // reference start of the op (read-relative)
+    __shared__ uint32_t s_xe[kFillWarps][kFillOps];          // reference end, bit 31 set when the op is not a match (D / N)
+    __shared__ long long s_q[kFillWarps][kFillOps];          // absolute query base index of reference offset 0 under this op
+    __shared__ uint16_t s_pref[kFillWarps][kFillOps];        // first segment of the op
+    __shared__ uint8_t s_wf[kFillWarps][kFillOps];           // first word of the op inside the block
+    __shared__ uint8_t s_segop[kFillWarps][32 + kFillOps];   // segment -> staged op
+    __shared__ uint32_t s_word[kFillWarps][32];
     __shared__ long long s_read;
     const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
-    const uint32_t* __restrict__ seq32 = reinterpret_cast<const uint32_t*>(seq4);
     for (;;) {
         __syncthreads();                                        // previous read's index and s_read no longer in use
         if (tid == 0) s_read = (long long)atomicAdd(next_read, 1ull);
@@ -291,12 +294,11 @@ __global__ void __launch_bounds__(kFillThreads) row_fill_kernel(const int32_t* _
         const int64_t c0 = cigar_off[r];
         const int32_t nops = (int32_t)(cigar_off[r + 1] - c0);
         const int32_t lseq = l_seq[r];
-        const int64_t q_base = 2 * seq_off[r];                  // absolute nibble index of the read's first base
+        const int64_t q_base = 2 * seq_off[r];                  // absolute index of the read's first base
         uint32_t* __restrict__ out = rows + rowoff[r];
         const int32_t nblk = (nw + 31) >> 5;
-        const OpsGlobal gops = {opstart + c0, cigar + c0};
         if (nblk > kFillIdx) {                                  // longer than the shared index: every word searches all ops
-            for (int32_t w = tid; w < nw; w += kFillThreads) out[w] = fill_word(gops, nops, 8 * w - d, span, lseq, seq32, q_base);
+            for (int32_t w = tid; w < nw; w += kFillThreads) out[w] = fill_word_global(opstart + c0, cigar + c0, nops, 8 * w - d, span, lseq, codes, q_base);
             continue;
         }
         // ---- 1. per block b, the op containing its first position max(256 b - d, 0)
@@ -312,21 +314,61 @@ __global__ void __launch_bounds__(kFillThreads) row_fill_kernel(const int32_t* _
         for (int32_t b = wi; b < nblk; b += kFillWarps) {
             const int32_t k0 = s_idx[b], k1 = b + 1 < nblk ? s_idx[b + 1] : nops - 1;
             const int32_t n = k1 - k0 + 1, w = 32 * b + lane;
-            uint32_t word = 0;
-            if (n <= kFillOps) {
-                __syncwarp();
-                for (int32_t j = lane; j < n; j += 32) {
-                    const int2 st = __ldg(opstart + c0 + k0 + j);
-                    s_ox[wi][j] = st.x; s_oy[wi][j] = st.y; s_ow[wi][j] = __ldg(cigar + c0 + k0 + j);
-                }
-                __syncwarp();
-                const OpsShared sops = {s_ox[wi], s_oy[wi], s_ow[wi]};
-                if (w < nw) word = fill_word(sops, n, 8 * w - d, span, lseq, seq32, q_base);
-            } else {
-                const OpsGlobal bops = {opstart + c0 + k0, cigar + c0 + k0};
-                if (w < nw) word = fill_word(bops, n, 8 * w - d, span, lseq, seq32, q_base);
+            const int32_t o_blk = 256 * b - d;                  // read-relative offset of the block's first nibble
+            if (n > kFillOps) {
+                if (w < nw) out[w] = fill_word_global(opstart + c0 + k0, cigar + c0 + k0, n, 8 * w - d, span, lseq, codes, q_base);
+                continue;
             }
-            if (w < nw) out[w] = word;
+            __syncwarp();
+            s_word[wi][lane] = 0xFFFFFFFFu;
+            int32_t carry = 0;
+            for (int32_t j0 = 0; j0 < n; j0 += 32) {
+                const int32_t j = j0 + lane;
+                int32_t cnt = 0, wf = 0;
+                if (j < n) {
+                    const uint32_t cw = __ldg(cigar + c0 + k0 + j);
+                    const int2 st = __ldg(opstart + c0 + k0 + j);
+                    const int32_t rl = cig_ref_len(cw);
+                    s_x[wi][j] = st.x;
+                    s_xe[wi][j] = (uint32_t)(st.x + rl) | (cig_is_match(cw) ? 0u : 0x80000000u);
+                    s_q[wi][j] = q_base + st.y - st.x;
+                    if (rl > 0) {
+                        wf = max(st.x - o_blk, 0) >> 3;
+                        const int32_t wl = min((st.x + rl - 1 - o_blk) >> 3, 31);
+                        cnt = max(wl - wf + 1, 0);             // 0 when the op lies before the block (cannot happen) or after it
+                    }
+                    s_wf[wi][j] = (uint8_t)wf;
+                }
+                const int32_t inc = warp_incl_scan32(cnt, lane);
+                const int32_t first = carry + inc - cnt;
+                if (j < n) s_pref[wi][j] = (uint16_t)first;
+                for (int32_t i = 0; i < cnt; i++) s_segop[wi][first + i] = (uint8_t)j;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            __syncwarp();
+            // ---- 3. lanes take segments
+            const int64_t q_end = q_base + lseq;
+            for (int32_t sg = lane; sg < carry; sg += 32) {
+                const int32_t j = s_segop[wi][sg];
+                const int32_t ww = (int32_t)s_wf[wi][j] + (sg - (int32_t)s_pref[wi][j]);
+                const int32_t o_w = o_blk + 8 * ww;
+                const uint32_t xe_enc = s_xe[wi][j];
+                const int32_t s0 = max(s_x[wi][j], o_w), s1 = min((int32_t)(xe_enc & 0x7FFFFFFFu), o_w + 8);
+                const int t = s0 - o_w, L = s1 - s0;           // 1 <= L <= 8
+                uint32_t vals = 0x44444444u;                    // '*': deletion, ref-skip, base beyond l_seq
+                if (!(xe_enc & 0x80000000u)) {
+                    const int64_t Q = s_q[wi][j] + s0;
+                    const int64_t left = q_end - Q;             // bases that exist from here on
+                    if (left > 0) {
+                        const uint32_t m = nib_mask((int)min((int64_t)L, left));
+                        vals = (fetch_codes8(codes, Q) & m) | (vals & ~m);
+                    }
+                }
+                const uint32_t m = nib_mask(L) << (4 * t);
+                atomicAnd(&s_word[wi][ww], ((vals << (4 * t)) & m) | ~m);
+            }
+            __syncwarp();
+            if (w < nw) out[w] = s_word[wi][lane];
         }
     }
 }
