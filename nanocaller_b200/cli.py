@@ -1,0 +1,263 @@
+"""`python -m nanocaller_b200 --bam X.bam --ref X.fa --mode snps --preset ont ...`
+
+The reference's command line (`NanoCaller:84-158`: same flags, defaults, preset table `:66-77`, region rules
+`nanocaller_src/utils.py:6-65`, chunk grid `utils.py:67-83`, output names `snpCaller.py:251-252`,
+`indelCaller.py:385-395`) driving the B200 path: BAM/FASTA -> staging arrays -> CUDA pileup + CNN -> VCF records ->
+sorted BGZF VCFs.  What is NOT here is everything the reference delegates to external programs between the two
+stages: `whatshap phase/haplotag` (`indelCaller.py:234-251`) — indel calling uses the HP/PS tags already present in
+`--bam`, as `--mode indels` does in the reference — and `rtg vcfdecompose` (`indelCaller.py:391`).  `--cpu` only sets
+the chunk grid (and with it the normalisation groups); the work runs on the GPU of
+`--device`.  There is no CPU fallback: without an sm_100 GPU the run fails in `nc_create`."""
+import argparse
+import datetime
+import gzip
+import os
+import sys
+import time
+
+PRESETS = {      # NanoCaller:66-77
+    "ont": dict(sequencing="ont", snp_model="ONT-HG002", indel_model="ONT-HG002", neighbor_threshold="0.4,0.6", ins_threshold=0.4,
+                del_threshold=0.6, enable_whatshap=False, impute_indel_phase=False),
+    "short_ont": dict(sequencing="short_ont", snp_model="ONT-HG002", indel_model="ONT-HG002", neighbor_threshold="0.3,0.7",
+                      ins_threshold=0.4, del_threshold=0.6, enable_whatshap=False, impute_indel_phase=False),
+    "ul_ont": dict(sequencing="ul_ont", snp_model="ONT-HG002", indel_model="ONT-HG002", neighbor_threshold="0.4,0.6", ins_threshold=0.4,
+                   del_threshold=0.6, enable_whatshap=False, impute_indel_phase=False),
+    "ul_ont_extreme": dict(sequencing="ul_ont_extreme", snp_model="ONT-HG002", indel_model="ONT-HG002", neighbor_threshold="0.4,0.6",
+                           ins_threshold=0.4, del_threshold=0.6, enable_whatshap=False, impute_indel_phase=False),
+    "ccs": dict(sequencing="pacbio", snp_model="CCS-HG002", indel_model="CCS-HG002", neighbor_threshold="0.3,0.7", ins_threshold=0.4,
+                del_threshold=0.4, enable_whatshap=True, impute_indel_phase=True),
+    "clr": dict(sequencing="pacbio", snp_model="CLR-HG002", indel_model="ONT-HG002", neighbor_threshold="0.3,0.6", ins_threshold=0.6,
+                del_threshold=0.6, win_size=10, small_win_size=2, enable_whatshap=True, impute_indel_phase=False),
+}
+
+
+def build_parser():
+    p = argparse.ArgumentParser(prog="nanocaller_b200", formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    req = p.add_argument_group("Required Arguments")
+    req.add_argument("--bam", required=True, help="BAM file (haplotagged with HP/PS tags for indel calling)")
+    req.add_argument("--ref", required=True, help="reference FASTA")
+    p.add_argument("--preset", choices=["ont", "ul_ont", "ul_ont_extreme", "ccs", "clr"], default=None)
+    p.add_argument("--mode", choices=["snps", "indels", "all"], default="all")
+    p.add_argument("--sequencing", choices=["short_ont", "ont", "ul_ont", "ul_ont_extreme", "pacbio"], default="ont")
+    p.add_argument("--cpu", type=int, default=1, help="sets the chunk grid exactly as in the reference (utils.py:72)")
+    p.add_argument("--mincov", type=int, default=4)
+    p.add_argument("--maxcov", type=int, default=160)
+    p.add_argument("--suppress_progress_bar", action="store_true", default=False)
+    p.add_argument("--haploid_genome", action="store_true", default=False)
+    p.add_argument("--haploid_X", action="store_true", default=False)
+    p.add_argument("--verbose", action="store_true", default=False)
+    p.add_argument("--output", type=str, default=None)
+    p.add_argument("--prefix", type=str, default="variant_calls")
+    p.add_argument("--sample", type=str, default="SAMPLE")
+    p.add_argument("--regions", nargs="*")
+    p.add_argument("--bed", type=str, default=None)
+    p.add_argument("--wgs_contigs", choices=["chr1-22XY", "1-22XY"], default=None)
+    p.add_argument("--exclude_bed", type=str, default=None, help="hg38 | hg19 | mm10 | mm39 (needs --nanocaller_src) or a BED path")
+    p.add_argument("--snp_model", default="ONT-HG002")
+    p.add_argument("--min_allele_freq", type=float, default=0.15)
+    p.add_argument("--min_nbr_sites", type=int, default=1)
+    p.add_argument("--neighbor_threshold", type=str, default="0.4,0.6")
+    p.add_argument("--supplementary", action="store_true", default=False)
+    p.add_argument("--disable_coverage_normalization", action="store_true", default=False)
+    p.add_argument("--indel_model", default="ONT-HG002")
+    p.add_argument("--ins_threshold", type=float, default=0.4)
+    p.add_argument("--del_threshold", type=float, default=0.6)
+    p.add_argument("--win_size", type=int, default=40)
+    p.add_argument("--small_win_size", type=int, default=4)
+    p.add_argument("--impute_indel_phase", action="store_true", default=False)
+    p.add_argument("--phase", action="store_true", default=False)
+    p.add_argument("--phase_qual_score", type=float, default=10)
+    p.add_argument("--enable_whatshap", action="store_true", default=False)
+    own = p.add_argument_group("nanocaller_b200")
+    own.add_argument("--device", type=int, default=0, help="CUDA device")
+    own.add_argument("--nanocaller_src", type=str, default=None, help="a NanoCaller checkout, for models / BED files that are not bundled")
+    return p
+
+
+def parse_args(argv):
+    """argparse + the preset rule of NanoCaller:164-174: a preset value applies unless the flag was given explicitly."""
+    args = build_parser().parse_args(argv)
+    args.supplementary = False                                   # NanoCaller:160
+    set_flags = {x.replace("-", "").split("=")[0] for x in argv if x.startswith("--")}
+    if args.preset:
+        for k, v in PRESETS[args.preset].items():
+            if k not in set_flags:
+                setattr(args, k, v)
+    if not args.output:
+        args.output = os.getcwd()
+    return args
+
+
+def get_regions_list(args, contig_lengths):
+    """utils.get_regions_list (utils.py:6-65).  `contig_lengths`: ordered {name: length} from the BAM header."""
+    ploidy = "haploid" if args.haploid_genome else "diploid"
+    regions = []
+    if args.wgs_contigs:
+        for c in list(range(1, 23)) + ["X", "Y"]:
+            name = ("chr%s" % c) if args.wgs_contigs == "chr1-22XY" else str(c)
+            if name in contig_lengths:
+                regions.append([name, 1, contig_lengths[name], ploidy])
+    elif args.regions:
+        for r in args.regions:
+            r2 = r.split(":")
+            if len(r2) == 1:
+                if r2[0] in contig_lengths:
+                    regions.append([r2[0], 1, contig_lengths[r2[0]], ploidy])
+                else:
+                    print("\n%s: Contig %s not present in the BAM file." % (datetime.datetime.now(), r2[0]), flush=True)
+            elif len(r2) == 2 and len(r2[1].split("-")) == 2:
+                a, b = r2[1].split("-")
+                regions.append([r2[0], int(a), int(b), ploidy])
+            else:
+                print("\n%s: Invalid region %s." % (datetime.datetime.now(), r), flush=True)
+    elif args.bed:
+        with open(args.bed) as f:
+            for line in f:
+                t = line.rstrip("\n").split()
+                if not t:
+                    continue
+                if t[0] in contig_lengths:
+                    regions.append([t[0], int(t[1]), int(t[2]), ploidy])
+                else:
+                    print("\n%s: Contig %s not present in the BAM file." % (datetime.datetime.now(), t[0]), flush=True)
+    else:
+        regions = [[c, 1, n, ploidy] for c, n in contig_lengths.items()]
+    if not regions:
+        print("\n%s: No valid regions found." % datetime.datetime.now(), flush=True)
+        raise SystemExit(2)
+    for r in regions:                                             # utils.py:54-60
+        if r[0] in ("chrY", "Y", "chrM", "M"):
+            r[3] = "haploid"
+        elif r[0] in ("chrX", "X"):
+            r[3] = "haploid" if args.haploid_X else "diploid"
+    return [tuple(r) for r in regions]
+
+
+def get_chunks(regions_list, cpu, max_chunk_size=500000, min_chunk_size=10000):
+    """utils.py:67-83: inclusive chunk ends, shared between neighbours."""
+    total = sum(r[2] - r[1] + 1 for r in regions_list)
+    size = min(max_chunk_size, max(min_chunk_size, total // cpu + 1))
+    return [{"chrom": c, "start": s, "end": min(end, s + size), "ploidy": pl}
+            for c, start, end, pl in regions_list for s in range(start, end, size)]
+
+
+def _load_exclude_bed(args):
+    """-> registered BED key or None.  Accepts the reference's genome names (files live in a NanoCaller checkout) or a path."""
+    from .host import sources
+    name = args.exclude_bed
+    if not name:
+        return None
+    path = name
+    if name in ("hg38", "hg19", "mm10", "mm39"):
+        if not args.nanocaller_src:
+            raise SystemExit("--exclude_bed %s: the BED files are not bundled; pass --nanocaller_src <NanoCaller checkout>" % name)
+        path = os.path.join(args.nanocaller_src, "nanocaller_src/release_data/bed_files/%s_centro_telo.bed.gz" % name)
+    opener = gzip.open if open(path, "rb").read(2) == b"\x1f\x8b" else open
+    table = {}
+    with opener(path, "rt") as f:
+        for line in f:
+            t = line.split()
+            if len(t) >= 3 and not line.startswith(("#", "track", "browser")):
+                table.setdefault(t[0], []).append((int(t[1]), int(t[2])))
+    sources.register_bed(path, table)
+    return path
+
+
+def _groups(chunks):
+    """Consecutive chunks of one (contig, ploidy): one staging + one batched launch sequence each."""
+    out = []
+    for c in chunks:
+        if out and out[-1][0]["chrom"] == c["chrom"] and out[-1][0]["ploidy"] == c["ploidy"]:
+            out[-1].append(c)
+        else:
+            out.append([c])
+    return out
+
+
+def run(args):
+    from .host import bamio, indel_caller, models, snp_caller, snp_pileups, vcfio
+    t0 = time.time()
+    threshold = [float(x) for x in args.neighbor_threshold.split(",")[:2]]
+    os.makedirs(args.output, exist_ok=True)
+    with open(os.path.join(args.output, "args"), "w") as f:      # NanoCaller:182-186
+        f.write("Command: python %s\n\n\n" % " ".join(sys.argv))
+        f.write("------Parameters Used For Variant Calling------\n")
+        for k, v in vars(args).items():
+            f.write("{}: {}\n".format(k, v))
+    readsets = bamio.open_alignment(args.bam, args.ref)
+    contig_lengths = {rs.chrom: rs.contig_len for rs in readsets}
+    regions = get_regions_list(args, contig_lengths)
+    exclude = _load_exclude_bed(args)
+    chrom_list = list(dict.fromkeys(r[0] for r in regions))
+    ctx = snp_pileups.context(args.device)                        # fails loudly without an sm_100 device
+    out = {}
+    t_read = time.time() - t0
+
+    if args.mode in ("snps", "all"):
+        t1 = time.time()
+        params = dict(sam_path=args.bam, fasta_path=args.ref, mincov=args.mincov, maxcov=args.maxcov, min_allele_freq=args.min_allele_freq,
+                      min_nbr_sites=args.min_nbr_sites, threshold=threshold, seq=args.sequencing, supplementary=args.supplementary,
+                      exclude_bed=exclude, disable_coverage_normalization=args.disable_coverage_normalization)
+        tensors, cov = models.get_SNP_model(args.snp_model, args.nanocaller_src)
+        if tensors is None:
+            print("Invalid SNP model name or path", flush=True)     # snpCaller.py:66-68
+            raise SystemExit(2)
+        chunks = get_chunks(regions, args.cpu)
+        hap = None
+        if any(c["ploidy"] == "haploid" for c in chunks):
+            hap = models.get_SNP_model("haploid", args.nanocaller_src)[0]          # snpCaller.py:74
+        lines = []
+        for grp in _groups(chunks):
+            lines += snp_caller.call_chunks(params, grp, (tensors, cov), hap_weights=hap, device=args.device)
+        allp = os.path.join(args.output, "%s.unfiltered.snps.vcf.gz" % args.prefix)
+        passp = os.path.join(args.output, "%s.snps.vcf.gz" % args.prefix)
+        vcfio.write_vcf(allp, "snps", chrom_list, lines, args.sample)
+        vcfio.write_vcf(passp, "snps", chrom_list, vcfio.pass_only(lines), args.sample)
+        out.update(unfiltered_snps=allp, snps=passp, n_snp_records=len(lines), snp_seconds=time.time() - t1)
+        print("\n%s: SNP calling completed. Time taken= %.4f\n" % (datetime.datetime.now(), time.time() - t1), flush=True)
+
+    if args.mode in ("indels", "all"):
+        t1 = time.time()
+        params = dict(sam_path=args.bam, fasta_path=args.ref, mincov=args.mincov, maxcov=args.maxcov, seq=args.sequencing,
+                      del_t=args.del_threshold, ins_t=args.ins_threshold, impute_indel_phase=args.impute_indel_phase,
+                      supplementary=args.supplementary, exclude_bed=exclude, win_size=args.win_size, small_win_size=args.small_win_size)
+        ind = models.get_indel_model(args.indel_model, args.nanocaller_src)
+        if ind is None:
+            print("Invalid indel model name or path", flush=True)
+            raise SystemExit(2)
+        chunks = get_chunks(regions, args.cpu, max_chunk_size=100000)
+        hap_ind = None
+        if any(c["ploidy"] == "haploid" for c in chunks):
+            hap_ind = models.get_indel_model("haploid", args.nanocaller_src)
+        lines = []
+        for c in chunks:
+            c = dict(c, sam_path=args.bam)                        # indelCaller.py:327-336 hands every chunk its (phased) BAM
+            lines += indel_caller.call_chunk(params, c, ind, hap_tensors=hap_ind, device=args.device)
+        indp = os.path.join(args.output, "%s.indels.vcf.gz" % args.prefix)
+        vcfio.write_vcf(indp, "indels", chrom_list, lines, args.sample)
+        out.update(indels=indp, n_indel_records=len(lines), indel_seconds=time.time() - t1)
+        print("\n%s: Indel calling completed. Time taken= %.4f\n" % (datetime.datetime.now(), time.time() - t1), flush=True)
+        if args.mode == "all":
+            final = os.path.join(args.output, "%s.vcf.gz" % args.prefix)
+            snp_lines = vcfio.read_records(out["snps"])
+            vcfio.write_vcf(final, "all", chrom_list, snp_lines + lines, args.sample)
+            out["final"] = final
+    out.update(read_seconds=t_read, launches=ctx.timings()["launches"])
+    return out
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    t = time.time()
+    args = parse_args(argv)
+    if args.regions and args.bed:
+        print("\n%s: Please use either --regions or --bed but not both." % datetime.datetime.now(), flush=True)
+        raise SystemExit(2)
+    print("\n%s: Starting nanocaller_b200.\n" % datetime.datetime.now(), flush=True)
+    out = run(args)
+    print("\n%s: Total Time Elapsed: %.2f seconds" % (datetime.datetime.now(), time.time() - t))
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -31,9 +31,25 @@ INDEL_HEADER = (
 
 
 def header(kind, contigs, sample="SAMPLE"):
-    """`contigs` in the order to print (the reference iterates a Python set for SNPs — order unspecified)."""
+    """`contigs` in the order to print (the reference iterates a Python set for SNPs — order unspecified).
+    kind 'all' = the merged file of `--mode all` (the reference's `bcftools concat` of the SNP and indel files,
+    indelCaller.py:385-395): the union of both headers."""
+    ctg = "".join("##contig=<ID=%s>\n" % c for c in contigs)
+    if kind == "all":
+        snp = SNP_HEADER.format(contigs=ctg, sample=sample).splitlines(True)
+        ind = INDEL_HEADER.format(contigs=ctg, sample=sample).splitlines(True)
+        extra = [ln for ln in ind if ln.startswith("##") and ln not in snp]
+        return "".join(snp[:-1] + extra + snp[-1:])
     tmpl = SNP_HEADER if kind == "snps" else INDEL_HEADER
-    return tmpl.format(contigs="".join("##contig=<ID=%s>\n" % c for c in contigs), sample=sample)
+    return tmpl.format(contigs=ctg, sample=sample)
+
+
+def read_records(path):
+    """Record lines (no header) of a VCF written by `write_vcf` (plain or BGZF)."""
+    import gzip
+    opener = gzip.open if open(path, "rb").read(2) == b"\x1f\x8b" else open
+    with opener(path, "rt") as f:
+        return [ln for ln in f if not ln.startswith("#")]
 
 
 def sort_records(lines, contigs):

@@ -1,0 +1,95 @@
+"""GPU, end to end through files: synthetic BAM + FASTA on disk -> `python -m nanocaller_b200` (cli.main) -> VCFs, against the
+oracle pipeline on the same reads (oracle tensors -> scaling -> fp32 CNN -> restated record code), with the reference's
+chunk grid for `--cpu 3`, a diploid and a haploid (chrY) contig, SNP and indel modes."""
+import gzip
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _world(tmp_path):
+    from nanocaller_b200.host import bamio
+    from nanocaller_b200.synth import make_world
+    a = make_world(chrom="chrA", preset="ont", contig_len=150_000, seed=11, coverage=24.0, indel_every=1500, indel_maxlen=12).reads
+    y = make_world(chrom="chrY", preset="ont", contig_len=40_000, seed=12, coverage=20.0, indel_every=1500, indel_maxlen=12).reads
+    bam, fa = str(tmp_path / "w.bam"), str(tmp_path / "w.fa")
+    bamio.write_bam(bam, [a, y])
+    bamio.write_fasta(fa, [a, y])
+    return bam, fa, [a, y]
+
+
+def _records(path):
+    with gzip.open(path, "rt") as f:
+        txt = f.read()
+    return [ln + "\n" for ln in txt.splitlines() if not ln.startswith("#")], txt
+
+
+def test_cli_snps_and_indels_from_files(tmp_path):
+    from nanocaller_b200 import cli
+    from nanocaller_b200.host import snp_pileups, sources, vcfio, weights as W
+    from nanocaller_b200.host.vcf_compare import compare_records
+    from oracle import cnn_oracle, indel_caller_oracle, indel_oracle, snp_caller_oracle, snp_oracle
+    bam, fa, worlds = _world(tmp_path)
+    sources.unregister_all()
+    snp_pileups.reset()
+    out = cli.main(["--bam", bam, "--ref", fa, "--mode", "all", "--preset", "ont", "--cpu", "3", "--output", str(tmp_path / "o"), "--prefix", "t", "--sample", "S"])
+    assert out["launches"] > 0
+
+    # ---- SNPs: oracle pipeline over the reference's chunk grid
+    regions = [("chrA", 1, 150_000, "diploid"), ("chrY", 1, 40_000, "haploid")]
+    dct = dict(threshold=[0.4, 0.6], mincov=4, maxcov=160, min_allele_freq=0.15, min_nbr_sites=1, seq="ont", supplementary=False)
+    tensors, meta = W.load_model("snp", "ONT-HG002")
+    hap, _ = W.load_model("snp", "haploid")
+    want = []
+    for ch in snp_oracle.get_chunks(regions, 3):
+        rs = worlds[0] if ch["chrom"] == "chrA" else worlds[1]
+        pos, ref, mat, dp, freq, depth, fwd, rev = snp_oracle.get_snp_testing_candidates(rs, dct, ch)
+        if len(pos) == 0:
+            continue
+        ref = np.asarray(ref, np.float32)
+        if ch["ploidy"] == "haploid":
+            x = snp_oracle.scale_counts(mat, 30.0, coverage=float(depth))
+            want += snp_caller_oracle.haploid_records(ch["chrom"], pos, ref, cnn_oracle.haploid_snp_model(hap, x, ref), dp, freq)
+        else:
+            x = snp_oracle.scale_counts(mat, meta["train_coverage"], coverage=float(depth))
+            want += snp_caller_oracle.diploid_records(ch["chrom"], pos, ref, cnn_oracle.snp_probs(tensors, x, ref), dp, freq, fwd, rev)
+    want = vcfio.sort_records(want, ["chrA", "chrY"])
+    got, txt = _records(out["unfiltered_snps"])
+    assert txt.startswith("##fileformat=VCFv4.2\n") and "##contig=<ID=chrA>\n##contig=<ID=chrY>\n" in txt and "FORMAT\tS\n" in txt
+    res = compare_records(got, want, tol=1e-4)
+    assert not res["mismatch"], res["mismatch"][:3]
+    assert res["identical"] + res["numeric_only"] + res["borderline"] == len(want) > 500
+    assert res["borderline"] <= max(1, len(want) // 500)
+    passed, _ = _records(out["snps"])
+    assert passed == [ln for ln in got if ln.split("\t")[6] == "PASS"] and 0 < len(passed) < len(got)
+
+    # ---- indels: oracle pipeline over the 100 kb indel grid (HP / PS tags come from the BAM)
+    idct = dict(mincov=4, maxcov=160, seq="ont", del_t=0.6, ins_t=0.4, impute_indel_phase=False, supplementary=False, win_size=40, small_win_size=4)
+    it, _ = W.load_model("indel", "ONT-HG002")
+    ih, _ = W.load_model("indel", "haploid")
+    want_i = []
+    for ch in snp_oracle.get_chunks(regions, 3, 100_000):
+        rs = worlds[0] if ch["chrom"] == "chrA" else worlds[1]
+        if ch["ploidy"] == "haploid":
+            pos, x, alleles = indel_oracle.get_indel_testing_candidates_haploid(rs, idct, ch)
+            if len(pos):
+                want_i += indel_caller_oracle.haploid_records(ch["chrom"], pos, cnn_oracle.haploid_indel_model(ih, np.asarray(x, np.float32)), alleles)
+        else:
+            pos, x0, x1, x2, alleles, phase = indel_oracle.get_indel_testing_candidates(rs, idct, ch)
+            if len(pos):
+                probs = cnn_oracle.indel_model(it, np.hstack([x0, x1, x2]).astype(np.float32))
+                want_i += indel_caller_oracle.diploid_records(ch["chrom"], pos, probs, alleles, phase)
+    want_i = vcfio.sort_records(want_i, ["chrA", "chrY"])
+    got_i, txt_i = _records(out["indels"])
+    assert "ID=GQ" in txt_i and len(got_i) == len(want_i) > 10
+    for a, b in zip(got_i, want_i):
+        fa_, fb_ = a.split("\t"), b.split("\t")
+        assert fa_[:5] == fb_[:5] and fa_[6:9] == fb_[6:9], (a, b)
+        assert abs(float(fa_[5]) - float(fb_[5])) < 0.02
+        assert fa_[9].split(":")[0] == fb_[9].split(":")[0]
+    merged, txt_m = _records(out["final"])
+    assert len(merged) == len(passed) + len(got_i) and "ID=PS" in txt_m and "ID=PR" in txt_m
+    keys = [(ln.split("\t")[0], int(ln.split("\t")[1])) for ln in merged]
+    assert keys == sorted(keys)
