@@ -647,7 +647,7 @@ int nc_snp_scan(nc_ctx* c, const NcSnpParams* P, const NcChunk* chunks, int32_t 
         NC_CUDA(c->d_meta.reserve((size_t)c->n_sites * sizeof(NcSiteMeta)));
         ta.mat = c->d_mat.as<int16_t>(); ta.meta = c->d_meta.as<NcSiteMeta>();
         ta.chunk_depth_sum = c->d_depth_sum.as<unsigned long long>(); ta.chunk_count = c->d_depth_cnt.as<unsigned long long>();
-        const unsigned tg = (unsigned)std::min<int64_t>(div_up(c->n_slots, kTensorWarps), (int64_t)c->sm_count * 16);
+        const unsigned tg = (unsigned)std::min<int64_t>(div_up(c->n_slots, kRunSlots), (int64_t)c->sm_count * 16);
         tensor_kernel<<<tg, kTensorWarps * 32, 0, c->stream>>>(ta); NC_LAUNCH_CHECK();
     }
     chunk_depth_kernel<<<(unsigned)div_up(n_chunks, 128), 128, 0, c->stream>>>(c->d_depth_sum.as<unsigned long long>(), c->d_depth_cnt.as<unsigned long long>(),

@@ -638,7 +638,14 @@ __constant__ int c_nbins[5] = {5, 3, 7, 7, 4};
 // Warp-cooperative neighbour choice.  Lanes 0..6 own the left bins, lanes 8..14 the right bins.
 // On return every lane holds (sel_lo, sel_cnt) of its bin (cnt 0 elsewhere); n_left / n_right are
 // warp-uniform.  wlo/whi = inclusive v_pos bounds of the chunk's pileup window (:156).
-__device__ __forceinline__ void choose_neighbours(const int32_t* __restrict__ nbr_pos, int32_t n_nbr, int seq,
+// `nbr_pos` may point to global or shared memory (plain loads): any sorted sub-range of the neighbour
+// list that contains every neighbour within the search radius of v gives the same choice.
+__device__ __forceinline__ int32_t lower_bound_plain(const int32_t* a, int32_t n, int32_t key) {
+    int32_t lo = 0, hi = n;
+    while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ void choose_neighbours(const int32_t* nbr_pos, int32_t n_nbr, int seq,
                                                   int32_t v, int32_t wlo, int32_t whi, int lane,
                                                   int32_t& sel_lo, int32_t& sel_cnt, int& n_left, int& n_right) {
     sel_lo = 0; sel_cnt = 0;
@@ -648,13 +655,13 @@ __device__ __forceinline__ void choose_neighbours(const int32_t* __restrict__ nb
         int32_t lo, hi;
         if (side == 0) {                                               // v-b <= p < v-a
             const int64_t from = max((int64_t)v - bs.b, (int64_t)wlo);
-            lo = lower_bound_i32(nbr_pos, n_nbr, (int32_t)max(from, (int64_t)INT32_MIN + 1));
-            hi = lower_bound_i32(nbr_pos, n_nbr, v - bs.a);
+            lo = lower_bound_plain(nbr_pos, n_nbr, (int32_t)max(from, (int64_t)INT32_MIN + 1));
+            hi = lower_bound_plain(nbr_pos, n_nbr, v - bs.a);
             if (hi > lo) { sel_cnt = min(hi - lo, bs.k); sel_lo = bs.far ? lo : hi - sel_cnt; }
         } else {                                                       // v+a < p <= v+b
             const int64_t to = min((int64_t)v + bs.b, (int64_t)whi);
-            lo = lower_bound_i32(nbr_pos, n_nbr, v + bs.a + 1);
-            hi = lower_bound_i32(nbr_pos, n_nbr, (int32_t)min(to + 1, (int64_t)INT32_MAX));
+            lo = lower_bound_plain(nbr_pos, n_nbr, v + bs.a + 1);
+            hi = lower_bound_plain(nbr_pos, n_nbr, (int32_t)min(to + 1, (int64_t)INT32_MAX));
             if (hi > lo) { sel_cnt = min(hi - lo, bs.k); sel_lo = bs.far ? hi - sel_cnt : lo; }
         }
     }
@@ -732,160 +739,330 @@ __global__ void keep_to_i32_kernel(const uint8_t* __restrict__ keep, int64_t n, 
     if (i < n) out[i] = keep[i];
 }
 
-// K2 — tensor build, one warp per candidate (generate_SNP_pileups.py:200-263).
-//   lanes as READS   walk the BAM-index window of reads that can cover the candidate, 32 at a time:
-//                    admission, code at the candidate (one nibble of the aligned row), strand depths;
-//   lanes as COLUMNS for every sampled read (first maxcov in BAM order, see DESIGN.md on :215-216) the
-//                    read's neighbour-matrix row is broadcast and lane c looks up the code at column c
-//                    (columns 32..40 ride on lanes 0..8), counting into 4 x 4 16-bit fields.
+// K2 — tensor build (generate_SNP_pileups.py:200-263), one warp per candidate site.
+//   lanes as READS   walk the reads that can cover the candidate, 32 at a time: code at the candidate
+//                    (one nibble of the aligned row), strand depths;
+//   lanes as COLUMNS for every sampled read (first maxcov in BAM order, see DESIGN.md on :215-216) lane c
+//                    looks up the code at column c in the read's neighbour-matrix row (columns 32..40
+//                    ride on lanes 0..8) and counts into 4 x 4 packed fields.
+// A CTA takes a RUN of consecutive slots (same region of the contig) and prepares once what the per-site
+// version recomputed for every site: the admitted reads overlapping the run, compacted in BAM order in
+// shared memory (~40 entries at 30x instead of a ~250-read BAM-index window per site), and the sub-range
+// of the neighbour list within the search radius of the run (binary searches over ~100 shared-memory
+// entries instead of the whole list).  Runs that do not fit (span > 64 kb, > 256 overlapping reads,
+// maxcov > 255) take the per-site generic path.
 constexpr int kTensorWarps = 4;
+constexpr int kRunSlots = 32;
+constexpr int kRunList = 256;
+constexpr int kRunNbr = 1024;
+
+struct SiteCols {                       // what a lane knows about its two tensor columns (lane, lane + 32)
+    int32_t j0, j1;                     // neighbour-list index (global numbering) or -1
+    int rc0, rc1, rc_v, nl, nr;
+};
+__device__ __forceinline__ uint64_t expand_fields_8_to_16(uint32_t x) {
+    return (uint64_t)(x & 0xFFu) | ((uint64_t)(x & 0xFF00u) << 8) | ((uint64_t)(x & 0xFF0000u) << 16) | ((uint64_t)(x & 0xFF000000u) << 24);
+}
+
+// neighbour choice + the lane's columns; nbr = sorted neighbour positions [0, n), nb_base = global index of nbr[0]
+__device__ __forceinline__ SiteCols site_columns(const TensorArgs& a, const int32_t* nbr, int32_t n, int32_t nb_base, int c, int32_t v, int lane) {
+    SiteCols sc;
+    const int32_t wlo = max(1, a.chunks[c].start - 50000), whi = a.chunks[c].end + 50000;
+    int32_t sel_lo, sel_cnt;
+    choose_neighbours(nbr, n, a.seq, v, wlo, whi, lane, sel_lo, sel_cnt, sc.nl, sc.nr);
+    const int32_t r0 = column_neighbour(lane, a.seq, sel_lo, sel_cnt, sc.nl, sc.nr);
+    const int32_t r1 = column_neighbour(lane + 32, a.seq, sel_lo, sel_cnt, sc.nl, sc.nr);
+    sc.rc_v = ref_code_of(__ldg(a.ref + ((int64_t)(v - 1) - a.ref_start)));
+    sc.rc0 = 4; sc.rc1 = 4;
+    if (lane == 20) sc.rc0 = sc.rc_v;
+    if (r0 >= 0) sc.rc0 = ref_code_of(__ldg(a.ref + ((int64_t)nbr[r0] - 1 - a.ref_start)));
+    if (r1 >= 0) sc.rc1 = ref_code_of(__ldg(a.ref + ((int64_t)nbr[r1] - 1 - a.ref_start)));
+    sc.j0 = r0 >= 0 ? r0 + nb_base : -1;
+    sc.j1 = r1 >= 0 ? r1 + nb_base : -1;
+    return sc;
+}
+
+// assemble [5][41][5] in shared memory, 16-byte coalesced stores, site metadata, chunk depth sums
+__device__ __forceinline__ void site_finish(const TensorArgs& a, int64_t orow, int c, int32_t v, int lane, int16_t* buf, const SiteCols& sc,
+                                            const uint64_t* acc0, const uint64_t* acc1, uint64_t fwd, uint64_t rev, int32_t dp, int32_t sampled) {
+    const uint32_t full = 0xffffffffu;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        fwd += __shfl_xor_sync(full, fwd, d);
+        rev += __shfl_xor_sync(full, rev, d);
+    }
+    for (int i = lane; i < NC_SNP_SITE_STRIDE / 8; i += 32) reinterpret_cast<uint4*>(buf)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int col = lane + 32 * half;
+        const int rc = half ? sc.rc1 : sc.rc0;
+        const bool real = half ? (sc.j1 >= 0) : (sc.j0 >= 0 || lane == 20);
+        if (real && col < NC_SNP_COLS) {
+            if (rc < 4) buf[col * 5 + rc] = 1;                                          // :249-251 total_ref
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint64_t av = half ? acc1[i] : acc0[i];
+                int16_t* o = buf + ((i + 1) * NC_SNP_COLS + col) * 5;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int32_t cnt = (int32_t)((av >> (16 * b)) & 0xFFFFull);
+                    o[b] = (int16_t)(b == rc ? -cnt : cnt);                             // :253 mat * (1 - 2*total_ref)
+                }
+                o[4] = (i == sc.rc_v) ? 1 : 0;                                          // :252
+            }
+        }
+    }
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(a.mat + orow * NC_SNP_SITE_STRIDE);
+    for (int i = lane; i < NC_SNP_SITE_STRIDE / 8; i += 32) dst[i] = reinterpret_cast<const uint4*>(buf)[i];
+    __syncwarp();
+    if (lane == 0) {
+        NcSiteMeta m;
+        m.pos = v; m.chunk = c; m.dp = dp;
+        int32_t alt = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t fb = (uint32_t)((fwd >> (16 * b)) & 0xFFFFull), rb = (uint32_t)((rev >> (16 * b)) & 0xFFFFull);
+            m.fwd[b] = (uint16_t)fb; m.rev[b] = (uint16_t)rb;
+            if (b != sc.rc_v) alt = max(alt, (int32_t)(fb + rb));
+        }
+        m.alt = alt;
+        m.ref_code = (uint8_t)sc.rc_v; m.n_left = (uint8_t)sc.nl; m.n_right = (uint8_t)sc.nr; m.reserved = 0;
+        m.sample_depth = sampled;
+        a.meta[orow] = m;
+        atomicAdd(a.chunk_depth_sum + c, (unsigned long long)sampled);
+        atomicAdd(a.chunk_count + c, 1ull);
+    }
+}
+
+// keep the lowest `room` set bits of cm (sample = the first maxcov covering reads in BAM order)
+__device__ __forceinline__ uint32_t take_first(uint32_t cm, int room) {
+    if (__popc(cm) <= room) return cm;
+    uint32_t m = cm, kept = 0;
+    for (int q = 0; q < room; q++) { const uint32_t low = m & (0u - m); kept |= low; m ^= low; }
+    return room > 0 ? kept : 0u;
+}
+
+// Generic per-site path: BAM-index window from the prefix-max of read ends, 16-bit count fields.
+__device__ __forceinline__ void tensor_site_generic(const TensorArgs& a, int64_t orow, int c, int32_t v, int lane, int16_t* buf) {
+    const uint32_t full = 0xffffffffu;
+    const int32_t p = v - 1;
+    const SiteCols sc = site_columns(a, a.nbr_pos, a.n_nbr, 0, c, v, lane);
+    const int64_t ihi = upper_bound_i32_64(a.pos, a.n_reads, p);
+    int64_t ilo;
+    {
+        int64_t lo = 0, hi = ihi;
+        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (__ldg(a.pmaxend + mid) <= p) lo = mid + 1; else hi = mid; }
+        ilo = lo;
+    }
+    uint64_t acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+    uint64_t fwd = 0, rev = 0;                                        // per-lane 4 x 16-bit strand depths
+    int32_t dp = 0, sampled = 0;
+    for (int64_t base = ilo; base < ihi; base += 32) {
+        const int64_t i = base + lane;
+        bool cover = false;
+        uint32_t code = 4;
+        int32_t nf = 0, nlen = 0;
+        int64_t noff = 0;
+        if (i < ihi) {
+            const int32_t rp = __ldg(a.pos + i), re = __ldg(a.end + i);
+            const uint32_t f = __ldg(a.flag + i);
+            if ((f & a.flag_filter) == 0 && rp <= p && p < re) {
+                cover = true;
+                code = (__ldg(a.rows + __ldg(a.rowoff + i) + ((p >> 3) - (rp >> 3))) >> (4 * (p & 7))) & 15u;
+                if (code < 4) { if (f & 0x10u) rev += 1ull << (16 * code); else fwd += 1ull << (16 * code); }
+                nf = __ldg(a.nfirst + i); nlen = __ldg(a.nlen + i); noff = __ldg(a.noff + i);
+            }
+        }
+        const uint32_t cm = __ballot_sync(full, cover);
+        if (cm == 0) continue;
+        dp += __popc(cm);
+        uint32_t take = take_first(cm, a.maxcov - sampled);
+        sampled += __popc(take);
+        while (take) {
+            const int k = __ffs(take) - 1;
+            take &= take - 1;
+            const uint32_t ci = __shfl_sync(full, code, k);
+            const int32_t rnf = __shfl_sync(full, nf, k), rnl = __shfl_sync(full, nlen, k);
+            const int64_t rno = __shfl_sync(full, noff, k);
+            if (ci >= 4) continue;                                     // '*' / N at the candidate: counted in depth only
+            uint32_t b0 = 4, b1 = 4;
+            if (lane == 20) b0 = ci;
+            if (sc.j0 >= 0) {
+                const uint32_t rel = (uint32_t)(sc.j0 - rnf);
+                if (rel < (uint32_t)rnl) { const uint32_t by = __ldg(a.nrows + rno + (rel >> 1)); b0 = (rel & 1u) ? (by >> 4) : (by & 15u); }
+            }
+            if (sc.j1 >= 0) {
+                const uint32_t rel = (uint32_t)(sc.j1 - rnf);
+                if (rel < (uint32_t)rnl) { const uint32_t by = __ldg(a.nrows + rno + (rel >> 1)); b1 = (rel & 1u) ? (by >> 4) : (by & 15u); }
+            }
+            const uint64_t i0 = b0 < 4 ? 1ull << (16 * b0) : 0ull, i1 = b1 < 4 ? 1ull << (16 * b1) : 0ull;
+            switch (ci) {                                              // warp-uniform
+                case 0: acc0[0] += i0; acc1[0] += i1; break;
+                case 1: acc0[1] += i0; acc1[1] += i1; break;
+                case 2: acc0[2] += i0; acc1[2] += i1; break;
+                default: acc0[3] += i0; acc1[3] += i1; break;
+            }
+        }
+    }
+    site_finish(a, orow, c, v, lane, buf, sc, acc0, acc1, fwd, rev, dp, sampled);
+}
+
+struct RunList {                        // admitted reads overlapping the run, BAM order (shared memory)
+    int32_t rp[kRunList], re[kRunList], nf[kRunList], nl[kRunList];
+    int64_t rowoff[kRunList], noff[kRunList];
+    uint8_t rev[kRunList];
+};
+
+// Fast per-site path over the run's compact read list; 8-bit count fields (maxcov <= 255).
+__device__ __forceinline__ void tensor_site_run(const TensorArgs& a, int64_t orow, int c, int32_t v, int lane, int16_t* buf,
+                                                const RunList& L, int cnt, const int32_t* nbr, int32_t n_nbr, int32_t nb_base) {
+    const uint32_t full = 0xffffffffu;
+    const int32_t p = v - 1;
+    const SiteCols sc = site_columns(a, nbr, n_nbr, nb_base, c, v, lane);
+    uint32_t a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};                // per candidate code: 4 x 8-bit counts by column code
+    uint64_t fwd = 0, rev = 0;
+    int32_t dp = 0, sampled = 0;
+    for (int base = 0; base < cnt; base += 32) {
+        const int e = base + lane;
+        bool cover = false;
+        uint32_t code = 4;
+        if (e < cnt) {
+            const int32_t rp = L.rp[e];
+            if (rp <= p && p < L.re[e]) {
+                cover = true;
+                code = (__ldg(a.rows + L.rowoff[e] + ((p >> 3) - (rp >> 3))) >> (4 * (p & 7))) & 15u;
+                if (code < 4) { if (L.rev[e]) rev += 1ull << (16 * code); else fwd += 1ull << (16 * code); }
+            }
+        }
+        const uint32_t cm = __ballot_sync(full, cover);
+        if (cm == 0) continue;
+        dp += __popc(cm);
+        uint32_t take = take_first(cm, a.maxcov - sampled);
+        sampled += __popc(take);
+        while (take) {
+            const int k = __ffs(take) - 1;
+            take &= take - 1;
+            const uint32_t ci = __shfl_sync(full, code, k);
+            if (ci >= 4) continue;                                     // '*' / N at the candidate: counted in depth only
+            const int e2 = base + k;
+            const int32_t rnf = L.nf[e2], rnl = L.nl[e2];
+            const uint8_t* __restrict__ row = a.nrows + L.noff[e2];
+            uint32_t b0 = 4, b1 = 4;
+            if (lane == 20) b0 = ci;
+            if (sc.j0 >= 0) {
+                const uint32_t rel = (uint32_t)(sc.j0 - rnf);
+                if (rel < (uint32_t)rnl) { const uint32_t by = __ldg(row + (rel >> 1)); b0 = (rel & 1u) ? (by >> 4) : (by & 15u); }
+            }
+            if (sc.j1 >= 0) {
+                const uint32_t rel = (uint32_t)(sc.j1 - rnf);
+                if (rel < (uint32_t)rnl) { const uint32_t by = __ldg(row + (rel >> 1)); b1 = (rel & 1u) ? (by >> 4) : (by & 15u); }
+            }
+            const uint32_t i0 = b0 < 4 ? 1u << (8 * b0) : 0u, i1 = b1 < 4 ? 1u << (8 * b1) : 0u;
+            switch (ci) {                                              // warp-uniform
+                case 0: a0[0] += i0; a1[0] += i1; break;
+                case 1: a0[1] += i0; a1[1] += i1; break;
+                case 2: a0[2] += i0; a1[2] += i1; break;
+                default: a0[3] += i0; a1[3] += i1; break;
+            }
+        }
+    }
+    uint64_t acc0[4], acc1[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { acc0[i] = expand_fields_8_to_16(a0[i]); acc1[i] = expand_fields_8_to_16(a1[i]); }
+    site_finish(a, orow, c, v, lane, buf, sc, acc0, acc1, fwd, rev, dp, sampled);
+}
 
 __global__ void __launch_bounds__(kTensorWarps * 32) tensor_kernel(const TensorArgs a) {
     __shared__ __align__(16) int16_t s_out[kTensorWarps][NC_SNP_SITE_STRIDE];
+    __shared__ RunList s_list;
+    __shared__ int32_t s_nbr[kRunNbr];
+    __shared__ int32_t s_v[kRunSlots], s_c[kRunSlots];
+    __shared__ int32_t s_wcnt[kTensorWarps];
+    __shared__ int64_t s_ilo, s_ihi;
+    __shared__ int32_t s_pmin, s_pmax, s_nb_lo, s_nb_hi, s_fast;
     const uint32_t full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     int16_t* buf = s_out[wib];
 
-    for (int64_t s = (int64_t)blockIdx.x * kTensorWarps + wib; s < a.n_slots; s += (int64_t)gridDim.x * kTensorWarps) {
-        int64_t orow = s;
-        if (a.outidx) {
-            orow = __ldg(a.outidx + s);
-            if (__ldg(a.outidx + s + 1) == orow) continue;                // dropped by min_nbr_sites
-        }
-        const int c = slot_chunk(a.chunk_off, a.n_chunks, s);
-        const int32_t v = __ldg(a.cand_pos + a.chunk_lo[c] + (s - a.chunk_off[c]));
-        const int32_t p = v - 1;
-        const int32_t wlo = max(1, a.chunks[c].start - 50000), whi = a.chunks[c].end + 50000;
-
-        // ---- neighbour choice and the lane's columns
-        int32_t sel_lo, sel_cnt; int nl, nr;
-        choose_neighbours(a.nbr_pos, a.n_nbr, a.seq, v, wlo, whi, lane, sel_lo, sel_cnt, nl, nr);
-        const int32_t j0 = column_neighbour(lane, a.seq, sel_lo, sel_cnt, nl, nr);
-        const int32_t j1 = column_neighbour(lane + 32, a.seq, sel_lo, sel_cnt, nl, nr);
-        const int rc_v = ref_code_of(__ldg(a.ref + ((int64_t)p - a.ref_start)));
-        int rc0 = 4, rc1 = 4;                                            // reference code of the lane's columns
-        if (lane == 20) rc0 = rc_v;
-        if (j0 >= 0) rc0 = ref_code_of(__ldg(a.ref + ((int64_t)__ldg(a.nbr_pos + j0) - 1 - a.ref_start)));
-        if (j1 >= 0) rc1 = ref_code_of(__ldg(a.ref + ((int64_t)__ldg(a.nbr_pos + j1) - 1 - a.ref_start)));
-
-        // ---- read window
-        const int64_t ihi = upper_bound_i32_64(a.pos, a.n_reads, p);
-        int64_t ilo;
-        {
-            int64_t lo = 0, hi = ihi;
-            while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (__ldg(a.pmaxend + mid) <= p) lo = mid + 1; else hi = mid; }
-            ilo = lo;
-        }
-
-        uint64_t acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
-        uint64_t fwd = 0, rev = 0;                                        // per-lane 4 x 16-bit strand depths
-        int32_t dp = 0, sampled = 0;
-
-        for (int64_t base = ilo; base < ihi; base += 32) {
-            const int64_t i = base + lane;
-            bool cover = false;
-            uint32_t code = 4;
-            int32_t nf = 0, nlen = 0;
-            int64_t noff = 0;
-            if (i < ihi) {
-                const int32_t rp = __ldg(a.pos + i), re = __ldg(a.end + i);
-                const uint32_t f = __ldg(a.flag + i);
-                if ((f & a.flag_filter) == 0 && rp <= p && p < re) {
-                    cover = true;
-                    code = (__ldg(a.rows + __ldg(a.rowoff + i) + ((p >> 3) - (rp >> 3))) >> (4 * (p & 7))) & 15u;
-                    if (code < 4) { if (f & 0x10u) rev += 1ull << (16 * code); else fwd += 1ull << (16 * code); }
-                    nf = __ldg(a.nfirst + i); nlen = __ldg(a.nlen + i); noff = __ldg(a.noff + i);
-                }
+    for (int64_t s0 = (int64_t)blockIdx.x * kRunSlots; s0 < a.n_slots; s0 += (int64_t)gridDim.x * kRunSlots) {
+        const int nslots = (int)min((int64_t)kRunSlots, a.n_slots - s0);
+        __syncthreads();                                               // previous run's shared state no longer in use
+        // ---- the run's sites and its position span
+        if (wib == 0) {
+            int32_t v = 0, c = 0, lo = INT32_MAX, hi = INT32_MIN;
+            if (lane < nslots) {
+                const int64_t s = s0 + lane;
+                c = slot_chunk(a.chunk_off, a.n_chunks, s);
+                v = __ldg(a.cand_pos + a.chunk_lo[c] + (s - a.chunk_off[c]));
+                lo = hi = v - 1;
             }
-            const uint32_t cm = __ballot_sync(full, cover);
-            if (cm == 0) continue;
-            dp += __popc(cm);
-            // sample = the first maxcov covering reads in BAM order
-            uint32_t take = cm;
-            const int room = a.maxcov - sampled;
-            if (__popc(cm) > room) {
-                // keep the lowest `room` set bits
-                uint32_t m = cm, kept = 0;
-                for (int q = 0; q < room; q++) { const uint32_t low = m & (0u - m); kept |= low; m ^= low; }
-                take = room > 0 ? kept : 0u;
+            s_v[lane] = v; s_c[lane] = c;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) { lo = min(lo, __shfl_xor_sync(full, lo, d)); hi = max(hi, __shfl_xor_sync(full, hi, d)); }
+            if (lane == 0) {
+                s_pmin = lo; s_pmax = hi;
+                s_fast = ((int64_t)hi - lo <= 65536 && a.maxcov <= 255) ? 1 : 0;
+                s_ihi = upper_bound_i32_64(a.pos, a.n_reads, hi);
+                int64_t l = 0, h = s_ihi;                             // first read whose prefix-max end exceeds the run's first position
+                while (l < h) { const int64_t mid = (l + h) >> 1; if (__ldg(a.pmaxend + mid) <= lo) l = mid + 1; else h = mid; }
+                s_ilo = l;
             }
-            sampled += __popc(take);
-            while (take) {
-                const int k = __ffs(take) - 1;
-                take &= take - 1;
-                const uint32_t ci = __shfl_sync(full, code, k);
-                const int32_t rnf = __shfl_sync(full, nf, k), rnl = __shfl_sync(full, nlen, k);
-                const int64_t rno = __shfl_sync(full, noff, k);
-                if (ci >= 4) continue;                                     // '*' / N at the candidate: counted in depth only
-                uint32_t b0 = 4, b1 = 4;
-                if (lane == 20) b0 = ci;
-                if (j0 >= 0) {
-                    const uint32_t rel = (uint32_t)(j0 - rnf);
-                    if (rel < (uint32_t)rnl) { const uint32_t by = __ldg(a.nrows + rno + (rel >> 1)); b0 = (rel & 1u) ? (by >> 4) : (by & 15u); }
-                }
-                if (j1 >= 0) {
-                    const uint32_t rel = (uint32_t)(j1 - rnf);
-                    if (rel < (uint32_t)rnl) { const uint32_t by = __ldg(a.nrows + rno + (rel >> 1)); b1 = (rel & 1u) ? (by >> 4) : (by & 15u); }
-                }
-                const uint64_t i0 = b0 < 4 ? 1ull << (16 * b0) : 0ull, i1 = b1 < 4 ? 1ull << (16 * b1) : 0ull;
-                switch (ci) {                                              // warp-uniform
-                    case 0: acc0[0] += i0; acc1[0] += i1; break;
-                    case 1: acc0[1] += i0; acc1[1] += i1; break;
-                    case 2: acc0[2] += i0; acc1[2] += i1; break;
-                    default: acc0[3] += i0; acc1[3] += i1; break;
-                }
+            if (lane == 1) {                                           // neighbours within the search radius of the run
+                const int32_t R = c_bins[a.seq][c_nbins[a.seq] - 1].b + 1;
+                s_nb_lo = lower_bound_i32(a.nbr_pos, a.n_nbr, (int32_t)max((int64_t)lo + 1 - R, (int64_t)INT32_MIN + 1));
+                s_nb_hi = lower_bound_i32(a.nbr_pos, a.n_nbr, (int32_t)min((int64_t)hi + 2 + R, (int64_t)INT32_MAX));
             }
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            fwd += __shfl_xor_sync(full, fwd, d);
-            rev += __shfl_xor_sync(full, rev, d);
-        }
-
-        // ---- assemble [5][41][5] in shared memory, then 16-byte coalesced stores
-        for (int i = lane; i < NC_SNP_SITE_STRIDE / 8; i += 32) reinterpret_cast<uint4*>(buf)[i] = make_uint4(0, 0, 0, 0);
-        __syncwarp();
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-            const int col = lane + 32 * half;
-            const int rc = half ? rc1 : rc0;
-            const bool real = half ? (j1 >= 0) : (j0 >= 0 || lane == 20);
-            if (real && col < NC_SNP_COLS) {
-                if (rc < 4) buf[col * 5 + rc] = 1;                                          // :249-251 total_ref
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint64_t av = half ? acc1[i] : acc0[i];
-                    int16_t* o = buf + ((i + 1) * NC_SNP_COLS + col) * 5;
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const int32_t cnt = (int32_t)((av >> (16 * b)) & 0xFFFFull);
-                        o[b] = (int16_t)(b == rc ? -cnt : cnt);                             // :253 mat * (1 - 2*total_ref)
-                    }
-                    o[4] = (i == rc_v) ? 1 : 0;                                             // :252
+        __syncthreads();
+        const int32_t pmin = s_pmin, pmax = s_pmax;
+        int cnt = 0;
+        if (s_fast) {
+            // ---- ordered compaction of the admitted reads overlapping [pmin, pmax]
+            const int64_t ilo = s_ilo, ihi = s_ihi;
+            for (int64_t base = ilo; base < ihi; base += kTensorWarps * 32) {
+                const int64_t i = base + tid;
+                bool keep = false;
+                int32_t rp = 0, re = 0; uint32_t f = 0;
+                if (i < ihi) {
+                    rp = __ldg(a.pos + i); re = __ldg(a.end + i); f = __ldg(a.flag + i);
+                    keep = (f & a.flag_filter) == 0 && rp <= pmax && re > pmin;
                 }
+                const uint32_t bm = __ballot_sync(full, keep);
+                if (lane == 0) s_wcnt[wib] = __popc(bm);
+                __syncthreads();
+                int off = cnt, tot = 0;
+#pragma unroll
+                for (int w = 0; w < kTensorWarps; w++) { const int n = s_wcnt[w]; if (w < wib) off += n; tot += n; }
+                const int slot = off + __popc(bm & ((1u << lane) - 1u));
+                if (keep && slot < kRunList) {
+                    s_list.rp[slot] = rp; s_list.re[slot] = re; s_list.rev[slot] = (uint8_t)((f >> 4) & 1u);
+                    s_list.rowoff[slot] = __ldg(a.rowoff + i);
+                    s_list.nf[slot] = __ldg(a.nfirst + i); s_list.nl[slot] = __ldg(a.nlen + i); s_list.noff[slot] = __ldg(a.noff + i);
+                }
+                cnt += tot;
+                __syncthreads();                                       // s_wcnt reused by the next round
             }
         }
-        __syncwarp();
-        uint4* dst = reinterpret_cast<uint4*>(a.mat + orow * NC_SNP_SITE_STRIDE);
-        for (int i = lane; i < NC_SNP_SITE_STRIDE / 8; i += 32) dst[i] = reinterpret_cast<const uint4*>(buf)[i];
-        __syncwarp();
-
-        if (lane == 0) {
-            NcSiteMeta m;
-            m.pos = v; m.chunk = c; m.dp = dp;
-            int32_t alt = 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const uint32_t fb = (uint32_t)((fwd >> (16 * b)) & 0xFFFFull), rb = (uint32_t)((rev >> (16 * b)) & 0xFFFFull);
-                m.fwd[b] = (uint16_t)fb; m.rev[b] = (uint16_t)rb;
-                if (b != rc_v) alt = max(alt, (int32_t)(fb + rb));
+        const bool fast = s_fast && cnt <= kRunList;
+        const int32_t nb_lo = s_nb_lo, nb_n = s_nb_hi - s_nb_lo;
+        const bool nbr_sm = nb_n <= kRunNbr;
+        if (fast && nbr_sm) for (int i = tid; i < nb_n; i += kTensorWarps * 32) s_nbr[i] = __ldg(a.nbr_pos + nb_lo + i);
+        __syncthreads();
+        // ---- a warp per site
+        for (int k = wib; k < nslots; k += kTensorWarps) {
+            const int64_t s = s0 + k;
+            int64_t orow = s;
+            if (a.outidx) {
+                orow = __ldg(a.outidx + s);
+                if (__ldg(a.outidx + s + 1) == orow) continue;         // dropped by min_nbr_sites
             }
-            m.alt = alt;
-            m.ref_code = (uint8_t)rc_v; m.n_left = (uint8_t)nl; m.n_right = (uint8_t)nr; m.reserved = 0;
-            m.sample_depth = sampled;
-            a.meta[orow] = m;
-            atomicAdd(a.chunk_depth_sum + c, (unsigned long long)sampled);
-            atomicAdd(a.chunk_count + c, 1ull);
+            const int c = s_c[k];
+            const int32_t v = s_v[k];
+            if (!fast) tensor_site_generic(a, orow, c, v, lane, buf);
+            else if (nbr_sm) tensor_site_run(a, orow, c, v, lane, buf, s_list, cnt, s_nbr, nb_n, nb_lo);
+            else tensor_site_run(a, orow, c, v, lane, buf, s_list, cnt, a.nbr_pos + nb_lo, nb_n, nb_lo);
         }
     }
 }
