@@ -586,10 +586,19 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
         bulk_g2s(s_c2, P.c2 + grp * tcg::C2_GROUP_BYTES, tcg::C2_GROUP_BYTES, &s_full[wg]);
     }
 
+#ifdef NC_TB_PROFILE
+    uint32_t prof[6], prof_last = (uint32_t)clock(), prof_n = 0;
+    for (int i = 0; i < 6; i++) prof[i] = 0;
+#define NC_TB_MARK(i) { const uint32_t now_ = (uint32_t)clock(); prof[i] += now_ - prof_last; prof_last = now_; if (i == 5) prof_n++; }
+#else
+#define NC_TB_MARK(i)
+#endif
     for (; grp < n_groups; grp += gstride) {
         const int64_t s0 = grp * 3;
+        NC_TB_MARK(0);
         // ---- the group's c2 image (30,720 B, already in plane layout) arrives by one TMA bulk copy
         ok = mbar_wait(&s_full[wg], lphase) && ok; lphase ^= 1;
+        NC_TB_MARK(1);
         tc_fence_before();
         wg_barrier(wg);
         if (wq == 0 && elect_one()) {
@@ -598,8 +607,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
             umma_commit(&s_bar[wg]);
         }
         __syncwarp();
+        NC_TB_MARK(2);
         ok = mbar_wait(&s_bar[wg], phase) && ok; phase ^= 1;
         tc_fence_after();
+        NC_TB_MARK(3);
         // the MMAs have consumed the smem image: the next group's copy overlaps the epilogue
         if (t == 0 && grp + gstride < n_groups) {
             mbar_expect_tx(&s_full[wg], tcg::C2_GROUP_BYTES);
@@ -634,9 +645,18 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
                 }
             }
         }
+        NC_TB_MARK(4);
         tc_fence_before();
         wg_barrier(wg);
+        NC_TB_MARK(5);
     }
+#ifdef NC_TB_PROFILE
+    if (blockIdx.x == 0 && wg == 0 && (t == 0 || t == 64) && prof_n > 0) {
+        printf("TB profile t=%d groups=%u cycles/group: loop %u tma_wait %u issue %u mma_wait %u epilogue %u barrier %u\n", t, prof_n,
+               prof[0] / prof_n, prof[1] / prof_n, prof[2] / prof_n, prof[3] / prof_n, prof[4] / prof_n, prof[5] / prof_n);
+    }
+#endif
+#undef NC_TB_MARK
     if (!ok && t == 0) atomicExch(P.err, 1);
     tc_fence_before();
     __syncthreads();
