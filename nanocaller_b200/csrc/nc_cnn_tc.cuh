@@ -138,6 +138,12 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     lo = pack_sat(a - ah, b - bh);
 }
 // 8 accumulator values -> bias + SELU -> hi / lo 16-byte words.  bias2 = [bias | bias * log2 e] rows of 8 floats: bias2[0..7], bias2[n_bias..]
+__device__ __forceinline__ void act_split8_nobias(const float* acc, uint4& hi, uint4& lo) {      // bias already inside the accumulator
+    split2(selu_acc(acc[0], 0.f, 0.f), selu_acc(acc[1], 0.f, 0.f), hi.x, lo.x);
+    split2(selu_acc(acc[2], 0.f, 0.f), selu_acc(acc[3], 0.f, 0.f), hi.y, lo.y);
+    split2(selu_acc(acc[4], 0.f, 0.f), selu_acc(acc[5], 0.f, 0.f), hi.z, lo.z);
+    split2(selu_acc(acc[6], 0.f, 0.f), selu_acc(acc[7], 0.f, 0.f), hi.w, lo.w);
+}
 __device__ __forceinline__ void act_split8(const float* acc, const float* bias, const float* bl, uint4& hi, uint4& lo) {
     const float4 b0 = *reinterpret_cast<const float4*>(bias), b1 = *reinterpret_cast<const float4*>(bias + 4);
     const float4 l0 = *reinterpret_cast<const float4*>(bl), l1 = *reinterpret_cast<const float4*>(bl + 4);
@@ -175,7 +181,7 @@ constexpr int C1_PITCH = 21;                   // columns per parity plane of c1
 constexpr int C1_ROWS = 5 * C1_PITCH;          // 105
 constexpr int C1_PLANE = C1_ROWS * 16;         // 1680 B per (part, parity, k-group)
 constexpr int C1_BYTES = 2 * 2 * 6 * C1_PLANE + 1024;
-constexpr int TILE1_START = 97;                // second conv1 tile covers output rows 97..224
+constexpr int TILE1_START = 96;                // second conv1 tile covers output rows 96..223 (valid: 128..220), so its first warp has no valid row
 constexpr int C2_PITCH = 10;
 constexpr int C2_SITE_ROWS = 4 * C2_PITCH;     // 40 rows per site and parity
 constexpr int C2_CHUNK = C2_SITE_ROWS * 16;    // 640 B per (part, parity, k-group)
@@ -409,6 +415,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
                 split2(v[0], v[1], hi.x, lo.x);
                 split2(v[2], v[3], hi.y, lo.y);
                 split2(v[4], 0.f, hi.z, lo.z);
+                hi.z |= 0x3C000000u;                                       // channel slot 5 = 1.0 on real pixels: multiplies the bias row of the centre tap
                 const int row = (h + 2) * tcg::WP + w + 2;
                 *reinterpret_cast<uint4*>(s_in + row * 16) = hi;
                 *reinterpret_cast<uint4*>(s_in + tcg::IN_PLANE + row * 16) = lo;
@@ -420,13 +427,13 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
     auto store_c1 = [&](int j, const float* v) {
         const int m = (j ? tcg::TILE1_START : 0) + t;
         const int h = m / tcg::WP, w = m - h * tcg::WP;
-        const bool valid = m < 225 && w < 41 && (j == 0 || m >= 128);
+        const bool valid = m < 225 && w < 41 && (j == 0 || m >= 128);      // tile 1: t >= 32, warp 0 skips the arithmetic altogether
         if (valid) {
             uint8_t* dst = s_c1 + ((w & 1) * 6) * tcg::C1_PLANE + (h * tcg::C1_PITCH + (w >> 1)) * 16;
 #pragma unroll
             for (int kg = 0; kg < 6; kg++) {
                 uint4 hi, lo;
-                act_split8(v + 8 * kg, s_bias + 8 * kg, s_bl + 8 * kg, hi, lo);
+                act_split8_nobias(v + 8 * kg, hi, lo);                     // conv1 bias rides on the centre tap (constant channel 5)
                 *reinterpret_cast<uint4*>(dst + kg * tcg::C1_PLANE) = hi;
                 *reinterpret_cast<uint4*>(dst + (12 + kg) * tcg::C1_PLANE) = lo;
             }
@@ -546,26 +553,40 @@ struct TBParams {
     uint8_t* c3_out; int* err;
 };
 constexpr int TB_WGS = 3;
-constexpr int TB_THREADS = TB_WGS * 128;
-constexpr int TB_SMEM_MISC = 128 * 4 + 96;
-constexpr int TB_SMEM = tcg::W3_BYTES + TB_WGS * tcg::C2_SMEM + TB_SMEM_MISC + 64;
+constexpr int TB_THREADS = TB_WGS * 128 + 32;               // three consumer warpgroups + one TMA producer warp
+#ifndef NC_TB_RING
+#define NC_TB_RING 5
+#endif
+constexpr int TB_RING = NC_TB_RING;                         // c2 group images in flight or in use (30,720 B each)
+constexpr int TB_SMEM_RING = TB_RING * tcg::C2_GROUP_BYTES + 512;   // + slack: junk GEMM rows read past the last plane
+constexpr int TB_SMEM_MISC = 128 * 4 + 128 + 16;            // bias, bias * log2e; mbarriers; TMEM slot
+constexpr int TB_SMEM = tcg::W3_BYTES + TB_SMEM_RING + TB_SMEM_MISC + 64;
+static_assert(TB_SMEM <= 232448, "TB shared memory exceeds the 227 KB per-CTA limit");
 
+// TB: conv3.  A group = three consecutive sites = one 128-row tile (40 rows per site) whose c2 image TA left in HBM in
+// exactly the shared-memory plane layout, so it arrives by ONE bulk copy.  The kernel is bound by the latency of that
+// copy (measured: ~8,500 cycles under load against ~1,900 of MMAs and ~2,700 of epilogue per group), so a producer warp
+// keeps a ring of TB_RING images in flight for the three consumer warpgroups (full / empty mbarriers per stage; the
+// stage is released by a tcgen05.commit, i.e. when the MMAs that read it have completed).
+// The CTA's i-th group is global group (i / 3) * 3 * gridDim + 3 * blockIdx + i % 3; warpgroup w consumes i = w mod 3.
 __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_w = smem;
-    float* s_bias = reinterpret_cast<float*>(smem + tcg::W3_BYTES + TB_WGS * tcg::C2_SMEM);
+    uint8_t* s_ring = smem + tcg::W3_BYTES;
+    float* s_bias = reinterpret_cast<float*>(s_ring + TB_SMEM_RING);
     float* s_bl = s_bias + 64;
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bl + 64);
-    uint64_t* s_full = s_bar + 4;
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bl + 64);      // [wg] MMAs of the warpgroup's current group done
+    uint64_t* s_full = s_bar + TB_WGS;                              // [stage] image landed
+    uint64_t* s_empty = s_full + TB_RING;                           // [stage] MMAs that read the image done
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_empty + TB_RING);
     const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = tid >> 5, wq = warp & 3;
-    uint8_t* s_c2 = smem + tcg::W3_BYTES + wg * tcg::C2_SMEM;
 
     for (int i = tid; i < tcg::W3_BYTES / 16; i += TB_THREADS) reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(P.wimg) + i);
     if (tid < 64) { const float b = P.bias[tid]; s_bias[tid] = b; s_bl[tid] = b * 1.4426950408889634f; }
-    for (int i = tid; i < TB_WGS * tcg::C2_SMEM / 16; i += TB_THREADS) reinterpret_cast<uint4*>(smem + tcg::W3_BYTES)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < TB_SMEM_RING / 16; i += TB_THREADS) reinterpret_cast<uint4*>(s_ring)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
-        for (int i = 0; i < TB_WGS; i++) { mbar_init(&s_bar[i], 1); mbar_init(&s_full[i], 1); }
+        for (int i = 0; i < TB_WGS; i++) mbar_init(&s_bar[i], 1);
+        for (int i = 0; i < TB_RING; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(s_tmem, 512);
@@ -573,49 +594,56 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *s_tmem + (uint32_t)wg * 128u;          // columns [0,64) = (a_hi + a_lo) w_hi, [64,128) = a_hi w_lo
-    const uint32_t tmem_lane = tmem + ((uint32_t)wq << 21);
-    const uint32_t c216 = smem_u32(s_c2) >> 4, w16 = smem_u32(s_w) >> 4;
-    uint32_t phase = 0, lphase = 0;
-    bool ok = true;
     const int64_t n_groups = (P.n_sites + 2) / 3;
     const int64_t gstride = (int64_t)gridDim.x * TB_WGS;
-    int64_t grp = (int64_t)blockIdx.x * TB_WGS + wg;
-    if (t == 0 && grp < n_groups) {
-        mbar_expect_tx(&s_full[wg], tcg::C2_GROUP_BYTES);
-        bulk_g2s(s_c2, P.c2 + grp * tcg::C2_GROUP_BYTES, tcg::C2_GROUP_BYTES, &s_full[wg]);
-    }
+    const int64_t gbase = (int64_t)blockIdx.x * TB_WGS;
+    bool ok = true;
 
-#ifdef NC_TB_PROFILE
-    uint32_t prof[6], prof_last = (uint32_t)clock(), prof_n = 0;
-    for (int i = 0; i < 6; i++) prof[i] = 0;
-#define NC_TB_MARK(i) { const uint32_t now_ = (uint32_t)clock(); prof[i] += now_ - prof_last; prof_last = now_; if (i == 5) prof_n++; }
-#else
-#define NC_TB_MARK(i)
-#endif
-    for (; grp < n_groups; grp += gstride) {
-        const int64_t s0 = grp * 3;
-        NC_TB_MARK(0);
-        // ---- the group's c2 image (30,720 B, already in plane layout) arrives by one TMA bulk copy
-        ok = mbar_wait(&s_full[wg], lphase) && ok; lphase ^= 1;
-        NC_TB_MARK(1);
+    if (wg == TB_WGS) {
+        // ===== producer warp: one bulk copy per group, in the CTA's consumption order
+        if (elect_one()) {
+            for (int64_t i = 0;; i++) {
+                const int64_t grp = (i / TB_WGS) * gstride + gbase + (i % TB_WGS);
+                if (grp >= n_groups) break;
+                const int st = (int)(i % TB_RING);
+                if (i >= TB_RING) ok = mbar_wait(&s_empty[st], (uint32_t)((i / TB_RING) - 1) & 1u) && ok;
+                mbar_expect_tx(&s_full[st], tcg::C2_GROUP_BYTES);
+                bulk_g2s(s_ring + st * tcg::C2_GROUP_BYTES, P.c2 + grp * tcg::C2_GROUP_BYTES, tcg::C2_GROUP_BYTES, &s_full[st]);
+            }
+            if (!ok) atomicExch(P.err, 1);
+        }
+        __syncwarp();
         tc_fence_before();
-        wg_barrier(wg);
+        __syncthreads();
+        return;
+    }
+    const uint32_t tmem = *s_tmem + (uint32_t)wg * 128u;          // columns [0,64) = (a_hi + a_lo) w_hi, [64,128) = a_hi w_lo
+    const uint32_t tmem_lane = tmem + ((uint32_t)wq << 21);
+    const uint32_t w16 = smem_u32(s_w) >> 4;
+    uint32_t phase = 0;
+    for (int64_t k = 0;; k++) {
+        const int64_t i = k * TB_WGS + wg;
+        const int64_t grp = k * gstride + gbase + wg;
+        if (grp >= n_groups) break;
+        const int64_t s0 = grp * 3;
+        const int st = (int)(i % TB_RING);
+        const uint32_t c216 = smem_u32(s_ring + st * tcg::C2_GROUP_BYTES) >> 4;
+        // ---- the group's c2 image (30,720 B, already in plane layout).  A parity wait is only safe one phase ahead, and the
+        // stage's previous user is ANOTHER warpgroup: first make sure that use is over (the condition the producer waited for
+        // before refilling), then the stage's full barrier is in this group's phase and the parity is unambiguous.
+        if (i >= TB_RING) ok = mbar_wait(&s_empty[st], (uint32_t)((i / TB_RING) - 1) & 1u) && ok;
+        ok = mbar_wait(&s_full[st], (uint32_t)(i / TB_RING) & 1u) && ok;
+        tc_fence_before();
+        wg_barrier(wg);                                              // the previous group's accumulators have been read by every warp
         if (wq == 0 && elect_one()) {
             tc_fence_after();
             issue_conv3_seq(c216, w16, tmem, std::make_integer_sequence<int, 12>{});
+            umma_commit(&s_empty[st]);                               // the producer may refill the stage
             umma_commit(&s_bar[wg]);
         }
         __syncwarp();
-        NC_TB_MARK(2);
         ok = mbar_wait(&s_bar[wg], phase) && ok; phase ^= 1;
         tc_fence_after();
-        NC_TB_MARK(3);
-        // the MMAs have consumed the smem image: the next group's copy overlaps the epilogue
-        if (t == 0 && grp + gstride < n_groups) {
-            mbar_expect_tx(&s_full[wg], tcg::C2_GROUP_BYTES);
-            bulk_g2s(s_c2, P.c2 + (grp + gstride) * tcg::C2_GROUP_BYTES, tcg::C2_GROUP_BYTES, &s_full[wg]);
-        }
         // ---- epilogue: row m = s*40 + h3*10 + w3 -> HBM c3 [tile][part][pos*8 + g][site % 128][8]
         {
             const int s = t / 40, r = t - s * 40, h3 = r / 10, w3 = r - h3 * 10;
@@ -633,7 +661,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
                 tmem_ld_wait();
                 if (valid) {
 #pragma unroll
-                    for (int i = 0; i < 32; i++) acc[i] += acc2[i];
+                    for (int i2 = 0; i2 < 32; i2++) acc[i2] += acc2[i2];
 #pragma unroll
                     for (int g = 0; g < 4; g++) {
                         uint4 hi, lo;
@@ -645,18 +673,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
                 }
             }
         }
-        NC_TB_MARK(4);
         tc_fence_before();
-        wg_barrier(wg);
-        NC_TB_MARK(5);
     }
-#ifdef NC_TB_PROFILE
-    if (blockIdx.x == 0 && wg == 0 && (t == 0 || t == 64) && prof_n > 0) {
-        printf("TB profile t=%d groups=%u cycles/group: loop %u tma_wait %u issue %u mma_wait %u epilogue %u barrier %u\n", t, prof_n,
-               prof[0] / prof_n, prof[1] / prof_n, prof[2] / prof_n, prof[3] / prof_n, prof[4] / prof_n, prof[5] / prof_n);
-    }
-#endif
-#undef NC_TB_MARK
     if (!ok && t == 0) atomicExch(P.err, 1);
     tc_fence_before();
     __syncthreads();
@@ -894,13 +912,17 @@ inline int tc_model_prepare(cudaStream_t stream, TcModel& T, int kind, const flo
         const int kh = t / 5, kw = t % 5;
         const size_t base = (size_t)c1_tap_off16(t) * 16;
         int row = 0;
-        auto put_branch = [&](const float* wtap) {            // wtap -> [ci 5][co 16]; 16 hi rows then 16 lo rows
+        auto put_branch = [&](const float* wtap, const float* bias16) {   // wtap -> [ci 5][co 16]; 16 hi rows then 16 lo rows
             for (int part = 0; part < 2; part++)
-                for (int n = 0; n < 16; n++) put_row(w1_img, base + (size_t)(row++) * 16, wtap + n, 16, 5, part);
+                for (int n = 0; n < 16; n++) {
+                    put_row(w1_img, base + (size_t)row * 16, wtap + n, 16, 5, part);
+                    if (t == 12) put_row(w1_img, base + (size_t)row * 16 + 10, bias16 + n, 0, 1, part);   // slot 5: the bias, met by the constant 1.0 channel
+                    row++;
+                }
         };
-        if (kh == 2) put_branch(w11 + (size_t)kw * 5 * 16);                 // 1x5 branch: columns 0..31
-        put_branch(w13 + (size_t)t * 5 * 16);                               // 5x5 branch
-        if (kw == 2) put_branch(w12 + (size_t)kh * 5 * 16);                 // 5x1 branch: columns 64..95 (32..63 of a column-tap tile)
+        if (kh == 2) put_branch(w11 + (size_t)kw * 5 * 16, b11);            // 1x5 branch: columns 0..31
+        put_branch(w13 + (size_t)t * 5 * 16, b13);                          // 5x5 branch
+        if (kw == 2) put_branch(w12 + (size_t)kh * 5 * 16, b12);            // 5x1 branch: columns 64..95 (32..63 of a column-tap tile)
         if (row != c1_tap_n(t)) { if (err) *err = "conv1 tile size mismatch"; return NC_EINVAL; }
     }
     // ---------------- conv2: [kh 2][kw 3][ci 48][co 32]; per (tap, chunk) [k-group 2][w_hi 32 | w_lo 32][8 slots]
