@@ -43,6 +43,18 @@ def workload(rank, length):
     return rs, chunks
 
 
+def measured_traffic():
+    """DRAM bytes per site of the kernel groups, from the committed `ncu --set full` capture (profiles/r1_kernel_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum per launch / sites of that launch).  None when the file is absent."""
+    p = os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -57,7 +69,7 @@ class ClockSampler:
     def __init__(self, index):
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
@@ -326,11 +338,23 @@ def main():
         cnn_ms = acc["cnn_ms"] / args.steps
         tensor_ms = acc["tensor_ms"] / args.steps
         ach = FLOP_PER_SITE * n_sites / (cnn_ms * 1e-3) / 1e12
-        roof = {"kernel": "CNN forward (tc_trunk_a + tc_trunk_b + tc_fc: tcgen05 kind::f16, 3 split-precision MMAs per product)",
-                "bound": "tensor", "achieved": ach, "peak": tflops, "unit": "TFLOP/s", "frac": ach / tflops, "traffic": None,
-                "peak_source": which + ", sustained bf16", "flop_per_site": FLOP_PER_SITE, "ms_per_launch_group": cnn_ms}
+        tr = measured_traffic() or {}
+        # operand-read model of the MMA programs (profiles/r1_umma_rate.txt): an M=128, K=16 MMA with both operands in
+        # shared memory costs 32 + N/4 cycles whatever the tensor pipe could do; per site: conv1 2 x 1080, conv2 1584, conv3 448, fc1 84
+        mma_cycles_per_site = 2 * 1080 + 1584 + 1344 / 3.0 + 27 * 4 * 100 / 128.0
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        mma_floor_ms = mma_cycles_per_site * n_sites / (148 * sm_clock * 1e6) * 1e3
+        roof = {"kernel": "CNN forward (tc_trunk_a + tc_trunk_b + tc_fc: tcgen05 kind::f16, fp16 hi/lo split operands, hi*hi + lo*hi + hi*lo)",
+                "bound": "tensor", "achieved": ach, "peak": tflops, "unit": "TFLOP/s", "frac": ach / tflops,
+                "traffic": (tr["cnn_dram_bytes_per_site"] * n_sites) if "cnn_dram_bytes_per_site" in tr else None,
+                "traffic_source": tr.get("source"),
+                "algorithmic_bytes": n_sites * (2064 + 2 * 10240 + 2 * 6912 + 16),
+                "peak_source": which + ", sustained bf16", "flop_per_site": FLOP_PER_SITE, "ms_per_launch_group": cnn_ms,
+                "mma_operand_model": {"cycles_per_site": mma_cycles_per_site, "floor_ms": mma_floor_ms, "frac_of_floor": mma_floor_ms / cnn_ms,
+                                      "note": "N <= 128 MMAs are bound by shared-memory operand reads (32 + N/4 cycles each), not by the bf16 peak"}}
         roof2 = {"kernel": "tensor_kernel (K2 pileup tensor build)", "bound": "hbm", "achieved": tbytes / (tensor_ms * 1e-3) / 1e9,
-                 "peak": hbm, "unit": "GB/s", "frac": tbytes / (tensor_ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                 "peak": hbm, "unit": "GB/s", "frac": tbytes / (tensor_ms * 1e-3) / 1e9 / hbm,
+                 "traffic": (tr["tensor_dram_bytes_per_site"] * n_sites) if "tensor_dram_bytes_per_site" in tr else None,
                  "bytes_per_site": tbytes / max(1, n_sites), "ms_per_launch": tensor_ms}
         cpu = None
         if world == 1:

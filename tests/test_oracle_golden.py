@@ -82,3 +82,25 @@ def test_get_cnd_pos_against_reference_source_rules():
     assert 59500 not in l and 59000 not in l
     assert r[:2] == [61500, 62000]             # last two of (60000, 62000]
     assert len(l) == 2 + 3 + 4 + 5 + 6 and len(r) == 20
+
+
+def test_golden_tensors_obey_the_size_independent_invariants():
+    """The invariants the GPU scale test relies on (tests/test_cuda_scale_properties.py) hold for the reference's own output."""
+    from tests.golden_util import check_tensor_invariants, golden_chunk, load_case
+    checked = 0
+    for name in ("ont_diploid", "hifi_pacbio", "ul_ont", "short_ont", "lowcov"):
+        rs, dct, chunks, bed, g = load_case(name)
+        for ci in range(len(chunks)):
+            w = golden_chunk(g, ci)
+            n = len(w["pos"])
+            if n == 0:
+                continue
+            x = np.asarray(w["mat"]).astype(np.int32).reshape(n, 5, 41, 5)
+            ref_code = np.asarray(w["ref"]).argmax(1)
+            real = (np.abs(x).sum((1, 3)) > 0)
+            n_left = real[:, :20].sum(1); n_right = real[:, 21:].sum(1)
+            sampled = np.minimum(np.asarray(w["dp"]), dct["maxcov"])
+            acgt = np.asarray(w["fwd"]).sum(1) + np.asarray(w["rev"]).sum(1)
+            check_tensor_invariants(x, ref_code, n_left, n_right, sampled, w["dp"], acgt, dct["maxcov"])
+            checked += n
+    assert checked > 1000
