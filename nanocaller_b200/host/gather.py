@@ -17,26 +17,60 @@ class _DeviceBytes:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-def gather_records(records, dist, world, device=None):
-    """records: uint8 tensor [n, W] (any n per rank).  Returns (tensor [sum n, W] in rank order, counts list)."""
+_BUFS = {}
+
+
+def _buffers(key, make):
+    if key not in _BUFS:
+        _BUFS[key] = make()
+    return _BUFS[key]
+
+
+def gather_records(records, dist, world, device=None, rank=None, to_host=False):
+    """records: uint8 tensor [n, W] (any n per rank).
+    Default: every rank gets (tensor [sum n, W] in rank order, counts) — an all-gather.
+    With `rank` given: a gather to rank 0 only; rank 0 gets the tensor (pinned host memory when `to_host`), the other
+    ranks get None.  Staging buffers are cached across calls (a per-step allocation costs more than the exchange)."""
     import torch
     dev = records.device if device is None else device
-    n = torch.tensor([records.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n)
-    counts = [int(c.item()) for c in counts]
-    nmax = max(counts) if counts else 0
     W = records.shape[1]
-    pad = torch.zeros((max(nmax, 1), W), dtype=torch.uint8, device=dev)
+    n = torch.tensor([records.shape[0]], dtype=torch.int64, device=dev)
+    cnt = _buffers(("cnt", world, str(dev)), lambda: torch.zeros(world, dtype=torch.int64, device=dev))
+    dist.all_gather(list(cnt.split(1)), n)         # the outputs are views of `cnt`
+    counts = [int(c) for c in cnt.tolist()]
+    nmax = max(max(counts), 1)
+    cap = _BUFS.get(("cap", world, W, str(dev)), 0)
+    if nmax > cap:
+        cap = int(nmax * 1.25) + 16
+        _BUFS[("cap", world, W, str(dev))] = cap
+        for k in [k for k in _BUFS if k[0] in ("pad", "parts", "pin") and k[1:] == (world, W, str(dev))]:
+            del _BUFS[k]
+    pad = _buffers(("pad", world, W, str(dev)), lambda: torch.zeros((cap, W), dtype=torch.uint8, device=dev))
     pad[:records.shape[0]] = records
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad)
-    return torch.cat([p[:c] for p, c in zip(parts, counts)], 0), counts
+    if rank is None:
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        return torch.cat([p[:c] for p, c in zip(parts, counts)], 0), counts
+    if rank == 0:
+        parts = _buffers(("parts", world, W, str(dev)), lambda: [torch.empty_like(pad) for _ in range(world)])
+        dist.gather(pad, parts, dst=0)
+        if not to_host:
+            return torch.cat([p[:c] for p, c in zip(parts, counts)], 0), counts
+        pin = _buffers(("pin", world, W, str(dev)), lambda: torch.empty((cap * world, W), dtype=torch.uint8, pin_memory=(dev.type == "cuda")))
+        off = 0
+        for p_, c in zip(parts, counts):
+            pin[off:off + c].copy_(p_[:c], non_blocking=True)
+            off += c
+        if dev.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        return pin[:off], counts
+    dist.gather(pad, None, dst=0)
+    return None, counts
 
 
 def gather_calls(ctx, dist, rank, world):
-    """All ranks: contribute the call records of the last scan+forward; rank 0 copies the gathered set to the host.
-    Returns the number of gathered sites."""
+    """All ranks: contribute the call records of the last scan+forward; rank 0 receives them in rank (= genomic) order
+    and copies them to pinned host memory.  Returns the number of gathered sites."""
     import torch
     ctx.sync()                                     # records are produced on the library's stream
     _, meta_ptr, probs_ptr, n = ctx.device_buffers()
@@ -46,10 +80,7 @@ def gather_calls(ctx, dist, rank, world):
         rec = torch.cat([probs, meta], 1)
     else:
         rec = torch.zeros((0, RECORD_BYTES), dtype=torch.uint8, device="cuda")
-    allrec, counts = gather_records(rec, dist, world)
-    if rank == 0:
-        host = allrec.cpu()
-        return int(host.shape[0])
+    host, counts = gather_records(rec, dist, world, rank=rank, to_host=True)
     return int(sum(counts))
 
 

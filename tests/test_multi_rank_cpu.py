@@ -67,6 +67,43 @@ def test_gather_records_world2_gloo():
             np.testing.assert_array_equal(meta["chunk"], want_m["chunk"])
 
 
+def _worker_root(rank, world, port, rounds, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = []
+    for counts in rounds:                                   # consecutive steps reuse (and grow) the cached staging buffers
+        _, _, rec = _records(rank, counts[rank])
+        host, got_counts = gather_records(torch.from_numpy(rec), dist, world, rank=rank, to_host=True)
+        out.append((None if host is None else host.numpy().copy(), got_counts))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_to_rank0_world2_gloo():
+    """The bench / product exchange: gather to rank 0 only, into cached buffers, over several steps of changing sizes."""
+    world = 2
+    rounds = [[7, 3], [2, 9], [40, 0], [5, 5]]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_root, args=(r, world, port, rounds, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for k, counts in enumerate(rounds):
+        host0, c0 = res[0][k]
+        host1, c1 = res[1][k]
+        assert c0 == counts and c1 == counts and host1 is None
+        probs, meta = split_records(host0)
+        np.testing.assert_array_equal(probs, np.concatenate([_records(r, counts[r])[0] for r in range(world)]))
+        np.testing.assert_array_equal(meta["pos"], np.concatenate([_records(r, counts[r])[1] for r in range(world)])["pos"])
+
+
 def test_shard_chunks_contiguous_balanced_and_complete():
     from oracle.snp_oracle import get_chunks
     chunks = get_chunks([("chr1", 1, 7_300_000, "diploid"), ("chr2", 1, 2_100_000, "diploid")], 1)
