@@ -190,7 +190,8 @@ constexpr int C2_GROUP_BYTES = 3 * C2_SITE_BYTES;      // 30720 B: three sites s
 constexpr int C2_PLANE = 3 * C2_CHUNK;         // three sites stacked: 1920 B
 constexpr int C2_SMEM = 2 * 2 * 4 * C2_PLANE + 512;
 constexpr int FC_KG = 27 * 8;                  // 216 k-groups of fc1 (27 positions x 64 channels)
-constexpr int C3_TILE_BYTES = 2 * FC_KG * 128 * 16;   // 884736 B per 128-site tile in HBM
+constexpr int C3_BLOCK_BYTES = 128 * 128;               // one (position, part) of a 128-site tile: [site][64 channels] fp16, 16 KB
+constexpr int C3_TILE_BYTES = 27 * 2 * C3_BLOCK_BYTES;  // 884736 B per 128-site tile in HBM: [position][part][site][64 channels]
 
 // What one MMA costs (measured, tools/umma_rate.cu): M = 128, K = 16, operands in shared memory, any N <= 128:
 // 32 + N/4 cycles, i.e. (A bytes + B bytes) / 128 B per clock -- the tensor pipe is never the limit here, the operand
@@ -644,13 +645,16 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
         __syncwarp();
         ok = mbar_wait(&s_bar[wg], phase) && ok; phase ^= 1;
         tc_fence_after();
-        // ---- epilogue: row m = s*40 + h3*10 + w3 -> HBM c3 [tile][part][pos*8 + g][site % 128][8]
+        // ---- epilogue: row m = s*40 + h3*10 + w3 -> HBM c3 [tile of 128 sites][pos 27][part 2][site][64 channels]: every thread
+        //      writes two full 128-byte lines (scattering 16-byte pieces into a k-group-major layout cost TB a third of its
+        //      time); the 16-byte chunks of a line are permuted (chunk ^ site % 8) so that fc1's bulk copy of the 16 KB block
+        //      IS the 128-byte-swizzle shared-memory image
         {
             const int s = t / 40, r = t - s * 40, h3 = r / 10, w3 = r - h3 * 10;
             const int64_t site = s0 + s;
             const bool valid = s < 3 && h3 < 3 && w3 < 9 && site < P.n_sites;
             const int pos = h3 * 9 + w3;
-            uint8_t* dst = P.c3_out + (site >> 7) * (int64_t)tcg::C3_TILE_BYTES + (int64_t)(pos * 8) * 2048 + (site & 127) * 16;
+            uint8_t* dst = P.c3_out + (site >> 7) * (int64_t)tcg::C3_TILE_BYTES + (int64_t)pos * (2 * tcg::C3_BLOCK_BYTES) + (site & 127) * 128;
 #pragma unroll 1
             for (int half = 0; half < 2; half++) {
                 float acc[32], acc2[32];
@@ -667,8 +671,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
                         uint4 hi, lo;
                         const int kg = half * 4 + g;
                         act_split8(acc + 8 * g, s_bias + 8 * kg, s_bl + 8 * kg, hi, lo);
-                        *reinterpret_cast<uint4*>(dst + (int64_t)kg * 2048) = hi;
-                        *reinterpret_cast<uint4*>(dst + (int64_t)(tcg::FC_KG + kg) * 2048) = lo;
+                        const int ck = (kg ^ (int)(site & 7)) * 16;                  // chunk position under the 128-byte swizzle
+                        *reinterpret_cast<uint4*>(dst + ck) = hi;
+                        *reinterpret_cast<uint4*>(dst + tcg::C3_BLOCK_BYTES + ck) = lo;
                     }
                 }
             }
@@ -695,7 +700,8 @@ struct TCParams {
 };
 constexpr int TC_STAGE_A = 2 * 8 * 2048;                    // 32768: [part][kg 8][128 rows][16 B]
 constexpr int TC_STAGE = TC_STAGE_A + tcg::WF_POS_BYTES;    // + 12288 of weights
-constexpr int TC_SMEM = 2 * TC_STAGE + 48 * 4 + 96 + 64;
+constexpr int TC_SMEM = 2 * TC_STAGE + 48 * 4 + 96 + 64 + 1024;     // + slack for the 1024-byte alignment of the stages
+static_assert(TC_STAGE % 1024 == 0, "stages must keep the 1024-byte alignment");
 
 __device__ __forceinline__ void snp_tail_row(const float* x, int64_t s, const TCParams& P) {
     const TailW& w = P.tail;
@@ -732,8 +738,20 @@ __device__ __forceinline__ void snp_tail_row(const float* x, int64_t s, const TC
     }
 }
 
+// K-major operand in the 128-byte-swizzle layout: rows of 128 B (64 fp16 along K), 16-byte chunk j of row r stored at chunk
+// j ^ (r & 7); 8-row groups 1024 B apart (SBO); the K = 16 slice of an MMA is selected by advancing the start address by 32 B.
+// The tile base must be 1024-byte aligned.
+__device__ __forceinline__ uint64_t sdesc_sw128(uint32_t addr16) {
+    return (uint64_t)(addr16 & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// TC: fc1 as a K-streamed GEMM over the 27 positions (K = 64 channels each) + the heads, 128 sites per CTA, 2 CTAs per SM.
+// TB leaves c3 in HBM as [position][part][site][64 channels] blocks of 16 KB whose 16-byte chunks are already permuted the
+// way the 128-byte swizzle wants them, so a block is ONE bulk copy and lands as a ready UMMA operand.  Warp 0 = TMA
+// producer, warp 1 = MMA issuer, two stages (full / empty mbarriers), all four warps run the epilogue.
 __global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzled tiles want 1024-byte alignment
     float* s_bias = reinterpret_cast<float*>(smem + 2 * TC_STAGE);
     uint64_t* s_full = reinterpret_cast<uint64_t*>(s_bias + 48);      // [2] TMA bytes landed
     uint64_t* s_empty = s_full + 2;                                    // [2] MMAs that read the stage have completed
@@ -764,8 +782,7 @@ __global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
                 if (pos >= 2) ok = mbar_wait(&s_empty[st], ((pos >> 1) - 1) & 1) && ok;
                 uint8_t* dst = smem + st * TC_STAGE;
                 mbar_expect_tx(&s_full[st], TC_STAGE);
-                bulk_g2s(dst, a_src + (int64_t)(pos * 8) * 2048, 16384, &s_full[st]);
-                bulk_g2s(dst + 16384, a_src + ((int64_t)tcg::FC_KG + pos * 8) * 2048, 16384, &s_full[st]);
+                bulk_g2s(dst, a_src + (int64_t)(pos * 2) * tcg::C3_BLOCK_BYTES, 2 * tcg::C3_BLOCK_BYTES, &s_full[st]);   // hi block, lo block
                 bulk_g2s(dst + TC_STAGE_A, P.wimg + (int64_t)pos * tcg::WF_POS_BYTES, tcg::WF_POS_BYTES, &s_full[st]);
             }
         }
@@ -781,9 +798,9 @@ __global__ void __launch_bounds__(128, 2) tc_fc_kernel(const TCParams P) {
                 const uint32_t b0 = (sb16 + TC_STAGE_A / 16) | (96u << 16);
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    const uint32_t a_hi = sb16 + (2 * c) * 128 + (128u << 16), a_lo = a_hi + 8 * 128;
-                    umma_f16(tmem, sdesc16(a_hi), sdesc16(b0 + c * (tcg::WF_TILE / 16)), make_idesc_f16(128, 96), (pos > 0 || c > 0) ? 1u : 0u);
-                    umma_f16(tmem, sdesc16(a_lo), sdesc16(b0 + c * (tcg::WF_TILE / 16)), make_idesc_f16(128, 48), 1u);
+                    const uint32_t a_hi = sb16 + 2 * c, a_lo = a_hi + tcg::C3_BLOCK_BYTES / 16;       // 32 B further along K per chunk
+                    umma_f16(tmem, sdesc_sw128(a_hi), sdesc16(b0 + c * (tcg::WF_TILE / 16)), make_idesc_f16(128, 96), (pos > 0 || c > 0) ? 1u : 0u);
+                    umma_f16(tmem, sdesc_sw128(a_lo), sdesc16(b0 + c * (tcg::WF_TILE / 16)), make_idesc_f16(128, 48), 1u);
                 }
                 umma_commit(&s_empty[st]);
             }

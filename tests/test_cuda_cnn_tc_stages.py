@@ -61,9 +61,12 @@ def test_trunk_stages_match_oracle():
     err2 = np.abs(got_c2 - want_c2).max()
     assert err2 < 2e-4, err2
 
-    tiles = (n + 127) // 128
-    raw = _trunk(x, n, 2, tiles * 884736).view(np.float16).reshape(tiles, 2, 216, 128, 8).astype(np.float32)
-    v = raw[:, 0] + raw[:, 1]                                   # [tile, kgroup, row, 8]
+    tiles = (n + 127) // 128                # c3 in HBM: [tile][position 27][part][site % 128][8 chunks of 8 channels], chunk j stored at j ^ (site % 8)
+    raw = _trunk(x, n, 2, tiles * 884736).view(np.float16).reshape(tiles, 27, 2, 128, 8, 8).astype(np.float32)
+    unsw = np.empty_like(raw)
+    for r in range(8):
+        unsw[:, :, :, r::8, :, :] = raw[:, :, :, r::8, np.arange(8) ^ r, :]
+    v = (unsw[:, :, 0] + unsw[:, :, 1]).reshape(tiles, 27, 128, 64)          # [tile, pos, site, ch]
     got_c3 = np.transpose(v, (0, 2, 1, 3)).reshape(tiles * 128, 27, 64)[:n].reshape(n, 3, 9, 64)
     err3 = np.abs(got_c3 - want_c3).max()
     assert err3 < 2e-4, err3
