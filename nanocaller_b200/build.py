@@ -3,6 +3,7 @@ they travel to the GPU box with the repo snapshot.
 
   libnanocaller_b200.so   nvcc, sm_100a only: CUDA kernels + the C-ABI (include/nanocaller_b200.h)
   libnc_synth.so          g++: synthetic world generator (test / bench infrastructure)
+  libnc_bamio.so          g++ -lz: native BGZF/BAM reader into the staging arrays (include/nanocaller_b200_io.h)
 
 `python -m nanocaller_b200.build` builds everything that is stale.
 """
@@ -16,6 +17,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_CUDA = os.path.join(HERE, "libnanocaller_b200.so")
 LIB_SYNTH = os.path.join(HERE, "libnc_synth.so")
+LIB_BAMIO = os.path.join(HERE, "libnc_bamio.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -50,6 +52,15 @@ def build_synth(force=False, verbose=False):
     return LIB_SYNTH
 
 
+def build_bamio(force=False, verbose=False):
+    """g++ -lz -pthread: native BGZF/BAM reader (include/nanocaller_b200_io.h)."""
+    src = os.path.join(CSRC, "bamio.cpp")
+    hdr = os.path.join(ROOT, "include", "nanocaller_b200_io.h")
+    if force or _stale(LIB_BAMIO, [src, hdr]):
+        _run(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", LIB_BAMIO, src, "-lz"], verbose)
+    return LIB_BAMIO
+
+
 def cuda_deps():
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(CUDA_DEPS_EXT)]
     deps.append(os.path.join(ROOT, "include", "nanocaller_b200.h"))
@@ -72,6 +83,7 @@ def build_cuda(force=False, verbose=False, extra=()):
 
 def build_all(force=False, verbose=False):
     build_synth(force, verbose)
+    build_bamio(force, verbose)
     build_cuda(force, verbose)
 
 

@@ -183,12 +183,98 @@ def write_fasta(path, readsets, width=60):
             off += rs.contig_len + (rs.contig_len + width - 1) // width
 
 
-def open_alignment(sam_path, fasta_path):
+# ---------------------------------------------------------------------------------------------- native reader (libnc_bamio.so)
+import ctypes  # noqa: E402
+
+_LIB = None
+
+
+class NcBamContig(ctypes.Structure):                     # include/nanocaller_b200_io.h
+    _fields_ = [("name", ctypes.c_char * 256), ("length", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("n_reads", ctypes.c_int64), ("n_cigar", ctypes.c_int64), ("n_seq", ctypes.c_int64)]
+
+
+IO_EXPORTS = ["nc_bam_open", "nc_bam_error", "nc_bam_n_contigs", "nc_bam_header_text", "nc_bam_contig", "nc_bam_fill",
+              "nc_bam_qname", "nc_bam_close"]
+
+
+def load_io_library():
+    """ctypes handle of libnc_bamio.so (built in-tree by nanocaller_b200.build)."""
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libnc_bamio.so")
+        if not os.path.exists(path):
+            from .. import build
+            build.build_bamio()
+        lib = ctypes.CDLL(path)
+        vp = ctypes.c_void_p
+        lib.nc_bam_open.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(vp)]
+        lib.nc_bam_error.argtypes = [vp]; lib.nc_bam_error.restype = ctypes.c_char_p
+        lib.nc_bam_n_contigs.argtypes = [vp]
+        lib.nc_bam_header_text.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]; lib.nc_bam_header_text.restype = ctypes.c_void_p
+        lib.nc_bam_contig.argtypes = [vp, ctypes.c_int, ctypes.POINTER(NcBamContig)]
+        lib.nc_bam_fill.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 9
+        lib.nc_bam_qname.argtypes = [vp, ctypes.c_int, ctypes.c_int64, ctypes.c_char_p, ctypes.c_int]
+        lib.nc_bam_close.argtypes = [vp]; lib.nc_bam_close.restype = None
+        _LIB = lib
+    return _LIB
+
+
+def read_bam_native(path, fasta=None, contigs=None, threads=0, alloc=None, qnames=False):
+    """Same result as `read_bam`, through libnc_bamio.so: parallel BGZF inflate + parallel record copy into the
+    staging arrays.  `alloc(shape, dtype)` lets the caller provide the arrays (e.g. pinned host memory for the H2D copy);
+    query names are only materialised with `qnames=True` (the device path has no use for them)."""
+    lib = load_io_library()
+    h = ctypes.c_void_p()
+    rc = lib.nc_bam_open(os.fsencode(path), int(threads), ctypes.byref(h))
+    try:
+        if rc != 0:
+            msg = (lib.nc_bam_error(h) or b"").decode() if h else "open failed"
+            if rc == -2:
+                raise FileNotFoundError("%s: %s" % (path, msg))
+            raise ValueError("%s: %s" % (path, msg))
+        ln = ctypes.c_int64()
+        tp = lib.nc_bam_header_text(h, ctypes.byref(ln))
+        text = ctypes.string_at(tp, ln.value).decode(errors="replace") if tp and ln.value else ""
+        mk = alloc or (lambda shape, dtype: np.empty(shape, dtype))
+        out = []
+        for i in range(lib.nc_bam_n_contigs(h)):
+            c = NcBamContig()
+            lib.nc_bam_contig(h, i, ctypes.byref(c))
+            name = c.name.decode()
+            if contigs is not None and name not in contigs:
+                continue
+            n = c.n_reads
+            pos, flag, lseq = mk(n, np.int32), mk(n, np.uint16), mk(n, np.int32)
+            cig_off, seq_off = mk(n + 1, np.int64), mk(n + 1, np.int64)
+            cigar, seq4 = mk(c.n_cigar, np.uint32), mk(c.n_seq, np.uint8)
+            hp, ps = np.empty(n, np.int8), np.empty(n, np.int32)
+            rc = lib.nc_bam_fill(h, i, int(threads), *[a.ctypes.data for a in (pos, flag, cig_off, cigar, seq_off, lseq, seq4, hp, ps)])
+            if rc != 0:
+                raise ValueError("%s: nc_bam_fill failed (%d)" % (path, rc))
+            qn = None
+            if qnames:
+                buf = ctypes.create_string_buffer(256)
+                qn = []
+                for k in range(n):
+                    lib.nc_bam_qname(h, i, k, buf, 256)
+                    qn.append(buf.value.decode())
+            ref = fasta.get(name) if fasta else None
+            if ref is None:
+                ref = np.full(c.length, ord("N"), np.uint8)
+            out.append(ReadSet(name, ref, pos, flag, cig_off, cigar, seq_off, lseq, seq4, hp, ps, qn))
+        return out, text
+    finally:
+        if h:
+            lib.nc_bam_close(h)
+
+
+def open_alignment(sam_path, fasta_path, native=True):
     """Parse `sam_path` (BAM) and `fasta_path` once and register the contigs as an alignment source."""
     from . import sources
     if not os.path.exists(sam_path):
         raise FileNotFoundError(sam_path)
     fasta = read_fasta(fasta_path) if fasta_path and os.path.exists(fasta_path) else None
-    readsets, _ = read_bam(sam_path, fasta)
+    readsets, _ = (read_bam_native if native else read_bam)(sam_path, fasta)
     sources.register_source(sam_path, readsets)
     return readsets

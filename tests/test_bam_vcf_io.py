@@ -53,3 +53,65 @@ def test_vcf_writer(tmp_path):
     assert txt.splitlines()[-5].endswith("FORMAT\tS1") and txt.endswith(s[-1])
     h = vcfio.header("indels", ["chr1"])
     assert "ID=GQ" in h and "ID=PS" in h and "LOW" not in h
+
+
+def test_native_bam_reader_matches_python_reader(tmp_path):
+    """libnc_bamio.so (parallel inflate + record copy) vs the pure-Python parser on the same files, array for array."""
+    rs1 = make_world(chrom="chrA", preset="ont", contig_len=60_000, seed=5, coverage=12.0, indel_every=900, indel_maxlen=9,
+                     junk_frac=0.05, untagged_frac=0.2).reads
+    rs2 = _handmade()
+    rs3 = make_world(chrom="chrB", preset="ont", contig_len=20_000, seed=6, coverage=5.0).reads
+    bam, fa = str(tmp_path / "n.bam"), str(tmp_path / "n.fa")
+    bamio.write_bam(bam, [rs1, rs2, rs3])
+    bamio.write_fasta(fa, [rs1, rs2, rs3])
+    fasta = bamio.read_fasta(fa)
+    want, text_w = bamio.read_bam(bam, fasta)
+    for threads in (1, 4):
+        got, text_g = bamio.read_bam_native(bam, fasta, threads=threads, qnames=True)
+        assert text_g == text_w and [g.chrom for g in got] == [w.chrom for w in want]
+        for g, w in zip(got, want):
+            _same(g, w)
+            assert g.qnames == w.qnames and g.contig_len == w.contig_len
+    only, _ = bamio.read_bam_native(bam, fasta, contigs={"tiny"})
+    assert [r.chrom for r in only] == ["tiny"] and only[0].checksum() == want[1].checksum()
+    # caller-provided buffers (what a pinned-memory stager passes)
+    pool = []
+
+    def alloc(shape, dtype):
+        a = np.zeros(shape, dtype)
+        pool.append(a)
+        return a
+    got, _ = bamio.read_bam_native(bam, fasta, alloc=alloc)
+    assert len(pool) == 7 * 3 and got[0].pos is pool[0] and got[0].checksum() == want[0].checksum()
+
+
+def test_native_bam_reader_errors(tmp_path):
+    import pytest
+    with pytest.raises(FileNotFoundError):
+        bamio.read_bam_native(str(tmp_path / "absent.bam"))
+    p = str(tmp_path / "garbage.bam")
+    open(p, "wb").write(b"this is not a BGZF stream at all, just text......")
+    with pytest.raises(ValueError, match="BGZF"):
+        bamio.read_bam_native(p)
+    p2 = str(tmp_path / "notbam.bam")
+    open(p2, "wb").write(bamio.bgzf_compress(b"VCF\x01 something else"))
+    with pytest.raises(ValueError, match="magic"):
+        bamio.read_bam_native(p2)
+    # truncated file: cut the valid BAM in the middle of a block
+    rs = _handmade()
+    p3 = str(tmp_path / "ok.bam")
+    bamio.write_bam(p3, [rs])
+    raw = open(p3, "rb").read()
+    p4 = str(tmp_path / "cut.bam")
+    open(p4, "wb").write(raw[:len(raw) // 2])
+    with pytest.raises(ValueError):
+        bamio.read_bam_native(p4)
+
+
+def test_io_header_symbols_exported():
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "nanocaller_b200_io.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(nc_bam_[a-z0-9_]+)\s*\(", src)))
+    lib = bamio.load_io_library()
+    assert names == sorted(bamio.IO_EXPORTS) and all(hasattr(lib, n) for n in names)
