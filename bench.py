@@ -356,13 +356,23 @@ def main():
         from oracle.snp_oracle import get_chunks as _gc
         ch_d = [(c["start"], c["end"]) for c in _gc([("chr20", 1, args.from_bam, "diploid")], 1)]
 
+        arena = {"buf": None, "off": 0}
+
         def pinned_alloc(shape, dtype):
-            n_ = int(np.prod(shape)) if not np.isscalar(shape) else int(shape)
-            tt = torch.empty(max(1, n_ * np.dtype(dtype).itemsize), dtype=torch.uint8, pin_memory=True)
-            keep.append(tt)
-            return tt.numpy()[:n_ * np.dtype(dtype).itemsize].view(dtype)
+            """Bump allocator over one pinned arena, reset every step (a real stager keeps such buffers for the whole run)."""
+            nb = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            if arena["buf"] is None:
+                tot = int((rs_d.pos.nbytes + rs_d.flag.nbytes + rs_d.cigar_off.nbytes + rs_d.cigar.nbytes + rs_d.seq_off.nbytes +
+                           rs_d.l_seq.nbytes + rs_d.seq4.nbytes) * 1.05) + (1 << 20)
+                tt = torch.empty(tot, dtype=torch.uint8, pin_memory=True)
+                keep.append(tt)
+                arena["buf"] = tt.numpy()
+            o = (arena["off"] + 63) & ~63
+            arena["off"] = o + nb
+            return arena["buf"][o:o + nb].view(dtype)
 
         def disk_step():
+            arena["off"] = 0
             fasta = bamio.read_fasta(fa_p)
             sets, _ = bamio.read_bam_native(bam_p, fasta, alloc=pinned_alloc)
             r = sets[0]

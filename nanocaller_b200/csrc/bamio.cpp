@@ -12,6 +12,10 @@
 //   4. records are copied into the caller's arrays in parallel.
 // C ABI, two calls: nc_bam_open parses and reports sizes, nc_bam_fill writes into caller-owned buffers (numpy or
 // pinned memory), nc_bam_close frees.  No htslib; zlib and pthreads only.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -36,8 +40,20 @@ struct Contig {
 
 }  // namespace
 
+// Uninitialised byte buffer: the inflate workers are the first to touch the pages, so the page faults are spread over the
+// threads instead of being paid by one zero-filling constructor.
+struct RawBuf {
+    uint8_t* p = nullptr;
+    size_t n = 0;
+    ~RawBuf() { free(p); }
+    bool alloc(size_t bytes) { free(p); p = (uint8_t*)malloc(bytes ? bytes : 1); n = p ? bytes : 0; return p != nullptr; }
+    const uint8_t* data() const { return p; }
+    uint8_t* data() { return p; }
+    size_t size() const { return n; }
+};
+
 struct nc_bam {
-    std::vector<uint8_t> data;      // inflated BAM stream
+    RawBuf data;                    // inflated BAM stream
     std::string text, err;
     std::vector<Contig> contigs;
     std::vector<int64_t> rec_off;   // byte offset of every mapped record's block_size field, grouped by contig
@@ -69,13 +85,12 @@ template <class F> void parallel_for(int64_t n, int threads, F f) {
     for (auto& th : pool) th.join();
 }
 
-int inflate_all(nc_bam* b, const std::vector<uint8_t>& file, int threads) {
+int inflate_all(nc_bam* b, const uint8_t* file, size_t n, int threads) {
     struct Blk { size_t off, csize; uint32_t isize; size_t out; };
     std::vector<Blk> blocks;
     size_t off = 0, total = 0;
-    const size_t n = file.size();
     while (off + 18 <= n) {
-        const uint8_t* p = file.data() + off;
+        const uint8_t* p = file + off;
         if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return fail(b, "not a BGZF stream (gzip member without the BC extra field)");
         const uint16_t xlen = rd<uint16_t>(p + 10);
         size_t x = 12, xend = 12 + xlen;
@@ -93,7 +108,7 @@ int inflate_all(nc_bam* b, const std::vector<uint8_t>& file, int threads) {
         off += blen;
     }
     if (off != n) return fail(b, "trailing bytes after the last BGZF block");
-    b->data.resize(total);
+    if (!b->data.alloc(total)) return fail(b, "out of memory");
     std::atomic<int> bad{0};
     parallel_for((int64_t)blocks.size(), threads, [&](int64_t i) {
         const Blk& k = blocks[i];
@@ -101,7 +116,7 @@ int inflate_all(nc_bam* b, const std::vector<uint8_t>& file, int threads) {
         z_stream zs;
         memset(&zs, 0, sizeof(zs));
         if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
-        zs.next_in = const_cast<Bytef*>(file.data() + k.off);
+        zs.next_in = const_cast<Bytef*>(file + k.off);
         zs.avail_in = (uInt)k.csize;
         zs.next_out = b->data.data() + k.out;
         zs.avail_out = k.isize;
@@ -169,21 +184,19 @@ int nc_bam_open(const char* path, int threads, nc_bam** out) {
     *out = nullptr;
     nc_bam* b = new nc_bam();
     *out = b;                                   // returned even on failure so that nc_bam_error can explain
-    FILE* f = fopen(path, "rb");
-    if (!f) { b->err = std::string("cannot open ") + path; return NC_IO_EOPEN; }
-    std::vector<uint8_t> file;
-    fseek(f, 0, SEEK_END);
-    const long sz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    file.resize(sz > 0 ? (size_t)sz : 0);
-    const size_t got = file.empty() ? 0 : fread(file.data(), 1, file.size(), f);
-    fclose(f);
-    if (got != file.size()) { b->err = "short read"; return NC_IO_EOPEN; }
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { b->err = std::string("cannot open ") + path; return NC_IO_EOPEN; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); b->err = "cannot stat the file"; return NC_IO_EOPEN; }
+    const size_t fsize = (size_t)st.st_size;
+    void* map = fsize ? mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;     // the compressed bytes are read straight from the page cache
+    close(fd);
+    if (fsize && map == MAP_FAILED) { b->err = "mmap failed"; return NC_IO_EOPEN; }
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    int rc = inflate_all(b, file, threads);
+    int rc = inflate_all(b, (const uint8_t*)map, fsize, threads);
+    if (map) munmap(map, fsize);
     if (rc) return rc;
-    std::vector<uint8_t>().swap(file);
-    const std::vector<uint8_t>& d = b->data;
+    const RawBuf& d = b->data;
     const size_t n = d.size();
     if (n < 12 || memcmp(d.data(), "BAM\1", 4) != 0) return fail(b, "not a BAM file (bad magic)");
     const int32_t l_text = rd<int32_t>(d.data() + 4);
