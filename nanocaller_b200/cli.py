@@ -236,9 +236,8 @@ def run(args):
         if any(c["ploidy"] == "haploid" for c in chunks):
             hap_ind = models.get_indel_model("haploid", args.nanocaller_src)
         lines = []
-        for c in chunks:
-            c = dict(c, sam_path=args.bam)                        # indelCaller.py:327-336 hands every chunk its (phased) BAM
-            lines += indel_caller.call_chunk(params, c, ind, hap_tensors=hap_ind, device=args.device)
+        for grp in _groups(chunks):                               # indelCaller.py:327-336 hands every chunk its (phased) BAM
+            lines += indel_caller.call_chunks(params, [dict(c, sam_path=args.bam) for c in grp], ind, hap_tensors=hap_ind, device=args.device)
         indp = os.path.join(args.output, "%s.indels.vcf.gz" % args.prefix)
         vcfio.write_vcf(indp, "indels", chrom_list, lines, args.sample)
         out.update(indels=indp, n_indel_records=len(lines), indel_seconds=time.time() - t1)

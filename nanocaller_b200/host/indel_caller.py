@@ -92,3 +92,37 @@ def call_chunk(params, chunk, indel_tensors, hap_tensors=None, device=0, impl=1)
     x = np.hstack([x0, x1, x2]).astype(np.float32)                       # indelCaller.py:83
     probs = ctx.indel_model_forward(x, haploid=False, impl=impl)
     return records_from_calls(chunk["chrom"], pos, probs, alleles, phase)
+
+
+def call_chunks(params, chunks, indel_tensors, hap_tensors=None, device=0, impl=1, batch=4096):
+    """All chunks of ONE contig and ploidy in one scan + build on the GPU and batched CNN forwards; the record decision stays
+    per chunk (the reference's `prev` overlap suppression restarts with every chunk, indelCaller.py:88-93).  Same lines as
+    `call_chunk` chunk by chunk."""
+    from . import weights as W
+    if not chunks:
+        return []
+    chrom, ploidy = chunks[0]["chrom"], chunks[0]["ploidy"]
+    assert all(c["chrom"] == chrom and c["ploidy"] == ploidy for c in chunks)
+    ctx = snp_pileups.context(device)
+    rs = sources.resolve(chunks[0]["sam_path"], chrom)
+    bed = sources.bed_intervals(params.get("exclude_bed"), chrom)
+    hap = ploidy == "haploid"
+    res = indel_pileups.candidates_for_chunks(ctx, rs, params, chunks, bed, haploid=hap)
+    xs = []
+    for r in res:
+        if len(r[0]):
+            xs.append(np.asarray(r[1], np.float32) if hap else np.hstack([r[1], r[2], r[3]]).astype(np.float32))   # indelCaller.py:83
+    if not xs:
+        return []
+    ctx.load_indel_weights(W.pack_indel_blob(hap_tensors if hap else indel_tensors), hap)
+    x = np.concatenate(xs)
+    probs = np.concatenate([ctx.indel_model_forward(x[b:b + batch], haploid=hap, impl=impl) for b in range(0, len(x), batch)])
+    out, o = [], 0
+    for r in res:
+        n = len(r[0])
+        if n == 0:
+            continue
+        p = probs[o:o + n]
+        o += n
+        out += haploid_records_from_calls(chrom, r[0], p, r[2]) if hap else records_from_calls(chrom, r[0], p, r[4], r[5])
+    return out
