@@ -755,6 +755,8 @@ constexpr int kTensorWarps = 4;
 constexpr int kRunSlots = 32;
 constexpr int kRunList = 256;
 constexpr int kRunNbr = 1024;
+constexpr int kMaskWords = 4;             // bit-parallel path: run lists of up to 128 reads as 4 x 32-bit masks
+constexpr int kMaskNbr = 256;             // ... and up to 256 staged neighbour sites
 
 struct SiteCols {                       // what a lane knows about its two tensor columns (lane, lane + 32)
     int32_t j0, j1;                     // neighbour-list index (global numbering) or -1
@@ -909,6 +911,26 @@ __device__ __forceinline__ void tensor_site_generic(const TensorArgs& a, int64_t
     site_finish(a, orow, c, v, lane, buf, sc, acc0, acc1, fwd, rev, dp, sampled);
 }
 
+// Warp-cooperative search in a sorted global array: 32 probes per round, so ~log32(n) dependent loads instead of log2(n).
+// Returns the first index with a[i] >= key (upper = false) or a[i] > key (upper = true); identical on all lanes.
+__device__ __forceinline__ int64_t warp_bound_i32(const int32_t* __restrict__ a, int64_t n, int32_t key, bool upper, int lane) {
+    const uint32_t full = 0xffffffffu;
+    int64_t lo = 0, hi = n;                                            // the answer lies in [lo, hi]
+    while (hi - lo > 32) {
+        const int64_t step = (hi - lo + 31) >> 5;
+        const int64_t idx = lo + (int64_t)lane * step;
+        bool before = false;
+        if (idx < hi) { const int32_t x = __ldg(a + idx); before = upper ? x <= key : x < key; }
+        const int k = __popc(__ballot_sync(full, before));             // probes lo, lo+step, ... that lie before the answer
+        if (k < 32) hi = min(hi, lo + (int64_t)k * step);
+        if (k > 0) lo = lo + (int64_t)(k - 1) * step + 1;
+    }
+    const int64_t idx = lo + lane;
+    bool before = false;
+    if (idx < hi) { const int32_t x = __ldg(a + idx); before = upper ? x <= key : x < key; }
+    return lo + __popc(__ballot_sync(full, before));
+}
+
 struct RunList {                        // admitted reads overlapping the run, BAM order (shared memory)
     int32_t rp[kRunList], re[kRunList], nf[kRunList], nl[kRunList];
     int64_t rowoff[kRunList], noff[kRunList];
@@ -974,10 +996,105 @@ __device__ __forceinline__ void tensor_site_run(const TensorArgs& a, int64_t oro
     site_finish(a, orow, c, v, lane, buf, sc, acc0, acc1, fwd, rev, dp, sampled);
 }
 
+// Bit-parallel per-site path.  With the run's reads numbered by their position in the compact list, "which reads have code b
+// at neighbour site j" is a bit mask M[j][b] (built once per run, a ballot per code with lanes as reads), "which sampled reads
+// have code i at the candidate" is a mask MS[i] (four ballots per site), and every tensor entry is
+//     mat[i][column of j][b] = popcount(MS[i] & M[j][b])                      (generate_SNP_pileups.py:221-247)
+// — 16 AND + POPC per column and mask word instead of a dependent lookup per (read, column).
+template <int W>
+__device__ __forceinline__ void tensor_site_masks(const TensorArgs& a, int64_t orow, int c, int32_t v, int lane, int16_t* buf,
+                                                  const RunList& L, int cnt, const int32_t* nbr, int32_t n_nbr, int32_t nb_base,
+                                                  const uint32_t* __restrict__ M) {
+    const uint32_t full = 0xffffffffu;
+    const int32_t p = v - 1;
+    const SiteCols sc = site_columns(a, nbr, n_nbr, nb_base, c, v, lane);
+    uint32_t cw[W], rv[W], ms[4][W];
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        cw[w] = 0; rv[w] = 0; ms[0][w] = ms[1][w] = ms[2][w] = ms[3][w] = 0;
+        if (32 * w < cnt) {                                            // warp-uniform
+            const int e = 32 * w + lane;
+            bool cover = false, rev = false;
+            uint32_t code = 4;
+            if (e < cnt) {
+                const int32_t rp = L.rp[e];
+                if (rp <= p && p < L.re[e]) {
+                    cover = true;
+                    rev = L.rev[e] != 0;
+                    code = (__ldg(a.rows + L.rowoff[e] + ((p >> 3) - (rp >> 3))) >> (4 * (p & 7))) & 15u;
+                }
+            }
+            cw[w] = __ballot_sync(full, cover);
+            rv[w] = __ballot_sync(full, cover && rev);
+            ms[0][w] = __ballot_sync(full, code == 0); ms[1][w] = __ballot_sync(full, code == 1);
+            ms[2][w] = __ballot_sync(full, code == 2); ms[3][w] = __ballot_sync(full, code == 3);
+        }
+    }
+    // depth, strand depths over ALL covering reads (:210-213), then the sample = first maxcov covering reads in BAM order (:215-216)
+    int32_t dp = 0;
+    uint64_t fwd = 0, rev = 0;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        dp += __popc(cw[w]);
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            fwd += (uint64_t)__popc(ms[b][w] & ~rv[w]) << (16 * b);
+            rev += (uint64_t)__popc(ms[b][w] & rv[w]) << (16 * b);
+        }
+    }
+    if (lane != 0) { fwd = 0; rev = 0; }                               // site_finish sums the lanes
+    int32_t sampled = dp;
+    if (dp > a.maxcov) {
+        sampled = a.maxcov;
+        int room = a.maxcov;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            const uint32_t keep = take_first(cw[w], room);
+            room -= __popc(keep);
+#pragma unroll
+            for (int i = 0; i < 4; i++) ms[i][w] &= keep;
+        }
+    }
+    // lanes as columns
+    uint64_t acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int32_t j = half ? sc.j1 : sc.j0;
+        uint64_t* acc = half ? acc1 : acc0;
+        if (half == 0 && lane == 20) {                                 // the candidate column: a read's column code is its candidate code
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int n = 0;
+#pragma unroll
+                for (int w = 0; w < W; w++) n += __popc(ms[i][w]);
+                acc[i] = (uint64_t)n << (16 * i);
+            }
+        } else if (j >= 0) {
+            const uint32_t* mj = M + (size_t)(j - nb_base) * 4 * kMaskWords;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                uint32_t m[W];
+                if (W == 1) m[0] = mj[b * kMaskWords];
+                else if (W == 2) { const uint2 t2 = *reinterpret_cast<const uint2*>(mj + b * kMaskWords); m[0] = t2.x; m[W - 1] = t2.y; }
+                else { const uint4 t4 = *reinterpret_cast<const uint4*>(mj + b * kMaskWords); m[0] = t4.x; m[1] = t4.y; m[2] = t4.z; if (W == 4) m[W - 1] = t4.w; }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    int n = 0;
+#pragma unroll
+                    for (int w = 0; w < W; w++) n += __popc(ms[i][w] & m[w]);
+                    acc[i] += (uint64_t)n << (16 * b);
+                }
+            }
+        }
+    }
+    site_finish(a, orow, c, v, lane, buf, sc, acc0, acc1, fwd, rev, dp, sampled);
+}
+
 __global__ void __launch_bounds__(kTensorWarps * 32) tensor_kernel(const TensorArgs a) {
     __shared__ __align__(16) int16_t s_out[kTensorWarps][NC_SNP_SITE_STRIDE];
     __shared__ RunList s_list;
     __shared__ int32_t s_nbr[kRunNbr];
+    __shared__ __align__(16) uint32_t s_mask[kMaskNbr * 4 * kMaskWords];     // M[neighbour][code][word]
     __shared__ int32_t s_v[kRunSlots], s_c[kRunSlots];
     __shared__ int32_t s_wcnt[kTensorWarps];
     __shared__ int64_t s_ilo, s_ihi;
@@ -1004,19 +1121,20 @@ __global__ void __launch_bounds__(kTensorWarps * 32) tensor_kernel(const TensorA
             if (lane == 0) {
                 s_pmin = lo; s_pmax = hi;
                 s_fast = ((int64_t)hi - lo <= 65536 && a.maxcov <= 255) ? 1 : 0;
-                s_ihi = upper_bound_i32_64(a.pos, a.n_reads, hi);
-                int64_t l = 0, h = s_ihi;                             // first read whose prefix-max end exceeds the run's first position
-                while (l < h) { const int64_t mid = (l + h) >> 1; if (__ldg(a.pmaxend + mid) <= lo) l = mid + 1; else h = mid; }
-                s_ilo = l;
-            }
-            if (lane == 1) {                                           // neighbours within the search radius of the run
-                const int32_t R = c_bins[a.seq][c_nbins[a.seq] - 1].b + 1;
-                s_nb_lo = lower_bound_i32(a.nbr_pos, a.n_nbr, (int32_t)max((int64_t)lo + 1 - R, (int64_t)INT32_MIN + 1));
-                s_nb_hi = lower_bound_i32(a.nbr_pos, a.n_nbr, (int32_t)min((int64_t)hi + 2 + R, (int64_t)INT32_MAX));
             }
         }
         __syncthreads();
         const int32_t pmin = s_pmin, pmax = s_pmax;
+        {
+            // ---- four searches, one per warp: the BAM-index window of reads that can overlap [pmin, pmax] (first read whose
+            //      prefix-max end exceeds pmin .. first read starting after pmax) and the neighbours within the search radius
+            const int32_t R = c_bins[a.seq][c_nbins[a.seq] - 1].b + 1;
+            if (wib == 0) { const int64_t r = warp_bound_i32(a.pos, a.n_reads, pmax, true, lane); if (lane == 0) s_ihi = r; }
+            else if (wib == 1) { const int64_t r = warp_bound_i32(a.pmaxend, a.n_reads, pmin, true, lane); if (lane == 0) s_ilo = r; }
+            else if (wib == 2) { const int64_t r = warp_bound_i32(a.nbr_pos, a.n_nbr, (int32_t)max((int64_t)pmin + 1 - R, (int64_t)INT32_MIN + 1), false, lane); if (lane == 0) s_nb_lo = (int32_t)r; }
+            else { const int64_t r = warp_bound_i32(a.nbr_pos, a.n_nbr, (int32_t)min((int64_t)pmax + 2 + R, (int64_t)INT32_MAX), false, lane); if (lane == 0) s_nb_hi = (int32_t)r; }
+        }
+        __syncthreads();
         int cnt = 0;
         if (s_fast) {
             // ---- ordered compaction of the admitted reads overlapping [pmin, pmax]
@@ -1049,6 +1167,27 @@ __global__ void __launch_bounds__(kTensorWarps * 32) tensor_kernel(const TensorA
         const int32_t nb_lo = s_nb_lo, nb_n = s_nb_hi - s_nb_lo;
         const bool nbr_sm = nb_n <= kRunNbr;
         if (fast && nbr_sm) for (int i = tid; i < nb_n; i += kTensorWarps * 32) s_nbr[i] = __ldg(a.nbr_pos + nb_lo + i);
+        const bool masks = fast && cnt <= 32 * kMaskWords && nb_n <= kMaskNbr;
+        if (masks) {
+            // ---- M[j][b]: lanes as reads, one ballot per code; a warp takes a contiguous quarter of the neighbours
+            const int per = (nb_n + kTensorWarps - 1) / kTensorWarps;
+            const int j_end = min(nb_n, (wib + 1) * per);
+            for (int jr = wib * per; jr < j_end; jr++) {
+#pragma unroll
+                for (int w = 0; w < kMaskWords; w++) {
+                    if (32 * w >= cnt) break;                          // warp-uniform: words past the list are never looked at
+                    uint32_t code = 15;
+                    const int e = 32 * w + lane;
+                    if (e < cnt) {
+                        const uint32_t rel = (uint32_t)(nb_lo + jr - s_list.nf[e]);
+                        if (rel < (uint32_t)s_list.nl[e]) { const uint32_t by = __ldg(a.nrows + s_list.noff[e] + (rel >> 1)); code = (rel & 1u) ? (by >> 4) : (by & 15u); }
+                    }
+                    const uint32_t m0 = __ballot_sync(full, code == 0), m1 = __ballot_sync(full, code == 1);
+                    const uint32_t m2 = __ballot_sync(full, code == 2), m3 = __ballot_sync(full, code == 3);
+                    if (lane < 4) s_mask[(jr * 4 + lane) * kMaskWords + w] = lane == 0 ? m0 : lane == 1 ? m1 : lane == 2 ? m2 : m3;
+                }
+            }
+        }
         __syncthreads();
         // ---- a warp per site
         for (int k = wib; k < nslots; k += kTensorWarps) {
@@ -1061,6 +1200,14 @@ __global__ void __launch_bounds__(kTensorWarps * 32) tensor_kernel(const TensorA
             const int c = s_c[k];
             const int32_t v = s_v[k];
             if (!fast) tensor_site_generic(a, orow, c, v, lane, buf);
+            else if (masks) {
+                switch ((cnt + 31) >> 5) {
+                    case 0: case 1: tensor_site_masks<1>(a, orow, c, v, lane, buf, s_list, cnt, s_nbr, nb_n, nb_lo, s_mask); break;
+                    case 2: tensor_site_masks<2>(a, orow, c, v, lane, buf, s_list, cnt, s_nbr, nb_n, nb_lo, s_mask); break;
+                    case 3: tensor_site_masks<3>(a, orow, c, v, lane, buf, s_list, cnt, s_nbr, nb_n, nb_lo, s_mask); break;
+                    default: tensor_site_masks<4>(a, orow, c, v, lane, buf, s_list, cnt, s_nbr, nb_n, nb_lo, s_mask); break;
+                }
+            }
             else if (nbr_sm) tensor_site_run(a, orow, c, v, lane, buf, s_list, cnt, s_nbr, nb_n, nb_lo);
             else tensor_site_run(a, orow, c, v, lane, buf, s_list, cnt, a.nbr_pos + nb_lo, nb_n, nb_lo);
         }

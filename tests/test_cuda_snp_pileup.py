@@ -88,6 +88,30 @@ def test_matches_oracle_on_fresh_world_with_downsampling():
     _compare(got, w, "fresh200x")
 
 
+@pytest.mark.parametrize("maxcov,coverage,seq", [(20, 30.0, "ont"), (160, 30.0, "ul_ont"), (12, 90.0, "pacbio")])
+def test_matches_oracle_on_fresh_world_small_maxcov(maxcov, coverage, seq):
+    """Down-sampling inside the bit-parallel path (run lists of <= 128 reads, maxcov below the depth) and other sequencing modes."""
+    from nanocaller_b200.host import snp_pileups
+    from nanocaller_b200.synth import make_world
+    from oracle import snp_oracle as O
+    from tests.golden.cases import BASE_DCT
+    rs = make_world(chrom="chrQ", preset="ont", contig_len=50_000, seed=77, coverage=coverage).reads
+    dct = dict(BASE_DCT, maxcov=maxcov, seq=seq)
+    chunks = [{"chrom": "chrQ", "start": 1, "end": 30_000, "ploidy": "diploid"}, {"chrom": "chrQ", "start": 30_000, "end": 50_000, "ploidy": "diploid"}]
+    ctx = _ctx()
+    snp_pileups._staged.clear()
+    snp_pileups.scan_chunks(ctx, rs, dct, chunks, "diploid")
+    mat, meta, depth, count = ctx.snp_fetch()
+    per = snp_pileups.unpack(mat, meta, depth, count, len(chunks))
+    keys = ("pos", "ref", "mat", "dp", "freq", "depth", "fwd", "rev")
+    for ci, ch in enumerate(chunks):
+        w = dict(zip(keys, O.get_snp_testing_candidates(rs, dct, ch)))
+        assert len(w["pos"]) > 50
+        _compare(per[ci], w, ("fresh", maxcov, seq, ci))
+    if maxcov < coverage:
+        assert meta["sample_depth"].max() == maxcov and meta["dp"].max() > maxcov
+
+
 def test_empty_inputs():
     from nanocaller_b200.host import capi, snp_pileups
     from nanocaller_b200.host.readset import ReadSet
