@@ -756,7 +756,7 @@ constexpr int kRunSlots = 32;
 constexpr int kRunList = 256;
 constexpr int kRunNbr = 1024;
 constexpr int kMaskWords = 4;             // bit-parallel path: run lists of up to 128 reads as 4 x 32-bit masks
-constexpr int kMaskNbr = 256;             // ... and up to 256 staged neighbour sites
+constexpr int kMaskNbr = 192;             // ... and up to 256 staged neighbour sites
 
 struct SiteCols {                       // what a lane knows about its two tensor columns (lane, lane + 32)
     int32_t j0, j1;                     // neighbour-list index (global numbering) or -1
@@ -1090,7 +1090,7 @@ __device__ __forceinline__ void tensor_site_masks(const TensorArgs& a, int64_t o
     site_finish(a, orow, c, v, lane, buf, sc, acc0, acc1, fwd, rev, dp, sampled);
 }
 
-__global__ void __launch_bounds__(kTensorWarps * 32) tensor_kernel(const TensorArgs a) {
+__global__ void __launch_bounds__(kTensorWarps * 32, 6) tensor_kernel(const TensorArgs a) {
     __shared__ __align__(16) int16_t s_out[kTensorWarps][NC_SNP_SITE_STRIDE];
     __shared__ RunList s_list;
     __shared__ int32_t s_nbr[kRunNbr];
