@@ -39,13 +39,9 @@ __global__ void __launch_bounds__(kTileThreads) indel_depth_kernel(const DepthAr
     const int32_t P0 = a.lo_al + kTilePos * (int32_t)blockIdx.x;
     const int32_t P1 = min(P0 + kTilePos, a.hi);
     for (int i = tid; i < 3 * kTilePos; i += kTileThreads) (&s_acc[0][0])[i] = 0;
-    if (tid == 0) {
-        s_cnt = 0;
-        s_ihi = upper_bound_i32_64(a.pos, a.n_reads, P1 - 1);
-        int64_t lo = 0, hi = a.n_reads;
-        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (__ldg(a.pmaxend + mid) <= P0) lo = mid + 1; else hi = mid; }
-        s_ilo = lo;
-    }
+    if (tid == 0) s_cnt = 0;
+    if (w == 0) { const int64_t r = warp_bound_i32(a.pos, a.n_reads, P1 - 1, true, lane); if (lane == 0) s_ihi = r; }
+    if (w == 1) { const int64_t r = warp_bound_i32(a.pmaxend, a.n_reads, P0, true, lane); if (lane == 0) s_ilo = r; }
     __syncthreads();
     const int64_t ilo = s_ilo, ihi = s_ihi;
     const int32_t Wbase = (P0 >> 3) + 32 * w, myw = Wbase + lane;

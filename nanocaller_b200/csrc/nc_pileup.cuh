@@ -70,6 +70,26 @@ __device__ __forceinline__ int64_t block_excl_scan64(int64_t v, int64_t* sm, int
     return r;
 }
 
+// Warp-cooperative search in a sorted global array: 32 probes per round, so ~log32(n) dependent loads instead of log2(n).
+// Returns the first index with a[i] >= key (upper = false) or a[i] > key (upper = true); identical on all lanes.
+__device__ __forceinline__ int64_t warp_bound_i32(const int32_t* __restrict__ a, int64_t n, int32_t key, bool upper, int lane) {
+    const uint32_t full = 0xffffffffu;
+    int64_t lo = 0, hi = n;                                            // the answer lies in [lo, hi]
+    while (hi - lo > 32) {
+        const int64_t step = (hi - lo + 31) >> 5;
+        const int64_t idx = lo + (int64_t)lane * step;
+        bool before = false;
+        if (idx < hi) { const int32_t x = __ldg(a + idx); before = upper ? x <= key : x < key; }
+        const int k = __popc(__ballot_sync(full, before));             // probes lo, lo+step, ... that lie before the answer
+        if (k < 32) hi = min(hi, lo + (int64_t)k * step);
+        if (k > 0) lo = lo + (int64_t)(k - 1) * step + 1;
+    }
+    const int64_t idx = lo + lane;
+    bool before = false;
+    if (idx < hi) { const int32_t x = __ldg(a + idx); before = upper ? x <= key : x < key; }
+    return lo + __popc(__ballot_sync(full, before));
+}
+
 // ------------------------------------------------------------------------------------------------
 // exclusive scan int32 -> int64 (out has n+1 entries, out[n] = total); three launches
 // ------------------------------------------------------------------------------------------------
@@ -415,13 +435,11 @@ __global__ void __launch_bounds__(kTileThreads) scan_kernel(const ScanArgs a) {
     const int32_t P0 = a.lo_al + kTilePos * (int32_t)blockIdx.x;
     const int32_t P1 = min(P0 + kTilePos, a.hi);
     for (int i = tid; i < 9 * kTilePos; i += kTileThreads) (&s_acc[0][0])[i] = 0;
-    if (tid == 0) {
-        s_cnt = 0; s_nbr = 0; s_cand = 0;
-        s_ihi = upper_bound_i32_64(a.pos, a.n_reads, P1 - 1);
-        int64_t lo = 0, hi = a.n_reads;                       // first read index whose prefix-max end exceeds P0
-        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (__ldg(a.pmaxend + mid) <= P0) lo = mid + 1; else hi = mid; }
-        s_ilo = lo;
-    }
+    if (tid == 0) { s_cnt = 0; s_nbr = 0; s_cand = 0; }
+    // BAM-index window of the tile, one warp-cooperative search each (32 probes per dependent load instead of 1):
+    // first read starting after the tile .. first read whose prefix-max end exceeds P0
+    if (w == 0) { const int64_t r = warp_bound_i32(a.pos, a.n_reads, P1 - 1, true, lane); if (lane == 0) s_ihi = r; }
+    if (w == 1) { const int64_t r = warp_bound_i32(a.pmaxend, a.n_reads, P0, true, lane); if (lane == 0) s_ilo = r; }
     __syncthreads();
     const int64_t ilo = s_ilo, ihi = s_ihi;
     const int32_t Wbase = (P0 >> 3) + 32 * w;                 // absolute word index of lane 0
@@ -909,26 +927,6 @@ __device__ __forceinline__ void tensor_site_generic(const TensorArgs& a, int64_t
         }
     }
     site_finish(a, orow, c, v, lane, buf, sc, acc0, acc1, fwd, rev, dp, sampled);
-}
-
-// Warp-cooperative search in a sorted global array: 32 probes per round, so ~log32(n) dependent loads instead of log2(n).
-// Returns the first index with a[i] >= key (upper = false) or a[i] > key (upper = true); identical on all lanes.
-__device__ __forceinline__ int64_t warp_bound_i32(const int32_t* __restrict__ a, int64_t n, int32_t key, bool upper, int lane) {
-    const uint32_t full = 0xffffffffu;
-    int64_t lo = 0, hi = n;                                            // the answer lies in [lo, hi]
-    while (hi - lo > 32) {
-        const int64_t step = (hi - lo + 31) >> 5;
-        const int64_t idx = lo + (int64_t)lane * step;
-        bool before = false;
-        if (idx < hi) { const int32_t x = __ldg(a + idx); before = upper ? x <= key : x < key; }
-        const int k = __popc(__ballot_sync(full, before));             // probes lo, lo+step, ... that lie before the answer
-        if (k < 32) hi = min(hi, lo + (int64_t)k * step);
-        if (k > 0) lo = lo + (int64_t)(k - 1) * step + 1;
-    }
-    const int64_t idx = lo + lane;
-    bool before = false;
-    if (idx < hi) { const int32_t x = __ldg(a + idx); before = upper ? x <= key : x < key; }
-    return lo + __popc(__ballot_sync(full, before));
 }
 
 struct RunList {                        // admitted reads overlapping the run, BAM order (shared memory)
