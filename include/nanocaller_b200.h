@@ -230,6 +230,15 @@ int nc_indel_fetch(nc_ctx* ctx, NcIndelSiteMeta* meta, float* tensors, uint8_t* 
 int nc_nw_trace(const uint8_t* query, int32_t n, const uint8_t* ref, int32_t m, int32_t gap_open, int32_t gap_extend,
                 int32_t match, int32_t mismatch, uint32_t* cigar_out, int32_t cap);
 
+/* allele_prediction(alt, ref_seq, max_range) (generate_indel_pileups.py:77-127) for a batch of consensus / reference-window pairs on
+ * `threads` host threads (<= 0: all cores): nc_nw_trace, then the reference's CIGAR walk.  Item i reads alt_len[i] codes at
+ * alt_codes + alt_off[i] and ref_len[i] codes at ref_codes + ref_off[i]; it returns the lengths of the allele strings
+ * ref_seq[:ref_out_len[i]] / alt[:alt_out_len[i]], or -1 / -1 where the reference returns (None, None). */
+int nc_allele_predict_batch(int64_t n_items, const uint8_t* alt_codes, const int64_t* alt_off, const int32_t* alt_len,
+                            const uint8_t* ref_codes, const int64_t* ref_off, const int32_t* ref_len, const int32_t* max_range,
+                            int32_t gap_open, int32_t gap_extend, int32_t match, int32_t mismatch, int32_t threads,
+                            int32_t* ref_out_len, int32_t* alt_out_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,8 @@
 // libnanocaller_b200.so — C-ABI (include/nanocaller_b200.h) over the sm_100a kernels.
 // One context = one device + one stream; every entry point returns 0 or a negative NC_E* code.
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdarg>
 #include <utility>
 
@@ -1016,6 +1018,67 @@ int nc_nw_trace(const uint8_t* q, int32_t n, const uint8_t* r, int32_t m, int32_
         else { if (nw >= cap) return NC_EOVERFLOW; out[nw++] = (1u << 4) | ops[k]; }
     }
     return nw;
+}
+
+// allele_prediction (generate_indel_pileups.py:77-127) for a batch of (consensus, reference window) pairs on host threads:
+// alignment by nc_nw_trace, then the reference's walk over the CIGAR, control flow kept line for line (including its
+// `sum(ref_cnt) - cnt` after a trailing insertion).  Outputs the prefix lengths of the reference / alternative allele
+// strings, or -1 / -1 where the reference returns (None, None).
+static void allele_predict_one(const uint8_t* alt, int32_t n, const uint8_t* ref, int32_t m, int32_t max_range, int32_t go, int32_t ge,
+                               int32_t match, int32_t mismatch, std::vector<uint32_t>& cig, int32_t* ref_out, int32_t* alt_out) {
+    *ref_out = -1; *alt_out = -1;
+    cig.resize((size_t)n + m + 2);
+    const int nw = nc_nw_trace(alt, n, ref, m, go, ge, match, mismatch, cig.data(), (int32_t)cig.size());
+    if (nw <= 0) return;
+    bool indel = false, mis_before = false;
+    int64_t ref_cnt[10] = {0}, alt_cnt[10] = {0}, mis_after[2] = {0, 0};
+    auto sum10 = [](const int64_t* a) { int64_t t = 0; for (int i = 0; i < 10; i++) t += a[i]; return t; };
+    int op = 0; int64_t cnt = 0;
+    for (int k = 0; k < nw; k++) {
+        op = (int)(cig[k] & 15u); cnt = (int64_t)(cig[k] >> 4);
+        if (op == 8 || op == 7) {
+            ref_cnt[op] += cnt; alt_cnt[op] += cnt;
+            if (indel) mis_after[op - 7] += cnt; else mis_before = true;
+        }
+        if (op == 1) { alt_cnt[op] += cnt; mis_after[0] = mis_after[1] = 0; indel = true; }
+        if (op == 2) { ref_cnt[op] += cnt; mis_after[0] = mis_after[1] = 0; indel = true; }
+        if (!indel && sum10(ref_cnt) >= (int64_t)max_range + 10) {
+            if (ref_cnt[8]) {
+                const int64_t out_len = op == 8 ? sum10(ref_cnt) : sum10(ref_cnt) - cnt;
+                *ref_out = (int32_t)out_len; *alt_out = (int32_t)out_len;
+            }
+            return;
+        }
+        if (indel && mis_after[0] + mis_after[1] > 20) break;
+    }
+    int64_t r = op == 8 ? sum10(ref_cnt) : sum10(ref_cnt) - cnt;
+    int64_t a = op == 8 ? sum10(alt_cnt) : sum10(alt_cnt) - cnt;
+    if (!mis_before) { r += 1; a += 1; }
+    *ref_out = (int32_t)r; *alt_out = (int32_t)a;
+}
+
+int nc_allele_predict_batch(int64_t n_items, const uint8_t* alt_codes, const int64_t* alt_off, const int32_t* alt_len, const uint8_t* ref_codes,
+                            const int64_t* ref_off, const int32_t* ref_len, const int32_t* max_range, int32_t go, int32_t ge, int32_t match,
+                            int32_t mismatch, int32_t threads, int32_t* ref_out_len, int32_t* alt_out_len) {
+    if (n_items < 0 || (n_items > 0 && (!alt_codes || !alt_off || !alt_len || !ref_codes || !ref_off || !ref_len || !max_range || !ref_out_len || !alt_out_len)))
+        return NC_EINVAL;
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n_items));
+    std::atomic<int64_t> next{0};
+    auto work = [&]() {
+        std::vector<uint32_t> cig;
+        for (;;) {
+            const int64_t i = next.fetch_add(1);
+            if (i >= n_items) return;
+            allele_predict_one(alt_codes + alt_off[i], alt_len[i], ref_codes + ref_off[i], ref_len[i], max_range[i], go, ge, match, mismatch, cig,
+                               ref_out_len + i, alt_out_len + i);
+        }
+    };
+    if (threads == 1) { work(); return NC_OK; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) pool.emplace_back(work);
+    for (auto& th : pool) th.join();
+    return NC_OK;
 }
 
 // ---- development probes (not part of the public header) -------------------------------------------------

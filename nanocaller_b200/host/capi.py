@@ -17,7 +17,7 @@ EXPORTS = ["nc_abi_version", "nc_create", "nc_destroy", "nc_last_error", "nc_syn
            "nc_device_sm_count", "nc_event_record", "nc_event_elapsed_ms", "nc_invalidate_decode", "nc_stage_reads", "nc_decode_reads", "nc_snp_scan", "nc_snp_fetch",
            "nc_load_snp_weights", "nc_snp_forward", "nc_snp_fetch_probs", "nc_snp_model_forward", "nc_snp_device_buffers",
            "nc_load_indel_weights", "nc_indel_model_forward", "nc_stage_tags", "nc_indel_scan", "nc_indel_fetch_variants",
-           "nc_indel_build", "nc_indel_fetch", "nc_nw_trace"]
+           "nc_indel_build", "nc_indel_fetch", "nc_nw_trace", "nc_allele_predict_batch"]
 
 
 class NcSnpParams(ctypes.Structure):
@@ -133,6 +133,26 @@ def nw_trace(query_codes, ref_codes, gap_open=9, gap_extend=1, match=20, mismatc
     if n < 0:
         raise NcError(n, "nc_nw_trace failed")
     return [(int(w & 15), int(w >> 4)) for w in out[:n]]
+
+
+def allele_predict_batch(alt_flat, alt_off, alt_len, ref_flat, ref_off, ref_len, max_range, threads=0,
+                         gap_open=9, gap_extend=1, match=20, mismatch=-10):
+    """Batch of allele_prediction calls (generate_indel_pileups.py:77-127) on host threads -> (ref_out_len, alt_out_len) int32
+    arrays, -1 where the reference returns (None, None)."""
+    lib = load_library()
+    n = len(alt_len)
+    alt_flat = np.ascontiguousarray(alt_flat, np.uint8); ref_flat = np.ascontiguousarray(ref_flat, np.uint8)
+    alt_off = np.ascontiguousarray(alt_off, np.int64); ref_off = np.ascontiguousarray(ref_off, np.int64)
+    alt_len = np.ascontiguousarray(alt_len, np.int32); ref_len = np.ascontiguousarray(ref_len, np.int32)
+    max_range = np.ascontiguousarray(max_range, np.int32)
+    ro, ao = np.empty(n, np.int32), np.empty(n, np.int32)
+    if n == 0:
+        return ro, ao
+    rc = lib.nc_allele_predict_batch(n, _p(alt_flat), _p(alt_off), _p(alt_len), _p(ref_flat), _p(ref_off), _p(ref_len), _p(max_range),
+                                     gap_open, gap_extend, match, mismatch, int(threads), _p(ro), _p(ao))
+    if rc != NC_OK:
+        raise NcError(rc, "nc_allele_predict_batch failed")
+    return ro, ao
 
 
 class Context:

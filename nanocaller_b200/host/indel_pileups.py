@@ -88,9 +88,42 @@ def candidates_for_chunks(ctx, rs, dct, chunks, bed=None, haploid=False):
     sites = order_variants(variants)
     meta, tensors, cns = ctx.indel_build(P, ch, sites)
     max_range = {0: max(10, int(dct["win_size"])), 1: 10}
+    # ---- allele prediction for every kept site and read group in one batched, multithreaded library call
+    okmask = meta["ok"][:, 2] > 0 if haploid else meta["ok"].min(1) > 0
+    kept = np.nonzero(okmask)[0]
+    groups = (2,) if haploid else (0, 1, 2)
+    pred = {}
+    if len(kept):
+        cap = cns.shape[2]
+        ref_rows, ref_off, ref_len = [], [], []
+        off = 0
+        for s in kept:
+            p0 = int(meta["pos"][s]) - 1
+            m = int(meta["ref_len"][s])
+            ref_rows.append(rs.ref[p0:p0 + m])
+            ref_off.append(off); ref_len.append(m)
+            off += m
+        ref_bytes = np.concatenate(ref_rows)
+        ref_flat = _REF_CODE[ref_bytes]
+        it_site = np.repeat(kept, len(groups))
+        it_grp = np.tile(np.asarray(groups), len(kept))
+        alt_off = (it_site.astype(np.int64) * cns.shape[1] + it_grp) * cap
+        alt_len = meta["cns_len"][it_site, it_grp].astype(np.int32)
+        r_off = np.repeat(np.asarray(ref_off, np.int64), len(groups))
+        r_len = np.repeat(np.asarray(ref_len, np.int32), len(groups))
+        mr = np.array([max_range[int(t)] for t in meta["type"][it_site]], np.int32)
+        ro, ao = capi.allele_predict_batch(cns.reshape(-1), alt_off, alt_len, ref_flat, r_off, r_len, mr)
+        ref_txt = ref_bytes.tobytes().decode()
+        for k in range(len(it_site)):
+            s, g = int(it_site[k]), int(it_grp[k])
+            if ro[k] < 0:
+                pred[(s, g)] = (None, None)
+            else:
+                b0 = int(r_off[k])
+                alt = BASES[cns[s, g, :alt_len[k]]].tobytes().decode()
+                pred[(s, g)] = (ref_txt[b0:b0 + min(int(ro[k]), int(r_len[k]))], alt[:int(ao[k])])
     res = []
     for ci in range(len(chunks)):
-        okmask = meta["ok"][:, 2] > 0 if haploid else meta["ok"].min(1) > 0
         sel = np.nonzero((meta["chunk"] == ci) & okmask)[0]
         if len(sel) == 0:
             res.append(([], [], []) if haploid else ([], [], [], [], [], []))       # generate_indel_pileups.py:363-364
@@ -98,16 +131,7 @@ def candidates_for_chunks(ctx, rs, dct, chunks, bed=None, haploid=False):
         pos = [int(p) for p in meta["pos"][sel]]
         alleles, phase = [], []
         for s in sel:
-            p0 = int(meta["pos"][s]) - 1
-            m = int(meta["ref_len"][s])
-            ref_b = rs.ref[p0:p0 + m]
-            ref_seq = ref_b.tobytes().decode()
-            rc = _REF_CODE[ref_b]
-            trip = []
-            for g in ((2,) if haploid else range(3)):
-                codes = cns[s, g, :meta["cns_len"][s, g]]
-                alt = BASES[codes].tobytes().decode()
-                trip.append(allele_prediction(alt, ref_seq, max_range[int(meta["type"][s])], codes, rc))
+            trip = [pred[(int(s), g)] for g in groups]
             alleles.append(trip[0] if haploid else trip)
             phase.append(int(meta["phase"][s]))
         x = tensors[sel].astype(np.float64)                                  # float32 values in a float64 container (:69-71)

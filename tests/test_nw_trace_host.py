@@ -41,3 +41,27 @@ def test_allele_prediction_matches_oracle():
             continue
         for mr in (10, 40):
             assert indel_pileups.allele_prediction(q, ref, mr) == indel_oracle.allele_prediction(q, ref, mr)
+
+
+def test_batched_allele_prediction_matches_the_python_walk():
+    """nc_allele_predict_batch (C++, threaded) vs host allele_prediction (the reference's control flow in Python), item by item."""
+    rng = np.random.RandomState(9)
+    pairs = []
+    while len(pairs) < 300:
+        q, ref = _rand_pair(rng)
+        if q:
+            pairs.append((q, ref, int(rng.choice([10, 40, 50]))))
+    pairs.append(("ACGTACGTAC", "ACGTACGTAC", 0))          # identical: no indel within range, no mismatch -> (None, None)
+    pairs.append(("ACGTTCGTACGGA", "ACGTACGTACGGA", 0))    # mismatch only
+    alt = [star_msa.encode(q) for q, _, _ in pairs]
+    ref = [star_msa.encode(r) for _, r, _ in pairs]
+    alt_off = np.concatenate([[0], np.cumsum([len(a) for a in alt])[:-1]])
+    ref_off = np.concatenate([[0], np.cumsum([len(r) for r in ref])[:-1]])
+    for threads in (1, 4):
+        ro, ao = capi.allele_predict_batch(np.concatenate(alt), alt_off, [len(a) for a in alt], np.concatenate(ref), ref_off,
+                                           [len(r) for r in ref], [m for _, _, m in pairs], threads=threads)
+        for k, (q, r, m) in enumerate(pairs):
+            want = indel_pileups.allele_prediction(q, r, m)
+            got = (None, None) if ro[k] < 0 else (r[:ro[k]], q[:ao[k]])
+            assert got == want, (q, r, m, got, want)
+    assert capi.allele_predict_batch(np.zeros(0, np.uint8), [], [], np.zeros(0, np.uint8), [], [], [])[0].size == 0
