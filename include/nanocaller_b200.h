@@ -239,6 +239,15 @@ int nc_allele_predict_batch(int64_t n_items, const uint8_t* alt_codes, const int
                             int32_t gap_open, int32_t gap_extend, int32_t match, int32_t mismatch, int32_t threads,
                             int32_t* ref_out_len, int32_t* alt_out_len);
 
+/* SNP genotype decision + VCF record text for n call records (snpCaller.py:113-163; haploid: :183-198) on `threads` host threads.
+ * probs4 = P(A), P(G), P(T), P(C) per site (the order of nc_snp_forward), alt_cnt / dp = the FQ value (generate_SNP_pileups.py:166),
+ * fwd4 / rev4 = strand depths by base code.  Writes the records back to back into `out` (capacity cap), line_off[n + 1] = start of
+ * every record (a candidate the reference writes no record for has an empty range), is_pass[n] = FILTER is PASS.
+ * Returns the number of bytes written, NC_EOVERFLOW when cap is too small (512 bytes per record always suffice). */
+int64_t nc_format_snp_records(const char* chrom, int64_t n, const int32_t* pos, const uint8_t* ref_code, const float* probs4,
+                              const int32_t* dp, const int32_t* alt_cnt, const uint16_t* fwd4, const uint16_t* rev4, int32_t haploid,
+                              int32_t threads, char* out, int64_t cap, int64_t* line_off, uint8_t* is_pass);
+
 #ifdef __cplusplus
 }
 #endif

@@ -206,14 +206,15 @@ def run(args):
         hap = None
         if any(c["ploidy"] == "haploid" for c in chunks):
             hap = models.get_SNP_model("haploid", args.nanocaller_src)[0]          # snpCaller.py:74
-        lines = []
+        parts = []
         for grp in _groups(chunks):
-            lines += snp_caller.call_chunks(params, grp, (tensors, cov), hap_weights=hap, device=args.device)
+            blob, off, ok, pos = snp_caller.call_chunks_blob(params, grp, (tensors, cov), hap_weights=hap, device=args.device)
+            parts.append((grp[0]["chrom"], blob, off, ok, pos))
         allp = os.path.join(args.output, "%s.unfiltered.snps.vcf.gz" % args.prefix)
         passp = os.path.join(args.output, "%s.snps.vcf.gz" % args.prefix)
-        vcfio.write_vcf(allp, "snps", chrom_list, lines, args.sample)
-        vcfio.write_vcf(passp, "snps", chrom_list, vcfio.pass_only(lines), args.sample)
-        out.update(unfiltered_snps=allp, snps=passp, n_snp_records=len(lines), snp_seconds=time.time() - t1)
+        n_all = vcfio.write_vcf_blobs(allp, "snps", chrom_list, parts, args.sample)
+        vcfio.write_vcf_blobs(passp, "snps", chrom_list, parts, args.sample, pass_only=True)
+        out.update(unfiltered_snps=allp, snps=passp, n_snp_records=n_all, snp_seconds=time.time() - t1)
         print("\n%s: SNP calling completed. Time taken= %.4f\n" % (datetime.datetime.now(), time.time() - t1), flush=True)
 
     if args.mode in ("indels", "all"):

@@ -1,6 +1,7 @@
 // libnanocaller_b200.so — C-ABI (include/nanocaller_b200.h) over the sm_100a kernels.
 // One context = one device + one stream; every entry point returns 0 or a negative NC_E* code.
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <thread>
 #include <cstdarg>
@@ -1079,6 +1080,92 @@ int nc_allele_predict_batch(int64_t n_items, const uint8_t* alt_codes, const int
     for (int t = 0; t < threads; t++) pool.emplace_back(work);
     for (auto& th : pool) th.join();
     return NC_OK;
+}
+
+// SNP genotype decision + VCF record text (snpCaller.py:113-163 diploid, :183-198 haploid) for n call records on host threads.
+// Same decisions and the same printf conversions as the reference's Python (% formatting of float64 values): QUAL from the
+// float32 probability widened to float64, PR= in A,C,G,T order, depths printed as integers.
+static int format_one_snp(char* o, const char* chrom, int32_t pos, int r, const float* p, int32_t dp, int32_t alt_cnt, const uint16_t* fw,
+                          const uint16_t* rv, int haploid, uint8_t* is_pass) {
+    static const char B[4] = {'A', 'G', 'T', 'C'};
+    const double freq = (double)alt_cnt / (double)dp;
+    char info[96];
+    snprintf(info, sizeof(info), "PR=%.4f,%.4f,%.4f,%.4f;FQ=%.4f", (double)p[0], (double)p[3], (double)p[1], (double)p[2], freq);
+    auto qual = [](float x, double cap, double mult) { return std::min(cap, -mult * log10(1e-10 + 1.0 - (double)x)); };
+    *is_pass = 0;
+    if (haploid) {
+        int pred = 0;
+        for (int i = 1; i < 4; i++) if (p[i] > p[pred]) pred = i;                      // np.argmax: first maximum
+        const bool pass = pred != r;
+        *is_pass = pass;
+        return sprintf(o, "%s\t%d\t.\t%c\t%c\t%.3f\t%s\t%s\tGT:DP:VF:AD:ADF:ADR\t1/1:%d:%.4f:.:.:.\n", chrom, pos, B[r], B[pred],
+                       qual(p[pred], 999.0, 100.0), pass ? "PASS" : "REF", info, dp, freq);
+    }
+    int order[4] = {0, 1, 2, 3};                                                       // stable ascending argsort
+    for (int i = 1; i < 4; i++) { const int v = order[i]; int j = i; while (j > 0 && p[order[j - 1]] > p[v]) { order[j] = order[j - 1]; j--; } order[j] = v; }
+    const int p1 = order[3], p2 = order[2];
+    int k = 0;
+    for (int i = 0; i < 4; i++) k += p[i] >= 0.5f;
+    const double q1 = qual(p[p1], 99.0, 10.0), q2 = qual(p[p2], 99.0, 10.0);
+    const int rf = fw[r], rr = rv[r];
+    if (k >= 2) {
+        int alt;
+        if (p1 == r) alt = p2;
+        else if (p2 == r && p[p2] >= 0.5f) alt = p1;
+        else if (p2 != r && p1 != r && p[p2] >= 0.5f) {
+            const int f1 = fw[p1], r1 = rv[p1], f2 = fw[p2], r2 = rv[p2];
+            *is_pass = 1;
+            return sprintf(o, "%s\t%d\t.\t%c\t%c,%c\t%.3f\tPASS\t%s\tGT:DP:VF:AD:ADF:ADR\t1/2:%d:%.4f,%.4f:%d,%d,%d:%d,%d,%d:%d,%d,%d\n", chrom, pos, B[r],
+                           B[p1], B[p2], q2, info, dp, (double)(f1 + r1) / dp, (double)(f2 + r2) / dp, rf + rr, f1 + r1, f2 + r2, rf, f1, f2, rr, r1, r2);
+        } else return 0;
+        const int af = fw[alt], ar = rv[alt];
+        *is_pass = 1;
+        return sprintf(o, "%s\t%d\t.\t%c\t%c\t%.3f\tPASS\t%s\tGT:DP:VF:AD:ADF:ADR\t0/1:%d:%.4f:%d,%d:%d,%d:%d,%d\n", chrom, pos, B[r], B[alt], q2, info, dp,
+                       (double)(af + ar) / dp, rf + rr, af + ar, rf, af, rr, ar);
+    }
+    if (k == 1 && r != p1) {
+        const int af = fw[p1], ar = rv[p1];
+        *is_pass = 1;
+        return sprintf(o, "%s\t%d\t.\t%c\t%c\t%.3f\tPASS\t%s\tGT:DP:VF:AD:ADF:ADR\t1/1:%d:%.4f:%d,%d:%d,%d:%d,%d\n", chrom, pos, B[r], B[p1], q1, info, dp,
+                       (double)(af + ar) / dp, rf + rr, af + ar, rf, af, rr, ar);
+    }
+    if (k == 1) return sprintf(o, "%s\t%d\t.\t%c\t.\t%.3f\tREF\t%s\tGT:DP:VF:AD:ADF:ADR\t./.:%d:.:.:.:.\n", chrom, pos, B[r], q1, info, dp);
+    return sprintf(o, "%s\t%d\t.\t%c\t.\t%.3f\tLOW\t%s\tGT:DP:VF:AD:ADF:ADR\t./.:%d:.:.:.:.\n", chrom, pos, B[r], 0.0, info, dp);
+}
+
+int64_t nc_format_snp_records(const char* chrom, int64_t n, const int32_t* pos, const uint8_t* ref_code, const float* probs4, const int32_t* dp,
+                              const int32_t* alt_cnt, const uint16_t* fwd4, const uint16_t* rev4, int32_t haploid, int32_t threads, char* out,
+                              int64_t cap, int64_t* line_off, uint8_t* is_pass) {
+    if (!chrom || n < 0 || strlen(chrom) > 200 || (n > 0 && (!pos || !ref_code || !probs4 || !dp || !alt_cnt || !fwd4 || !rev4 || !out || !line_off || !is_pass)))
+        return NC_EINVAL;
+    constexpr int SLOT = 512;                                                         // a record is < 200 characters + the contig name
+    std::vector<char> tmp((size_t)std::max<int64_t>(n, 1) * SLOT);
+    std::vector<int32_t> len((size_t)n);
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads, (n + 4095) / 4096));
+    std::atomic<int64_t> next{0};
+    std::atomic<int> bad{0};
+    auto work = [&]() {
+        for (;;) {
+            const int64_t a = next.fetch_add(4096);
+            if (a >= n) return;
+            const int64_t e = std::min(n, a + 4096);
+            for (int64_t i = a; i < e; i++) {
+                if (ref_code[i] > 3 || dp[i] <= 0) { bad = 1; len[(size_t)i] = 0; is_pass[i] = 0; continue; }
+                len[(size_t)i] = format_one_snp(tmp.data() + (size_t)i * SLOT, chrom, pos[i], ref_code[i], probs4 + 4 * i, dp[i], alt_cnt[i], fwd4 + 4 * i,
+                                                rev4 + 4 * i, haploid, is_pass + i);
+            }
+        }
+    };
+    if (threads == 1) work();
+    else { std::vector<std::thread> pool; for (int t = 0; t < threads; t++) pool.emplace_back(work); for (auto& th : pool) th.join(); }
+    if (bad) return NC_EINVAL;
+    int64_t total = 0;
+    for (int64_t i = 0; i < n; i++) { line_off[i] = total; total += len[(size_t)i]; }
+    line_off[n] = total;
+    if (total > cap) return NC_EOVERFLOW;
+    for (int64_t i = 0; i < n; i++) memcpy(out + line_off[i], tmp.data() + (size_t)i * SLOT, (size_t)len[(size_t)i]);
+    return total;
 }
 
 // ---- development probes (not part of the public header) -------------------------------------------------

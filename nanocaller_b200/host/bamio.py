@@ -16,16 +16,23 @@ from .readset import ReadSet
 _BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 
 
-def bgzf_compress(data, level=4):
-    """bytes -> BGZF stream (64 KiB blocks with the BC extra field, plus the EOF marker)."""
-    out = []
-    for off in range(0, len(data), 0xff00):
-        chunk = data[off:off + 0xff00]
-        co = zlib.compressobj(level, zlib.DEFLATED, -15)
-        body = co.compress(chunk) + co.flush()
-        bsize = len(body) + 25
-        out.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize) + body +
-                   struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+def _bgzf_block(chunk, level):
+    co = zlib.compressobj(level, zlib.DEFLATED, -15)
+    body = co.compress(chunk) + co.flush()
+    return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(body) + 25) + body +
+            struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+
+
+def bgzf_compress(data, level=4, threads=None):
+    """bytes -> BGZF stream (64 KiB blocks with the BC extra field, plus the EOF marker).  Blocks are independent gzip members:
+    large inputs are deflated on a thread pool (zlib releases the GIL)."""
+    chunks = [data[off:off + 0xff00] for off in range(0, len(data), 0xff00)]
+    if len(chunks) >= 64:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(threads or min(32, os.cpu_count() or 1)) as ex:
+            out = list(ex.map(lambda c: _bgzf_block(c, level), chunks, chunksize=16))
+    else:
+        out = [_bgzf_block(c, level) for c in chunks]
     out.append(_BGZF_EOF)
     return b"".join(out)
 

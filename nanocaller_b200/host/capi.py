@@ -17,7 +17,8 @@ EXPORTS = ["nc_abi_version", "nc_create", "nc_destroy", "nc_last_error", "nc_syn
            "nc_device_sm_count", "nc_event_record", "nc_event_elapsed_ms", "nc_invalidate_decode", "nc_stage_reads", "nc_decode_reads", "nc_snp_scan", "nc_snp_fetch",
            "nc_load_snp_weights", "nc_snp_forward", "nc_snp_fetch_probs", "nc_snp_model_forward", "nc_snp_device_buffers",
            "nc_load_indel_weights", "nc_indel_model_forward", "nc_stage_tags", "nc_indel_scan", "nc_indel_fetch_variants",
-           "nc_indel_build", "nc_indel_fetch", "nc_nw_trace", "nc_allele_predict_batch"]
+           "nc_indel_build", "nc_indel_fetch", "nc_nw_trace", "nc_allele_predict_batch",
+           "nc_format_snp_records"]
 
 
 class NcSnpParams(ctypes.Structure):
@@ -100,7 +101,7 @@ def load_library():
     lib.nc_nw_trace.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp, i32]
     for name in EXPORTS:
         if name not in ("nc_destroy", "nc_last_error"):
-            getattr(lib, name).restype = ctypes.c_int
+            getattr(lib, name).restype = ctypes.c_int64 if name == "nc_format_snp_records" else ctypes.c_int
     _lib = lib
     return lib
 
@@ -153,6 +154,27 @@ def allele_predict_batch(alt_flat, alt_off, alt_len, ref_flat, ref_off, ref_len,
     if rc != NC_OK:
         raise NcError(rc, "nc_allele_predict_batch failed")
     return ro, ao
+
+
+def format_snp_records(chrom, pos, ref_code, probs, dp, alt, fwd, rev, haploid=False, threads=0):
+    """Decision + record text of snpCaller.py:113-163 / :183-198 in the library (threaded).  -> (bytes blob, line_off int64[n+1],
+    is_pass bool[n]); the records are blob[line_off[i]:line_off[i+1]]."""
+    lib = load_library()
+    n = len(pos)
+    pos = np.ascontiguousarray(pos, np.int32); ref_code = np.ascontiguousarray(ref_code, np.uint8)
+    probs = np.ascontiguousarray(probs, np.float32).reshape(n, 4)
+    dp = np.ascontiguousarray(dp, np.int32); alt = np.ascontiguousarray(alt, np.int32)
+    fwd = np.ascontiguousarray(fwd, np.uint16).reshape(n, 4); rev = np.ascontiguousarray(rev, np.uint16).reshape(n, 4)
+    out = np.empty(max(1, n) * 512, np.uint8)
+    off = np.zeros(n + 1, np.int64)
+    ok = np.zeros(max(1, n), np.uint8)
+    f = lib.nc_format_snp_records
+    f.argtypes = [ctypes.c_char_p, ctypes.c_int64] + [ctypes.c_void_p] * 7 + [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    tot = f(chrom.encode(), n, _p(pos), _p(ref_code), _p(probs), _p(dp), _p(alt), _p(fwd), _p(rev), 1 if haploid else 0, int(threads),
+            _p(out), out.size, _p(off), _p(ok))
+    if tot < 0:
+        raise NcError(int(tot), "nc_format_snp_records failed")
+    return out[:tot].tobytes(), off, ok[:n].astype(bool)
 
 
 class Context:

@@ -80,15 +80,17 @@ def records_from_calls(chrom, pos, ref_code, probs, dp, freq, fwd_dp, rev_dp, pl
     return out
 
 
-def call_chunks(params, chunks, snp_weights, hap_weights=None, device=0, impl=0):
-    """All chunks of ONE contig: returns the unfiltered VCF record lines in (chunk, position) order — what
-    snpCaller.caller writes for those chunks (snpCaller.py:83-198).
+def call_chunks_blob(params, chunks, snp_weights, hap_weights=None, device=0, impl=0, threads=0):
+    """All chunks of ONE contig on the GPU, records formatted by the library (nc_format_snp_records, threaded):
+    -> (blob bytes, line_off int64[n+1], is_pass bool[n], pos int32[n]) in (chunk, position) order — what snpCaller.caller writes
+    for those chunks (snpCaller.py:83-198).
 
     params: the reference's dict (sam_path, fasta_path, threshold, mincov, maxcov, min_allele_freq, min_nbr_sites, seq,
             supplementary, exclude_bed, disable_coverage_normalization)
     snp_weights: (tensors, train_coverage) of the diploid model; hap_weights: tensors of the haploid model."""
+    empty = (b"", np.zeros(1, np.int64), np.zeros(0, bool), np.zeros(0, np.int32))
     if not chunks:
-        return []
+        return empty
     chrom, ploidy = chunks[0]["chrom"], chunks[0]["ploidy"]
     assert all(c["chrom"] == chrom and c["ploidy"] == ploidy for c in chunks)
     ctx = snp_pileups.context(device)
@@ -106,8 +108,15 @@ def call_chunks(params, chunks, snp_weights, hap_weights=None, device=0, impl=0)
     bed = sources.bed_intervals(params.get("exclude_bed"), chrom)
     n = snp_pileups.scan_chunks(ctx, rs, params, chunks, ploidy, bed)
     if n == 0:
-        return []
+        return empty
     probs = ctx.snp_forward(normalize=normalize, impl=impl)
     _, meta, _, _ = ctx.snp_fetch(want_mat=False)
-    freq = meta["alt"].astype(np.float64) / meta["dp"].astype(np.float64)
-    return records_from_calls(chrom, meta["pos"], meta["ref_code"], probs, meta["dp"], freq, meta["fwd"], meta["rev"], ploidy)
+    blob, off, ok = capi.format_snp_records(chrom, meta["pos"], meta["ref_code"], probs, meta["dp"], meta["alt"], meta["fwd"], meta["rev"],
+                                            haploid=(ploidy == "haploid"), threads=threads)
+    return blob, off, ok, meta["pos"].astype(np.int32)
+
+
+def call_chunks(params, chunks, snp_weights, hap_weights=None, device=0, impl=0):
+    """`call_chunks_blob` as a list of VCF record lines (the unfiltered records of those chunks, in order)."""
+    blob, off, _, _ = call_chunks_blob(params, chunks, snp_weights, hap_weights, device, impl)
+    return [blob[off[i]:off[i + 1]].decode() for i in range(len(off) - 1) if off[i + 1] > off[i]]

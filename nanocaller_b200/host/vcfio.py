@@ -71,3 +71,37 @@ def write_vcf(path, kind, contigs, lines, sample="SAMPLE"):
     data = (header(kind, contigs, sample) + "".join(sort_records(lines, contigs))).encode()
     with open(path, "wb") as f:
         f.write(bgzf_compress(data) if path.endswith(".gz") else data)
+
+
+def write_vcf_blobs(path, kind, contigs, parts, sample="SAMPLE", pass_only=False):
+    """Like `write_vcf` for records that arrive as byte blobs: parts = [(chrom, blob, line_off, is_pass, pos), ...], each in
+    (chunk, position) order (what `snp_caller.call_chunks_blob` returns).  Output order = contig order, then position, stable
+    (both records of a shared chunk boundary are kept in chunk order, like `sort_records`)."""
+    import numpy as np
+    rank = {c: i for i, c in enumerate(contigs)}
+    by_contig = {}
+    for part in parts:
+        by_contig.setdefault(part[0], []).append(part)
+    body, n_written = [], 0
+    for chrom in sorted(by_contig, key=lambda c: rank.get(c, len(rank))):
+        group = [p for p in by_contig[chrom] if len(p[4])]
+        if not group:
+            continue
+        pos = np.concatenate([p[4] for p in group])
+        has = np.concatenate([np.diff(p[2]) > 0 for p in group])
+        keep = has & (np.concatenate([p[3] for p in group]) if pass_only else True)
+        in_order = len(pos) < 2 or not np.any(np.diff(pos) < 0)
+        if len(group) == 1 and in_order and keep.all():
+            body.append(group[0][1])                                   # the common case: one part, already sorted, nothing dropped
+            n_written += len(pos)
+            continue
+        part_of = np.concatenate([np.full(len(p[4]), i) for i, p in enumerate(group)])
+        local = np.concatenate([np.arange(len(p[4])) for p in group])
+        idx = np.arange(len(pos)) if in_order else np.argsort(pos, kind="stable")
+        idx = idx[keep[idx]]
+        body.append(b"".join(group[part_of[k]][1][group[part_of[k]][2][local[k]]:group[part_of[k]][2][local[k] + 1]] for k in idx.tolist()))
+        n_written += len(idx)
+    data = header(kind, contigs, sample).encode() + b"".join(body)
+    with open(path, "wb") as f:
+        f.write(bgzf_compress(data) if path.endswith(".gz") else data)
+    return n_written

@@ -115,3 +115,37 @@ def test_io_header_symbols_exported():
     names = sorted(set(re.findall(r"\b(nc_bam_[a-z0-9_]+)\s*\(", src)))
     lib = bamio.load_io_library()
     assert names == sorted(bamio.IO_EXPORTS) and all(hasattr(lib, n) for n in names)
+
+
+def test_write_vcf_blobs_equals_line_writer(tmp_path):
+    """The blob writer used by the command line (records formatted by the library) against sort_records / pass_only / write_vcf on the
+    same records: several parts per contig, out-of-order regions, shared-boundary duplicates, PASS filter, threaded BGZF."""
+    from nanocaller_b200.host import capi
+    rng = np.random.RandomState(3)
+    parts, lines = [], []
+    for chrom, lo, hi, n in (("chr2", 1, 9000, 300), ("chr1", 5000, 9000, 200), ("chr1", 1, 5000, 250), ("chr3", 1, 100, 0)):
+        pos = np.sort(rng.randint(lo, hi + 1, n)).astype(np.int32)
+        if n:
+            pos[-1] = hi
+            pos[0] = lo                                            # chr1: 5000 appears in two parts (shared boundary)
+        probs = rng.rand(n, 4).astype(np.float32)
+        ref = rng.randint(0, 4, n).astype(np.uint8)
+        fwd = rng.randint(0, 40, (n, 4)).astype(np.uint16); rev = rng.randint(0, 40, (n, 4)).astype(np.uint16)
+        dp = (fwd.sum(1) + rev.sum(1) + 1).astype(np.int32)
+        alt = np.minimum(dp, rng.randint(0, 30, n)).astype(np.int32)
+        blob, off, ok = capi.format_snp_records(chrom, pos, ref, probs, dp, alt, fwd, rev)
+        parts.append((chrom, blob, off, ok, pos))
+        lines += [blob[off[i]:off[i + 1]].decode() for i in range(n) if off[i + 1] > off[i]]
+    contigs = ["chr1", "chr2", "chr3"]
+    for pass_only in (False, True):
+        a, b = str(tmp_path / ("a%d.vcf.gz" % pass_only)), str(tmp_path / ("b%d.vcf.gz" % pass_only))
+        sel = vcfio.pass_only(lines) if pass_only else lines
+        vcfio.write_vcf(a, "snps", contigs, sel, "S")
+        n = vcfio.write_vcf_blobs(b, "snps", contigs, parts, "S", pass_only=pass_only)
+        ta, tb = gzip.open(a, "rt").read(), gzip.open(b, "rt").read()
+        assert ta == tb and n == len(sel) > 100
+    big = os.urandom(5_000_000)
+    z = bamio.bgzf_compress(big)
+    p = str(tmp_path / "big.gz")
+    open(p, "wb").write(z)
+    assert gzip.open(p, "rb").read() == big and z.endswith(bamio._BGZF_EOF)

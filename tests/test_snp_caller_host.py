@@ -53,3 +53,34 @@ def test_haploid_records_match_oracle():
 
 def test_empty():
     assert records_from_calls("c", [], [], np.zeros((0, 4), np.float32), [], [], [], []) == []
+
+
+def test_native_record_formatter_matches_python(monkeypatch=None):
+    """nc_format_snp_records (C++, threaded) vs records_from_calls (numpy / Python), line for line, on random call records with
+    probabilities pushed onto the decision boundaries."""
+    from nanocaller_b200.host import capi, snp_caller
+    rng = np.random.RandomState(12)
+    n = 20_000
+    probs = rng.rand(n, 4).astype(np.float32)
+    probs[rng.rand(n, 4) < 0.08] = np.float32(0.5)                       # exactly on the threshold
+    probs[rng.rand(n, 4) < 0.05] = np.float32(1.0)
+    probs[rng.rand(n, 4) < 0.05] = np.float32(0.0)
+    tie = rng.rand(n) < 0.1
+    probs[tie, 1] = probs[tie, 3]                                         # ties: the stable argsort decides
+    pos = np.sort(rng.randint(1, 5_000_000, n)).astype(np.int32)
+    ref = rng.randint(0, 4, n).astype(np.uint8)
+    fwd = rng.randint(0, 90, (n, 4)).astype(np.uint16)
+    rev = rng.randint(0, 90, (n, 4)).astype(np.uint16)
+    dp = (fwd.sum(1) + rev.sum(1) + rng.randint(1, 9, n)).astype(np.int32)
+    alt = np.array([max(int(fwd[i, b]) + int(rev[i, b]) for b in range(4) if b != ref[i]) for i in range(n)], np.int32)
+    freq = alt.astype(np.float64) / dp.astype(np.float64)
+    for haploid in (False, True):
+        want = snp_caller.records_from_calls("chr7", pos, ref, probs, dp, freq, fwd, rev, "haploid" if haploid else "diploid")
+        for threads in (1, 5):
+            blob, off, ok = capi.format_snp_records("chr7", pos, ref, probs, dp, alt, fwd, rev, haploid=haploid, threads=threads)
+            got = [blob[off[i]:off[i + 1]].decode() for i in range(n) if off[i + 1] > off[i]]
+            assert got == want
+            flt = [ln.split("\t")[6] == "PASS" for ln in want]
+            assert ok[np.diff(off) > 0].tolist() == flt
+    blob, off, ok = capi.format_snp_records("c", [], [], np.zeros((0, 4), np.float32), [], [], np.zeros((0, 4)), np.zeros((0, 4)))
+    assert blob == b"" and off.tolist() == [0]
