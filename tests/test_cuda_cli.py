@@ -93,3 +93,45 @@ def test_cli_snps_and_indels_from_files(tmp_path):
     assert len(merged) == len(passed) + len(got_i) and "ID=PS" in txt_m and "ID=PR" in txt_m
     keys = [(ln.split("\t")[0], int(ln.split("\t")[1])) for ln in merged]
     assert keys == sorted(keys)
+
+
+def test_cli_ccs_preset_regions_and_exclude_bed(tmp_path):
+    """`--preset ccs --mode snps` (pacbio neighbour rule, CCS-HG002 model, thresholds 0.3,0.7), regions given out of order with an
+    explicit sub-range, an exclude BED given by path: records against the oracle pipeline with the same parameters."""
+    from nanocaller_b200 import cli
+    from nanocaller_b200.host import snp_pileups, sources, vcfio, weights as W
+    from nanocaller_b200.host.vcf_compare import compare_records
+    from oracle import cnn_oracle, snp_caller_oracle, snp_oracle
+    bam, fa, worlds = _world(tmp_path)
+    bed = str(tmp_path / "ex.bed")
+    with open(bed, "w") as f:
+        f.write("chrA\t20000\t26000\nchrA\t90000\t90500\n")
+    sources.unregister_all()
+    snp_pileups.reset()
+    out = cli.main(["--bam", bam, "--ref", fa, "--mode", "snps", "--preset", "ccs", "--cpu", "2", "--regions", "chrY", "chrA:10001-120000",
+                    "--exclude_bed", bed, "--output", str(tmp_path / "o2"), "--prefix", "c"])
+    regions = [("chrY", 1, 40_000, "haploid"), ("chrA", 10_001, 120_000, "diploid")]
+    dct = dict(threshold=[0.3, 0.7], mincov=4, maxcov=160, min_allele_freq=0.15, min_nbr_sites=1, seq="pacbio", supplementary=False)
+    tensors, meta = W.load_model("snp", "CCS-HG002")
+    hap, _ = W.load_model("snp", "haploid")
+    ivs = {"chrA": [(20000, 26000), (90000, 90500)]}
+    want = []
+    for ch in snp_oracle.get_chunks(regions, 2):
+        rs = worlds[0] if ch["chrom"] == "chrA" else worlds[1]
+        pos, ref, mat, dp, freq, depth, fwd, rev = snp_oracle.get_snp_testing_candidates(rs, dct, ch, ivs.get(ch["chrom"]))
+        if len(pos) == 0:
+            continue
+        ref = np.asarray(ref, np.float32)
+        if ch["ploidy"] == "haploid":
+            x = snp_oracle.scale_counts(mat, 30.0, coverage=float(depth))
+            want += snp_caller_oracle.haploid_records(ch["chrom"], pos, ref, cnn_oracle.haploid_snp_model(hap, x, ref), dp, freq)
+        else:
+            x = snp_oracle.scale_counts(mat, meta["train_coverage"], coverage=float(depth))
+            want += snp_caller_oracle.diploid_records(ch["chrom"], pos, ref, cnn_oracle.snp_probs(tensors, x, ref), dp, freq, fwd, rev)
+    want = vcfio.sort_records(want, ["chrY", "chrA"])                      # header / output order follows the order of --regions
+    got, txt = _records(out["unfiltered_snps"])
+    assert txt.index("##contig=<ID=chrY>") < txt.index("##contig=<ID=chrA>")
+    assert not any(20000 <= int(ln.split("\t")[1]) < 26000 for ln in got if ln.startswith("chrA"))
+    res = compare_records(got, want, tol=1e-4)
+    assert not res["mismatch"], res["mismatch"][:3]
+    assert res["identical"] + res["numeric_only"] + res["borderline"] == len(want) > 300
