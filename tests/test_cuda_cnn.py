@@ -43,6 +43,23 @@ def test_snp_model_forward_matches_oracle(model, impl):
     assert np.abs(got - want).max() < TOL, np.abs(got - want).max()
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 127, 128, 129, 443, 444, 445, 1333])
+def test_tensor_core_path_ragged_batches(n):
+    """Batch sizes around every tiling boundary of the tensor-core path: 3 sites per conv3 group, 128 sites per fc1 tile,
+    444 sites per wave of the conv1/conv2 kernel (148 SMs x 3 warpgroups), a few groups per TB ring."""
+    from nanocaller_b200.host import weights as W
+    from oracle import cnn_oracle, snp_oracle
+    tensors, meta = W.load_model("snp", "ONT-HG002")
+    ctx = _ctx()
+    ctx.load_snp_weights(W.pack_snp_blob(tensors, False), meta["train_coverage"], False)
+    x, ref, dp, depth = _golden_x("ont_diploid", n)
+    assert len(x) == n
+    x = snp_oracle.scale_counts(x, meta["train_coverage"], coverage=float(depth[0]))
+    want = np.concatenate(cnn_oracle.snp_model(tensors, x, ref), 1)
+    got = ctx.snp_model_forward(x, ref, haploid=False, impl=0)
+    assert got.shape == want.shape and np.abs(got - want).max() < TOL, np.abs(got - want).max()
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 def test_haploid_snp_model_forward_matches_oracle(impl):
     from nanocaller_b200.host import weights as W
