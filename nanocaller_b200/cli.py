@@ -184,9 +184,9 @@ def run(args):
         f.write("------Parameters Used For Variant Calling------\n")
         for k, v in vars(args).items():
             f.write("{}: {}\n".format(k, v))
-    readsets = bamio.open_alignment(args.bam, args.ref)
-    contig_lengths = {rs.chrom: rs.contig_len for rs in readsets}
+    contig_lengths = bamio.bam_contigs(args.bam)                  # utils.py:9-50 asks the BAM header, not the FASTA
     regions = get_regions_list(args, contig_lengths)
+    bamio.open_alignment(args.bam, args.ref, contigs={r[0] for r in regions})     # only the contigs that will be called
     exclude = _load_exclude_bed(args)
     chrom_list = list(dict.fromkeys(r[0] for r in regions))
     ctx = snp_pileups.context(args.device)                        # fails loudly without an sm_100 device

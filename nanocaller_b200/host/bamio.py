@@ -158,19 +158,50 @@ def read_bam(path, fasta=None, contigs=None):
     return out, text
 
 
-def read_fasta(path):
-    """-> {contig: uint8 array of the sequence bytes, case preserved} (plain or gzip/BGZF-compressed FASTA)."""
-    opener = gzip.open if open(path, "rb").read(2) == b"\x1f\x8b" else open
+def read_fasta(path, contigs=None):
+    """-> {contig: uint8 array of the sequence bytes, case preserved}.  With a `.fai` next to an uncompressed FASTA only the
+    requested contigs are read (seek + one numpy pass that drops the line ends) — what pysam.FastaFile.fetch does for the
+    reference (generate_SNP_pileups.py:135-137).  Without an index (or for gzip/BGZF input) the file is scanned."""
+    with open(path, "rb") as f:
+        gz = f.read(2) == b"\x1f\x8b"
+    fai = path + ".fai"
+    if not gz and os.path.exists(fai):
+        out = {}
+        with open(fai) as idx, open(path, "rb") as f:
+            for line in idx:
+                t = line.rstrip("\n").split("\t")
+                if len(t) < 5:
+                    continue
+                name, length, offset, linebases, linewidth = t[0], int(t[1]), int(t[2]), int(t[3]), int(t[4])
+                if contigs is not None and name not in contigs:
+                    continue
+                if length == 0 or linebases <= 0:
+                    out[name] = np.zeros(0, np.uint8)
+                    continue
+                nlines = (length + linebases - 1) // linebases
+                f.seek(offset)
+                raw = np.frombuffer(f.read((nlines - 1) * linewidth + (length - (nlines - 1) * linebases)), np.uint8)
+                if linewidth == linebases or nlines == 1:
+                    seq = raw[:length].copy()
+                else:
+                    full = (nlines - 1) * linewidth
+                    body = raw[:full].reshape(nlines - 1, linewidth)[:, :linebases].reshape(-1)
+                    seq = np.concatenate([body, raw[full:full + length - (nlines - 1) * linebases]])
+                if len(seq) != length:
+                    raise ValueError("%s: %s is shorter than its index says" % (path, name))
+                out[name] = seq
+        return out
+    opener = gzip.open if gz else open
     out, name, chunks = {}, None, []
     with opener(path, "rb") as f:
         for line in f:
             if line.startswith(b">"):
-                if name is not None:
+                if name is not None and (contigs is None or name in contigs):
                     out[name] = np.frombuffer(b"".join(chunks), np.uint8).copy()
                 name, chunks = line[1:].split()[0].decode(), []
-            else:
+            elif contigs is None or name in contigs:
                 chunks.append(line.strip())
-    if name is not None:
+    if name is not None and (contigs is None or name in contigs):
         out[name] = np.frombuffer(b"".join(chunks), np.uint8).copy()
     return out
 
@@ -276,12 +307,30 @@ def read_bam_native(path, fasta=None, contigs=None, threads=0, alloc=None, qname
             lib.nc_bam_close(h)
 
 
-def open_alignment(sam_path, fasta_path, native=True):
-    """Parse `sam_path` (BAM) and `fasta_path` once and register the contigs as an alignment source."""
+def bam_contigs(path):
+    """Ordered {contig: length} from the BAM header (`sam_file.references` / `get_reference_length`, utils.py:9-50); reads only
+    the head of the file."""
+    with gzip.open(path, "rb") as f:
+        head = f.read(12)
+        if head[:4] != b"BAM\x01":
+            raise ValueError("%s: not a BAM file" % path)
+        l_text = struct.unpack_from("<i", head, 4)[0]
+        rest = head[8:] + f.read(l_text)                     # 4 bytes already read past l_text
+        n_ref = struct.unpack_from("<i", rest, l_text)[0]
+        out = {}
+        for _ in range(n_ref):
+            ln = struct.unpack("<i", f.read(4))[0]
+            name = f.read(ln)[:-1].decode()
+            out[name] = struct.unpack("<i", f.read(4))[0]
+        return out
+
+
+def open_alignment(sam_path, fasta_path, native=True, contigs=None):
+    """Parse `sam_path` (BAM) and `fasta_path` once and register the contigs (all, or the named ones) as an alignment source."""
     from . import sources
     if not os.path.exists(sam_path):
         raise FileNotFoundError(sam_path)
-    fasta = read_fasta(fasta_path) if fasta_path and os.path.exists(fasta_path) else None
-    readsets, _ = (read_bam_native if native else read_bam)(sam_path, fasta)
+    fasta = read_fasta(fasta_path, contigs) if fasta_path and os.path.exists(fasta_path) else None
+    readsets, _ = (read_bam_native if native else read_bam)(sam_path, fasta, contigs=contigs)
     sources.register_source(sam_path, readsets)
     return readsets

@@ -149,3 +149,35 @@ def test_write_vcf_blobs_equals_line_writer(tmp_path):
     p = str(tmp_path / "big.gz")
     open(p, "wb").write(z)
     assert gzip.open(p, "rb").read() == big and z.endswith(bamio._BGZF_EOF)
+
+
+def test_fasta_index_reader_equals_scan(tmp_path):
+    """read_fasta through the .fai (seek + numpy, selected contigs only) gives the bytes of the line-by-line scan: line widths that do
+    and do not divide the contig length, a one-line contig, lower-case soft-masked bases preserved."""
+    rng = np.random.RandomState(8)
+    from nanocaller_b200.host.readset import ReadSet
+    sets = []
+    for name, n in (("a", 1234), ("b", 60), ("c", 61), ("d", 7), ("e", 120)):
+        ref = rng.choice(np.frombuffer(b"ACGTacgtN", np.uint8), n)
+        sets.append(ReadSet(name, ref, [], [], [0], np.zeros(0, np.uint32), [0], [], np.zeros(0, np.uint8)))
+    fa = str(tmp_path / "r.fa")
+    bamio.write_fasta(fa, sets, width=60)
+    via_index = bamio.read_fasta(fa)
+    os.rename(fa + ".fai", fa + ".fai.off")
+    via_scan = bamio.read_fasta(fa)
+    os.rename(fa + ".fai.off", fa + ".fai")
+    assert list(via_index) == list(via_scan) == [s.chrom for s in sets]
+    for s_ in sets:
+        np.testing.assert_array_equal(via_index[s_.chrom], s_.ref)
+        np.testing.assert_array_equal(via_scan[s_.chrom], s_.ref)
+    only = bamio.read_fasta(fa, contigs={"c", "e"})
+    assert list(only) == ["c", "e"] and only["c"].tobytes() == sets[2].ref.tobytes()
+
+
+def test_bam_contigs_from_header(tmp_path):
+    rs1 = make_world(chrom="chrA", preset="ont", contig_len=20_000, seed=3, coverage=3.0).reads
+    rs2 = _handmade()
+    bam = str(tmp_path / "h.bam")
+    bamio.write_bam(bam, [rs1, rs2])
+    assert bamio.bam_contigs(bam) == {"chrA": 20_000, "tiny": rs2.contig_len}
+    assert list(bamio.bam_contigs(bam)) == ["chrA", "tiny"]
