@@ -39,6 +39,10 @@ typedef struct NcBamContig {
 /* Reads and inflates the whole file with `threads` workers (<= 0: all cores) and indexes the records.  *out is set even on
  * failure (for nc_bam_error) and must be closed. */
 int nc_bam_open(const char* path, int threads, nc_bam** out);
+/* The same for a subset of contigs of a BAM that has a BAI index next to it: only the BGZF blocks holding the named contigs'
+ * records are inflated (samfile.fetch(chrom, ...), generate_SNP_pileups.py:141,156).  Every reference of the header is listed by
+ * nc_bam_contig; contigs that were not asked for (or have no reads) report n_reads = 0. */
+int nc_bam_open_region(const char* path, const char* bai_path, const char* const* names, int n_names, int threads, nc_bam** out);
 const char* nc_bam_error(const nc_bam* b);
 int nc_bam_n_contigs(const nc_bam* b);
 const char* nc_bam_header_text(const nc_bam* b, int64_t* len);

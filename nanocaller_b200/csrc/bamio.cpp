@@ -85,11 +85,13 @@ template <class F> void parallel_for(int64_t n, int threads, F f) {
     for (auto& th : pool) th.join();
 }
 
-int inflate_all(nc_bam* b, const uint8_t* file, size_t n, int threads) {
-    struct Blk { size_t off, csize; uint32_t isize; size_t out; };
-    std::vector<Blk> blocks;
-    size_t off = 0, total = 0;
-    while (off + 18 <= n) {
+struct Blk { size_t start, off, csize; uint32_t isize; size_t out; };     // block start, payload offset / size, inflated size, output offset
+
+// Appends the BGZF blocks of file[cbeg, cend) to `blocks` (cend = file size: all of them); `total` = running inflated size.
+int block_table(nc_bam* b, const uint8_t* file, size_t n, size_t cbeg, size_t cend, std::vector<Blk>& blocks, size_t& total) {
+    size_t off = cbeg;
+    while (off < cend) {
+        if (off + 18 > n) return fail(b, "truncated or malformed BGZF block");
         const uint8_t* p = file + off;
         if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return fail(b, "not a BGZF stream (gzip member without the BC extra field)");
         const uint16_t xlen = rd<uint16_t>(p + 10);
@@ -102,12 +104,16 @@ int inflate_all(nc_bam* b, const uint8_t* file, size_t n, int threads) {
         }
         if (bsize < 0 || off + (size_t)bsize + 1 > n) return fail(b, "truncated or malformed BGZF block");
         const size_t blen = (size_t)bsize + 1;
+        if (blen < xend + 8) return fail(b, "truncated or malformed BGZF block");
         const uint32_t isize = rd<uint32_t>(p + blen - 4);
-        blocks.push_back({off + xend, blen - xend - 8, isize, total});
+        blocks.push_back({off, off + xend, blen - xend - 8, isize, total});
         total += isize;
         off += blen;
     }
-    if (off != n) return fail(b, "trailing bytes after the last BGZF block");
+    return NC_IO_OK;
+}
+
+int inflate_blocks(nc_bam* b, const uint8_t* file, const std::vector<Blk>& blocks, size_t total, int threads) {
     if (!b->data.alloc(total)) return fail(b, "out of memory");
     std::atomic<int> bad{0};
     parallel_for((int64_t)blocks.size(), threads, [&](int64_t i) {
@@ -127,6 +133,95 @@ int inflate_all(nc_bam* b, const uint8_t* file, size_t n, int threads) {
     if (bad) return fail(b, "inflate failed (corrupt BGZF block)");
     return NC_IO_OK;
 }
+
+int inflate_all(nc_bam* b, const uint8_t* file, size_t n, int threads) {
+    std::vector<Blk> blocks;
+    size_t total = 0;
+    const int rc = block_table(b, file, n, 0, n, blocks, total);
+    if (rc) return rc;
+    return inflate_blocks(b, file, blocks, total, threads);
+}
+
+// BAM header at d[0, n): text, reference names and lengths.  Returns the offset of the first record, 0 when more bytes are
+// needed, or -1 on a format error.
+int64_t parse_header(nc_bam* b, const uint8_t* d, size_t n) {
+    if (n < 12) return 0;
+    if (memcmp(d, "BAM\1", 4) != 0) { fail(b, "not a BAM file (bad magic)"); return -1; }
+    const int32_t l_text = rd<int32_t>(d + 4);
+    if (l_text < 0) { fail(b, "truncated BAM header"); return -1; }
+    if (8 + (size_t)l_text + 4 > n) return 0;
+    size_t off = 8 + (size_t)l_text;
+    const int32_t n_ref = rd<int32_t>(d + off);
+    off += 4;
+    if (n_ref < 0) { fail(b, "negative reference count"); return -1; }
+    std::vector<Contig> refs((size_t)n_ref);
+    for (int32_t i = 0; i < n_ref; i++) {
+        if (off + 4 > n) return 0;
+        const int32_t l_name = rd<int32_t>(d + off);
+        if (l_name <= 0) { fail(b, "truncated reference list"); return -1; }
+        if (off + 4 + (size_t)l_name + 4 > n) return 0;
+        refs[i].name.assign((const char*)d + off + 4, (size_t)l_name - 1);
+        refs[i].length = rd<int32_t>(d + off + 4 + l_name);
+        off += 8 + (size_t)l_name;
+    }
+    b->text.assign((const char*)d + 8, (size_t)l_text);
+    b->contigs.swap(refs);
+    return (int64_t)off;
+}
+
+// Walks the records of data[off, end): boundaries and per-contig totals.  only_rid >= 0: stop at the first record of another
+// reference (region reads).
+int scan_records(nc_bam* b, size_t off, size_t end, int32_t only_rid, std::vector<std::vector<int64_t>>& per) {
+    const uint8_t* d = b->data.data();
+    const int32_t n_ref = (int32_t)b->contigs.size();
+    int32_t last_rid = -1, last_pos = -1;
+    while (off + 4 <= end) {
+        const int32_t bs = rd<int32_t>(d + off);
+        if (bs < 32 || off + 4 + (size_t)bs > end) return only_rid >= 0 ? NC_IO_OK : fail(b, "truncated alignment record");
+        const uint8_t* r = d + off + 4;
+        const int32_t rid = rd<int32_t>(r), pos = rd<int32_t>(r + 4);
+        if (only_rid >= 0 && rid != only_rid) break;
+        const uint8_t l_name = r[8];
+        const uint16_t n_cig = rd<uint16_t>(r + 12);
+        const int32_t l_seq = rd<int32_t>(r + 16);
+        if (l_seq < 0 || 32 + (size_t)l_name + 4 * (size_t)n_cig + (size_t)(l_seq + 1) / 2 + (size_t)l_seq > (size_t)bs) return fail(b, "alignment record fields exceed its size");
+        if (rid >= 0 && rid < n_ref) {
+            if (rid < last_rid || (rid == last_rid && pos < last_pos)) b->sorted = false;
+            last_rid = rid; last_pos = pos;
+            Contig& c = b->contigs[(size_t)rid];
+            c.n_reads++; c.n_cigar += n_cig; c.n_seq += (l_seq + 1) / 2;
+            per[(size_t)rid].push_back((int64_t)off);
+        }
+        off += 4 + (size_t)bs;
+    }
+    if (!b->sorted) return fail(b, "BAM is not coordinate-sorted");
+    return NC_IO_OK;
+}
+
+void finish_index(nc_bam* b, std::vector<std::vector<int64_t>>& per) {
+    for (size_t i = 0; i < b->contigs.size(); i++) {
+        b->contigs[i].first_rec = (int64_t)b->rec_off.size();
+        b->rec_off.insert(b->rec_off.end(), per[i].begin(), per[i].end());
+    }
+}
+
+struct MapFile {                       // read-only mapping of a file: the compressed bytes come straight from the page cache
+    const uint8_t* p = nullptr;
+    size_t n = 0;
+    int err = 0;
+    explicit MapFile(const char* path) {
+        const int fd = open(path, O_RDONLY);
+        if (fd < 0) { err = 1; return; }
+        struct stat st;
+        if (fstat(fd, &st) != 0) { close(fd); err = 1; return; }
+        n = (size_t)st.st_size;
+        void* m = n ? mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+        close(fd);
+        if (n && m == MAP_FAILED) { err = 2; n = 0; return; }
+        p = (const uint8_t*)m;
+    }
+    ~MapFile() { if (p) munmap((void*)p, n); }
+};
 
 // integer value of a fixed-width aux field, or false
 bool aux_int(uint8_t type, const uint8_t* p, int32_t* out) {
@@ -184,63 +279,130 @@ int nc_bam_open(const char* path, int threads, nc_bam** out) {
     *out = nullptr;
     nc_bam* b = new nc_bam();
     *out = b;                                   // returned even on failure so that nc_bam_error can explain
-    const int fd = open(path, O_RDONLY);
-    if (fd < 0) { b->err = std::string("cannot open ") + path; return NC_IO_EOPEN; }
-    struct stat st;
-    if (fstat(fd, &st) != 0) { close(fd); b->err = "cannot stat the file"; return NC_IO_EOPEN; }
-    const size_t fsize = (size_t)st.st_size;
-    void* map = fsize ? mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;     // the compressed bytes are read straight from the page cache
-    close(fd);
-    if (fsize && map == MAP_FAILED) { b->err = "mmap failed"; return NC_IO_EOPEN; }
+    MapFile f(path);
+    if (f.err) { b->err = std::string(f.err == 1 ? "cannot open " : "cannot map ") + path; return NC_IO_EOPEN; }
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    int rc = inflate_all(b, (const uint8_t*)map, fsize, threads);
-    if (map) munmap(map, fsize);
+    int rc = inflate_all(b, f.p, f.n, threads);
     if (rc) return rc;
-    const RawBuf& d = b->data;
-    const size_t n = d.size();
-    if (n < 12 || memcmp(d.data(), "BAM\1", 4) != 0) return fail(b, "not a BAM file (bad magic)");
-    const int32_t l_text = rd<int32_t>(d.data() + 4);
-    if (l_text < 0 || 8 + (size_t)l_text + 4 > n) return fail(b, "truncated BAM header");
-    b->text.assign((const char*)d.data() + 8, (size_t)l_text);
-    size_t off = 8 + (size_t)l_text;
-    const int32_t n_ref = rd<int32_t>(d.data() + off);
-    off += 4;
-    if (n_ref < 0) return fail(b, "negative reference count");
-    b->contigs.resize((size_t)n_ref);
-    for (int32_t i = 0; i < n_ref; i++) {
-        if (off + 4 > n) return fail(b, "truncated reference list");
-        const int32_t l_name = rd<int32_t>(d.data() + off);
-        if (l_name <= 0 || off + 4 + (size_t)l_name + 4 > n) return fail(b, "truncated reference list");
-        b->contigs[i].name.assign((const char*)d.data() + off + 4, (size_t)l_name - 1);
-        b->contigs[i].length = rd<int32_t>(d.data() + off + 4 + l_name);
-        off += 8 + (size_t)l_name;
-    }
-    // record boundaries and per-contig totals
-    std::vector<std::vector<int64_t>> per((size_t)n_ref);
-    int32_t last_rid = -1, last_pos = -1;
-    while (off + 4 <= n) {
-        const int32_t bs = rd<int32_t>(d.data() + off);
-        if (bs < 32 || off + 4 + (size_t)bs > n) return fail(b, "truncated alignment record");
-        const uint8_t* r = d.data() + off + 4;
-        const int32_t rid = rd<int32_t>(r), pos = rd<int32_t>(r + 4);
-        const uint8_t l_name = r[8];
-        const uint16_t n_cig = rd<uint16_t>(r + 12);
-        const int32_t l_seq = rd<int32_t>(r + 16);
-        if (l_seq < 0 || 32 + (size_t)l_name + 4 * (size_t)n_cig + (size_t)(l_seq + 1) / 2 + (size_t)l_seq > (size_t)bs) return fail(b, "alignment record fields exceed its size");
-        if (rid >= 0 && rid < n_ref) {
-            if (rid < last_rid || (rid == last_rid && pos < last_pos)) b->sorted = false;
-            last_rid = rid; last_pos = pos;
-            Contig& c = b->contigs[(size_t)rid];
-            c.n_reads++; c.n_cigar += n_cig; c.n_seq += (l_seq + 1) / 2;
-            per[(size_t)rid].push_back((int64_t)off);
+    const int64_t first = parse_header(b, b->data.data(), b->data.size());
+    if (first < 0) return NC_IO_EFORMAT;
+    if (first == 0) return fail(b, b->data.size() < 4 || memcmp(b->data.data(), "BAM\1", 4) != 0 ? "not a BAM file (bad magic)" : "truncated BAM header");
+    std::vector<std::vector<int64_t>> per(b->contigs.size());
+    rc = scan_records(b, (size_t)first, b->data.size(), -1, per);
+    if (rc) return rc;
+    finish_index(b, per);
+    return NC_IO_OK;
+}
+
+// Region read through a BAI index: only the BGZF blocks that hold the named contigs' records are inflated (what
+// samfile.fetch(chrom, ...) does for the reference, generate_SNP_pileups.py:141,156).  The handle lists every reference of the
+// header; contigs that were not asked for report zero reads.
+int nc_bam_open_region(const char* path, const char* bai_path, const char* const* names, int n_names, int threads, nc_bam** out) {
+    if (!path || !bai_path || !out || n_names < 0 || (n_names > 0 && !names)) return NC_IO_EINVAL;
+    *out = nullptr;
+    nc_bam* b = new nc_bam();
+    *out = b;
+    MapFile f(path), x(bai_path);
+    if (f.err) { b->err = std::string("cannot open ") + path; return NC_IO_EOPEN; }
+    if (x.err) { b->err = std::string("cannot open ") + bai_path; return NC_IO_EOPEN; }
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    // ---- header: inflate leading blocks one at a time until it parses
+    std::vector<uint8_t> head;
+    {
+        size_t off = 0;
+        for (;;) {
+            std::vector<Blk> one;
+            size_t tot = 0;
+            if (off >= f.n) return fail(b, "truncated BAM header");
+            // one block: its end is found by the table walker
+            int rc = block_table(b, f.p, f.n, off, off + 1, one, tot);
+            if (rc) return rc;
+            const Blk& k = one[0];
+            const size_t at = head.size();
+            head.resize(at + k.isize);
+            if (k.isize) {
+                z_stream zs;
+                memset(&zs, 0, sizeof(zs));
+                if (inflateInit2(&zs, -15) != Z_OK) return fail(b, "inflate failed");
+                zs.next_in = const_cast<Bytef*>(f.p + k.off); zs.avail_in = (uInt)k.csize;
+                zs.next_out = head.data() + at; zs.avail_out = k.isize;
+                const int zr = inflate(&zs, Z_FINISH);
+                inflateEnd(&zs);
+                if (zr != Z_STREAM_END) return fail(b, "inflate failed (corrupt BGZF block)");
+            }
+            off = k.off + k.csize + 8;
+            const int64_t first = parse_header(b, head.data(), head.size());
+            if (first < 0) return NC_IO_EFORMAT;
+            if (first > 0) break;
         }
-        off += 4 + (size_t)bs;
     }
-    if (!b->sorted) return fail(b, "BAM is not coordinate-sorted");
-    for (int32_t i = 0; i < n_ref; i++) {
-        b->contigs[i].first_rec = (int64_t)b->rec_off.size();
-        b->rec_off.insert(b->rec_off.end(), per[i].begin(), per[i].end());
+    const int32_t n_ref = (int32_t)b->contigs.size();
+    // ---- BAI: per reference the smallest chunk begin and the largest chunk end (virtual offsets)
+    std::vector<uint64_t> vbeg((size_t)n_ref, UINT64_MAX), vend((size_t)n_ref, 0);
+    {
+        const uint8_t* p = x.p;
+        const uint8_t* e = x.p + x.n;
+        if (x.n < 8 || memcmp(p, "BAI\1", 4) != 0) return fail(b, "not a BAI index (bad magic)");
+        const int32_t nr = rd<int32_t>(p + 4);
+        p += 8;
+        if (nr != n_ref) return fail(b, "BAI index does not match the BAM header (reference count)");
+        for (int32_t i = 0; i < nr; i++) {
+            if (p + 4 > e) return fail(b, "truncated BAI index");
+            const int32_t n_bin = rd<int32_t>(p); p += 4;
+            for (int32_t k = 0; k < n_bin; k++) {
+                if (p + 8 > e) return fail(b, "truncated BAI index");
+                const uint32_t bin = rd<uint32_t>(p);
+                const int32_t n_chunk = rd<int32_t>(p + 4);
+                p += 8;
+                if (n_chunk < 0 || p + 16 * (size_t)n_chunk > e) return fail(b, "truncated BAI index");
+                if (bin != 37450)                           // the pseudo-bin carries counts, not chunks
+                    for (int32_t c = 0; c < n_chunk; c++) {
+                        vbeg[i] = std::min(vbeg[i], rd<uint64_t>(p + 16 * c));
+                        vend[i] = std::max(vend[i], rd<uint64_t>(p + 16 * c + 8));
+                    }
+                p += 16 * (size_t)n_chunk;
+            }
+            if (p + 4 > e) return fail(b, "truncated BAI index");
+            const int32_t n_intv = rd<int32_t>(p); p += 4;
+            if (n_intv < 0 || p + 8 * (size_t)n_intv > e) return fail(b, "truncated BAI index");
+            p += 8 * (size_t)n_intv;
+        }
     }
+    // ---- block tables of the requested contigs, one inflate, one record walk per contig
+    struct Seg { int32_t rid; size_t data_beg, data_end; };
+    std::vector<Seg> segs;
+    std::vector<Blk> blocks;
+    size_t total = 0;
+    for (int k = 0; k < n_names; k++) {
+        int32_t rid = -1;
+        for (int32_t i = 0; i < n_ref; i++) if (b->contigs[i].name == names[k]) { rid = i; break; }
+        if (rid < 0 || vbeg[rid] == UINT64_MAX) continue;        // unknown name or no reads: the contig stays empty
+        bool dup = false;
+        for (const Seg& sg : segs) dup |= sg.rid == rid;
+        if (dup) continue;
+        const size_t cbeg = (size_t)(vbeg[rid] >> 16), cend_blk = (size_t)(vend[rid] >> 16);
+        const uint32_t ubeg = (uint32_t)(vbeg[rid] & 0xFFFF), uend = (uint32_t)(vend[rid] & 0xFFFF);
+        if (cbeg >= f.n || cend_blk > f.n) return fail(b, "BAI index points past the end of the BAM file");
+        const size_t seg0 = total, nb0 = blocks.size();
+        int rc = block_table(b, f.p, f.n, cbeg, uend > 0 ? cend_blk + 1 : cend_blk, blocks, total);
+        if (rc) return rc;
+        // data offset of the last record's end: start of the block at cend_blk (if it was included) + uend
+        size_t end_data = total;
+        if (uend > 0) {
+            for (size_t q = nb0; q < blocks.size(); q++)
+                if (blocks[q].start == cend_blk) { end_data = blocks[q].out + uend; break; }
+        }
+        segs.push_back({rid, seg0 + ubeg, std::min(end_data, total)});
+    }
+    int rc = inflate_blocks(b, f.p, blocks, total, threads);
+    if (rc) return rc;
+    std::vector<std::vector<int64_t>> per((size_t)n_ref);
+    for (const Seg& sg : segs) {
+        if (sg.data_beg > sg.data_end) return fail(b, "BAI index is inconsistent with the BAM file");
+        rc = scan_records(b, sg.data_beg, sg.data_end, sg.rid, per);
+        if (rc) return rc;
+    }
+    finish_index(b, per);
     return NC_IO_OK;
 }
 

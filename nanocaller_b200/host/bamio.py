@@ -42,13 +42,16 @@ def bgzf_decompress(path):
         return f.read()
 
 
-def write_bam(path, readsets, header_text=None):
-    """Write coordinate-sorted ReadSets (one per contig) as a BAM file.  qual is written as 0xff (absent)."""
+def write_bam(path, readsets, header_text=None, index=False):
+    """Write coordinate-sorted ReadSets (one per contig) as a BAM file.  qual is written as 0xff (absent).
+    index=True also writes `path + ".bai"` (bins, chunks and the 16 kb linear index of the SAM specification)."""
     text = header_text or ("@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % (rs.chrom, rs.contig_len) for rs in readsets))
     parts = [b"BAM\x01", struct.pack("<i", len(text)), text.encode(), struct.pack("<i", len(readsets))]
     for rs in readsets:
         nm = rs.chrom.encode() + b"\0"
         parts += [struct.pack("<i", len(nm)), nm, struct.pack("<i", rs.contig_len)]
+    u = sum(len(p) for p in parts)
+    recs = []                                                # (rid, beg, end, bin, u_start, u_end)
     for rid, rs in enumerate(readsets):
         ends = rs.ref_end
         for i in range(rs.n):
@@ -60,12 +63,51 @@ def write_bam(path, readsets, header_text=None):
             if rs.hp[i] > 0:
                 aux = b"HPC" + struct.pack("<B", int(rs.hp[i])) + b"PSi" + struct.pack("<i", int(rs.ps[i]))
             pos = int(rs.pos[i])
-            bin_ = _reg2bin(pos, max(pos + 1, int(ends[i])))
+            end = max(pos + 1, int(ends[i]))
+            bin_ = _reg2bin(pos, end)
             core = struct.pack("<iiBBHHHiiii", rid, pos, len(name), 60, bin_, len(cig), int(rs.flag[i]), l_seq, -1, -1, 0)
             body = core + name + cig.astype("<u4").tobytes() + seq.tobytes()[:(l_seq + 1) // 2] + b"\xff" * l_seq + aux
-            parts.append(struct.pack("<i", len(body)) + body)
+            rec = struct.pack("<i", len(body)) + body
+            parts.append(rec)
+            recs.append((rid, pos, end, bin_, u, u + len(rec)))
+            u += len(rec)
+    stream = b"".join(parts)
+    blocks = [_bgzf_block(stream[off:off + 0xff00], 4) for off in range(0, len(stream), 0xff00)]
     with open(path, "wb") as f:
-        f.write(bgzf_compress(b"".join(parts)))
+        f.write(b"".join(blocks) + _BGZF_EOF)
+    if not index:
+        return
+    coff = np.concatenate([[0], np.cumsum([len(b) for b in blocks])]).astype(np.int64)
+
+    def voff(x):
+        return (int(coff[x // 0xff00]) << 16) | (x % 0xff00)
+    out = [b"BAI\x01", struct.pack("<i", len(readsets))]
+    for rid, rs in enumerate(readsets):
+        bins, linear = {}, {}
+        for r, beg, end, bin_, u0, u1 in recs:
+            if r != rid:
+                continue
+            v0, v1 = voff(u0), voff(u1)
+            ch = bins.setdefault(bin_, [])
+            if ch and ch[-1][1] == v0:
+                ch[-1][1] = v1
+            else:
+                ch.append([v0, v1])
+            for w in range(beg >> 14, ((end - 1) >> 14) + 1):
+                linear[w] = min(linear.get(w, v0), v0)
+        out.append(struct.pack("<i", len(bins)))
+        for bin_ in sorted(bins):
+            out.append(struct.pack("<Ii", bin_, len(bins[bin_])))
+            for v0, v1 in bins[bin_]:
+                out.append(struct.pack("<QQ", v0, v1))
+        n_intv = (max(linear) + 1) if linear else 0
+        out.append(struct.pack("<i", n_intv))
+        last = 0
+        for w in range(n_intv):
+            last = linear.get(w, last)
+            out.append(struct.pack("<Q", last))
+    with open(path + ".bai", "wb") as f:
+        f.write(b"".join(out))
 
 
 def _reg2bin(beg, end):
@@ -232,7 +274,7 @@ class NcBamContig(ctypes.Structure):                     # include/nanocaller_b2
                 ("n_reads", ctypes.c_int64), ("n_cigar", ctypes.c_int64), ("n_seq", ctypes.c_int64)]
 
 
-IO_EXPORTS = ["nc_bam_open", "nc_bam_error", "nc_bam_n_contigs", "nc_bam_header_text", "nc_bam_contig", "nc_bam_fill",
+IO_EXPORTS = ["nc_bam_open", "nc_bam_open_region", "nc_bam_error", "nc_bam_n_contigs", "nc_bam_header_text", "nc_bam_contig", "nc_bam_fill",
               "nc_bam_qname", "nc_bam_close"]
 
 
@@ -247,6 +289,7 @@ def load_io_library():
         lib = ctypes.CDLL(path)
         vp = ctypes.c_void_p
         lib.nc_bam_open.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(vp)]
+        lib.nc_bam_open_region.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
         lib.nc_bam_error.argtypes = [vp]; lib.nc_bam_error.restype = ctypes.c_char_p
         lib.nc_bam_n_contigs.argtypes = [vp]
         lib.nc_bam_header_text.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]; lib.nc_bam_header_text.restype = ctypes.c_void_p
@@ -258,13 +301,27 @@ def load_io_library():
     return _LIB
 
 
-def read_bam_native(path, fasta=None, contigs=None, threads=0, alloc=None, qnames=False):
+def find_bai(path):
+    for cand in (path + ".bai", os.path.splitext(path)[0] + ".bai"):
+        if os.path.exists(cand):
+            return cand
+    return None
+
+
+def read_bam_native(path, fasta=None, contigs=None, threads=0, alloc=None, qnames=False, use_index=True):
     """Same result as `read_bam`, through libnc_bamio.so: parallel BGZF inflate + parallel record copy into the
     staging arrays.  `alloc(shape, dtype)` lets the caller provide the arrays (e.g. pinned host memory for the H2D copy);
-    query names are only materialised with `qnames=True` (the device path has no use for them)."""
+    query names are only materialised with `qnames=True` (the device path has no use for them).  With `contigs` given and a
+    BAI index next to the file, only the blocks of those contigs are inflated (nc_bam_open_region)."""
     lib = load_io_library()
     h = ctypes.c_void_p()
-    rc = lib.nc_bam_open(os.fsencode(path), int(threads), ctypes.byref(h))
+    bai = find_bai(path) if (contigs is not None and use_index) else None
+    if bai:
+        names = [c.encode() for c in sorted(contigs)]
+        arr = (ctypes.c_char_p * max(1, len(names)))(*names)
+        rc = lib.nc_bam_open_region(os.fsencode(path), os.fsencode(bai), arr, len(names), int(threads), ctypes.byref(h))
+    else:
+        rc = lib.nc_bam_open(os.fsencode(path), int(threads), ctypes.byref(h))
     try:
         if rc != 0:
             msg = (lib.nc_bam_error(h) or b"").decode() if h else "open failed"

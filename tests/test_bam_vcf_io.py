@@ -181,3 +181,31 @@ def test_bam_contigs_from_header(tmp_path):
     bamio.write_bam(bam, [rs1, rs2])
     assert bamio.bam_contigs(bam) == {"chrA": 20_000, "tiny": rs2.contig_len}
     assert list(bamio.bam_contigs(bam)) == ["chrA", "tiny"]
+
+
+def test_region_read_through_bai_equals_whole_file_read(tmp_path):
+    """nc_bam_open_region (only the named contigs' BGZF blocks are inflated, located through the BAI) against the whole-file reader,
+    for every subset of contigs, with records that straddle BGZF block boundaries and a contig without reads."""
+    from nanocaller_b200.host.readset import ReadSet
+    rs1 = make_world(chrom="chrA", preset="ont", contig_len=80_000, seed=5, coverage=10.0, indel_every=900, indel_maxlen=9).reads
+    rs2 = _handmade()
+    empty = ReadSet("void", np.frombuffer(b"ACGT" * 10, np.uint8), [], [], [0], np.zeros(0, np.uint32), [0], [], np.zeros(0, np.uint8))
+    rs3 = make_world(chrom="chrB", preset="ont", contig_len=50_000, seed=6, coverage=8.0).reads
+    bam = str(tmp_path / "i.bam")
+    bamio.write_bam(bam, [rs1, rs2, empty, rs3], index=True)
+    assert os.path.getsize(bam) > 3 * 65536 and bamio.find_bai(bam) == bam + ".bai"
+    whole, text = bamio.read_bam_native(bam, use_index=False)
+    by_name = {r.chrom: r for r in whole}
+    for subset in ({"chrA"}, {"tiny"}, {"chrB"}, {"void"}, {"chrB", "tiny"}, {"chrA", "chrB", "tiny", "void"}, {"nope"}):
+        got, text_g = bamio.read_bam_native(bam, contigs=subset, threads=3)
+        assert text_g == text and sorted(g.chrom for g in got) == sorted(subset & set(by_name))
+        for g in got:
+            _same(g, by_name[g.chrom])
+            assert g.n == by_name[g.chrom].n
+    # a BAI that does not belong to the file is refused, not silently misread
+    other = str(tmp_path / "o.bam")
+    bamio.write_bam(other, [rs2], index=True)
+    os.replace(other + ".bai", bam + ".bai")
+    import pytest
+    with pytest.raises(ValueError, match="BAI"):
+        bamio.read_bam_native(bam, contigs={"chrA"})
