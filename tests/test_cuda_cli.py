@@ -15,7 +15,7 @@ def _world(tmp_path):
     a = make_world(chrom="chrA", preset="ont", contig_len=150_000, seed=11, coverage=24.0, indel_every=1500, indel_maxlen=12).reads
     y = make_world(chrom="chrY", preset="ont", contig_len=40_000, seed=12, coverage=20.0, indel_every=1500, indel_maxlen=12).reads
     bam, fa = str(tmp_path / "w.bam"), str(tmp_path / "w.fa")
-    bamio.write_bam(bam, [a, y])
+    bamio.write_bam(bam, [a, y], index=True)                 # with a BAI the command line reads only the contigs it calls
     bamio.write_fasta(fa, [a, y])
     return bam, fa, [a, y]
 
