@@ -86,3 +86,23 @@ def test_call_chunk_records_match_oracle_pipeline():
         assert fa[:5] == fb[:5] and fa[6:9] == fb[6:9], (a, b)
         assert abs(float(fa[5]) - float(fb[5])) < 0.02
         assert fa[9].split(":")[0] == fb[9].split(":")[0]
+
+
+def test_gpu_indel_path_recovers_the_truth_indels():
+    """Ground truth for the product path: GPU scan / slices / star alignment / indel CNN + host allele and genotype code on a synthetic
+    contig with known indels (exact length, zygosity)."""
+    from nanocaller_b200.host import indel_caller, snp_pileups, sources, weights as W
+    from nanocaller_b200.synth import make_world
+    from tests.test_oracle_truth import _truth_indels, score_indel_calls
+    w = make_world(chrom="chrT", preset="ont", contig_len=400_000, seed=33, coverage=30.0, indel_every=1500, indel_maxlen=12)
+    truth = _truth_indels(w)
+    sources.unregister_all()
+    snp_pileups._staged.clear()
+    sources.register_source("mem://truth", w.reads)
+    idct = dict(mincov=4, maxcov=160, seq="ont", del_t=0.6, ins_t=0.4, impute_indel_phase=False, supplementary=False, win_size=40, small_win_size=4,
+                fasta_path="mem://truth")
+    it, _ = W.load_model("indel", "ONT-HG002")
+    chunks = [{"chrom": "chrT", "start": s, "end": min(400_000, s + 100_000), "ploidy": "diploid", "sam_path": "mem://truth"} for s in range(1, 400_000, 100_000)]
+    lines = indel_caller.call_chunks(idct, chunks, it)
+    found, right = score_indel_calls(lines, truth)
+    assert len(truth) > 200 and found / len(truth) > 0.85 and right / found > 0.95 and len(lines) < 1.4 * len(truth), (found, right, len(lines), len(truth))

@@ -42,3 +42,45 @@ def test_released_model_through_the_restatement_recovers_the_truth_snps():
         if f[6] == "PASS" and p in truth and f[4] == truth[p][0]:
             right_rot += 1
     assert right_rot < 0.5 * right
+
+
+def _truth_indels(w):
+    idx = np.nonzero(w.indel & 63)[0]
+    return {int(p) + 1: (int(w.indel[p] & 63), bool(w.indel[p] & 0x40), bool(w.indel[p] & 0x80)) for p in idx}
+
+
+def score_indel_calls(lines, truth):
+    """-> (truth indels found with the exact length within the candidate window, of those with the right zygosity)."""
+    found = right = 0
+    used = set()
+    for ln in lines:
+        f = ln.split("\t")
+        p, ref, alts, gt = int(f[1]), f[3], f[4].split(","), f[9].split(":")[0]
+        for tpos, (L, ins, hom) in truth.items():
+            if tpos not in used and abs(tpos - p) <= 45 and (L if ins else -L) in [len(a) - len(ref) for a in alts]:
+                found += 1
+                used.add(tpos)
+                right += (gt == "1/1") == hom
+                break
+    return found, right
+
+
+def test_indel_restatement_with_the_own_msa_recovers_the_truth_indels():
+    """MUSCLE and parasail are replaced by this repository's own alignments (unpinnable against the reference): what can be checked
+    is that the whole indel path — scan, slices, star alignment tensors, released ONT-HG002 indel CNN, allele extraction, genotype
+    rule — finds the synthetic world's indels with the exact length and zygosity."""
+    from nanocaller_b200.host import weights as W
+    from nanocaller_b200.synth import make_world
+    from oracle import cnn_oracle, indel_caller_oracle, indel_oracle, snp_oracle
+    w = make_world(chrom="chrT", preset="ont", contig_len=80_000, seed=33, coverage=30.0, indel_every=1500, indel_maxlen=12)
+    truth = _truth_indels(w)
+    assert len(truth) >= 40
+    idct = dict(mincov=4, maxcov=160, seq="ont", del_t=0.6, ins_t=0.4, impute_indel_phase=False, supplementary=False, win_size=40, small_win_size=4)
+    it, _ = W.load_model("indel", "ONT-HG002")
+    lines = []
+    for ch in snp_oracle.get_chunks([("chrT", 1, 80_000, "diploid")], 1, 100_000):
+        pos, x0, x1, x2, alleles, phase = indel_oracle.get_indel_testing_candidates(w.reads, idct, ch)
+        if len(pos):
+            lines += indel_caller_oracle.diploid_records("chrT", pos, cnn_oracle.indel_model(it, np.hstack([x0, x1, x2]).astype(np.float32)), alleles, phase)
+    found, right = score_indel_calls(lines, truth)
+    assert found / len(truth) > 0.8 and right / found > 0.9 and len(lines) < 1.5 * len(truth), (found, right, len(lines), len(truth))
