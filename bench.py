@@ -258,7 +258,7 @@ def main():
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     ctx.event_record(0)
-    acc = {"decode_ms": 0.0, "scan_ms": 0.0, "tensor_ms": 0.0, "cnn_ms": 0.0}
+    acc = {"decode_ms": 0.0, "scan_ms": 0.0, "tensor_ms": 0.0, "cnn_ms": 0.0, "cnn_a_ms": 0.0}
     for _ in range(args.steps):
         n_sites = step_resident()
         tm = ctx.timings()
@@ -422,6 +422,16 @@ def main():
                 "peak_source": which + ", sustained bf16", "flop_per_site": FLOP_PER_SITE, "ms_per_launch_group": cnn_ms,
                 "mma_operand_model": {"cycles_per_site": mma_cycles_per_site, "floor_ms": mma_floor_ms, "frac_of_floor": mma_floor_ms / cnn_ms,
                                       "note": "N <= 128 MMAs are bound by shared-memory operand reads (32 + N/4 cycles each), not by the bf16 peak"}}
+        ta_ms = acc["cnn_a_ms"] / args.steps
+        if ta_ms > 0:
+            ta_flop = 2 * (82_000 + 82_000 + 410_000 + 737_280)                 # conv1_1 + conv1_2 + conv1_3 + conv2 MACs per site
+            ta_ach = ta_flop * n_sites / (ta_ms * 1e-3) / 1e12
+            ta_floor = (2 * 1080 + 1584) * n_sites / (148 * sm_clock * 1e6) * 1e3
+            roof["dominant_kernel"] = {"kernel": "tc_trunk_a_kernel (conv1_1 + conv1_2 + conv1_3 + conv2 of every site; %.0f %% of the step)" % (100 * ta_ms / ms_per_step),
+                                       "ms_per_launch": ta_ms, "flop_per_site": ta_flop, "achieved": ta_ach, "peak": tflops, "unit": "TFLOP/s",
+                                       "frac": ta_ach / tflops, "mma_operand_floor_ms": ta_floor, "frac_of_operand_floor": ta_floor / ta_ms,
+                                       "traffic": (tr.get("per_kernel", {}).get("tc_trunk_a_kernel", {}).get("dram_bytes", 0) / max(1, tr.get("sites", 1)) * n_sites) or None,
+                                       "algorithmic_bytes": n_sites * (2064 + 10240)}
         roof2 = {"kernel": "tensor_kernel (K2 pileup tensor build)", "bound": "hbm", "achieved": tbytes / (tensor_ms * 1e-3) / 1e9,
                  "peak": hbm, "unit": "GB/s", "frac": tbytes / (tensor_ms * 1e-3) / 1e9 / hbm,
                  "traffic": (tr["tensor_dram_bytes_per_site"] * n_sites) if "tensor_dram_bytes_per_site" in tr else None,

@@ -95,6 +95,8 @@ typedef struct NcTimings {
     uint64_t launches;       /* kernels launched by this library on this context since create */
     uint64_t tensor_bytes;   /* algorithmic bytes of the last K2 launch        */
     uint64_t scan_bytes;     /* algorithmic bytes of the last K0+K1 pass                      */
+    float    cnn_a_ms;       /* part of cnn_ms spent in the conv1+conv2 kernel (tensor-core path), else 0 */
+    float    reserved;
 } NcTimings;
 
 int         nc_abi_version(void);

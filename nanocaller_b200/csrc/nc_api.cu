@@ -70,9 +70,9 @@ struct nc_ctx {
     Model snp[2], indel[2];
     DevBuf ws_c1, ws_c2, ws_c3, ws_f1, ws_sf, ws_sd, ws_x, ws_ref, ws_out;
     // timings
-    cudaEvent_t ev[12] = {};     // 0-7 phase timings, 8-11 user slots (nc_event_record)
+    cudaEvent_t ev[13] = {};     // 0-7 phase timings, 8-11 user slots (nc_event_record), 12 end of the conv1/conv2 kernel
     NcTimings tm = {};
-    bool tm_decode = false, tm_scan = false, tm_cnn = false;
+    bool tm_decode = false, tm_scan = false, tm_cnn = false, tm_cnn_a = false;
 };
 
 namespace {
@@ -305,7 +305,7 @@ int cnn_forward(nc_ctx* c, Model& M, int impl, int in_mode, const void* in_dev, 
         return cnn_forward_f32(c, M, in_mode, in_dev, in_site_stride, n, meta, ref4, scale_f, scale_d, out_full, probs);
     uint64_t launches = 0;
     int rc = tc_forward_ex(c->stream, M.tc, in_mode, in_dev, in_site_stride, n, meta, ref4, scale_f, scale_d, tail_weights(M),
-                           out_full, probs, c->sm_count, &launches, &c->err, 0);
+                           out_full, probs, c->sm_count, &launches, &c->err, 0, c->ev[12]);
     c->launches += launches;
     return rc;
 }
@@ -396,6 +396,8 @@ int nc_get_timings(nc_ctx* c, NcTimings* out) {
         NC_CUDA(cudaEventElapsedTime(&c->tm.tensor_ms, c->ev[4], c->ev[5]));
     }
     if (c->tm_cnn) { NC_CUDA(cudaEventElapsedTime(&c->tm.cnn_ms, c->ev[6], c->ev[7])); }
+    c->tm.cnn_a_ms = 0.f;
+    if (c->tm_cnn && c->tm_cnn_a) { NC_CUDA(cudaEventElapsedTime(&c->tm.cnn_a_ms, c->ev[6], c->ev[12])); }
     c->tm.launches = c->launches;
     *out = c->tm;
     return NC_OK;
@@ -710,6 +712,7 @@ int nc_snp_forward(nc_ctx* c, int normalize, int impl, float* probs) {
     }
     NC_CUDA(cudaEventRecord(c->ev[7], c->stream));
     c->tm_cnn = true;
+    c->tm_cnn_a = n > 0 && impl == 0 && M.tc.ready;          // ev[12] was recorded after the conv1/conv2 kernel of THIS forward
     c->have_probs = true;
     if (probs && n > 0) {
         NC_CUDA(cudaMemcpyAsync(probs, c->d_probs.p, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));

@@ -1000,7 +1000,8 @@ inline int tc_model_prepare(cudaStream_t stream, TcModel& T, int kind, const flo
 // stop_after: 0 = full forward, 1 = after TA, 2 = after TB (debug entry points).
 inline int tc_forward_ex(cudaStream_t stream, TcModel& T, int in_mode, const void* in_dev, int64_t in_site_stride, int64_t n,
                          const NcSiteMeta* meta, const float* ref4, const float* scale_f, const double* scale_d, const TailW& tw,
-                         float* out_full, float* probs, int sm_count, uint64_t* launches, std::string* err, int stop_after) {
+                         float* out_full, float* probs, int sm_count, uint64_t* launches, std::string* err, int stop_after,
+                         cudaEvent_t ev_after_ta = nullptr) {
     using namespace tcg;
     if (!T.ready) return NC_ESTATE;
     if (n <= 0) return NC_OK;
@@ -1025,6 +1026,7 @@ inline int tc_forward_ex(cudaStream_t stream, TcModel& T, int in_mode, const voi
     tc_trunk_a_kernel<<<ga, TA_THREADS, TA_SMEM, stream>>>(pa);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "TA launch");
     (*launches)++;
+    if (ev_after_ta && (e = cudaEventRecord(ev_after_ta, stream)) != cudaSuccess) return cuda_fail(e, "TA event");
     if (stop_after == 1) return NC_OK;
     TBParams pb = {};
     pb.c2 = T.c2.as<uint8_t>(); pb.n_sites = n; pb.wimg = T.wimg_b.as<uint8_t>(); pb.bias = bias + 80;

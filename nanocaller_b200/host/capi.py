@@ -30,7 +30,7 @@ class NcSnpParams(ctypes.Structure):
 class NcTimings(ctypes.Structure):
     _fields_ = [("decode_ms", ctypes.c_float), ("scan_ms", ctypes.c_float), ("tensor_ms", ctypes.c_float),
                 ("cnn_ms", ctypes.c_float), ("launches", ctypes.c_uint64), ("tensor_bytes", ctypes.c_uint64),
-                ("scan_bytes", ctypes.c_uint64)]
+                ("scan_bytes", ctypes.c_uint64), ("cnn_a_ms", ctypes.c_float), ("reserved", ctypes.c_float)]
 
 
 class NcIndelParams(ctypes.Structure):
