@@ -1010,12 +1010,15 @@ inline int tc_forward_ex(cudaStream_t stream, TcModel& T, int in_mode, const voi
     const int64_t n_tiles = (n + 127) / 128;
     if ((e = T.c2.reserve((size_t)((n + 2) / 3) * C2_GROUP_BYTES)) != cudaSuccess) return cuda_fail(e, "c2 alloc");
     if ((e = T.c3.reserve((size_t)n_tiles * C3_TILE_BYTES)) != cudaSuccess) return cuda_fail(e, "c3 alloc");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};                 // function attributes are per device: one flag per ordinal (one process may open several)
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    const bool tracked = dev >= 0 && dev < 64;
+    if (!tracked || !attr_set[dev]) {
         if ((e = cudaFuncSetAttribute(tc_trunk_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM)) != cudaSuccess) return cuda_fail(e, "TA smem attr");
         if ((e = cudaFuncSetAttribute(tc_trunk_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM)) != cudaSuccess) return cuda_fail(e, "TB smem attr");
         if ((e = cudaFuncSetAttribute(tc_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)) != cudaSuccess) return cuda_fail(e, "TC smem attr");
-        attr_set = true;
+        if (tracked) attr_set[dev] = true;
     }
     const float* bias = T.bias.as<float>();
     TAParams pa = {};

@@ -112,6 +112,31 @@ def test_matches_oracle_on_fresh_world_small_maxcov(maxcov, coverage, seq):
         assert meta["sample_depth"].max() == maxcov and meta["dp"].max() > maxcov
 
 
+def test_unsorted_and_overlapping_chunks_match_oracle():
+    """The batched scan takes chunks as given: out of order, overlapping, nested and tiny ones; every chunk equals the oracle's
+    result for that chunk (runs of consecutive slots then straddle jumps in position: the generic per-site path)."""
+    from nanocaller_b200.host import snp_pileups
+    from nanocaller_b200.synth import make_world
+    from oracle import snp_oracle as O
+    from tests.golden.cases import BASE_DCT
+    rs = make_world(chrom="chrU", preset="ont", contig_len=160_000, seed=78, coverage=25.0).reads
+    dct = dict(BASE_DCT)
+    spans = [(120_001, 160_000), (1, 40_000), (30_000, 90_000), (35_000, 36_000), (159_990, 160_000), (70_000, 70_000)]
+    chunks = [{"chrom": "chrU", "start": a, "end": b, "ploidy": "diploid"} for a, b in spans]
+    ctx = _ctx()
+    snp_pileups._staged.clear()
+    snp_pileups.scan_chunks(ctx, rs, dct, chunks, "diploid")
+    mat, meta, depth, count = ctx.snp_fetch()
+    per = snp_pileups.unpack(mat, meta, depth, count, len(chunks))
+    keys = ("pos", "ref", "mat", "dp", "freq", "depth", "fwd", "rev")
+    total = 0
+    for ci, ch in enumerate(chunks):
+        w = dict(zip(keys, O.get_snp_testing_candidates(rs, dct, ch)))
+        _compare(per[ci], w, ("unsorted", ci))
+        total += len(w["pos"])
+    assert total == len(meta) > 1000
+
+
 def test_empty_inputs():
     from nanocaller_b200.host import capi, snp_pileups
     from nanocaller_b200.host.readset import ReadSet
