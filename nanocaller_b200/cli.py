@@ -212,8 +212,8 @@ def run(args):
             parts.append((grp[0]["chrom"], blob, off, ok, pos))
         allp = os.path.join(args.output, "%s.unfiltered.snps.vcf.gz" % args.prefix)
         passp = os.path.join(args.output, "%s.snps.vcf.gz" % args.prefix)
-        n_all = vcfio.write_vcf_blobs(allp, "snps", chrom_list, parts, args.sample)
-        vcfio.write_vcf_blobs(passp, "snps", chrom_list, parts, args.sample, pass_only=True)
+        n_all = vcfio.write_vcf_blobs(allp, "snps", chrom_list, parts, args.sample, index=True)      # + .csi, like tabix -fp vcf --csi (snpCaller.py:283)
+        vcfio.write_vcf_blobs(passp, "snps", chrom_list, parts, args.sample, pass_only=True, index=True)
         out.update(unfiltered_snps=allp, snps=passp, n_snp_records=n_all, snp_seconds=time.time() - t1)
         print("\n%s: SNP calling completed. Time taken= %.4f\n" % (datetime.datetime.now(), time.time() - t1), flush=True)
 
@@ -240,13 +240,13 @@ def run(args):
         for grp in _groups(chunks):                               # indelCaller.py:327-336 hands every chunk its (phased) BAM
             lines += indel_caller.call_chunks(params, [dict(c, sam_path=args.bam) for c in grp], ind, hap_tensors=hap_ind, device=args.device)
         indp = os.path.join(args.output, "%s.indels.vcf.gz" % args.prefix)
-        vcfio.write_vcf(indp, "indels", chrom_list, lines, args.sample)
+        vcfio.write_vcf(indp, "indels", chrom_list, lines, args.sample, index=True)
         out.update(indels=indp, n_indel_records=len(lines), indel_seconds=time.time() - t1)
         print("\n%s: Indel calling completed. Time taken= %.4f\n" % (datetime.datetime.now(), time.time() - t1), flush=True)
         if args.mode == "all":
             final = os.path.join(args.output, "%s.vcf.gz" % args.prefix)
             snp_lines = vcfio.read_records(out["snps"])
-            vcfio.write_vcf(final, "all", chrom_list, snp_lines + lines, args.sample)
+            vcfio.write_vcf(final, "all", chrom_list, snp_lines + lines, args.sample, index=True)
             out["final"] = final
     out.update(read_seconds=t_read, launches=ctx.timings()["launches"])
     return out

@@ -144,6 +144,13 @@ def test_write_vcf_blobs_equals_line_writer(tmp_path):
         n = vcfio.write_vcf_blobs(b, "snps", contigs, parts, "S", pass_only=pass_only)
         ta, tb = gzip.open(a, "rt").read(), gzip.open(b, "rt").read()
         assert ta == tb and n == len(sel) > 100
+        c = str(tmp_path / ("c%d.vcf.gz" % pass_only))
+        vcfio.write_vcf_blobs(c, "snps", contigs, parts, "S", pass_only=pass_only, index=True)      # the vectorised CSI path
+        assert gzip.open(c, "rt").read() == ta
+        for chrom, beg, end in (("chr1", 0, 10_000), ("chr1", 4990, 5010), ("chr2", 100, 2000), ("chr3", 0, 50), ("chr1", 8999, 9000)):
+            want = [ln for ln in sel if ln.split("\t")[0] == chrom and beg <= int(ln.split("\t")[1]) - 1 < end]
+            want = [ln for ln in vcfio.sort_records(want, contigs)]
+            assert vcfio.csi_query(c, chrom, beg, end) == want, (chrom, beg, end)
     big = os.urandom(5_000_000)
     z = bamio.bgzf_compress(big)
     p = str(tmp_path / "big.gz")
@@ -209,3 +216,46 @@ def test_region_read_through_bai_equals_whole_file_read(tmp_path):
     import pytest
     with pytest.raises(ValueError, match="BAI"):
         bamio.read_bam_native(bam, contigs={"chrA"})
+
+
+def test_csi_index_round_trip(tmp_path):
+    """write_indexed: BGZF VCF + CSI index (what `tabix -fp vcf --csi` leaves, snpCaller.py:283-285).  Region queries through the index
+    return exactly the records a linear scan finds, for SNP records and for indel records with long REF alleles spanning bin borders."""
+    import struct
+    rng = np.random.RandomState(4)
+    lines = []
+    for chrom, n in (("chr1", 6000), ("chr2", 2500)):
+        pos = np.unique(rng.randint(1, 3_000_000, n))
+        for p_ in pos:
+            if rng.rand() < 0.1:
+                ref = "A" + "".join(rng.choice(list("ACGT"), rng.randint(1, 60)))          # deletion: a long REF allele
+                lines.append("%s\t%d\t.\t%s\tA\t30.00\tPASS\t.\tGT:GQ\t1/1:30.00\n" % (chrom, p_, ref))
+            else:
+                lines.append("%s\t%d\t.\tC\tT\t12.000\tPASS\tPR=0.1,0.2,0.3,0.9;FQ=0.5\tGT:DP:VF:AD:ADF:ADR\t0/1:30:0.5:15,15:8,7:7,8\n" % (chrom, p_))
+    # a record sitting exactly on a 16 kb window border, with a REF reaching across it
+    lines.append("chr1\t%d\t.\t%s\tG\t9.00\tPASS\t.\tGT:GQ\t0|1:9.00\n" % (16384 * 7 - 2, "G" + "T" * 9))
+    contigs = ["chr1", "chr2", "chr3"]
+    data = (vcfio.header("all", contigs, "S") + "".join(vcfio.sort_records(lines, contigs))).encode()
+    path = str(tmp_path / "x.vcf.gz")
+    vcfio.write_indexed(path, data)
+    assert gzip.open(path, "rb").read() == data and len(data) > 8 * 0xff00          # several BGZF blocks: virtual offsets matter
+    idx = gzip.open(path + ".csi", "rb").read()
+    assert idx[:4] == b"CSI\x01" and struct.unpack_from("<ii", idx, 4) == (14, 5)
+    recs = [ln for ln in data.decode().splitlines(True) if not ln.startswith("#")]
+
+    def scan(chrom, beg, end):
+        out = []
+        for ln in recs:
+            f = ln.split("\t", 4)
+            b = int(f[1]) - 1
+            if f[0] == chrom and b < end and b + len(f[3]) > beg:
+                out.append(ln)
+        return out
+    regions = [("chr1", 0, 3_000_000), ("chr2", 1_000_000, 1_000_500), ("chr1", 16384 * 7 - 5, 16384 * 7 + 1), ("chr1", 16384 * 7, 16384 * 7 + 3),
+               ("chr3", 0, 1000), ("chrZ", 0, 10), ("chr2", 2_999_000, 3_100_000)]
+    regions += [("chr1", int(a), int(a) + int(rng.randint(1, 200_000))) for a in rng.randint(0, 3_000_000, 25)]
+    for chrom, beg, end in regions:
+        assert vcfio.csi_query(path, chrom, beg, end) == scan(chrom, beg, end), (chrom, beg, end)
+    # bin arithmetic against the values of the specification's own examples
+    assert vcfio._reg2bin(0, 1) == 4681 and vcfio._reg2bin(0, 16385) == 585 and vcfio._reg2bin(16384, 32768) == 4682
+    assert vcfio._bin_first_window(4681) == 0 and vcfio._bin_first_window(585) == 0 and vcfio._bin_first_window(586) == 8 and vcfio._bin_first_window(1) == 0

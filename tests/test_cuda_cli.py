@@ -64,6 +64,12 @@ def test_cli_snps_and_indels_from_files(tmp_path):
     assert res["borderline"] <= max(1, len(want) // 500)
     passed, _ = _records(out["snps"])
     assert passed == [ln for ln in got if ln.split("\t")[6] == "PASS"] and 0 < len(passed) < len(got)
+    # every output comes with its CSI index (tabix -fp vcf --csi in the reference): a region query through it equals the scan
+    import os
+    for key in ("unfiltered_snps", "snps", "indels", "final"):
+        assert os.path.exists(out[key] + ".csi"), key
+    q = vcfio.csi_query(out["unfiltered_snps"], "chrA", 50_000, 60_000)
+    assert q == [ln for ln in got if ln.startswith("chrA\t") and 50_000 <= int(ln.split("\t")[1]) - 1 < 60_000] and len(q) > 50
 
     # ---- indels: oracle pipeline over the 100 kb indel grid (HP / PS tags come from the BAM)
     idct = dict(mincov=4, maxcov=160, seq="ont", del_t=0.6, ins_t=0.4, impute_indel_phase=False, supplementary=False, win_size=40, small_win_size=4)
