@@ -10,7 +10,7 @@ using namespace nc;
 
 // mode bit0: 4 issuing warps (else 1); bit1: A start address walks (tap shifts) instead of staying put;
 // bit2: the two K groups of A are 6656 B apart (another plane) instead of adjacent-ish
-__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int mode, long long* out) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int M, int N, int iters, int mode, long long* out) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int mode
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const uint32_t a16 = smem_u32(smem) >> 4, b16 = smem_u32(smem + 96 * 1024) >> 4;
-    const uint32_t idesc = make_idesc_f16(128, N);
+    const uint32_t idesc = make_idesc_f16(M, N);
     const uint32_t a_lbo = (mode & 4) ? 416u : 105u;
     long long t0 = clock64();
     if (warp < nissue && elect_one()) {
@@ -55,14 +55,15 @@ int main() {
     long long* d; cudaMalloc(&d, 8);
     cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int iters = 4096;
-    printf("M=128 K=16 kind::f16 SS no-swizzle; cycles per MMA (148 CTAs, one per SM)\n");
+  for (int M : {128, 64}) {
+    printf("M=%d K=16 kind::f16 SS no-swizzle; cycles per MMA (148 CTAs, one per SM)\n", M);
     printf("%5s %10s %10s %10s %10s %10s\n", "N", "1w/fixed", "4w/fixed", "1w/walk", "4w/walk", "4w/walk/far");
     for (int N : {8, 16, 32, 48, 64, 96, 128}) {
         printf("%5d", N);
         for (int mode : {0, 1, 2, 3, 7}) {
             long long h = 0;
             for (int rep = 0; rep < 2; rep++) {
-                rate_kernel<<<148, 128, 200 * 1024>>>(N, iters, mode, d);
+                rate_kernel<<<148, 128, 200 * 1024>>>(M, N, iters, mode, d);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf(" err %s\n", cudaGetErrorString(e)); return 1; }
                 cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
@@ -71,5 +72,6 @@ int main() {
         }
         printf("\n");
     }
+  }
     return 0;
 }
