@@ -141,3 +141,24 @@ def test_cli_ccs_preset_regions_and_exclude_bed(tmp_path):
     res = compare_records(got, want, tol=1e-4)
     assert not res["mismatch"], res["mismatch"][:3]
     assert res["identical"] + res["numeric_only"] + res["borderline"] == len(want) > 300
+
+
+def test_cli_indels_on_an_untagged_bam_gives_empty_outputs(tmp_path):
+    """No HP tags: both haplotype depths stay below mincov (generate_indel_pileups.py:252), so the reference finds no candidates; the
+    command line must come back with header-only, indexed outputs (and say that impute_indel_phase is not built when asked for it)."""
+    from nanocaller_b200 import cli
+    from nanocaller_b200.host import bamio, snp_pileups, sources
+    from nanocaller_b200.synth import make_world
+    rs = make_world(chrom="chrN", preset="ont", contig_len=60_000, seed=13, coverage=15.0, indel_every=1500, indel_maxlen=12, untagged_frac=1.0).reads
+    assert int((rs.hp > 0).sum()) == 0
+    bam, fa = str(tmp_path / "u.bam"), str(tmp_path / "u.fa")
+    bamio.write_bam(bam, [rs], index=True)
+    bamio.write_fasta(fa, [rs])
+    sources.unregister_all()
+    snp_pileups.reset()
+    out = cli.main(["--bam", bam, "--ref", fa, "--mode", "indels", "--preset", "ccs", "--output", str(tmp_path / "o3")])
+    assert out["n_indel_records"] == 0
+    recs, txt = _records(out["indels"])
+    assert recs == [] and txt.startswith("##fileformat=VCFv4.2\n") and "##contig=<ID=chrN>" in txt
+    import os
+    assert os.path.exists(out["indels"] + ".csi")
