@@ -5,6 +5,7 @@
 #include <atomic>
 #include <thread>
 #include <cstdarg>
+#include <cstdlib>
 #include <utility>
 
 #include "nc_common.cuh"
@@ -70,10 +71,18 @@ struct nc_ctx {
     Model snp[2], indel[2];
     DevBuf ws_c1, ws_c2, ws_c3, ws_f1, ws_sf, ws_sd, ws_x, ws_ref, ws_out;
     // timings
+    cudaEvent_t ev_block = nullptr;   // blocking-sync event (NC_BLOCKING_SYNC=1), else spin on the stream
     cudaEvent_t ev[13] = {};     // 0-7 phase timings, 8-11 user slots (nc_event_record), 12 end of the conv1/conv2 kernel
     NcTimings tm = {};
     bool tm_decode = false, tm_scan = false, tm_cnn = false, tm_cnn_a = false;
 };
+
+static inline cudaError_t nc_stream_wait(nc_ctx* c) {
+    if (!c->ev_block) return cudaStreamSynchronize(c->stream);
+    cudaError_t e = cudaEventRecord(c->ev_block, c->stream);
+    return e == cudaSuccess ? cudaEventSynchronize(c->ev_block) : e;
+}
+
 
 namespace {
 
@@ -95,6 +104,9 @@ int fail(nc_ctx* c, int code, const char* fmt, ...) {
                         __FILE__, __LINE__, #call, cudaGetErrorString(e_));                        \
     } while (0)
 
+// Wait for the context's stream.  With NC_BLOCKING_SYNC=1 in the environment the host thread sleeps on an event created with
+// cudaEventBlockingSync instead of spinning (several ranks and two pipelined contexts per rank share the host's cores).  Off by
+// default: measured at 2 GPUs it does not help (39.6 against 40.6 M sites/s end to end) and costs 8 % of the resident figure.
 #define NC_LAUNCH_CHECK()                                                                          \
     do {                                                                                           \
         c->launches++;                                                                             \
@@ -125,7 +137,7 @@ int device_scan(nc_ctx* c, const int32_t* in, int64_t n, int64_t* out) {
 int read_i64(nc_ctx* c, const int64_t* dev, int64_t* out) {
     NC_CUDA(c->pin.reserve(64));
     NC_CUDA(cudaMemcpyAsync(c->pin.p, dev, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-    NC_CUDA(cudaStreamSynchronize(c->stream));
+    NC_CUDA(nc_stream_wait(c));
     *out = *c->pin.as<int64_t>();
     return NC_OK;
 }
@@ -173,7 +185,7 @@ int model_init(nc_ctx* c, Model& M, int kind, const float* blob, size_t n_floats
         rc = upload(c, M.ktab[l], tab.data(), tab.size() * sizeof(int32_t));
         if (rc) return rc;
     }
-    NC_CUDA(cudaStreamSynchronize(c->stream));     // `tab` is pageable host memory
+    NC_CUDA(nc_stream_wait(c));     // `tab` is pageable host memory
     rc = tc_model_prepare(c->stream, M.tc, kind, blob, n_floats, &c->err);
     if (rc) return rc;
     M.loaded = true;
@@ -315,7 +327,7 @@ int tc_check(nc_ctx* c, Model& M) {
     if (!M.tc.ready) return NC_OK;
     NC_CUDA(c->pin.reserve(64));
     NC_CUDA(cudaMemcpyAsync(c->pin.p, M.tc.err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    NC_CUDA(cudaStreamSynchronize(c->stream));
+    NC_CUDA(nc_stream_wait(c));
     if (*c->pin.as<int>() != 0) return fail(c, NC_ECUDA, "tensor-core CNN kernel: mbarrier wait timed out");
     return NC_OK;
 }
@@ -345,6 +357,8 @@ int nc_create(int device, nc_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NC_ECUDA; }
     for (auto& e : c->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { delete c; return NC_ECUDA; }
+    const char* bs = getenv("NC_BLOCKING_SYNC");
+    if (bs && bs[0] == '1' && cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) { delete c; return NC_ECUDA; }
     *out = c;
     return NC_OK;
 }
@@ -352,7 +366,7 @@ int nc_create(int device, nc_ctx** out) {
 void nc_destroy(nc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    nc_stream_wait(c);
     DevBuf* bufs[] = {&c->d_pos, &c->d_flag, &c->d_cigar_off, &c->d_cigar, &c->d_seq_off, &c->d_lseq, &c->d_seq4, &c->d_ref, &c->d_fill_counter, &c->d_seqc,
                       &c->d_end, &c->d_nwords, &c->d_opstart, &c->d_pmaxend, &c->d_rowoff, &c->d_rows, &c->d_flags,
                       &c->d_tile_nbr, &c->d_tile_cand, &c->d_nbr_off, &c->d_cand_off, &c->d_nbr_pos, &c->d_cand_pos, &c->d_bed,
@@ -371,6 +385,7 @@ void nc_destroy(nc_ctx* c) {
     }
     c->pin.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->ev_block) cudaEventDestroy(c->ev_block);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -380,7 +395,7 @@ const char* nc_last_error(const nc_ctx* c) { return c ? c->err.c_str() : "null c
 int nc_sync(nc_ctx* c) {
     if (!c) return NC_EINVAL;
     NC_CUDA(cudaSetDevice(c->device));
-    NC_CUDA(cudaStreamSynchronize(c->stream));
+    NC_CUDA(nc_stream_wait(c));
     return NC_OK;
 }
 
@@ -389,7 +404,7 @@ int nc_device_sm_count(nc_ctx* c) { return c ? c->sm_count : NC_EINVAL; }
 int nc_get_timings(nc_ctx* c, NcTimings* out) {
     if (!c || !out) return NC_EINVAL;
     NC_CUDA(cudaSetDevice(c->device));
-    NC_CUDA(cudaStreamSynchronize(c->stream));
+    NC_CUDA(nc_stream_wait(c));
     if (c->tm_decode) { NC_CUDA(cudaEventElapsedTime(&c->tm.decode_ms, c->ev[0], c->ev[1])); }
     if (c->tm_scan) {
         NC_CUDA(cudaEventElapsedTime(&c->tm.scan_ms, c->ev[2], c->ev[3]));
@@ -556,7 +571,7 @@ int nc_snp_scan(nc_ctx* c, const NcSnpParams* P, const NcChunk* chunks, int32_t 
     const int32_t n_merged = (int32_t)(merged.size() / 2);
     if ((rc = upload(c, c->d_bed, merged.data(), merged.size() * 4))) return rc;
     if ((rc = upload(c, c->d_chunks, chunks, (size_t)n_chunks * sizeof(NcChunk)))) return rc;
-    NC_CUDA(cudaStreamSynchronize(c->stream));     // host vectors above are pageable
+    NC_CUDA(nc_stream_wait(c));     // host vectors above are pageable
 
     const uint32_t flag_filter = P->supplementary ? 0x704u : 0xF04u;
     const int32_t lo_al = (int32_t)lo & ~7;
@@ -673,7 +688,7 @@ int nc_snp_fetch(nc_ctx* c, int16_t* mat, NcSiteMeta* meta, double* chunk_depth,
     if (meta && c->n_sites) NC_CUDA(cudaMemcpyAsync(meta, c->d_meta.p, (size_t)c->n_sites * sizeof(NcSiteMeta), cudaMemcpyDeviceToHost, c->stream));
     if (chunk_depth && c->n_chunks) NC_CUDA(cudaMemcpyAsync(chunk_depth, c->d_chunk_depth.p, (size_t)c->n_chunks * 8, cudaMemcpyDeviceToHost, c->stream));
     if (chunk_count && c->n_chunks) NC_CUDA(cudaMemcpyAsync(chunk_count, c->d_chunk_count.p, (size_t)c->n_chunks * 8, cudaMemcpyDeviceToHost, c->stream));
-    NC_CUDA(cudaStreamSynchronize(c->stream));
+    NC_CUDA(nc_stream_wait(c));
     return NC_OK;
 }
 
@@ -716,7 +731,7 @@ int nc_snp_forward(nc_ctx* c, int normalize, int impl, float* probs) {
     c->have_probs = true;
     if (probs && n > 0) {
         NC_CUDA(cudaMemcpyAsync(probs, c->d_probs.p, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        NC_CUDA(cudaStreamSynchronize(c->stream));
+        NC_CUDA(nc_stream_wait(c));
         if (impl == 0) return tc_check(c, M);
     }
     return NC_OK;
@@ -727,7 +742,7 @@ int nc_snp_fetch_probs(nc_ctx* c, float* probs) {
     if (!c->scanned || !c->have_probs) return fail(c, NC_ESTATE, "nc_snp_fetch_probs before nc_snp_forward");
     NC_CUDA(cudaSetDevice(c->device));
     if (c->n_sites) NC_CUDA(cudaMemcpyAsync(probs, c->d_probs.p, (size_t)c->n_sites * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    NC_CUDA(cudaStreamSynchronize(c->stream));
+    NC_CUDA(nc_stream_wait(c));
     return tc_check(c, c->snp[c->scan_haploid ? 1 : 0]);
 }
 
@@ -748,7 +763,7 @@ int nc_snp_model_forward(nc_ctx* c, const float* x, const float* ref_onehot, int
                          haploid ? nullptr : c->ws_out.as<float>(), haploid ? c->ws_out.as<float>() : nullptr);
     if (rc) return rc;
     NC_CUDA(cudaMemcpyAsync(out, c->ws_out.p, (size_t)n * nout * 4, cudaMemcpyDeviceToHost, c->stream));
-    NC_CUDA(cudaStreamSynchronize(c->stream));
+    NC_CUDA(nc_stream_wait(c));
     return impl == 0 ? tc_check(c, M) : NC_OK;
 }
 
@@ -766,7 +781,7 @@ int nc_indel_model_forward(nc_ctx* c, const float* x, int64_t n, int haploid, in
     int rc = cnn_forward(c, M, impl, 0, c->ws_x.p, site, n, nullptr, nullptr, nullptr, nullptr, c->ws_out.as<float>(), nullptr);
     if (rc) return rc;
     NC_CUDA(cudaMemcpyAsync(out, c->ws_out.p, (size_t)n * nout * 4, cudaMemcpyDeviceToHost, c->stream));
-    NC_CUDA(cudaStreamSynchronize(c->stream));
+    NC_CUDA(nc_stream_wait(c));
     return NC_OK;
 }
 
@@ -803,7 +818,7 @@ int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int3
         std::vector<int8_t> z8((size_t)c->n_reads, 0); std::vector<int32_t> z32((size_t)c->n_reads, 0);
         int rc0 = nc_stage_tags(c, z8.data(), z32.data());
         if (rc0) return rc0;
-        NC_CUDA(cudaStreamSynchronize(c->stream));
+        NC_CUDA(nc_stream_wait(c));
     }
     if (P->win_size < 1 || P->small_win_size < 1 || P->win_size > 190) return fail(c, NC_EINVAL, "win_size must be in 1..190");
     NC_CUDA(cudaSetDevice(c->device));
@@ -832,7 +847,7 @@ int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int3
     const int32_t n_merged = (int32_t)(merged.size() / 2);
     if ((rc = upload(c, c->d_bed, merged.data(), merged.size() * 4))) return rc;
     if ((rc = upload(c, c->d_chunks, chunks, (size_t)n_chunks * sizeof(NcChunk)))) return rc;
-    NC_CUDA(cudaStreamSynchronize(c->stream));
+    NC_CUDA(nc_stream_wait(c));
 
     const uint32_t flag_filter = P->supplementary ? 0x704u : 0xF04u;
     const int32_t lo_al = (int32_t)lo & ~7;
@@ -908,7 +923,7 @@ int nc_indel_fetch_variants(nc_ctx* c, NcIndelVariant* out) {
         if (!out) return fail(c, NC_EINVAL, "nc_indel_fetch_variants: null output");
         NC_CUDA(cudaMemcpyAsync(out, c->d_variants.p, (size_t)c->n_variants * sizeof(NcIndelVariant), cudaMemcpyDeviceToHost, c->stream));
     }
-    NC_CUDA(cudaStreamSynchronize(c->stream));
+    NC_CUDA(nc_stream_wait(c));
     return NC_OK;
 }
 
@@ -977,7 +992,7 @@ int nc_indel_fetch(nc_ctx* c, NcIndelSiteMeta* meta, float* tensors, uint8_t* cn
         if (tensors) NC_CUDA(cudaMemcpyAsync(tensors, c->d_itensors.p, n * 3 * 1280 * 4, cudaMemcpyDeviceToHost, c->stream));
         if (cns) NC_CUDA(cudaMemcpyAsync(cns, c->d_icns.p, n * 3 * NC_INDEL_CNS_MAX, cudaMemcpyDeviceToHost, c->stream));
     }
-    NC_CUDA(cudaStreamSynchronize(c->stream));
+    NC_CUDA(nc_stream_wait(c));
     return NC_OK;
 }
 
@@ -1191,7 +1206,7 @@ int nc_debug_umma(nc_ctx* c, const void* a_img, int a_bytes, const void* b_img, 
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout.p, (size_t)128 * ncols * 4, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(&herr, derr.p, 4, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) e = nc_stream_wait(c);
         if (e != cudaSuccess) { rc = fail(c, NC_ECUDA, "nc_debug_umma: %s", cudaGetErrorString(e)); break; }
         if (herr) rc = fail(c, NC_ECUDA, "nc_debug_umma: mbarrier wait timed out");
     } while (0);
@@ -1216,7 +1231,7 @@ int nc_debug_tc_trunk(nc_ctx* c, const float* x, int64_t n, int haploid, int sta
     const size_t have = stage == 1 ? (size_t)((n + 2) / 3) * tcg::C2_GROUP_BYTES : (size_t)((n + 127) / 128) * tcg::C3_TILE_BYTES;
     if (raw_bytes < have) return fail(c, NC_EINVAL, "nc_debug_tc_trunk: output buffer too small (%zu < %zu)", raw_bytes, have);
     NC_CUDA(cudaMemcpyAsync(raw, stage == 1 ? M.tc.c2.p : M.tc.c3.p, have, cudaMemcpyDeviceToHost, c->stream));
-    NC_CUDA(cudaStreamSynchronize(c->stream));
+    NC_CUDA(nc_stream_wait(c));
     return tc_check(c, M);
 }
 
