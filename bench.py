@@ -293,6 +293,9 @@ def main():
         ctx2 = capi.Context(local)
         ctx2.load_snp_weights(W.pack_snp_blob(tensors, False), meta["train_coverage"], False)
         ctxs = [ctx, ctx2]
+        blocking = world >= 4                           # 2 x N host threads on one host: sleeping waits beat spinning ones from 4 ranks on
+        for c_ in ctxs:
+            c_.set_blocking_sync(blocking)
         bufs = []
         for c in ctxs:
             tp = torch.empty((int(n_sites * 1.2) + 16, 4), dtype=torch.float32, pin_memory=True)
@@ -459,6 +462,7 @@ def main():
                        "ms_per_step": e2e_max / args.steps * 1e3, "gathered_sites": int(n_gathered),
                        "mode": ("2 contexts per GPU, H2D of one contig overlapped with kernels of the other"
                                 + ("; every step ends with the NCCL gather of its call records to rank 0" if world > 1 else "")) if pipelined else "serial",
+                       "host_waits": "blocking (cudaEventBlockingSync)" if (pipelined and world >= 4) else "spinning",
                        "serial_value": tot_sites / (e2e_serial_s / args.steps)},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_pileup": roof2, "cpu_baseline": cpu}
         if from_bam:

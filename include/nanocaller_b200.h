@@ -104,6 +104,9 @@ int         nc_create(int device, nc_ctx** out);
 void        nc_destroy(nc_ctx* ctx);
 const char* nc_last_error(const nc_ctx* ctx);
 int         nc_sync(nc_ctx* ctx);
+/* on != 0: host waits of this context sleep (cudaEventBlockingSync) instead of spinning — for hosts where several contexts /
+ * ranks share few cores (the reference's analogue is one worker process per --cpu, snpCaller.py:238).  Default: spin. */
+int         nc_set_blocking_sync(nc_ctx* ctx, int on);
 int         nc_get_timings(nc_ctx* ctx, NcTimings* out);
 int         nc_device_sm_count(nc_ctx* ctx);
 

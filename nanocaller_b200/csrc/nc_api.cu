@@ -104,9 +104,10 @@ int fail(nc_ctx* c, int code, const char* fmt, ...) {
                         __FILE__, __LINE__, #call, cudaGetErrorString(e_));                        \
     } while (0)
 
-// Wait for the context's stream.  With NC_BLOCKING_SYNC=1 in the environment the host thread sleeps on an event created with
-// cudaEventBlockingSync instead of spinning (several ranks and two pipelined contexts per rank share the host's cores).  Off by
-// default: measured at 2 GPUs it does not help (39.6 against 40.6 M sites/s end to end) and costs 8 % of the resident figure.
+// Wait for the context's stream.  After nc_set_blocking_sync(ctx, 1) (or with NC_BLOCKING_SYNC=1 in the environment) the host
+// thread sleeps on an event created with cudaEventBlockingSync instead of spinning.  Measured with 4 ranks x 2 pipelined contexts
+// on one host: 63.3 against 52.1 M sites/s end to end, at the price of 8 % of the device-resident figure (wake-up latency at
+// every host sync of a scan); neutral at 2 ranks.  Off by default.
 #define NC_LAUNCH_CHECK()                                                                          \
     do {                                                                                           \
         c->launches++;                                                                             \
@@ -340,6 +341,14 @@ int tc_check(nc_ctx* c, Model& M) {
 extern "C" {
 
 int nc_abi_version(void) { return NC_ABI_VERSION; }
+
+int nc_set_blocking_sync(nc_ctx* c, int on) {
+    if (!c) return NC_EINVAL;
+    NC_CUDA(cudaSetDevice(c->device));
+    if (on && !c->ev_block) { NC_CUDA(cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming)); }
+    if (!on && c->ev_block) { NC_CUDA(nc_stream_wait(c)); cudaEventDestroy(c->ev_block); c->ev_block = nullptr; }
+    return NC_OK;
+}
 
 int nc_create(int device, nc_ctx** out) {
     if (!out) return NC_EINVAL;

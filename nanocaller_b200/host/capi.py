@@ -13,7 +13,7 @@ NC_OK, NC_ECUDA, NC_EINVAL, NC_ESTATE, NC_ENOMEM, NC_EOVERFLOW = 0, -1, -2, -3, 
 SEQ_CODES = {"ont": 0, "short_ont": 1, "ul_ont": 2, "ul_ont_extreme": 3, "pacbio": 4}
 SITE_ELEMS, SITE_STRIDE = 1025, 1032
 
-EXPORTS = ["nc_abi_version", "nc_create", "nc_destroy", "nc_last_error", "nc_sync", "nc_get_timings",
+EXPORTS = ["nc_abi_version", "nc_create", "nc_destroy", "nc_last_error", "nc_sync", "nc_set_blocking_sync", "nc_get_timings",
            "nc_device_sm_count", "nc_event_record", "nc_event_elapsed_ms", "nc_invalidate_decode", "nc_stage_reads", "nc_decode_reads", "nc_snp_scan", "nc_snp_fetch",
            "nc_load_snp_weights", "nc_snp_forward", "nc_snp_fetch_probs", "nc_snp_model_forward", "nc_snp_device_buffers",
            "nc_load_indel_weights", "nc_indel_model_forward", "nc_stage_tags", "nc_indel_scan", "nc_indel_fetch_variants",
@@ -77,6 +77,7 @@ def load_library():
     lib.nc_last_error.argtypes = [vp]
     lib.nc_last_error.restype = ctypes.c_char_p
     lib.nc_sync.argtypes = [vp]
+    lib.nc_set_blocking_sync.argtypes = [vp, ctypes.c_int]
     lib.nc_get_timings.argtypes = [vp, ctypes.POINTER(NcTimings)]
     lib.nc_device_sm_count.argtypes = [vp]
     lib.nc_event_record.argtypes = [vp, ctypes.c_int]
@@ -312,6 +313,10 @@ class Context:
 
     def sync(self):
         self._check(self._lib.nc_sync(self._h))
+
+    def set_blocking_sync(self, on=True):
+        """Host waits sleep instead of spinning (several contexts / ranks on few host cores)."""
+        self._check(self._lib.nc_set_blocking_sync(self._h, 1 if on else 0))
 
     def timings(self):
         t = NcTimings()

@@ -165,3 +165,22 @@ def test_error_paths():
                          z2, np.zeros(0, np.uint8), np.frombuffer(b"ACGT", np.uint8))
     assert e.value.code == capi.NC_EINVAL
     ctx.close()
+
+
+def test_blocking_sync_mode_gives_the_same_results():
+    """nc_set_blocking_sync only changes how the host waits: same tensors with sleeping waits."""
+    from nanocaller_b200.host import capi
+    from nanocaller_b200.synth import make_world
+    from tests.golden.cases import BASE_DCT
+    import zlib
+    rs = make_world(chrom="chrW", preset="ont", contig_len=80_000, seed=5, coverage=20.0).reads
+    out = []
+    for on in (False, True, False):
+        ctx = capi.Context(0)
+        ctx.set_blocking_sync(on)
+        ctx.stage_reads(rs)
+        n = ctx.snp_scan(capi.snp_params(dict(BASE_DCT), "diploid"), [(1, 80_000)])
+        mat, meta, depth, count = ctx.snp_fetch()
+        out.append((n, zlib.crc32(mat.tobytes()), zlib.crc32(meta.tobytes())))
+        ctx.close()
+    assert out[0] == out[1] == out[2] and out[0][0] > 300
