@@ -3,7 +3,7 @@
 CPU restatement of the reference's diploid indel feature path over an in-memory `ReadSet`
 (paths under /root/reference/nanocaller_src/):
 
-  get_indel_testing_candidates   generate_indel_pileups.py:129-370   (impute_indel_phase branch :278-304 not restated)
+  get_indel_testing_candidates   generate_indel_pileups.py:129-370   (incl. the impute_indel_phase branch :278-304, :309-313)
   msa (tensor / consensus part)  generate_indel_pileups.py:12-73     on top of oracle/star_msa.star_msa  (stands in for MUSCLE)
   allele_prediction              generate_indel_pileups.py:77-127    on top of oracle/star_msa.nw_trace  (stands in for parasail)
 
@@ -138,9 +138,60 @@ def allele_prediction(alt, ref_seq, max_range):
     return ref_seq[:ref_out_len], alt[:alt_out_len]
 
 
-def scan_variants(rs, dct, chunk, bed_intervals=None, haploid=False):
-    """Pass 1 (generate_indel_pileups.py:213-275; haploid: generate_indel_pileups_haploid.py:199-241):
-    -> dict {key v_pos: type 0 | 1}."""
+def read_token(rs, i, p0):
+    """Upper-cased pileup string of read i at column p0 with add_indels=True (appendix C.4; generate_indel_pileups.py:279):
+    base letter / '*' / '<' '>' and, on the last column of a CIGAR op that is followed by an insertion or deletion,
+    '+L<inserted bases>' or '-L' + 'N' * L."""
+    cg = rs.read_cigar(i)
+    x, y = int(rs.pos[i]), 0
+    for k, w in enumerate(cg):
+        op, ln = int(w & 15), int(w >> 4)
+        r, q = ln * int(_REF_CONSUME[op]), ln * int(_QRY_CONSUME[op])
+        if r and x <= p0 < x + r:
+            nib = rs.read_nibbles(i)
+            if op in (0, 7, 8):
+                qi = y + (p0 - x)
+                tok = chr(_NIB[nib[qi]]) if qi < len(nib) else "N"
+            elif op == 2:
+                tok = "*"
+            else:
+                tok = "<" if (int(rs.flag[i]) & 0x10) else ">"
+            if p0 == x + r - 1:
+                L = dict(read_events(rs, i)).get(p0, 0)
+                if L > 0:
+                    qn = y + q                                   # P ops between the insertions consume no query
+                    tok += "+%d%s" % (L, _NIB[nib[qn:qn + L]].tobytes().decode())
+                elif L < 0:
+                    tok += "-%d%s" % (-L, "N" * (-L))
+            return tok
+        x += r
+        y += q
+    raise ValueError("position not covered")
+
+
+def impute_column(tokens, mincov):
+    """generate_indel_pileups.py:287-300 for one column: `tokens` = upper-cased pileup strings in pileup order.
+    -> None, or (indices of read_names_0, indices of read_names_1)."""
+    n = len(tokens)
+    groups = {}
+    for k, s in enumerate(tokens):
+        groups.setdefault(s, []).append(k)
+    counts = sorted([(x, len(groups[x])) for x in groups], key=lambda x: x[1], reverse=True)
+    if counts[0][1] <= 0.8 * n:
+        names0 = list(groups[counts[0][0]])
+        names1 = list(groups[counts[1][0]]) if counts[1][1] >= mincov else [k for k in range(n) if k not in set(names0)]
+    else:
+        names0 = groups[counts[0][0]][:counts[0][1] // 2]
+        names1 = groups[counts[0][0]][counts[0][1] // 2:]
+    if len(names0) >= mincov and len(names1) >= mincov:
+        return names0, names1
+    return None
+
+
+def scan_variants(rs, dct, chunk, bed_intervals=None, haploid=False, extra_out=None):
+    """Pass 1 (generate_indel_pileups.py:213-304; haploid: generate_indel_pileups_haploid.py:199-241):
+    -> dict {key v_pos: type 0 | 1}.  With dct['impute_indel_phase'], `extra_out` (a dict) receives
+    extra_variants {key: (read indices of read_names_0, of read_names_1)} (:278-304)."""
     start, end = chunk["start"], chunk["end"]
     W, SW = dct["win_size"], dct["small_win_size"]
     mincov, ins_t, del_t = dct["mincov"], dct["ins_t"], dct["del_t"]
@@ -152,9 +203,23 @@ def scan_variants(rs, dct, chunk, bed_intervals=None, haploid=False):
     adm = np.nonzero(((rs.flag & flag) == 0) & (rs.pos < hi) & (rs.ref_end > lo) & (rs.ref_end > rs.pos))[0]
     depth = np.zeros((3, n + 1), np.int64)           # hap0, hap1, all
     ev_pos = {k: [] for k in range(8)}               # (hap, kind) -> list of (rank-space handled later) (p0, read)
+    impute = bool(dct.get("impute_indel_phase")) and not haploid
+    col_del = np.zeros(n + 1, np.int64)              # '*' and '-' characters among the first two of every read's string (:283)
+    col_ins = np.zeros(n + 1, np.int64)              # '+' characters
     for i in adm:
         a, b = max(lo, int(rs.pos[i])) - lo, min(hi, int(rs.ref_end[i])) - lo
         depth[2, a] += 1; depth[2, b] -= 1
+        if impute:
+            cg = rs.read_cigar(int(i))
+            x = int(rs.pos[i])
+            for w in cg:
+                op, ln = int(w & 15), int(w >> 4)
+                if op == 2:
+                    col_del[max(lo, x) - lo:max(0, min(hi, x + ln) - lo)] += 1
+                x += ln * int(_REF_CONSUME[op])
+            for p0, L in read_events(rs, int(i)):
+                if lo <= p0 < hi:
+                    (col_del if L < 0 else col_ins)[p0 - lo] += 1
         h = 0 if haploid else int(rs.hp[i]) - 1
         if h in (0, 1):
             depth[h, a] += 1; depth[h, b] -= 1
@@ -225,6 +290,18 @@ def scan_variants(rs, dct, chunk, bed_intervals=None, haploid=False):
             elif max([dels0, dels1]) >= del_t or max([inss0, inss1]) >= ins_t or (dels0 + inss0) >= 0.9 or (dels1 + inss1) >= 0.9:
                 prev = v_pos + 10
                 variants[max(1, v_pos - 10)] = 1
+        elif impute and int(depth[2, c]) >= 2 * mincov:                      # :278
+            ltot = int(depth[2, c])
+            if del_t <= col_del[c] / ltot or ins_t <= col_ins[c] / ltot:     # :283-285
+                p0 = lo + int(c)
+                cov = [int(i) for i in adm if rs.pos[i] <= p0 < rs.ref_end[i]]
+                assert len(cov) == ltot
+                got = impute_column([read_token(rs, i, p0) for i in cov], mincov)
+                if got is not None:
+                    prev = v_pos + 10
+                    variants[max(1, v_pos - 10)] = 1
+                    if extra_out is not None:
+                        extra_out[max(1, v_pos - 10)] = ([cov[k] for k in got[0]], [cov[k] for k in got[1]])
     return variants
 
 
@@ -263,7 +340,8 @@ def get_indel_testing_candidates(rs, dct, chunk, bed_intervals=None):
     """generate_indel_pileups.py:129-370 -> (pos, x0, x1, x2, alleles, phase)."""
     W = dct["win_size"]
     max_range = {0: max(10, W), 1: 10}
-    variants = scan_variants(rs, dct, chunk, bed_intervals)
+    extra = {}
+    variants = scan_variants(rs, dct, chunk, bed_intervals, extra_out=extra)
     pos, X0, X1, X2, alleles, phase = [], [], [], [], [], []
     for v_pos in sorted(variants):
         ss = site_slices(rs, dct, chunk, v_pos)
@@ -271,14 +349,19 @@ def get_indel_testing_candidates(rs, dct, chunk, bed_intervals=None):
             continue
         ref, reads = ss
         tot = [s for _, _, s in reads]
-        h0 = [(i, s) for i, hp, s in reads if hp == 1]
-        h1 = [(i, s) for i, hp, s in reads if hp == 2]
+        if v_pos in extra:                                                   # :309-313: the imputed read sets win over the HP tags
+            n0, n1 = set(extra[v_pos][0]), set(extra[v_pos][1])
+            h0 = [(i, s) for i, hp, s in reads if i in n0]
+            h1 = [(i, s) for i, hp, s in reads if i not in n0 and i in n1]
+        else:
+            h0 = [(i, s) for i, hp, s in reads if hp == 1]
+            h1 = [(i, s) for i, hp, s in reads if hp == 2]
         f0, d0, a0, r0 = msa_tensor([s for _, s in h0], ref, 2, dct["maxcov"])
         f1, d1, a1, r1 = msa_tensor([s for _, s in h1], ref, 2, dct["maxcov"])
         ft, dt, at, rt = msa_tensor(tot, ref, dct["mincov"], dct["maxcov"])
         if f0 and f1 and ft:
             pos.append(v_pos); X0.append(d0); X1.append(d1); X2.append(dt)
-            phase.append(int(rs.ps[h0[0][0]]))
+            phase.append(int(rs.ps[h0[0][0]]) if rs.hp[h0[0][0]] > 0 else None)     # phase_dict (:180-186): None without an HP tag
             mr = max_range[variants[v_pos]]
             alleles.append([allele_prediction(a0, r0, mr), allele_prediction(a1, r1, mr), allele_prediction(at, rt, mr)])
     if not pos:

@@ -23,6 +23,14 @@ INDEL_CASES = {
     "indel_haploid": (lambda: _world(chrom="chrX", preset="ont", contig_len=40_000, seed=43, coverage=30.0, indel_every=1200, indel_maxlen=20,
                                      het_every=0, hom_every=0, sys_per_10k=0, ploidy=1),
                       {"del_t": 0.5}, [("chrX", 1, 40_000, "haploid")], 1, 100000),
+    # impute_indel_phase (generate_indel_pileups.py:278-304): most reads carry no HP tag, so most columns lack phased coverage and
+    # the read sets come from grouping the pileup strings of the column
+    "indel_impute_hifi": (lambda: _world(chrom="chr3", preset="hifi", contig_len=40_000, seed=44, coverage=32.0, indel_every=800, indel_maxlen=30,
+                                         het_every=0, hom_every=0, sys_per_10k=0, untagged_frac=0.8),
+                          {"seq": "pacbio", "ins_t": 0.4, "del_t": 0.4, "impute_indel_phase": True}, [("chr3", 1, 40_000, "diploid")], 2, 100000),
+    "indel_impute_ont": (lambda: _world(chrom="chr4", preset="ont", contig_len=30_000, seed=45, coverage=30.0, indel_every=700, indel_maxlen=12,
+                                        het_every=0, hom_every=0, sys_per_10k=0, untagged_frac=1.0),
+                         {"ins_t": 0.3, "del_t": 0.4, "impute_indel_phase": True}, [("chr4", 1, 30_000, "diploid")], 1, 100000),
 }
 
 
