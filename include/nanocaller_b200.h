@@ -200,13 +200,15 @@ typedef struct NcIndelParams {
     int32_t window_after;            /* 160, or 260 for dct['seq'] == 'pacbio' (:136-139)           */
     int32_t supplementary;
     int32_t haploid;                 /* generate_indel_pileups_haploid.py: one window set / one MSA over all reads */
-    int32_t reserved;
+    int32_t impute_indel_phase;      /* dct['impute_indel_phase'] (:278-304); ignored by the haploid caller */
 } NcIndelParams;
 
-typedef struct NcIndelVariant { int32_t key, type, chunk; } NcIndelVariant;   /* variants[key] = type (:268,:274) */
+/* variants[key] = type (:268,:274,:301).  src = 0, or for a candidate found by impute_indel_phase the 1-based column whose
+ * pileup strings define the two read sets (extra_variants[key], :302); nc_indel_build recomputes the sets from that column. */
+typedef struct NcIndelVariant { int32_t key, type, chunk, src; } NcIndelVariant;
 
 typedef struct NcIndelSiteMeta {
-    int32_t pos, chunk, type, phase, ref_len;
+    int32_t pos, chunk, type, phase, ref_len;   /* phase: PS of the first hap0 read; -1 = that read has no HP tag (imputed sites) */
     int32_t n[3];                    /* reads used per group: HP1, HP2, all                         */
     int32_t cns_len[3];
     int32_t ok[3];                   /* msa() flag per group (:48)                                  */

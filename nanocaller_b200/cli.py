@@ -222,12 +222,6 @@ def run(args):
         params = dict(sam_path=args.bam, fasta_path=args.ref, mincov=args.mincov, maxcov=args.maxcov, seq=args.sequencing,
                       del_t=args.del_threshold, ins_t=args.ins_threshold, impute_indel_phase=args.impute_indel_phase,
                       supplementary=args.supplementary, exclude_bed=exclude, win_size=args.win_size, small_win_size=args.small_win_size)
-        if args.impute_indel_phase:
-            # generate_indel_pileups.py:278-304 (pseudo-phasing by allele clustering where phased depth is missing) is not built:
-            # such columns are skipped, exactly as they are with the flag off.  Said loudly, because `--preset ccs` sets the flag.
-            print("\n%s: WARNING --impute_indel_phase is not implemented in nanocaller_b200; columns without phased coverage are skipped."
-                  % datetime.datetime.now(), flush=True)
-            params["impute_indel_phase"] = False
         ind = models.get_indel_model(args.indel_model, args.nanocaller_src)
         if ind is None:
             print("Invalid indel model name or path", flush=True)

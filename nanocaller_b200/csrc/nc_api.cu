@@ -65,6 +65,9 @@ struct nc_ctx {
     bool tags_staged = false, indel_scanned = false, indel_built = false;
     DevBuf d_hp, d_ps, d_idepth, d_em, d_grank, d_empos, d_ichunks, d_nem1, d_rankoff, d_diff, d_uscan, d_hit, d_variants, d_icount;
     DevBuf d_isites, d_site_m, d_site_cnt, d_site_off, d_eread, d_eqpn, d_eslice, d_eacode, d_einslen, d_einsfirst, d_en, d_itensors, d_icns, d_imeta;
+    // impute_indel_phase: per-column indel marks, pending / source columns and their grouped reads
+    DevBuf d_cdel, d_cins, d_imp_g, d_imp_cols, d_imp_cnt, d_imp_off, d_imp_read, d_imp_ch, d_imp_ind, d_imp_qn, d_imp_gid, d_imp_rep, d_imp_gcnt,
+           d_imp_label, d_imp_ok, d_site_imp, d_egrp;
     int64_t n_variants = 0, n_isites = 0, indel_R = 0;
     int32_t indel_lo_al = 0;
     // CNN
@@ -385,6 +388,8 @@ void nc_destroy(nc_ctx* c) {
                       &c->d_hp, &c->d_ps, &c->d_idepth, &c->d_em, &c->d_grank, &c->d_empos, &c->d_ichunks, &c->d_nem1, &c->d_rankoff, &c->d_diff,
                       &c->d_uscan, &c->d_hit, &c->d_variants, &c->d_icount, &c->d_isites, &c->d_site_m, &c->d_site_cnt, &c->d_site_off, &c->d_eread,
                       &c->d_eqpn, &c->d_eslice, &c->d_eacode, &c->d_einslen, &c->d_einsfirst, &c->d_en, &c->d_itensors, &c->d_icns, &c->d_imeta,
+                      &c->d_cdel, &c->d_cins, &c->d_imp_g, &c->d_imp_cols, &c->d_imp_cnt, &c->d_imp_off, &c->d_imp_read, &c->d_imp_ch, &c->d_imp_ind,
+                      &c->d_imp_qn, &c->d_imp_gid, &c->d_imp_rep, &c->d_imp_gcnt, &c->d_imp_label, &c->d_imp_ok, &c->d_site_imp, &c->d_egrp,
                       &c->ws_c1, &c->ws_c2, &c->ws_c3, &c->ws_f1, &c->ws_sf, &c->ws_sd, &c->ws_x, &c->ws_ref, &c->ws_out};
     for (DevBuf* b : bufs) b->release();
     for (Model* m : {&c->snp[0], &c->snp[1], &c->indel[0], &c->indel[1]}) {
@@ -817,6 +822,35 @@ int nc_stage_tags(nc_ctx* c, const int8_t* hp, const int32_t* ps) {
     return NC_OK;
 }
 
+// impute_indel_phase (generate_indel_pileups.py:287-300) for the columns listed in c->d_imp_cols: reads of every column in BAM
+// order (d_imp_off / d_imp_read), their read-set labels (d_imp_label) and the `both sets >= mincov` flag (d_imp_ok).
+static int impute_columns(nc_ctx* c, const NcIndelParams* P, int64_t n_cols) {
+    int rc;
+    NC_CUDA(c->d_imp_cnt.reserve((size_t)n_cols * 4));
+    NC_CUDA(c->d_imp_off.reserve((size_t)(n_cols + 1) * 8));
+    NC_CUDA(c->d_imp_ok.reserve((size_t)n_cols * 4));
+    ImputeArgs ia = {};
+    ia.n_reads = c->n_reads; ia.pos = c->d_pos.as<int32_t>(); ia.end = c->d_end.as<int32_t>(); ia.flag = c->d_flag.as<uint16_t>();
+    ia.pmaxend = c->d_pmaxend.as<int32_t>(); ia.cigar_off = c->d_cigar_off.as<int64_t>(); ia.cigar = c->d_cigar.as<uint32_t>();
+    ia.opstart = c->d_opstart.as<int2>(); ia.seq_off = c->d_seq_off.as<int64_t>(); ia.l_seq = c->d_lseq.as<int32_t>(); ia.seq4 = c->d_seq4.as<uint8_t>();
+    ia.flag_filter = P->supplementary ? 0x704u : 0xF04u; ia.mincov = P->mincov;
+    ia.cols = c->d_imp_cols.as<int32_t>(); ia.n_cols = n_cols; ia.col_cnt = c->d_imp_cnt.as<int32_t>(); ia.col_off = c->d_imp_off.as<int64_t>();
+    ia.col_ok = c->d_imp_ok.as<int32_t>();
+    const unsigned wg = (unsigned)div_up(n_cols * 32, 128);
+    indel_impute_reads_kernel<false><<<wg, 128, 0, c->stream>>>(ia); NC_LAUNCH_CHECK();
+    if ((rc = device_scan(c, ia.col_cnt, n_cols, c->d_imp_off.as<int64_t>()))) return rc;
+    int64_t n_entries = 0;
+    if ((rc = read_i64(c, c->d_imp_off.as<int64_t>() + n_cols, &n_entries))) return rc;
+    const size_t ne = (size_t)std::max<int64_t>(n_entries, 1);
+    NC_CUDA(c->d_imp_read.reserve(ne * 4)); NC_CUDA(c->d_imp_ch.reserve(ne)); NC_CUDA(c->d_imp_ind.reserve(ne * 4)); NC_CUDA(c->d_imp_qn.reserve(ne * 4));
+    NC_CUDA(c->d_imp_gid.reserve(ne * 4)); NC_CUDA(c->d_imp_rep.reserve(ne * 4)); NC_CUDA(c->d_imp_gcnt.reserve(ne * 4)); NC_CUDA(c->d_imp_label.reserve(ne));
+    ia.e_read = c->d_imp_read.as<int32_t>(); ia.e_ch = c->d_imp_ch.as<uint8_t>(); ia.e_ind = c->d_imp_ind.as<int32_t>(); ia.e_qn = c->d_imp_qn.as<int32_t>();
+    ia.e_gid = c->d_imp_gid.as<int32_t>(); ia.g_rep = c->d_imp_rep.as<int32_t>(); ia.g_cnt = c->d_imp_gcnt.as<int32_t>(); ia.e_label = c->d_imp_label.as<int8_t>();
+    indel_impute_reads_kernel<true><<<wg, 128, 0, c->stream>>>(ia); NC_LAUNCH_CHECK();
+    indel_impute_group_kernel<<<(unsigned)div_up(n_cols, 64), 64, 0, c->stream>>>(ia); NC_LAUNCH_CHECK();
+    return NC_OK;
+}
+
 int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int32_t n_chunks, const int32_t* bed, int32_t n_bed,
                   int64_t* n_variants) {
     if (!c || !P || !n_variants || n_chunks < 0 || (n_chunks > 0 && !chunks) || n_bed < 0 || (n_bed > 0 && !bed))
@@ -910,7 +944,34 @@ int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int3
     dd.chunks = c->d_ichunks.as<IndelChunk>(); dd.n_chunks = n_chunks; dd.R = R; dd.uscan = c->d_uscan.as<int64_t>(); dd.em_pos = c->d_empos.as<int32_t>();
     dd.depth = c->d_idepth.as<uint16_t>(); dd.n_al = n_al; dd.lo_al = lo_al; dd.mincov = P->mincov; dd.haploid = P->haploid; dd.ins_t = P->ins_t; dd.del_t = P->del_t;
     dd.hit = c->d_hit.as<uint8_t>(); dd.n_hits = c->d_icount.as<unsigned long long>();
+    const bool impute = P->impute_indel_phase && !P->haploid;
+    if (impute) {
+        NC_CUDA(c->d_cdel.reserve((size_t)n_al * 4)); NC_CUDA(c->d_cins.reserve((size_t)n_al * 4));
+        NC_CUDA(cudaMemsetAsync(c->d_cdel.p, 0, (size_t)n_al * 4, c->stream));
+        NC_CUDA(cudaMemsetAsync(c->d_cins.p, 0, (size_t)n_al * 4, c->stream));
+        ImputeCountArgs ic = {};
+        ic.n_reads = c->n_reads; ic.pos = da.pos; ic.end = da.end; ic.flag = da.flag; ic.cigar_off = ea.cigar_off; ic.cigar = ea.cigar;
+        ic.lo_al = lo_al; ic.lo = (int32_t)lo; ic.hi = (int32_t)hi; ic.flag_filter = flag_filter;
+        ic.cdel = c->d_cdel.as<int32_t>(); ic.cins = c->d_cins.as<int32_t>();
+        indel_impute_count_kernel<<<(unsigned)div_up(c->n_reads, 128), 128, 0, c->stream>>>(ic); NC_LAUNCH_CHECK();
+        dd.impute = 1; dd.cdel = ic.cdel; dd.cins = ic.cins;
+    }
     indel_decide_kernel<<<(unsigned)div_up(R, 256), 256, 0, c->stream>>>(dd); NC_LAUNCH_CHECK();
+    if (impute) {
+        int64_t n_pending = 0;
+        if ((rc = read_i64(c, c->d_icount.as<int64_t>() + 2, &n_pending))) return rc;
+        if (n_pending > 0) {
+            NC_CUDA(c->d_imp_g.reserve((size_t)n_pending * 8)); NC_CUDA(c->d_imp_cols.reserve((size_t)n_pending * 4));
+            indel_impute_collect_kernel<<<(unsigned)div_up(R, 256), 256, 0, c->stream>>>(c->d_hit.as<uint8_t>(), R, c->d_ichunks.as<IndelChunk>(), n_chunks,
+                                                                                       c->d_empos.as<int32_t>(), c->d_imp_g.as<int64_t>(), c->d_imp_cols.as<int32_t>(),
+                                                                                       c->d_icount.as<unsigned long long>() + 3);
+            NC_LAUNCH_CHECK();
+            if ((rc = impute_columns(c, P, n_pending))) return rc;
+            indel_impute_apply_kernel<<<(unsigned)div_up(n_pending, 256), 256, 0, c->stream>>>(c->d_imp_g.as<int64_t>(), c->d_imp_ok.as<int32_t>(), n_pending,
+                                                                                             c->d_hit.as<uint8_t>(), c->d_icount.as<unsigned long long>());
+            NC_LAUNCH_CHECK();
+        }
+    }
     int64_t n_hits = 0;
     if ((rc = read_i64(c, c->d_icount.as<int64_t>(), &n_hits))) return rc;
     NC_CUDA(c->d_variants.reserve((size_t)std::max<int64_t>(n_hits, 1) * sizeof(NcIndelVariant)));
@@ -947,6 +1008,22 @@ int nc_indel_build(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int
     if (n_sites == 0) { c->indel_built = true; return NC_OK; }
     for (int64_t i = 0; i < n_sites; i++)
         if (sites[i].chunk < 0 || sites[i].chunk >= n_chunks) return fail(c, NC_EINVAL, "site %lld names chunk %d of %d", (long long)i, sites[i].chunk, n_chunks);
+    // sites found by impute_indel_phase: recompute the two read sets from the source column (generate_indel_pileups.py:309-313)
+    std::vector<int32_t> site_imp((size_t)n_sites, -1), imp_cols;
+    for (int64_t i = 0; i < n_sites; i++) {
+        if (sites[i].src == 0) continue;
+        const int64_t p = (int64_t)sites[i].src - 1;
+        if (p < c->ref_start || p >= c->ref_start + c->ref_len) return fail(c, NC_EINVAL, "site %lld: source column %d outside the staged reference", (long long)i, sites[i].src);
+        site_imp[(size_t)i] = (int32_t)imp_cols.size();
+        imp_cols.push_back((int32_t)p);
+    }
+    const bool any_imp = !imp_cols.empty();
+    if (any_imp) {
+        if ((rc = upload(c, c->d_imp_cols, imp_cols.data(), imp_cols.size() * 4))) return rc;
+        if ((rc = upload(c, c->d_site_imp, site_imp.data(), site_imp.size() * 4))) return rc;
+        NC_CUDA(nc_stream_wait(c));                       // the host vectors go out of use before the next blocking call anyway; keep it simple
+        if ((rc = impute_columns(c, P, (int64_t)imp_cols.size()))) return rc;
+    }
     if ((rc = upload(c, c->d_chunks, chunks, (size_t)n_chunks * sizeof(NcChunk)))) return rc;
     if ((rc = upload(c, c->d_isites, sites, (size_t)n_sites * sizeof(NcIndelVariant)))) return rc;
     NC_CUDA(c->d_site_m.reserve((size_t)n_sites * 4));
@@ -968,13 +1045,17 @@ int nc_indel_build(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int
     int64_t n_entries = 0;
     if ((rc = read_i64(c, c->d_site_off.as<int64_t>() + n_sites, &n_entries))) return rc;
     const size_t ne = (size_t)std::max<int64_t>(n_entries, 1);
-    NC_CUDA(c->d_eread.reserve(ne * 4)); NC_CUDA(c->d_eqpn.reserve(ne * 4)); NC_CUDA(c->d_en.reserve(ne * 4));
+    NC_CUDA(c->d_eread.reserve(ne * 4)); NC_CUDA(c->d_eqpn.reserve(ne * 4)); NC_CUDA(c->d_en.reserve(ne * 4)); NC_CUDA(c->d_egrp.reserve(ne));
     NC_CUDA(c->d_eslice.reserve(ne * sa.nmax)); NC_CUDA(c->d_eacode.reserve(ne * sa.mmax));
     NC_CUDA(c->d_einslen.reserve(ne * (sa.mmax + 1) * 2)); NC_CUDA(c->d_einsfirst.reserve(ne * (sa.mmax + 1) * 2));
     NC_CUDA(c->d_itensors.reserve((size_t)n_sites * 3 * 1280 * 4));
     NC_CUDA(c->d_icns.reserve((size_t)n_sites * 3 * NC_INDEL_CNS_MAX));
     NC_CUDA(c->d_imeta.reserve((size_t)n_sites * sizeof(NcIndelSiteMeta)));
-    sa.e_read = c->d_eread.as<int32_t>(); sa.e_qpn = c->d_eqpn.as<int32_t>(); sa.e_n = c->d_en.as<int32_t>();
+    sa.e_read = c->d_eread.as<int32_t>(); sa.e_qpn = c->d_eqpn.as<int32_t>(); sa.e_n = c->d_en.as<int32_t>(); sa.e_grp = c->d_egrp.as<int8_t>();
+    if (any_imp) {
+        sa.site_imp = c->d_site_imp.as<int32_t>(); sa.imp_off = c->d_imp_off.as<int64_t>();
+        sa.imp_read = c->d_imp_read.as<int32_t>(); sa.imp_label = c->d_imp_label.as<int8_t>();
+    }
     sa.e_slice = c->d_eslice.as<uint8_t>(); sa.e_acode = c->d_eacode.as<uint8_t>(); sa.e_inslen = c->d_einslen.as<uint16_t>();
     sa.e_insfirst = c->d_einsfirst.as<uint16_t>(); sa.tensors = c->d_itensors.as<float>(); sa.cns = c->d_icns.as<uint8_t>();
     sa.meta = c->d_imeta.as<NcIndelSiteMeta>();

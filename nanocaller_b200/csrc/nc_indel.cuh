@@ -6,7 +6,9 @@
 //   I3 msa       MUSCLE is an external binary (:30); this library aligns every slice to the reference window with its
 //                own, fully specified star alignment (oracle/star_msa.py states it) and builds the column-frequency
 //                tensors and the consensus exactly as `msa` does (:54-71)
-// The impute_indel_phase branch (:278-304) is not built.
+//   I1 impute   impute_indel_phase (:278-304): columns without phased coverage on both haplotypes whose pileup strings carry
+//                enough indel marks are split into two read sets by grouping equal strings; pass 2 then uses those sets in
+//                place of the HP tags (:309-313)
 #pragma once
 #include "nc_common.cuh"
 #include "nc_pileup.cuh"
@@ -223,6 +225,8 @@ struct DecideArgs {
     const int32_t* em_pos; const uint16_t* depth; int64_t n_al; int32_t lo_al;
     int32_t mincov, haploid; double ins_t, del_t;
     uint8_t* hit; unsigned long long* n_hits;
+    // impute_indel_phase (:278-285): per-column indel marks of all reads; pending columns get hit 4 and are counted in n_hits[2]
+    int32_t impute; const int32_t* cdel; const int32_t* cins;
 };
 __global__ void indel_decide_kernel(const DecideArgs a) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -253,10 +257,17 @@ __global__ void indel_decide_kernel(const DecideArgs a) {
             }
             if (fmax(f[0], f[4]) >= a.del_t || fmax(f[2], f[6]) >= a.ins_t) hit = 1;
             else if (fmax(f[1], f[5]) >= a.del_t || fmax(f[3], f[7]) >= a.ins_t || (f[1] + f[3]) >= 0.9 || (f[5] + f[7]) >= 0.9) hit = 2;
+        } else if (a.impute) {
+            const int32_t lt = a.depth[2 * a.n_al + pi];
+            if (lt > 0 && lt >= 2 * a.mincov) {
+                const double fd = (double)a.cdel[pi] / (double)lt, fi = (double)a.cins[pi] / (double)lt;
+                if (a.del_t <= fd || a.ins_t <= fi) hit = 4;
+            }
         }
     }
     a.hit[g] = hit;
-    if (hit) atomicAdd(a.n_hits, 1ull);
+    if (hit == 4) atomicAdd(a.n_hits + 2, 1ull);
+    else if (hit) atomicAdd(a.n_hits, 1ull);
 }
 
 // I1.4 greedy pass with `prev` (:249,267,273): one warp per chunk walks its columns in order.
@@ -282,7 +293,8 @@ __global__ void indel_greedy_kernel(const IndelChunk* __restrict__ chunks, int32
             prev = vl + back;
             if (lane == 0) {
                 const unsigned long long slot = atomicAdd(n_out, 1ull);
-                NcIndelVariant nv; nv.key = max(1, vl - back); nv.type = hl - 1; nv.chunk = c;
+                NcIndelVariant nv; nv.key = max(1, vl - back); nv.type = hl == 1 ? 0 : 1; nv.chunk = c;
+                nv.src = hl == 3 ? vl : 0;             // extra_variants: the read sets come from this column (:302)
                 out[slot] = nv;
             }
         }
@@ -305,6 +317,9 @@ struct SiteArgs {
     int32_t* site_cnt;         // covering reads per site
     const int64_t* site_off;   // [n_sites+1] entry offsets
     int32_t* e_read; int32_t* e_qpn;
+    int8_t* e_grp;             // read group of the entry: 0 / 1 (HP 1 / 2, or the imputed read sets of the site), -1 neither
+    // imputed sites (:309-313): site_imp[s] = index of the site's source column in the imputed-column tables, or -1
+    const int32_t* site_imp; const int64_t* imp_off; const int32_t* imp_read; const int8_t* imp_label;
     // alignment outputs, stride per entry
     uint8_t* e_slice; uint8_t* e_acode; uint16_t* e_inslen; uint16_t* e_insfirst; int32_t* e_n;
     int32_t nmax, mmax;
@@ -321,6 +336,206 @@ __device__ __forceinline__ void read_window(const int32_t* pos, const int32_t* p
     int64_t lo = 0, hi = ihi;
     while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (__ldg(pmaxend + mid) <= p) lo = mid + 1; else hi = mid; }
     ilo = lo;
+}
+
+// Indel annotation of the pileup string on the LAST column of reference-consuming op k (appendix C.4): > 0 inserted bases
+// (*qn = query index of the first one), < 0 deleted bases, 0 none.  k1 = end of the read's CIGAR words.
+__device__ __forceinline__ int32_t op_indel(const uint32_t* __restrict__ cigar, const int2* __restrict__ opstart, int64_t k, int64_t k1, int32_t* qn) {
+    if (k + 1 >= k1) return 0;
+    const uint32_t op = __ldg(cigar + k) & 15u, w1 = __ldg(cigar + k + 1), op2 = w1 & 15u;
+    if (op2 == 2u && op != 2u) {
+        int32_t tot = (int32_t)(w1 >> 4);
+        for (int64_t j = k + 2; j < k1; j++) {
+            const uint32_t w2 = __ldg(cigar + j), o2 = w2 & 15u;
+            if (o2 == 2u) tot += (int32_t)(w2 >> 4);
+            else if (o2 == 1u || o2 == 4u || o2 == 0u || o2 == 7u || o2 == 8u) break;
+        }
+        return -tot;
+    }
+    if (op2 == 1u || (op2 == 6u && k + 2 < k1)) {
+        int32_t tot = 0; int64_t first = -1;
+        for (int64_t j = k + 1; j < k1; j++) {
+            const uint32_t w2 = __ldg(cigar + j), o2 = w2 & 15u;
+            if (o2 == 1u) { if (first < 0) first = j; tot += (int32_t)(w2 >> 4); }
+            else if (o2 != 6u) break;
+        }
+        if (tot > 0 && qn && opstart) *qn = __ldg(&opstart[first].y);
+        return tot;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// I1 impute (:278-304).  (a) per column, over all admitted reads: cdel = '*' and '-' marks, cins = '+' marks among the
+// first two characters of the pileup strings (:281-285).
+// ------------------------------------------------------------------------------------------------
+struct ImputeCountArgs {
+    int64_t n_reads;
+    const int32_t* pos; const int32_t* end; const uint16_t* flag;
+    const int64_t* cigar_off; const uint32_t* cigar;
+    int32_t lo_al, lo, hi; uint32_t flag_filter;
+    int32_t* cdel; int32_t* cins;        // [n_al], zeroed
+};
+__global__ void indel_impute_count_kernel(const ImputeCountArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_reads) return;
+    if ((a.flag[r] & a.flag_filter) != 0) return;
+    const int32_t rp = a.pos[r], re = a.end[r];
+    if (re <= rp || re <= a.lo || rp >= a.hi) return;
+    const int64_t k0 = a.cigar_off[r], k1 = a.cigar_off[r + 1];
+    int32_t x = rp;
+    for (int64_t k = k0; k < k1; k++) {
+        const uint32_t cw = __ldg(a.cigar + k);
+        const int32_t rl = cig_ref_len(cw);
+        if (rl == 0) continue;
+        if ((cw & 15u) == 2u)
+            for (int32_t q = max(x, a.lo); q < min(x + rl, a.hi); q++) atomicAdd(a.cdel + (q - a.lo_al), 1);
+        const int32_t plast = x + rl - 1;
+        x += rl;
+        if (plast >= a.hi) break;
+        if (plast < a.lo) continue;
+        const int32_t ind = op_indel(a.cigar, nullptr, k, k1, nullptr);
+        if (ind < 0) atomicAdd(a.cdel + (plast - a.lo_al), 1);
+        else if (ind > 0) atomicAdd(a.cins + (plast - a.lo_al), 1);
+    }
+}
+
+// (b) the columns the decide kernel left pending (hit == 4) -> compact list
+__global__ void indel_impute_collect_kernel(const uint8_t* __restrict__ hit, int64_t R, const IndelChunk* __restrict__ chunks, int32_t n_chunks,
+                                            const int32_t* __restrict__ em_pos, int64_t* __restrict__ out_g, int32_t* __restrict__ out_col,
+                                            unsigned long long* __restrict__ n_out) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= R || hit[g] != 4) return;
+    int c;
+    { int lo = 0, hi = n_chunks; while (lo < hi) { int mid = (lo + hi) >> 1; if (chunks[mid].rank_off <= g) lo = mid + 1; else hi = mid; } c = lo - 1; }
+    const unsigned long long slot = atomicAdd(n_out, 1ull);
+    out_g[slot] = g;
+    out_col[slot] = em_pos[chunks[c].grank_lo + (g - chunks[c].rank_off)];
+}
+
+// (c) reads of a column in pileup (BAM) order with their pileup-string descriptors: warp per column, count / fill
+struct ImputeArgs {
+    int64_t n_reads;
+    const int32_t* pos; const int32_t* end; const uint16_t* flag; const int32_t* pmaxend;
+    const int64_t* cigar_off; const uint32_t* cigar; const int2* opstart;
+    const int64_t* seq_off; const int32_t* l_seq; const uint8_t* seq4;
+    uint32_t flag_filter; int32_t mincov;
+    const int32_t* cols; int64_t n_cols;   // 0-based column positions
+    int32_t* col_cnt; const int64_t* col_off;
+    int32_t* e_read; uint8_t* e_ch; int32_t* e_ind; int32_t* e_qn;     // per (column, read) entry
+    int32_t* e_gid; int32_t* g_rep; int32_t* g_cnt;                    // scratch of the grouping, entry-sized
+    int8_t* e_label;                                                   // 0 read_names_0, 1 read_names_1, -1 neither
+    int32_t* col_ok;
+};
+__device__ __forceinline__ uint32_t read_nibble(const uint8_t* __restrict__ sq, int32_t q) {
+    const uint32_t b = __ldg(sq + (q >> 1));
+    return (q & 1) ? (b & 15u) : (b >> 4);
+}
+template <bool FILL>
+__global__ void __launch_bounds__(128) indel_impute_reads_kernel(const ImputeArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= a.n_cols) return;
+    const int32_t p = a.cols[c];
+    int64_t ilo, ihi;
+    read_window(a.pos, a.pmaxend, a.n_reads, p, ilo, ihi);
+    const int64_t off = FILL ? a.col_off[c] : 0;
+    int32_t cnt = 0;
+    for (int64_t base = ilo; base < ihi; base += 32) {
+        const int64_t i = base + lane;
+        bool cover = false;
+        if (i < ihi) {
+            const int32_t rp = __ldg(a.pos + i), re = __ldg(a.end + i);
+            cover = (__ldg(a.flag + i) & a.flag_filter) == 0 && rp <= p && p < re;
+        }
+        const uint32_t cm = __ballot_sync(0xffffffffu, cover);
+        if (FILL && cover) {
+            const int64_t e = off + cnt + __popc(cm & ((1u << lane) - 1u));
+            const int64_t c0 = a.cigar_off[i];
+            const int32_t nops = (int32_t)(a.cigar_off[i + 1] - c0), os = p - __ldg(a.pos + i);
+            int32_t lo = 0, hi = nops;
+            while (lo < hi) { int32_t mid = (lo + hi) >> 1; if (__ldg(&a.opstart[c0 + mid].x) <= os) lo = mid + 1; else hi = mid; }
+            const int32_t k = lo - 1;
+            const uint32_t cw = __ldg(a.cigar + c0 + k);
+            const int2 st = __ldg(a.opstart + c0 + k);
+            uint32_t ch;                                               // 0..15 base nibble, 16 '*', 17 '>', 18 '<'
+            if (cig_is_match(cw)) {
+                const int32_t q = st.y + (os - st.x);
+                ch = q < __ldg(a.l_seq + i) ? read_nibble(a.seq4 + __ldg(a.seq_off + i), q) : 15u;
+            } else ch = (cw & 15u) == 2u ? 16u : ((__ldg(a.flag + i) & 0x10u) ? 18u : 17u);
+            int32_t qn = 0, ind = 0;
+            if (os == st.x + cig_ref_len(cw) - 1) ind = op_indel(a.cigar, a.opstart, c0 + k, c0 + nops, &qn);
+            a.e_read[e] = (int32_t)i; a.e_ch[e] = (uint8_t)ch; a.e_ind[e] = ind; a.e_qn[e] = qn;
+        }
+        cnt += __popc(cm);
+    }
+    if (!FILL && lane == 0) a.col_cnt[c] = cnt;
+}
+
+// (d) grouping of equal strings and the two read sets (:287-300): one thread per column, in pileup order like the reference
+__device__ inline bool impute_same_token(const ImputeArgs& a, int64_t e1, int64_t e2) {
+    if (a.e_ch[e1] != a.e_ch[e2] || a.e_ind[e1] != a.e_ind[e2]) return false;
+    const int32_t L = a.e_ind[e1];
+    if (L <= 0) return true;                                           // '-L' + 'N' * L carries no bases
+    const int64_t r1 = a.e_read[e1], r2 = a.e_read[e2];
+    const int32_t q1 = a.e_qn[e1], q2 = a.e_qn[e2];
+    const int32_t n1 = max(0, min(L, __ldg(a.l_seq + r1) - q1)), n2 = max(0, min(L, __ldg(a.l_seq + r2) - q2));
+    if (n1 != n2) return false;
+    const uint8_t* s1 = a.seq4 + __ldg(a.seq_off + r1);
+    const uint8_t* s2 = a.seq4 + __ldg(a.seq_off + r2);
+    for (int32_t t = 0; t < n1; t++)
+        if (read_nibble(s1, q1 + t) != read_nibble(s2, q2 + t)) return false;
+    return true;
+}
+__global__ void indel_impute_group_kernel(const ImputeArgs a) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_cols) return;
+    const int64_t off = a.col_off[c];
+    const int32_t n = (int32_t)(a.col_off[c + 1] - off);
+    int32_t G = 0;
+    for (int32_t k = 0; k < n; k++) {
+        int32_t found = -1;
+        for (int32_t g = 0; g < G && found < 0; g++)
+            if (impute_same_token(a, off + k, off + a.g_rep[off + g])) found = g;
+        if (found < 0) { found = G++; a.g_rep[off + found] = k; a.g_cnt[off + found] = 0; }
+        a.e_gid[off + k] = found;
+        a.g_cnt[off + found]++;
+    }
+    int32_t n0 = 0, n1 = 0;
+    if (n > 0) {
+        int32_t g0 = 0;                                                // stable descending sort: first maximum, then first maximum of the rest
+        for (int32_t g = 1; g < G; g++) if (a.g_cnt[off + g] > a.g_cnt[off + g0]) g0 = g;
+        const int32_t c0 = a.g_cnt[off + g0];
+        if ((double)c0 <= 0.8 * (double)n) {                           // :293 (then G >= 2)
+            int32_t g1 = -1;
+            for (int32_t g = 0; g < G; g++) if (g != g0 && (g1 < 0 || a.g_cnt[off + g] > a.g_cnt[off + g1])) g1 = g;
+            const int32_t c1 = a.g_cnt[off + g1];
+            const bool second = c1 >= a.mincov;                        // :295 else: all the other reads of the column
+            for (int32_t k = 0; k < n; k++) {
+                const int32_t g = a.e_gid[off + k];
+                a.e_label[off + k] = g == g0 ? 0 : ((!second || g == g1) ? 1 : -1);
+            }
+            n0 = c0; n1 = second ? c1 : n - c0;
+        } else {                                                       // :297-298 the top group is halved
+            const int32_t half = c0 / 2;
+            int32_t seen = 0;
+            for (int32_t k = 0; k < n; k++) {
+                if (a.e_gid[off + k] != g0) { a.e_label[off + k] = -1; continue; }
+                a.e_label[off + k] = seen < half ? 0 : 1;
+                seen++;
+            }
+            n0 = half; n1 = c0 - half;
+        }
+    }
+    a.col_ok[c] = (n0 >= a.mincov && n1 >= a.mincov) ? 1 : 0;
+}
+// (e) pending columns -> hit 3 (imputed small-window candidate, :300-303) or 0
+__global__ void indel_impute_apply_kernel(const int64_t* __restrict__ gl, const int32_t* __restrict__ ok, int64_t n, uint8_t* __restrict__ hit,
+                                          unsigned long long* __restrict__ n_hits) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    hit[gl[i]] = ok[i] ? 3 : 0;
+    if (ok[i]) atomicAdd(n_hits, 1ull);
 }
 
 // pass A (count) / pass B (fill): warp per site
@@ -364,6 +579,16 @@ __global__ void __launch_bounds__(128) indel_site_reads_kernel(const SiteArgs a)
             const int32_t k = lo - 1;
             const int2 st = __ldg(a.opstart + c0 + k);
             a.e_qpn[e] = cig_is_match(__ldg(a.cigar + c0 + k)) ? st.y + (os - st.x) : st.y;
+            const int32_t imp = a.site_imp ? __ldg(a.site_imp + s) : -1;
+            int grp = -1;
+            if (imp < 0) { const int h = __ldg(a.hp + i); grp = (h == 1 || h == 2) ? h - 1 : -1; }
+            else {                                  // the source column lists its reads in ascending BAM index
+                int64_t lo2 = __ldg(a.imp_off + imp), hi2 = __ldg(a.imp_off + imp + 1);
+                const int64_t end2 = hi2;
+                while (lo2 < hi2) { const int64_t mid = (lo2 + hi2) >> 1; if (__ldg(a.imp_read + mid) < (int32_t)i) lo2 = mid + 1; else hi2 = mid; }
+                if (lo2 < end2 && __ldg(a.imp_read + lo2) == (int32_t)i) grp = __ldg(a.imp_label + lo2);
+            }
+            a.e_grp[e] = (int8_t)grp;
         }
         cnt += __popc(cm);
     }
@@ -477,10 +702,7 @@ __global__ void __launch_bounds__(96) indel_msa_kernel(const SiteArgs a) {
     const int32_t cnt = m > 0 ? a.site_cnt[s] : 0;
     const int32_t mincov = g == 2 ? a.mincov : 2;
     // membership: first maxcov reads of the group in pileup order (deterministic rule for the unseeded random.sample, :19)
-    auto member = [&](int32_t k) -> bool {
-        const int h = __ldg(a.hp + a.e_read[e0 + k]);
-        return g == 2 || h == g + 1;
-    };
+    auto member = [&](int32_t k) -> bool { return g == 2 || a.e_grp[e0 + k] == g; };
     // n_g and the first member
     for (int32_t k0 = 0; k0 < cnt; k0 += 32) {
         const int32_t k = k0 + lane;
@@ -589,7 +811,8 @@ __global__ void __launch_bounds__(96) indel_msa_kernel(const SiteArgs a) {
         mt->cns_len[g] = ok ? min(cl, a.cmax) : 0;
         mt->ok[g] = ok ? 1 : 0;
         if (g == 0) { mt->pos = a.sites[s].key; mt->chunk = a.sites[s].chunk; mt->type = a.sites[s].type; mt->ref_len = m;
-                      mt->phase = (ok && first_read >= 0) ? __ldg(a.ps + first_read) : 0; }
+                      const bool imputed = a.site_imp && a.site_imp[s] >= 0;      // phase_dict gives None for a read without HP: -1
+                      mt->phase = (ok && first_read >= 0) ? ((imputed && __ldg(a.hp + first_read) <= 0) ? -1 : __ldg(a.ps + first_read)) : 0; }
     }
 }
 

@@ -36,10 +36,10 @@ class NcTimings(ctypes.Structure):
 class NcIndelParams(ctypes.Structure):
     _fields_ = [("ins_t", ctypes.c_double), ("del_t", ctypes.c_double), ("mincov", ctypes.c_int32), ("maxcov", ctypes.c_int32),
                 ("win_size", ctypes.c_int32), ("small_win_size", ctypes.c_int32), ("window_after", ctypes.c_int32),
-                ("supplementary", ctypes.c_int32), ("haploid", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("supplementary", ctypes.c_int32), ("haploid", ctypes.c_int32), ("impute_indel_phase", ctypes.c_int32)]
 
 
-VARIANT_DTYPE = np.dtype([("key", "<i4"), ("type", "<i4"), ("chunk", "<i4")])
+VARIANT_DTYPE = np.dtype([("key", "<i4"), ("type", "<i4"), ("chunk", "<i4"), ("src", "<i4")])
 INDEL_META_DTYPE = np.dtype([("pos", "<i4"), ("chunk", "<i4"), ("type", "<i4"), ("phase", "<i4"), ("ref_len", "<i4"),
                              ("n", "<i4", (3,)), ("cns_len", "<i4", (3,)), ("ok", "<i4", (3,))])
 INDEL_CNS_MAX = 544
@@ -122,7 +122,7 @@ def indel_params(dct, haploid=False):
     """NcIndelParams from the reference's `dct` (generate_indel_pileups.py:136-157)."""
     return NcIndelParams(float(dct["ins_t"]), float(dct["del_t"]), int(dct["mincov"]), int(dct["maxcov"]), int(dct["win_size"]),
                          int(dct["small_win_size"]), 260 if dct["seq"] == "pacbio" else 160, 1 if dct.get("supplementary") else 0,
-                         1 if haploid else 0, 0)
+                         1 if haploid else 0, 1 if (dct.get("impute_indel_phase") and not haploid) else 0)
 
 
 def nw_trace(query_codes, ref_codes, gap_open=9, gap_extend=1, match=20, mismatch=-10):

@@ -61,24 +61,25 @@ def allele_prediction(alt, ref_seq, max_range, alt_codes=None, ref_codes=None):
 
 
 def order_variants(variants):
-    """The reference keeps `variants` in a dict (a later hit on the same key overwrites the type, :268,:274) and visits
-    the keys in column order in pass 2 (:306-320).  Device hits arrive in (chunk, column) order per chunk."""
+    """The reference keeps `variants` in a dict (a later hit on the same key overwrites the type, :268,:274,:301) and visits
+    the keys in column order in pass 2 (:306-320); `extra_variants` (:302) is a second dict that keeps the source column of the
+    last imputed hit on a key and wins in pass 2 (:309).  Device hits arrive in (chunk, column) order per chunk."""
     out = []
     for c in np.unique(variants["chunk"]):
         sel = variants[variants["chunk"] == c]
-        d = {}
-        for k, t in zip(sel["key"].tolist(), sel["type"].tolist()):
+        d, extra = {}, {}
+        for k, t, src in zip(sel["key"].tolist(), sel["type"].tolist(), sel["src"].tolist()):
             d[k] = t
+            if src:
+                extra[k] = src
         for k in sorted(d):
-            out.append((k, d[k], int(c)))
+            out.append((k, d[k], int(c), extra.get(k, 0)))
     return np.array(out, dtype=capi.VARIANT_DTYPE) if out else np.zeros(0, capi.VARIANT_DTYPE)
 
 
 def candidates_for_chunks(ctx, rs, dct, chunks, bed=None, haploid=False):
     """Scan + build for a list of chunk dicts of one contig; -> per-chunk reference-shaped tuples
     (diploid: 6-tuple of generate_indel_pileups.py:370; haploid: 3-tuple of generate_indel_pileups_haploid.py:277)."""
-    if dct.get("impute_indel_phase") and not haploid:
-        raise NotImplementedError("impute_indel_phase (generate_indel_pileups.py:278-304) is not built")
     snp_pileups.stage(ctx, rs)
     ctx.stage_tags(rs.hp, rs.ps)
     P = capi.indel_params(dct, haploid)
@@ -133,7 +134,8 @@ def candidates_for_chunks(ctx, rs, dct, chunks, bed=None, haploid=False):
         for s in sel:
             trip = [pred[(int(s), g)] for g in groups]
             alleles.append(trip[0] if haploid else trip)
-            phase.append(int(meta["phase"][s]))
+            ph = int(meta["phase"][s])
+            phase.append(None if ph == -1 else ph)                              # imputed site whose first hap0 read has no HP tag (:355)
         x = tensors[sel].astype(np.float64)                                  # float32 values in a float64 container (:69-71)
         res.append((pos, x[:, 2], alleles) if haploid else (pos, x[:, 0], x[:, 1], x[:, 2], alleles, phase))
     return res

@@ -143,22 +143,44 @@ def test_cli_ccs_preset_regions_and_exclude_bed(tmp_path):
     assert res["identical"] + res["numeric_only"] + res["borderline"] == len(want) > 300
 
 
-def test_cli_indels_on_an_untagged_bam_gives_empty_outputs(tmp_path):
-    """No HP tags: both haplotype depths stay below mincov (generate_indel_pileups.py:252), so the reference finds no candidates; the
-    command line must come back with header-only, indexed outputs (and say that impute_indel_phase is not built when asked for it)."""
+def test_cli_indels_on_an_untagged_bam(tmp_path):
+    """No HP tags: both haplotype depths stay below mincov (generate_indel_pileups.py:252).  Without impute_indel_phase the reference finds
+    no candidates and the command line must come back with header-only, indexed outputs; with it (`--preset ccs` sets the flag,
+    NanoCaller:74) the read sets come from the pileup strings (:278-304) and the records must equal the oracle pipeline's."""
+    import os
     from nanocaller_b200 import cli
-    from nanocaller_b200.host import bamio, snp_pileups, sources
+    from nanocaller_b200.host import bamio, snp_pileups, sources, vcfio, weights as W
     from nanocaller_b200.synth import make_world
-    rs = make_world(chrom="chrN", preset="ont", contig_len=60_000, seed=13, coverage=15.0, indel_every=1500, indel_maxlen=12, untagged_frac=1.0).reads
+    from oracle import cnn_oracle, indel_caller_oracle, indel_oracle, snp_oracle
+    rs = make_world(chrom="chrN", preset="hifi", contig_len=60_000, seed=13, coverage=30.0, indel_every=1500, indel_maxlen=12, untagged_frac=1.0).reads
     assert int((rs.hp > 0).sum()) == 0
     bam, fa = str(tmp_path / "u.bam"), str(tmp_path / "u.fa")
     bamio.write_bam(bam, [rs], index=True)
     bamio.write_fasta(fa, [rs])
     sources.unregister_all()
     snp_pileups.reset()
-    out = cli.main(["--bam", bam, "--ref", fa, "--mode", "indels", "--preset", "ccs", "--output", str(tmp_path / "o3")])
+    out = cli.main(["--bam", bam, "--ref", fa, "--mode", "indels", "--preset", "ont", "--output", str(tmp_path / "o3")])
     assert out["n_indel_records"] == 0
     recs, txt = _records(out["indels"])
     assert recs == [] and txt.startswith("##fileformat=VCFv4.2\n") and "##contig=<ID=chrN>" in txt
-    import os
     assert os.path.exists(out["indels"] + ".csi")
+
+    sources.unregister_all()
+    snp_pileups.reset()
+    out = cli.main(["--bam", bam, "--ref", fa, "--mode", "indels", "--preset", "ccs", "--cpu", "2", "--output", str(tmp_path / "o4")])
+    idct = dict(mincov=4, maxcov=160, seq="pacbio", del_t=0.4, ins_t=0.4, impute_indel_phase=True, supplementary=False, win_size=40, small_win_size=4)
+    it, _ = W.load_model("indel", "CCS-HG002")
+    want = []
+    for ch in snp_oracle.get_chunks([("chrN", 1, 60_000, "diploid")], 2, 100_000):
+        pos, x0, x1, x2, alleles, phase = indel_oracle.get_indel_testing_candidates(rs, idct, ch)
+        if len(pos):
+            probs = cnn_oracle.indel_model(it, np.hstack([x0, x1, x2]).astype(np.float32))
+            want += indel_caller_oracle.diploid_records(ch["chrom"], pos, probs, alleles, phase)
+    want = vcfio.sort_records(want, ["chrN"])
+    got, _ = _records(out["indels"])
+    assert len(got) == len(want) > 10
+    for a, b in zip(got, want):
+        fa_, fb_ = a.split("\t"), b.split("\t")
+        assert fa_[:5] == fb_[:5] and fa_[6:9] == fb_[6:9], (a, b)
+        assert abs(float(fa_[5]) - float(fb_[5])) < 0.02
+        assert fa_[9].split(":")[0] == fb_[9].split(":")[0]
