@@ -270,6 +270,19 @@ def main():
     clocks = sampler.stop() if sampler else None
     launches = ctx.timings()["launches"] - l0
     tbytes = ctx.timings()["tensor_bytes"]
+    # SURVEY 8(d) algorithmic bytes of the tensor build: 5 B per (sampled read, real column) + 1025 int16 + 64 B of site data,
+    # from the site records of the last step (untimed)
+    survey_bytes = None
+    try:
+        import numpy as _np
+        _m = _np.empty(max(1, int(n_sites)), capi.META_DTYPE)
+        _pr = _np.empty((max(1, int(n_sites)), 4), _np.float32)
+        ctx.fetch_calls(_pr, _m)
+        _m = _m[:int(n_sites)]
+        _cols = _m["n_left"].astype(_np.int64) + _m["n_right"].astype(_np.int64) + 1
+        survey_bytes = int((5 * _m["sample_depth"].astype(_np.int64) * _cols).sum() + int(n_sites) * (1025 * 2 + 64))
+    except Exception as _e:                                   # a reporting extra must never cost the bench line
+        sys.stderr.write("bench: survey byte count skipped: %r\n" % (_e,))
 
     # ---- end-to-end figure, serial: stage -> kernels -> fetch, one contig after the other
     for _ in range(args.warmup):
@@ -438,7 +451,12 @@ def main():
         roof2 = {"kernel": "tensor_kernel (K2 pileup tensor build)", "bound": "hbm", "achieved": tbytes / (tensor_ms * 1e-3) / 1e9,
                  "peak": hbm, "unit": "GB/s", "frac": tbytes / (tensor_ms * 1e-3) / 1e9 / hbm,
                  "traffic": (tr["tensor_dram_bytes_per_site"] * n_sites) if "tensor_dram_bytes_per_site" in tr else None,
-                 "bytes_per_site": tbytes / max(1, n_sites), "ms_per_launch": tensor_ms}
+                 "bytes_per_site": tbytes / max(1, n_sites), "ms_per_launch": tensor_ms,
+                 "note": "achieved counts the bytes this kernel has to move (int16 tensor + site record); survey_8d counts SURVEY 8(d)'s "
+                         "B2 = 5 B per (sampled read, real column) + 1025 int16 + 64 B, i.e. the read-code lists a per-site kernel would stream"}
+        if survey_bytes:
+            roof2["survey_8d"] = {"bytes_per_site": survey_bytes / max(1, n_sites), "achieved": survey_bytes / (tensor_ms * 1e-3) / 1e9,
+                                  "frac": survey_bytes / (tensor_ms * 1e-3) / 1e9 / hbm}
         cpu = None
         if world == 1:
             cores = os.cpu_count() or 1
