@@ -4,6 +4,7 @@ they travel to the GPU box with the repo snapshot.
   libnanocaller_b200.so   nvcc, sm_100a only: CUDA kernels + the C-ABI (include/nanocaller_b200.h)
   libnc_synth.so          g++: synthetic world generator (test / bench infrastructure)
   libnc_bamio.so          g++ -lz: native BGZF/BAM reader into the staging arrays (include/nanocaller_b200_io.h)
+  libnc_phase.so          g++: read-based phasing + haplotagging between the SNP and indel stages (include/nanocaller_b200_phase.h)
 
 `python -m nanocaller_b200.build` builds everything that is stale.
 """
@@ -18,6 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_CUDA = os.path.join(HERE, "libnanocaller_b200.so")
 LIB_SYNTH = os.path.join(HERE, "libnc_synth.so")
 LIB_BAMIO = os.path.join(HERE, "libnc_bamio.so")
+LIB_PHASE = os.path.join(HERE, "libnc_phase.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -61,6 +63,15 @@ def build_bamio(force=False, verbose=False):
     return LIB_BAMIO
 
 
+def build_phase(force=False, verbose=False):
+    """g++ -pthread: host-side phasing / haplotagging (include/nanocaller_b200_phase.h)."""
+    src = os.path.join(CSRC, "phase.cpp")
+    hdr = os.path.join(ROOT, "include", "nanocaller_b200_phase.h")
+    if force or _stale(LIB_PHASE, [src, hdr]):
+        _run(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", LIB_PHASE, src], verbose)
+    return LIB_PHASE
+
+
 def cuda_deps():
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(CUDA_DEPS_EXT)]
     deps.append(os.path.join(ROOT, "include", "nanocaller_b200.h"))
@@ -84,6 +95,7 @@ def build_cuda(force=False, verbose=False, extra=()):
 def build_all(force=False, verbose=False):
     build_synth(force, verbose)
     build_bamio(force, verbose)
+    build_phase(force, verbose)
     build_cuda(force, verbose)
 
 

@@ -3,9 +3,11 @@
 The reference's command line (`NanoCaller:84-158`: same flags, defaults, preset table `:66-77`, region rules
 `nanocaller_src/utils.py:6-65`, chunk grid `utils.py:67-83`, output names `snpCaller.py:251-252`,
 `indelCaller.py:385-395`) driving the B200 path: BAM/FASTA -> staging arrays -> CUDA pileup + CNN -> VCF records ->
-sorted BGZF VCFs.  What is NOT here is everything the reference delegates to external programs between the two
-stages: `whatshap phase/haplotag` (`indelCaller.py:234-251`) — indel calling uses the HP/PS tags already present in
-`--bam`, as `--mode indels` does in the reference — and `rtg vcfdecompose` (`indelCaller.py:391`).  `--cpu` only sets
+sorted BGZF VCFs.  Between the two stages the reference shells out to `whatshap phase/haplotag`
+(`indelCaller.py:234-251`); here `host/phasing.py` (libnc_phase.so, an own algorithm) phases the PASS SNP calls and tags
+the reads in memory — in `--mode all` when the contig's reads carry no HP tags yet, or whenever `--phase` is given;
+reads that are already haplotagged are used as they are (as `--mode indels` does in the reference).  Not here:
+`--enable_whatshap`'s genotype revision and `rtg vcfdecompose` (`indelCaller.py:391`).  `--cpu` only sets
 the chunk grid (and with it the normalisation groups); the work runs on the GPU of
 `--device`.  There is no CPU fallback: without an sm_100 GPU the run fails in `nc_create`."""
 import argparse
@@ -174,6 +176,38 @@ def _groups(chunks):
     return out
 
 
+def _phase_stage(args, regions, chrom_list, out):
+    """indelCaller.phase_run (indelCaller.py:190-262): PASS SNP records of every diploid contig -> phased records + haplotagged
+    reads (host/phasing.py); haploid contigs pass through (:191-199).  Writes `{prefix}.snps.phased.vcf.gz` (:360)."""
+    from .host import phasing, sources, vcfio
+    t1 = time.time()
+    by_chrom = {}
+    for ln in vcfio.read_records(out["snps"]):
+        by_chrom.setdefault(ln.split("\t", 1)[0], []).append(ln)
+    ploidy_of = {}
+    for r in regions:
+        ploidy_of.setdefault(r[0], r[3])
+    phased_lines, pstats = [], {}
+    for chrom in chrom_list:
+        lines_c = by_chrom.get(chrom, [])
+        if ploidy_of[chrom] == "haploid":
+            phased_lines += lines_c
+            continue
+        rs = sources.resolve(args.bam, chrom)
+        if not args.phase and int((rs.hp > 0).sum()) > 0:
+            print("\n%s: %s: reads are already haplotagged; HP/PS tags of the BAM are used (give --phase to re-phase)."
+                  % (datetime.datetime.now(), chrom), flush=True)
+            phased_lines += lines_c
+            continue
+        new_lines, st = phasing.phase_snp_records(lines_c, rs, args.phase_qual_score, supplementary=args.supplementary)
+        phased_lines += new_lines
+        pstats[chrom] = st
+    php = os.path.join(args.output, "%s.snps.phased.vcf.gz" % args.prefix)
+    vcfio.write_vcf(php, "phased_snps", chrom_list, phased_lines, args.sample, index=True)
+    out.update(phased_snps=php, phase_stats=pstats, phase_seconds=time.time() - t1)
+    print("\n%s: Phasing completed. Time taken= %.4f\n" % (datetime.datetime.now(), time.time() - t1), flush=True)
+
+
 def run(args):
     from .host import bamio, indel_caller, models, snp_caller, snp_pileups, vcfio
     t0 = time.time()
@@ -217,6 +251,9 @@ def run(args):
         out.update(unfiltered_snps=allp, snps=passp, n_snp_records=n_all, snp_seconds=time.time() - t1)
         print("\n%s: SNP calling completed. Time taken= %.4f\n" % (datetime.datetime.now(), time.time() - t1), flush=True)
 
+    if args.mode == "all" or (args.mode == "snps" and args.phase):      # indelCaller.phase_run (indelCaller.py:190-262), NanoCaller:41
+        _phase_stage(args, regions, chrom_list, out)
+
     if args.mode in ("indels", "all"):
         t1 = time.time()
         params = dict(sam_path=args.bam, fasta_path=args.ref, mincov=args.mincov, maxcov=args.maxcov, seq=args.sequencing,
@@ -239,7 +276,7 @@ def run(args):
         print("\n%s: Indel calling completed. Time taken= %.4f\n" % (datetime.datetime.now(), time.time() - t1), flush=True)
         if args.mode == "all":
             final = os.path.join(args.output, "%s.vcf.gz" % args.prefix)
-            snp_lines = vcfio.read_records(out["snps"])
+            snp_lines = vcfio.read_records(out["phased_snps"])             # indelCaller.py:395 concatenates the phased SNP file
             vcfio.write_vcf(final, "all", chrom_list, snp_lines + lines, args.sample, index=True)
             out["final"] = final
     out.update(read_seconds=t_read, launches=ctx.timings()["launches"])

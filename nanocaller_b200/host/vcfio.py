@@ -40,6 +40,9 @@ def header(kind, contigs, sample="SAMPLE"):
         ind = INDEL_HEADER.format(contigs=ctg, sample=sample).splitlines(True)
         extra = [ln for ln in ind if ln.startswith("##") and ln not in snp]
         return "".join(snp[:-1] + extra + snp[-1:])
+    if kind == "phased_snps":                    # the SNP header plus the PS line the phasing step adds (what `whatshap phase` writes, indelCaller.py:237)
+        snp = SNP_HEADER.format(contigs=ctg, sample=sample).splitlines(True)
+        return "".join(snp[:-1] + ['##FORMAT=<ID=PS,Number=1,Type=Integer,Description="Phase set identifier">\n'] + snp[-1:])
     tmpl = SNP_HEADER if kind == "snps" else INDEL_HEADER
     return tmpl.format(contigs=ctg, sample=sample)
 

@@ -184,3 +184,52 @@ def test_cli_indels_on_an_untagged_bam(tmp_path):
         assert fa_[:5] == fb_[:5] and fa_[6:9] == fb_[6:9], (a, b)
         assert abs(float(fa_[5]) - float(fb_[5])) < 0.02
         assert fa_[9].split(":")[0] == fb_[9].split(":")[0]
+
+
+def test_cli_mode_all_phases_an_untagged_bam(tmp_path):
+    """`--mode all` on a BAM without HP tags: the SNP calls are phased and the reads haplotagged in memory (host/phasing.py, in place of
+    `whatshap phase` / `haplotag`, indelCaller.py:237,:244), so the indel stage finds (nearly) the same variants as on the same reads
+    carrying the generator's true haplotype tags; the phased SNP file and the merged file carry the phased genotypes."""
+    import copy
+    import os
+    from nanocaller_b200 import cli
+    from nanocaller_b200.host import bamio, snp_pileups, sources
+    from nanocaller_b200.synth import make_world
+    rs = make_world(chrom="chrB", preset="ont", contig_len=300_000, seed=21, coverage=30.0, indel_every=1500, indel_maxlen=12).reads
+    truth_hp = rs.hp.copy()
+    assert set(np.unique(truth_hp).tolist()) == {1, 2}
+    un = copy.copy(rs)
+    un.hp, un.ps = np.zeros_like(rs.hp), np.zeros_like(rs.ps)
+    fa = str(tmp_path / "b.fa")
+    bamio.write_fasta(fa, [rs])
+    runs = {}
+    for tag, r in (("tagged", rs), ("untagged", un)):
+        bam = str(tmp_path / (tag + ".bam"))
+        bamio.write_bam(bam, [r], index=True)
+        sources.unregister_all()
+        snp_pileups.reset()
+        out = cli.main(["--bam", bam, "--ref", fa, "--mode", "all", "--preset", "ont", "--cpu", "2", "--output", str(tmp_path / tag)])
+        runs[tag] = (out, _records(out["indels"])[0], _records(out["phased_snps"])[0], sources.resolve(bam, "chrB"))
+    out_t, ind_t, ph_t, _ = runs["tagged"]
+    out_u, ind_u, ph_u, rs_u = runs["untagged"]
+    # tagged BAM: the tags are used as they are, nothing is phased
+    assert out_t["phase_stats"] == {} and not any("|" in ln.split("\t")[9] for ln in ph_t)
+    # untagged BAM: phased hets with PS, reads tagged like the truth (up to the naming of the two haplotypes per block)
+    st = out_u["phase_stats"]["chrB"]
+    assert st["het_sites"] > 150 and st["phased_sites"] >= 0.95 * st["het_sites"] and st["tagged_reads"] >= 0.85 * st["reads"]
+    n_ph = sum("|" in ln.split("\t")[9] for ln in ph_u)
+    assert n_ph == st["phased_sites"] and all(ln.split("\t")[8].endswith(":PS") for ln in ph_u if "|" in ln.split("\t")[9])
+    assert len(ph_u) == len(ph_t) and [ln.split("\t")[:5] for ln in ph_u] == [ln.split("\t")[:5] for ln in ph_t]
+    both = (truth_hp > 0) & (rs_u.hp > 0)
+    agree = total = 0
+    for ps in np.unique(rs_u.ps[both]):
+        m = both & (rs_u.ps == ps)
+        same = int((truth_hp[m] == rs_u.hp[m]).sum())
+        agree += max(same, int(m.sum()) - same); total += int(m.sum())
+    assert total >= 0.85 * rs.n and agree >= 0.97 * total, (agree, total)
+    # indel calls: the same variants as with the true tags
+    key = lambda ln: tuple(ln.split("\t")[:2]) + (ln.split("\t")[3],) + (tuple(sorted(ln.split("\t")[4].split(","))),)
+    kt, ku = {key(ln) for ln in ind_t}, {key(ln) for ln in ind_u}
+    assert len(kt) > 100 and len(kt & ku) >= 0.9 * len(kt) and len(ku) <= 1.1 * len(kt), (len(kt), len(ku), len(kt & ku))
+    merged = _records(out_u["final"])[0]
+    assert len(merged) == len(ph_u) + len(ind_u) and os.path.exists(out_u["phased_snps"] + ".csi")
