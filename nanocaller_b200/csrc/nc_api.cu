@@ -1062,8 +1062,8 @@ int nc_indel_build(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int
     indel_site_reads_kernel<true><<<sg, 128, 0, c->stream>>>(sa); NC_LAUNCH_CHECK();
     if (n_entries > 0) {
         const int smem = kAlignWarps * kRowsMax * 32 * 4;
-        static bool attr = false;
-        if (!attr) { NC_CUDA(cudaFuncSetAttribute(indel_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+        // function attributes are per device and one process may open contexts on several: set it on every call (cheap, no sync)
+        NC_CUDA(cudaFuncSetAttribute(indel_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_entries, kAlignWarps), (int64_t)c->sm_count * 12);
         indel_align_kernel<<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries); NC_LAUNCH_CHECK();
     }
