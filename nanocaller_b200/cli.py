@@ -7,7 +7,8 @@ sorted BGZF VCFs.  Between the two stages the reference shells out to `whatshap 
 (`indelCaller.py:234-251`); here `host/phasing.py` (libnc_phase.so, an own algorithm) phases the PASS SNP calls and tags
 the reads in memory — in `--mode all` when the contig's reads carry no HP tags yet, or whenever `--phase` is given;
 reads that are already haplotagged are used as they are (as `--mode indels` does in the reference).  Not here:
-`--enable_whatshap`'s genotype revision and `rtg vcfdecompose` (`indelCaller.py:391`).  `--cpu` only sets
+`--enable_whatshap`'s genotype revision.  `rtg vcfdecompose | vcffilter --non-snps-only` (`indelCaller.py:391`) has an own-rule
+stand-in behind `--decompose_indels` (`host/vcf_decompose.py`, off by default).  `--cpu` only sets
 the chunk grid (and with it the normalisation groups); the work runs on the GPU of
 `--device`.  There is no CPU fallback: without an sm_100 GPU the run fails in `nc_create`."""
 import argparse
@@ -67,6 +68,10 @@ def build_parser():
     p.add_argument("--win_size", type=int, default=40)
     p.add_argument("--small_win_size", type=int, default=4)
     p.add_argument("--impute_indel_phase", action="store_true", default=False)
+    p.add_argument("--decompose_indels", action="store_true", default=False,
+                   help="normalise the indel records like the reference's `rtg vcfdecompose | rtg vcffilter --non-snps-only` step "
+                        "(indelCaller.py:391) with this package's own rule set (host/vcf_decompose.py); the records as the indel stage "
+                        "wrote them are kept in intermediate_indel_files/{prefix}.raw.indel.vcf. Off by default: not pinned against rtg.")
     p.add_argument("--phase", action="store_true", default=False)
     p.add_argument("--phase_qual_score", type=float, default=10)
     p.add_argument("--enable_whatshap", action="store_true", default=False)
@@ -271,6 +276,13 @@ def run(args):
         for grp in _groups(chunks):                               # indelCaller.py:327-336 hands every chunk its (phased) BAM
             lines += indel_caller.call_chunks(params, [dict(c, sam_path=args.bam) for c in grp], ind, hap_tensors=hap_ind, device=args.device)
         indp = os.path.join(args.output, "%s.indels.vcf.gz" % args.prefix)
+        if args.decompose_indels:                                 # indelCaller.py:369,:391
+            from .host import vcf_decompose
+            raw_dir = os.path.join(args.output, "intermediate_indel_files")
+            os.makedirs(raw_dir, exist_ok=True)
+            out["raw_indels"] = os.path.join(raw_dir, "%s.raw.indel.vcf" % args.prefix)
+            vcfio.write_vcf(out["raw_indels"], "indels", chrom_list, lines, args.sample)
+            lines = vcf_decompose.decompose_records(vcfio.sort_records(lines, chrom_list), contigs=chrom_list)
         vcfio.write_vcf(indp, "indels", chrom_list, lines, args.sample, index=True)
         out.update(indels=indp, n_indel_records=len(lines), indel_seconds=time.time() - t1)
         print("\n%s: Indel calling completed. Time taken= %.4f\n" % (datetime.datetime.now(), time.time() - t1), flush=True)
