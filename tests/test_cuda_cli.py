@@ -233,3 +233,24 @@ def test_cli_mode_all_phases_an_untagged_bam(tmp_path):
     assert len(kt) > 100 and len(kt & ku) >= 0.9 * len(kt) and len(ku) <= 1.1 * len(kt), (len(kt), len(ku), len(kt & ku))
     merged = _records(out_u["final"])[0]
     assert len(merged) == len(ph_u) + len(ind_u) and os.path.exists(out_u["phased_snps"] + ".csi")
+
+
+def test_cli_decompose_indels_flag(tmp_path):
+    """`--decompose_indels`: the records of the indel stage go to intermediate_indel_files/{prefix}.raw.indel.vcf (indelCaller.py:369) and
+    `{prefix}.indels.vcf.gz` holds their normalised form (host/vcf_decompose.py, in place of indelCaller.py:391)."""
+    from nanocaller_b200 import cli
+    from nanocaller_b200.host import snp_pileups, sources, vcfio
+    from nanocaller_b200.host.vcf_decompose import decompose_records
+    bam, fa, worlds = _world(tmp_path)
+    outs = {}
+    for tag, extra in (("plain", []), ("dec", ["--decompose_indels"])):
+        sources.unregister_all()
+        snp_pileups.reset()
+        outs[tag] = cli.main(["--bam", bam, "--ref", fa, "--mode", "indels", "--preset", "ont", "--cpu", "3", "--regions", "chrA",
+                              "--output", str(tmp_path / tag)] + extra)
+    plain = vcfio.read_records(outs["plain"]["indels"])
+    raw = vcfio.read_records(outs["dec"]["raw_indels"])
+    dec = vcfio.read_records(outs["dec"]["indels"])
+    assert raw == plain and len(plain) > 20 and "raw_indels" not in outs["plain"]
+    assert dec == decompose_records(plain, contigs=["chrA"]) and dec != plain
+    assert sum(len(ln.split("\t")[3]) for ln in dec) < sum(len(ln.split("\t")[3]) for ln in plain)      # padding context is gone
