@@ -3,15 +3,18 @@
 //
 // Algorithm:
 //   1. allele table: one CIGAR walk per read against the sorted site list (threads over reads);
-//   2. phase blocks: connected components of sites linked by a phasing read that is informative at both;
-//   3. left-to-right pass: every read carries a score (> 0: believed to come from haplotype 1); a site's orientation is the
-//      vote of its reads, weighted by their clamped scores; the reads' scores are then updated with the decision;
-//   4. refinement sweeps: every site is re-decided against the scores the reads have WITHOUT that site (a local search on the
-//      minimum-error-correction objective); a flip updates the scores at once;
-//   5. haplotag: sign of a read's agreement count over the phased sites of its best-supported block.
+//   2. usable sites: both alleles seen in >= 2 phasing reads and the rarer one in >= 15 % of them;
+//   3. pairwise linkage of every usable site with the next 16 sites: cis = reads showing the same allele index at both,
+//      trans = different; a link is accepted when |cis - trans| >= 3 and >= 60 % of the reads that see both sites;
+//   4. maximum spanning forest over the accepted links, strongest first (union-find with parity): the components with >= 2
+//      sites are the phase blocks, the parity along the tree is the orientation; sites that link to nothing stay unphased;
+//   5. refinement sweeps: every phased site is re-decided against the scores its reads have WITHOUT that site (a local search
+//      on the minimum-error-correction objective); a flip updates the scores at once;
+//   6. haplotag: sign of a read's agreement count over the phased sites of its best-supported block.
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <utility>
 #include <numeric>
 #include <thread>
 #include <vector>
@@ -25,13 +28,6 @@ inline int qry_len(uint32_t w) { return ((0x193u >> (w & 15)) & 1u) ? (int)(w >>
 inline bool is_match(uint32_t w) { return ((0x181u >> (w & 15)) & 1u) != 0; }                  // M = X
 
 inline int clamp2(int v) { return v > 2 ? 2 : (v < -2 ? -2 : v); }
-
-struct Dsu {
-    std::vector<int32_t> p;
-    explicit Dsu(size_t n) : p(n) { std::iota(p.begin(), p.end(), 0); }
-    int32_t find(int32_t x) { while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; } return x; }
-    void unite(int32_t a, int32_t b) { a = find(a); b = find(b); if (a != b) { if (a < b) p[b] = a; else p[a] = b; } }   // root = smallest index
-};
 
 }  // namespace
 
@@ -93,55 +89,104 @@ extern "C" int nc_phase_sites(int64_t n_reads, const uint8_t* read_use, const in
     for (int64_t j = 0; j < n_sites; j++) { site_hap[j] = -1; site_block[j] = -1; }
     for (int64_t r = 0; r < n_reads; r++) { read_hp[r] = 0; read_block[r] = -1; }
     if (n_reads == 0 || n_sites == 0) return 0;
+    constexpr int kPairSpan = 16;          // a site is compared with the next 16 sites
+    constexpr int kMinMinor = 2;           // usable site: both alleles seen in >= 2 phasing reads ...
+    constexpr double kMinMinorFrac = 0.15; // ... and the rarer one in >= 15 % of them
+    constexpr int kMinLink = 3;            // accepted link: |cis - trans| >= 3 ...
+    constexpr double kMinLinkFrac = 0.6;   // ... and >= 60 % of the reads that see both sites
 
-    // site -> (read, allele) lists of the phasing reads, and the phase blocks
-    std::vector<int64_t> soff((size_t)n_sites + 1, 0);
-    Dsu dsu((size_t)n_sites);
+    // usable sites: a call whose reads (almost) all show one allele carries no phase information and would tie everything to it
+    std::vector<int32_t> cnt0((size_t)n_sites, 0), cnt1((size_t)n_sites, 0);
     for (int64_t r = 0; r < n_reads; r++) {
         if (!read_use[r]) continue;
-        int64_t prev = -1;
         for (int64_t e = pair_off[r]; e < pair_off[r + 1]; e++) {
             if (allele[e] == NC_PHASE_NONE) continue;
             const int64_t j = first_site[r] + (e - pair_off[r]);
-            soff[(size_t)j + 1]++;
-            if (prev >= 0) dsu.unite((int32_t)prev, (int32_t)j);
-            prev = j;
+            (allele[e] ? cnt1 : cnt0)[(size_t)j]++;
         }
     }
-    for (int64_t j = 0; j < n_sites; j++) soff[(size_t)j + 1] += soff[(size_t)j];
+    std::vector<uint8_t> usable((size_t)n_sites, 0);
+    for (int64_t j = 0; j < n_sites; j++) {
+        const int32_t mn = std::min(cnt0[(size_t)j], cnt1[(size_t)j]), tot = cnt0[(size_t)j] + cnt1[(size_t)j];
+        usable[(size_t)j] = mn >= kMinMinor && (double)mn >= kMinMinorFrac * (double)tot;
+    }
+
+    // site -> (read, allele) lists of the phasing reads over usable sites
+    std::vector<int64_t> soff((size_t)n_sites + 1, 0);
+    for (int64_t j = 0; j < n_sites; j++) soff[(size_t)j + 1] = soff[(size_t)j] + (usable[(size_t)j] ? cnt0[(size_t)j] + cnt1[(size_t)j] : 0);
     std::vector<int32_t> sread((size_t)soff[(size_t)n_sites]);
     std::vector<uint8_t> sall((size_t)soff[(size_t)n_sites]);
+    // pairwise linkage: cis = reads showing the same allele index at both sites, trans = different
+    std::vector<int32_t> cis((size_t)n_sites * kPairSpan, 0), trans((size_t)n_sites * kPairSpan, 0);
     {
         std::vector<int64_t> fill(soff.begin(), soff.end() - 1);
+        std::vector<std::pair<int64_t, uint8_t>> mine;
         for (int64_t r = 0; r < n_reads; r++) {
             if (!read_use[r]) continue;
+            mine.clear();
             for (int64_t e = pair_off[r]; e < pair_off[r + 1]; e++) {
                 if (allele[e] == NC_PHASE_NONE) continue;
                 const int64_t j = first_site[r] + (e - pair_off[r]);
+                if (!usable[(size_t)j]) continue;
                 sread[(size_t)fill[(size_t)j]] = (int32_t)r; sall[(size_t)fill[(size_t)j]] = allele[e]; fill[(size_t)j]++;
+                mine.emplace_back(j, allele[e]);
             }
+            for (size_t a = 0; a < mine.size(); a++)
+                for (size_t b = a + 1; b < mine.size() && mine[b].first - mine[a].first <= kPairSpan; b++) {
+                    const size_t k = (size_t)mine[a].first * kPairSpan + (size_t)(mine[b].first - mine[a].first - 1);
+                    if (mine[a].second == mine[b].second) cis[k]++; else trans[k]++;
+                }
         }
     }
-    std::vector<int32_t> bsize((size_t)n_sites, 0);
-    for (int64_t j = 0; j < n_sites; j++) bsize[(size_t)dsu.find((int32_t)j)]++;
-
-    // left-to-right pass
-    std::vector<int32_t> score((size_t)n_reads, 0);
-    std::vector<int8_t> h((size_t)n_sites, 0);
-    for (int64_t j = 0; j < n_sites; j++) {
-        int64_t vote = 0;
-        for (int64_t e = soff[(size_t)j]; e < soff[(size_t)j + 1]; e++) {
-            const int w = clamp2(score[(size_t)sread[(size_t)e]]);
-            vote += sall[(size_t)e] == 1 ? w : -w;
+    // maximum spanning forest over the accepted links (strongest first), union-find with parity: par[j] = orientation of j
+    // relative to its root
+    struct Edge { int32_t s, i, j; uint8_t flip; };
+    std::vector<Edge> edges;
+    for (int64_t i = 0; i < n_sites; i++)
+        for (int d = 0; d < kPairSpan && i + d + 1 < n_sites; d++) {
+            const int32_t c = cis[(size_t)i * kPairSpan + d], t = trans[(size_t)i * kPairSpan + d];
+            const int32_t s = std::abs(c - t);
+            if (s >= kMinLink && (double)s >= kMinLinkFrac * (double)(c + t)) edges.push_back({s, (int32_t)i, (int32_t)(i + d + 1), (uint8_t)(t > c)});
         }
-        h[(size_t)j] = vote > 0 ? 1 : 0;
+    std::stable_sort(edges.begin(), edges.end(), [](const Edge& a, const Edge& b) { return a.s > b.s; });
+    std::vector<int32_t> root((size_t)n_sites);
+    std::iota(root.begin(), root.end(), 0);
+    std::vector<uint8_t> par((size_t)n_sites, 0);
+    auto find = [&](int32_t x, uint8_t& p) {             // -> root of x; p = parity of x relative to that root (with path compression)
+        int32_t r = x; uint8_t acc = 0;
+        while (root[(size_t)r] != r) { acc ^= par[(size_t)r]; r = root[(size_t)r]; }
+        int32_t y = x; uint8_t py = acc;
+        while (root[(size_t)y] != y) { const int32_t nxt = root[(size_t)y]; const uint8_t pn = py ^ par[(size_t)y]; root[(size_t)y] = r; par[(size_t)y] = py; y = nxt; py = pn; }
+        p = acc;
+        return r;
+    };
+    for (const Edge& e : edges) {
+        uint8_t pi, pj;
+        const int32_t ri = find(e.i, pi), rj = find(e.j, pj);
+        if (ri == rj) continue;
+        const uint8_t rel = pi ^ pj ^ e.flip;            // parity between the two roots
+        if (ri < rj) { root[(size_t)rj] = ri; par[(size_t)rj] = rel; } else { root[(size_t)ri] = rj; par[(size_t)ri] = rel; }   // root = smallest index
+    }
+    std::vector<int32_t> bsize((size_t)n_sites, 0), blk((size_t)n_sites, -1);
+    std::vector<int8_t> h((size_t)n_sites, -1);
+    for (int64_t j = 0; j < n_sites; j++) { uint8_t p; blk[(size_t)j] = find((int32_t)j, p); bsize[(size_t)blk[(size_t)j]]++; }
+    for (int64_t j = 0; j < n_sites; j++) {
+        if (!usable[(size_t)j] || bsize[(size_t)blk[(size_t)j]] < 2) continue;
+        uint8_t p; find((int32_t)j, p);
+        h[(size_t)j] = (int8_t)p;                        // the block's first site has orientation 0
+    }
+    // read scores over the phased sites, then refinement sweeps: every site is re-decided against the scores its reads have
+    // WITHOUT that site (a local search on the minimum-error-correction objective); a flip updates the scores at once
+    std::vector<int32_t> score((size_t)n_reads, 0);
+    for (int64_t j = 0; j < n_sites; j++) {
+        if (h[(size_t)j] < 0) continue;
         for (int64_t e = soff[(size_t)j]; e < soff[(size_t)j + 1]; e++)
             score[(size_t)sread[(size_t)e]] += sall[(size_t)e] == (uint8_t)h[(size_t)j] ? 1 : -1;
     }
-    // refinement sweeps
     for (int it = 0; it < iterations; it++) {
         int64_t flips = 0;
         for (int64_t j = 0; j < n_sites; j++) {
+            if (h[(size_t)j] < 0) continue;
             int64_t vote = 0;
             for (int64_t e = soff[(size_t)j]; e < soff[(size_t)j + 1]; e++) {
                 const int own = sall[(size_t)e] == (uint8_t)h[(size_t)j] ? 1 : -1;
@@ -160,9 +205,17 @@ extern "C" int nc_phase_sites(int64_t n_reads, const uint8_t* read_use, const in
         }
         if (flips == 0) break;
     }
+    // keep the convention "first site of a block is A|B" after the sweeps
+    std::vector<int8_t> first_h((size_t)n_sites, -1);
+    for (int64_t j = 0; j < n_sites; j++)
+        if (h[(size_t)j] >= 0 && first_h[(size_t)blk[(size_t)j]] < 0) first_h[(size_t)blk[(size_t)j]] = h[(size_t)j];
+    std::vector<int32_t> first_site_of((size_t)n_sites, -1);
     for (int64_t j = 0; j < n_sites; j++) {
-        const int32_t root = dsu.find((int32_t)j);
-        if (bsize[(size_t)root] >= 2 && soff[(size_t)j + 1] > soff[(size_t)j]) { site_hap[j] = h[(size_t)j]; site_block[j] = root; }
+        if (h[(size_t)j] < 0) continue;
+        const int32_t b = blk[(size_t)j];
+        if (first_site_of[(size_t)b] < 0) first_site_of[(size_t)b] = (int32_t)j;
+        site_hap[j] = (int8_t)(h[(size_t)j] ^ first_h[(size_t)b]);
+        site_block[j] = first_site_of[(size_t)b];
     }
     // haplotag every read against the phased sites; the block with the strongest evidence gives the tag
     for (int64_t r = 0; r < n_reads; r++) {

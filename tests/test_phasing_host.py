@@ -179,3 +179,33 @@ def test_cli_phase_stage_from_a_pass_vcf(tmp_path):
     agree, total = _block_agreement(truth, w.reads.hp, w.reads.ps)
     assert total >= 0.9 * w.reads.n and agree >= 0.99 * total
     sources.unregister_all()
+
+
+@pytest.mark.parametrize("preset,cov,het", [("ont", 30.0, 1000), ("ont", 12.0, 1000), ("ont", 30.0, 8000), ("hifi", 15.0, 3000)])
+def test_false_heterozygous_calls_do_not_disturb_the_phasing(preset, cov, het):
+    """A third more sites that are no variants at all (every read shows the reference base up to sequencing errors): they stay unphased
+    and the reads are tagged exactly as without them."""
+    from nanocaller_b200.host import phasing
+    w = _world(chrom="chrJ", preset=preset, contig_len=1_000_000, seed=61, coverage=cov, het_every=het, hom_every=3000)
+    rs = w.reads
+    truth = rs.hp.copy()
+    lines = _truth_lines(w, hom_too=False)
+    _, st0 = phasing.phase_snp_records(lines, rs)
+    hp0, ps0 = rs.hp.copy(), rs.ps.copy()
+    have = {int(l.split("\t")[1]) for l in lines}
+    rng = np.random.RandomState(4)
+    junk = []
+    for p in rng.choice(np.arange(1000, 999_000), size=max(20, len(lines) // 3), replace=False).tolist():
+        ref = chr(rs.ref[p - 1])
+        if p in have or ref not in "ACGT":
+            continue
+        alt = [c for c in "ACGT" if c != ref][rng.randint(3)]
+        junk.append("%s\t%d\t.\t%s\t%s\t30.00\tPASS\t.\tGT:DP:VF:AD:ADF:ADR\t0/1:30:0.5000:15,15:8,7:7,8\n" % (rs.chrom, p, ref, alt))
+    mixed = sorted(lines + junk, key=lambda l: int(l.split("\t")[1]))
+    out, st = phasing.phase_snp_records(mixed, rs)
+    assert st["het_sites"] == st0["het_sites"] + len(junk) and abs(st["phased_sites"] - st0["phased_sites"]) <= 0.01 * st0["phased_sites"]
+    junk_phased = sum("|" in ln.split("\t")[9] for ln in out if int(ln.split("\t")[1]) not in have)
+    assert junk_phased <= 0.02 * len(junk)              # at low coverage two sequencing errors can make a false site look usable
+    assert (rs.hp == hp0).mean() >= 0.995
+    agree, total = _block_agreement(truth, rs.hp, rs.ps)
+    assert total >= (0.8 if het >= 8000 else 0.95) * rs.n and agree >= 0.995 * total, (agree, total, rs.n)
