@@ -140,9 +140,11 @@ def get_regions_list(args, contig_lengths):
     return [tuple(r) for r in regions]
 
 
-def get_chunks(regions_list, cpu, max_chunk_size=500000, min_chunk_size=10000):
-    """utils.py:67-83: inclusive chunk ends, shared between neighbours."""
-    total = sum(r[2] - r[1] + 1 for r in regions_list)
+def get_chunks(regions_list, cpu, max_chunk_size=500000, min_chunk_size=10000, total=None):
+    """utils.py:67-83: inclusive chunk ends, shared between neighbours.  `total`: the base count that sizes the chunks when
+    `regions_list` is one rank's share of a multi-GPU run (host/multi.py) — the reference sums over ALL regions (:72)."""
+    if total is None:
+        total = sum(r[2] - r[1] + 1 for r in regions_list)
     size = min(max_chunk_size, max(min_chunk_size, total // cpu + 1))
     return [{"chrom": c, "start": s, "end": min(end, s + size), "ploidy": pl}
             for c, start, end, pl in regions_list for s in range(start, end, size)]
@@ -241,7 +243,7 @@ def run(args):
         if tensors is None:
             print("Invalid SNP model name or path", flush=True)     # snpCaller.py:66-68
             raise SystemExit(2)
-        chunks = get_chunks(regions, args.cpu)
+        chunks = get_chunks(regions, args.cpu, total=getattr(args, "_total_bases", None))
         hap = None
         if any(c["ploidy"] == "haploid" for c in chunks):
             hap = models.get_SNP_model("haploid", args.nanocaller_src)[0]          # snpCaller.py:74
@@ -268,7 +270,7 @@ def run(args):
         if ind is None:
             print("Invalid indel model name or path", flush=True)
             raise SystemExit(2)
-        chunks = get_chunks(regions, args.cpu, max_chunk_size=100000)
+        chunks = get_chunks(regions, args.cpu, max_chunk_size=100000, total=getattr(args, "_total_bases", None))
         hap_ind = None
         if any(c["ploidy"] == "haploid" for c in chunks):
             hap_ind = models.get_indel_model("haploid", args.nanocaller_src)
@@ -303,6 +305,21 @@ def main(argv=None):
         print("\n%s: Please use either --regions or --bed but not both." % datetime.datetime.now(), flush=True)
         raise SystemExit(2)
     print("\n%s: Starting nanocaller_b200.\n" % datetime.datetime.now(), flush=True)
+    from .host import multi
+    rank, world, local = multi.env_world()
+    if world > 1:                                                 # torchrun: one process per GPU, contigs sharded (host/multi.py)
+        import torch
+        import torch.distributed as dist
+        from .host import bamio
+        cuda = torch.cuda.is_available()
+        if cuda:
+            torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl" if cuda else "gloo")
+        regions = get_regions_list(args, bamio.bam_contigs(args.bam))
+        out = multi.run_distributed(args, run, regions, dist, device=("cuda:%d" % local) if cuda else "cpu")
+        print("\n%s: Total Time Elapsed: %.2f seconds" % (datetime.datetime.now(), time.time() - t))
+        return out
     out = run(args)
     print("\n%s: Total Time Elapsed: %.2f seconds" % (datetime.datetime.now(), time.time() - t))
     return out

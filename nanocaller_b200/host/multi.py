@@ -1,0 +1,99 @@
+"""The command line on several GPUs of one box: `python -m torch.distributed.run --nproc-per-node N -m nanocaller_b200 ...`.
+
+The reference fans chunks out to `--cpu` worker processes, each writing its own intermediate VCF, and the parent concatenates
+them (snpCaller.py:204-280, indelCaller.py:340-395).  Here one process drives one GPU.  The sharding unit of the command line is
+the CONTIG: phasing between the stages needs all SNP calls and all reads of a contig in one place (indelCaller.phase_run works
+per contig as well, indelCaller.py:190), and chunks stay what they are on one GPU — the chunk grid is computed from the total of
+ALL regions (utils.py:72), so every record is identical to the single-GPU run.  Contigs go to ranks longest-first onto the least
+loaded rank.  The one exchange is the gather of the ranks' record text to rank 0 (sizes, then padded byte tensors: NCCL on the
+GPU box, gloo in the CPU test), which merges, sorts, compresses and indexes.  (bench.py and host/shard.py shard by chunk.)"""
+import copy
+import os
+
+import numpy as np
+
+
+def env_world():
+    """(rank, world, local_rank) from the torchrun environment; (0, 1, 0) outside it."""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def assign_contigs(regions, world):
+    """regions: (contig, start, end, ploidy) tuples -> list of `world` lists of regions; contigs are kept whole, placed longest
+    first on the least loaded rank (ties: lowest rank), each rank's regions in input order."""
+    span = {}
+    for c, s, e, _ in regions:
+        span[c] = span.get(c, 0) + (e - s + 1)
+    load = [0] * world
+    owner = {}
+    for c in sorted(span, key=lambda c: (-span[c], list(span).index(c))):
+        r = min(range(world), key=lambda r: (load[r], r))
+        owner[c] = r
+        load[r] += span[c]
+    return [[reg for reg in regions if owner[reg[0]] == r] for r in range(world)]
+
+
+def gather_bytes(data, dist, rank, world, device="cpu"):
+    """Every rank contributes a bytes object; rank 0 gets the list of all of them in rank order, the others None."""
+    import torch
+    n = torch.tensor([len(data)], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(max(sizes), 1)
+    buf = torch.zeros(cap, dtype=torch.uint8, device=device)
+    if len(data):
+        buf[:len(data)] = torch.from_numpy(np.frombuffer(data, np.uint8).copy()).to(device)
+    if rank == 0:
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.gather(buf, parts, dst=0)
+        return [p[:s].cpu().numpy().tobytes() for p, s in zip(parts, sizes)]
+    dist.gather(buf, None, dst=0)
+    return None
+
+
+OUTPUT_KINDS = (("unfiltered_snps", "%s.unfiltered.snps.vcf.gz", "snps"), ("snps", "%s.snps.vcf.gz", "snps"),
+                ("phased_snps", "%s.snps.phased.vcf.gz", "phased_snps"), ("indels", "%s.indels.vcf.gz", "indels"),
+                ("final", "%s.vcf.gz", "all"))
+
+
+def run_distributed(args, run_fn, regions, dist, device="cpu"):
+    """Run `run_fn` (cli.run) on this rank's contigs into `{output}/rank{r}` and merge the ranks' records on rank 0 into the
+    reference's output names under `{output}`.  -> rank 0: dict like cli.run's; other ranks: {'rank': r}."""
+    from . import vcfio
+    rank, world, local = env_world()
+    mine = assign_contigs(regions, world)[rank]
+    chrom_list = list(dict.fromkeys(r[0] for r in regions))
+    out_r = {}
+    if mine:
+        sub = copy.copy(args)
+        sub.regions = ["%s:%d-%d" % (c, s, e) for c, s, e, _ in mine]
+        sub.bed = None
+        sub.wgs_contigs = None
+        sub.output = os.path.join(args.output, "rank%d" % rank)
+        sub.device = local
+        sub._total_bases = sum(e - s + 1 for _, s, e, _ in regions)          # utils.py:72 sizes the chunks from ALL regions
+        out_r = run_fn(sub)
+    merged = {"rank": rank, "world": world, "contigs_per_rank": [sorted({r[0] for r in part}) for part in assign_contigs(regions, world)]}
+    for key, name, kind in OUTPUT_KINDS:
+        have = dist_any(key in out_r, dist, world, device)
+        if not have:
+            continue
+        text = "".join(vcfio.read_records(out_r[key])).encode() if key in out_r else b""
+        parts = gather_bytes(text, dist, rank, world, device)
+        if rank == 0:
+            lines = [ln + "\n" for p in parts for ln in p.decode().split("\n") if ln]
+            path = os.path.join(args.output, name % args.prefix)
+            vcfio.write_vcf(path, kind, chrom_list, lines, args.sample, index=True)
+            merged[key] = path
+            merged["n_%s_records" % key] = len(lines)
+    dist.barrier()
+    return merged
+
+
+def dist_any(flag, dist, world, device="cpu"):
+    """True on every rank if `flag` is true on any rank."""
+    import torch
+    t = torch.tensor([1 if flag else 0], dtype=torch.int64, device=device)
+    dist.all_reduce(t)
+    return int(t.item()) > 0

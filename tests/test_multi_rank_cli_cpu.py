@@ -1,0 +1,111 @@
+"""CPU, world_size 2 over gloo: the command line's multi-GPU driver (host/multi.py) — contigs sharded over ranks, every rank running
+the single-GPU flow on its share with the chunk grid of the whole run, record text gathered to rank 0 and merged into the reference's
+output names.  The GPU stages are replaced by a deterministic stand-in (`_fake_run`): this checks the plumbing, not the kernels."""
+import argparse
+import gzip
+import os
+import socket
+
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nanocaller_b200 import cli
+from nanocaller_b200.host import multi, vcfio
+
+REGIONS = [("chr1", 1, 900_000, "diploid"), ("chr2", 1, 400_000, "diploid"), ("chr3", 1, 350_000, "diploid"),
+           ("chrX", 1, 300_000, "diploid"), ("chrY", 1, 100_000, "haploid")]
+CONTIGS = [r[0] for r in REGIONS]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_run(args):
+    """Stand-in for cli.run: one SNP record per chunk start and one indel record per indel chunk of the regions it is given."""
+    os.makedirs(args.output, exist_ok=True)
+    regions = []
+    for r in args.regions:
+        c, se = r.split(":")
+        s, e = se.split("-")
+        regions.append((c, int(s), int(e), "haploid" if c == "chrY" else "diploid"))
+    total = getattr(args, "_total_bases", None)
+    snps = ["%s\t%d\t.\tA\tC\t%d.00\tPASS\t.\tGT:DP:VF:AD:ADF:ADR\t0/1:30:0.5000:15,15:8,7:7,8\n" % (ch["chrom"], ch["start"] + 7, 20 + ch["start"] % 9)
+            for ch in cli.get_chunks(regions, args.cpu, total=total)]
+    indels = ["%s\t%d\t.\tAT\tA\t12.00\tPASS\t.\tGT:GQ\t1/1:9.00\n" % (ch["chrom"], ch["start"] + 3)
+              for ch in cli.get_chunks(regions, args.cpu, max_chunk_size=100000, total=total)]
+    chrom_list = list(dict.fromkeys(r[0] for r in regions))
+    out = {}
+    for key, name, kind in multi.OUTPUT_KINDS:
+        lines = indels if key == "indels" else (snps + indels if key == "final" else snps)
+        out[key] = os.path.join(args.output, name % args.prefix)
+        vcfio.write_vcf(out[key], kind, chrom_list, lines, args.sample, index=True)
+    return out
+
+
+def _args(output):
+    return argparse.Namespace(regions=None, bed=None, wgs_contigs=None, output=output, prefix="t", sample="S", cpu=3, device=0)
+
+
+def _worker(rank, world, port, output, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = multi.run_distributed(_args(output), _fake_run, REGIONS, dist)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_command_line_world2_gloo(tmp_path):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, str(tmp_path / "multi"), q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    single = _args(str(tmp_path / "single"))
+    single.regions = ["%s:%d-%d" % r[:3] for r in REGIONS]
+    want = _fake_run(single)
+    got = res[0]
+    assert got["contigs_per_rank"] == [["chr1", "chrY"], ["chr2", "chr3", "chrX"]] and "snps" not in res[1]
+    for key, name, kind in multi.OUTPUT_KINDS:
+        assert got[key] == str(tmp_path / "multi" / (name % "t")) and os.path.exists(got[key] + ".csi")
+        with gzip.open(got[key], "rt") as f, gzip.open(want[key], "rt") as g:
+            assert f.read() == g.read(), key                  # header, contig order, records: identical to the single-process run
+    q = vcfio.csi_query(got["final"], "chr3", 0, 200_000)
+    assert len(q) > 0 and all(ln.startswith("chr3\t") for ln in q)
+
+
+def test_assign_contigs_keeps_contigs_whole_and_balances():
+    regs = [("a", 1, 1000, "diploid"), ("b", 1, 400, "diploid"), ("a", 2000, 2500, "diploid"), ("c", 1, 700, "diploid"), ("d", 1, 300, "diploid")]
+    for world in (1, 2, 3, 8):
+        parts = multi.assign_contigs(regs, world)
+        assert len(parts) == world and sorted(r for p in parts for r in p) == sorted(regs)
+        owners = {}
+        for k, p in enumerate(parts):
+            for r in p:
+                assert owners.setdefault(r[0], k) == k             # a contig lives on one rank
+            assert p == [r for r in regs if r in p]               # input order kept
+    two = multi.assign_contigs(regs, 2)
+    loads = [sum(e - s + 1 for _, s, e, _ in p) for p in two]
+    assert loads == [1501, 1400]
+
+
+def test_chunk_grid_of_a_share_equals_the_grid_of_the_whole_run():
+    """utils.py:72 sizes the chunks from the total of all regions: a rank that is handed a subset must be told that total."""
+    small = [("c1", 1, 90_000, "diploid"), ("c2", 1, 50_000, "diploid"), ("c3", 1, 30_000, "diploid")]
+    whole = cli.get_chunks(small, 4)
+    total = sum(e - s + 1 for _, s, e, _ in small)
+    parts = multi.assign_contigs(small, 2)
+    again = [c for p in parts for c in cli.get_chunks(p, 4, total=total)]
+    assert sorted(map(str, again)) == sorted(map(str, whole))
+    assert sorted(map(str, [c for p in parts for c in cli.get_chunks(p, 4)])) != sorted(map(str, whole))
