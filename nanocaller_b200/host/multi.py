@@ -64,7 +64,7 @@ def run_distributed(args, run_fn, regions, dist, device="cpu"):
     rank, world, local = env_world()
     mine = assign_contigs(regions, world)[rank]
     chrom_list = list(dict.fromkeys(r[0] for r in regions))
-    out_r = {}
+    out_r, failure = {}, None
     if mine:
         sub = copy.copy(args)
         sub.regions = ["%s:%d-%d" % (c, s, e) for c, s, e, _ in mine]
@@ -73,7 +73,14 @@ def run_distributed(args, run_fn, regions, dist, device="cpu"):
         sub.output = os.path.join(args.output, "rank%d" % rank)
         sub.device = local
         sub._total_bases = sum(e - s + 1 for _, s, e, _ in regions)          # utils.py:72 sizes the chunks from ALL regions
-        out_r = run_fn(sub)
+        try:
+            out_r = run_fn(sub)
+        except BaseException as e:                                # the other ranks must not wait in a collective for this one
+            failure = e
+    if dist_any(failure is not None, dist, world, device):
+        if failure is not None:
+            raise failure
+        raise RuntimeError("nanocaller_b200: another rank failed; rank %d stops" % rank)
     merged = {"rank": rank, "world": world, "contigs_per_rank": [sorted({r[0] for r in part}) for part in assign_contigs(regions, world)]}
     for key, name, kind in OUTPUT_KINDS:
         have = dist_any(key in out_r, dist, world, device)

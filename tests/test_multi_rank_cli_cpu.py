@@ -109,3 +109,35 @@ def test_chunk_grid_of_a_share_equals_the_grid_of_the_whole_run():
     again = [c for p in parts for c in cli.get_chunks(p, 4, total=total)]
     assert sorted(map(str, again)) == sorted(map(str, whole))
     assert sorted(map(str, [c for p in parts for c in cli.get_chunks(p, 4)])) != sorted(map(str, whole))
+
+
+def _failing_run(args):
+    if any(r.startswith("chr2:") for r in args.regions):
+        raise RuntimeError("boom on the rank that owns chr2")
+    return _fake_run(args)
+
+
+def _worker_fail(rank, world, port, output, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        multi.run_distributed(_args(output), _failing_run, REGIONS, dist)
+        q.put((rank, "no error"))
+    except RuntimeError as e:
+        q.put((rank, str(e)))
+    dist.destroy_process_group()
+
+
+def test_a_failing_rank_stops_all_ranks_instead_of_hanging_them(tmp_path):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_fail, args=(r, world, port, str(tmp_path / "f"), q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[1].startswith("boom") and "another rank failed" in res[0]
