@@ -56,6 +56,13 @@ int nc_bam_fill(const nc_bam* b, int i, int threads, int32_t* pos, uint16_t* fla
 /* Query name of read k of contig i (debugging / duplicate-name checks; not needed by the device path). */
 int nc_bam_qname(const nc_bam* b, int i, int64_t k, char* out, int cap);
 
+/* Haplotagged copy of contig i's records into a new BAM file (the reference's intermediate_phase_files/{contig}.phased.bam,
+ * written there by `whatshap haplotag | samtools view -b`, indelCaller.py:244): records are copied whole (names, qualities,
+ * aux fields) except that existing HP / PS fields are dropped and, where hp[k] > 0, `HP:C:hp[k]` and `PS:i:ps[k]` are appended
+ * (k counts the contig's mapped records in file order, as nc_bam_fill does).  The header keeps all references.  No index is
+ * written.  level: zlib level 0..9; threads <= 0: all cores. */
+int nc_bam_write_tagged(const nc_bam* b, int i, const int8_t* hp, const int32_t* ps, const char* out_path, int level, int threads);
+
 void nc_bam_close(nc_bam* b);
 
 #ifdef __cplusplus

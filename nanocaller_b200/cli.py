@@ -68,6 +68,9 @@ def build_parser():
     p.add_argument("--win_size", type=int, default=40)
     p.add_argument("--small_win_size", type=int, default=4)
     p.add_argument("--impute_indel_phase", action="store_true", default=False)
+    p.add_argument("--write_phased_bam", action="store_true", default=False,
+                   help="also write intermediate_phase_files/{contig}.phased.bam (indelCaller.py:244): the contig's records copied whole with "
+                        "the HP / PS tags of the phasing step. The indel stage does not need the file (the tags are staged from memory).")
     p.add_argument("--decompose_indels", action="store_true", default=False,
                    help="normalise the indel records like the reference's `rtg vcfdecompose | rtg vcffilter --non-snps-only` step "
                         "(indelCaller.py:391) with this package's own rule set (host/vcf_decompose.py); the records as the indel stage "
@@ -209,6 +212,11 @@ def _phase_stage(args, regions, chrom_list, out):
         new_lines, st = phasing.phase_snp_records(lines_c, rs, args.phase_qual_score, supplementary=args.supplementary)
         phased_lines += new_lines
         pstats[chrom] = st
+        if args.write_phased_bam and os.path.exists(args.bam):
+            from .host import bamio
+            pdir = os.path.join(args.output, "intermediate_phase_files")
+            os.makedirs(pdir, exist_ok=True)
+            st["phased_bam"] = bamio.write_haplotagged_bam(args.bam, chrom, rs.hp, rs.ps, os.path.join(pdir, "%s.phased.bam" % chrom))
     php = os.path.join(args.output, "%s.snps.phased.vcf.gz" % args.prefix)
     vcfio.write_vcf(php, "phased_snps", chrom_list, phased_lines, args.sample, index=True)
     out.update(phased_snps=php, phase_stats=pstats, phase_seconds=time.time() - t1)

@@ -470,6 +470,105 @@ int nc_bam_qname(const nc_bam* b, int i, int64_t k, char* out, int cap) {
     return NC_IO_OK;
 }
 
+// Haplotagged copy of one contig's records (what `whatshap haplotag ... | samtools view -b` leaves in
+// intermediate_phase_files/{contig}.phased.bam, indelCaller.py:244): every record is copied as it is — name, qualities and all
+// other aux fields — with its HP / PS fields removed and, where hp[k] > 0, `HP:C` and `PS:i` appended.  The header lists all
+// references of the source file.  BGZF blocks of <= 0xff00 payload bytes are deflated in parallel.
+int nc_bam_write_tagged(const nc_bam* b, int i, const int8_t* hp, const int32_t* ps, const char* out_path, int level, int threads) {
+    if (!b || !out_path || i < 0 || i >= (int)b->contigs.size()) return NC_IO_EINVAL;
+    const Contig& c = b->contigs[(size_t)i];
+    if (c.n_reads > 0 && (!hp || !ps)) return NC_IO_EINVAL;
+    std::vector<uint8_t> u;
+    auto put32 = [&](int32_t v) { uint8_t t[4]; memcpy(t, &v, 4); u.insert(u.end(), t, t + 4); };
+    u.insert(u.end(), {'B', 'A', 'M', 1});
+    put32((int32_t)b->text.size());
+    u.insert(u.end(), b->text.begin(), b->text.end());
+    put32((int32_t)b->contigs.size());
+    for (const Contig& k : b->contigs) {
+        put32((int32_t)k.name.size() + 1);
+        u.insert(u.end(), k.name.begin(), k.name.end());
+        u.push_back(0);
+        put32(k.length);
+    }
+    const uint8_t* d = b->data.data();
+    for (int64_t k = 0; k < c.n_reads; k++) {
+        const size_t off = (size_t)b->rec_off[(size_t)(c.first_rec + k)];
+        const int32_t bs = rd<int32_t>(d + off);
+        const uint8_t* r = d + off + 4;
+        const uint8_t l_name = r[8];
+        const uint16_t n_cig = rd<uint16_t>(r + 12);
+        const int32_t l_seq = rd<int32_t>(r + 16);
+        const size_t fixed = 32 + (size_t)l_name + 4 * (size_t)n_cig + (size_t)(l_seq + 1) / 2 + (size_t)l_seq;
+        const size_t at = u.size();
+        put32(0);                                               // block_size, patched below
+        u.insert(u.end(), r, r + fixed);
+        const uint8_t* p = r + fixed;
+        const uint8_t* end = r + bs;
+        while (p + 3 <= end) {                                  // copy every aux field except HP / PS
+            const uint8_t* f0 = p;
+            const uint8_t t0 = p[0], t1 = p[1], type = p[2];
+            p += 3;
+            const int fs = aux_size(type);
+            if (fs > 0) p += fs;
+            else if (type == 'Z' || type == 'H') { while (p < end && *p) p++; p++; }
+            else if (type == 'B') {
+                if (p + 5 > end) { p = end; break; }
+                const int es = aux_size(p[0]);
+                const int32_t cnt = rd<int32_t>(p + 1);
+                if (es < 0 || cnt < 0) { p = end; break; }
+                p += 5 + (size_t)es * (size_t)cnt;
+            } else { p = end; }                                 // unknown type: keep the rest verbatim
+            if (p > end) p = end;
+            const bool drop = (t0 == 'H' && t1 == 'P') || (t0 == 'P' && t1 == 'S');
+            if (!drop) u.insert(u.end(), f0, p);
+        }
+        if (p < end) u.insert(u.end(), p, end);
+        if (hp[k] > 0) {
+            u.insert(u.end(), {'H', 'P', 'C', (uint8_t)hp[k], 'P', 'S', 'i'});
+            put32(ps[k]);
+        }
+        const int32_t nbs = (int32_t)(u.size() - at - 4);
+        memcpy(u.data() + at, &nbs, 4);
+    }
+    // BGZF
+    const size_t kPayload = 0xff00;
+    const int64_t nblk = (int64_t)((u.size() + kPayload - 1) / kPayload);
+    std::vector<std::vector<uint8_t>> out((size_t)nblk);
+    std::atomic<int> bad{0};
+    if (level < 0 || level > 9) level = 4;
+    parallel_for(nblk, threads, [&](int64_t j) {
+        const size_t o = (size_t)j * kPayload, n = std::min(kPayload, u.size() - o);
+        std::vector<uint8_t>& blk = out[(size_t)j];
+        blk.resize(18 + compressBound((uLong)n) + 8);
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad = 1; return; }
+        zs.next_in = u.data() + o; zs.avail_in = (uInt)n;
+        zs.next_out = blk.data() + 18; zs.avail_out = (uInt)(blk.size() - 18 - 8);
+        const int rc = deflate(&zs, Z_FINISH);
+        const size_t cs = zs.total_out;
+        deflateEnd(&zs);
+        if (rc != Z_STREAM_END || 18 + cs + 8 > 0x10000) { bad = 1; return; }
+        static const uint8_t head[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+        memcpy(blk.data(), head, 16);
+        const uint16_t bsize = (uint16_t)(18 + cs + 8 - 1);
+        memcpy(blk.data() + 16, &bsize, 2);
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), u.data() + o, (uInt)n), isz = (uint32_t)n;
+        memcpy(blk.data() + 18 + cs, &crc, 4);
+        memcpy(blk.data() + 18 + cs + 4, &isz, 4);
+        blk.resize(18 + cs + 8);
+    });
+    if (bad) return NC_IO_EFORMAT;
+    FILE* f = fopen(out_path, "wb");
+    if (!f) return NC_IO_EOPEN;
+    bool ok = true;
+    for (auto& blk : out) ok = ok && fwrite(blk.data(), 1, blk.size(), f) == blk.size();
+    static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    ok = ok && fwrite(eof, 1, 28, f) == 28;
+    ok = (fclose(f) == 0) && ok;
+    return ok ? NC_IO_OK : NC_IO_EOPEN;
+}
+
 void nc_bam_close(nc_bam* b) { delete b; }
 
 }  // extern "C"

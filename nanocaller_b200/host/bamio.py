@@ -275,7 +275,7 @@ class NcBamContig(ctypes.Structure):                     # include/nanocaller_b2
 
 
 IO_EXPORTS = ["nc_bam_open", "nc_bam_open_region", "nc_bam_error", "nc_bam_n_contigs", "nc_bam_header_text", "nc_bam_contig", "nc_bam_fill",
-              "nc_bam_qname", "nc_bam_close"]
+              "nc_bam_qname", "nc_bam_write_tagged", "nc_bam_close"]
 
 
 def load_io_library():
@@ -296,6 +296,7 @@ def load_io_library():
         lib.nc_bam_contig.argtypes = [vp, ctypes.c_int, ctypes.POINTER(NcBamContig)]
         lib.nc_bam_fill.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 9
         lib.nc_bam_qname.argtypes = [vp, ctypes.c_int, ctypes.c_int64, ctypes.c_char_p, ctypes.c_int]
+        lib.nc_bam_write_tagged.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
         lib.nc_bam_close.argtypes = [vp]; lib.nc_bam_close.restype = None
         _LIB = lib
     return _LIB
@@ -362,6 +363,44 @@ def read_bam_native(path, fasta=None, contigs=None, threads=0, alloc=None, qname
     finally:
         if h:
             lib.nc_bam_close(h)
+
+
+def write_haplotagged_bam(path, chrom, hp, ps, out_path, level=4, threads=0):
+    """`{contig}.phased.bam` of the reference (indelCaller.py:244-245): the records of `chrom` in `path`, copied whole, with HP / PS
+    replaced by the given per-read tags (file order of the contig's mapped records, i.e. the ReadSet's order).  Uses the BAI when
+    there is one, so only that contig is inflated."""
+    lib = load_io_library()
+    h = ctypes.c_void_p()
+    bai = find_bai(path)
+    if bai:
+        arr = (ctypes.c_char_p * 1)(chrom.encode())
+        rc = lib.nc_bam_open_region(os.fsencode(path), os.fsencode(bai), arr, 1, int(threads), ctypes.byref(h))
+    else:
+        rc = lib.nc_bam_open(os.fsencode(path), int(threads), ctypes.byref(h))
+    try:
+        if rc != 0:
+            raise ValueError("%s: %s" % (path, (lib.nc_bam_error(h) or b"").decode() if h else "open failed"))
+        idx = -1
+        c = NcBamContig()
+        for i in range(lib.nc_bam_n_contigs(h)):
+            lib.nc_bam_contig(h, i, ctypes.byref(c))
+            if c.name.decode() == chrom:
+                idx = i
+                break
+        if idx < 0:
+            raise KeyError("contig %r is not in %s" % (chrom, path))
+        hp = np.ascontiguousarray(hp, np.int8)
+        ps = np.ascontiguousarray(ps, np.int32)
+        if len(hp) != c.n_reads or len(ps) != c.n_reads:
+            raise ValueError("%d tags for %d records of %s" % (len(hp), c.n_reads, chrom))
+        rc = lib.nc_bam_write_tagged(h, idx, hp.ctypes.data_as(ctypes.c_void_p), ps.ctypes.data_as(ctypes.c_void_p), os.fsencode(out_path),
+                                     int(level), int(threads))
+        if rc != 0:
+            raise IOError("nc_bam_write_tagged(%s) failed (%d)" % (out_path, rc))
+    finally:
+        if h:
+            lib.nc_bam_close(h)
+    return out_path
 
 
 def bam_contigs(path):

@@ -259,3 +259,36 @@ def test_csi_index_round_trip(tmp_path):
     # bin arithmetic against the values of the specification's own examples
     assert vcfio._reg2bin(0, 1) == 4681 and vcfio._reg2bin(0, 16385) == 585 and vcfio._reg2bin(16384, 32768) == 4682
     assert vcfio._bin_first_window(4681) == 0 and vcfio._bin_first_window(585) == 0 and vcfio._bin_first_window(586) == 8 and vcfio._bin_first_window(1) == 0
+
+
+def test_haplotagged_bam_copy(tmp_path):
+    """nc_bam_write_tagged: the records of one contig copied whole with new HP / PS tags — read back by the native reader and by the
+    pure-Python parser; existing tags are replaced, untagged reads carry none, names survive."""
+    import numpy as np
+    from nanocaller_b200.host import bamio
+    from nanocaller_b200.synth import make_world
+    a = make_world(chrom="chrA", preset="ont", contig_len=60_000, seed=31, coverage=12.0, untagged_frac=0.3).reads
+    b = make_world(chrom="chrB", preset="ont", contig_len=30_000, seed=32, coverage=8.0).reads
+    src = str(tmp_path / "s.bam")
+    bamio.write_bam(src, [a, b], index=True)
+    rng = np.random.RandomState(3)
+    hp = rng.randint(0, 3, a.n).astype(np.int8)
+    ps = np.where(hp > 0, rng.randint(1, 60_000, a.n), 0).astype(np.int32)
+    assert (a.hp != hp).any()
+    for use_bai in (True, False):
+        if not use_bai:
+            import os
+            os.remove(src + ".bai")
+        out = bamio.write_haplotagged_bam(src, "chrA", hp, ps, str(tmp_path / ("chrA.phased.%d.bam" % use_bai)), threads=3)
+        for reader in (bamio.read_bam_native, bamio.read_bam):
+            got = {r.chrom: r for r in reader(out)[0]}
+            assert "chrB" not in got or got["chrB"].n == 0                # header keeps both references, records are chrA's only
+            g = got["chrA"]
+            for f in ("pos", "flag", "cigar_off", "cigar", "seq_off", "l_seq", "seq4"):
+                assert np.array_equal(getattr(g, f), getattr(a, f)), f
+            assert np.array_equal(g.hp, hp) and np.array_equal(g.ps[hp > 0], ps[hp > 0]) and not g.ps[hp == 0].any()
+        names = [r for r in bamio.read_bam_native(out, qnames=True)[0] if r.chrom == "chrA"][0]
+        assert [names.qname(k) for k in (0, 1, a.n - 1)] == [a.qname(k) for k in (0, 1, a.n - 1)]
+    import pytest
+    with pytest.raises(ValueError):
+        bamio.write_haplotagged_bam(src, "chrA", hp[:-1], ps[:-1], str(tmp_path / "x.bam"))

@@ -209,3 +209,31 @@ def test_false_heterozygous_calls_do_not_disturb_the_phasing(preset, cov, het):
     assert (rs.hp == hp0).mean() >= 0.995
     agree, total = _block_agreement(truth, rs.hp, rs.ps)
     assert total >= (0.8 if het >= 8000 else 0.95) * rs.n and agree >= 0.995 * total, (agree, total, rs.n)
+
+
+def test_cli_phase_stage_writes_the_haplotagged_bam(tmp_path):
+    """--write_phased_bam: intermediate_phase_files/{contig}.phased.bam carries the tags the phasing step gave the reads (indelCaller.py:244)."""
+    from nanocaller_b200 import cli
+    from nanocaller_b200.host import bamio, sources, vcfio
+    w = _world(chrom="chrV", preset="ont", contig_len=80_000, seed=57, coverage=20.0, het_every=1000, hom_every=0)
+    rs = w.reads
+    lines = _truth_lines(w)
+    rs.hp[:] = 0
+    rs.ps[:] = 0
+    bam, fa = str(tmp_path / "v.bam"), str(tmp_path / "v.fa")
+    bamio.write_bam(bam, [rs], index=True)
+    bamio.write_fasta(fa, [rs])
+    passp = str(tmp_path / "t.snps.vcf.gz")
+    vcfio.write_vcf(passp, "snps", ["chrV"], lines, "S", index=True)
+    sources.unregister_all()
+    bamio.open_alignment(bam, fa, contigs={"chrV"})
+    args = cli.parse_args(["--bam", bam, "--ref", fa, "--mode", "all", "--preset", "ont", "--output", str(tmp_path), "--prefix", "t", "--write_phased_bam"])
+    out = {"snps": passp}
+    cli._phase_stage(args, [("chrV", 1, 80_000, "diploid")], ["chrV"], out)
+    pb = out["phase_stats"]["chrV"]["phased_bam"]
+    assert pb == str(tmp_path / "intermediate_phase_files" / "chrV.phased.bam")
+    mem = sources.resolve(bam, "chrV")
+    got = [r for r in bamio.read_bam_native(pb)[0] if r.chrom == "chrV"][0]
+    assert int((mem.hp > 0).sum()) > 0.9 * mem.n
+    assert np.array_equal(got.hp, mem.hp) and np.array_equal(got.ps, mem.ps) and np.array_equal(got.pos, mem.pos)
+    sources.unregister_all()
