@@ -237,3 +237,35 @@ def test_cli_phase_stage_writes_the_haplotagged_bam(tmp_path):
     assert int((mem.hp > 0).sum()) > 0.9 * mem.n
     assert np.array_equal(got.hp, mem.hp) and np.array_equal(got.ps, mem.ps) and np.array_equal(got.pos, mem.pos)
     sources.unregister_all()
+
+
+def test_two_alternative_alleles_are_phased_like_ref_alt():
+    """`1/2` calls (both haplotypes non-reference): allele A = ALT1, B = ALT2.  Rewriting 0/1 records (REF r, ALT a) as 1/2 records over a
+    third base (REF x, ALT r,a) must give the same phase: `0|1` <-> `1|2`, `1|0` <-> `2|1`, same PS, same read tags."""
+    from nanocaller_b200.host import phasing
+    w = _world(chrom="chrM2", preset="ont", contig_len=150_000, seed=58, coverage=25.0, het_every=1200, hom_every=0)
+    rs = w.reads
+    lines = _truth_lines(w)
+    out01, st01 = phasing.phase_snp_records(lines, rs)
+    hp01 = rs.hp.copy()
+    alt_lines = []
+    for k, ln in enumerate(lines):
+        f = ln.rstrip("\n").split("\t")
+        if k % 2 == 0:
+            x = [c for c in "ACGT" if c not in (f[3], f[4])][0]
+            f[3], f[4] = x, f[3] + "," + f[4]
+            f[9] = "1/2" + f[9][3:]
+        alt_lines.append("\t".join(f) + "\n")
+    out12, st12 = phasing.phase_snp_records(alt_lines, rs)
+    assert st12 == st01 and np.array_equal(rs.hp, hp01)
+    conv = {"0|1": "1|2", "1|0": "2|1"}
+    n = 0
+    for k, (a, b) in enumerate(zip(out01, out12)):
+        ga, gb = a.rstrip("\n").split("\t")[9], b.rstrip("\n").split("\t")[9]
+        if "|" not in ga:
+            assert "|" not in gb
+            continue
+        want = conv[ga[:3]] if k % 2 == 0 else ga[:3]
+        assert gb[:3] == want and gb.rsplit(":", 1)[1] == ga.rsplit(":", 1)[1]
+        n += 1
+    assert n > 80
