@@ -3,7 +3,7 @@
  * Replaces what the reference delegates to an external program between its two stages:
  *   `whatshap phase`    indelCaller.py:237   heterozygous SNP calls (QUAL >= --phase_qual_score, :232) -> phased genotypes + PS
  *   `whatshap haplotag` indelCaller.py:244   reads -> HP / PS tags, which generate_indel_pileups.py:180-188 then reads
- * WhatsHap itself is not part of the reference repository (environment.yml:13) and cannot be had in this image, so this
+ * WhatsHap itself is not part of the reference repository (environment.yml:15) and cannot be had in this image, so this
  * is a separately specified algorithm, validated against the synthetic generator's true haplotypes —
  * "parity unpinned" against WhatsHap.  Plain C ABI, host memory only, no CUDA: it runs between the GPU stages.
  *
