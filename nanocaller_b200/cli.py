@@ -191,6 +191,9 @@ def _phase_stage(args, regions, chrom_list, out):
     reads (host/phasing.py); haploid contigs pass through (:191-199).  Writes `{prefix}.snps.phased.vcf.gz` (:360)."""
     from .host import phasing, sources, vcfio
     t1 = time.time()
+    if getattr(args, "enable_whatshap", False):
+        print("\n%s: note: --enable_whatshap (WhatsHap's --distrust-genotypes --include-homozygous, indelCaller.py:225) is not reproduced: "
+              "genotypes are phased as called." % datetime.datetime.now(), flush=True)
     by_chrom = {}
     for ln in vcfio.read_records(out["snps"]):
         by_chrom.setdefault(ln.split("\t", 1)[0], []).append(ln)
