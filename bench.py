@@ -37,7 +37,7 @@ MODEL = "ONT-HG002"
 
 def workload(rank, length):
     from nanocaller_b200.synth import make_world
-    from oracle.snp_oracle import get_chunks       # bench.py may use the oracle for the CPU arm / chunk grid only
+    from nanocaller_b200.cli import get_chunks     # the product's chunk grid (utils.py:67-83); oracle/ is only used by the CPU arm
     rs = make_world(chrom="chr20", preset="ont", contig_len=length, seed=20 + rank, coverage=30.0).reads
     chunks = get_chunks([("chr20", 1, length, "diploid")], 1)
     return rs, chunks
@@ -369,7 +369,7 @@ def main():
         tmpd = tempfile.mkdtemp(prefix="nc_bench_")
         bam_p, fa_p = os.path.join(tmpd, "d.bam"), os.path.join(tmpd, "d.fa")
         bamio.write_bam(bam_p, [rs_d]); bamio.write_fasta(fa_p, [rs_d])
-        from oracle.snp_oracle import get_chunks as _gc
+        from nanocaller_b200.cli import get_chunks as _gc
         ch_d = [(c["start"], c["end"]) for c in _gc([("chr20", 1, args.from_bam, "diploid")], 1)]
 
         arena = {"buf": None, "off": 0}
