@@ -79,59 +79,51 @@ def components(pos, ref, alt):
 
 def decompose_records(lines, contigs=None, keep_snps=False):
     """Record lines of the indel stage -> normalised record lines (rules 1-5)."""
-    out = []                                                 # (contig rank, pos, seq no, fields)
     rank = {}
     for ln in lines:
-        f = ln.rstrip("\n").split("\t")
-        rank.setdefault(f[0], len(rank))
+        rank.setdefault(ln.split("\t", 1)[0], len(rank))
     if contigs:
         rank = {c: i for i, c in enumerate(contigs)}
+    out = []                                                 # (contig rank, pos, input order, emit order, fields, ref, alt, gt)
     for n, ln in enumerate(lines):
         f = ln.rstrip("\n").split("\t")
         pos, ref, alts = int(f[1]), f[3], f[4].split(",")
-        sample = f[9].split(":")
-        gt = sample[0]
+        gt = f[9].split(":", 1)[0]
         sep = "|" if "|" in gt else "/"
-        two = len(alts) == 2 and sorted(gt.replace("|", "/").split("/")) == ["1", "2"]
-        comps = {}                                           # (pos, ref, alt) -> set of allele indices carrying it
-        order = []
+        idx = gt.replace("|", "/").split("/")
+        two = len(alts) == 2 and sorted(idx) == ["1", "2"]
+        found = {}                                           # (pos, ref, alt) -> haplotypes (0 left of the bar, 1 right) carrying it
         for k, alt in enumerate(alts):
-            for (p, r, a, kind) in components(pos, ref, alt):
+            hap = idx.index(str(k + 1)) if two else None
+            for p, r, a, kind in components(pos, ref, alt):
                 if kind == "snp" and not keep_snps:
                     continue
-                key = (p, r, a)
-                if key not in comps:
-                    comps[key] = set(); order.append(key)
-                comps[key].add(k)
-        first_is_1 = gt.replace("|", "/").split("/")[0] == "1"
-        merged = {}                                          # same POS + REF with different ALTs from the two alleles -> one 1|2 record
-        for key in order:
-            p, r, a = key
-            if two:
-                ks = comps[key]
-                if len(ks) == 2:
-                    g = "1" + sep + "1"
-                else:
-                    k = next(iter(ks))
-                    on_first = (k == 0) == first_is_1        # allele index 0 is ALT '1'
-                    g = ("1" + sep + "0") if on_first else ("0" + sep + "1")
-                    other = merged.get((p, r))
-                    if other is not None and other[2] != g and len(other[3]) == 1 and "1" + sep + "1" not in (other[2], g):
-                        a1, a2_ = (other[1], a) if other[2].startswith("1") else (a, other[1])
-                        other[1], other[2] = a1 + "," + a2_, "1" + sep + "2"
-                        other[3].append(k)
-                        continue
-                rec = [p, a, g, [0]]
-                merged.setdefault((p, r), rec)
-                out.append((rank.get(f[0], len(rank)), p, n, f, r, rec))
-            else:
-                rec = [p, a, gt, [0]]
-                out.append((rank.get(f[0], len(rank)), p, n, f, r, rec))
-    out.sort(key=lambda t: (t[0], t[1], t[2]))
+                found.setdefault((p, r, a), set()).add(hap)
+        emit = []                                            # [pos, ref, alt, gt] in order of first appearance
+        if not two:
+            emit = [[p, r, a, gt] for (p, r, a) in found]
+        else:
+            by_site = {}
+            for (p, r, a), haps in found.items():
+                if len(haps) == 2:
+                    emit.append([p, r, a, "1" + sep + "1"])
+                    continue
+                h = next(iter(haps))
+                mate = by_site.get((p, r))
+                if mate is not None and mate[4] != h:        # two different ALTs on the same POS and REF, one per haplotype: 1|2 again
+                    first, second = (mate[2], a) if mate[4] == 0 else (a, mate[2])
+                    mate[2], mate[3] = first + "," + second, "1" + sep + "2"
+                    continue
+                rec = [p, r, a, ("1" + sep + "0") if h == 0 else ("0" + sep + "1"), h]
+                by_site.setdefault((p, r), rec)
+                emit.append(rec)
+        for e, rec in enumerate(emit):
+            out.append((rank.get(f[0], len(rank)), rec[0], n, e, f, rec[1], rec[2], rec[3]))
+    out.sort(key=lambda t: t[:4])
     res = []
-    for _, p, _, f, r, rec in out:
-        g = list(f)
-        g[1], g[3], g[4] = str(p), r, rec[1]
-        g[9] = ":".join([rec[2]] + f[9].split(":")[1:])
-        res.append("\t".join(g) + "\n")
+    for _, p, _, _, f, r, a, g in out:
+        h = list(f)
+        h[1], h[3], h[4] = str(p), r, a
+        h[9] = ":".join([g] + f[9].split(":")[1:])
+        res.append("\t".join(h) + "\n")
     return res
