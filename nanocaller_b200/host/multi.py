@@ -1,11 +1,12 @@
 """The command line on several GPUs of one box: `python -m torch.distributed.run --nproc-per-node N -m nanocaller_b200 ...`.
 
 The reference fans chunks out to `--cpu` worker processes, each writing its own intermediate VCF, and the parent concatenates
-them (snpCaller.py:204-280, indelCaller.py:340-395).  Here one process drives one GPU.  The sharding unit of the command line is
-the CONTIG: phasing between the stages needs all SNP calls and all reads of a contig in one place (indelCaller.phase_run works
-per contig as well, indelCaller.py:190), and chunks stay what they are on one GPU — the chunk grid is computed from the total of
-ALL regions (utils.py:72), so every record is identical to the single-GPU run.  Contigs go to ranks longest-first onto the least
-loaded rank.  The one exchange is the gather of the ranks' record text to rank 0 (sizes, then padded byte tensors: NCCL on the
+them (snpCaller.py:204-280, indelCaller.py:340-395).  Here one process drives one GPU.  When phasing or indel calling is part
+of the run the sharding unit is the CONTIG: phasing between the stages needs all SNP calls and all reads of a contig in one place
+(indelCaller.phase_run works per contig as well, indelCaller.py:190); contigs go to ranks longest-first onto the least loaded
+rank.  `--mode snps` without `--phase` has no such coupling and is cut into contiguous runs of chunks instead, so one long contig
+spreads over all GPUs.  Either way chunks stay what they are on one GPU — the chunk grid is computed from the total of ALL regions
+(utils.py:72) — so every record is identical to the single-GPU run.  The one exchange is the gather of the ranks' record text to rank 0 (sizes, then padded byte tensors: NCCL on the
 GPU box, gloo in the CPU test), which merges, sorts, compresses and indexes.  (bench.py and host/shard.py shard by chunk.)"""
 import copy
 import os
@@ -31,6 +32,44 @@ def assign_contigs(regions, world):
         owner[c] = r
         load[r] += span[c]
     return [[reg for reg in regions if owner[reg[0]] == r] for r in range(world)]
+
+
+def _contiguous_partition(weights, world):
+    """Indices 0..n-1 cut into `world` contiguous runs of about equal weight; every rank gets at least one item when n >= world."""
+    n, out, i, rem = len(weights), [], 0, float(sum(weights))
+    for r in range(world):
+        left = world - r
+        if left == 1:
+            out.append(list(range(i, n)))
+            break
+        target, j, acc = rem / left, i, 0.0
+        while j < n and (n - j) > (left - 1) and (acc == 0.0 or acc + weights[j] / 2.0 <= target):
+            acc += weights[j]
+            j += 1
+        out.append(list(range(i, j)))
+        rem -= acc
+        i = j
+    return out
+
+
+def assign_chunk_runs(regions, world, cpu):
+    """SNP calling without phasing has no coupling between chunks (snpCaller.py:83-86), so a single long contig can be split as well:
+    the chunk grid of the whole run (utils.py:67-83) is cut into `world` contiguous, balanced runs (host/shard.py) and every run is
+    handed over as regions that start and end on grid points — `get_chunks(share, cpu, total=whole run)` then reproduces exactly the
+    chunks of that run, shared boundaries included.  -> list of `world` lists of (contig, start, end, ploidy)."""
+    from ..cli import get_chunks
+    chunks = get_chunks(regions, cpu)
+    out = []
+    for idxs in _contiguous_partition([c["end"] - c["start"] + 1 for c in chunks], world):
+        regs = []
+        for i in idxs:
+            c = chunks[i]
+            if regs and regs[-1][0] == c["chrom"] and regs[-1][2] == c["start"] and regs[-1][3] == c["ploidy"]:
+                regs[-1][2] = c["end"]
+            else:
+                regs.append([c["chrom"], c["start"], c["end"], c["ploidy"]])
+        out.append([tuple(r) for r in regs])
+    return out
 
 
 def gather_bytes(data, dist, rank, world, device="cpu"):
@@ -62,7 +101,9 @@ def run_distributed(args, run_fn, regions, dist, device="cpu"):
     reference's output names under `{output}`.  -> rank 0: dict like cli.run's; other ranks: {'rank': r}."""
     from . import vcfio
     rank, world, local = env_world()
-    mine = assign_contigs(regions, world)[rank]
+    by_chunk = getattr(args, "mode", "all") == "snps" and not getattr(args, "phase", False)
+    shares = assign_chunk_runs(regions, world, args.cpu) if by_chunk else assign_contigs(regions, world)
+    mine = shares[rank]
     chrom_list = list(dict.fromkeys(r[0] for r in regions))
     out_r, failure = {}, None
     if mine:
@@ -81,7 +122,8 @@ def run_distributed(args, run_fn, regions, dist, device="cpu"):
         if failure is not None:
             raise failure
         raise RuntimeError("nanocaller_b200: another rank failed; rank %d stops" % rank)
-    merged = {"rank": rank, "world": world, "contigs_per_rank": [sorted({r[0] for r in part}) for part in assign_contigs(regions, world)]}
+    merged = {"rank": rank, "world": world, "sharding": "chunk runs" if by_chunk else "contigs",
+              "contigs_per_rank": [sorted({r[0] for r in part}) for part in shares], "regions_per_rank": shares}
     for key, name, kind in OUTPUT_KINDS:
         have = dist_any(key in out_r, dist, world, device)
         if not have:

@@ -141,3 +141,60 @@ def test_a_failing_rank_stops_all_ranks_instead_of_hanging_them(tmp_path):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res[1].startswith("boom") and "another rank failed" in res[0]
+
+
+def test_chunk_runs_reproduce_the_grid_of_the_whole_run():
+    """`--mode snps`: the ranks' regions start and end on grid points, and their chunk lists put together are the grid of the whole run,
+    in order, for small (grid sized by total // cpu) and large (500 kb chunks) inputs."""
+    cases = [([("c1", 1, 90_000, "diploid"), ("c2", 1, 50_000, "diploid"), ("c3", 5_000, 30_000, "haploid")], 4),
+             ([("chr20", 1, 64_444_167, "diploid")], 16), ([("a", 1, 2_300_000, "diploid"), ("b", 100, 1_200_000, "diploid")], 2)]
+    for regs, cpu in cases:
+        whole = cli.get_chunks(regs, cpu)
+        total = sum(e - s + 1 for _, s, e, _ in regs)
+        for world in (1, 2, 3, 8):
+            shares = multi.assign_chunk_runs(regs, world, cpu)
+            assert len(shares) == world
+            again = [c for share in shares for c in cli.get_chunks(share, cpu, total=total)]
+            assert again == whole, (regs, cpu, world)
+            if len(whole) >= world:
+                assert all(shares)                                 # nobody idles when there is a chunk for everyone
+
+
+def _worker_snps(rank, world, port, output, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a = _args(output)
+    a.mode, a.phase = "snps", False
+    out = multi.run_distributed(a, _fake_run_snps, [("chr1", 1, 900_000, "diploid")], dist)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _fake_run_snps(args):
+    out = _fake_run(args)
+    return {k: out[k] for k in ("unfiltered_snps", "snps")}
+
+
+def test_snps_mode_splits_one_contig_over_the_ranks_world2_gloo(tmp_path):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_snps, args=(r, world, port, str(tmp_path / "multi"), q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    single = _args(str(tmp_path / "single"))
+    single.regions = ["chr1:1-900000"]
+    want = _fake_run_snps(single)
+    got = res[0]
+    assert got["sharding"] == "chunk runs" and got["contigs_per_rank"] == [["chr1"], ["chr1"]] and "indels" not in got
+    r0, r1 = got["regions_per_rank"]
+    assert r0[0][1] == 1 and r0[-1][2] == r1[0][1] and r1[-1][2] == 900_000          # the runs meet on a shared grid point
+    for key in ("unfiltered_snps", "snps"):
+        with gzip.open(got[key], "rt") as f, gzip.open(want[key], "rt") as g:
+            assert f.read() == g.read(), key
