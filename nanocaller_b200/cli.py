@@ -239,6 +239,9 @@ def run(args):
     contig_lengths = bamio.bam_contigs(args.bam)                  # utils.py:9-50 asks the BAM header, not the FASTA
     regions = get_regions_list(args, contig_lengths)
     bamio.open_alignment(args.bam, args.ref, contigs={r[0] for r in regions})     # only the contigs that will be called
+    if getattr(args, "_read_windows", None):                      # one rank of a chunk-sharded run (host/multi.py): keep its part of every contig
+        from .host import sources
+        sources.restrict(args.bam, args._read_windows)
     exclude = _load_exclude_bed(args)
     chrom_list = list(dict.fromkeys(r[0] for r in regions))
     ctx = snp_pileups.context(args.device)                        # fails loudly without an sm_100 device

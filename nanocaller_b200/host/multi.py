@@ -72,6 +72,18 @@ def assign_chunk_runs(regions, world, cpu):
     return out
 
 
+READ_MARGIN = 60_000      # the SNP scan piles up [start - 50000, end + 50000] (generate_SNP_pileups.py:156); 10 kb to spare
+
+
+def read_windows(regions):
+    """{contig: (lo0, hi0)} covering every region of the share plus the pileup flank."""
+    out = {}
+    for c, s, e, _ in regions:
+        lo, hi = max(0, s - 1 - READ_MARGIN), e + READ_MARGIN
+        out[c] = (min(lo, out[c][0]), max(hi, out[c][1])) if c in out else (lo, hi)
+    return out
+
+
 def gather_bytes(data, dist, rank, world, device="cpu"):
     """Every rank contributes a bytes object; rank 0 gets the list of all of them in rank order, the others None."""
     import torch
@@ -114,6 +126,8 @@ def run_distributed(args, run_fn, regions, dist, device="cpu"):
         sub.output = os.path.join(args.output, "rank%d" % rank)
         sub.device = local
         sub._total_bases = sum(e - s + 1 for _, s, e, _ in regions)          # utils.py:72 sizes the chunks from ALL regions
+        if by_chunk:                                                          # stage only the reads this rank's chunks can see
+            sub._read_windows = read_windows(mine)
         try:
             out_r = run_fn(sub)
         except BaseException as e:                                # the other ranks must not wait in a collective for this one

@@ -121,6 +121,22 @@ class ReadSet:
         return ReadSet(chrom, ref_arr, pos, flag, cig_off, np.array(cig_words, np.uint32), seq_off,
                        l_seq, np.array(seq_bytes, np.uint8), hp, ps, qnames)
 
+    def window(self, lo0, hi0):
+        """Reads that can overlap the 0-based half-open reference window [lo0, hi0), as a ReadSet over VIEWS of this one's arrays:
+        the contiguous BAM-order range from the first read ending after lo0 to the last read starting before hi0 (reads in between
+        that end before lo0 stay in — they overlap nothing in the window, and the range stays contiguous).  The reference sequence
+        is kept whole, so coordinates do not change.  Used to hand one rank of a chunk-sharded run only its part of a contig."""
+        after = np.nonzero(self.ref_end > lo0)[0]
+        i0 = int(after[0]) if len(after) else self.n
+        i1 = max(i0, int(np.searchsorted(self.pos, hi0, side="left")))
+        c0, s0 = int(self.cigar_off[i0]), int(self.seq_off[i0])
+        w = ReadSet(self.chrom, self.ref, self.pos[i0:i1], self.flag[i0:i1], self.cigar_off[i0:i1 + 1] - c0,
+                    self.cigar[c0:int(self.cigar_off[i1])], self.seq_off[i0:i1 + 1] - s0, self.l_seq[i0:i1],
+                    self.seq4[s0:int(self.seq_off[i1])], self.hp[i0:i1], self.ps[i0:i1],
+                    None if self.qnames is None else self.qnames[i0:i1])
+        w._ref_end = np.ascontiguousarray(self.ref_end[i0:i1])
+        return w
+
     def subset(self, keep):
         """New ReadSet with reads where boolean mask `keep` is set (arrays re-packed)."""
         idx = np.nonzero(keep)[0]

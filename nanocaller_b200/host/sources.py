@@ -46,6 +46,14 @@ def resolve(sam_path, chrom):
         raise FileNotFoundError("no alignment source registered for %r contig %r" % (sam_path, chrom))
 
 
+def restrict(sam_path, windows):
+    """windows: {contig: (lo0, hi0)} — replace the registered read sets of those contigs by `ReadSet.window(lo0, hi0)`."""
+    reg = _REGISTRY[sam_path]
+    for chrom, (lo0, hi0) in windows.items():
+        if chrom in reg:
+            reg[chrom] = reg[chrom].window(lo0, hi0)
+
+
 def contigs(sam_path):
     return list(_REGISTRY[sam_path])
 

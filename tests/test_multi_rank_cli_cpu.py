@@ -198,3 +198,28 @@ def test_snps_mode_splits_one_contig_over_the_ranks_world2_gloo(tmp_path):
     for key in ("unfiltered_snps", "snps"):
         with gzip.open(got[key], "rt") as f, gzip.open(want[key], "rt") as g:
             assert f.read() == g.read(), key
+
+
+def test_a_rank_sees_the_same_candidates_through_its_read_window():
+    """Chunk-sharded `--mode snps`: a rank stages `ReadSet.window` of its share (+ the 50 kb pileup flank).  The reference's tensors for
+    the chunks of that share are the same from the window as from the whole contig (oracle on both)."""
+    import numpy as np
+    from nanocaller_b200.synth import make_world
+    from oracle import snp_oracle
+    rs = make_world(chrom="chrW", preset="ont", contig_len=400_000, seed=81, coverage=14.0).reads
+    dct = dict(threshold=[0.4, 0.6], mincov=4, maxcov=160, min_allele_freq=0.15, min_nbr_sites=1, seq="ont", supplementary=False)
+    regs = [("chrW", 1, 400_000, "diploid")]
+    cpu = 20                                                  # 20,001-base chunks
+    shares = multi.assign_chunk_runs(regs, 4, cpu)
+    share = shares[2]
+    win = multi.read_windows(share)["chrW"]
+    sub = rs.window(*win)
+    assert 0 < sub.n < 0.75 * rs.n and sub.contig_len == rs.contig_len
+    assert sub.checksum() == rs.subset((np.arange(rs.n) >= np.nonzero(rs.ref_end > win[0])[0][0]) & (rs.pos < win[1])).checksum()
+    chunks = cli.get_chunks(share, cpu, total=400_000)
+    for ch in (chunks[0], chunks[-1]):
+        a = snp_oracle.get_snp_testing_candidates(rs, dct, ch)
+        b = snp_oracle.get_snp_testing_candidates(sub, dct, ch)
+        assert len(a[0]) > 20
+        for x, y in zip(a, b):
+            assert np.array_equal(np.asarray(x), np.asarray(y))
