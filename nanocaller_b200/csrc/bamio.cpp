@@ -490,8 +490,46 @@ int nc_bam_write_tagged(const nc_bam* b, int i, const int8_t* hp, const int32_t*
         u.push_back(0);
         put32(k.length);
     }
+    // BGZF output in batches: the stream is deflated and written every ~64 MB, so memory stays bounded for any contig size
+    const size_t kPayload = 0xff00, kBatch = kPayload * 1024;
+    if (level < 0 || level > 9) level = 4;
+    FILE* f = fopen(out_path, "wb");
+    if (!f) return NC_IO_EOPEN;
+    bool ok = true;
+    auto flush = [&](bool all) {                                // writes every full block of `u` (all = the tail as well)
+        const size_t n_full = all ? u.size() : (u.size() / kPayload) * kPayload;
+        if (n_full == 0) return;
+        const int64_t nblk = (int64_t)((n_full + kPayload - 1) / kPayload);
+        std::vector<std::vector<uint8_t>> out((size_t)nblk);
+        std::atomic<int> bad{0};
+        parallel_for(nblk, threads, [&](int64_t j) {
+            const size_t o = (size_t)j * kPayload, n = std::min(kPayload, n_full - o);
+            std::vector<uint8_t>& blk = out[(size_t)j];
+            blk.resize(18 + compressBound((uLong)n) + 8);
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad = 1; return; }
+            zs.next_in = u.data() + o; zs.avail_in = (uInt)n;
+            zs.next_out = blk.data() + 18; zs.avail_out = (uInt)(blk.size() - 18 - 8);
+            const int rc = deflate(&zs, Z_FINISH);
+            const size_t cs = zs.total_out;
+            deflateEnd(&zs);
+            if (rc != Z_STREAM_END || 18 + cs + 8 > 0x10000) { bad = 1; return; }
+            static const uint8_t head[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+            memcpy(blk.data(), head, 16);
+            const uint16_t bsize = (uint16_t)(18 + cs + 8 - 1);
+            memcpy(blk.data() + 16, &bsize, 2);
+            const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), u.data() + o, (uInt)n), isz = (uint32_t)n;
+            memcpy(blk.data() + 18 + cs, &crc, 4);
+            memcpy(blk.data() + 18 + cs + 4, &isz, 4);
+            blk.resize(18 + cs + 8);
+        });
+        if (bad) { ok = false; return; }
+        for (auto& blk : out) ok = ok && fwrite(blk.data(), 1, blk.size(), f) == blk.size();
+        u.erase(u.begin(), u.begin() + (std::ptrdiff_t)n_full);
+    };
     const uint8_t* d = b->data.data();
-    for (int64_t k = 0; k < c.n_reads; k++) {
+    for (int64_t k = 0; k < c.n_reads && ok; k++) {
         const size_t off = (size_t)b->rec_off[(size_t)(c.first_rec + k)];
         const int32_t bs = rd<int32_t>(d + off);
         const uint8_t* r = d + off + 4;
@@ -529,40 +567,9 @@ int nc_bam_write_tagged(const nc_bam* b, int i, const int8_t* hp, const int32_t*
         }
         const int32_t nbs = (int32_t)(u.size() - at - 4);
         memcpy(u.data() + at, &nbs, 4);
+        if (u.size() >= kBatch) flush(false);
     }
-    // BGZF
-    const size_t kPayload = 0xff00;
-    const int64_t nblk = (int64_t)((u.size() + kPayload - 1) / kPayload);
-    std::vector<std::vector<uint8_t>> out((size_t)nblk);
-    std::atomic<int> bad{0};
-    if (level < 0 || level > 9) level = 4;
-    parallel_for(nblk, threads, [&](int64_t j) {
-        const size_t o = (size_t)j * kPayload, n = std::min(kPayload, u.size() - o);
-        std::vector<uint8_t>& blk = out[(size_t)j];
-        blk.resize(18 + compressBound((uLong)n) + 8);
-        z_stream zs;
-        memset(&zs, 0, sizeof(zs));
-        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad = 1; return; }
-        zs.next_in = u.data() + o; zs.avail_in = (uInt)n;
-        zs.next_out = blk.data() + 18; zs.avail_out = (uInt)(blk.size() - 18 - 8);
-        const int rc = deflate(&zs, Z_FINISH);
-        const size_t cs = zs.total_out;
-        deflateEnd(&zs);
-        if (rc != Z_STREAM_END || 18 + cs + 8 > 0x10000) { bad = 1; return; }
-        static const uint8_t head[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
-        memcpy(blk.data(), head, 16);
-        const uint16_t bsize = (uint16_t)(18 + cs + 8 - 1);
-        memcpy(blk.data() + 16, &bsize, 2);
-        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), u.data() + o, (uInt)n), isz = (uint32_t)n;
-        memcpy(blk.data() + 18 + cs, &crc, 4);
-        memcpy(blk.data() + 18 + cs + 4, &isz, 4);
-        blk.resize(18 + cs + 8);
-    });
-    if (bad) return NC_IO_EFORMAT;
-    FILE* f = fopen(out_path, "wb");
-    if (!f) return NC_IO_EOPEN;
-    bool ok = true;
-    for (auto& blk : out) ok = ok && fwrite(blk.data(), 1, blk.size(), f) == blk.size();
+    if (ok) flush(true);
     static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     ok = ok && fwrite(eof, 1, 28, f) == 28;
     ok = (fclose(f) == 0) && ok;

@@ -292,3 +292,22 @@ def test_haplotagged_bam_copy(tmp_path):
     import pytest
     with pytest.raises(ValueError):
         bamio.write_haplotagged_bam(src, "chrA", hp[:-1], ps[:-1], str(tmp_path / "x.bam"))
+
+
+def test_haplotagged_bam_copy_in_batches(tmp_path):
+    """More than one 64 MB batch of uncompressed records: the writer deflates and writes as it goes; the copy reads back identical."""
+    import numpy as np
+    from nanocaller_b200.host import bamio
+    from nanocaller_b200.synth import make_world
+    a = make_world(chrom="chrL", preset="ont", contig_len=3_000_000, seed=33, coverage=30.0, untagged_frac=1.0).reads
+    src = str(tmp_path / "l.bam")
+    bamio.write_bam(src, [a])
+    approx = int((a.l_seq.astype(np.int64) * 3 // 2 + 4 * np.diff(a.cigar_off) + 40).sum())
+    assert approx > 2.2 * 0xff00 * 1024                          # at least three batches
+    hp = (np.arange(a.n) % 3).astype(np.int8)
+    ps = np.where(hp > 0, 1234, 0).astype(np.int32)
+    out = bamio.write_haplotagged_bam(src, "chrL", hp, ps, str(tmp_path / "l.phased.bam"))
+    g = bamio.read_bam_native(out)[0][0]
+    for f in ("pos", "flag", "cigar_off", "cigar", "seq_off", "l_seq", "seq4"):
+        assert np.array_equal(getattr(g, f), getattr(a, f)), f
+    assert np.array_equal(g.hp, hp) and np.array_equal(g.ps, ps)
