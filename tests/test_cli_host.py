@@ -57,3 +57,14 @@ def test_product_cli_does_not_import_the_oracle():
     tree = ast.parse(inspect.getsource(cli))
     names = [n.module or "" for n in ast.walk(tree) if isinstance(n, ast.ImportFrom)] + [a.name for n in ast.walk(tree) if isinstance(n, ast.Import) for a in n.names]
     assert not any(n.startswith("oracle") for n in names)
+
+
+def test_every_reference_flag_is_accepted():
+    """tests/golden/reference_cli_flags.txt = the add_argument names of the reference script (NanoCaller:84-158, extracted by
+    tests/golden/make_cli_flags.py): the parser knows every one of them, and its own additions are the documented four."""
+    import os
+    from nanocaller_b200 import cli
+    want = set(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cli_flags.txt")).read().split())
+    have = {s for a in cli.build_parser()._actions for s in a.option_strings if s.startswith("--")}
+    assert len(want) > 30 and want <= have | {"--help"}, sorted(want - have)
+    assert have - want - {"--help"} == {"--device", "--nanocaller_src", "--write_phased_bam", "--decompose_indels"}
