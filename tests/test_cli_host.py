@@ -59,12 +59,17 @@ def test_product_cli_does_not_import_the_oracle():
     assert not any(n.startswith("oracle") for n in names)
 
 
-def test_every_reference_flag_is_accepted():
-    """tests/golden/reference_cli_flags.txt = the add_argument names of the reference script (NanoCaller:84-158, extracted by
-    tests/golden/make_cli_flags.py): the parser knows every one of them, and its own additions are the documented four."""
+def test_every_reference_flag_is_accepted_with_the_reference_default():
+    """tests/golden/reference_cli_flags.txt = the add_argument names and defaults of the reference script (NanoCaller:84-158, extracted
+    by tests/golden/make_cli_flags.py): the parser knows every flag, has the same default for it, and its own additions are the
+    documented four."""
+    import ast
     import os
     from nanocaller_b200 import cli
-    want = set(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cli_flags.txt")).read().split())
-    have = {s for a in cli.build_parser()._actions for s in a.option_strings if s.startswith("--")}
-    assert len(want) > 30 and want <= have | {"--help"}, sorted(want - have)
-    assert have - want - {"--help"} == {"--device", "--nanocaller_src", "--write_phased_bam", "--decompose_indels"}
+    rows = [ln.rstrip("\n").split("\t") for ln in open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cli_flags.txt"))]
+    want = {k: ast.literal_eval(v) for k, v in rows}
+    acts = {s: a for a in cli.build_parser()._actions for s in a.option_strings if s.startswith("--")}
+    assert len(want) > 30 and set(want) <= set(acts), sorted(set(want) - set(acts))
+    for k, v in want.items():
+        assert acts[k].default == v, (k, acts[k].default, v)
+    assert set(acts) - set(want) - {"--help"} == {"--device", "--nanocaller_src", "--write_phased_bam", "--decompose_indels"}
