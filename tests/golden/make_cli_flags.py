@@ -19,3 +19,17 @@ with open(os.path.join(HERE, "reference_cli_flags.txt"), "w") as f:
     for k in sorted(rows):
         f.write("%s\t%s\n" % (k, rows[k]))
 print(len(rows), "flags")
+
+# the preset table (NanoCaller:66-77) as JSON
+import json
+
+i = src.index("preset_dict={") + len("preset_dict=")
+depth = 0
+for j in range(i, len(src)):
+    if src[j] == "{":
+        depth += 1
+    elif src[j] == "}":
+        depth -= 1
+        if depth == 0:
+            break
+json.dump(ast.literal_eval(src[i:j + 1]), open(os.path.join(HERE, "reference_presets.json"), "w"), indent=1, sort_keys=True)

@@ -73,3 +73,12 @@ def test_every_reference_flag_is_accepted_with_the_reference_default():
     for k, v in want.items():
         assert acts[k].default == v, (k, acts[k].default, v)
     assert set(acts) - set(want) - {"--help"} == {"--device", "--nanocaller_src", "--write_phased_bam", "--decompose_indels"}
+
+
+def test_preset_table_equals_the_reference():
+    """tests/golden/reference_presets.json = `preset_dict` of the reference script (NanoCaller:66-77, extracted by make_cli_flags.py)."""
+    import json
+    import os
+    from nanocaller_b200 import cli
+    want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_presets.json")))
+    assert cli.PRESETS == want and len(want) == 6
