@@ -33,3 +33,11 @@ for j in range(i, len(src)):
         if depth == 0:
             break
 json.dump(ast.literal_eval(src[i:j + 1]), open(os.path.join(HERE, "reference_presets.json"), "w"), indent=1, sort_keys=True)
+
+# VCF header lines written by snpCaller.call_manager (snpCaller.py:259-276) and indelCaller.call_manager (indelCaller.py:373-383)
+hdr = {}
+for name, fn in (("snps", "snpCaller.py"), ("indels", "indelCaller.py")):
+    text = open("/root/reference/nanocaller_src/" + fn).read()
+    lines = re.findall(r"outfile\.write\(b'((?:##|#CHROM)[^']*)'", text)
+    hdr[name] = [ln.replace("\\n", "").replace("\\t", "\t") for ln in lines]
+json.dump(hdr, open(os.path.join(HERE, "reference_vcf_headers.json"), "w"), indent=1)

@@ -311,3 +311,16 @@ def test_haplotagged_bam_copy_in_batches(tmp_path):
     for f in ("pos", "flag", "cigar_off", "cigar", "seq_off", "l_seq", "seq4"):
         assert np.array_equal(getattr(g, f), getattr(a, f)), f
     assert np.array_equal(g.hp, hp) and np.array_equal(g.ps, ps)
+
+
+def test_vcf_headers_equal_the_reference_literals():
+    """tests/golden/reference_vcf_headers.json = the header lines the reference writes (snpCaller.py:259-276, indelCaller.py:373-383,
+    extracted by tests/golden/make_cli_flags.py; `%s` stands for the contig / sample name)."""
+    import json
+    import os
+    from nanocaller_b200.host import vcfio
+    want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vcf_headers.json")))
+    for kind in ("snps", "indels"):
+        ref = [ln.replace("%s", "X") for ln in want[kind]]
+        got = [ln for ln in vcfio.header(kind, ["X"], "X").split("\n") if ln]
+        assert got == ref and len(ref) >= 7, kind
