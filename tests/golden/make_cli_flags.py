@@ -41,3 +41,11 @@ for name, fn in (("snps", "snpCaller.py"), ("indels", "indelCaller.py")):
     lines = re.findall(r"outfile\.write\(b'((?:##|#CHROM)[^']*)'", text)
     hdr[name] = [ln.replace("\\n", "").replace("\\t", "\t") for ln in lines]
 json.dump(hdr, open(os.path.join(HERE, "reference_vcf_headers.json"), "w"), indent=1)
+
+# model name tables (snpCaller.py:16-34, indelCaller.py:17-24)
+tables = {}
+for key, fn, var in (("snp", "snpCaller.py", "snp_model_dict"), ("indel", "indelCaller.py", "indel_model_dict")):
+    text = open("/root/reference/nanocaller_src/" + fn).read()
+    i = text.index(var + "={") + len(var) + 1
+    tables[key] = ast.literal_eval(text[i:text.index("}", i) + 1])
+json.dump(tables, open(os.path.join(HERE, "reference_model_tables.json"), "w"), indent=1, sort_keys=True)

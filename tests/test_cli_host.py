@@ -82,3 +82,12 @@ def test_preset_table_equals_the_reference():
     from nanocaller_b200 import cli
     want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_presets.json")))
     assert cli.PRESETS == want and len(want) == 6
+
+
+def test_model_name_tables_equal_the_reference():
+    """tests/golden/reference_model_tables.json = snp_model_dict / indel_model_dict of the reference (snpCaller.py:16-34, indelCaller.py:17-24)."""
+    import json
+    import os
+    from nanocaller_b200.host import weights
+    want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_model_tables.json")))
+    assert weights.SNP_MODEL_DICT == want["snp"] and weights.INDEL_MODEL_DICT == want["indel"]
