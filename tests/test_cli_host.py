@@ -91,3 +91,30 @@ def test_model_name_tables_equal_the_reference():
     from nanocaller_b200.host import weights
     want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_model_tables.json")))
     assert weights.SNP_MODEL_DICT == want["snp"] and weights.INDEL_MODEL_DICT == want["indel"]
+
+
+def test_regions_list_equals_the_unmodified_reference(tmp_path, capsys):
+    """tests/golden/reference_regions.json = answers (regions, exit codes, messages) of the unmodified `utils.get_regions_list`
+    (utils.py:6-65) run over the pysam shim (tests/golden/make_regions_golden.py) on eleven argument scenarios."""
+    import argparse
+    import json
+    import os
+    import pytest
+    from nanocaller_b200 import cli
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_regions.json")))
+    bed = tmp_path / "r.bed"
+    bed.write_text(g["bed"])
+    assert len(g["scenarios"]) >= 11
+    for sc in g["scenarios"]:
+        lengths = dict((n, l) for n, l in g["contigs"][sc["source"]])
+        args = argparse.Namespace(wgs_contigs=sc.get("wgs_contigs"), regions=sc.get("regions"), bed=str(bed) if sc.get("bed") else None,
+                                  haploid_genome=sc.get("haploid_genome", False), haploid_X=sc.get("haploid_X", False))
+        capsys.readouterr()
+        if isinstance(sc["result"], dict):
+            with pytest.raises(SystemExit) as e:
+                cli.get_regions_list(args, lengths)
+            assert e.value.code == sc["result"]["exit"], sc["name"]
+        else:
+            assert [list(r) for r in cli.get_regions_list(args, lengths)] == sc["result"], sc["name"]
+        msgs = [ln.split(": ", 1)[1] for ln in capsys.readouterr().out.splitlines() if ": " in ln]
+        assert msgs == sc["messages"], sc["name"]
