@@ -23,7 +23,8 @@ def compare_records(got_lines, want_lines, tol=1e-4):
             res["identical"] += 1
             continue
         a, b = _parse(g), _parse(w)
-        pr_ok = all(abs(x - y) <= tol + 1e-4 * 0.5 for x, y in zip(a["pr"], b["pr"]))      # printed with 4 decimals
+        pr_ok = all(abs(x - y) <= tol + 1e-4 + 1e-9 for x, y in zip(a["pr"], b["pr"]))     # printed with 4 decimals: two values on either
+                                                                                          # side of a rounding boundary print one unit apart
         same_call = all(a[k] == b[k] for k in ("key", "ref", "alt", "filter", "fq", "fmt", "sample"))
         if same_call and pr_ok:
             # QUAL = -10 log10(1e-10 + 1 - p): d(QUAL)/dp = 10 / (ln 10 (1 - p)); allow the change caused by a tol shift
