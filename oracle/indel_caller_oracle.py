@@ -4,7 +4,9 @@ Restatement of the indel genotype decision and VCF record formatting of the refe
 (indelCaller.py:74-152 diploid, :159-182 haploid), taking CNN probabilities and allele strings as input.
 Kept line for line (including the `prev` overlap suppression and the QUAL quirk: the min(99, ...) value is discarded,
 SURVEY appendix F.12).  Float semantics as in the reference's environment: `-10*np.log10(1e-6 + p)` on float32
-probabilities is evaluated in float64 for the scalar expressions and in float32 for `qual_all` (unused)."""
+probabilities is evaluated in float64 for the scalar expressions and in float32 for `qual_all` (unused).
+Pinned: tests/test_indel_records_golden.py holds it to the records the UNMODIFIED `indelCaller.indel_run` wrote over oracle/shim
+(tests/golden/records_indel_*.vcf.txt, made by tests/golden/make_golden_indel_records.py)."""
 import numpy as np
 
 

@@ -45,6 +45,9 @@ class Model:
         self._loaded = True
         return _LoadStatus()
 
+    def build(self, input_shape=None):
+        return None
+
     def __call__(self, inputs, training=False):
         if not self._loaded:                       # the reference builds the haploid model with one dummy call before loading
             return None

@@ -3,6 +3,8 @@
 Restatement of the SNP genotype decision and VCF record formatting of the reference worker
 (snpCaller.py:113-163 diploid, :183-198 haploid), taking the CNN probabilities as input.
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may import it.
+Pinned: tests/test_snp_records_golden.py holds it to the records the UNMODIFIED `snpCaller.caller` wrote over oracle/shim
+(tests/golden/records_*.vcf.txt, made by tests/golden/make_golden_records.py).
 
 Float semantics follow the reference's pinned environment (environment.yml:9, numpy<2):
 `1e-10 + 1 - probs[j,k]` mixes a Python float with a float32 scalar, which legacy promotion
