@@ -104,3 +104,32 @@ def test_golden_tensors_obey_the_size_independent_invariants():
             check_tensor_invariants(x, ref_code, n_left, n_right, sampled, w["dp"], acgt, dct["maxcov"])
             checked += n
     assert checked > 1000
+
+
+def test_cnn_restatement_equals_the_reference_model_classes():
+    """tests/golden/model_probs.npz = outputs of the UNMODIFIED model_architect*.py classes run over oracle/shim/tensorflow (which
+    supplies only conv / dense / selu / softmax / sigmoid) with the released weights (tests/golden/make_golden_model_probs.py): the
+    restatement the CUDA kernels are held to has the same wiring — all five SNP heads including the unused GT head."""
+    import os
+    import sys
+    from nanocaller_b200.host import weights as W
+    from oracle import cnn_oracle
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gdir, "model_probs.npz"))
+    sys.path.insert(0, gdir)
+    try:
+        from make_golden_model_probs import inputs
+    finally:
+        sys.path.remove(gdir)
+    x, ref, xi = inputs(int(g["seed"]), int(g["n"]))
+    snp, _ = W.load_model("snp", "ONT-HG002")
+    outs = cnn_oracle.snp_model(snp, x, ref)
+    for k, o in zip(("snp_A", "snp_G", "snp_T", "snp_C", "snp_GT"), outs):
+        assert np.abs(o - g[k]).max() < 2e-5, k
+    hap, _ = W.load_model("snp", "haploid")
+    assert np.abs(cnn_oracle.haploid_snp_model(hap, x, ref) - g["snp_haploid"]).max() < 2e-5
+    ind, _ = W.load_model("indel", "ONT-HG002")
+    assert np.abs(cnn_oracle.indel_model(ind, xi) - g["indel"]).max() < 2e-5
+    hind, _ = W.load_model("indel", "haploid")
+    assert np.abs(cnn_oracle.haploid_indel_model(hind, xi[:, 10:15]) - g["indel_haploid"]).max() < 2e-5
+    assert g["snp_A"].std() > 0.05 and g["indel"].std() > 0.05          # the inputs exercise the models
