@@ -9,13 +9,6 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle", "shim"))
-sys.path.insert(0, "/root/reference")
-
-from nanocaller_src.model_architect import SNP_model  # noqa: E402  (reference, unchanged)
-from nanocaller_src.model_architect_SNP_haploid import haploid_SNP_model  # noqa: E402
-from nanocaller_src.model_architect_indel import Indel_model  # noqa: E402
-from nanocaller_src.model_architect_indels_haploid import haploid_Indel_model  # noqa: E402
 
 REL = "/root/reference/nanocaller_src/release_data/"
 
@@ -32,6 +25,12 @@ def inputs(seed=11, n=48):
 
 
 def main():
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "shim"))
+    sys.path.insert(0, "/root/reference")
+    from nanocaller_src.model_architect import SNP_model  # (reference, unchanged)
+    from nanocaller_src.model_architect_SNP_haploid import haploid_SNP_model
+    from nanocaller_src.model_architect_indel import Indel_model
+    from nanocaller_src.model_architect_indels_haploid import haploid_Indel_model
     x, ref, xi = inputs()
     out = {"seed": np.array(11), "n": np.array(len(x))}
     m = SNP_model()
