@@ -14,8 +14,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name,model,haploid,disable", [("ont_diploid", "ONT-HG002", False, False), ("haploid", "haploid", True, False),
-                                                        ("lowcov", "ONT-HG002", False, False)])
+@pytest.mark.parametrize("name,model,haploid,disable", [("ont_diploid", "ONT-HG002", False, False), ("haploid", "haploid", True, False)])
 def test_product_records_match_the_reference_worker(name, model, haploid, disable):
     from nanocaller_b200.host import snp_caller, sources, weights as W
     from nanocaller_b200.host.vcf_compare import compare_records
