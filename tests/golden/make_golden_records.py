@@ -25,7 +25,8 @@ from nanocaller_src import snpCaller  # noqa: E402  (reference, unchanged)
 from nanocaller_src.utils import get_chunks  # noqa: E402  (reference, unchanged)
 from tests.golden.cases import case_inputs  # noqa: E402
 
-RECORD_CASES = {"ont_diploid": {}, "haploid": {}, "ont_subregion_bed": {"disable_coverage_normalization": True}, "lowcov": {}}
+RECORD_CASES = {"ont_diploid": {}, "haploid": {}, "ont_subregion_bed": {"disable_coverage_normalization": True}, "lowcov": {},
+                "hifi_pacbio": {"snp_model": "CCS-HG002"}}
 
 
 def run_case(name, over):
