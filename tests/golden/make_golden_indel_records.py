@@ -25,7 +25,8 @@ from nanocaller_src import indelCaller  # noqa: E402  (reference, unchanged)
 from nanocaller_src.utils import get_chunks  # noqa: E402
 from tests.golden.indel_cases import indel_case_inputs  # noqa: E402
 
-RECORD_CASES = {"indel_ont": "ONT-HG002", "indel_haploid": "ONT-HG002", "indel_impute_hifi": "CCS-HG002"}
+RECORD_CASES = {"indel_ont": "ONT-HG002", "indel_haploid": "ONT-HG002", "indel_impute_hifi": "CCS-HG002", "indel_sub": "ONT-HG002",
+                "indel_impute_ont": "ONT-HG002"}
 
 
 def run_case(name, model):

@@ -15,7 +15,8 @@ from oracle import cnn_oracle, indel_caller_oracle
 from tests.test_indel_oracle_golden import load_indel_case
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = {"indel_ont": "ONT-HG002", "indel_haploid": "ONT-HG002", "indel_impute_hifi": "CCS-HG002"}
+CASES = {"indel_ont": "ONT-HG002", "indel_haploid": "ONT-HG002", "indel_impute_hifi": "CCS-HG002", "indel_sub": "ONT-HG002",
+         "indel_impute_ont": "ONT-HG002"}
 
 
 def _same(got, want, tag):
