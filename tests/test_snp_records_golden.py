@@ -6,7 +6,8 @@ model_architect*.py classes, only conv / dense / selu / softmax come from the sh
 (tests/golden/make_golden_records.py).  Checked here, CPU only:
   * oracle chain  snp_oracle tensors -> scale_counts -> cnn_oracle -> snp_caller_oracle records   (what the GPU tests hold the
     product to), and
-  * the host's own record code (host/snp_caller.records_from_calls) on the same probabilities.
+  * the host's own record code (host/snp_caller.records_from_calls) and the library's threaded formatter the product path uses
+    (nc_format_snp_records) on the same probabilities.
 The fixtures were made under NumPy 2 (the coverage scaling multiplies in float64 there, in float32 under the reference's pinned
 NumPy < 2, snpCaller.py:96), so QUAL / PR digits may differ in the last place: `compare_records` allows that and nothing else."""
 import os
@@ -70,12 +71,20 @@ def _host_records(chrom, haploid, pos, ref, probs, dp, freq, fwd, rev):
     return snp_caller.records_from_calls(chrom, pos, np.argmax(ref, 1), probs, dp, freq, fwd, rev, ploidy="haploid" if haploid else "diploid")
 
 
+def _library_records(chrom, haploid, pos, ref, probs, dp, freq, fwd, rev):
+    """nc_format_snp_records: the formatter the product path uses (host threads inside libnanocaller_b200.so)."""
+    from nanocaller_b200.host import capi
+    alt = np.rint(np.asarray(freq, np.float64) * np.asarray(dp)).astype(np.int32)          # freq = alt / dp (generate_SNP_pileups.py:166)
+    blob, off, _ = capi.format_snp_records(chrom, pos, np.argmax(ref, 1), probs, dp, alt, fwd, rev, haploid=haploid, threads=2)
+    return [blob[off[i]:off[i + 1]].decode() for i in range(len(off) - 1)]
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_records_match_the_unmodified_reference_worker(name):
-    rs, (got_o, got_h) = _chain(name, CASES[name], [_oracle_records, _host_records])
+    rs, (got_o, got_h, got_l) = _chain(name, CASES[name], [_oracle_records, _host_records, _library_records])
     want = _fixture(name, rs)
     assert len(want) > 300
-    for tag, got in (("oracle", got_o), ("host", got_h)):
+    for tag, got in (("oracle", got_o), ("host", got_h), ("library", got_l)):
         res = compare_records(got, want, tol=2e-6)
         assert not res["mismatch"], (tag, res["mismatch"][:2])
         assert res["borderline"] == 0 and res["identical"] >= 0.94 * len(want), (tag, res["identical"], res["numeric_only"], len(want))
