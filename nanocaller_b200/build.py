@@ -8,6 +8,8 @@ they travel to the GPU box with the repo snapshot.
 
 `python -m nanocaller_b200.build` builds everything that is stale.
 """
+import contextlib
+import fcntl
 import os
 import shutil
 import subprocess
@@ -36,6 +38,28 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+@contextlib.contextmanager
+def _locked(target):
+    """One builder at a time per target: under `torch.distributed.run` every rank imports this module at once, and a rank
+    must never dlopen a half-written library.  The compile goes to a temporary file that is renamed into place."""
+    with open(target + ".lock", "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
+
+
+def _compile(cmd_before_out, target, cmd_after_out, verbose):
+    tmp = "%s.tmp%d" % (target, os.getpid())
+    try:
+        _run(list(cmd_before_out) + ["-o", tmp] + list(cmd_after_out), verbose)
+        os.replace(tmp, target)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+
+
 def _run(cmd, verbose):
     if verbose:
         print("+", " ".join(cmd), flush=True)
@@ -49,8 +73,9 @@ def _run(cmd, verbose):
 
 def build_synth(force=False, verbose=False):
     src = os.path.join(CSRC, "synth.cpp")
-    if force or _stale(LIB_SYNTH, [src]):
-        _run(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", LIB_SYNTH, src], verbose)
+    with _locked(LIB_SYNTH):
+        if force or _stale(LIB_SYNTH, [src]):
+            _compile(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread"], LIB_SYNTH, [src], verbose)
     return LIB_SYNTH
 
 
@@ -58,8 +83,9 @@ def build_bamio(force=False, verbose=False):
     """g++ -lz -pthread: native BGZF/BAM reader (include/nanocaller_b200_io.h)."""
     src = os.path.join(CSRC, "bamio.cpp")
     hdr = os.path.join(ROOT, "include", "nanocaller_b200_io.h")
-    if force or _stale(LIB_BAMIO, [src, hdr]):
-        _run(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", LIB_BAMIO, src, "-lz"], verbose)
+    with _locked(LIB_BAMIO):
+        if force or _stale(LIB_BAMIO, [src, hdr]):
+            _compile(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "include")], LIB_BAMIO, [src, "-lz"], verbose)
     return LIB_BAMIO
 
 
@@ -67,8 +93,9 @@ def build_phase(force=False, verbose=False):
     """g++ -pthread: host-side phasing / haplotagging (include/nanocaller_b200_phase.h)."""
     src = os.path.join(CSRC, "phase.cpp")
     hdr = os.path.join(ROOT, "include", "nanocaller_b200_phase.h")
-    if force or _stale(LIB_PHASE, [src, hdr]):
-        _run(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", LIB_PHASE, src], verbose)
+    with _locked(LIB_PHASE):
+        if force or _stale(LIB_PHASE, [src, hdr]):
+            _compile(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "include")], LIB_PHASE, [src], verbose)
     return LIB_PHASE
 
 
@@ -84,11 +111,10 @@ def build_cuda(force=False, verbose=False, extra=()):
         if os.path.exists(LIB_CUDA):
             return LIB_CUDA  # prebuilt library travelled with the snapshot
         raise RuntimeError("nvcc not found and no prebuilt libnanocaller_b200.so")
-    if force or _stale(LIB_CUDA, cuda_deps()):
-        srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
-        cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-I", os.path.join(ROOT, "include"), "-I", CSRC,
-                                                   "-o", LIB_CUDA] + srcs + ["-lcudart"]
-        _run(cmd, verbose)
+    with _locked(LIB_CUDA):
+        if force or _stale(LIB_CUDA, cuda_deps()):
+            srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
+            _compile([nvcc] + NVCC_FLAGS + list(extra) + ["-I", os.path.join(ROOT, "include"), "-I", CSRC], LIB_CUDA, srcs + ["-lcudart"], verbose)
     return LIB_CUDA
 
 

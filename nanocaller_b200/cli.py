@@ -237,7 +237,7 @@ def run(args):
         for k, v in vars(args).items():
             f.write("{}: {}\n".format(k, v))
     contig_lengths = bamio.bam_contigs(args.bam)                  # utils.py:9-50 asks the BAM header, not the FASTA
-    regions = get_regions_list(args, contig_lengths)
+    regions = getattr(args, "_regions", None) or get_regions_list(args, contig_lengths)     # _regions: one rank's share (host/multi.py)
     bamio.open_alignment(args.bam, args.ref, contigs={r[0] for r in regions})     # only the contigs that will be called
     if getattr(args, "_read_windows", None):                      # one rank of a chunk-sharded run (host/multi.py): keep its part of every contig
         from .host import sources

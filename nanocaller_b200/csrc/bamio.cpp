@@ -169,6 +169,8 @@ int64_t parse_header(nc_bam* b, const uint8_t* d, size_t n) {
     return (int64_t)off;
 }
 
+int64_t real_cigar_count(const uint8_t* r, int32_t bs);     // long-CIGAR aware (CG:B,I), defined with real_cigar below
+
 // Walks the records of data[off, end): boundaries and per-contig totals.  only_rid >= 0: stop at the first record of another
 // reference (region reads).
 int scan_records(nc_bam* b, size_t off, size_t end, int32_t only_rid, std::vector<std::vector<int64_t>>& per) {
@@ -189,7 +191,7 @@ int scan_records(nc_bam* b, size_t off, size_t end, int32_t only_rid, std::vecto
             if (rid < last_rid || (rid == last_rid && pos < last_pos)) b->sorted = false;
             last_rid = rid; last_pos = pos;
             Contig& c = b->contigs[(size_t)rid];
-            c.n_reads++; c.n_cigar += n_cig; c.n_seq += (l_seq + 1) / 2;
+            c.n_reads++; c.n_cigar += real_cigar_count(r, bs); c.n_seq += (l_seq + 1) / 2;
             per[(size_t)rid].push_back((int64_t)off);
         }
         off += 4 + (size_t)bs;
@@ -269,6 +271,41 @@ void scan_tags(const uint8_t* p, const uint8_t* end, int8_t* hp, int32_t* ps) {
         }
     }
 }
+
+// Long CIGARs (SAM spec 4.2.2): a read with more than 65,535 operations — routine for the ultra-long ONT reads the ul_ont presets
+// target — stores the placeholder `<l_seq>S<reference length>N` in the CIGAR field and the real operations in a CG:B,I aux
+// array; htslib (and so pysam in the reference, generate_SNP_pileups.py:141,156) restores it transparently.  Returns the
+// operations a consumer must see: the aux array when the record is such a placeholder, else the CIGAR field itself.
+struct CigarView { const uint8_t* p; int64_t n; };
+CigarView real_cigar(const uint8_t* r, int32_t bs) {
+    const uint8_t l_name = r[8];
+    const uint16_t n_cig = rd<uint16_t>(r + 12);
+    const int32_t l_seq = rd<int32_t>(r + 16);
+    const uint8_t* cg = r + 32 + l_name;
+    CigarView v = {cg, n_cig};
+    if (n_cig != 2) return v;
+    const uint32_t c0 = rd<uint32_t>(cg), c1 = rd<uint32_t>(cg + 4);
+    if ((c0 & 15u) != 4u || (int64_t)(c0 >> 4) != (int64_t)l_seq || (c1 & 15u) != 3u) return v;
+    const uint8_t* p = cg + 8 + (size_t)(l_seq + 1) / 2 + (size_t)l_seq;
+    const uint8_t* end = r + bs;
+    while (p + 3 <= end) {
+        const uint8_t t0 = p[0], t1 = p[1], type = p[2];
+        p += 3;
+        const int fs = aux_size(type);
+        if (fs > 0) { p += fs; }
+        else if (type == 'Z' || type == 'H') { while (p < end && *p) p++; p++; }
+        else if (type == 'B') {
+            if (p + 5 > end) return v;
+            const int es = aux_size(p[0]);
+            const int32_t cnt = rd<int32_t>(p + 1);
+            if (es < 0 || cnt < 0 || p + 5 + (size_t)es * (size_t)cnt > end) return v;
+            if (t0 == 'C' && t1 == 'G' && p[0] == 'I') { v.p = p + 5; v.n = cnt; return v; }
+            p += 5 + (size_t)es * (size_t)cnt;
+        } else return v;
+    }
+    return v;
+}
+int64_t real_cigar_count(const uint8_t* r, int32_t bs) { return real_cigar(r, bs).n; }
 
 }  // namespace
 
@@ -435,7 +472,7 @@ int nc_bam_fill(const nc_bam* b, int i, int threads, int32_t* pos, uint16_t* fla
     for (int64_t k = 0; k < c.n_reads; k++) {
         const uint8_t* r = d + ro[k] + 4;
         cigar_off[k] = co; seq_off[k] = so;
-        co += rd<uint16_t>(r + 12);
+        co += real_cigar(r, rd<int32_t>(r - 4)).n;
         so += (rd<int32_t>(r + 16) + 1) / 2;
     }
     cigar_off[c.n_reads] = co; seq_off[c.n_reads] = so;
@@ -451,7 +488,8 @@ int nc_bam_fill(const nc_bam* b, int i, int threads, int32_t* pos, uint16_t* fla
         const int32_t ls = rd<int32_t>(r + 16);
         l_seq[k] = ls;
         const uint8_t* p = r + 32 + l_name;
-        if (n_cig) memcpy(cigar + cigar_off[k], p, 4 * (size_t)n_cig);
+        const CigarView cv = real_cigar(r, bs);
+        if (cv.n) memcpy(cigar + cigar_off[k], cv.p, 4 * (size_t)cv.n);
         p += 4 * (size_t)n_cig;
         const size_t nb = (size_t)(ls + 1) / 2;
         if (nb) memcpy(seq4 + seq_off[k], p, nb);

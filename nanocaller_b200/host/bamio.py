@@ -65,8 +65,12 @@ def write_bam(path, readsets, header_text=None, index=False):
             pos = int(rs.pos[i])
             end = max(pos + 1, int(ends[i]))
             bin_ = _reg2bin(pos, end)
-            core = struct.pack("<iiBBHHHiiii", rid, pos, len(name), 60, bin_, len(cig), int(rs.flag[i]), l_seq, -1, -1, 0)
-            body = core + name + cig.astype("<u4").tobytes() + seq.tobytes()[:(l_seq + 1) // 2] + b"\xff" * l_seq + aux
+            cig_field = cig.astype("<u4")
+            if len(cig) > 65535:         # SAM spec 4.2.2: placeholder `<l_seq>S<ref_len>N` + the real operations in CG:B,I
+                aux += b"CGBI" + struct.pack("<i", len(cig)) + cig_field.tobytes()
+                cig_field = np.array([(l_seq << 4) | 4, ((end - pos) << 4) | 3], "<u4")
+            core = struct.pack("<iiBBHHHiiii", rid, pos, len(name), 60, bin_, len(cig_field), int(rs.flag[i]), l_seq, -1, -1, 0)
+            body = core + name + cig_field.tobytes() + seq.tobytes()[:(l_seq + 1) // 2] + b"\xff" * l_seq + aux
             rec = struct.pack("<i", len(body)) + body
             parts.append(rec)
             recs.append((rid, pos, end, bin_, u, u + len(rec)))
@@ -123,7 +127,8 @@ _AUX_FMT = {ord("c"): "<b", ord("C"): "<B", ord("s"): "<h", ord("S"): "<H", ord(
 
 
 def _aux_ints(buf, off, end, want=(b"HP", b"PS")):
-    """Integer values of the wanted aux tags of one record."""
+    """Integer values of the wanted aux tags of one record; a CG:B,I array (the real CIGAR of a read with more than 65,535
+    operations, SAM spec 4.2.2) is returned under b"CG" as a uint32 array."""
     out = {}
     while off + 3 <= end:
         tag, typ = bytes(buf[off:off + 2]), buf[off + 2]
@@ -137,6 +142,8 @@ def _aux_ints(buf, off, end, want=(b"HP", b"PS")):
         elif typ == ord("B"):
             sub = buf[off]
             n = struct.unpack_from("<i", buf, off + 1)[0]
+            if tag == b"CG" and sub == ord("I"):
+                out[b"CG"] = np.frombuffer(buf, "<u4", n, off + 5)
             off += 5 + n * _AUX_FIXED.get(sub, 1)
         else:
             break
@@ -180,6 +187,8 @@ def read_bam(path, fasta=None, contigs=None):
         seq = np.frombuffer(buf, np.uint8, nb, p)
         p += nb + l_seq
         tags = _aux_ints(buf, p, off)
+        if n_cig == 2 and b"CG" in tags and (int(cig[0]) & 15) == 4 and (int(cig[0]) >> 4) == l_seq and (int(cig[1]) & 15) == 3:
+            cig = tags[b"CG"]            # long-CIGAR placeholder `<l_seq>S<ref_len>N`: htslib / pysam hand the reference the real one
         d = per[rid]
         d["pos"].append(pos); d["flag"].append(flag); d["lseq"].append(l_seq); d["cig"].append(cig); d["seq"].append(seq)
         d["hp"].append(tags.get(b"HP", 0)); d["ps"].append(tags.get(b"PS", 0)); d["qn"].append(qn)

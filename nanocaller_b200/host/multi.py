@@ -120,7 +120,8 @@ def run_distributed(args, run_fn, regions, dist, device="cpu"):
     out_r, failure = {}, None
     if mine:
         sub = copy.copy(args)
-        sub.regions = ["%s:%d-%d" % (c, s, e) for c, s, e, _ in mine]
+        sub.regions = ["%s:%d-%d" % (c, s, e) for c, s, e, _ in mine]      # for the `args` log only
+        sub._regions = [tuple(r) for r in mine]                                # the share itself: contig names may hold ':' (HLA-A*01:01:01:01)
         sub.bed = None
         sub.wgs_contigs = None
         sub.output = os.path.join(args.output, "rank%d" % rank)

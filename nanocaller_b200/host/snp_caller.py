@@ -99,11 +99,11 @@ def call_chunks_blob(params, chunks, snp_weights, hap_weights=None, device=0, im
         if hap_weights is None:
             raise ValueError("haploid region needs the haploid SNP model")
         ctx.load_snp_weights(W.pack_snp_blob(hap_weights, True), 30.0, True)                  # snpCaller.py:73
-        normalize = True
     else:
         tensors, tc = snp_weights
         ctx.load_snp_weights(W.pack_snp_blob(tensors, False), tc, False)
-        normalize = not params.get("disable_coverage_normalization", False)
+    # both ploidy branches honour --disable_coverage_normalization (snpCaller.py:93-96 diploid, :169-172 haploid: hap_train_coverage / dp)
+    normalize = not params.get("disable_coverage_normalization", False)
     rs = sources.resolve(params["sam_path"], chrom)
     bed = sources.bed_intervals(params.get("exclude_bed"), chrom)
     n = snp_pileups.scan_chunks(ctx, rs, params, chunks, ploidy, bed)

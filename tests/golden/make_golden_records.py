@@ -26,11 +26,14 @@ from nanocaller_src.utils import get_chunks  # noqa: E402  (reference, unchanged
 from tests.golden.cases import case_inputs  # noqa: E402
 
 RECORD_CASES = {"ont_diploid": {}, "haploid": {}, "ont_subregion_bed": {"disable_coverage_normalization": True}, "lowcov": {},
-                "hifi_pacbio": {"snp_model": "CCS-HG002"}}
+                "hifi_pacbio": {"snp_model": "CCS-HG002"},
+                # haploid contig with --disable_coverage_normalization (snpCaller.py:169-170: hap_train_coverage / dp per site)
+                "haploid_nonorm": {"_case": "haploid", "disable_coverage_normalization": True}}
 
 
 def run_case(name, over):
-    rs, dct, regions, cpu, bed = case_inputs(name)
+    over = dict(over)
+    rs, dct, regions, cpu, bed = case_inputs(over.pop("_case", name))
     pysam.unregister_all()
     pysam.register("mem://bam", rs)
     if bed is not None:

@@ -324,3 +324,40 @@ def test_vcf_headers_equal_the_reference_literals():
         ref = [ln.replace("%s", "X") for ln in want[kind]]
         got = [ln for ln in vcfio.header(kind, ["X"], "X").split("\n") if ln]
         assert got == ref and len(ref) >= 7, kind
+
+
+def test_long_cigar_cg_tag_round_trip(tmp_path):
+    """A read with more than 65,535 CIGAR operations is stored as `<l_seq>S<ref_len>N` + CG:B,I (SAM spec 4.2.2; routine for the
+    ultra-long reads of the ul_ont presets).  htslib restores the real CIGAR for the reference; both readers here must too."""
+    from nanocaller_b200.host.readset import ReadSet
+    rng = np.random.default_rng(11)
+    n_ops = 70_001                                         # alternating 2M 1D ... : 35,001 M + 35,000 D
+    ops = np.empty(n_ops, np.uint32)
+    ops[0::2] = (2 << 4) | 0
+    ops[1::2] = (1 << 4) | 2
+    l_long = 2 * 35_001
+    short = np.array([(50 << 4) | 0], np.uint32)
+    contig = 3 * 35_001 + 200
+    ref = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, contig)]
+    lseq = np.array([50, l_long, 50], np.int32)
+    seq_bytes = (lseq.astype(np.int64) + 1) // 2
+    seq_off = np.concatenate([[0], np.cumsum(seq_bytes)])
+    nib = np.array([1, 2, 4, 8], np.uint8)[rng.integers(0, 4, int(seq_off[-1]) * 2)]
+    seq4 = (nib[0::2] << 4 | nib[1::2]).astype(np.uint8)
+    cigar = np.concatenate([short, ops, short])
+    cig_off = np.array([0, 1, 1 + n_ops, 2 + n_ops], np.int64)
+    rs = ReadSet("chrL", ref, [5, 10, 60], [0, 16, 0], cig_off, cigar, seq_off, lseq, seq4, hp=[1, 2, 0], ps=[7, 7, 0])
+    bam, fa = str(tmp_path / "l.bam"), str(tmp_path / "l.fa")
+    bamio.write_bam(bam, [rs], index=True)
+    bamio.write_fasta(fa, [rs])
+    fasta = bamio.read_fasta(fa)
+    # the file really holds the placeholder: n_cigar_op of the long read is 2
+    import struct
+    buf = bamio.bgzf_decompress(bam)
+    assert buf.count(b"CGBI" + struct.pack("<i", n_ops)) == 1
+    got_py, _ = bamio.read_bam(bam, fasta)
+    _same(got_py[0], rs)
+    for threads in (1, 3):
+        got_n, _ = bamio.read_bam_native(bam, fasta, threads=threads)
+        _same(got_n[0], rs)
+    assert int(got_py[0].ref_end[1]) == 10 + 3 * 35_000 + 2

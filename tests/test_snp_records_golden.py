@@ -22,7 +22,7 @@ from tests.golden_util import load_case
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = {"ont_diploid": {}, "haploid": {}, "ont_subregion_bed": {"disable_coverage_normalization": True}, "lowcov": {},
-         "hifi_pacbio": {"snp_model": "CCS-HG002"}}
+         "hifi_pacbio": {"snp_model": "CCS-HG002"}, "haploid_nonorm": {"_case": "haploid", "disable_coverage_normalization": True}}
 _models = {}
 
 
@@ -39,7 +39,7 @@ def _fixture(name, rs):
 
 
 def _chain(name, over, record_fns):
-    rs, dct, chunks, bed, g = load_case(name)
+    rs, dct, chunks, bed, g = load_case(over.get("_case", name))
     tensors, meta = _model(over.get("snp_model", "ONT-HG002"))
     hap, _ = _model("haploid")
     out = [[] for _ in record_fns]
