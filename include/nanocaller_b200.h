@@ -94,7 +94,9 @@ typedef struct NcTimings {
     float    cnn_ms;         /* K3: CNN forward                                               */
     uint64_t launches;       /* kernels launched by this library on this context since create */
     uint64_t tensor_bytes;   /* algorithmic bytes of the last K2 launch        */
-    uint64_t scan_bytes;     /* algorithmic bytes of the last K0+K1 pass                      */
+    uint64_t scan_bytes;     /* SURVEY.md 8(d) B1 of the last K0+K1 pass: 4 B per CIGAR op + 4-bit bases + 16 B per read + 1 B per
+                              * piled reference position + 5 B per (read, neighbour site); the candidates' (read, site) pairs
+                              * are added by the caller from NcSiteMeta.dp */
     float    cnn_a_ms;       /* part of cnn_ms spent in the conv1+conv2 kernel (tensor-core path), else 0 */
     float    reserved;
 } NcTimings;
@@ -148,6 +150,10 @@ int nc_snp_scan(nc_ctx* ctx, const NcSnpParams* params, const NcChunk* chunks, i
  *   chunk_depth double [n_chunks]   mean(len(sample)) per chunk (:274), 0 for empty chunks
  *   chunk_count int64  [n_chunks]   candidates emitted per chunk */
 int nc_snp_fetch(nc_ctx* ctx, int16_t* mat, NcSiteMeta* meta, double* chunk_depth, int64_t* chunk_count);
+
+/* Tensors of `count` consecutive sites starting at site `first` of the last scan (sites are in (chunk, position) order, so
+ * a chunk is one range): int16 [count][NC_SNP_SITE_STRIDE]. */
+int nc_snp_fetch_range(nc_ctx* ctx, int64_t first, int64_t count, int16_t* mat);
 
 /* Model weights: packed fp32 blob in the canonical tensor order of
  * nanocaller_b200/host/weights.py (`pack_snp_blob`): conv1_1 k,b  conv1_2 k,b  conv1_3 k,b
@@ -230,6 +236,32 @@ int nc_indel_fetch_variants(nc_ctx* ctx, NcIndelVariant* out);
 int nc_indel_build(nc_ctx* ctx, const NcIndelParams* params, const NcChunk* chunks, int32_t n_chunks,
                    const NcIndelVariant* sites, int64_t n_sites);
 int nc_indel_fetch(nc_ctx* ctx, NcIndelSiteMeta* meta, float* tensors, uint8_t* cns);
+
+/* Tensors of `count` consecutive sites of the last build starting at site `first`: float32 [count][3][5][128][2]. */
+int nc_indel_fetch_range(nc_ctx* ctx, int64_t first, int64_t count, float* tensors);
+
+/* indel_model(batch_x_all) (indelCaller.py:83-85) / hap_indel_model(batch_x) (:171) on the tensors of the last nc_indel_build,
+ * which stay on the device: [n_sites][3][5][128][2] IS np.hstack([x0, x1, x2]) = [n_sites][15][128][2] (diploid); the haploid
+ * model reads group 2.  Every built site gets a row (the host drops the sites whose msa() flags are not all set, :342-348).
+ * probs (host, may be NULL): float32 [n_sites][4] softmax / [n_sites][1] sigmoid.  impl as in nc_snp_forward. */
+int nc_indel_forward(nc_ctx* ctx, int impl, float* probs);
+int nc_indel_fetch_probs(nc_ctx* ctx, float* probs);
+
+/* Device-side timings (CUDA events on the context stream, host synchronisation gaps included) of the last nc_indel_scan /
+ * nc_indel_build / nc_indel_forward, and the unit counts their rooflines are computed from. */
+typedef struct NcIndelTimings {
+    float    scan_ms;        /* I1: depth per haplotype, indel events, window sets, decision, greedy `prev` pass */
+    float    reads_ms;       /* I2: reads and query slices of every key position                               */
+    float    align_ms;       /* I3: slice x reference-window alignment (indel_align_kernel)                    */
+    float    msa_ms;         /* I3: column merge, frequencies, tensors, consensus (indel_msa_kernel)           */
+    float    cnn_ms;         /* M3 / M4: nc_indel_forward                                                      */
+    float    reserved[3];
+    uint64_t n_sites;        /* key positions of the last build                                               */
+    uint64_t n_entries;      /* (site, read group member) slices aligned by the last build                    */
+    uint64_t scan_bytes;     /* algorithmic bytes of the scan: aligned rows + CIGARs once, 6 B of depth + 1 B flag per column */
+    uint64_t build_bytes;    /* algorithmic bytes of the build: slices + reference windows read, tensors + consensus written */
+} NcIndelTimings;
+int nc_get_indel_timings(nc_ctx* ctx, NcIndelTimings* out);
 
 /* Host-side global affine alignment with traceback, replaces parasail.nw_trace(query, ref, open, extend, matrix)
  * (generate_indel_pileups.py:79): codes A0 G1 T2 C3; cigar_out receives (len << 4 | op) words, op '='7 'X'8 'I'1 'D'2.

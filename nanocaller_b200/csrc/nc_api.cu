@@ -46,6 +46,7 @@ struct nc_ctx {
     // staged contig
     bool staged = false, decoded = false, scanned = false;
     int64_t n_reads = 0, n_cigar = 0, n_seq = 0, ref_start = 0, ref_len = 0;
+    uint64_t decode_bytes = 0;
     DevBuf d_pos, d_flag, d_cigar_off, d_cigar, d_seq_off, d_lseq, d_seq4, d_ref, d_fill_counter, d_seqc;
     // decode products
     DevBuf d_end, d_nwords, d_opstart, d_pmaxend, d_rowoff, d_rows;
@@ -76,6 +77,11 @@ struct nc_ctx {
     // timings
     cudaEvent_t ev_block = nullptr;   // blocking-sync event (NC_BLOCKING_SYNC=1), else spin on the stream
     cudaEvent_t ev[13] = {};     // 0-7 phase timings, 8-11 user slots (nc_event_record), 12 end of the conv1/conv2 kernel
+    cudaEvent_t evi[8] = {};     // indel path: 0-1 scan, 2-5 build (start, slices, align, msa), 6-7 CNN
+    NcIndelTimings tmi = {};
+    bool tmi_scan = false, tmi_build = false, tmi_cnn = false, have_iprobs = false;
+    int build_haploid = 0;
+    DevBuf d_iprobs;
     NcTimings tm = {};
     bool tm_decode = false, tm_scan = false, tm_cnn = false, tm_cnn_a = false;
 };
@@ -369,6 +375,8 @@ int nc_create(int device, nc_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NC_ECUDA; }
     for (auto& e : c->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { delete c; return NC_ECUDA; }
+    for (auto& e : c->evi)
+        if (cudaEventCreate(&e) != cudaSuccess) { delete c; return NC_ECUDA; }
     const char* bs = getenv("NC_BLOCKING_SYNC");
     if (bs && bs[0] == '1' && cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) { delete c; return NC_ECUDA; }
     *out = c;
@@ -399,6 +407,8 @@ void nc_destroy(nc_ctx* c) {
     }
     c->pin.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->evi) if (e) cudaEventDestroy(e);
+    c->d_iprobs.release();
     if (c->ev_block) cudaEventDestroy(c->ev_block);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -533,8 +543,9 @@ int nc_decode_reads(nc_ctx* c) {
     }
     NC_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->tm_decode = true;
-    // algorithmic bytes of K0: BAM-native input once + the aligned rows once
-    c->tm.scan_bytes = (uint64_t)c->n_cigar * 4 + (uint64_t)c->n_seq + (uint64_t)n * 16 + (uint64_t)c->n_row_words * 4;
+    // SURVEY 8(d) B1, read side: BAM-native CIGAR words + 4-bit bases + a 16-byte header per read
+    c->decode_bytes = (uint64_t)c->n_cigar * 4 + (uint64_t)c->n_seq + (uint64_t)n * 16;
+    c->tm.scan_bytes = c->decode_bytes;
     c->decoded = true;
     return NC_OK;
 }
@@ -616,8 +627,6 @@ int nc_snp_scan(nc_ctx* c, const NcSnpParams* P, const NcChunk* chunks, int32_t 
                                                                         c->d_cand_off.as<int64_t>(), c->d_nbr_pos.as<int32_t>(),
                                                                         c->d_cand_pos.as<int32_t>());
     NC_LAUNCH_CHECK();
-    // K0 bytes were counted at decode; K1 reads every aligned row once, the reference once, and writes one flag byte per position
-    c->tm.scan_bytes = (uint64_t)c->n_row_words * 4 + (uint64_t)(hi - lo) * 2 + (uint64_t)c->n_reads * 10;
 
     // neighbour matrix
     NC_CUDA(c->d_nfirst.reserve((size_t)c->n_reads * 4));
@@ -632,6 +641,9 @@ int nc_snp_scan(nc_ctx* c, const NcSnpParams* P, const NcChunk* chunks, int32_t 
     int64_t n_nbytes = 0;
     if ((rc = read_i64(c, c->d_noff.as<int64_t>() + c->n_reads, &n_nbytes))) return rc;
     NC_CUDA(c->d_nrows.reserve((size_t)std::max<int64_t>(n_nbytes, 16)));
+    // SURVEY 8(d) B1 = reads (CIGAR + bases + header) + one reference byte per piled position + 5 B per (read, kept site):
+    // the neighbour matrix holds one nibble per (read, neighbour site), i.e. 2 * n_nbytes pairs; the host adds the candidates' reads
+    c->tm.scan_bytes = c->decode_bytes + (uint64_t)(hi - lo) + (uint64_t)10 * (uint64_t)n_nbytes;
     nmat_fill_kernel<<<rg, 256, 0, c->stream>>>(c->n_reads, c->d_pos.as<int32_t>(), c->d_rowoff.as<int64_t>(), c->d_rows.as<uint32_t>(),
                                                 c->d_nbr_pos.as<int32_t>(), c->d_nfirst.as<int32_t>(), c->d_nlen.as<int32_t>(),
                                                 c->d_noff.as<int64_t>(), c->d_nrows.as<uint8_t>());
@@ -702,6 +714,16 @@ int nc_snp_fetch(nc_ctx* c, int16_t* mat, NcSiteMeta* meta, double* chunk_depth,
     if (meta && c->n_sites) NC_CUDA(cudaMemcpyAsync(meta, c->d_meta.p, (size_t)c->n_sites * sizeof(NcSiteMeta), cudaMemcpyDeviceToHost, c->stream));
     if (chunk_depth && c->n_chunks) NC_CUDA(cudaMemcpyAsync(chunk_depth, c->d_chunk_depth.p, (size_t)c->n_chunks * 8, cudaMemcpyDeviceToHost, c->stream));
     if (chunk_count && c->n_chunks) NC_CUDA(cudaMemcpyAsync(chunk_count, c->d_chunk_count.p, (size_t)c->n_chunks * 8, cudaMemcpyDeviceToHost, c->stream));
+    NC_CUDA(nc_stream_wait(c));
+    return NC_OK;
+}
+
+int nc_snp_fetch_range(nc_ctx* c, int64_t first, int64_t count, int16_t* mat) {
+    if (!c) return NC_EINVAL;
+    if (!c->scanned) return fail(c, NC_ESTATE, "nc_snp_fetch_range before nc_snp_scan");
+    if (first < 0 || count < 0 || first + count > c->n_sites || (count > 0 && !mat)) return fail(c, NC_EINVAL, "nc_snp_fetch_range: bad range");
+    NC_CUDA(cudaSetDevice(c->device));
+    if (count) NC_CUDA(cudaMemcpyAsync(mat, c->d_mat.as<int16_t>() + first * NC_SNP_SITE_STRIDE, (size_t)count * NC_SNP_SITE_STRIDE * 2, cudaMemcpyDeviceToHost, c->stream));
     NC_CUDA(nc_stream_wait(c));
     return NC_OK;
 }
@@ -867,7 +889,7 @@ int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int3
     NC_CUDA(cudaSetDevice(c->device));
     int rc = nc_decode_reads(c);
     if (rc) return rc;
-    c->indel_scanned = c->indel_built = false; c->n_variants = 0;
+    c->indel_scanned = c->indel_built = false; c->n_variants = 0; c->tmi_scan = false;
     for (int i = 0; i + 1 < n_chunks; i++)
         if (chunks[i + 1].start < chunks[i].start) return fail(c, NC_EINVAL, "indel chunks must be sorted by start");
     int64_t lo = INT64_MAX, hi = INT64_MIN;
@@ -896,6 +918,7 @@ int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int3
     const int32_t lo_al = (int32_t)lo & ~7;
     const int64_t n_tiles = div_up(hi - lo_al, kTilePos), n_al = n_tiles * kTilePos;
     c->indel_lo_al = lo_al;
+    NC_CUDA(cudaEventRecord(c->evi[0], c->stream));
     NC_CUDA(c->d_idepth.reserve((size_t)3 * n_al * 2));
     NC_CUDA(c->d_em.reserve((size_t)n_al * 4));
     NC_CUDA(c->d_grank.reserve((size_t)(n_al + 1) * 8));
@@ -980,6 +1003,10 @@ int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int3
                                                                                             c->d_icount.as<unsigned long long>() + 1);
     NC_LAUNCH_CHECK();
     if ((rc = read_i64(c, c->d_icount.as<int64_t>() + 1, &c->n_variants))) return rc;
+    NC_CUDA(cudaEventRecord(c->evi[1], c->stream));
+    c->tmi_scan = true;
+    // aligned rows and CIGAR words once, three u16 depths written and read + the emitted flag per scanned column
+    c->tmi.scan_bytes = (uint64_t)c->n_row_words * 4 + (uint64_t)c->n_cigar * 4 + (uint64_t)(hi - lo) * 13;
     c->indel_scanned = true;
     *n_variants = c->n_variants;
     return NC_OK;
@@ -1004,8 +1031,10 @@ int nc_indel_build(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int
     NC_CUDA(cudaSetDevice(c->device));
     int rc = nc_decode_reads(c);
     if (rc) return rc;
-    c->indel_built = false; c->n_isites = n_sites;
+    c->indel_built = false; c->n_isites = n_sites; c->have_iprobs = false; c->tmi_build = false; c->build_haploid = P->haploid ? 1 : 0;
+    c->tmi.n_sites = (uint64_t)n_sites; c->tmi.n_entries = 0; c->tmi.build_bytes = 0;
     if (n_sites == 0) { c->indel_built = true; return NC_OK; }
+    NC_CUDA(cudaEventRecord(c->evi[2], c->stream));
     for (int64_t i = 0; i < n_sites; i++)
         if (sites[i].chunk < 0 || sites[i].chunk >= n_chunks) return fail(c, NC_EINVAL, "site %lld names chunk %d of %d", (long long)i, sites[i].chunk, n_chunks);
     // sites found by impute_indel_phase: recompute the two read sets from the source column (generate_indel_pileups.py:309-313)
@@ -1060,6 +1089,7 @@ int nc_indel_build(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int
     sa.e_insfirst = c->d_einsfirst.as<uint16_t>(); sa.tensors = c->d_itensors.as<float>(); sa.cns = c->d_icns.as<uint8_t>();
     sa.meta = c->d_imeta.as<NcIndelSiteMeta>();
     indel_site_reads_kernel<true><<<sg, 128, 0, c->stream>>>(sa); NC_LAUNCH_CHECK();
+    NC_CUDA(cudaEventRecord(c->evi[3], c->stream));
     if (n_entries > 0) {
         const int smem = kAlignWarps * kRowsMax * 32 * 4;
         // function attributes are per device and one process may open contexts on several: set it on every call (cheap, no sync)
@@ -1067,7 +1097,14 @@ int nc_indel_build(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int
         const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_entries, kAlignWarps), (int64_t)c->sm_count * 12);
         indel_align_kernel<<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries); NC_LAUNCH_CHECK();
     }
+    NC_CUDA(cudaEventRecord(c->evi[4], c->stream));
     indel_msa_kernel<<<(unsigned)n_sites, 96, 0, c->stream>>>(sa); NC_LAUNCH_CHECK();
+    NC_CUDA(cudaEventRecord(c->evi[5], c->stream));
+    c->tmi_build = true; c->tmi.n_entries = (uint64_t)n_entries;
+    // per aligned slice: the query slice and the reference window (one byte per base); per site: 3 x [5][128][2] fp32 tensors,
+    // the consensus strings and the site record
+    c->tmi.build_bytes = (uint64_t)n_entries * (uint64_t)(2 * (P->window_after + 1)) +
+                         (uint64_t)n_sites * (3 * 1280 * 4 + 3 * NC_INDEL_CNS_MAX + sizeof(NcIndelSiteMeta));
     c->indel_built = true;
     return NC_OK;
 }
@@ -1083,6 +1120,67 @@ int nc_indel_fetch(nc_ctx* c, NcIndelSiteMeta* meta, float* tensors, uint8_t* cn
         if (cns) NC_CUDA(cudaMemcpyAsync(cns, c->d_icns.p, n * 3 * NC_INDEL_CNS_MAX, cudaMemcpyDeviceToHost, c->stream));
     }
     NC_CUDA(nc_stream_wait(c));
+    return NC_OK;
+}
+
+int nc_indel_fetch_range(nc_ctx* c, int64_t first, int64_t count, float* tensors) {
+    if (!c) return NC_EINVAL;
+    if (!c->indel_built) return fail(c, NC_ESTATE, "nc_indel_fetch_range before nc_indel_build");
+    if (first < 0 || count < 0 || first + count > c->n_isites || (count > 0 && !tensors)) return fail(c, NC_EINVAL, "nc_indel_fetch_range: bad range");
+    NC_CUDA(cudaSetDevice(c->device));
+    if (count) NC_CUDA(cudaMemcpyAsync(tensors, c->d_itensors.as<float>() + first * 3 * 1280, (size_t)count * 3 * 1280 * 4, cudaMemcpyDeviceToHost, c->stream));
+    NC_CUDA(nc_stream_wait(c));
+    return NC_OK;
+}
+
+int nc_indel_forward(nc_ctx* c, int impl, float* probs) {
+    if (!c) return NC_EINVAL;
+    if (!c->indel_built) return fail(c, NC_ESTATE, "nc_indel_forward before nc_indel_build");
+    NC_CUDA(cudaSetDevice(c->device));
+    const int hap = c->build_haploid;
+    Model& M = c->indel[hap];
+    if (!M.loaded) return fail(c, NC_ESTATE, "nc_indel_forward: no %s indel weights loaded", hap ? "haploid" : "diploid");
+    const int64_t n = c->n_isites;
+    const int nout = hap ? 1 : 4;
+    NC_CUDA(cudaEventRecord(c->evi[6], c->stream));
+    if (n > 0) {
+        NC_CUDA(c->d_iprobs.reserve((size_t)n * nout * sizeof(float)));
+        // [n][3][5][128][2] is the hstack of the three groups (indelCaller.py:83); the haploid model reads group 2 of every site
+        const float* x = c->d_itensors.as<float>() + (hap ? 2 * 1280 : 0);
+        int rc = cnn_forward(c, M, impl, 0, x, 3 * 1280, n, nullptr, nullptr, nullptr, nullptr, c->d_iprobs.as<float>(), nullptr);
+        if (rc) return rc;
+    }
+    NC_CUDA(cudaEventRecord(c->evi[7], c->stream));
+    c->tmi_cnn = true; c->have_iprobs = true;
+    if (probs && n > 0) {
+        NC_CUDA(cudaMemcpyAsync(probs, c->d_iprobs.p, (size_t)n * nout * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        NC_CUDA(nc_stream_wait(c));
+        if (impl == 0) return tc_check(c, M);
+    }
+    return NC_OK;
+}
+
+int nc_indel_fetch_probs(nc_ctx* c, float* probs) {
+    if (!c || !probs) return fail(c, NC_EINVAL, "nc_indel_fetch_probs: null argument");
+    if (!c->indel_built || !c->have_iprobs) return fail(c, NC_ESTATE, "nc_indel_fetch_probs before nc_indel_forward");
+    NC_CUDA(cudaSetDevice(c->device));
+    if (c->n_isites) NC_CUDA(cudaMemcpyAsync(probs, c->d_iprobs.p, (size_t)c->n_isites * (c->build_haploid ? 1 : 4) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    NC_CUDA(nc_stream_wait(c));
+    return tc_check(c, c->indel[c->build_haploid]);
+}
+
+int nc_get_indel_timings(nc_ctx* c, NcIndelTimings* out) {
+    if (!c || !out) return NC_EINVAL;
+    NC_CUDA(cudaSetDevice(c->device));
+    NC_CUDA(nc_stream_wait(c));
+    if (c->tmi_scan) { NC_CUDA(cudaEventElapsedTime(&c->tmi.scan_ms, c->evi[0], c->evi[1])); }
+    if (c->tmi_build) {
+        NC_CUDA(cudaEventElapsedTime(&c->tmi.reads_ms, c->evi[2], c->evi[3]));
+        NC_CUDA(cudaEventElapsedTime(&c->tmi.align_ms, c->evi[3], c->evi[4]));
+        NC_CUDA(cudaEventElapsedTime(&c->tmi.msa_ms, c->evi[4], c->evi[5]));
+    }
+    if (c->tmi_cnn) { NC_CUDA(cudaEventElapsedTime(&c->tmi.cnn_ms, c->evi[6], c->evi[7])); }
+    *out = c->tmi;
     return NC_OK;
 }
 

@@ -14,10 +14,10 @@ SEQ_CODES = {"ont": 0, "short_ont": 1, "ul_ont": 2, "ul_ont_extreme": 3, "pacbio
 SITE_ELEMS, SITE_STRIDE = 1025, 1032
 
 EXPORTS = ["nc_abi_version", "nc_create", "nc_destroy", "nc_last_error", "nc_sync", "nc_set_blocking_sync", "nc_get_timings",
-           "nc_device_sm_count", "nc_event_record", "nc_event_elapsed_ms", "nc_invalidate_decode", "nc_stage_reads", "nc_decode_reads", "nc_snp_scan", "nc_snp_fetch",
+           "nc_device_sm_count", "nc_event_record", "nc_event_elapsed_ms", "nc_invalidate_decode", "nc_stage_reads", "nc_decode_reads", "nc_snp_scan", "nc_snp_fetch", "nc_snp_fetch_range", "nc_indel_fetch_range",
            "nc_load_snp_weights", "nc_snp_forward", "nc_snp_fetch_probs", "nc_snp_model_forward", "nc_snp_device_buffers",
            "nc_load_indel_weights", "nc_indel_model_forward", "nc_stage_tags", "nc_indel_scan", "nc_indel_fetch_variants",
-           "nc_indel_build", "nc_indel_fetch", "nc_nw_trace", "nc_allele_predict_batch",
+           "nc_indel_build", "nc_indel_fetch", "nc_indel_forward", "nc_indel_fetch_probs", "nc_get_indel_timings", "nc_nw_trace", "nc_allele_predict_batch",
            "nc_format_snp_records"]
 
 
@@ -37,6 +37,12 @@ class NcIndelParams(ctypes.Structure):
     _fields_ = [("ins_t", ctypes.c_double), ("del_t", ctypes.c_double), ("mincov", ctypes.c_int32), ("maxcov", ctypes.c_int32),
                 ("win_size", ctypes.c_int32), ("small_win_size", ctypes.c_int32), ("window_after", ctypes.c_int32),
                 ("supplementary", ctypes.c_int32), ("haploid", ctypes.c_int32), ("impute_indel_phase", ctypes.c_int32)]
+
+
+class NcIndelTimings(ctypes.Structure):
+    _fields_ = [("scan_ms", ctypes.c_float), ("reads_ms", ctypes.c_float), ("align_ms", ctypes.c_float), ("msa_ms", ctypes.c_float),
+                ("cnn_ms", ctypes.c_float), ("reserved", ctypes.c_float * 3), ("n_sites", ctypes.c_uint64), ("n_entries", ctypes.c_uint64),
+                ("scan_bytes", ctypes.c_uint64), ("build_bytes", ctypes.c_uint64)]
 
 
 VARIANT_DTYPE = np.dtype([("key", "<i4"), ("type", "<i4"), ("chunk", "<i4"), ("src", "<i4")])
@@ -87,6 +93,8 @@ def load_library():
     lib.nc_decode_reads.argtypes = [vp]
     lib.nc_snp_scan.argtypes = [vp, ctypes.POINTER(NcSnpParams), vp, i32, vp, i32, ctypes.POINTER(i64)]
     lib.nc_snp_fetch.argtypes = [vp, vp, vp, vp, vp]
+    lib.nc_snp_fetch_range.argtypes = [vp, i64, i64, vp]
+    lib.nc_indel_fetch_range.argtypes = [vp, i64, i64, vp]
     lib.nc_load_snp_weights.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_double, ctypes.c_int]
     lib.nc_snp_forward.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
     lib.nc_snp_fetch_probs.argtypes = [vp, vp]
@@ -99,6 +107,9 @@ def load_library():
     lib.nc_indel_fetch_variants.argtypes = [vp, vp]
     lib.nc_indel_build.argtypes = [vp, ctypes.POINTER(NcIndelParams), vp, i32, vp, i64]
     lib.nc_indel_fetch.argtypes = [vp, vp, vp, vp]
+    lib.nc_indel_forward.argtypes = [vp, ctypes.c_int, vp]
+    lib.nc_indel_fetch_probs.argtypes = [vp, vp]
+    lib.nc_get_indel_timings.argtypes = [vp, ctypes.POINTER(NcIndelTimings)]
     lib.nc_nw_trace.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp, i32]
     for name in EXPORTS:
         if name not in ("nc_destroy", "nc_last_error"):
@@ -190,6 +201,8 @@ class Context:
         self._h = h
         self.device = device
         self.n_sites = 0
+        self.n_isites = 0
+        self._indel_haploid = False
         self.n_chunks = 0
         self._keep = []
 
@@ -237,16 +250,48 @@ class Context:
         self._check(self._lib.nc_indel_fetch_variants(self._h, _p(out) if n.value else None))
         return out
 
-    def indel_build(self, params, chunks, sites):
+    def indel_build(self, params, chunks, sites, want_tensors=True, fetch=True):
+        """Pass 2 + msa for `sites`; -> (meta, tensors or None, cns).  want_tensors=False leaves the tensors on the device
+        (for `indel_forward`); fetch=False copies nothing back (-> None)."""
         ch = np.array([(int(s), int(e)) for s, e in chunks], dtype=CHUNK_DTYPE)
         sites = np.ascontiguousarray(sites, VARIANT_DTYPE)
         n = len(sites)
         self._check(self._lib.nc_indel_build(self._h, ctypes.byref(params), _p(ch) if len(ch) else None, len(ch), _p(sites) if n else None, n))
+        self.n_isites, self._indel_haploid = n, bool(params.haploid)
+        if not fetch:
+            return None
         meta = np.empty(n, INDEL_META_DTYPE)
-        tensors = np.empty((n, 3, 5, 128, 2), np.float32)
+        tensors = np.empty((n, 3, 5, 128, 2), np.float32) if want_tensors else None
         cns = np.empty((n, 3, INDEL_CNS_MAX), np.uint8)
-        self._check(self._lib.nc_indel_fetch(self._h, _p(meta) if n else None, _p(tensors) if n else None, _p(cns) if n else None))
+        self._check(self._lib.nc_indel_fetch(self._h, _p(meta) if n else None, _p(tensors) if (n and want_tensors) else None, _p(cns) if n else None))
         return meta, tensors, cns
+
+    def indel_fetch(self, want_tensors=False):
+        n = self.n_isites
+        meta = np.empty(n, INDEL_META_DTYPE)
+        tensors = np.empty((n, 3, 5, 128, 2), np.float32) if want_tensors else None
+        cns = np.empty((n, 3, INDEL_CNS_MAX), np.uint8)
+        self._check(self._lib.nc_indel_fetch(self._h, _p(meta) if n else None, _p(tensors) if (n and want_tensors) else None, _p(cns) if n else None))
+        return meta, tensors, cns
+
+    def indel_forward(self, impl=0, fetch=True):
+        """Indel CNN on the device-resident tensors of the last `indel_build` -> float32 [n_sites, 4] (haploid: [n_sites, 1])."""
+        n = self.n_isites
+        probs = np.empty((n, 1 if self._indel_haploid else 4), np.float32) if fetch else None
+        self._check(self._lib.nc_indel_forward(self._h, impl, _p(probs) if fetch and n else None))
+        return probs
+
+    def indel_fetch_probs(self, out):
+        """Probabilities of the last `indel_forward` into a caller-owned (e.g. pinned) float32 array [n_sites, 4 or 1]."""
+        if self.n_isites == 0:
+            return
+        assert out.nbytes >= self.n_isites * (4 if self._indel_haploid else 16)
+        self._check(self._lib.nc_indel_fetch_probs(self._h, _p(out)))
+
+    def indel_timings(self):
+        t = NcIndelTimings()
+        self._check(self._lib.nc_get_indel_timings(self._h, ctypes.byref(t)))
+        return {k: getattr(t, k) for k, _ in NcIndelTimings._fields_ if k != "reserved"}
 
     def decode_reads(self):
         self._check(self._lib.nc_decode_reads(self._h))
@@ -271,6 +316,16 @@ class Context:
         self._check(self._lib.nc_snp_fetch(self._h, _p(mat) if want_mat and n else None, _p(meta) if n else None,
                                            _p(depth) if nc else None, _p(count) if nc else None))
         return mat, meta, depth, count
+
+    def snp_fetch_range(self, first, count):
+        mat = np.empty((count, SITE_STRIDE), np.int16)
+        self._check(self._lib.nc_snp_fetch_range(self._h, int(first), int(count), _p(mat) if count else None))
+        return mat
+
+    def indel_fetch_range(self, first, count):
+        t = np.empty((count, 3, 5, 128, 2), np.float32)
+        self._check(self._lib.nc_indel_fetch_range(self._h, int(first), int(count), _p(t) if count else None))
+        return t
 
     # ---- models
     def load_snp_weights(self, blob, train_coverage, haploid):

@@ -94,10 +94,10 @@ def call_chunk(params, chunk, indel_tensors, hap_tensors=None, device=0, impl=1)
     return records_from_calls(chunk["chrom"], pos, probs, alleles, phase)
 
 
-def call_chunks(params, chunks, indel_tensors, hap_tensors=None, device=0, impl=1, batch=4096):
-    """All chunks of ONE contig and ploidy in one scan + build on the GPU and batched CNN forwards; the record decision stays
-    per chunk (the reference's `prev` overlap suppression restarts with every chunk, indelCaller.py:88-93).  Same lines as
-    `call_chunk` chunk by chunk."""
+def call_chunks(params, chunks, indel_tensors, hap_tensors=None, device=0, impl=0):
+    """All chunks of ONE contig and ploidy: one scan + build on the GPU, the indel CNN on the tensors where they lie (they never
+    leave the device), alleles by one batched library call; the record decision stays per chunk (the reference's `prev` overlap
+    suppression restarts with every chunk, indelCaller.py:88-93).  Same lines as `call_chunk` chunk by chunk."""
     from . import weights as W
     if not chunks:
         return []
@@ -107,22 +107,15 @@ def call_chunks(params, chunks, indel_tensors, hap_tensors=None, device=0, impl=
     rs = sources.resolve(chunks[0]["sam_path"], chrom)
     bed = sources.bed_intervals(params.get("exclude_bed"), chrom)
     hap = ploidy == "haploid"
-    res = indel_pileups.candidates_for_chunks(ctx, rs, params, chunks, bed, haploid=hap)
-    xs = []
-    for r in res:
-        if len(r[0]):
-            xs.append(np.asarray(r[1], np.float32) if hap else np.hstack([r[1], r[2], r[3]]).astype(np.float32))   # indelCaller.py:83
-    if not xs:
+    meta, _, cns = indel_pileups.scan_build(ctx, rs, params, chunks, bed, haploid=hap, want_tensors=False)
+    if len(meta) == 0 or not indel_pileups.kept_sites(meta, hap).any():
         return []
     ctx.load_indel_weights(W.pack_indel_blob(hap_tensors if hap else indel_tensors), hap)
-    x = np.concatenate(xs)
-    probs = np.concatenate([ctx.indel_model_forward(x[b:b + batch], haploid=hap, impl=impl) for b in range(0, len(x), batch)])
-    out, o = [], 0
-    for r in res:
-        n = len(r[0])
-        if n == 0:
+    probs = ctx.indel_forward(impl=impl)                                   # a row per built site; only the kept ones are read
+    pred = indel_pileups.AllelePredictions(rs, params, meta, cns, hap).strings()
+    out = []
+    for sel, pos, alleles, phase in indel_pileups.per_chunk_calls(meta, pred, len(chunks), hap):
+        if len(sel) == 0:
             continue
-        p = probs[o:o + n]
-        o += n
-        out += haploid_records_from_calls(chrom, r[0], p, r[2]) if hap else records_from_calls(chrom, r[0], p, r[4], r[5])
+        out += haploid_records_from_calls(chrom, pos, probs[sel], alleles) if hap else records_from_calls(chrom, pos, probs[sel], alleles, phase)
     return out

@@ -63,72 +63,102 @@ def allele_prediction(alt, ref_seq, max_range, alt_codes=None, ref_codes=None):
 def order_variants(variants):
     """The reference keeps `variants` in a dict (a later hit on the same key overwrites the type, :268,:274,:301) and visits
     the keys in column order in pass 2 (:306-320); `extra_variants` (:302) is a second dict that keeps the source column of the
-    last imputed hit on a key and wins in pass 2 (:309).  Device hits arrive in (chunk, column) order per chunk."""
-    out = []
-    for c in np.unique(variants["chunk"]):
-        sel = variants[variants["chunk"] == c]
-        d, extra = {}, {}
-        for k, t, src in zip(sel["key"].tolist(), sel["type"].tolist(), sel["src"].tolist()):
-            d[k] = t
-            if src:
-                extra[k] = src
-        for k in sorted(d):
-            out.append((k, d[k], int(c), extra.get(k, 0)))
-    return np.array(out, dtype=capi.VARIANT_DTYPE) if out else np.zeros(0, capi.VARIANT_DTYPE)
+    last imputed hit on a key and wins in pass 2 (:309).  Device hits arrive in column order within a chunk (one warp per chunk
+    appends them); chunks interleave.  Vectorised: stable sort by (chunk, key), the last entry of every group gives the type,
+    the last entry with a source column gives `src`."""
+    n = len(variants)
+    if n == 0:
+        return np.zeros(0, capi.VARIANT_DTYPE)
+    key, chunk = variants["key"].astype(np.int64), variants["chunk"].astype(np.int64)
+    order = np.lexsort((np.arange(n), key, chunk))
+    k, c, t, src = key[order], chunk[order], variants["type"][order], variants["src"][order]
+    first = np.ones(n, bool)
+    first[1:] = (k[1:] != k[:-1]) | (c[1:] != c[:-1])
+    last = np.ones(n, bool)
+    last[:-1] = first[1:]
+    ar = np.arange(n)
+    start = np.maximum.accumulate(np.where(first, ar, 0))                 # index of the group's first entry
+    nz = np.maximum.accumulate(np.where(src != 0, ar, -1))                # index of the latest entry with a source column
+    src_last = np.where(nz >= start, src[np.maximum(nz, 0)], 0)
+    out = np.zeros(int(last.sum()), capi.VARIANT_DTYPE)
+    out["key"], out["type"], out["chunk"], out["src"] = k[last], t[last], c[last], src_last[last]
+    return out
 
 
-def candidates_for_chunks(ctx, rs, dct, chunks, bed=None, haploid=False):
-    """Scan + build for a list of chunk dicts of one contig; -> per-chunk reference-shaped tuples
-    (diploid: 6-tuple of generate_indel_pileups.py:370; haploid: 3-tuple of generate_indel_pileups_haploid.py:277)."""
+def scan_build(ctx, rs, dct, chunks, bed=None, haploid=False, want_tensors=True):
+    """Pass 1 (scan), the dict semantics of `variants`, pass 2 + msa (build) for a list of chunk dicts of one contig.
+    -> (meta, tensors or None, cns); with want_tensors=False the tensors stay on the device for `Context.indel_forward`."""
     snp_pileups.stage(ctx, rs)
     ctx.stage_tags(rs.hp, rs.ps)
     P = capi.indel_params(dct, haploid)
     ch = [(c["start"], c["end"]) for c in chunks]
     variants = ctx.indel_scan(P, ch, bed)
-    # hits of one chunk are produced in column order by one warp; keep that order when applying the dict semantics
     sites = order_variants(variants)
-    meta, tensors, cns = ctx.indel_build(P, ch, sites)
-    max_range = {0: max(10, int(dct["win_size"])), 1: 10}
-    # ---- allele prediction for every kept site and read group in one batched, multithreaded library call
-    okmask = meta["ok"][:, 2] > 0 if haploid else meta["ok"].min(1) > 0
-    kept = np.nonzero(okmask)[0]
-    groups = (2,) if haploid else (0, 1, 2)
-    pred = {}
-    if len(kept):
+    return ctx.indel_build(P, ch, sites, want_tensors=want_tensors)
+
+
+def kept_sites(meta, haploid):
+    """msa() succeeded for every group the caller uses (generate_indel_pileups.py:342-348)."""
+    return meta["ok"][:, 2] > 0 if haploid else meta["ok"].min(1) > 0
+
+
+class AllelePredictions:
+    """allele_prediction (generate_indel_pileups.py:77-127) for every kept site and read group, as arrays: item k is site
+    `site[k]`, group `grp[k]`; ref_out / alt_out = lengths of the allele strings (-1 / -1: the reference returns (None, None))."""
+
+    def __init__(self, rs, dct, meta, cns, haploid, threads=0):
+        self.groups = (2,) if haploid else (0, 1, 2)
+        self.cns, self.meta = cns, meta
+        kept = np.nonzero(kept_sites(meta, haploid))[0]
+        self.kept = kept
+        ng = len(self.groups)
+        self.site = np.repeat(kept, ng)
+        self.grp = np.tile(np.asarray(self.groups), len(kept))
+        if len(kept) == 0:
+            self.ref_out = self.alt_out = self.alt_len = self.r_len = np.zeros(0, np.int32)
+            self.r_off = np.zeros(0, np.int64)
+            self.ref_bytes = np.zeros(0, np.uint8)
+            return
+        p0 = meta["pos"][kept].astype(np.int64) - 1
+        m = meta["ref_len"][kept].astype(np.int64)
+        off = np.zeros(len(kept) + 1, np.int64)
+        np.cumsum(m, out=off[1:])
+        idx = np.repeat(p0 - off[:-1], m) + np.arange(off[-1])                 # flat gather of the reference windows
+        self.ref_bytes = rs.ref[idx]
+        ref_flat = _REF_CODE[self.ref_bytes]
         cap = cns.shape[2]
-        ref_rows, ref_off, ref_len = [], [], []
-        off = 0
-        for s in kept:
-            p0 = int(meta["pos"][s]) - 1
-            m = int(meta["ref_len"][s])
-            ref_rows.append(rs.ref[p0:p0 + m])
-            ref_off.append(off); ref_len.append(m)
-            off += m
-        ref_bytes = np.concatenate(ref_rows)
-        ref_flat = _REF_CODE[ref_bytes]
-        it_site = np.repeat(kept, len(groups))
-        it_grp = np.tile(np.asarray(groups), len(kept))
-        alt_off = (it_site.astype(np.int64) * cns.shape[1] + it_grp) * cap
-        alt_len = meta["cns_len"][it_site, it_grp].astype(np.int32)
-        r_off = np.repeat(np.asarray(ref_off, np.int64), len(groups))
-        r_len = np.repeat(np.asarray(ref_len, np.int32), len(groups))
-        mr = np.array([max_range[int(t)] for t in meta["type"][it_site]], np.int32)
-        ro, ao = capi.allele_predict_batch(cns.reshape(-1), alt_off, alt_len, ref_flat, r_off, r_len, mr)
-        ref_txt = ref_bytes.tobytes().decode()
-        for k in range(len(it_site)):
-            s, g = int(it_site[k]), int(it_grp[k])
-            if ro[k] < 0:
+        alt_off = (self.site.astype(np.int64) * cns.shape[1] + self.grp) * cap
+        self.alt_len = meta["cns_len"][self.site, self.grp].astype(np.int32)
+        self.r_off = np.repeat(off[:-1], ng)
+        self.r_len = np.repeat(m.astype(np.int32), ng)
+        win = max(10, int(dct["win_size"]))
+        mr = np.where(meta["type"][self.site] == 0, win, 10).astype(np.int32)   # max_range (:209)
+        self.ref_out, self.alt_out = capi.allele_predict_batch(cns.reshape(-1), alt_off, self.alt_len, ref_flat, self.r_off, self.r_len, mr,
+                                                               threads=threads)
+
+    def strings(self):
+        """{(site, group): (ref, alt) or (None, None)}"""
+        pred = {}
+        ref_txt = self.ref_bytes.tobytes().decode()
+        cns = self.cns
+        for k in range(len(self.site)):
+            s, g = int(self.site[k]), int(self.grp[k])
+            if self.ref_out[k] < 0:
                 pred[(s, g)] = (None, None)
             else:
-                b0 = int(r_off[k])
-                alt = BASES[cns[s, g, :alt_len[k]]].tobytes().decode()
-                pred[(s, g)] = (ref_txt[b0:b0 + min(int(ro[k]), int(r_len[k]))], alt[:int(ao[k])])
-    res = []
-    for ci in range(len(chunks)):
+                b0 = int(self.r_off[k])
+                alt = BASES[cns[s, g, :self.alt_len[k]]].tobytes().decode()
+                pred[(s, g)] = (ref_txt[b0:b0 + min(int(self.ref_out[k]), int(self.r_len[k]))], alt[:int(self.alt_out[k])])
+        return pred
+
+
+def per_chunk_calls(meta, pred, n_chunks, haploid):
+    """-> per chunk (site indices, pos list, alleles list, phase list) of the kept sites, in key order."""
+    okmask = kept_sites(meta, haploid)
+    groups = (2,) if haploid else (0, 1, 2)
+    out = []
+    for ci in range(n_chunks):
         sel = np.nonzero((meta["chunk"] == ci) & okmask)[0]
-        if len(sel) == 0:
-            res.append(([], [], []) if haploid else ([], [], [], [], [], []))       # generate_indel_pileups.py:363-364
-            continue
         pos = [int(p) for p in meta["pos"][sel]]
         alleles, phase = [], []
         for s in sel:
@@ -136,6 +166,20 @@ def candidates_for_chunks(ctx, rs, dct, chunks, bed=None, haploid=False):
             alleles.append(trip[0] if haploid else trip)
             ph = int(meta["phase"][s])
             phase.append(None if ph == -1 else ph)                              # imputed site whose first hap0 read has no HP tag (:355)
+        out.append((sel, pos, alleles, phase))
+    return out
+
+
+def candidates_for_chunks(ctx, rs, dct, chunks, bed=None, haploid=False):
+    """Scan + build for a list of chunk dicts of one contig; -> per-chunk reference-shaped tuples
+    (diploid: 6-tuple of generate_indel_pileups.py:370; haploid: 3-tuple of generate_indel_pileups_haploid.py:277)."""
+    meta, tensors, cns = scan_build(ctx, rs, dct, chunks, bed, haploid)
+    pred = AllelePredictions(rs, dct, meta, cns, haploid).strings()
+    res = []
+    for sel, pos, alleles, phase in per_chunk_calls(meta, pred, len(chunks), haploid):
+        if len(sel) == 0:
+            res.append(([], [], []) if haploid else ([], [], [], [], [], []))       # generate_indel_pileups.py:363-364
+            continue
         x = tensors[sel].astype(np.float64)                                  # float32 values in a float64 container (:69-71)
         res.append((pos, x[:, 2], alleles) if haploid else (pos, x[:, 0], x[:, 1], x[:, 2], alleles, phase))
     return res

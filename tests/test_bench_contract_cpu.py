@@ -1,4 +1,5 @@
-"""CPU: the reference arm of bench.py (`--impl reference`: the oracle port on the host cores) prints ONE JSON line that carries the
+"""CPU: the reference arm of bench.py (`--impl reference`: the unmodified reference workers from oracle/_ref when built, else the
+oracle port, on the host cores) prints ONE JSON line that carries the
 contract's keys, on a small contig so that it runs in seconds here."""
 import json
 import os
@@ -18,7 +19,8 @@ def test_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"].startswith("candidate sites/sec") and d["unit"] == "sites/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import build_ref
+    assert d["cpu_baseline"]["kind"] == ("reference" if build_ref.built() else "port") and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
