@@ -785,7 +785,7 @@ def measure(kind, args, rank, world, local, dist, with_cpu=True, pipelined_ok=Tr
             out["roofline_indel_scan"]["frac"] = out["roofline_indel_scan"]["achieved"] / hbm
 
     # ---- untimed: what the timed step produced against the oracle on sampled chunks, and the CPU baseline
-    if with_cpu and world == 1:
+    if with_cpu and world == 1 and os.environ.get("NC_BENCH_NO_CPU") != "1":       # NC_BENCH_NO_CPU=1: profiler runs
         cores = os.cpu_count() or 1
         try:
             pool = make_pool(rs, cores, with_indel=do_indel)

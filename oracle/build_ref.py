@@ -1,8 +1,9 @@
 """ORACLE / TEST INFRASTRUCTURE ONLY — recipe that makes `oracle/_ref/` from the reference where it lies.
 
 The reference (WGLab/NanoCaller) is pure Python, so "compiling it from its own sources" means byte-compiling the modules of
-the hot path, unchanged, from /root/reference into sourceless `.pyc` files under oracle/_ref/nanocaller_src/ (git-ignored, not
-gpurun-ignored: the directory travels to the GPU box like a built .so; /root/reference itself does not exist there).  The
+the hot path, unchanged, from /root/reference into marshalled code objects `<module>.refbin` under oracle/_ref/nanocaller_src/
+(git-ignored, not gpurun-ignored: the directory travels to the GPU box like a built .so; /root/reference itself does not exist
+there; `.pyc` files do not travel, hence the own suffix and the small loader in `activate`).  The
 released weights the workers look up next to their own module file (snpCaller.py:36-40, indelCaller.py:26-31) are copied as
 data.  Nothing here is product code, and no reference source text enters the repository.
 
@@ -11,8 +12,10 @@ data.  Nothing here is product code, and no reference source text enters the rep
 Used by: bench.py --impl reference (the CPU arm runs `snpCaller.caller` / `indelCaller.indel_run` — the reference's own worker
 functions — over oracle/shim), tests that compare against the reference itself.
 """
+import importlib.abc
+import importlib.util
+import marshal
 import os
-import py_compile
 import shutil
 import sys
 
@@ -29,8 +32,11 @@ def available():
     return os.path.isdir(os.path.join(REF, "nanocaller_src"))
 
 
+SUFFIX = ".refbin"
+
+
 def built():
-    return os.path.exists(os.path.join(OUT, "nanocaller_src", "generate_SNP_pileups.pyc"))
+    return os.path.exists(os.path.join(OUT, "nanocaller_src", "generate_SNP_pileups" + SUFFIX))
 
 
 def build(verbose=False):
@@ -42,14 +48,18 @@ def build(verbose=False):
     os.makedirs(dst, exist_ok=True)
     for m in MODULES:
         p = os.path.join(src, m + ".py")
-        c = os.path.join(dst, m + ".pyc")
+        c = os.path.join(dst, m + SUFFIX)
         if not os.path.exists(p):
             if m == "__init__":
-                open(os.path.join(dst, "__init__.py"), "w").close()       # namespace marker only
-                continue
+                continue                                                  # the package object is made by the loader
             raise FileNotFoundError(p)
         if not os.path.exists(c) or os.path.getmtime(c) < os.path.getmtime(p):
-            py_compile.compile(p, cfile=c, doraise=True, invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+            with open(p, "rb") as f:
+                code = compile(f.read(), "nanocaller_src/%s.py" % m, "exec", dont_inherit=True)
+            with open(c + ".tmp", "wb") as f:
+                f.write(("%d.%d\n" % sys.version_info[:2]).encode())      # marshal is version-bound: same image here and on the GPU box
+                marshal.dump(code, f)
+            os.replace(c + ".tmp", c)
             if verbose:
                 print("compiled", p, "->", c)
     # released weights (data): every model file the two workers can name
@@ -70,13 +80,46 @@ def build(verbose=False):
     return built()
 
 
+class _RefFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Imports `nanocaller_src` and its modules from the marshalled code objects of oracle/_ref."""
+    PKG = "nanocaller_src"
+
+    def find_spec(self, name, path=None, target=None):
+        d = os.path.join(OUT, self.PKG)
+        if name == self.PKG:
+            return importlib.util.spec_from_loader(name, self, origin=d, is_package=True)
+        if name.startswith(self.PKG + ".") and os.path.exists(os.path.join(d, name.split(".", 1)[1] + SUFFIX)):
+            return importlib.util.spec_from_loader(name, self, origin=os.path.join(d, name.split(".", 1)[1] + SUFFIX))
+        return None
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        d = os.path.join(OUT, self.PKG)
+        if module.__name__ == self.PKG:
+            module.__path__ = [d]
+            module.__file__ = os.path.join(d, "__init__.py")
+            return
+        short = module.__name__.split(".", 1)[1]
+        module.__file__ = os.path.join(d, short + ".py")          # the workers look their weights up next to __file__ (snpCaller.py:38)
+        with open(os.path.join(d, short + SUFFIX), "rb") as f:
+            ver = f.readline().decode().strip()
+            if ver != "%d.%d" % sys.version_info[:2]:
+                raise ImportError("oracle/_ref was built with Python %s" % ver)
+            code = marshal.load(f)
+        exec(code, module.__dict__)
+
+
 def activate():
-    """Put the shims and the byte-compiled reference on sys.path (shims first: `import pysam` must find oracle/shim/pysam.py)."""
+    """Make `import pysam / intervaltree / parasail / tensorflow` find the stand-ins of oracle/shim and `import nanocaller_src`
+    the byte-compiled reference; put the `muscle` stand-in on PATH."""
     shim = os.path.join(HERE, "shim")
-    for p in (OUT, shim):
-        if p in sys.path:
-            sys.path.remove(p)
-        sys.path.insert(0, p)
+    if shim in sys.path:
+        sys.path.remove(shim)
+    sys.path.insert(0, shim)
+    if not any(isinstance(f, _RefFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _RefFinder())
     os.environ["PATH"] = os.path.join(shim, "bin") + os.pathsep + os.environ.get("PATH", "")      # the `muscle` stand-in
 
 
