@@ -45,7 +45,7 @@ DCT = dict(threshold=[0.4, 0.6], mincov=4, maxcov=160, min_allele_freq=0.15, min
 IDCT = dict(mincov=4, maxcov=160, seq="ont", del_t=0.6, ins_t=0.4, impute_indel_phase=False, supplementary=False,
             win_size=40, small_win_size=4, exclude_bed=None)      # ONT preset, NanoCaller:66
 MODEL = "ONT-HG002"
-INDEL_CNN_ON_TENSOR_CORES = False      # flipped when Indel_model runs on tcgen05 (impl 0); until then impl 0 falls through to the fp32 kernels
+INDEL_CNN_ON_TENSOR_CORES = True       # Indel_model / haploid_Indel_model run on tcgen05 (nc_cnn_tc_indel.cuh) with impl 0
 WORKLOADS = {
     "snps": dict(tag="configs[1]", chrom="chr20", length=60_000_000, seed=20, synth={}),
     "all": dict(tag="configs[2]", chrom="chr1", length=250_000_000, seed=1, synth=dict(indel_every=2000, indel_maxlen=50)),

@@ -12,6 +12,7 @@
 #include "nc_pileup.cuh"
 #include "nc_cnn.cuh"
 #include "nc_cnn_tc.cuh"
+#include "nc_cnn_tc_indel.cuh"
 #include "nc_indel.cuh"
 
 using namespace nc;
@@ -196,7 +197,7 @@ int model_init(nc_ctx* c, Model& M, int kind, const float* blob, size_t n_floats
         if (rc) return rc;
     }
     NC_CUDA(nc_stream_wait(c));     // `tab` is pageable host memory
-    rc = tc_model_prepare(c->stream, M.tc, kind, blob, n_floats, &c->err);
+    rc = kind < 2 ? tc_model_prepare(c->stream, M.tc, kind, blob, n_floats, &c->err) : tci_model_prepare(c->stream, M.tc, kind, blob, n_floats, &c->err);
     if (rc) return rc;
     M.loaded = true;
     return NC_OK;
@@ -323,9 +324,15 @@ int cnn_forward(nc_ctx* c, Model& M, int impl, int in_mode, const void* in_dev, 
     if (impl == 1)
         return cnn_forward_f32(c, M, in_mode, in_dev, in_site_stride, n, meta, ref4, scale_f, scale_d, out_full, probs);
     if (impl != 0) return fail(c, NC_EINVAL, "impl must be 0 (tcgen05) or 1 (fp32 CUDA cores)");
-    if (!M.tc.ready)    // no tensor-core image for this model kind (indel models): the fp32 kernels are the GPU implementation
-        return cnn_forward_f32(c, M, in_mode, in_dev, in_site_stride, n, meta, ref4, scale_f, scale_d, out_full, probs);
+    if (!M.tc.ready) return fail(c, NC_ESTATE, "no tensor-core operand image for model kind %d", M.kind);
     uint64_t launches = 0;
+    if (M.kind >= 2) {
+        if (in_mode != 0) return fail(c, NC_EINVAL, "the indel models read fp32 tensors");
+        int rci = tci_forward(c->stream, M.tc, reinterpret_cast<const float*>(in_dev), in_site_stride, n, tail_weights(M), out_full, c->sm_count,
+                              &launches, &c->err, 0);
+        c->launches += launches;
+        return rci;
+    }
     int rc = tc_forward_ex(c->stream, M.tc, in_mode, in_dev, in_site_stride, n, meta, ref4, scale_f, scale_d, tail_weights(M),
                            out_full, probs, c->sm_count, &launches, &c->err, 0, c->ev[12]);
     c->launches += launches;
@@ -818,7 +825,7 @@ int nc_indel_model_forward(nc_ctx* c, const float* x, int64_t n, int haploid, in
     if (rc) return rc;
     NC_CUDA(cudaMemcpyAsync(out, c->ws_out.p, (size_t)n * nout * 4, cudaMemcpyDeviceToHost, c->stream));
     NC_CUDA(nc_stream_wait(c));
-    return NC_OK;
+    return impl == 0 ? tc_check(c, M) : NC_OK;
 }
 
 int nc_snp_device_buffers(nc_ctx* c, void** mat_dev, void** meta_dev, void** probs_dev, int64_t* n_sites) {
@@ -1418,6 +1425,27 @@ int nc_debug_tc_trunk(nc_ctx* c, const float* x, int64_t n, int haploid, int sta
     if (rc) return rc;
     const size_t have = stage == 1 ? (size_t)((n + 2) / 3) * tcg::C2_GROUP_BYTES : (size_t)((n + 127) / 128) * tcg::C3_TILE_BYTES;
     if (raw_bytes < have) return fail(c, NC_EINVAL, "nc_debug_tc_trunk: output buffer too small (%zu < %zu)", raw_bytes, have);
+    NC_CUDA(cudaMemcpyAsync(raw, stage == 1 ? M.tc.c2.p : M.tc.c3.p, have, cudaMemcpyDeviceToHost, c->stream));
+    NC_CUDA(nc_stream_wait(c));
+    return tc_check(c, M);
+}
+
+// Indel tensor-core trunk up to `stage` (1: c2 slabs after conv1 + conv2, 2: c3 after conv3) on fp32 inputs [n][H][128][2]; returns the raw
+// fp16 hi/lo activation image (layouts in nc_cnn_tc_indel.cuh).  n <= 32768 (one batch).
+int nc_debug_tci_trunk(nc_ctx* c, const float* x, int64_t n, int haploid, int stage, void* raw, size_t raw_bytes) {
+    if (!c || !x || !raw || n <= 0 || n > 32768 || (stage != 1 && stage != 2)) return fail(c, NC_EINVAL, "nc_debug_tci_trunk: bad argument");
+    NC_CUDA(cudaSetDevice(c->device));
+    Model& M = c->indel[haploid ? 1 : 0];
+    if (!M.loaded || !M.tc.ready) return fail(c, NC_ESTATE, "nc_debug_tci_trunk: no tensor-core indel model loaded");
+    const int64_t site = (int64_t)M.Hin * M.Win * M.Cin;
+    NC_CUDA(c->ws_x.reserve((size_t)n * site * 4));
+    NC_CUDA(cudaMemcpyAsync(c->ws_x.p, x, (size_t)n * site * 4, cudaMemcpyHostToDevice, c->stream));
+    uint64_t launches = 0;
+    int rc = tci_forward(c->stream, M.tc, c->ws_x.as<float>(), site, n, tail_weights(M), nullptr, c->sm_count, &launches, &c->err, stage);
+    c->launches += launches;
+    if (rc) return rc;
+    const size_t have = stage == 1 ? (size_t)n * tci::n_slabs(M.Hin) * tci::SLAB_BYTES : (size_t)n * tci::n_pos(M.Hin) * tci::C3_POS_BYTES;
+    if (raw_bytes < have) return fail(c, NC_EINVAL, "nc_debug_tci_trunk: output buffer too small (%zu < %zu)", raw_bytes, have);
     NC_CUDA(cudaMemcpyAsync(raw, stage == 1 ? M.tc.c2.p : M.tc.c3.p, have, cudaMemcpyDeviceToHost, c->stream));
     NC_CUDA(nc_stream_wait(c));
     return tc_check(c, M);

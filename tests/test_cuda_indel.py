@@ -106,3 +106,21 @@ def test_gpu_indel_path_recovers_the_truth_indels():
     lines = indel_caller.call_chunks(idct, chunks, it)
     found, right = score_indel_calls(lines, truth)
     assert len(truth) > 200 and found / len(truth) > 0.85 and right / found > 0.95 and len(lines) < 1.4 * len(truth), (found, right, len(lines), len(truth))
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_device_resident_indel_forward_matches_oracle(impl):
+    """nc_indel_forward: the CNN on the tensors where nc_indel_build left them (no host round trip) vs the fp32 oracle on the fetched tensors."""
+    from nanocaller_b200.host import indel_pileups, snp_pileups, weights as W
+    from oracle import cnn_oracle
+    rs, dct, chunks, g = load_indel_case("indel_ont")
+    ctx = snp_pileups.context(0)
+    meta, tensors, cns = indel_pileups.scan_build(ctx, rs, dct, chunks, want_tensors=True)
+    w, _ = W.load_model("indel", "ONT-HG002")
+    ctx.load_indel_weights(W.pack_indel_blob(w), False)
+    got = ctx.indel_forward(impl=impl)
+    keep = indel_pileups.kept_sites(meta, False)
+    want = cnn_oracle.indel_model(w, tensors.reshape(len(meta), 15, 128, 2))
+    assert keep.sum() > 10 and got.shape == (len(meta), 4)
+    assert float(np.abs(got[keep] - np.asarray(want)[keep]).max()) < 1e-4
+    assert float(np.abs(got - np.asarray(want)).max()) < 1e-4           # sites msa() rejected carry zero tensors: still a defined input
