@@ -523,7 +523,7 @@ def measure(kind, args, rank, world, local, dist, with_cpu=True, pipelined_ok=Tr
     sampler = ClockSampler(local) if rank == 0 else None
     ctx.event_record(0)
     acc = {"decode_ms": 0.0, "scan_ms": 0.0, "tensor_ms": 0.0, "cnn_ms": 0.0, "cnn_a_ms": 0.0}
-    iacc = {"scan_ms": 0.0, "reads_ms": 0.0, "align_ms": 0.0, "msa_ms": 0.0, "cnn_ms": 0.0}
+    iacc = {"scan_ms": 0.0, "reads_ms": 0.0, "align_ms": 0.0, "msa_ms": 0.0, "allele_ms": 0.0, "cnn_ms": 0.0}
     itm = None
     for _ in range(args.steps):
         n_sites, n_isites, _ = step_resident()
@@ -608,7 +608,7 @@ def measure(kind, args, rank, world, local, dist, with_cpu=True, pipelined_ok=Tr
         b = fetch_results(c, n, ni, tag, got)
         if do_indel and ni:
             t = time.perf_counter()
-            indel_pileups.AllelePredictions(rs, IDCT, got[0], got[2], False)      # I4 on host threads (nc_allele_predict_batch)
+            indel_pileups.AllelePredictions(rs, IDCT, got[0], got[2], False, device_lengths=c.indel_fetch_alleles())   # I4 ran on the GPU after msa; this gathers the windows
             allele_s[0] += time.perf_counter() - t
         return n + ni, b
 
@@ -758,18 +758,19 @@ def measure(kind, args, rank, world, local, dist, with_cpu=True, pipelined_ok=Tr
     if do_indel:
         iph = {k: v / args.steps for k, v in iacc.items()}
         out["indel_phase_ms"] = iph
-        out["e2e"]["allele_predict_host_ms"] = allele_ms
+        out["e2e"]["allele_gather_host_ms"] = allele_ms
         n_ent = int(itm["n_entries"]) if itm else 0
         wa = 161
         cells = n_ent * wa * wa                                 # full DP table per (slice, reference window) pair
         out["roofline_indel"] = {
-            "kernel": "indel build (indel_site_reads + indel_align + indel_msa)", "bound": "hbm", "peak": hbm, "unit": "GB/s",
+            "kernel": "indel build (indel_site_reads + indel_align + indel_msa + indel_allele)", "bound": "hbm", "peak": hbm, "unit": "GB/s",
             "algorithmic_bytes": int(itm["build_bytes"]) if itm else None,
-            "ms_per_launch_group": iph["reads_ms"] + iph["align_ms"] + iph["msa_ms"],
-            "achieved": (itm["build_bytes"] / ((iph["reads_ms"] + iph["align_ms"] + iph["msa_ms"]) * 1e-3) / 1e9) if itm else None,
+            "ms_per_launch_group": iph["reads_ms"] + iph["align_ms"] + iph["msa_ms"] + iph["allele_ms"],
+            "achieved": (itm["build_bytes"] / ((iph["reads_ms"] + iph["align_ms"] + iph["msa_ms"] + iph["allele_ms"]) * 1e-3) / 1e9) if itm else None,
             "traffic": (tr["indel_build_dram_bytes_per_site"] * n_isites) if "indel_build_dram_bytes_per_site" in tr else None,
             "per_kernel_ms": {"indel_scan (depth, events, windows, decide, greedy)": iph["scan_ms"], "indel_site_reads": iph["reads_ms"],
-                              "indel_align": iph["align_ms"], "indel_msa": iph["msa_ms"], "indel CNN": iph["cnn_ms"]},
+                              "indel_align": iph["align_ms"], "indel_msa": iph["msa_ms"], "indel_allele (consensus x reference NW + allele walk)": iph["allele_ms"],
+                              "indel CNN": iph["cnn_ms"]},
             "aligned_slices": n_ent, "dp_cell_updates_per_s": cells / (iph["align_ms"] * 1e-3) if iph["align_ms"] > 0 else None,
             "note": "the alignment is integer dynamic programming (161 x 161 cells per slice): neither HBM nor the tensor pipe bounds it; "
                     "bytes = slices + reference windows read, tensors + consensus written"}

@@ -237,6 +237,12 @@ int nc_indel_build(nc_ctx* ctx, const NcIndelParams* params, const NcChunk* chun
                    const NcIndelVariant* sites, int64_t n_sites);
 int nc_indel_fetch(nc_ctx* ctx, NcIndelSiteMeta* meta, float* tensors, uint8_t* cns);
 
+/* allele_prediction (generate_indel_pileups.py:77-127) of the last build, computed on the device right after msa: int32
+ * [n_sites][3][2] = (length of the reference allele string ref_seq[:r], length of the alternative allele string alt[:a]) per read
+ * group, -1 / -1 where the reference returns (None, None) or the site was not kept (:342-348), -2 / -2 if an item did not fit the
+ * device scratch (the caller then uses nc_allele_predict_batch for it).  Same alignment as nc_nw_trace. */
+int nc_indel_fetch_alleles(nc_ctx* ctx, int32_t* out);
+
 /* Tensors of `count` consecutive sites of the last build starting at site `first`: float32 [count][3][5][128][2]. */
 int nc_indel_fetch_range(nc_ctx* ctx, int64_t first, int64_t count, float* tensors);
 
@@ -255,7 +261,8 @@ typedef struct NcIndelTimings {
     float    align_ms;       /* I3: slice x reference-window alignment (indel_align_kernel)                    */
     float    msa_ms;         /* I3: column merge, frequencies, tensors, consensus (indel_msa_kernel)           */
     float    cnn_ms;         /* M3 / M4: nc_indel_forward                                                      */
-    float    reserved[3];
+    float    allele_ms;      /* I4: consensus x reference alignment + allele lengths (indel_allele_kernel)     */
+    float    reserved[2];
     uint64_t n_sites;        /* key positions of the last build                                               */
     uint64_t n_entries;      /* (site, read group member) slices aligned by the last build                    */
     uint64_t scan_bytes;     /* algorithmic bytes of the scan: aligned rows + CIGARs once, 6 B of depth + 1 B flag per column */

@@ -78,11 +78,11 @@ struct nc_ctx {
     // timings
     cudaEvent_t ev_block = nullptr;   // blocking-sync event (NC_BLOCKING_SYNC=1), else spin on the stream
     cudaEvent_t ev[13] = {};     // 0-7 phase timings, 8-11 user slots (nc_event_record), 12 end of the conv1/conv2 kernel
-    cudaEvent_t evi[8] = {};     // indel path: 0-1 scan, 2-5 build (start, slices, align, msa), 6-7 CNN
+    cudaEvent_t evi[9] = {};     // indel path: 0-1 scan, 2-5 build (start, slices, align, msa), 6-7 CNN, 8 allele prediction (after msa)
     NcIndelTimings tmi = {};
     bool tmi_scan = false, tmi_build = false, tmi_cnn = false, have_iprobs = false;
     int build_haploid = 0;
-    DevBuf d_iprobs;
+    DevBuf d_iprobs, d_ialleles, d_allele_dirs, d_allele_ops;
     NcTimings tm = {};
     bool tm_decode = false, tm_scan = false, tm_cnn = false, tm_cnn_a = false;
 };
@@ -415,7 +415,7 @@ void nc_destroy(nc_ctx* c) {
     c->pin.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->evi) if (e) cudaEventDestroy(e);
-    c->d_iprobs.release();
+    c->d_iprobs.release(); c->d_ialleles.release(); c->d_allele_dirs.release(); c->d_allele_ops.release();
     if (c->ev_block) cudaEventDestroy(c->ev_block);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1098,15 +1098,39 @@ int nc_indel_build(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int
     indel_site_reads_kernel<true><<<sg, 128, 0, c->stream>>>(sa); NC_LAUNCH_CHECK();
     NC_CUDA(cudaEventRecord(c->evi[3], c->stream));
     if (n_entries > 0) {
-        const int smem = kAlignWarps * kRowsMax * 32 * 4;
+        // direction rows 1..n, n <= window_after; strips of 6 columns cover reference windows up to 192 columns (ONT: 161), 9 up to 288
+        const int rows = P->window_after + 2;
+        const int smem = kAlignWarps * align_smem_per_warp(rows);
+        const bool narrow = P->window_after + 1 <= 192;
         // function attributes are per device and one process may open contexts on several: set it on every call (cheap, no sync)
-        NC_CUDA(cudaFuncSetAttribute(indel_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_entries, kAlignWarps), (int64_t)c->sm_count * 12);
-        indel_align_kernel<<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries); NC_LAUNCH_CHECK();
+        if (narrow) NC_CUDA(cudaFuncSetAttribute(indel_align_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else NC_CUDA(cudaFuncSetAttribute(indel_align_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_entries, kAlignWarps), (int64_t)c->sm_count * 16);
+        if (narrow) indel_align_kernel<6><<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries, rows);
+        else indel_align_kernel<9><<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries, rows);
+        NC_LAUNCH_CHECK();
     }
     NC_CUDA(cudaEventRecord(c->evi[4], c->stream));
     indel_msa_kernel<<<(unsigned)n_sites, 96, 0, c->stream>>>(sa); NC_LAUNCH_CHECK();
     NC_CUDA(cudaEventRecord(c->evi[5], c->stream));
+    {
+        // I4: consensus x reference window -> allele lengths (generate_indel_pileups.py:77-127), one warp per (site, group)
+        const bool narrow = P->window_after + 1 <= 192;
+        const int64_t n_warps = std::min<int64_t>(n_sites * 3, (int64_t)c->sm_count * 16);
+        const int rows_cap = NC_INDEL_CNS_MAX + 1;
+        NC_CUDA(c->d_ialleles.reserve((size_t)n_sites * 3 * 2 * sizeof(int32_t)));
+        NC_CUDA(c->d_allele_dirs.reserve((size_t)n_warps * rows_cap * 32 * (narrow ? 4 : 8)));
+        NC_CUDA(c->d_allele_ops.reserve((size_t)n_warps * (NC_INDEL_CNS_MAX + 272)));
+        AlleleArgs aa = {};
+        aa.n_sites = n_sites; aa.sites = sa.sites; aa.meta = sa.meta; aa.cns = sa.cns; aa.cmax = sa.cmax; aa.ref = sa.ref; aa.ref_start = c->ref_start;
+        aa.win = P->win_size; aa.haploid = P->haploid; aa.go = 9; aa.ge = 1; aa.match = 20; aa.mismatch = -10;     // parasail call of :79-80
+        aa.scratch = c->d_allele_dirs.p; aa.rows_cap = rows_cap; aa.ops_scratch = c->d_allele_ops.as<uint8_t>(); aa.out = c->d_ialleles.as<int32_t>();
+        const unsigned gb = (unsigned)div_up(n_warps * 32, 128);
+        if (narrow) indel_allele_kernel<6, uint32_t><<<gb, 128, 0, c->stream>>>(aa);
+        else indel_allele_kernel<9, uint64_t><<<gb, 128, 0, c->stream>>>(aa);
+        NC_LAUNCH_CHECK();
+    }
+    NC_CUDA(cudaEventRecord(c->evi[8], c->stream));
     c->tmi_build = true; c->tmi.n_entries = (uint64_t)n_entries;
     // per aligned slice: the query slice and the reference window (one byte per base); per site: 3 x [5][128][2] fp32 tensors,
     // the consensus strings and the site record
@@ -1125,6 +1149,18 @@ int nc_indel_fetch(nc_ctx* c, NcIndelSiteMeta* meta, float* tensors, uint8_t* cn
         if (meta) NC_CUDA(cudaMemcpyAsync(meta, c->d_imeta.p, n * sizeof(NcIndelSiteMeta), cudaMemcpyDeviceToHost, c->stream));
         if (tensors) NC_CUDA(cudaMemcpyAsync(tensors, c->d_itensors.p, n * 3 * 1280 * 4, cudaMemcpyDeviceToHost, c->stream));
         if (cns) NC_CUDA(cudaMemcpyAsync(cns, c->d_icns.p, n * 3 * NC_INDEL_CNS_MAX, cudaMemcpyDeviceToHost, c->stream));
+    }
+    NC_CUDA(nc_stream_wait(c));
+    return NC_OK;
+}
+
+int nc_indel_fetch_alleles(nc_ctx* c, int32_t* out) {
+    if (!c) return NC_EINVAL;
+    if (!c->indel_built) return fail(c, NC_ESTATE, "nc_indel_fetch_alleles before nc_indel_build");
+    NC_CUDA(cudaSetDevice(c->device));
+    if (c->n_isites) {
+        if (!out) return fail(c, NC_EINVAL, "nc_indel_fetch_alleles: null output");
+        NC_CUDA(cudaMemcpyAsync(out, c->d_ialleles.p, (size_t)c->n_isites * 3 * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     }
     NC_CUDA(nc_stream_wait(c));
     return NC_OK;
@@ -1185,6 +1221,7 @@ int nc_get_indel_timings(nc_ctx* c, NcIndelTimings* out) {
         NC_CUDA(cudaEventElapsedTime(&c->tmi.reads_ms, c->evi[2], c->evi[3]));
         NC_CUDA(cudaEventElapsedTime(&c->tmi.align_ms, c->evi[3], c->evi[4]));
         NC_CUDA(cudaEventElapsedTime(&c->tmi.msa_ms, c->evi[4], c->evi[5]));
+        NC_CUDA(cudaEventElapsedTime(&c->tmi.allele_ms, c->evi[5], c->evi[8]));
     }
     if (c->tmi_cnn) { NC_CUDA(cudaEventElapsedTime(&c->tmi.cnn_ms, c->evi[6], c->evi[7])); }
     *out = c->tmi;

@@ -597,15 +597,26 @@ __global__ void __launch_bounds__(128) indel_site_reads_kernel(const SiteArgs a)
 
 // Star alignment step 1: global linear-gap NW of one read slice against the reference window, one warp per entry.
 // match +2, mismatch -4, gap -3; direction DIAG if the diagonal attains the max, else UP (read base unaligned), else LEFT.
-// Lane l owns reference columns [l*CW, (l+1)*CW); rows are processed as a skewed wavefront (lane l works on row t-l).
+// Lane l owns reference columns [l*CW, (l+1)*CW) (CW = 6 for windows up to 192 columns, 9 up to 288); rows are processed as a
+// skewed wavefront (lane l works on row t-l).  Everything the wavefront and the traceback touch sits in shared memory — the
+// read slice, the direction words, the aligned codes and the insertion tables — and leaves with coalesced stores at the end:
+// the first version read the slice back from global memory in every step and ran the traceback (lane 0, ~n + m dependent steps)
+// on read-modify-writes to global memory, 357 ms for configs[2]'s 4.1 M slices.
 constexpr int kAlignWarps = 2;
-constexpr int kCW = 9;                      // 32 * 9 = 288 >= 261 reference columns
 constexpr int kRowsMax = 264;
+constexpr int kAlignAux = 4 * 272 + 2 * 2 * 272;        // per warp: slice, aligned codes (bytes); insertion length / first (u16)
+__host__ __device__ constexpr int align_smem_per_warp(int rows) { return rows * 32 * 4 + kAlignAux; }
 
-__global__ void __launch_bounds__(kAlignWarps * 32) indel_align_kernel(const SiteArgs a, int64_t n_entries) {
-    extern __shared__ uint32_t s_dir_all[];                      // per warp [kRowsMax][32] direction words (2 bits per column)
+template <int CW>
+__global__ void __launch_bounds__(kAlignWarps * 32) indel_align_kernel(const SiteArgs a, int64_t n_entries, int rows) {
+    extern __shared__ __align__(16) uint8_t s_align_all[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint32_t* s_dir = s_dir_all + (size_t)wib * kRowsMax * 32;
+    uint8_t* s_base = s_align_all + (size_t)wib * align_smem_per_warp(rows);
+    uint32_t* s_dir = reinterpret_cast<uint32_t*>(s_base);       // [rows][32] direction words (2 bits per column of the lane's strip)
+    uint8_t* s_slice = s_base + (size_t)rows * 128;               // [272]
+    uint8_t* s_ac = s_slice + 272;                                // [272] (+ 544 spare)
+    uint16_t* s_il = reinterpret_cast<uint16_t*>(s_slice + 4 * 272);
+    uint16_t* s_if = s_il + 272;
     const uint32_t full = 0xffffffffu;
     for (int64_t e = (int64_t)blockIdx.x * kAlignWarps + wib; e < n_entries; e += (int64_t)gridDim.x * kAlignWarps) {
         int64_t s;
@@ -620,39 +631,40 @@ __global__ void __launch_bounds__(kAlignWarps * 32) indel_align_kernel(const Sit
         uint8_t* o_ac = a.e_acode + e * a.mmax;
         uint16_t* o_il = a.e_inslen + e * (a.mmax + 1);
         uint16_t* o_if = a.e_insfirst + e * (a.mmax + 1);
-        // slice codes -> global (also read back as the DP's read sequence)
+        // slice codes -> shared (the DP's read sequence) and global (the msa kernel reads inserted bases from it)
         for (int i = lane; i < n; i += 32) {
             const int32_t q = q0 + i;
             const uint32_t b = __ldg(sq + (q >> 1));
             const uint32_t bn = (q & 1) ? (b & 15u) : (b >> 4);
-            o_slice[i] = (uint8_t)((kNibToCode >> (4 * bn)) & 15u);
+            const uint8_t c = (uint8_t)((kNibToCode >> (4 * bn)) & 15u);
+            s_slice[i] = c; o_slice[i] = c;
         }
-        for (int j = lane; j <= m; j += 32) { o_il[j] = 0; o_if[j] = 0; }
+        for (int j = lane; j <= m; j += 32) { s_il[j] = 0; s_if[j] = 0; }
         __syncwarp();
         // reference codes of the lane's strip
-        int refc[kCW];
+        int refc[CW];
 #pragma unroll
-        for (int k = 0; k < kCW; k++) {
-            const int j = lane * kCW + k;         // 0-based reference column
+        for (int k = 0; k < CW; k++) {
+            const int j = lane * CW + k;         // 0-based reference column
             refc[k] = j < m ? ref_code_of(__ldg(a.ref + ((int64_t)p + j - a.ref_start))) : 7;
         }
         // H of the previous row for the strip: hp[k] = H[i-1][j0+k+1], hleft = H[i-1][j0] (column left of the strip)
-        int32_t hp[kCW];
+        int32_t hp[CW];
 #pragma unroll
-        for (int k = 0; k < kCW; k++) hp[k] = -3 * (lane * kCW + k + 1);
-        int32_t h_left_prev = -3 * (lane * kCW);              // H[i-1][j0]
+        for (int k = 0; k < CW; k++) hp[k] = -3 * (lane * CW + k + 1);
+        int32_t h_left_prev = -3 * (lane * CW);               // H[i-1][j0]
         int32_t last_out = 0;                                   // H[i][last column of strip] of the row finished in the previous step
         for (int t = 1; t <= n + 31; t++) {
             // value of the left neighbour's strip end for the row this lane works on now: lane-1 finished row i at step t-1
             const int32_t from_left = __shfl_up_sync(full, last_out, 1);
             const int i = t - lane;
             if (i >= 1 && i <= n) {
-                const int rb = o_slice[i - 1];
+                const int rb = s_slice[i - 1];
                 const int32_t h_left_cur = lane == 0 ? -3 * i : from_left;        // H[i][j0]
                 int32_t diag_in = h_left_prev, left = h_left_cur;
                 uint32_t dw = 0;
 #pragma unroll
-                for (int k = 0; k < kCW; k++) {
+                for (int k = 0; k < CW; k++) {
                     const int32_t sc = (refc[k] == rb && rb < 4) ? 2 : -4;
                     const int32_t dg = diag_in + sc, up = hp[k] - 3, lf = left - 3;
                     const int32_t best = max(dg, max(up, lf));
@@ -668,19 +680,22 @@ __global__ void __launch_bounds__(kAlignWarps * 32) indel_align_kernel(const Sit
             }
         }
         __syncwarp();
-        // traceback (lane 0) from (n, m)
+        // traceback (lane 0) from (n, m), in shared memory
         if (lane == 0) {
             int i = n, j = m;
             while (i > 0 || j > 0) {
                 uint32_t d;
                 if (i == 0) d = 2u; else if (j == 0) d = 1u;
-                else d = (s_dir[i * 32 + (j - 1) / kCW] >> (2 * ((j - 1) % kCW))) & 3u;
-                if (d == 0u) { o_ac[j - 1] = o_slice[i - 1]; i--; j--; }
-                else if (d == 1u) { o_il[j]++; o_if[j] = (uint16_t)(i - 1); i--; }
-                else { o_ac[j - 1] = 5; j--; }
+                else d = (s_dir[i * 32 + (j - 1) / CW] >> (2 * ((j - 1) % CW))) & 3u;
+                if (d == 0u) { s_ac[j - 1] = s_slice[i - 1]; i--; j--; }
+                else if (d == 1u) { s_il[j]++; s_if[j] = (uint16_t)(i - 1); i--; }
+                else { s_ac[j - 1] = 5; j--; }
             }
             a.e_n[e] = n;
         }
+        __syncwarp();
+        for (int j = lane; j < m; j += 32) o_ac[j] = s_ac[j];
+        for (int j = lane; j <= m; j += 32) { o_il[j] = s_il[j]; o_if[j] = s_if[j]; }
         __syncwarp();
     }
 }
@@ -813,6 +828,140 @@ __global__ void __launch_bounds__(96) indel_msa_kernel(const SiteArgs a) {
         if (g == 0) { mt->pos = a.sites[s].key; mt->chunk = a.sites[s].chunk; mt->type = a.sites[s].type; mt->ref_len = m;
                       const bool imputed = a.site_imp && a.site_imp[s] >= 0;      // phase_dict gives None for a read without HP: -1
                       mt->phase = (ok && first_read >= 0) ? ((imputed && __ldg(a.hp + first_read) <= 0) ? -1 : __ldg(a.ps + first_read)) : 0; }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// I4 — allele_prediction (generate_indel_pileups.py:77-127) on the device: global affine alignment of the consensus against the
+// reference window with traceback (the reference calls parasail.nw_trace(alt, ref, 9, 1, matrix 20 / -10), :79; this is the same
+// recurrence and the same tie rules as nc_nw_trace on the host: H prefers DIAG, then F ('I'), then E ('D'); E / F prefer extension),
+// then the reference's walk over the CIGAR.  One warp per (site, read group); lane l owns reference columns [l*CW, (l+1)*CW), rows
+// run as a skewed wavefront; four flag bits per cell go to a per-warp scratch in global memory (L2), the traceback and the walk are
+// sequential on lane 0.  out[(site * 3 + group) * 2] = {ref_out_len, alt_out_len}, -1 / -1 where the reference returns (None, None).
+// ------------------------------------------------------------------------------------------------
+struct AlleleArgs {
+    int64_t n_sites; const NcIndelVariant* sites; const NcIndelSiteMeta* meta; const uint8_t* cns; int32_t cmax;
+    const uint8_t* ref; int64_t ref_start; int32_t win; int32_t haploid;
+    int32_t go, ge, match, mismatch;
+    void* scratch; int32_t rows_cap;           // per warp [rows_cap][32] flag words
+    uint8_t* ops_scratch;                      // per warp [cmax + 272] reversed alignment ops
+    int32_t* out;
+};
+
+template <int CW, typename WordT>
+__global__ void __launch_bounds__(128) indel_allele_kernel(const AlleleArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    WordT* dirs = reinterpret_cast<WordT*>(a.scratch) + warp_global * (int64_t)a.rows_cap * 32;
+    uint8_t* ops = a.ops_scratch + warp_global * (int64_t)(a.cmax + 272);
+    const uint32_t full = 0xffffffffu;
+    const int32_t NEG = -(1 << 28);
+    for (int64_t item = warp_global; item < a.n_sites * 3; item += n_warps) {
+        const int64_t s = item / 3;
+        const int g = (int)(item - s * 3);
+        const NcIndelSiteMeta mt = a.meta[s];
+        const bool kept = a.haploid ? (g == 2 && mt.ok[2] > 0) : (mt.ok[0] > 0 && mt.ok[1] > 0 && mt.ok[2] > 0);
+        if (!kept) { if (lane == 0) { a.out[item * 2] = -1; a.out[item * 2 + 1] = -1; } continue; }
+        const int32_t n = mt.cns_len[g], m = mt.ref_len;
+        const uint8_t* q = a.cns + item * a.cmax;
+        const int64_t p = (int64_t)mt.pos - 1 - a.ref_start;
+        int32_t ref_out = -1, alt_out = -1;
+        if (n + 1 <= a.rows_cap && m <= 32 * CW) {
+            int refc[CW];
+#pragma unroll
+            for (int k = 0; k < CW; k++) { const int j = lane * CW + k; refc[k] = j < m ? ref_code_of(__ldg(a.ref + p + j)) : 7; }
+            // previous row of the strip: H[i-1][j0+k+1], F[i-1][j0+k+1]; row 0: H = E = -go - ge * (j - 1), F = NEG
+            int32_t hp[CW], fp[CW];
+#pragma unroll
+            for (int k = 0; k < CW; k++) { hp[k] = -a.go - a.ge * (lane * CW + k); fp[k] = NEG; }
+            int32_t h_left_prev = lane == 0 ? 0 : -a.go - a.ge * (lane * CW - 1);         // H[i-1][j0]
+            int32_t out_h = 0, out_e = 0;                                                // H / E at the strip's last column of the row just finished
+            for (int t = 1; t <= n + 31; t++) {
+                const int32_t in_h = __shfl_up_sync(full, out_h, 1), in_e = __shfl_up_sync(full, out_e, 1);
+                const int i = t - lane;
+                if (i >= 1 && i <= n) {
+                    const int qb = __ldg(q + i - 1);
+                    const int32_t h_left_cur = lane == 0 ? -a.go - a.ge * (i - 1) : in_h;    // H[i][j0]  (column 0: H = F = -go - ge (i - 1), E = NEG)
+                    int32_t e_left = lane == 0 ? NEG : in_e;                                 // E[i][j0]
+                    int32_t diag_in = h_left_prev, left = h_left_cur;
+                    WordT dw = 0;
+#pragma unroll
+                    for (int k = 0; k < CW; k++) {
+                        const int32_t sc = (refc[k] == qb) ? a.match : a.mismatch;
+                        const int32_t f_ext = fp[k] - a.ge, f = max(f_ext, hp[k] - a.go);
+                        const int32_t e_ext = e_left - a.ge, e = max(e_ext, left - a.go);
+                        const int32_t dg = diag_in + sc;
+                        const int32_t best = max(dg, max(f, e));
+                        const uint32_t fl = (best == dg ? 1u : 0u) | (best == f ? 2u : 0u) | (f == f_ext ? 4u : 0u) | (e == e_ext ? 8u : 0u);
+                        dw |= (WordT)fl << (4 * k);
+                        diag_in = hp[k];
+                        hp[k] = best; fp[k] = f;
+                        left = best; e_left = e;
+                    }
+                    dirs[(int64_t)i * 32 + lane] = dw;
+                    h_left_prev = h_left_cur;
+                    out_h = left; out_e = e_left;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                // traceback (nc_nw_trace): ops in reverse order
+                int i = n, j = m, state = 0, nops = 0;
+                while (i > 0 || j > 0) {
+                    uint32_t fl = 0;
+                    if (i > 0 && j > 0) fl = (uint32_t)(dirs[(int64_t)i * 32 + (j - 1) / CW] >> (4 * ((j - 1) % CW))) & 15u;
+                    if (state == 0) {
+                        if (i > 0 && j > 0 && (fl & 1u)) { ops[nops++] = (__ldg(q + i - 1) == ref_code_of(__ldg(a.ref + p + j - 1))) ? 7 : 8; i--; j--; }
+                        else if (i > 0 && (j == 0 || (fl & 2u))) state = 1;
+                        else state = 2;
+                    } else if (state == 1) {
+                        ops[nops++] = 1;
+                        const bool ext = i > 1 && (j == 0 || (fl & 4u));
+                        i--;
+                        if (!ext) state = 0;
+                    } else {
+                        ops[nops++] = 2;
+                        const bool ext = j > 1 && (i == 0 || (fl & 8u));
+                        j--;
+                        if (!ext) state = 0;
+                    }
+                }
+                // the reference's walk over the run-length CIGAR, control flow kept line for line (allele_predict_one on the host)
+                const int32_t max_range = mt.type == 0 ? max(10, a.win) : 10;
+                bool indel = false, mis_before = false, done = false;
+                int32_t rc7 = 0, rc8 = 0, rc2 = 0, ac7 = 0, ac8 = 0, ac1 = 0, ma0 = 0, ma1 = 0;
+                int op = 0; int32_t cnt = 0;
+                int k = nops - 1;
+                while (k >= 0 && !done) {
+                    op = ops[k]; cnt = 0;
+                    while (k >= 0 && ops[k] == op) { cnt++; k--; }
+                    if (op == 8 || op == 7) {
+                        if (op == 7) { rc7 += cnt; ac7 += cnt; } else { rc8 += cnt; ac8 += cnt; }
+                        if (indel) { if (op == 7) ma0 += cnt; else ma1 += cnt; } else mis_before = true;
+                    }
+                    if (op == 1) { ac1 += cnt; ma0 = ma1 = 0; indel = true; }
+                    if (op == 2) { rc2 += cnt; ma0 = ma1 = 0; indel = true; }
+                    const int32_t rsum = rc7 + rc8 + rc2;
+                    if (!indel && rsum >= max_range + 10) {
+                        if (rc8) { const int32_t ol = op == 8 ? rsum : rsum - cnt; ref_out = ol; alt_out = ol; }
+                        done = true;
+                        break;
+                    }
+                    if (indel && ma0 + ma1 > 20) break;
+                }
+                if (!done && nops > 0) {
+                    const int32_t rsum = rc7 + rc8 + rc2, asum = ac7 + ac8 + ac1;
+                    int32_t r = op == 8 ? rsum : rsum - cnt, al = op == 8 ? asum : asum - cnt;
+                    if (!mis_before) { r += 1; al += 1; }
+                    ref_out = r; alt_out = al;
+                }
+            }
+        } else if (lane == 0) {
+            ref_out = -2; alt_out = -2;                       // does not fit the scratch: the host aligns this one (nc_allele_predict_batch)
+        }
+        if (lane == 0) { a.out[item * 2] = ref_out; a.out[item * 2 + 1] = alt_out; }
+        __syncwarp();
     }
 }
 

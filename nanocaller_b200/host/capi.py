@@ -17,7 +17,7 @@ EXPORTS = ["nc_abi_version", "nc_create", "nc_destroy", "nc_last_error", "nc_syn
            "nc_device_sm_count", "nc_event_record", "nc_event_elapsed_ms", "nc_invalidate_decode", "nc_stage_reads", "nc_decode_reads", "nc_snp_scan", "nc_snp_fetch", "nc_snp_fetch_range", "nc_indel_fetch_range",
            "nc_load_snp_weights", "nc_snp_forward", "nc_snp_fetch_probs", "nc_snp_model_forward", "nc_snp_device_buffers",
            "nc_load_indel_weights", "nc_indel_model_forward", "nc_stage_tags", "nc_indel_scan", "nc_indel_fetch_variants",
-           "nc_indel_build", "nc_indel_fetch", "nc_indel_forward", "nc_indel_fetch_probs", "nc_get_indel_timings", "nc_nw_trace", "nc_allele_predict_batch",
+           "nc_indel_build", "nc_indel_fetch", "nc_indel_forward", "nc_indel_fetch_probs", "nc_indel_fetch_alleles", "nc_get_indel_timings", "nc_nw_trace", "nc_allele_predict_batch",
            "nc_format_snp_records"]
 
 
@@ -41,7 +41,7 @@ class NcIndelParams(ctypes.Structure):
 
 class NcIndelTimings(ctypes.Structure):
     _fields_ = [("scan_ms", ctypes.c_float), ("reads_ms", ctypes.c_float), ("align_ms", ctypes.c_float), ("msa_ms", ctypes.c_float),
-                ("cnn_ms", ctypes.c_float), ("reserved", ctypes.c_float * 3), ("n_sites", ctypes.c_uint64), ("n_entries", ctypes.c_uint64),
+                ("cnn_ms", ctypes.c_float), ("allele_ms", ctypes.c_float), ("reserved", ctypes.c_float * 2), ("n_sites", ctypes.c_uint64), ("n_entries", ctypes.c_uint64),
                 ("scan_bytes", ctypes.c_uint64), ("build_bytes", ctypes.c_uint64)]
 
 
@@ -109,6 +109,7 @@ def load_library():
     lib.nc_indel_fetch.argtypes = [vp, vp, vp, vp]
     lib.nc_indel_forward.argtypes = [vp, ctypes.c_int, vp]
     lib.nc_indel_fetch_probs.argtypes = [vp, vp]
+    lib.nc_indel_fetch_alleles.argtypes = [vp, vp]
     lib.nc_get_indel_timings.argtypes = [vp, ctypes.POINTER(NcIndelTimings)]
     lib.nc_nw_trace.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp, i32]
     for name in EXPORTS:
@@ -273,6 +274,12 @@ class Context:
         cns = np.empty((n, 3, INDEL_CNS_MAX), np.uint8)
         self._check(self._lib.nc_indel_fetch(self._h, _p(meta) if n else None, _p(tensors) if (n and want_tensors) else None, _p(cns) if n else None))
         return meta, tensors, cns
+
+    def indel_fetch_alleles(self):
+        """Device allele prediction of the last build: int32 [n_sites, 3, 2] = (ref allele length, alt allele length), -1 = none."""
+        out = np.empty((self.n_isites, 3, 2), np.int32)
+        self._check(self._lib.nc_indel_fetch_alleles(self._h, _p(out) if self.n_isites else None))
+        return out
 
     def indel_forward(self, impl=0, fetch=True):
         """Indel CNN on the device-resident tensors of the last `indel_build` -> float32 [n_sites, 4] (haploid: [n_sites, 1])."""

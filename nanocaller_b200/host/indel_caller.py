@@ -112,7 +112,7 @@ def call_chunks(params, chunks, indel_tensors, hap_tensors=None, device=0, impl=
         return []
     ctx.load_indel_weights(W.pack_indel_blob(hap_tensors if hap else indel_tensors), hap)
     probs = ctx.indel_forward(impl=impl)                                   # a row per built site; only the kept ones are read
-    pred = indel_pileups.AllelePredictions(rs, params, meta, cns, hap).strings()
+    pred = indel_pileups.AllelePredictions(rs, params, meta, cns, hap, device_lengths=ctx.indel_fetch_alleles()).strings()
     out = []
     for sel, pos, alleles, phase in indel_pileups.per_chunk_calls(meta, pred, len(chunks), hap):
         if len(sel) == 0:

@@ -106,7 +106,9 @@ class AllelePredictions:
     """allele_prediction (generate_indel_pileups.py:77-127) for every kept site and read group, as arrays: item k is site
     `site[k]`, group `grp[k]`; ref_out / alt_out = lengths of the allele strings (-1 / -1: the reference returns (None, None))."""
 
-    def __init__(self, rs, dct, meta, cns, haploid, threads=0):
+    def __init__(self, rs, dct, meta, cns, haploid, threads=0, device_lengths=None):
+        """device_lengths: int32 [n_sites, 3, 2] from nc_indel_fetch_alleles (the alignment ran on the GPU right after msa); without it,
+        or for items it marks -2, the same alignment runs on host threads (nc_allele_predict_batch)."""
         self.groups = (2,) if haploid else (0, 1, 2)
         self.cns, self.meta = cns, meta
         kept = np.nonzero(kept_sites(meta, haploid))[0]
@@ -133,8 +135,17 @@ class AllelePredictions:
         self.r_len = np.repeat(m.astype(np.int32), ng)
         win = max(10, int(dct["win_size"]))
         mr = np.where(meta["type"][self.site] == 0, win, 10).astype(np.int32)   # max_range (:209)
-        self.ref_out, self.alt_out = capi.allele_predict_batch(cns.reshape(-1), alt_off, self.alt_len, ref_flat, self.r_off, self.r_len, mr,
-                                                               threads=threads)
+        if device_lengths is not None:
+            dl = np.asarray(device_lengths, np.int32)[self.site, self.grp]
+            self.ref_out, self.alt_out = dl[:, 0].copy(), dl[:, 1].copy()
+            todo = np.nonzero(self.ref_out == -2)[0]
+        else:
+            self.ref_out, self.alt_out = np.empty(len(self.site), np.int32), np.empty(len(self.site), np.int32)
+            todo = np.arange(len(self.site))
+        if len(todo):
+            ro, ao = capi.allele_predict_batch(cns.reshape(-1), alt_off[todo], self.alt_len[todo], ref_flat, self.r_off[todo], self.r_len[todo],
+                                               mr[todo], threads=threads)
+            self.ref_out[todo], self.alt_out[todo] = ro, ao
 
     def strings(self):
         """{(site, group): (ref, alt) or (None, None)}"""
@@ -174,7 +185,7 @@ def candidates_for_chunks(ctx, rs, dct, chunks, bed=None, haploid=False):
     """Scan + build for a list of chunk dicts of one contig; -> per-chunk reference-shaped tuples
     (diploid: 6-tuple of generate_indel_pileups.py:370; haploid: 3-tuple of generate_indel_pileups_haploid.py:277)."""
     meta, tensors, cns = scan_build(ctx, rs, dct, chunks, bed, haploid)
-    pred = AllelePredictions(rs, dct, meta, cns, haploid).strings()
+    pred = AllelePredictions(rs, dct, meta, cns, haploid, device_lengths=ctx.indel_fetch_alleles()).strings()
     res = []
     for sel, pos, alleles, phase in per_chunk_calls(meta, pred, len(chunks), haploid):
         if len(sel) == 0:

@@ -124,3 +124,25 @@ def test_device_resident_indel_forward_matches_oracle(impl):
     assert keep.sum() > 10 and got.shape == (len(meta), 4)
     assert float(np.abs(got[keep] - np.asarray(want)[keep]).max()) < 1e-4
     assert float(np.abs(got - np.asarray(want)).max()) < 1e-4           # sites msa() rejected carry zero tensors: still a defined input
+
+
+@pytest.mark.parametrize("preset,seq", [("ont", "ont"), ("hifi", "pacbio")])
+def test_device_allele_prediction_equals_host_alignment(preset, seq):
+    """indel_allele_kernel (affine NW + traceback + the reference's CIGAR walk on the GPU) against nc_allele_predict_batch (the same on
+    host threads) for every kept (site, group) of a synthetic contig: identical allele lengths, none deferred to the host."""
+    from nanocaller_b200.host import indel_pileups, snp_pileups
+    from nanocaller_b200.synth import make_world
+    rs = make_world(chrom="chrQ", preset=preset, contig_len=300_000, seed=41, coverage=30.0, indel_every=1200, indel_maxlen=40).reads
+    dct = dict(mincov=4, maxcov=160, seq=seq, del_t=0.6, ins_t=0.4, impute_indel_phase=False, supplementary=False, win_size=40, small_win_size=4)
+    chunks = [{"chrom": "chrQ", "start": s, "end": min(300_000, s + 100_000), "ploidy": "diploid"} for s in range(1, 300_000, 100_000)]
+    ctx = snp_pileups.context(0)
+    snp_pileups._staged.clear()
+    meta, _, cns = indel_pileups.scan_build(ctx, rs, dct, chunks, want_tensors=False)
+    dev = ctx.indel_fetch_alleles()
+    host = indel_pileups.AllelePredictions(rs, dct, meta, cns, False)
+    devp = indel_pileups.AllelePredictions(rs, dct, meta, cns, False, device_lengths=dev)
+    assert len(host.site) > 300 and not (dev == -2).any()
+    assert np.array_equal(host.ref_out, devp.ref_out) and np.array_equal(host.alt_out, devp.alt_out)
+    assert (host.ref_out >= 0).sum() > 50 and (host.ref_out < 0).sum() > 50
+    kept = indel_pileups.kept_sites(meta, False)
+    assert (dev[~kept] == -1).all()
