@@ -1099,15 +1099,15 @@ int nc_indel_build(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int
     NC_CUDA(cudaEventRecord(c->evi[3], c->stream));
     if (n_entries > 0) {
         // direction rows 1..n, n <= window_after; strips of 6 columns cover reference windows up to 192 columns (ONT: 161), 9 up to 288
-        const int rows = P->window_after + 2;
-        const int smem = kAlignWarps * align_smem_per_warp(rows);
+        const int rows = (P->window_after + 2 + 1) & ~1;            // even: keeps the per-warp blocks 16-byte aligned with 2-byte words
         const bool narrow = P->window_after + 1 <= 192;
+        const int smem = kAlignWarps * align_smem_per_warp(rows, narrow ? 2 : 4);
         // function attributes are per device and one process may open contexts on several: set it on every call (cheap, no sync)
-        if (narrow) NC_CUDA(cudaFuncSetAttribute(indel_align_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        else NC_CUDA(cudaFuncSetAttribute(indel_align_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (narrow) NC_CUDA(cudaFuncSetAttribute(indel_align_kernel<6, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else NC_CUDA(cudaFuncSetAttribute(indel_align_kernel<9, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_entries, kAlignWarps), (int64_t)c->sm_count * 16);
-        if (narrow) indel_align_kernel<6><<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries, rows);
-        else indel_align_kernel<9><<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries, rows);
+        if (narrow) indel_align_kernel<6, uint16_t><<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries, rows);
+        else indel_align_kernel<9, uint32_t><<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries, rows);
         NC_LAUNCH_CHECK();
     }
     NC_CUDA(cudaEventRecord(c->evi[4], c->stream));

@@ -602,18 +602,20 @@ __global__ void __launch_bounds__(128) indel_site_reads_kernel(const SiteArgs a)
 // read slice, the direction words, the aligned codes and the insertion tables — and leaves with coalesced stores at the end:
 // the first version read the slice back from global memory in every step and ran the traceback (lane 0, ~n + m dependent steps)
 // on read-modify-writes to global memory, 357 ms for configs[2]'s 4.1 M slices.
-constexpr int kAlignWarps = 2;
+constexpr int kAlignWarps = 4;
 constexpr int kRowsMax = 264;
 constexpr int kAlignAux = 4 * 272 + 2 * 2 * 272;        // per warp: slice, aligned codes (bytes); insertion length / first (u16)
-__host__ __device__ constexpr int align_smem_per_warp(int rows) { return rows * 32 * 4 + kAlignAux; }
+__host__ __device__ constexpr int align_smem_per_warp(int rows, int word_bytes) { return rows * 32 * word_bytes + kAlignAux; }
 
-template <int CW>
+// WordT: direction word of one lane and row, 2 bits per column of its strip (u16 for CW = 6, u32 for CW = 9): 12.6 KB of shared memory per
+// warp for the 161-column ONT window, i.e. 16 resident warps per SM to hide the sequential traceback of each
+template <int CW, typename WordT>
 __global__ void __launch_bounds__(kAlignWarps * 32) indel_align_kernel(const SiteArgs a, int64_t n_entries, int rows) {
     extern __shared__ __align__(16) uint8_t s_align_all[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint8_t* s_base = s_align_all + (size_t)wib * align_smem_per_warp(rows);
-    uint32_t* s_dir = reinterpret_cast<uint32_t*>(s_base);       // [rows][32] direction words (2 bits per column of the lane's strip)
-    uint8_t* s_slice = s_base + (size_t)rows * 128;               // [272]
+    uint8_t* s_base = s_align_all + (size_t)wib * align_smem_per_warp(rows, (int)sizeof(WordT));
+    WordT* s_dir = reinterpret_cast<WordT*>(s_base);             // [rows][32] direction words
+    uint8_t* s_slice = s_base + (size_t)rows * 32 * sizeof(WordT);   // [272]
     uint8_t* s_ac = s_slice + 272;                                // [272] (+ 544 spare)
     uint16_t* s_il = reinterpret_cast<uint16_t*>(s_slice + 4 * 272);
     uint16_t* s_if = s_il + 272;
@@ -674,7 +676,7 @@ __global__ void __launch_bounds__(kAlignWarps * 32) indel_align_kernel(const Sit
                     hp[k] = best;
                     left = best;
                 }
-                s_dir[i * 32 + lane] = dw;
+                s_dir[i * 32 + lane] = (WordT)dw;
                 h_left_prev = h_left_cur;
                 last_out = left;
             }
@@ -686,7 +688,7 @@ __global__ void __launch_bounds__(kAlignWarps * 32) indel_align_kernel(const Sit
             while (i > 0 || j > 0) {
                 uint32_t d;
                 if (i == 0) d = 2u; else if (j == 0) d = 1u;
-                else d = (s_dir[i * 32 + (j - 1) / CW] >> (2 * ((j - 1) % CW))) & 3u;
+                else d = ((uint32_t)s_dir[i * 32 + (j - 1) / CW] >> (2 * ((j - 1) % CW))) & 3u;
                 if (d == 0u) { s_ac[j - 1] = s_slice[i - 1]; i--; j--; }
                 else if (d == 1u) { s_il[j]++; s_if[j] = (uint16_t)(i - 1); i--; }
                 else { s_ac[j - 1] = 5; j--; }
