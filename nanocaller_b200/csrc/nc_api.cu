@@ -1467,6 +1467,22 @@ int nc_debug_tc_trunk(nc_ctx* c, const float* x, int64_t n, int haploid, int sta
     return tc_check(c, M);
 }
 
+// Validation switch for the tensor-core SNP kernels: on != 0 runs the instantiations that count activations sitting on the fp16
+// saturation value (cvt.rn.satfinite clamps silently); *count (may be NULL) receives the count since the weights were loaded / last reset.
+int nc_debug_saturation(nc_ctx* c, int haploid, int on, int reset, int64_t* count) {
+    if (!c) return NC_EINVAL;
+    NC_CUDA(cudaSetDevice(c->device));
+    Model& M = c->snp[haploid ? 1 : 0];
+    if (!M.loaded || !M.tc.ready) return fail(c, NC_ESTATE, "nc_debug_saturation: no tensor-core SNP model loaded");
+    M.tc.audit = on != 0;
+    NC_CUDA(c->pin.reserve(64));
+    NC_CUDA(cudaMemcpyAsync(c->pin.p, M.tc.err.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    NC_CUDA(nc_stream_wait(c));
+    if (count) *count = *c->pin.as<int>();
+    if (reset) NC_CUDA(cudaMemsetAsync(M.tc.err.as<int>() + 1, 0, sizeof(int), c->stream));
+    return NC_OK;
+}
+
 // Indel tensor-core trunk up to `stage` (1: c2 slabs after conv1 + conv2, 2: c3 after conv3) on fp32 inputs [n][H][128][2]; returns the raw
 // fp16 hi/lo activation image (layouts in nc_cnn_tc_indel.cuh).  n <= 32768 (one batch).
 int nc_debug_tci_trunk(nc_ctx* c, const float* x, int64_t n, int haploid, int stage, void* raw, size_t raw_bytes) {

@@ -137,6 +137,12 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     hi = pack_sat(ah, bh);
     lo = pack_sat(a - ah, b - bh);
 }
+// Saturation audit (validation builds of the kernels, template flag SAT): cvt.rn.satfinite clamps |x| > 65504 to the largest finite
+// fp16 silently; count the hi halves that sit exactly on that value so that a test can assert the clamp never engages.
+__device__ __forceinline__ uint32_t sat_halves(const uint4& hi) {
+    const uint32_t k = 0x7BFF7BFFu, m = 0x7FFF7FFFu;
+    return (__vcmpeq2(hi.x & m, k) | __vcmpeq2(hi.y & m, k) | __vcmpeq2(hi.z & m, k) | __vcmpeq2(hi.w & m, k)) != 0u ? 1u : 0u;
+}
 // 8 accumulator values -> bias + SELU -> hi / lo 16-byte words.  bias2 = [bias | bias * log2 e] rows of 8 floats: bias2[0..7], bias2[n_bias..]
 __device__ __forceinline__ void act_split8_nobias(const float* acc, uint4& hi, uint4& lo) {      // bias already inside the accumulator
     split2(selu_acc(acc[0], 0.f, 0.f), selu_acc(acc[1], 0.f, 0.f), hi.x, lo.x);
@@ -318,6 +324,7 @@ __device__ __forceinline__ void tmem_ld_pair16(uint32_t addr, float* v) {
 //   conv1 tile 0 in flight : previous site's conv2 epilogue (bias, SELU, fp16 split, HBM stores)
 //   conv1 tile 1 in flight : tile 0 epilogue (bias, SELU, split -> c1 planes in shared memory)
 //   conv2 in flight        : next site's int16 tensor -> scaled fp16 hi/lo input planes
+template <bool SAT>
 __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_w = smem;
@@ -374,6 +381,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
     uint64_t* bar = &s_bar[wg];
     uint32_t phase = 0;
     bool ok = true;
+    uint32_t sat = 0;
 
     int64_t site = (int64_t)blockIdx.x * TA_WGS + wg;
     const bool raw_mode = P.in_mode != 0;
@@ -416,6 +424,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
                 split2(v[0], v[1], hi.x, lo.x);
                 split2(v[2], v[3], hi.y, lo.y);
                 split2(v[4], 0.f, hi.z, lo.z);
+                if (SAT) sat += sat_halves(hi);
                 hi.z |= 0x3C000000u;                                       // channel slot 5 = 1.0 on real pixels: multiplies the bias row of the centre tap
                 const int row = (h + 2) * tcg::WP + w + 2;
                 *reinterpret_cast<uint4*>(s_in + row * 16) = hi;
@@ -435,6 +444,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
             for (int kg = 0; kg < 6; kg++) {
                 uint4 hi, lo;
                 act_split8_nobias(v + 8 * kg, hi, lo);                     // conv1 bias rides on the centre tap (constant channel 5)
+                if (SAT) sat += sat_halves(hi);
                 *reinterpret_cast<uint4*>(dst + kg * tcg::C1_PLANE) = hi;
                 *reinterpret_cast<uint4*>(dst + (12 + kg) * tcg::C1_PLANE) = lo;
             }
@@ -456,6 +466,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
             for (int kg = 0; kg < 4; kg++) {
                 uint4 hi, lo;
                 act_split8(acc + 8 * kg, s_bias + 48 + 8 * kg, s_bl + 48 + 8 * kg, hi, lo);
+                if (SAT) sat += sat_halves(hi);
                 *reinterpret_cast<uint4*>(dst + kg * tcg::C2_PLANE) = hi;
                 *reinterpret_cast<uint4*>(dst + (8 + kg) * tcg::C2_PLANE) = lo;
             }
@@ -540,6 +551,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_trunk_a_kernel(const TAParam
 #endif
 #undef NC_TA_MARK
     if (!ok && t == 0) atomicExch(P.err, 1);
+    if (SAT && sat) atomicAdd(P.err + 1, (int)sat);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(*s_tmem, 512);
@@ -570,6 +582,7 @@ static_assert(TB_SMEM <= 232448, "TB shared memory exceeds the 227 KB per-CTA li
 // keeps a ring of TB_RING images in flight for the three consumer warpgroups (full / empty mbarriers per stage; the
 // stage is released by a tcgen05.commit, i.e. when the MMAs that read it have completed).
 // The CTA's i-th group is global group (i / 3) * 3 * gridDim + 3 * blockIdx + i % 3; warpgroup w consumes i = w mod 3.
+template <bool SAT>
 __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_w = smem;
@@ -621,7 +634,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
     const uint32_t tmem = *s_tmem + (uint32_t)wg * 128u;          // columns [0,64) = (a_hi + a_lo) w_hi, [64,128) = a_hi w_lo
     const uint32_t tmem_lane = tmem + ((uint32_t)wq << 21);
     const uint32_t w16 = smem_u32(s_w) >> 4;
-    uint32_t phase = 0;
+    uint32_t phase = 0, sat = 0;
     for (int64_t k = 0;; k++) {
         const int64_t i = k * TB_WGS + wg;
         const int64_t grp = k * gstride + gbase + wg;
@@ -671,6 +684,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
                         uint4 hi, lo;
                         const int kg = half * 4 + g;
                         act_split8(acc + 8 * g, s_bias + 8 * kg, s_bl + 8 * kg, hi, lo);
+                        if (SAT) sat += sat_halves(hi);
                         const int ck = (kg ^ (int)(site & 7)) * 16;                  // chunk position under the 128-byte swizzle
                         *reinterpret_cast<uint4*>(dst + ck) = hi;
                         *reinterpret_cast<uint4*>(dst + tcg::C3_BLOCK_BYTES + ck) = lo;
@@ -681,6 +695,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_trunk_b_kernel(const TBParam
         tc_fence_before();
     }
     if (!ok && t == 0) atomicExch(P.err, 1);
+    if (SAT && sat) atomicAdd(P.err + 1, (int)sat);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(*s_tmem, 512);
@@ -876,6 +891,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const uint8_t* a_img
 // ------------------------------------------------------------------------------------------------
 struct TcModel {
     bool ready = false;
+    bool audit = false;                          // run the validation instantiations that count fp16 saturation (err[1])
     int kind = 0;
     DevBuf wimg_a, wimg_b, wimg_c, bias;         // bias: b1(48) b2(32) b3(64) bf(48)
     DevBuf c2, c3, err;
@@ -1015,8 +1031,10 @@ inline int tc_forward_ex(cudaStream_t stream, TcModel& T, int in_mode, const voi
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
     const bool tracked = dev >= 0 && dev < 64;
     if (!tracked || !attr_set[dev]) {
-        if ((e = cudaFuncSetAttribute(tc_trunk_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM)) != cudaSuccess) return cuda_fail(e, "TA smem attr");
-        if ((e = cudaFuncSetAttribute(tc_trunk_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM)) != cudaSuccess) return cuda_fail(e, "TB smem attr");
+        if ((e = cudaFuncSetAttribute(tc_trunk_a_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM)) != cudaSuccess) return cuda_fail(e, "TA smem attr");
+        if ((e = cudaFuncSetAttribute(tc_trunk_b_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM)) != cudaSuccess) return cuda_fail(e, "TB smem attr");
+        if ((e = cudaFuncSetAttribute(tc_trunk_a_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM)) != cudaSuccess) return cuda_fail(e, "TA smem attr");
+        if ((e = cudaFuncSetAttribute(tc_trunk_b_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM)) != cudaSuccess) return cuda_fail(e, "TB smem attr");
         if ((e = cudaFuncSetAttribute(tc_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)) != cudaSuccess) return cuda_fail(e, "TC smem attr");
         if (tracked) attr_set[dev] = true;
     }
@@ -1026,7 +1044,8 @@ inline int tc_forward_ex(cudaStream_t stream, TcModel& T, int in_mode, const voi
     pa.wimg = T.wimg_a.as<uint8_t>(); pa.bias1 = bias; pa.bias2 = bias + 48;
     pa.c2_out = T.c2.as<uint8_t>(); pa.err = T.err.as<int>();
     const unsigned ga = (unsigned)std::min<int64_t>((n + TA_WGS - 1) / TA_WGS, sm_count);
-    tc_trunk_a_kernel<<<ga, TA_THREADS, TA_SMEM, stream>>>(pa);
+    if (T.audit) tc_trunk_a_kernel<true><<<ga, TA_THREADS, TA_SMEM, stream>>>(pa);
+    else tc_trunk_a_kernel<false><<<ga, TA_THREADS, TA_SMEM, stream>>>(pa);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "TA launch");
     (*launches)++;
     if (ev_after_ta && (e = cudaEventRecord(ev_after_ta, stream)) != cudaSuccess) return cuda_fail(e, "TA event");
@@ -1036,7 +1055,8 @@ inline int tc_forward_ex(cudaStream_t stream, TcModel& T, int in_mode, const voi
     pb.c3_out = T.c3.as<uint8_t>(); pb.err = T.err.as<int>();
     const int64_t n_groups = (n + 2) / 3;
     const unsigned gb = (unsigned)std::min<int64_t>((n_groups + TB_WGS - 1) / TB_WGS, sm_count);
-    tc_trunk_b_kernel<<<gb, TB_THREADS, TB_SMEM, stream>>>(pb);
+    if (T.audit) tc_trunk_b_kernel<true><<<gb, TB_THREADS, TB_SMEM, stream>>>(pb);
+    else tc_trunk_b_kernel<false><<<gb, TB_THREADS, TB_SMEM, stream>>>(pb);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "TB launch");
     (*launches)++;
     if (stop_after == 2) return NC_OK;
