@@ -175,6 +175,11 @@ def _load_exclude_bed(args):
     return path
 
 
+def _contig_lengths(bam):
+    from .host import bamio, sources
+    return sources.contig_lengths(bam) if bam.startswith("mem://") else bamio.bam_contigs(bam)
+
+
 def _groups(chunks):
     """Consecutive chunks of one (contig, ploidy): one staging + one batched launch sequence each."""
     out = []
@@ -236,9 +241,10 @@ def run(args):
         f.write("------Parameters Used For Variant Calling------\n")
         for k, v in vars(args).items():
             f.write("{}: {}\n".format(k, v))
-    contig_lengths = bamio.bam_contigs(args.bam)                  # utils.py:9-50 asks the BAM header, not the FASTA
+    contig_lengths = _contig_lengths(args.bam)                    # utils.py:9-50 asks the BAM header, not the FASTA
     regions = getattr(args, "_regions", None) or get_regions_list(args, contig_lengths)     # _regions: one rank's share (host/multi.py)
-    bamio.open_alignment(args.bam, args.ref, contigs={r[0] for r in regions})     # only the contigs that will be called
+    if not args.bam.startswith("mem://"):                         # mem://: an in-memory source registered by the caller (host/sources.py)
+        bamio.open_alignment(args.bam, args.ref, contigs={r[0] for r in regions})     # only the contigs that will be called
     if getattr(args, "_read_windows", None):                      # one rank of a chunk-sharded run (host/multi.py): keep its part of every contig
         from .host import sources
         sources.restrict(args.bam, args._read_windows)
@@ -330,7 +336,7 @@ def main(argv=None):
             torch.cuda.set_device(local)
         if not dist.is_initialized():
             dist.init_process_group("nccl" if cuda else "gloo")
-        regions = get_regions_list(args, bamio.bam_contigs(args.bam))
+        regions = get_regions_list(args, _contig_lengths(args.bam))
         out = multi.run_distributed(args, run, regions, dist, device=("cuda:%d" % local) if cuda else "cpu")
         print("\n%s: Total Time Elapsed: %.2f seconds" % (datetime.datetime.now(), time.time() - t))
         return out

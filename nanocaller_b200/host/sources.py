@@ -16,6 +16,28 @@ def register_source(path, readsets):
     _REGISTRY[path] = {rs.chrom: rs for rs in readsets}
 
 
+class _Lazy:
+    """A contig whose ReadSet is made on first use (a rank of a multi-GPU run only materialises the contigs it owns)."""
+
+    def __init__(self, length, factory):
+        self.length, self.factory = int(length), factory
+
+
+def register_lazy(path, contigs):
+    """contigs: ordered {chrom: (length, factory)}; factory() -> ReadSet, called on the first `resolve` of that contig."""
+    _REGISTRY[path] = {c: _Lazy(n, f) for c, (n, f) in contigs.items()}
+
+
+def contig_lengths(path):
+    """Ordered {contig: length} of a registered in-memory source (what the BAM header gives for a file, utils.py:9-50)."""
+    return {c: (v.length if isinstance(v, _Lazy) else v.contig_len) for c, v in _REGISTRY[path].items()}
+
+
+def release(path, chrom):
+    """Drop a materialised lazy contig (frees host memory once its stage is done)."""
+    _REGISTRY.get(path, {}).pop(chrom, None)
+
+
 def register_bed(path, intervals):
     """intervals: {chrom: [(start, end), ...]} — stands for a tabix-indexed exclude BED."""
     _BEDS[path] = intervals
@@ -41,9 +63,12 @@ def resolve(sam_path, chrom):
             from . import bamio
             bamio.open_alignment(sam_path, _FASTA_FOR.get(sam_path))
     try:
-        return _REGISTRY[sam_path][chrom]
+        rs = _REGISTRY[sam_path][chrom]
     except KeyError:
         raise FileNotFoundError("no alignment source registered for %r contig %r" % (sam_path, chrom))
+    if isinstance(rs, _Lazy):
+        rs = _REGISTRY[sam_path][chrom] = rs.factory()
+    return rs
 
 
 def restrict(sam_path, windows):
@@ -51,7 +76,7 @@ def restrict(sam_path, windows):
     reg = _REGISTRY[sam_path]
     for chrom, (lo0, hi0) in windows.items():
         if chrom in reg:
-            reg[chrom] = reg[chrom].window(lo0, hi0)
+            reg[chrom] = resolve(sam_path, chrom).window(lo0, hi0)
 
 
 def contigs(sam_path):
