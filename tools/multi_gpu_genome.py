@@ -35,6 +35,9 @@ CONFIGS = {
 }
 
 
+GEN = {"seconds": 0.0, "bases": 0}
+
+
 def genome(config, mb):
     from nanocaller_b200.synth import make_world
     total = sum(n for _, n in GRCH38_MB)
@@ -46,7 +49,11 @@ def genome(config, mb):
         preset = kw.pop("preset")
 
         def factory(name=name, length=length, i=i, kw=kw, preset=preset):
-            return make_world(chrom=name, preset=preset, contig_len=length, seed=1000 + i, **kw).reads
+            t = time.time()
+            rs = make_world(chrom=name, preset=preset, contig_len=length, seed=1000 + i, **kw).reads
+            GEN["seconds"] += time.time() - t
+            GEN["bases"] += rs.aligned_bases()
+            return rs
         contigs[name] = (length, factory)
     return contigs
 
@@ -68,9 +75,20 @@ def main():
     t0 = time.time()
     out = cli.main(argv)
     dt = time.time() - t0
+    gen = [GEN["seconds"], float(GEN["bases"])]
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor(gen, dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
+        ts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(ts, t)
+        gen = [max(x[0].item() for x in ts), sum(x[1].item() for x in ts)]
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
-    res = {"config": a.config, "megabases": a.mb, "n_gpus": world, "seconds": dt, "contigs": len(genome(a.config, a.mb)),
+    res = {"config": a.config, "megabases": a.mb, "n_gpus": world, "seconds": dt, "read_generation_seconds_max_rank": gen[0],
+           "seconds_without_read_generation": dt - gen[0], "aligned_bases": gen[1], "contigs": len(genome(a.config, a.mb)),
            "sharding": out.get("sharding", "single process"), "records": {k: v for k, v in out.items() if k.startswith("n_")},
            "seconds_by_stage": {k: v for k, v in out.items() if k.endswith("_seconds")}}
     if a.compare:
