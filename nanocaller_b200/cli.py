@@ -225,8 +225,9 @@ def _phase_stage(args, regions, chrom_list, out):
             pdir = os.path.join(args.output, "intermediate_phase_files")
             os.makedirs(pdir, exist_ok=True)
             st["phased_bam"] = bamio.write_haplotagged_bam(args.bam, chrom, rs.hp, rs.ps, os.path.join(pdir, "%s.phased.bam" % chrom))
-    php = os.path.join(args.output, "%s.snps.phased.vcf.gz" % args.prefix)
-    vcfio.write_vcf(php, "phased_snps", chrom_list, phased_lines, args.sample, index=True)
+    partial = bool(getattr(args, "_partial", False))              # one rank of a multi-GPU run: plain text, merged and compressed by rank 0
+    php = os.path.join(args.output, "%s.snps.phased.vcf%s" % (args.prefix, "" if partial else ".gz"))
+    vcfio.write_vcf(php, "phased_snps", chrom_list, phased_lines, args.sample, index=not partial)
     out.update(phased_snps=php, phase_stats=pstats, phase_seconds=time.time() - t1)
     print("\n%s: Phasing completed. Time taken= %.4f\n" % (datetime.datetime.now(), time.time() - t1), flush=True)
 
@@ -250,6 +251,10 @@ def run(args):
         sources.restrict(args.bam, args._read_windows)
     exclude = _load_exclude_bed(args)
     chrom_list = list(dict.fromkeys(r[0] for r in regions))
+    # one rank of a multi-GPU run (host/multi.py): its record files are read back by the merge on rank 0, so they stay plain text
+    # without an index; the reference's compressed, indexed outputs are written once, by rank 0
+    partial = bool(getattr(args, "_partial", False))
+    gz, idx = ("" if partial else ".gz"), not partial
     ctx = snp_pileups.context(args.device)                        # fails loudly without an sm_100 device
     out = {}
     t_read = time.time() - t0
@@ -271,10 +276,10 @@ def run(args):
         for grp in _groups(chunks):
             blob, off, ok, pos = snp_caller.call_chunks_blob(params, grp, (tensors, cov), hap_weights=hap, device=args.device)
             parts.append((grp[0]["chrom"], blob, off, ok, pos))
-        allp = os.path.join(args.output, "%s.unfiltered.snps.vcf.gz" % args.prefix)
-        passp = os.path.join(args.output, "%s.snps.vcf.gz" % args.prefix)
-        n_all = vcfio.write_vcf_blobs(allp, "snps", chrom_list, parts, args.sample, index=True)      # + .csi, like tabix -fp vcf --csi (snpCaller.py:283)
-        vcfio.write_vcf_blobs(passp, "snps", chrom_list, parts, args.sample, pass_only=True, index=True)
+        allp = os.path.join(args.output, "%s.unfiltered.snps.vcf%s" % (args.prefix, gz))
+        passp = os.path.join(args.output, "%s.snps.vcf%s" % (args.prefix, gz))
+        n_all = vcfio.write_vcf_blobs(allp, "snps", chrom_list, parts, args.sample, index=idx)      # + .csi, like tabix -fp vcf --csi (snpCaller.py:283)
+        vcfio.write_vcf_blobs(passp, "snps", chrom_list, parts, args.sample, pass_only=True, index=idx)
         out.update(unfiltered_snps=allp, snps=passp, n_snp_records=n_all, snp_seconds=time.time() - t1)
         print("\n%s: SNP calling completed. Time taken= %.4f\n" % (datetime.datetime.now(), time.time() - t1), flush=True)
 
@@ -297,7 +302,7 @@ def run(args):
         lines = []
         for grp in _groups(chunks):                               # indelCaller.py:327-336 hands every chunk its (phased) BAM
             lines += indel_caller.call_chunks(params, [dict(c, sam_path=args.bam) for c in grp], ind, hap_tensors=hap_ind, device=args.device)
-        indp = os.path.join(args.output, "%s.indels.vcf.gz" % args.prefix)
+        indp = os.path.join(args.output, "%s.indels.vcf%s" % (args.prefix, gz))
         if args.decompose_indels:                                 # indelCaller.py:369,:391
             from .host import vcf_decompose
             raw_dir = os.path.join(args.output, "intermediate_indel_files")
@@ -305,13 +310,13 @@ def run(args):
             out["raw_indels"] = os.path.join(raw_dir, "%s.raw.indel.vcf" % args.prefix)
             vcfio.write_vcf(out["raw_indels"], "indels", chrom_list, lines, args.sample)
             lines = vcf_decompose.decompose_records(vcfio.sort_records(lines, chrom_list), contigs=chrom_list)
-        vcfio.write_vcf(indp, "indels", chrom_list, lines, args.sample, index=True)
+        vcfio.write_vcf(indp, "indels", chrom_list, lines, args.sample, index=idx)
         out.update(indels=indp, n_indel_records=len(lines), indel_seconds=time.time() - t1)
         print("\n%s: Indel calling completed. Time taken= %.4f\n" % (datetime.datetime.now(), time.time() - t1), flush=True)
         if args.mode == "all":
-            final = os.path.join(args.output, "%s.vcf.gz" % args.prefix)
+            final = os.path.join(args.output, "%s.vcf%s" % (args.prefix, gz))
             snp_lines = vcfio.read_records(out["phased_snps"])             # indelCaller.py:395 concatenates the phased SNP file
-            vcfio.write_vcf(final, "all", chrom_list, snp_lines + lines, args.sample, index=True)
+            vcfio.write_vcf(final, "all", chrom_list, snp_lines + lines, args.sample, index=idx)
             out["final"] = final
     out.update(read_seconds=t_read, launches=ctx.timings()["launches"])
     return out

@@ -126,6 +126,7 @@ def run_distributed(args, run_fn, regions, dist, device="cpu"):
         sub.wgs_contigs = None
         sub.output = os.path.join(args.output, "rank%d" % rank)
         sub.device = local
+        sub._partial = True                                                   # record files of a rank stay plain text (cli.run)
         sub._total_bases = sum(e - s + 1 for _, s, e, _ in regions)          # utils.py:72 sizes the chunks from ALL regions
         if by_chunk:                                                          # stage only the reads this rank's chunks can see
             sub._read_windows = read_windows(mine)
