@@ -130,6 +130,29 @@ int nc_stage_reads(nc_ctx* ctx, int64_t n_reads, const int32_t* pos, const uint1
                    const int32_t* l_seq, const uint8_t* seq4, const uint8_t* ref,
                    int64_t ref_start, int64_t ref_len);
 
+/* ---- device-side BAM input (replaces pysam.Samfile / htslib BGZF + record decoding at generate_SNP_pileups.py:134-156 and
+ * generate_indel_pileups.py:147-185 for file-backed runs): the COMPRESSED file bytes cross PCIe, BGZF blocks are inflated on the GPU
+ * (one thread per block), the record chain is walked there and every mapped record is decoded into the same device arrays
+ * nc_stage_reads fills (long CIGARs are restored from CG:B,I, HP / PS tags are staged as by nc_stage_tags). ---- */
+typedef struct NcBamDeviceContig {
+    char    name[256];
+    int32_t length;          /* @SQ LN of the BAM header                                   */
+    int32_t reserved;
+    int64_t n_reads;         /* records with this refID                                    */
+    int64_t n_tagged;        /* of which carry an HP tag of 1 or 2                         */
+} NcBamDeviceContig;
+
+/* Reads `path` (a BGZF-compressed BAM; the whole file is inflated into device memory, so it has to fit), parses the header and walks
+ * the records.  *n_contigs = references of the header.  Replaces any BAM opened on this context before. */
+int nc_bam_device_open(nc_ctx* ctx, const char* path, int32_t* n_contigs);
+int nc_bam_device_contig(nc_ctx* ctx, int32_t i, NcBamDeviceContig* out);
+/* nc_stage_reads + nc_stage_tags for contig i of the opened BAM, from the inflated stream on the device; `ref` as in nc_stage_reads. */
+int nc_bam_device_stage(nc_ctx* ctx, int32_t i, const uint8_t* ref, int64_t ref_start, int64_t ref_len);
+/* Frees the inflated stream (staged contigs stay valid). */
+int nc_bam_device_close(nc_ctx* ctx);
+/* Milliseconds of the last nc_bam_device_open: host (mmap + block table + copy into pinned memory), H2D, inflate kernel, record walk + fields. */
+int nc_bam_device_timings(nc_ctx* ctx, float ms[4], int64_t* compressed_bytes, int64_t* inflated_bytes);
+
 /* K0 — htslib pileup-engine replacement (generate_SNP_pileups.py:156):
  * turns every staged read into a reference-aligned row of 4-bit codes (A0 G1 T2 C3, 4 for a
  * deletion / N / anything else).  Called implicitly by nc_snp_scan when needed. */

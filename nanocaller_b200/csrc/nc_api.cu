@@ -14,6 +14,13 @@
 #include "nc_cnn_tc.cuh"
 #include "nc_cnn_tc_indel.cuh"
 #include "nc_indel.cuh"
+#include "nc_bgzf.cuh"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <chrono>
 
 using namespace nc;
 
@@ -83,6 +90,15 @@ struct nc_ctx {
     bool tmi_scan = false, tmi_build = false, tmi_cnn = false, have_iprobs = false;
     int build_haploid = 0;
     DevBuf d_iprobs, d_ialleles, d_allele_dirs, d_allele_ops;
+    // device-side BAM input
+    struct BamContig { std::string name; int32_t length = 0; int64_t first = 0, n = 0, n_tagged = 0; };
+    DevBuf d_bam_comp, d_bam_blocks, d_bam, d_bam_recoff, d_bam_rid, d_bam_pos, d_bam_flag, d_bam_lseq, d_bam_ncig, d_bam_nseq, d_bam_cigsrc, d_bam_seqsrc,
+           d_bam_hp, d_bam_ps, d_bam_err, d_bam_out;
+    PinBuf pin_bam;
+    std::vector<BamContig> bam_contigs;
+    int64_t bam_records = 0, bam_bytes = 0, bam_comp_bytes = 0;
+    float bam_ms[4] = {0, 0, 0, 0};
+    bool bam_open = false;
     NcTimings tm = {};
     bool tm_decode = false, tm_scan = false, tm_cnn = false, tm_cnn_a = false;
 };
@@ -351,6 +367,26 @@ int tc_check(nc_ctx* c, Model& M) {
 
 }  // namespace
 
+namespace {
+struct MapRO {
+    const uint8_t* p = nullptr; size_t n = 0; bool ok = false;
+    explicit MapRO(const char* path) {
+        const int fd = open(path, O_RDONLY);
+        if (fd < 0) return;
+        struct stat st;
+        if (fstat(fd, &st) == 0) {
+            n = (size_t)st.st_size;
+            void* m = n ? mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+            if (!n || m != MAP_FAILED) { p = (const uint8_t*)m; ok = true; }
+        }
+        close(fd);
+    }
+    ~MapRO() { if (p) munmap((void*)p, n); }
+};
+template <class T> T rd_le(const uint8_t* p) { T v; memcpy(&v, p, sizeof(T)); return v; }
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+
 // ================================================================================================
 // C-ABI
 // ================================================================================================
@@ -416,6 +452,9 @@ void nc_destroy(nc_ctx* c) {
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->evi) if (e) cudaEventDestroy(e);
     c->d_iprobs.release(); c->d_ialleles.release(); c->d_allele_dirs.release(); c->d_allele_ops.release();
+    for (DevBuf* b : {&c->d_bam_comp, &c->d_bam_blocks, &c->d_bam, &c->d_bam_recoff, &c->d_bam_rid, &c->d_bam_pos, &c->d_bam_flag, &c->d_bam_lseq, &c->d_bam_ncig,
+                      &c->d_bam_nseq, &c->d_bam_cigsrc, &c->d_bam_seqsrc, &c->d_bam_hp, &c->d_bam_ps, &c->d_bam_err, &c->d_bam_out}) b->release();
+    c->pin_bam.release();
     if (c->ev_block) cudaEventDestroy(c->ev_block);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1418,6 +1457,244 @@ int64_t nc_format_snp_records(const char* chrom, int64_t n, const int32_t* pos, 
     return total;
 }
 
+
+// ---- device-side BAM input -----------------------------------------------------------------------------------------
+int nc_bam_device_close(nc_ctx* c) {
+    if (!c) return NC_EINVAL;
+    NC_CUDA(cudaSetDevice(c->device));
+    NC_CUDA(nc_stream_wait(c));
+    for (DevBuf* b : {&c->d_bam_comp, &c->d_bam_blocks, &c->d_bam, &c->d_bam_recoff, &c->d_bam_rid, &c->d_bam_pos, &c->d_bam_flag, &c->d_bam_lseq, &c->d_bam_ncig,
+                      &c->d_bam_nseq, &c->d_bam_cigsrc, &c->d_bam_seqsrc, &c->d_bam_hp, &c->d_bam_ps}) b->release();
+    c->bam_open = false; c->bam_contigs.clear(); c->bam_records = 0;
+    return NC_OK;
+}
+
+int nc_bam_device_open(nc_ctx* c, const char* path, int32_t* n_contigs) {
+    if (!c || !path || !n_contigs) return fail(c, NC_EINVAL, "nc_bam_device_open: null argument");
+    *n_contigs = 0;
+    NC_CUDA(cudaSetDevice(c->device));
+    c->bam_open = false; c->bam_contigs.clear();
+    const double t0 = now_ms();
+    MapRO f(path);
+    if (!f.ok) return fail(c, NC_EINVAL, "cannot open %s", path);
+    // ---- BGZF block table from the block headers (BSIZE) and trailers (ISIZE)
+    std::vector<BgzfBlock> blocks;
+    int64_t total = 0;
+    for (size_t off = 0; off < f.n;) {
+        if (off + 18 > f.n) return fail(c, NC_EINVAL, "truncated or malformed BGZF block");
+        const uint8_t* p = f.p + off;
+        if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return fail(c, NC_EINVAL, "not a BGZF stream");
+        const uint16_t xlen = rd_le<uint16_t>(p + 10);
+        size_t x = 12; const size_t xend = 12 + (size_t)xlen;
+        int bsize = -1;
+        while (x + 4 <= xend && off + x + 4 <= f.n) {
+            const uint16_t slen = rd_le<uint16_t>(p + x + 2);
+            if (p[x] == 'B' && p[x + 1] == 'C' && slen == 2) bsize = rd_le<uint16_t>(p + x + 4);
+            x += 4 + slen;
+        }
+        const size_t blen = (size_t)bsize + 1;
+        if (bsize < 0 || off + blen > f.n || blen < xend + 8) return fail(c, NC_EINVAL, "truncated or malformed BGZF block");
+        const uint32_t isize = rd_le<uint32_t>(p + blen - 4);
+        if (isize) blocks.push_back({(int64_t)(off + xend), (int32_t)(blen - xend - 8), (int32_t)isize, total});
+        total += isize;
+        off += blen;
+    }
+    if (blocks.empty() || total < 12) return fail(c, NC_EINVAL, "empty BAM file");
+    size_t free_b = 0, total_b = 0;
+    NC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if ((size_t)total + f.n + (size_t)total / 8 > free_b / 2) return fail(c, NC_ENOMEM, "inflated BAM (%lld bytes) does not fit the device budget", (long long)total);
+    // ---- compressed bytes -> pinned -> device (threads: page-cache reads + first touch of the pinned pages)
+    NC_CUDA(c->pin_bam.reserve(f.n + blocks.size() * sizeof(BgzfBlock) + 64));
+    uint8_t* pin = c->pin_bam.as<uint8_t>();
+    {
+        const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        const size_t per = (f.n + nt - 1) / nt;
+        for (int t = 0; t < nt; t++) pool.emplace_back([&, t]() { const size_t a = t * per, e = std::min(f.n, a + per); if (a < e) memcpy(pin + a, f.p + a, e - a); });
+        for (auto& th : pool) th.join();
+    }
+    const size_t blk_at = (f.n + 63) & ~(size_t)63;
+    memcpy(pin + blk_at, blocks.data(), blocks.size() * sizeof(BgzfBlock));
+    const double t1 = now_ms();
+    NC_CUDA(c->d_bam_comp.reserve(blk_at + blocks.size() * sizeof(BgzfBlock)));
+    NC_CUDA(c->d_bam.reserve((size_t)total + 64));
+    NC_CUDA(c->d_bam_err.reserve(64));
+    NC_CUDA(c->d_bam_out.reserve(64));
+    NC_CUDA(cudaMemsetAsync(c->d_bam_err.p, 0, 64, c->stream));
+    cudaEvent_t e0 = c->evi[0], e1 = c->evi[1], e2 = c->evi[2], e3 = c->evi[3];
+    NC_CUDA(cudaEventRecord(e0, c->stream));
+    NC_CUDA(cudaMemcpyAsync(c->d_bam_comp.p, pin, blk_at + blocks.size() * sizeof(BgzfBlock), cudaMemcpyHostToDevice, c->stream));
+    NC_CUDA(cudaEventRecord(e1, c->stream));
+    NC_CUDA(cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kInflSmem));
+    const int64_t nb = (int64_t)blocks.size();
+    bgzf_inflate_kernel<<<(unsigned)div_up(nb, kInflThreads), kInflThreads, kInflSmem, c->stream>>>(
+        c->d_bam_comp.as<uint8_t>(), reinterpret_cast<const BgzfBlock*>(c->d_bam_comp.as<uint8_t>() + blk_at), nb, c->d_bam.as<uint8_t>(), c->d_bam_err.as<int>());
+    NC_LAUNCH_CHECK();
+    NC_CUDA(cudaEventRecord(e2, c->stream));
+    // ---- header: magic, text, references (D2H of the head of the stream, more if the reference list is long)
+    std::vector<uint8_t> head;
+    size_t want = std::min<size_t>((size_t)total, 1 << 20);
+    int64_t first = 0;
+    std::vector<nc_ctx::BamContig> contigs;
+    for (;;) {
+        head.resize(want);
+        NC_CUDA(cudaMemcpyAsync(head.data(), c->d_bam.p, want, cudaMemcpyDeviceToHost, c->stream));
+        NC_CUDA(nc_stream_wait(c));
+        int herr[4] = {0, 0, 0, 0};
+        NC_CUDA(cudaMemcpy(herr, c->d_bam_err.p, sizeof(herr), cudaMemcpyDeviceToHost));
+        if (herr[0]) return fail(c, NC_EINVAL, "BGZF inflate failed for %d block(s) (corrupt or unsupported DEFLATE stream)", herr[0]);
+        const uint8_t* d = head.data();
+        if (memcmp(d, "BAM\1", 4) != 0) return fail(c, NC_EINVAL, "not a BAM file (bad magic)");
+        const int32_t l_text = rd_le<int32_t>(d + 4);
+        bool more = false;
+        size_t off = 8 + (size_t)std::max(l_text, 0);
+        contigs.clear();
+        if (l_text < 0) return fail(c, NC_EINVAL, "truncated BAM header");
+        if (off + 4 > want) more = true;
+        else {
+            const int32_t n_ref = rd_le<int32_t>(d + off);
+            off += 4;
+            if (n_ref < 0) return fail(c, NC_EINVAL, "negative reference count");
+            for (int32_t i = 0; i < n_ref && !more; i++) {
+                if (off + 4 > want) { more = true; break; }
+                const int32_t l_name = rd_le<int32_t>(d + off);
+                if (l_name <= 0) return fail(c, NC_EINVAL, "truncated reference list");
+                if (off + 8 + (size_t)l_name > want) { more = true; break; }
+                nc_ctx::BamContig bc;
+                bc.name.assign((const char*)d + off + 4, (size_t)l_name - 1);
+                bc.length = rd_le<int32_t>(d + off + 4 + l_name);
+                contigs.push_back(bc);
+                off += 8 + (size_t)l_name;
+            }
+        }
+        if (!more) { first = (int64_t)off; break; }
+        if (want >= (size_t)total) return fail(c, NC_EINVAL, "truncated BAM header");
+        want = std::min<size_t>((size_t)total, want * 8);
+    }
+    // ---- record chain, then fields (parallel)
+    const int64_t cap = total / 96 + 4096;
+    NC_CUDA(c->d_bam_recoff.reserve((size_t)cap * 8));
+    bam_walk_kernel<<<1, 32, 0, c->stream>>>(c->d_bam.as<uint8_t>(), first, total, c->d_bam_recoff.as<int64_t>(), cap, c->d_bam_out.as<int64_t>());
+    NC_LAUNCH_CHECK();
+    int64_t wo[2] = {0, 0};
+    NC_CUDA(cudaMemcpyAsync(wo, c->d_bam_out.p, sizeof(wo), cudaMemcpyDeviceToHost, c->stream));
+    NC_CUDA(nc_stream_wait(c));
+    if (!wo[1]) return fail(c, NC_EINVAL, "truncated alignment record");
+    if (wo[0] > cap) return fail(c, NC_EOVERFLOW, "%lld records: more than the device reader's table holds (records shorter than 96 bytes on average)", (long long)wo[0]);
+    const int64_t nrec = wo[0];
+    const size_t nr = (size_t)std::max<int64_t>(nrec, 1);
+    NC_CUDA(c->d_bam_rid.reserve(nr * 4)); NC_CUDA(c->d_bam_pos.reserve(nr * 4)); NC_CUDA(c->d_bam_flag.reserve(nr * 2)); NC_CUDA(c->d_bam_lseq.reserve(nr * 4));
+    NC_CUDA(c->d_bam_ncig.reserve(nr * 4)); NC_CUDA(c->d_bam_nseq.reserve(nr * 4)); NC_CUDA(c->d_bam_cigsrc.reserve(nr * 8)); NC_CUDA(c->d_bam_seqsrc.reserve(nr * 8));
+    NC_CUDA(c->d_bam_hp.reserve(nr)); NC_CUDA(c->d_bam_ps.reserve(nr * 4));
+    std::vector<int32_t> rid((size_t)nrec);
+    std::vector<int8_t> hp((size_t)nrec);
+    if (nrec > 0) {
+        BamFields bf = {c->d_bam_rid.as<int32_t>(), c->d_bam_pos.as<int32_t>(), c->d_bam_flag.as<uint16_t>(), c->d_bam_lseq.as<int32_t>(), c->d_bam_ncig.as<int32_t>(),
+                        c->d_bam_nseq.as<int32_t>(), c->d_bam_cigsrc.as<int64_t>(), c->d_bam_seqsrc.as<int64_t>(), c->d_bam_hp.as<int8_t>(), c->d_bam_ps.as<int32_t>()};
+        bam_fields_kernel<<<(unsigned)div_up(nrec, 128), 128, 0, c->stream>>>(c->d_bam.as<uint8_t>(), c->d_bam_recoff.as<int64_t>(), nrec, bf, c->d_bam_err.as<int>());
+        NC_LAUNCH_CHECK();
+        NC_CUDA(cudaMemcpyAsync(rid.data(), c->d_bam_rid.p, (size_t)nrec * 4, cudaMemcpyDeviceToHost, c->stream));
+        NC_CUDA(cudaMemcpyAsync(hp.data(), c->d_bam_hp.p, (size_t)nrec, cudaMemcpyDeviceToHost, c->stream));
+    }
+    NC_CUDA(cudaEventRecord(e3, c->stream));
+    NC_CUDA(nc_stream_wait(c));
+    int herr[4] = {0, 0, 0, 0};
+    NC_CUDA(cudaMemcpy(herr, c->d_bam_err.p, sizeof(herr), cudaMemcpyDeviceToHost));
+    if (herr[1]) return fail(c, NC_EINVAL, "alignment record fields exceed its size (%d records)", herr[1]);
+    // records are grouped by reference in a coordinate-sorted file (unmapped, refID -1, last)
+    int32_t last = INT32_MIN;
+    for (int64_t i = 0; i < nrec; i++) {
+        const int32_t r = rid[(size_t)i];
+        if (r >= 0 && r < (int32_t)contigs.size()) {
+            if (last != r) {
+                if (contigs[(size_t)r].n > 0 || (last >= 0 && r < last)) return fail(c, NC_EINVAL, "BAM is not coordinate-sorted");
+                contigs[(size_t)r].first = i;
+            }
+            contigs[(size_t)r].n++;
+            if (hp[(size_t)i] == 1 || hp[(size_t)i] == 2) contigs[(size_t)r].n_tagged++;
+        }
+        last = r;
+    }
+    c->bam_contigs.swap(contigs);
+    c->bam_records = nrec; c->bam_bytes = total; c->bam_comp_bytes = (int64_t)f.n;
+    c->bam_ms[0] = (float)(t1 - t0);
+    NC_CUDA(cudaEventElapsedTime(&c->bam_ms[1], e0, e1));
+    NC_CUDA(cudaEventElapsedTime(&c->bam_ms[2], e1, e2));
+    NC_CUDA(cudaEventElapsedTime(&c->bam_ms[3], e2, e3));
+    c->d_bam_comp.release();                                       // the compressed copy is no longer needed
+    c->bam_open = true;
+    *n_contigs = (int32_t)c->bam_contigs.size();
+    return NC_OK;
+}
+
+int nc_bam_device_contig(nc_ctx* c, int32_t i, NcBamDeviceContig* out) {
+    if (!c || !out) return NC_EINVAL;
+    if (!c->bam_open) return fail(c, NC_ESTATE, "nc_bam_device_contig before nc_bam_device_open");
+    if (i < 0 || i >= (int32_t)c->bam_contigs.size()) return fail(c, NC_EINVAL, "contig index %d out of range", i);
+    const auto& bc = c->bam_contigs[(size_t)i];
+    memset(out, 0, sizeof(*out));
+    snprintf(out->name, sizeof(out->name), "%s", bc.name.c_str());
+    out->length = bc.length; out->n_reads = bc.n; out->n_tagged = bc.n_tagged;
+    return NC_OK;
+}
+
+int nc_bam_device_timings(nc_ctx* c, float ms[4], int64_t* compressed_bytes, int64_t* inflated_bytes) {
+    if (!c || !ms) return NC_EINVAL;
+    for (int i = 0; i < 4; i++) ms[i] = c->bam_ms[i];
+    if (compressed_bytes) *compressed_bytes = c->bam_comp_bytes;
+    if (inflated_bytes) *inflated_bytes = c->bam_bytes;
+    return NC_OK;
+}
+
+int nc_bam_device_stage(nc_ctx* c, int32_t i, const uint8_t* ref, int64_t ref_start, int64_t ref_len) {
+    if (!c) return NC_EINVAL;
+    if (!c->bam_open) return fail(c, NC_ESTATE, "nc_bam_device_stage before nc_bam_device_open");
+    if (i < 0 || i >= (int32_t)c->bam_contigs.size()) return fail(c, NC_EINVAL, "contig index %d out of range", i);
+    if (ref_len < 0 || ref_start < 0 || (ref_len > 0 && !ref)) return fail(c, NC_EINVAL, "nc_bam_device_stage: bad reference argument");
+    if (ref_start + ref_len > 0x7fffff00ll) return fail(c, NC_EOVERFLOW, "contig coordinates must fit 31 bits");
+    NC_CUDA(cudaSetDevice(c->device));
+    c->staged = c->decoded = c->scanned = false;
+    c->have_probs = false; c->tags_staged = c->indel_scanned = c->indel_built = false;
+    const auto& bc = c->bam_contigs[(size_t)i];
+    const int64_t n = bc.n, first = bc.first;
+    int rc;
+    NC_CUDA(c->d_pos.reserve((size_t)std::max<int64_t>(n, 1) * 4)); NC_CUDA(c->d_flag.reserve((size_t)std::max<int64_t>(n, 1) * 2));
+    NC_CUDA(c->d_lseq.reserve((size_t)std::max<int64_t>(n, 1) * 4)); NC_CUDA(c->d_hp.reserve((size_t)std::max<int64_t>(n, 1))); NC_CUDA(c->d_ps.reserve((size_t)std::max<int64_t>(n, 1) * 4));
+    NC_CUDA(c->d_cigar_off.reserve((size_t)(n + 1) * 8)); NC_CUDA(c->d_seq_off.reserve((size_t)(n + 1) * 8));
+    int64_t n_cig = 0, n_seq = 0;
+    if (n > 0) {
+        NC_CUDA(cudaMemcpyAsync(c->d_pos.p, c->d_bam_pos.as<int32_t>() + first, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+        NC_CUDA(cudaMemcpyAsync(c->d_flag.p, c->d_bam_flag.as<uint16_t>() + first, (size_t)n * 2, cudaMemcpyDeviceToDevice, c->stream));
+        NC_CUDA(cudaMemcpyAsync(c->d_lseq.p, c->d_bam_lseq.as<int32_t>() + first, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+        NC_CUDA(cudaMemcpyAsync(c->d_hp.p, c->d_bam_hp.as<int8_t>() + first, (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+        NC_CUDA(cudaMemcpyAsync(c->d_ps.p, c->d_bam_ps.as<int32_t>() + first, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+        NC_CUDA(cudaMemsetAsync(c->d_bam_err.as<int>() + 2, 0, sizeof(int), c->stream));
+        bam_sorted_kernel<<<(unsigned)div_up(n, 256), 256, 0, c->stream>>>(c->d_pos.as<int32_t>(), n, c->d_bam_err.as<int>()); NC_LAUNCH_CHECK();
+        if ((rc = device_scan(c, c->d_bam_ncig.as<int32_t>() + first, n, c->d_cigar_off.as<int64_t>()))) return rc;
+        if ((rc = device_scan(c, c->d_bam_nseq.as<int32_t>() + first, n, c->d_seq_off.as<int64_t>()))) return rc;
+        if ((rc = read_i64(c, c->d_cigar_off.as<int64_t>() + n, &n_cig))) return rc;
+        if ((rc = read_i64(c, c->d_seq_off.as<int64_t>() + n, &n_seq))) return rc;
+        int herr = 0;
+        NC_CUDA(cudaMemcpy(&herr, c->d_bam_err.as<int>() + 2, sizeof(int), cudaMemcpyDeviceToHost));
+        if (herr) return fail(c, NC_EINVAL, "reads must be coordinate-sorted");
+    } else {
+        NC_CUDA(cudaMemsetAsync(c->d_cigar_off.p, 0, 8, c->stream)); NC_CUDA(cudaMemsetAsync(c->d_seq_off.p, 0, 8, c->stream));
+    }
+    NC_CUDA(c->d_cigar.reserve((size_t)std::max<int64_t>(n_cig, 4) * 4));
+    NC_CUDA(c->d_seq4.reserve((size_t)std::max<int64_t>(n_seq, 16)));
+    if (n > 0) {
+        BamFields bf = {c->d_bam_rid.as<int32_t>(), c->d_bam_pos.as<int32_t>(), c->d_bam_flag.as<uint16_t>(), c->d_bam_lseq.as<int32_t>(), c->d_bam_ncig.as<int32_t>(),
+                        c->d_bam_nseq.as<int32_t>(), c->d_bam_cigsrc.as<int64_t>(), c->d_bam_seqsrc.as<int64_t>(), c->d_bam_hp.as<int8_t>(), c->d_bam_ps.as<int32_t>()};
+        bam_copy_kernel<<<(unsigned)div_up(n * 32, 128), 128, 0, c->stream>>>(c->d_bam.as<uint8_t>(), first, n, bf, c->d_cigar_off.as<int64_t>(), c->d_seq_off.as<int64_t>(),
+                                                                             c->d_cigar.as<uint32_t>(), c->d_seq4.as<uint8_t>());
+        NC_LAUNCH_CHECK();
+    }
+    if ((rc = upload(c, c->d_ref, ref, (size_t)ref_len))) return rc;
+    c->n_reads = n; c->n_cigar = n_cig; c->n_seq = n_seq; c->ref_start = ref_start; c->ref_len = ref_len;
+    c->staged = true; c->tags_staged = true;
+    return NC_OK;
+}
+
 // ---- development probes (not part of the public header) -------------------------------------------------
 int nc_debug_umma(nc_ctx* c, const void* a_img, int a_bytes, const void* b_img, int b_bytes, const void* prog, int n_ops,
                   int N, int ncols, float* out) {
@@ -1480,6 +1757,25 @@ int nc_debug_saturation(nc_ctx* c, int haploid, int on, int reset, int64_t* coun
     NC_CUDA(nc_stream_wait(c));
     if (count) *count = *c->pin.as<int>();
     if (reset) NC_CUDA(cudaMemsetAsync(M.tc.err.as<int>() + 1, 0, sizeof(int), c->stream));
+    return NC_OK;
+}
+
+// Copies the staged contig (nc_stage_reads / nc_bam_device_stage) back to the host: sizes first (any array pointer may be NULL).
+int nc_debug_fetch_staged(nc_ctx* c, int64_t* n_reads, int64_t* n_cigar, int64_t* n_seq, int32_t* pos, uint16_t* flag, int64_t* cigar_off, uint32_t* cigar,
+                          int64_t* seq_off, int32_t* l_seq, uint8_t* seq4, int8_t* hp, int32_t* ps) {
+    if (!c) return NC_EINVAL;
+    if (!c->staged) return fail(c, NC_ESTATE, "nc_debug_fetch_staged before staging");
+    NC_CUDA(cudaSetDevice(c->device));
+    if (n_reads) *n_reads = c->n_reads;
+    if (n_cigar) *n_cigar = c->n_cigar;
+    if (n_seq) *n_seq = c->n_seq;
+    const size_t n = (size_t)c->n_reads;
+    auto get = [&](void* dst, const DevBuf& src, size_t bytes) -> cudaError_t { return (dst && bytes) ? cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess; };
+    NC_CUDA(get(pos, c->d_pos, n * 4)); NC_CUDA(get(flag, c->d_flag, n * 2)); NC_CUDA(get(cigar_off, c->d_cigar_off, (n + 1) * 8));
+    NC_CUDA(get(cigar, c->d_cigar, (size_t)c->n_cigar * 4)); NC_CUDA(get(seq_off, c->d_seq_off, (n + 1) * 8)); NC_CUDA(get(l_seq, c->d_lseq, n * 4));
+    NC_CUDA(get(seq4, c->d_seq4, (size_t)c->n_seq));
+    if (c->tags_staged) { NC_CUDA(get(hp, c->d_hp, n)); NC_CUDA(get(ps, c->d_ps, n * 4)); }
+    NC_CUDA(nc_stream_wait(c));
     return NC_OK;
 }
 

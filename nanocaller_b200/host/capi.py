@@ -17,7 +17,8 @@ EXPORTS = ["nc_abi_version", "nc_create", "nc_destroy", "nc_last_error", "nc_syn
            "nc_device_sm_count", "nc_event_record", "nc_event_elapsed_ms", "nc_invalidate_decode", "nc_stage_reads", "nc_decode_reads", "nc_snp_scan", "nc_snp_fetch", "nc_snp_fetch_range", "nc_indel_fetch_range",
            "nc_load_snp_weights", "nc_snp_forward", "nc_snp_fetch_probs", "nc_snp_model_forward", "nc_snp_device_buffers",
            "nc_load_indel_weights", "nc_indel_model_forward", "nc_stage_tags", "nc_indel_scan", "nc_indel_fetch_variants",
-           "nc_indel_build", "nc_indel_fetch", "nc_indel_forward", "nc_indel_fetch_probs", "nc_indel_fetch_alleles", "nc_get_indel_timings", "nc_nw_trace", "nc_allele_predict_batch",
+           "nc_indel_build", "nc_indel_fetch", "nc_indel_forward", "nc_indel_fetch_probs", "nc_indel_fetch_alleles",
+           "nc_bam_device_open", "nc_bam_device_contig", "nc_bam_device_stage", "nc_bam_device_close", "nc_bam_device_timings", "nc_get_indel_timings", "nc_nw_trace", "nc_allele_predict_batch",
            "nc_format_snp_records"]
 
 
@@ -43,6 +44,11 @@ class NcIndelTimings(ctypes.Structure):
     _fields_ = [("scan_ms", ctypes.c_float), ("reads_ms", ctypes.c_float), ("align_ms", ctypes.c_float), ("msa_ms", ctypes.c_float),
                 ("cnn_ms", ctypes.c_float), ("allele_ms", ctypes.c_float), ("reserved", ctypes.c_float * 2), ("n_sites", ctypes.c_uint64), ("n_entries", ctypes.c_uint64),
                 ("scan_bytes", ctypes.c_uint64), ("build_bytes", ctypes.c_uint64)]
+
+
+class NcBamDeviceContig(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 256), ("length", ctypes.c_int32), ("reserved", ctypes.c_int32), ("n_reads", ctypes.c_int64),
+                ("n_tagged", ctypes.c_int64)]
 
 
 VARIANT_DTYPE = np.dtype([("key", "<i4"), ("type", "<i4"), ("chunk", "<i4"), ("src", "<i4")])
@@ -111,6 +117,11 @@ def load_library():
     lib.nc_indel_fetch_probs.argtypes = [vp, vp]
     lib.nc_indel_fetch_alleles.argtypes = [vp, vp]
     lib.nc_get_indel_timings.argtypes = [vp, ctypes.POINTER(NcIndelTimings)]
+    lib.nc_bam_device_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(i32)]
+    lib.nc_bam_device_contig.argtypes = [vp, i32, ctypes.POINTER(NcBamDeviceContig)]
+    lib.nc_bam_device_stage.argtypes = [vp, i32, vp, i64, i64]
+    lib.nc_bam_device_close.argtypes = [vp]
+    lib.nc_bam_device_timings.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 4), ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.nc_nw_trace.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp, i32]
     for name in EXPORTS:
         if name not in ("nc_destroy", "nc_last_error"):
@@ -239,6 +250,47 @@ class Context:
         ps = np.ascontiguousarray(ps, np.int32)
         self._keep_tags = (hp, ps)
         self._check(self._lib.nc_stage_tags(self._h, _p(hp), _p(ps)))
+
+    # ---- device-side BAM input
+    def bam_device_open(self, path):
+        """Inflate + parse `path` on the GPU -> list of (name, length, n_reads, n_tagged) in header order."""
+        n = ctypes.c_int32(0)
+        self._check(self._lib.nc_bam_device_open(self._h, os.fsencode(path), ctypes.byref(n)))
+        out = []
+        for i in range(n.value):
+            c = NcBamDeviceContig()
+            self._check(self._lib.nc_bam_device_contig(self._h, i, ctypes.byref(c)))
+            out.append((c.name.decode(), int(c.length), int(c.n_reads), int(c.n_tagged)))
+        return out
+
+    def bam_device_stage(self, index, ref, ref_start=0):
+        ref = np.ascontiguousarray(ref, np.uint8)
+        self._keep = (ref,)
+        self._check(self._lib.nc_bam_device_stage(self._h, int(index), _p(ref), int(ref_start), len(ref)))
+
+    def bam_device_close(self):
+        self._check(self._lib.nc_bam_device_close(self._h))
+
+    def bam_device_timings(self):
+        ms = (ctypes.c_float * 4)()
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        self._check(self._lib.nc_bam_device_timings(self._h, ctypes.byref(ms), ctypes.byref(a), ctypes.byref(b)))
+        return {"host_ms": ms[0], "h2d_ms": ms[1], "inflate_ms": ms[2], "records_ms": ms[3], "compressed_bytes": a.value, "inflated_bytes": b.value}
+
+    def fetch_staged(self):
+        """The staged contig back on the host (validation): dict of the BAM-native arrays."""
+        lib = self._lib
+        i64 = ctypes.c_int64
+        lib.nc_debug_fetch_staged.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(i64)] * 3 + [ctypes.c_void_p] * 9
+        lib.nc_debug_fetch_staged.restype = ctypes.c_int
+        n, nc_, ns = i64(0), i64(0), i64(0)
+        self._check(lib.nc_debug_fetch_staged(self._h, ctypes.byref(n), ctypes.byref(nc_), ctypes.byref(ns), *([None] * 9)))
+        d = dict(pos=np.empty(n.value, np.int32), flag=np.empty(n.value, np.uint16), cigar_off=np.empty(n.value + 1, np.int64),
+                 cigar=np.empty(nc_.value, np.uint32), seq_off=np.empty(n.value + 1, np.int64), l_seq=np.empty(n.value, np.int32),
+                 seq4=np.empty(ns.value, np.uint8), hp=np.zeros(n.value, np.int8), ps=np.zeros(n.value, np.int32))
+        self._check(lib.nc_debug_fetch_staged(self._h, None, None, None, _p(d["pos"]), _p(d["flag"]), _p(d["cigar_off"]), _p(d["cigar"]) if nc_.value else None,
+                                              _p(d["seq_off"]), _p(d["l_seq"]), _p(d["seq4"]) if ns.value else None, _p(d["hp"]), _p(d["ps"])))
+        return d
 
     # ---- indel feature path
     def indel_scan(self, params, chunks, bed=None):

@@ -11,7 +11,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 STRUCTS = {
-    "nanocaller_b200.h": ["NcSnpParams", "NcChunk", "NcSiteMeta", "NcTimings", "NcIndelParams", "NcIndelVariant", "NcIndelSiteMeta", "NcIndelTimings"],
+    "nanocaller_b200.h": ["NcSnpParams", "NcChunk", "NcSiteMeta", "NcTimings", "NcIndelParams", "NcIndelVariant", "NcIndelSiteMeta", "NcIndelTimings", "NcBamDeviceContig"],
     "nanocaller_b200_io.h": ["NcBamContig"],
 }
 
@@ -62,7 +62,7 @@ def test_struct_layouts_match_the_headers(tmp_path):
     from nanocaller_b200.host import bamio, capi
     want = _c_layout(tmp_path)
     mirrors = {"NcSnpParams": capi.NcSnpParams, "NcChunk": capi.CHUNK_DTYPE, "NcSiteMeta": capi.META_DTYPE, "NcTimings": capi.NcTimings,
-               "NcIndelParams": capi.NcIndelParams, "NcIndelVariant": capi.VARIANT_DTYPE, "NcIndelSiteMeta": capi.INDEL_META_DTYPE, "NcIndelTimings": capi.NcIndelTimings,
+               "NcIndelParams": capi.NcIndelParams, "NcIndelVariant": capi.VARIANT_DTYPE, "NcIndelSiteMeta": capi.INDEL_META_DTYPE, "NcIndelTimings": capi.NcIndelTimings, "NcBamDeviceContig": capi.NcBamDeviceContig,
                "NcBamContig": bamio.NcBamContig}
     assert sorted(mirrors) == sorted(want)
     for name, m in mirrors.items():
