@@ -71,6 +71,9 @@ def build_parser():
     p.add_argument("--write_phased_bam", action="store_true", default=False,
                    help="also write intermediate_phase_files/{contig}.phased.bam (indelCaller.py:244): the contig's records copied whole with "
                         "the HP / PS tags of the phasing step. The indel stage does not need the file (the tags are staged from memory).")
+    p.add_argument("--host_bam_reader", action="store_true", default=False,
+                   help="inflate and decode the BAM on the host (libnc_bamio, zlib) instead of on the GPU. The device reader is the default; it "
+                        "needs the inflated file to fit in device memory and falls back to the host reader by itself when it does not.")
     p.add_argument("--decompose_indels", action="store_true", default=False,
                    help="normalise the indel records like the reference's `rtg vcfdecompose | rtg vcffilter --non-snps-only` step "
                         "(indelCaller.py:391) with this package's own rule set (host/vcf_decompose.py); the records as the indel stage "
@@ -212,11 +215,13 @@ def _phase_stage(args, regions, chrom_list, out):
             phased_lines += lines_c
             continue
         rs = sources.resolve(args.bam, chrom)
-        if not args.phase and int((rs.hp > 0).sum()) > 0:
+        tagged = rs.n_tagged if isinstance(rs, sources.DeviceContig) else int((rs.hp > 0).sum())
+        if not args.phase and tagged > 0:
             print("\n%s: %s: reads are already haplotagged; HP/PS tags of the BAM are used (give --phase to re-phase)."
                   % (datetime.datetime.now(), chrom), flush=True)
             phased_lines += lines_c
             continue
+        rs = sources.host_reads(args.bam, chrom)                  # phasing walks the reads on the host
         new_lines, st = phasing.phase_snp_records(lines_c, rs, args.phase_qual_score, supplementary=args.supplementary)
         phased_lines += new_lines
         pstats[chrom] = st
@@ -244,8 +249,19 @@ def run(args):
             f.write("{}: {}\n".format(k, v))
     contig_lengths = _contig_lengths(args.bam)                    # utils.py:9-50 asks the BAM header, not the FASTA
     regions = getattr(args, "_regions", None) or get_regions_list(args, contig_lengths)     # _regions: one rank's share (host/multi.py)
+    ctx = snp_pileups.context(args.device)                        # fails loudly without an sm_100 device
     if not args.bam.startswith("mem://"):                         # mem://: an in-memory source registered by the caller (host/sources.py)
-        bamio.open_alignment(args.bam, args.ref, contigs={r[0] for r in regions})     # only the contigs that will be called
+        wanted = {r[0] for r in regions}                          # only the contigs that will be called
+        opened = False
+        if not args.host_bam_reader and not getattr(args, "_read_windows", None):
+            from .host import capi
+            try:                                                  # BGZF inflate + record decoding on the GPU: only compressed bytes cross PCIe
+                bamio.open_alignment_device(ctx, args.bam, args.ref, contigs=wanted)
+                opened = True
+            except capi.NcError as e:
+                print("\n%s: device BAM reader not used (%s); reading on the host." % (datetime.datetime.now(), e), flush=True)
+        if not opened:
+            bamio.open_alignment(args.bam, args.ref, contigs=wanted)
     if getattr(args, "_read_windows", None):                      # one rank of a chunk-sharded run (host/multi.py): keep its part of every contig
         from .host import sources
         sources.restrict(args.bam, args._read_windows)

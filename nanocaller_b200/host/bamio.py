@@ -430,6 +430,27 @@ def bam_contigs(path):
         return out
 
 
+def open_alignment_device(ctx, sam_path, fasta_path, contigs=None):
+    """Like `open_alignment`, but the BAM is inflated and decoded on the GPU (nc_bam_device_open): registers `DeviceContig`s.
+    Raises capi.NcError when the file does not fit the device budget or is not a BGZF BAM (the caller falls back to the host reader)."""
+    from . import sources
+    if not os.path.exists(sam_path):
+        raise FileNotFoundError(sam_path)
+    table = ctx.bam_device_open(sam_path)
+    names = [t[0] for t in table if contigs is None or t[0] in contigs]
+    fasta = read_fasta(fasta_path, set(names)) if fasta_path and os.path.exists(fasta_path) else {}
+    out = []
+    for i, (name, length, n_reads, n_tagged) in enumerate(table):
+        if contigs is not None and name not in contigs:
+            continue
+        ref = fasta.get(name)
+        if ref is None:
+            ref = np.full(length, ord("N"), np.uint8)
+        out.append(sources.DeviceContig(ctx, sam_path, i, name, ref, length, n_reads, n_tagged))
+    sources._REGISTRY[sam_path] = {c.chrom: c for c in out}
+    return out
+
+
 def open_alignment(sam_path, fasta_path, native=True, contigs=None):
     """Parse `sam_path` (BAM) and `fasta_path` once and register the contigs (all, or the named ones) as an alignment source."""
     from . import sources

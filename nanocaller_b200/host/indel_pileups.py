@@ -89,7 +89,8 @@ def scan_build(ctx, rs, dct, chunks, bed=None, haploid=False, want_tensors=True)
     """Pass 1 (scan), the dict semantics of `variants`, pass 2 + msa (build) for a list of chunk dicts of one contig.
     -> (meta, tensors or None, cns); with want_tensors=False the tensors stay on the device for `Context.indel_forward`."""
     snp_pileups.stage(ctx, rs)
-    ctx.stage_tags(rs.hp, rs.ps)
+    if not isinstance(rs, sources.DeviceContig):          # a device-decoded contig brings its HP / PS tags along
+        ctx.stage_tags(rs.hp, rs.ps)
     P = capi.indel_params(dct, haploid)
     ch = [(c["start"], c["end"]) for c in chunks]
     variants = ctx.indel_scan(P, ch, bed)

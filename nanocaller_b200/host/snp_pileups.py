@@ -30,7 +30,10 @@ def stage(ctx, rs):
     """Upload a contig unless it is the one already staged on this context."""
     key = id(ctx)
     if _staged.get(key) is not rs:
-        ctx.stage_reads(rs)
+        if isinstance(rs, sources.DeviceContig):          # reads already on the device (nc_bam_device_open): no host copy exists
+            ctx.bam_device_stage(rs.index, rs.ref)
+        else:
+            ctx.stage_reads(rs)
         _staged[key] = rs
 
 

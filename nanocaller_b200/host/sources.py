@@ -38,6 +38,30 @@ def release(path, chrom):
     _REGISTRY.get(path, {}).pop(chrom, None)
 
 
+class DeviceContig:
+    """A contig whose reads were inflated and decoded on the GPU (Context.bam_device_open): the host only holds the reference
+    bytes; staging is a device-to-device step (Context.bam_device_stage).  `materialise()` swaps in a host ReadSet (native
+    reader) for the steps that need the reads on the host: phasing of untagged reads, chunk-window sharding."""
+
+    def __init__(self, ctx, path, index, chrom, ref, length, n_reads, n_tagged):
+        self.ctx, self.path, self.index, self.chrom, self.ref = ctx, path, index, chrom, ref
+        self.contig_len, self.n, self.n_tagged = int(length), int(n_reads), int(n_tagged)
+
+    def materialise(self):
+        from . import bamio
+        fasta = {self.chrom: self.ref}
+        sets, _ = bamio.read_bam_native(self.path, fasta, contigs={self.chrom})
+        rs = sets[0]
+        _REGISTRY[self.path][self.chrom] = rs
+        return rs
+
+
+def host_reads(sam_path, chrom):
+    """`resolve`, but always a host ReadSet."""
+    rs = resolve(sam_path, chrom)
+    return rs.materialise() if isinstance(rs, DeviceContig) else rs
+
+
 def register_bed(path, intervals):
     """intervals: {chrom: [(start, end), ...]} — stands for a tabix-indexed exclude BED."""
     _BEDS[path] = intervals
@@ -76,7 +100,7 @@ def restrict(sam_path, windows):
     reg = _REGISTRY[sam_path]
     for chrom, (lo0, hi0) in windows.items():
         if chrom in reg:
-            reg[chrom] = resolve(sam_path, chrom).window(lo0, hi0)
+            reg[chrom] = host_reads(sam_path, chrom).window(lo0, hi0)
 
 
 def contigs(sam_path):

@@ -72,7 +72,7 @@ def test_every_reference_flag_is_accepted_with_the_reference_default():
     assert len(want) > 30 and set(want) <= set(acts), sorted(set(want) - set(acts))
     for k, v in want.items():
         assert acts[k].default == v, (k, acts[k].default, v)
-    assert set(acts) - set(want) - {"--help"} == {"--device", "--nanocaller_src", "--write_phased_bam", "--decompose_indels"}
+    assert set(acts) - set(want) - {"--help"} == {"--device", "--nanocaller_src", "--write_phased_bam", "--decompose_indels", "--host_bam_reader"}
 
 
 def test_preset_table_equals_the_reference():
