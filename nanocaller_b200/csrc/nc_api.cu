@@ -1525,9 +1525,8 @@ int nc_bam_device_open(nc_ctx* c, const char* path, int32_t* n_contigs) {
     NC_CUDA(cudaEventRecord(e0, c->stream));
     NC_CUDA(cudaMemcpyAsync(c->d_bam_comp.p, pin, blk_at + blocks.size() * sizeof(BgzfBlock), cudaMemcpyHostToDevice, c->stream));
     NC_CUDA(cudaEventRecord(e1, c->stream));
-    NC_CUDA(cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kInflSmem));
     const int64_t nb = (int64_t)blocks.size();
-    bgzf_inflate_kernel<<<(unsigned)div_up(nb, kInflThreads), kInflThreads, kInflSmem, c->stream>>>(
+    bgzf_inflate_kernel<<<(unsigned)div_up(nb, kInflWarps), kInflWarps * 32, 0, c->stream>>>(
         c->d_bam_comp.as<uint8_t>(), reinterpret_cast<const BgzfBlock*>(c->d_bam_comp.as<uint8_t>() + blk_at), nb, c->d_bam.as<uint8_t>(), c->d_bam_err.as<int>());
     NC_LAUNCH_CHECK();
     NC_CUDA(cudaEventRecord(e2, c->stream));

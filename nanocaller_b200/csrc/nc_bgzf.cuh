@@ -3,9 +3,11 @@
 // leaves the path.  Replaces what the reference gets from pysam / htslib when it opens the alignment file in every call
 // (nanocaller_src/generate_SNP_pileups.py:134-156, generate_indel_pileups.py:147-185).
 //
-//   bgzf_inflate_kernel   one THREAD per BGZF block (blocks are independent raw-DEFLATE members of <= 64 KB, RFC 1951): stored,
-//                         fixed and dynamic Huffman blocks; canonical-code decoding with per-thread count / symbol tables in shared
-//                         memory (the layout of Mark Adler's puff.c restated), LZ77 copies inside the block's own output.
+//   bgzf_inflate_kernel   one WARP per BGZF block (blocks are independent raw-DEFLATE members of <= 64 KB, RFC 1951): stored, fixed
+//                         and dynamic Huffman blocks.  Lane 0 owns the bit stream (canonical-code tables as in Mark Adler's puff.c plus
+//                         a 9-bit lookup table, all in shared memory) and decodes 32 symbols at a time; the warp writes them out:
+//                         literals in one step, LZ77 matches as cooperative copies.  (A first version with one thread per block ran at
+//                         4.5 GB/s: every byte of a match was a dependent store -> load round trip through L2.)
 //   bam_walk_kernel       the record chain (every record starts with its own size, SAM spec 4.2): one thread follows it and writes
 //                         the record offsets; everything after that is parallel over records.
 //   bam_fields_kernel     thread per record: core fields, HP / PS aux tags, the CG:B,I long-CIGAR convention.
@@ -17,10 +19,16 @@ namespace nc {
 
 struct BgzfBlock { int64_t in_off; int32_t in_len; int32_t out_len; int64_t out_off; };     // = NcBgzfBlock of the C header
 
-constexpr int kInflThreads = 64;
-// per thread, all in shared memory and indexed [entry][thread]: literal/length counts (16) and symbols (288), distance counts (16)
-// and symbols (32), code lengths while a dynamic header is read (320 bytes)
-constexpr int kInflSmem = kInflThreads * ((16 + 288 + 16 + 32) * 2 + 320);
+constexpr int kInflWarps = 4;                 // warps (= BGZF blocks in flight) per CTA
+constexpr int kLutBits = 9;                   // primary lookup: codes of up to 9 bits resolve with one shared-memory read
+// per warp, in shared memory: canonical-code tables (count per length, symbols by (length, value)) for the literal/length and the
+// distance code, code lengths while a dynamic header is read, the two lookup tables, and a queue of 32 decoded symbols
+struct InflWarp {
+    uint16_t lcnt[16], lsym[288], dcnt[16], dsym[32];
+    uint16_t llut[1 << kLutBits], dlut[1 << kLutBits];       // (symbol << 4) | code length, 0 = longer code: walk the canonical table
+    uint8_t lens[320];
+    uint16_t q_len[32], q_dist[32];                          // queue: dist == 0 -> literal byte in q_len
+};
 
 __constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
 __constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -43,119 +51,211 @@ struct BitReader {
 };
 
 // canonical Huffman table from code lengths len[0..n): cnt[l] = codes of length l, sym = symbols ordered by (length, value).
-// Returns 0 for a complete code, > 0 incomplete, < 0 over-subscribed (puff.c `construct`).
+// Returns 0 for a complete code, > 0 incomplete, < 0 over-subscribed (the construction of Mark Adler's puff.c).  One thread.
 template <class LenAt>
-__device__ __forceinline__ int huff_build(uint16_t* cnt, uint16_t* sym, int stride, LenAt len_at, int n) {
-    for (int l = 0; l <= 15; l++) cnt[l * stride] = 0;
-    for (int s = 0; s < n; s++) cnt[len_at(s) * stride]++;
+__device__ __forceinline__ int huff_build(uint16_t* cnt, uint16_t* sym, LenAt len_at, int n) {
+    for (int l = 0; l <= 15; l++) cnt[l] = 0;
+    for (int s = 0; s < n; s++) cnt[len_at(s)]++;
     if (cnt[0] == n) return 0;
     int left = 1;
-    for (int l = 1; l <= 15; l++) { left <<= 1; left -= cnt[l * stride]; if (left < 0) return left; }
+    for (int l = 1; l <= 15; l++) { left <<= 1; left -= cnt[l]; if (left < 0) return left; }
     uint16_t offs[16];
     offs[1] = 0;
-    for (int l = 1; l < 15; l++) offs[l + 1] = offs[l] + cnt[l * stride];
-    for (int s = 0; s < n; s++) { const int l = len_at(s); if (l) sym[(offs[l]++) * stride] = (uint16_t)s; }
+    for (int l = 1; l < 15; l++) offs[l + 1] = offs[l] + cnt[l];
+    for (int s = 0; s < n; s++) { const int l = len_at(s); if (l) sym[offs[l]++] = (uint16_t)s; }
     return left;
 }
-__device__ __forceinline__ int huff_decode(BitReader& br, const uint16_t* cnt, const uint16_t* sym, int stride) {
+// lookup table of the codes of up to kLutBits bits (DEFLATE packs codes most significant bit first into an LSB-first stream, so
+// the table is indexed by the bit-reversed code); all lanes of the warp fill it
+__device__ __forceinline__ void huff_lut(const uint16_t* cnt, const uint16_t* sym, uint16_t* lut, int lane) {
+    for (int i = lane; i < (1 << kLutBits); i += 32) lut[i] = 0;
+    __syncwarp();
+    int total = 0;
+    for (int l = 1; l <= kLutBits; l++) total += cnt[l];
+    for (int i = lane; i < total; i += 32) {
+        int l = 1, first = 0, index = 0;                  // canonical code of the i-th symbol in (length, value) order
+        while (i >= index + cnt[l]) { index += cnt[l]; first = (first + cnt[l]) << 1; l++; }
+        const uint32_t code = (uint32_t)(first + (i - index));
+        const uint32_t rev = __brev(code) >> (32 - l);
+        const uint16_t e = (uint16_t)((sym[i] << 4) | l);
+        for (uint32_t k = rev; k < (1u << kLutBits); k += 1u << l) lut[k] = e;
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ int huff_decode(BitReader& br, const uint16_t* cnt, const uint16_t* sym, const uint16_t* lut) {
+    const uint32_t e = lut[(uint32_t)br.buf & ((1u << kLutBits) - 1u)];
+    if (e) { const int l = (int)(e & 15u); br.buf >>= l; br.cnt -= l; return (int)(e >> 4); }
     int code = 0, first = 0, index = 0;
 #pragma unroll 1
     for (int l = 1; l <= 15; l++) {
         code |= (int)(br.buf & 1ull); br.buf >>= 1; br.cnt--;
-        const int count = cnt[l * stride];
-        if (code - count < first) return sym[(index + (code - first)) * stride];
+        const int count = cnt[l];
+        if (code - count < first) return sym[index + (code - first)];
         index += count; first += count; first <<= 1; code <<= 1;
     }
     return -1;
 }
 
-// err[0] = number of blocks that failed to decode
-__global__ void __launch_bounds__(kInflThreads) bgzf_inflate_kernel(const uint8_t* __restrict__ in, const BgzfBlock* __restrict__ blocks, int64_t n_blocks,
-                                                                    uint8_t* __restrict__ out, int* __restrict__ err) {
-    extern __shared__ __align__(16) uint8_t s_infl[];
-    const int t = threadIdx.x, S = kInflThreads;
-    uint16_t* lcnt = reinterpret_cast<uint16_t*>(s_infl) + t;                  // [16][S]
-    uint16_t* lsym = reinterpret_cast<uint16_t*>(s_infl) + 16 * S + t;         // [288][S]
-    uint16_t* dcnt = reinterpret_cast<uint16_t*>(s_infl) + (16 + 288) * S + t; // [16][S]
-    uint16_t* dsym = reinterpret_cast<uint16_t*>(s_infl) + (16 + 288 + 16) * S + t;   // [32][S]
-    uint8_t* lens = s_infl + (size_t)(16 + 288 + 16 + 32) * 2 * S + t;         // [320][S]
-    const int64_t b = (int64_t)blockIdx.x * S + t;
+// One WARP per BGZF block: lane 0 reads the bit stream and decodes up to 32 symbols into a queue, then all lanes write them out —
+// literals in one parallel step, every match as a cooperative copy (back-references with distance < length repeat the pattern).
+// err[0] = number of blocks that failed to decode.
+__global__ void __launch_bounds__(kInflWarps * 32) bgzf_inflate_kernel(const uint8_t* __restrict__ in, const BgzfBlock* __restrict__ blocks, int64_t n_blocks,
+                                                                       uint8_t* __restrict__ out, int* __restrict__ err) {
+    __shared__ InflWarp s_w[kInflWarps];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    InflWarp& W = s_w[wib];
+    const uint32_t full = 0xffffffffu;
+    const int64_t b = (int64_t)blockIdx.x * kInflWarps + wib;
     if (b >= n_blocks) return;
     const BgzfBlock bk = blocks[b];
     uint8_t* o = out + bk.out_off;
     const int out_len = bk.out_len;
     BitReader br;
     br.p = in + bk.in_off; br.end = br.p + bk.in_len; br.buf = 0; br.cnt = 0;
-    int op = 0;
+    int op = 0;                                            // warp-uniform output position
+    int state = 0;                                         // lane 0: 0 = expect a block header, 1 = inside a Huffman block; broadcast below
     bool bad = false, last = false;
-    while (!last && !bad) {
-        br.refill();
-        last = br.bits(1) != 0;
-        const uint32_t type = br.bits(2);
-        if (type == 0) {
-            br.bits(br.cnt & 7);                                               // to the byte boundary
-            br.refill();
-            const uint32_t len = br.bits(16), nlen = br.bits(16);
-            if ((len ^ 0xFFFFu) != nlen) { bad = true; break; }
-            const uint8_t* src = br.p - (br.cnt >> 3);                         // bytes still sitting in the bit buffer are given back
-            if (src + len > br.end || op + (int)len > out_len) { bad = true; break; }
-            for (uint32_t i = 0; i < len; i++) o[op + i] = __ldg(src + i);
-            op += (int)len;
-            br.p = src + len; br.buf = 0; br.cnt = 0;
+    for (;;) {
+        // ---- lane 0: headers and up to 32 symbols
+        int nq = 0, stored_len = -1;
+        const uint8_t* stored_src = nullptr;
+        int need_tables = 0;                               // 1: fixed code, 2: dynamic code lengths are in W.lens
+        int nlen = 0, ndist = 0;
+        if (lane == 0 && !bad) {
+            if (state == 0) {
+                if (last) state = 3;                       // done
+                else {
+                    br.refill();
+                    last = br.bits(1) != 0;
+                    const uint32_t type = br.bits(2);
+                    if (type == 0) {
+                        br.bits(br.cnt & 7);               // to the byte boundary
+                        br.refill();
+                        const uint32_t len = br.bits(16), nl = br.bits(16);
+                        const uint8_t* src = br.p - (br.cnt >> 3);     // bytes still sitting in the bit buffer are given back
+                        if ((len ^ 0xFFFFu) != nl || src + len > br.end || op + (int)len > out_len) bad = true;
+                        else { stored_len = (int)len; stored_src = src; br.p = src + len; br.buf = 0; br.cnt = 0; }
+                    } else if (type == 1) { need_tables = 1; state = 1; }
+                    else if (type == 2) {
+                        br.refill();
+                        nlen = (int)br.bits(5) + 257; ndist = (int)br.bits(5) + 1;
+                        const int ncode = (int)br.bits(4) + 4;
+                        if (nlen > 286 || ndist > 30) bad = true;
+                        else {
+                            for (int i = 0; i < 19; i++) W.lens[i] = 0;
+                            for (int i = 0; i < ncode; i++) { br.refill(); W.lens[c_clen_order[i]] = (uint8_t)br.bits(3); }
+                            // the code-length code uses the distance table's slots while the lengths are read (no lookup table: 19 symbols)
+                            if (huff_build(W.dcnt, W.dsym, [&](int s) { return (int)W.lens[s]; }, 19) != 0) bad = true;
+                            int idx = 0;
+                            while (idx < nlen + ndist && !bad) {
+                                br.refill();
+                                int code = 0, first = 0, index = 0, sy = -1;
+                                for (int l = 1; l <= 7; l++) {
+                                    code |= (int)(br.buf & 1ull); br.buf >>= 1; br.cnt--;
+                                    const int count = W.dcnt[l];
+                                    if (code - count < first) { sy = W.dsym[index + (code - first)]; break; }
+                                    index += count; first += count; first <<= 1; code <<= 1;
+                                }
+                                if (sy < 0) { bad = true; break; }
+                                if (sy < 16) { W.lens[idx++] = (uint8_t)sy; continue; }
+                                int prev = 0, rep;
+                                if (sy == 16) { if (idx == 0) { bad = true; break; } prev = W.lens[idx - 1]; rep = 3 + (int)br.bits(2); }
+                                else if (sy == 17) rep = 3 + (int)br.bits(3);
+                                else rep = 11 + (int)br.bits(7);
+                                if (idx + rep > nlen + ndist) { bad = true; break; }
+                                while (rep--) W.lens[idx++] = (uint8_t)prev;
+                            }
+                            if (!bad && W.lens[256] == 0) bad = true;
+                            if (!bad) { need_tables = 2; state = 1; }
+                        }
+                    } else bad = true;
+                }
+            }
+        }
+        // ---- warp: broadcast what lane 0 found
+        bad = __shfl_sync(full, (int)bad, 0) != 0;
+        if (bad) break;
+        state = __shfl_sync(full, state, 0);
+        if (state == 3) break;
+        stored_len = __shfl_sync(full, stored_len, 0);
+        if (stored_len >= 0) {
+            const uint64_t sp = __shfl_sync(full, (uint64_t)(uintptr_t)stored_src, 0);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>((uintptr_t)sp);
+            for (int i = lane; i < stored_len; i += 32) o[op + i] = __ldg(src + i);
+            op += stored_len;
+            __syncwarp();
             continue;
         }
-        if (type == 3) { bad = true; break; }
-        if (type == 1) {
-            huff_build(lcnt, lsym, S, [](int s) { return s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8; }, 288);
-            huff_build(dcnt, dsym, S, [](int) { return 5; }, 30);
-        } else {
-            br.refill();
-            const int nlen = (int)br.bits(5) + 257, ndist = (int)br.bits(5) + 1, ncode = (int)br.bits(4) + 4;
-            if (nlen > 286 || ndist > 30) { bad = true; break; }
-            for (int i = 0; i < 19; i++) lens[i * S] = 0;
-            for (int i = 0; i < ncode; i++) { br.refill(); lens[c_clen_order[i] * S] = (uint8_t)br.bits(3); }
-            // the code-length code lives in the distance table slots while the lengths are read
-            if (huff_build(dcnt, dsym, S, [&](int s) { return (int)lens[s * S]; }, 19) != 0) { bad = true; break; }
-            int idx = 0;
-            while (idx < nlen + ndist && !bad) {
-                br.refill();
-                const int sy = huff_decode(br, dcnt, dsym, S);
-                if (sy < 0) { bad = true; break; }
-                if (sy < 16) { lens[(idx++) * S] = (uint8_t)sy; continue; }
-                int prev = 0, rep;
-                if (sy == 16) { if (idx == 0) { bad = true; break; } prev = lens[(idx - 1) * S]; rep = 3 + (int)br.bits(2); }
-                else if (sy == 17) rep = 3 + (int)br.bits(3);
-                else rep = 11 + (int)br.bits(7);
-                if (idx + rep > nlen + ndist) { bad = true; break; }
-                while (rep--) lens[(idx++) * S] = (uint8_t)prev;
+        need_tables = __shfl_sync(full, need_tables, 0);
+        if (need_tables) {
+            if (lane == 0) {
+                if (need_tables == 1) {
+                    huff_build(W.lcnt, W.lsym, [](int s) { return s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8; }, 288);
+                    huff_build(W.dcnt, W.dsym, [](int) { return 5; }, 30);
+                } else {
+                    const int el = huff_build(W.lcnt, W.lsym, [&](int s) { return (int)W.lens[s]; }, nlen);
+                    if (el < 0 || (el > 0 && nlen - W.lcnt[0] != 1)) bad = true;
+                    const int ed = huff_build(W.dcnt, W.dsym, [&](int s) { return (int)W.lens[nlen + s]; }, ndist);
+                    if (ed < 0 || (ed > 0 && ndist - W.dcnt[0] != 1)) bad = true;
+                }
             }
+            bad = __shfl_sync(full, (int)bad, 0) != 0;
             if (bad) break;
-            if (lens[256 * S] == 0) { bad = true; break; }
-            const int el = huff_build(lcnt, lsym, S, [&](int s) { return (int)lens[s * S]; }, nlen);
-            if (el < 0 || (el > 0 && nlen - lcnt[0] != 1)) { bad = true; break; }
-            const int ed = huff_build(dcnt, dsym, S, [&](int s) { return (int)lens[(nlen + s) * S]; }, ndist);
-            if (ed < 0 || (ed > 0 && ndist - dcnt[0] != 1)) { bad = true; break; }
+            __syncwarp();
+            huff_lut(W.lcnt, W.lsym, W.llut, lane);
+            huff_lut(W.dcnt, W.dsym, W.dlut, lane);
         }
-        // ---- the block's symbols
-        for (;;) {
-            br.refill();
-            int sy = huff_decode(br, lcnt, lsym, S);
-            if (sy < 0) { bad = true; break; }
-            if (sy < 256) { if (op >= out_len) { bad = true; break; } o[op++] = (uint8_t)sy; continue; }
-            if (sy == 256) break;
-            sy -= 257;
-            if (sy >= 29) { bad = true; break; }
-            br.refill();
-            const int len = c_len_base[sy] + (int)br.bits(c_len_extra[sy]);
-            const int ds = huff_decode(br, dcnt, dsym, S);
-            if (ds < 0 || ds >= 30) { bad = true; break; }
-            br.refill();
-            const int dist = c_dist_base[ds] + (int)br.bits(c_dist_extra[ds]);
-            if (dist > op || op + len > out_len) { bad = true; break; }
-            for (int i = 0; i < len; i++) { o[op] = o[op - dist]; op++; }
+        // ---- lane 0: decode up to 32 symbols of the current Huffman block
+        if (lane == 0) {
+            int room = out_len - op;
+            while (nq < 32) {
+                br.refill();
+                int sy = huff_decode(br, W.lcnt, W.lsym, W.llut);
+                if (sy < 0) { bad = true; break; }
+                if (sy < 256) { if (room < 1) { bad = true; break; } W.q_len[nq] = (uint16_t)sy; W.q_dist[nq] = 0; nq++; room--; continue; }
+                if (sy == 256) { state = 0; break; }
+                sy -= 257;
+                if (sy >= 29) { bad = true; break; }
+                br.refill();
+                const int len = c_len_base[sy] + (int)br.bits(c_len_extra[sy]);
+                const int ds = huff_decode(br, W.dcnt, W.dsym, W.dlut);
+                if (ds < 0 || ds >= 30) { bad = true; break; }
+                br.refill();
+                const int dist = c_dist_base[ds] + (int)br.bits(c_dist_extra[ds]);
+                if (len > room) { bad = true; break; }
+                W.q_len[nq] = (uint16_t)len; W.q_dist[nq] = (uint16_t)dist; nq++; room -= len;
+            }
         }
+        bad = __shfl_sync(full, (int)bad, 0) != 0;
+        if (bad) break;
+        state = __shfl_sync(full, state, 0);
+        nq = __shfl_sync(full, nq, 0);
+        __syncwarp();
+        // ---- warp: write the queue.  Output offsets by a prefix sum over the symbols' lengths; literals first (independent bytes),
+        //      then the matches in stream order (a match may read what an earlier symbol of the same batch wrote)
+        const int my_dist = lane < nq ? (int)W.q_dist[lane] : 0;
+        const int my_len = lane < nq ? (my_dist ? (int)W.q_len[lane] : 1) : 0;
+        int incl = my_len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(full, incl, d); if (lane >= d) incl += v; }
+        const int my_off = op + incl - my_len;
+        if (lane < nq && my_dist == 0) o[my_off] = (uint8_t)W.q_len[lane];
+        uint32_t mm = __ballot_sync(full, lane < nq && my_dist != 0);
+        __syncwarp();
+        while (mm) {
+            const int k = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const int len = __shfl_sync(full, my_len, k), dist = __shfl_sync(full, my_dist, k), at = __shfl_sync(full, my_off, k);
+            if (dist > at) { bad = true; break; }             // warp-uniform
+            const uint8_t* src = o + at - dist;
+            if (dist >= len) { for (int i = lane; i < len; i += 32) o[at + i] = __ldcg(src + i); }
+            else { for (int i = lane; i < len; i += 32) o[at + i] = __ldcg(src + i % dist); }
+            __syncwarp();
+        }
+        if (bad) break;
+        op += __shfl_sync(full, incl, 31);
     }
-    if (bad || op != out_len) atomicAdd(err, 1);
+    if (lane == 0 && (bad || op != out_len)) atomicAdd(err, 1);
 }
 
 // ---- BAM records -----------------------------------------------------------------------------------------------------
