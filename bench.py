@@ -876,7 +876,7 @@ def from_bam_figure(args, local):
     rs_d = make_world(chrom="chr20", preset="ont", contig_len=args.from_bam, seed=20, coverage=30.0).reads
     tmpd = tempfile.mkdtemp(prefix="nc_bench_")
     bam_p, fa_p = os.path.join(tmpd, "d.bam"), os.path.join(tmpd, "d.fa")
-    bamio.write_bam(bam_p, [rs_d]); bamio.write_fasta(fa_p, [rs_d])
+    bamio.write_bam(bam_p, [rs_d], index=True); bamio.write_fasta(fa_p, [rs_d])
     ch_d = [(c["start"], c["end"]) for c in get_chunks([("chr20", 1, args.from_bam, "diploid")], 1)]
     ctx = capi.Context(local)
     tensors, meta = W.load_model("snp", MODEL)
@@ -946,7 +946,7 @@ def from_bam_figure(args, local):
     res = {"value": n_d / dt_d, "unit": "sites/s", "ms_per_step": dt_d * 1e3, "contig_bp": args.from_bam, "sites": int(n_d),
            "bam_bytes": os.path.getsize(bam_p), "host_threads": os.cpu_count(),
            "path": "nc_bam_device_open (mmap -> pinned -> H2D of the COMPRESSED file, bgzf_inflate_kernel, record walk + decoding kernels) -> nc_bam_device_stage -> kernels -> D2H; file in the page cache",
-           "device_reader_ms": {k: tm[k] for k in ("host_ms", "h2d_ms", "inflate_ms", "records_ms")},
+           "device_reader_ms": {k: tm[k] for k in ("host_ms", "h2d_ms", "inflate_ms", "records_ms")}, "record_walk": tm["record_walk"],
            "inflate_GBps_out": tm["inflated_bytes"] / (tm["inflate_ms"] * 1e-3) / 1e9 if tm["inflate_ms"] > 0 else None,
            "inflated_bytes": tm["inflated_bytes"],
            "host_reader": {"value": n_h / dt_h, "unit": "sites/s", "ms_per_step": dt_h * 1e3, "sites": int(n_h),

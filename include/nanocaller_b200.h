@@ -152,6 +152,9 @@ int nc_bam_device_stage(nc_ctx* ctx, int32_t i, const uint8_t* ref, int64_t ref_
 int nc_bam_device_close(nc_ctx* ctx);
 /* Milliseconds of the last nc_bam_device_open: host (mmap + block table + copy into pinned memory), H2D, inflate kernel, record walk + fields. */
 int nc_bam_device_timings(nc_ctx* ctx, float ms[4], int64_t* compressed_bytes, int64_t* inflated_bytes);
+/* 1 when the record chain of the open BAM was followed in parallel from the record starts its BAI index (`path`.bai or the path with
+ * .bai for .bam) lists, 0 when one thread walked it (no index, or an index that does not match the file). */
+int nc_bam_device_walk_mode(nc_ctx* ctx);
 
 /* K0 — htslib pileup-engine replacement (generate_SNP_pileups.py:156):
  * turns every staged read into a reference-aligned row of 4-bit codes (A0 G1 T2 C3, 4 for a

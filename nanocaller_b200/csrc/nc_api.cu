@@ -98,7 +98,7 @@ struct nc_ctx {
     std::vector<BamContig> bam_contigs;
     int64_t bam_records = 0, bam_bytes = 0, bam_comp_bytes = 0;
     float bam_ms[4] = {0, 0, 0, 0};
-    bool bam_open = false;
+    bool bam_open = false, bam_walk_parallel = false;
     NcTimings tm = {};
     bool tm_decode = false, tm_scan = false, tm_cnn = false, tm_cnn_a = false;
 };
@@ -1479,6 +1479,7 @@ int nc_bam_device_open(nc_ctx* c, const char* path, int32_t* n_contigs) {
     if (!f.ok) return fail(c, NC_EINVAL, "cannot open %s", path);
     // ---- BGZF block table from the block headers (BSIZE) and trailers (ISIZE)
     std::vector<BgzfBlock> blocks;
+    std::vector<int64_t> block_start;                              // file offset of every listed block (virtual offsets name blocks by it)
     int64_t total = 0;
     for (size_t off = 0; off < f.n;) {
         if (off + 18 > f.n) return fail(c, NC_EINVAL, "truncated or malformed BGZF block");
@@ -1495,7 +1496,7 @@ int nc_bam_device_open(nc_ctx* c, const char* path, int32_t* n_contigs) {
         const size_t blen = (size_t)bsize + 1;
         if (bsize < 0 || off + blen > f.n || blen < xend + 8) return fail(c, NC_EINVAL, "truncated or malformed BGZF block");
         const uint32_t isize = rd_le<uint32_t>(p + blen - 4);
-        if (isize) blocks.push_back({(int64_t)(off + xend), (int32_t)(blen - xend - 8), (int32_t)isize, total});
+        if (isize) { blocks.push_back({(int64_t)(off + xend), (int32_t)(blen - xend - 8), (int32_t)isize, total}); block_start.push_back((int64_t)off); }
         total += isize;
         off += blen;
     }
@@ -1570,14 +1571,85 @@ int nc_bam_device_open(nc_ctx* c, const char* path, int32_t* n_contigs) {
         if (want >= (size_t)total) return fail(c, NC_EINVAL, "truncated BAM header");
         want = std::min<size_t>((size_t)total, want * 8);
     }
-    // ---- record chain, then fields (parallel)
+    // ---- record chain, then fields (parallel).  With a BAI index next to the file its virtual offsets give record starts all over
+    //      the stream, and the chain is followed from all of them at once; without one (or if a segment does not close) one thread walks it.
     const int64_t cap = total / 96 + 4096;
     NC_CUDA(c->d_bam_recoff.reserve((size_t)cap * 8));
-    bam_walk_kernel<<<1, 32, 0, c->stream>>>(c->d_bam.as<uint8_t>(), first, total, c->d_bam_recoff.as<int64_t>(), cap, c->d_bam_out.as<int64_t>());
-    NC_LAUNCH_CHECK();
     int64_t wo[2] = {0, 0};
-    NC_CUDA(cudaMemcpyAsync(wo, c->d_bam_out.p, sizeof(wo), cudaMemcpyDeviceToHost, c->stream));
-    NC_CUDA(nc_stream_wait(c));
+    bool walked = false;
+    {
+        std::vector<int64_t> starts;
+        std::string bai = std::string(path) + ".bai";
+        MapRO x(bai.c_str());
+        if (!x.ok) { bai = path; if (bai.size() > 4 && bai.compare(bai.size() - 4, 4, ".bam") == 0) { bai = bai.substr(0, bai.size() - 4) + ".bai"; } MapRO y(bai.c_str()); if (y.ok) { std::swap(x.p, y.p); std::swap(x.n, y.n); x.ok = true; y.ok = false; } }
+        if (x.ok && x.n >= 8 && memcmp(x.p, "BAI\1", 4) == 0) {
+            auto add = [&](uint64_t v) {
+                if (!v) return;
+                const int64_t co = (int64_t)(v >> 16), uo = (int64_t)(v & 0xffff);
+                const auto it = std::lower_bound(block_start.begin(), block_start.end(), co);
+                if (it == block_start.end() || *it != co) return;
+                const BgzfBlock& bk = blocks[(size_t)(it - block_start.begin())];
+                if (uo < bk.out_len && bk.out_off + uo >= first) starts.push_back(bk.out_off + uo);
+            };
+            size_t o = 8; bool okb = true;
+            const int32_t n_ref = rd_le<int32_t>(x.p + 4);
+            for (int32_t r = 0; r < n_ref && okb; r++) {
+                if (o + 4 > x.n) { okb = false; break; }
+                const int32_t n_bin = rd_le<int32_t>(x.p + o); o += 4;
+                for (int32_t b = 0; b < n_bin && okb; b++) {
+                    if (o + 8 > x.n) { okb = false; break; }
+                    const uint32_t bin = rd_le<uint32_t>(x.p + o); const int32_t n_chunk = rd_le<int32_t>(x.p + o + 4); o += 8;
+                    if (n_chunk < 0 || o + 16ull * (size_t)n_chunk > x.n) { okb = false; break; }
+                    if (bin != 37450) for (int32_t k = 0; k < n_chunk; k++) add(rd_le<uint64_t>(x.p + o + 16ull * k));      // 37450: the metadata pseudo-bin
+                    o += 16ull * (size_t)n_chunk;
+                }
+                if (!okb || o + 4 > x.n) { okb = false; break; }
+                const int32_t n_intv = rd_le<int32_t>(x.p + o); o += 4;
+                if (n_intv < 0 || o + 8ull * (size_t)n_intv > x.n) { okb = false; break; }
+                for (int32_t k = 0; k < n_intv; k++) add(rd_le<uint64_t>(x.p + o + 8ull * k));
+                o += 8ull * (size_t)n_intv;
+            }
+            if (okb) {
+                starts.push_back(first);
+                std::sort(starts.begin(), starts.end());
+                starts.erase(std::unique(starts.begin(), starts.end()), starts.end());
+            } else starts.clear();
+        }
+        if (starts.size() >= 64) {
+            const int64_t ns = (int64_t)starts.size();
+            DevBuf d_st, d_cnt, d_off;
+            cudaError_t e_ = d_st.reserve((size_t)ns * 8);
+            if (e_ == cudaSuccess) e_ = d_cnt.reserve((size_t)ns * 4);
+            if (e_ == cudaSuccess) e_ = d_off.reserve((size_t)(ns + 1) * 8);
+            if (e_ == cudaSuccess) e_ = cudaMemcpyAsync(d_st.p, starts.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, c->stream);
+            int rcw = NC_OK;
+            if (e_ == cudaSuccess) {
+                bam_walk_seg_kernel<false><<<(unsigned)div_up(ns, 128), 128, 0, c->stream>>>(c->d_bam.as<uint8_t>(), d_st.as<int64_t>(), ns, total, d_cnt.as<int32_t>(), nullptr,
+                                                                                           nullptr, c->d_bam_err.as<int>());
+                c->launches++;
+                rcw = device_scan(c, d_cnt.as<int32_t>(), ns, d_off.as<int64_t>());
+                int64_t nrec_seg = 0;
+                if (!rcw) rcw = read_i64(c, d_off.as<int64_t>() + ns, &nrec_seg);
+                int herr4[4] = {0, 0, 0, 0};
+                if (!rcw && cudaMemcpy(herr4, c->d_bam_err.p, sizeof(herr4), cudaMemcpyDeviceToHost) == cudaSuccess && herr4[3] == 0 && nrec_seg <= cap) {
+                    bam_walk_seg_kernel<true><<<(unsigned)div_up(ns, 128), 128, 0, c->stream>>>(c->d_bam.as<uint8_t>(), d_st.as<int64_t>(), ns, total, nullptr, d_off.as<int64_t>(),
+                                                                                              c->d_bam_recoff.as<int64_t>(), c->d_bam_err.as<int>());
+                    c->launches++;
+                    if (nc_stream_wait(c) == cudaSuccess) { wo[0] = nrec_seg; wo[1] = 1; walked = true; }
+                }
+            }
+            cudaStreamSynchronize(c->stream);
+            d_st.release(); d_cnt.release(); d_off.release();
+            if (rcw) return rcw;
+        }
+    }
+    if (!walked) {
+        bam_walk_kernel<<<1, 32, 0, c->stream>>>(c->d_bam.as<uint8_t>(), first, total, c->d_bam_recoff.as<int64_t>(), cap, c->d_bam_out.as<int64_t>());
+        NC_LAUNCH_CHECK();
+        NC_CUDA(cudaMemcpyAsync(wo, c->d_bam_out.p, sizeof(wo), cudaMemcpyDeviceToHost, c->stream));
+        NC_CUDA(nc_stream_wait(c));
+    }
+    c->bam_walk_parallel = walked;
     if (!wo[1]) return fail(c, NC_EINVAL, "truncated alignment record");
     if (wo[0] > cap) return fail(c, NC_EOVERFLOW, "%lld records: more than the device reader's table holds (records shorter than 96 bytes on average)", (long long)wo[0]);
     const int64_t nrec = wo[0];
@@ -1620,7 +1692,6 @@ int nc_bam_device_open(nc_ctx* c, const char* path, int32_t* n_contigs) {
     NC_CUDA(cudaEventElapsedTime(&c->bam_ms[1], e0, e1));
     NC_CUDA(cudaEventElapsedTime(&c->bam_ms[2], e1, e2));
     NC_CUDA(cudaEventElapsedTime(&c->bam_ms[3], e2, e3));
-    c->d_bam_comp.release();                                       // the compressed copy is no longer needed
     c->bam_open = true;
     *n_contigs = (int32_t)c->bam_contigs.size();
     return NC_OK;
@@ -1636,6 +1707,8 @@ int nc_bam_device_contig(nc_ctx* c, int32_t i, NcBamDeviceContig* out) {
     out->length = bc.length; out->n_reads = bc.n; out->n_tagged = bc.n_tagged;
     return NC_OK;
 }
+
+int nc_bam_device_walk_mode(nc_ctx* c) { return (c && c->bam_open) ? (c->bam_walk_parallel ? 1 : 0) : NC_ESTATE; }
 
 int nc_bam_device_timings(nc_ctx* c, float ms[4], int64_t* compressed_bytes, int64_t* inflated_bytes) {
     if (!c || !ms) return NC_EINVAL;

@@ -278,6 +278,29 @@ __global__ void bam_walk_kernel(const uint8_t* __restrict__ d, int64_t first, in
     out[0] = n; out[1] = off == end ? 1 : 0;
 }
 
+// Parallel version of the walk when record starts are known (the BAI index lists the virtual offset of a record for every 16 kb
+// window and every bin chunk): walker w follows the chain from start[w] and must land exactly on start[w + 1] (`end` for the last).
+// FILL = false: cnt[w] = records of the segment; FILL = true: rec_off[off[w] ...] = their offsets.  err[3] counts segments that do not
+// land on the next start (the caller then falls back to the single walker).
+template <bool FILL>
+__global__ void bam_walk_seg_kernel(const uint8_t* __restrict__ d, const int64_t* __restrict__ start, int64_t n_seg, int64_t end,
+                                    int32_t* __restrict__ cnt, const int64_t* __restrict__ off, int64_t* __restrict__ rec_off, int* __restrict__ err) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_seg) return;
+    int64_t p = start[w];
+    const int64_t stop = w + 1 < n_seg ? start[w + 1] : end;
+    int64_t n = 0, o = FILL ? off[w] : 0;
+    while (p < stop) {
+        if (p + 4 > end) break;
+        const int64_t bs = (int32_t)ld_u32(d + p);
+        if (bs < 32 || p + 4 + bs > end) break;
+        if (FILL) rec_off[o + n] = p;
+        n++;
+        p += 4 + bs;
+    }
+    if (!FILL) { cnt[w] = (int32_t)n; if (p != stop) atomicAdd(err + 3, 1); }
+}
+
 struct BamFields {
     int32_t* rid; int32_t* pos; uint16_t* flag; int32_t* lseq; int32_t* ncig; int32_t* nseq;     // nseq = (l_seq + 1) / 2
     int64_t* cig_src; int64_t* seq_src; int8_t* hp; int32_t* ps;

@@ -18,7 +18,7 @@ EXPORTS = ["nc_abi_version", "nc_create", "nc_destroy", "nc_last_error", "nc_syn
            "nc_load_snp_weights", "nc_snp_forward", "nc_snp_fetch_probs", "nc_snp_model_forward", "nc_snp_device_buffers",
            "nc_load_indel_weights", "nc_indel_model_forward", "nc_stage_tags", "nc_indel_scan", "nc_indel_fetch_variants",
            "nc_indel_build", "nc_indel_fetch", "nc_indel_forward", "nc_indel_fetch_probs", "nc_indel_fetch_alleles",
-           "nc_bam_device_open", "nc_bam_device_contig", "nc_bam_device_stage", "nc_bam_device_close", "nc_bam_device_timings", "nc_get_indel_timings", "nc_nw_trace", "nc_allele_predict_batch",
+           "nc_bam_device_open", "nc_bam_device_contig", "nc_bam_device_stage", "nc_bam_device_close", "nc_bam_device_timings", "nc_bam_device_walk_mode", "nc_get_indel_timings", "nc_nw_trace", "nc_allele_predict_batch",
            "nc_format_snp_records"]
 
 
@@ -121,6 +121,7 @@ def load_library():
     lib.nc_bam_device_contig.argtypes = [vp, i32, ctypes.POINTER(NcBamDeviceContig)]
     lib.nc_bam_device_stage.argtypes = [vp, i32, vp, i64, i64]
     lib.nc_bam_device_close.argtypes = [vp]
+    lib.nc_bam_device_walk_mode.argtypes = [vp]
     lib.nc_bam_device_timings.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 4), ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.nc_nw_trace.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp, i32]
     for name in EXPORTS:
@@ -275,7 +276,8 @@ class Context:
         ms = (ctypes.c_float * 4)()
         a, b = ctypes.c_int64(0), ctypes.c_int64(0)
         self._check(self._lib.nc_bam_device_timings(self._h, ctypes.byref(ms), ctypes.byref(a), ctypes.byref(b)))
-        return {"host_ms": ms[0], "h2d_ms": ms[1], "inflate_ms": ms[2], "records_ms": ms[3], "compressed_bytes": a.value, "inflated_bytes": b.value}
+        return {"host_ms": ms[0], "h2d_ms": ms[1], "inflate_ms": ms[2], "records_ms": ms[3], "compressed_bytes": a.value, "inflated_bytes": b.value,
+                "record_walk": "parallel from the BAI's record starts" if self._lib.nc_bam_device_walk_mode(self._h) == 1 else "single walker"}
 
     def fetch_staged(self):
         """The staged contig back on the host (validation): dict of the BAM-native arrays."""

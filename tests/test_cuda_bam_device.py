@@ -110,3 +110,28 @@ def test_snp_scan_from_a_device_staged_file_matches_host_staging(tmp_path):
     mat1, meta1, depth1, _ = ctx.snp_fetch()
     assert n0 == n1 > 3000 and np.array_equal(mat0[:, :1025], mat1[:, :1025]) and meta0.tobytes() == meta1.tobytes() and depth0[0] == depth1[0]
     ctx.bam_device_close()
+
+
+def test_bai_seeded_parallel_walk_equals_single_walker(tmp_path):
+    """With a BAI next to the file the record chain is followed from all the record starts the index lists; same arrays as without."""
+    from nanocaller_b200.host import snp_pileups
+    rs1 = make_world(chrom="chrA", preset="ont", contig_len=900_000, seed=5, coverage=20.0, indel_every=900, indel_maxlen=9, untagged_frac=0.2).reads
+    rs2 = make_world(chrom="chrB", preset="hifi", contig_len=500_000, seed=6, coverage=12.0).reads
+    bam, plain = str(tmp_path / "i.bam"), str(tmp_path / "p.bam")
+    bamio.write_bam(bam, [rs1, rs2], index=True)
+    bamio.write_bam(plain, [rs1, rs2])
+    ctx = snp_pileups.context(0)
+    snp_pileups._staged.clear()
+    got = {}
+    for tag, path in (("indexed", bam), ("plain", plain)):
+        table = ctx.bam_device_open(path)
+        got[tag] = (table, ctx.bam_device_timings()["record_walk"])
+        for i, w in enumerate((rs1, rs2)):
+            ctx.bam_device_stage(i, w.ref)
+            arr = ctx.fetch_staged()
+            for k in KEYS:
+                want = getattr(w, k) if k != "ps" else np.where(w.hp > 0, w.ps, 0)
+                np.testing.assert_array_equal(arr[k], want, err_msg="%s %s %s" % (tag, w.chrom, k))
+    assert got["indexed"][0] == got["plain"][0]
+    assert got["indexed"][1].startswith("parallel") and got["plain"][1] == "single walker"
+    ctx.bam_device_close()
