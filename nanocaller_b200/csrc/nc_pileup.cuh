@@ -802,6 +802,68 @@ __device__ __forceinline__ SiteCols site_columns(const TensorArgs& a, const int3
     return sc;
 }
 
+// Same result as site_columns for the sites of a RUN whose neighbour range is staged in shared memory (nbr[0, n), reference codes
+// nbr_rc): a warp visits its sites in ascending (chunk, position) order, so the 2 x 7 bin boundaries only move forward — every
+// bin lane keeps its two list indices (st_lo, st_hi) from the previous site and advances them instead of running two binary
+// searches per bin and site (first = true: search).  The tensor column of every chosen neighbour comes from a prefix sum over the
+// bins' counts (left list = farthest bin first, right list = nearest bin first) written to a 41-entry table, instead of a walk
+// over all bins per column; reference codes come from the staged copies instead of dependent global loads.
+__device__ __forceinline__ SiteCols site_columns_run(const TensorArgs& a, const int32_t* nbr, const uint8_t* nbr_rc, int32_t n, int32_t nb_base, int c, int32_t v,
+                                                     int rc_v, int lane, bool first, int32_t& st_lo, int32_t& st_hi, int8_t* colj) {
+    const uint32_t full = 0xffffffffu;
+    SiteCols sc;
+    const int32_t wlo = max(1, a.chunks[c].start - 50000), whi = a.chunks[c].end + 50000;
+    const int side = lane >> 3, bin = lane & 7, nb = c_nbins[a.seq];
+    const bool owner = lane < 16 && bin < nb;
+    int32_t sel_lo = 0, sel_cnt = 0;
+    if (owner) {
+        const BinSpec bs = c_bins[a.seq][bin];
+        int32_t key_lo, key_hi;
+        if (side == 0) { key_lo = (int32_t)max(max((int64_t)v - bs.b, (int64_t)wlo), (int64_t)INT32_MIN + 1); key_hi = v - bs.a; }
+        else { key_lo = v + bs.a + 1; key_hi = (int32_t)min(min((int64_t)v + bs.b, (int64_t)whi) + 1, (int64_t)INT32_MAX); }
+        if (first) { st_lo = lower_bound_plain(nbr, n, key_lo); st_hi = lower_bound_plain(nbr, n, key_hi); }
+        else {
+            while (st_lo < n && nbr[st_lo] < key_lo) st_lo++;
+            while (st_hi < n && nbr[st_hi] < key_hi) st_hi++;
+        }
+        if (st_hi > st_lo) {
+            sel_cnt = min(st_hi - st_lo, bs.k);
+            sel_lo = side == 0 ? (bs.far ? st_lo : st_hi - sel_cnt) : (bs.far ? st_hi - sel_cnt : st_lo);
+        }
+    }
+    // left list ascending = farthest bin first: bin b starts after the bins b' > b; right list: after the bins b' < b
+    int before = 0, l = 0, r = 0;
+#pragma unroll
+    for (int b = 0; b < 7; b++) {
+        const int cl = __shfl_sync(full, sel_cnt, b), cr = __shfl_sync(full, sel_cnt, 8 + b);
+        l += cl; r += cr;
+        if (side == 0 && b > bin) before += cl;
+        if (side == 1 && b < bin) before += cr;
+    }
+    sc.nl = l; sc.nr = r;
+    colj[lane] = -1;
+    if (lane < 9) colj[32 + lane] = -1;
+    __syncwarp();
+    if (owner) {
+        const int col0 = side == 0 ? 20 - l + before : 21 + before;
+        int16_t* colw = reinterpret_cast<int16_t*>(colj + 48);
+        for (int t = 0; t < sel_cnt; t++) { colj[col0 + t] = 0; colw[col0 + t] = (int16_t)(sel_lo + t); }
+    }
+    __syncwarp();
+    const int16_t* colv = reinterpret_cast<const int16_t*>(colj + 48);
+    const int32_t r0 = colj[lane] == 0 ? (int32_t)colv[lane] : -1;
+    const int32_t r1 = (lane < 9 && colj[32 + lane] == 0) ? (int32_t)colv[32 + lane] : -1;
+    sc.rc_v = rc_v;
+    sc.rc0 = 4; sc.rc1 = 4;
+    if (lane == 20) sc.rc0 = rc_v;
+    if (r0 >= 0) sc.rc0 = nbr_rc[r0];
+    if (r1 >= 0) sc.rc1 = nbr_rc[r1];
+    sc.j0 = r0 >= 0 ? r0 + nb_base : -1;
+    sc.j1 = r1 >= 0 ? r1 + nb_base : -1;
+    __syncwarp();                                                      // the table is reused by the warp's next site
+    return sc;
+}
+
 // assemble [5][41][5] in shared memory, 16-byte coalesced stores, site metadata, chunk depth sums
 __device__ __forceinline__ void site_finish(const TensorArgs& a, int64_t orow, int c, int32_t v, int lane, int16_t* buf, const SiteCols& sc,
                                             const uint64_t* acc0, const uint64_t* acc1, uint64_t fwd, uint64_t rev, int32_t dp, int32_t sampled) {
@@ -937,10 +999,9 @@ struct RunList {                        // admitted reads overlapping the run, B
 
 // Fast per-site path over the run's compact read list; 8-bit count fields (maxcov <= 255).
 __device__ __forceinline__ void tensor_site_run(const TensorArgs& a, int64_t orow, int c, int32_t v, int lane, int16_t* buf,
-                                                const RunList& L, int cnt, const int32_t* nbr, int32_t n_nbr, int32_t nb_base) {
+                                                const RunList& L, int cnt, const SiteCols& sc) {
     const uint32_t full = 0xffffffffu;
     const int32_t p = v - 1;
-    const SiteCols sc = site_columns(a, nbr, n_nbr, nb_base, c, v, lane);
     uint32_t a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};                // per candidate code: 4 x 8-bit counts by column code
     uint64_t fwd = 0, rev = 0;
     int32_t dp = 0, sampled = 0;
@@ -1001,11 +1062,10 @@ __device__ __forceinline__ void tensor_site_run(const TensorArgs& a, int64_t oro
 // — 16 AND + POPC per column and mask word instead of a dependent lookup per (read, column).
 template <int W>
 __device__ __forceinline__ void tensor_site_masks(const TensorArgs& a, int64_t orow, int c, int32_t v, int lane, int16_t* buf,
-                                                  const RunList& L, int cnt, const int32_t* nbr, int32_t n_nbr, int32_t nb_base,
+                                                  const RunList& L, int cnt, int32_t nb_base, const SiteCols& sc,
                                                   const uint32_t* __restrict__ M) {
     const uint32_t full = 0xffffffffu;
     const int32_t p = v - 1;
-    const SiteCols sc = site_columns(a, nbr, n_nbr, nb_base, c, v, lane);
     uint32_t cw[W], rv[W], ms[4][W];
 #pragma unroll
     for (int w = 0; w < W; w++) {
@@ -1094,6 +1154,8 @@ __global__ void __launch_bounds__(kTensorWarps * 32, 6) tensor_kernel(const Tens
     __shared__ int32_t s_nbr[kRunNbr];
     __shared__ __align__(16) uint32_t s_mask[kMaskNbr * 4 * kMaskWords];     // M[neighbour][code][word]
     __shared__ int32_t s_v[kRunSlots], s_c[kRunSlots];
+    __shared__ uint8_t s_nbr_rc[kRunNbr], s_rcv[kRunSlots];                   // reference codes of the staged neighbours / of the run's candidates
+    __shared__ __align__(4) int8_t s_colj[kTensorWarps][48 + 2 * 48];         // per warp: column -> chosen neighbour (flag bytes, then int16 indices)
     __shared__ int32_t s_wcnt[kTensorWarps];
     __shared__ int64_t s_ilo, s_ihi;
     __shared__ int32_t s_pmin, s_pmax, s_nb_lo, s_nb_hi, s_fast;
@@ -1114,6 +1176,7 @@ __global__ void __launch_bounds__(kTensorWarps * 32, 6) tensor_kernel(const Tens
                 lo = hi = v - 1;
             }
             s_v[lane] = v; s_c[lane] = c;
+            s_rcv[lane] = lane < nslots ? (uint8_t)ref_code_of(__ldg(a.ref + ((int64_t)(v - 1) - a.ref_start))) : (uint8_t)4;
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) { lo = min(lo, __shfl_xor_sync(full, lo, d)); hi = max(hi, __shfl_xor_sync(full, hi, d)); }
             if (lane == 0) {
@@ -1164,7 +1227,12 @@ __global__ void __launch_bounds__(kTensorWarps * 32, 6) tensor_kernel(const Tens
         const bool fast = s_fast && cnt <= kRunList;
         const int32_t nb_lo = s_nb_lo, nb_n = s_nb_hi - s_nb_lo;
         const bool nbr_sm = nb_n <= kRunNbr;
-        if (fast && nbr_sm) for (int i = tid; i < nb_n; i += kTensorWarps * 32) s_nbr[i] = __ldg(a.nbr_pos + nb_lo + i);
+        if (fast && nbr_sm)
+            for (int i = tid; i < nb_n; i += kTensorWarps * 32) {
+                const int32_t np = __ldg(a.nbr_pos + nb_lo + i);
+                s_nbr[i] = np;
+                s_nbr_rc[i] = (uint8_t)ref_code_of(__ldg(a.ref + ((int64_t)np - 1 - a.ref_start)));
+            }
         const bool masks = fast && cnt <= 32 * kMaskWords && nb_n <= kMaskNbr;
         if (masks) {
             // ---- M[j][b]: lanes as reads, one ballot per code; a warp takes a contiguous quarter of the neighbours
@@ -1187,7 +1255,9 @@ __global__ void __launch_bounds__(kTensorWarps * 32, 6) tensor_kernel(const Tens
             }
         }
         __syncthreads();
-        // ---- a warp per site
+        // ---- a warp per site; with the neighbours staged, the bin boundaries are carried from one site of the warp to the next
+        int32_t st_lo = 0, st_hi = 0;
+        int prev_c = -1;                                               // a new chunk may lie anywhere (and clips differently): search again
         for (int k = wib; k < nslots; k += kTensorWarps) {
             const int64_t s = s0 + k;
             int64_t orow = s;
@@ -1197,17 +1267,19 @@ __global__ void __launch_bounds__(kTensorWarps * 32, 6) tensor_kernel(const Tens
             }
             const int c = s_c[k];
             const int32_t v = s_v[k];
-            if (!fast) tensor_site_generic(a, orow, c, v, lane, buf);
-            else if (masks) {
+            if (!fast) { tensor_site_generic(a, orow, c, v, lane, buf); continue; }
+            SiteCols sc;
+            if (nbr_sm) { sc = site_columns_run(a, s_nbr, s_nbr_rc, nb_n, nb_lo, c, v, s_rcv[k], lane, c != prev_c, st_lo, st_hi, s_colj[wib]); prev_c = c; }
+            else sc = site_columns(a, a.nbr_pos + nb_lo, nb_n, nb_lo, c, v, lane);
+            if (masks) {
                 switch ((cnt + 31) >> 5) {
-                    case 0: case 1: tensor_site_masks<1>(a, orow, c, v, lane, buf, s_list, cnt, s_nbr, nb_n, nb_lo, s_mask); break;
-                    case 2: tensor_site_masks<2>(a, orow, c, v, lane, buf, s_list, cnt, s_nbr, nb_n, nb_lo, s_mask); break;
-                    case 3: tensor_site_masks<3>(a, orow, c, v, lane, buf, s_list, cnt, s_nbr, nb_n, nb_lo, s_mask); break;
-                    default: tensor_site_masks<4>(a, orow, c, v, lane, buf, s_list, cnt, s_nbr, nb_n, nb_lo, s_mask); break;
+                    case 0: case 1: tensor_site_masks<1>(a, orow, c, v, lane, buf, s_list, cnt, nb_lo, sc, s_mask); break;
+                    case 2: tensor_site_masks<2>(a, orow, c, v, lane, buf, s_list, cnt, nb_lo, sc, s_mask); break;
+                    case 3: tensor_site_masks<3>(a, orow, c, v, lane, buf, s_list, cnt, nb_lo, sc, s_mask); break;
+                    default: tensor_site_masks<4>(a, orow, c, v, lane, buf, s_list, cnt, nb_lo, sc, s_mask); break;
                 }
             }
-            else if (nbr_sm) tensor_site_run(a, orow, c, v, lane, buf, s_list, cnt, s_nbr, nb_n, nb_lo);
-            else tensor_site_run(a, orow, c, v, lane, buf, s_list, cnt, a.nbr_pos + nb_lo, nb_n, nb_lo);
+            else tensor_site_run(a, orow, c, v, lane, buf, s_list, cnt, sc);
         }
     }
 }
