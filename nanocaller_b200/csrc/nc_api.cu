@@ -999,10 +999,10 @@ int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int3
     NC_CUDA(cudaMemsetAsync(c->d_diff.p, 0, (size_t)8 * R * 4, c->stream));
     EventArgs ea = {};
     ea.n_reads = c->n_reads; ea.pos = da.pos; ea.end = da.end; ea.flag = da.flag; ea.hp = da.hp; ea.cigar_off = c->d_cigar_off.as<int64_t>();
-    ea.cigar = c->d_cigar.as<uint32_t>(); ea.chunks = c->d_ichunks.as<IndelChunk>(); ea.n_chunks = n_chunks; ea.em = c->d_em.as<int32_t>();
+    ea.cigar = c->d_cigar.as<uint32_t>(); ea.opstart = c->d_opstart.as<int2>(); ea.chunks = c->d_ichunks.as<IndelChunk>(); ea.n_chunks = n_chunks; ea.em = c->d_em.as<int32_t>();
     ea.grank = c->d_grank.as<int64_t>(); ea.lo_al = lo_al; ea.flag_filter = flag_filter; ea.win = P->win_size; ea.small_win = P->small_win_size; ea.haploid = P->haploid;
     ea.diff = c->d_diff.as<int32_t>(); ea.R = R;
-    indel_events_kernel<<<(unsigned)div_up(c->n_reads, 128), 128, 0, c->stream>>>(ea); NC_LAUNCH_CHECK();
+    indel_events_kernel<<<(unsigned)div_up(c->n_reads * 32, 128), 128, 0, c->stream>>>(ea); NC_LAUNCH_CHECK();
     NC_CUDA(c->d_uscan.reserve((size_t)8 * (R + 1) * 8));
     for (int k = 0; k < 8; k++)
         if ((rc = device_scan(c, c->d_diff.as<int32_t>() + (int64_t)k * R, R, c->d_uscan.as<int64_t>() + (int64_t)k * (R + 1)))) return rc;
