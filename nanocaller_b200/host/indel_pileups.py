@@ -109,33 +109,17 @@ class AllelePredictions:
 
     def __init__(self, rs, dct, meta, cns, haploid, threads=0, device_lengths=None):
         """device_lengths: int32 [n_sites, 3, 2] from nc_indel_fetch_alleles (the alignment ran on the GPU right after msa); without it,
-        or for items it marks -2, the same alignment runs on host threads (nc_allele_predict_batch)."""
+        or for items it marks -2, the same alignment runs on host threads (nc_allele_predict_batch).  The reference windows are only
+        gathered on the host when something needs them (host alignment, allele strings)."""
         self.groups = (2,) if haploid else (0, 1, 2)
-        self.cns, self.meta = cns, meta
+        self.cns, self.meta, self.rs = cns, meta, rs
         kept = np.nonzero(kept_sites(meta, haploid))[0]
         self.kept = kept
         ng = len(self.groups)
         self.site = np.repeat(kept, ng)
         self.grp = np.tile(np.asarray(self.groups), len(kept))
-        if len(kept) == 0:
-            self.ref_out = self.alt_out = self.alt_len = self.r_len = np.zeros(0, np.int32)
-            self.r_off = np.zeros(0, np.int64)
-            self.ref_bytes = np.zeros(0, np.uint8)
-            return
-        p0 = meta["pos"][kept].astype(np.int64) - 1
-        m = meta["ref_len"][kept].astype(np.int64)
-        off = np.zeros(len(kept) + 1, np.int64)
-        np.cumsum(m, out=off[1:])
-        idx = np.repeat(p0 - off[:-1], m) + np.arange(off[-1])                 # flat gather of the reference windows
-        self.ref_bytes = rs.ref[idx]
-        ref_flat = _REF_CODE[self.ref_bytes]
-        cap = cns.shape[2]
-        alt_off = (self.site.astype(np.int64) * cns.shape[1] + self.grp) * cap
-        self.alt_len = meta["cns_len"][self.site, self.grp].astype(np.int32)
-        self.r_off = np.repeat(off[:-1], ng)
-        self.r_len = np.repeat(m.astype(np.int32), ng)
-        win = max(10, int(dct["win_size"]))
-        mr = np.where(meta["type"][self.site] == 0, win, 10).astype(np.int32)   # max_range (:209)
+        self._windows = None
+        self.alt_len = meta["cns_len"][self.site, self.grp].astype(np.int32) if len(kept) else np.zeros(0, np.int32)
         if device_lengths is not None:
             dl = np.asarray(device_lengths, np.int32)[self.site, self.grp]
             self.ref_out, self.alt_out = dl[:, 0].copy(), dl[:, 1].copy()
@@ -144,23 +128,44 @@ class AllelePredictions:
             self.ref_out, self.alt_out = np.empty(len(self.site), np.int32), np.empty(len(self.site), np.int32)
             todo = np.arange(len(self.site))
         if len(todo):
-            ro, ao = capi.allele_predict_batch(cns.reshape(-1), alt_off[todo], self.alt_len[todo], ref_flat, self.r_off[todo], self.r_len[todo],
+            ref_bytes, r_off, r_len = self.windows()
+            cap = cns.shape[2]
+            alt_off = (self.site.astype(np.int64) * cns.shape[1] + self.grp) * cap
+            win = max(10, int(dct["win_size"]))
+            mr = np.where(meta["type"][self.site] == 0, win, 10).astype(np.int32)   # max_range (:209)
+            ro, ao = capi.allele_predict_batch(cns.reshape(-1), alt_off[todo], self.alt_len[todo], _REF_CODE[ref_bytes], r_off[todo], r_len[todo],
                                                mr[todo], threads=threads)
             self.ref_out[todo], self.alt_out[todo] = ro, ao
+
+    def windows(self):
+        """(reference bytes of all kept sites' windows back to back, per item offset, per item length)"""
+        if self._windows is None:
+            kept, ng = self.kept, len(self.groups)
+            if len(kept) == 0:
+                self._windows = (np.zeros(0, np.uint8), np.zeros(0, np.int64), np.zeros(0, np.int32))
+            else:
+                p0 = self.meta["pos"][kept].astype(np.int64) - 1
+                m = self.meta["ref_len"][kept].astype(np.int64)
+                off = np.zeros(len(kept) + 1, np.int64)
+                np.cumsum(m, out=off[1:])
+                idx = np.repeat(p0 - off[:-1], m) + np.arange(off[-1])             # flat gather of the reference windows
+                self._windows = (self.rs.ref[idx], np.repeat(off[:-1], ng), np.repeat(m.astype(np.int32), ng))
+        return self._windows
 
     def strings(self):
         """{(site, group): (ref, alt) or (None, None)}"""
         pred = {}
-        ref_txt = self.ref_bytes.tobytes().decode()
+        ref_bytes, r_off, r_len = self.windows()
+        ref_txt = ref_bytes.tobytes().decode()
         cns = self.cns
         for k in range(len(self.site)):
             s, g = int(self.site[k]), int(self.grp[k])
             if self.ref_out[k] < 0:
                 pred[(s, g)] = (None, None)
             else:
-                b0 = int(self.r_off[k])
+                b0 = int(r_off[k])
                 alt = BASES[cns[s, g, :self.alt_len[k]]].tobytes().decode()
-                pred[(s, g)] = (ref_txt[b0:b0 + min(int(self.ref_out[k]), int(self.r_len[k]))], alt[:int(self.alt_out[k])])
+                pred[(s, g)] = (ref_txt[b0:b0 + min(int(self.ref_out[k]), int(r_len[k]))], alt[:int(self.alt_out[k])])
         return pred
 
 

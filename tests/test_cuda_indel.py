@@ -142,7 +142,7 @@ def test_device_allele_prediction_equals_host_alignment(preset, seq):
     host = indel_pileups.AllelePredictions(rs, dct, meta, cns, False)
     devp = indel_pileups.AllelePredictions(rs, dct, meta, cns, False, device_lengths=dev)
     assert len(host.site) > 300 and not (dev == -2).any()
-    assert np.array_equal(host.ref_out, devp.ref_out) and np.array_equal(host.alt_out, devp.alt_out)
+    assert np.array_equal(host.ref_out, devp.ref_out) and np.array_equal(host.alt_out, devp.alt_out) and host.strings() == devp.strings()
     assert (host.ref_out >= 0).sum() > 50 and (host.ref_out < 0).sum() > 50
     kept = indel_pileups.kept_sites(meta, False)
     assert (dev[~kept] == -1).all()
