@@ -1003,9 +1003,8 @@ int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int3
     ea.grank = c->d_grank.as<int64_t>(); ea.lo_al = lo_al; ea.flag_filter = flag_filter; ea.win = P->win_size; ea.small_win = P->small_win_size; ea.haploid = P->haploid;
     ea.diff = c->d_diff.as<int32_t>(); ea.R = R;
     indel_events_kernel<<<(unsigned)div_up(c->n_reads * 32, 128), 128, 0, c->stream>>>(ea); NC_LAUNCH_CHECK();
-    NC_CUDA(c->d_uscan.reserve((size_t)8 * (R + 1) * 8));
-    for (int k = 0; k < 8; k++)
-        if ((rc = device_scan(c, c->d_diff.as<int32_t>() + (int64_t)k * R, R, c->d_uscan.as<int64_t>() + (int64_t)k * (R + 1)))) return rc;
+    NC_CUDA(c->d_uscan.reserve((size_t)(8 * R + 1) * 8));
+    if ((rc = device_scan(c, c->d_diff.as<int32_t>(), 8 * R, c->d_uscan.as<int64_t>()))) return rc;      // all eight kinds in one scan (DecideArgs::uscan)
     NC_CUDA(c->d_hit.reserve((size_t)R));
     NC_CUDA(c->d_icount.reserve(64));
     NC_CUDA(cudaMemsetAsync(c->d_icount.p, 0, 64, c->stream));

@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(128) indel_events_kernel(const EventArgs a) {
 // ------------------------------------------------------------------------------------------------
 struct DecideArgs {
     const IndelChunk* chunks; int32_t n_chunks; int64_t R;
-    const int64_t* uscan;      // [8][R+1] exclusive scans of diff
+    const int64_t* uscan;      // [8 * R + 1]: ONE exclusive scan over the eight concatenated difference arrays — every interval adds +1 and -1 inside its
+                               // own chunk's rank range, so each array (each chunk) sums to zero and the running sum restarts at 0 by itself
     const int32_t* em_pos; const uint16_t* depth; int64_t n_al; int32_t lo_al;
     int32_t mincov, haploid; double ins_t, del_t;
     uint8_t* hit; unsigned long long* n_hits;
@@ -273,7 +274,7 @@ __global__ void indel_decide_kernel(const DecideArgs a) {
             if (l0 >= a.mincov) {                      // generate_indel_pileups_haploid.py:224-241
                 double f[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) f[k] = l0 > 0 ? (double)a.uscan[(int64_t)k * (a.R + 1) + g + 1] / (double)l0 : 0.0;
+                for (int k = 0; k < 4; k++) f[k] = l0 > 0 ? (double)a.uscan[(int64_t)k * a.R + g + 1] / (double)l0 : 0.0;
                 if (f[0] >= a.del_t || f[2] >= a.ins_t) hit = 1;
                 else if (f[1] >= a.del_t || f[3] >= a.ins_t || (f[1] + f[3]) >= 0.9) hit = 2;
             }
@@ -282,7 +283,7 @@ __global__ void indel_decide_kernel(const DecideArgs a) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int32_t l = k < 4 ? l0 : l1;
-                f[k] = l > 0 ? (double)a.uscan[(int64_t)k * (a.R + 1) + g + 1] / (double)l : 0.0;
+                f[k] = l > 0 ? (double)a.uscan[(int64_t)k * a.R + g + 1] / (double)l : 0.0;
             }
             if (fmax(f[0], f[4]) >= a.del_t || fmax(f[2], f[6]) >= a.ins_t) hit = 1;
             else if (fmax(f[1], f[5]) >= a.del_t || fmax(f[3], f[7]) >= a.ins_t || (f[1] + f[3]) >= 0.9 || (f[5] + f[7]) >= 0.9) hit = 2;
@@ -811,33 +812,44 @@ __global__ void __launch_bounds__(96) indel_msa_kernel(const SiteArgs a) {
             }
             cns_sym[cc] = (uint8_t)bi;
         }
-        // insertion columns: slot j (before reference base j, or after the last one for j = m), k-th inserted base
-        for (int j = 0; j <= m; j++) {
-            const int w = width[j];
-            if (w == 0) continue;                          // warp-uniform (shared memory)
-            const int cstart = (j < m ? col[j] : L) - w;
-            for (int kk = lane; kk < w; kk += 32) {
-                int32_t c[5] = {0, 0, 0, 0, 0};
-                int32_t seen2 = 0;
-                for (int32_t k = 0; k < cnt && seen2 < n_use; k++) {
-                    if (!member(k)) continue;
-                    seen2++;
-                    const int64_t e = e0 + k;
-                    const uint16_t il = a.e_inslen[e * (a.mmax + 1) + j];
-                    int code = 4;
-                    if (kk < il) { code = a.e_slice[e * a.nmax + a.e_insfirst[e * (a.mmax + 1) + j] + kk]; if (code > 3) code = 4; }
-                    c[code]++;
-                }
-                const int cc = cstart + kk;
-                float best = -1.f; int bi = 0;
+        // insertion columns: slot j (before reference base j, or after the last one for j = m), kk-th inserted base.  Lanes take
+        // insertion COLUMNS (all slots' columns numbered consecutively: column q of the alignment is an insertion column iff it
+        // is not col[j] of a reference base), not the 1-3 columns of one slot at a time — that loop ran at 6 of 32 lanes.
+        {
+            const int32_t n_ins = L - m;                            // = carry
+            for (int32_t q0 = 0; q0 < n_ins; q0 += 32) {
+                const int32_t q = q0 + lane;
+                if (q < n_ins) {
+                    // slot j = number of reference bases whose insertion blocks end at or before the q-th insertion column:
+                    // the insertion columns of slots 0..j total col[j] - j (col[j] = j + sum of widths up to j); find the first j with col[j] - j > q
+                    int lo = 0, hi = m;                             // slot m (after the last base) when no j < m qualifies
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int32_t)col[mid] - mid > q) hi = mid; else lo = mid + 1; }
+                    const int j = lo;
+                    const int w = width[j];
+                    const int before = (j < m ? (int32_t)col[j] - j : n_ins) - w;      // insertion columns of the slots before j
+                    const int kk = q - before;
+                    const int cc = (j < m ? (int32_t)col[j] : L) - w + kk;
+                    int32_t c[5] = {0, 0, 0, 0, 0};
+                    int32_t seen2 = 0;
+                    for (int32_t k = 0; k < cnt && seen2 < n_use; k++) {
+                        if (!member(k)) continue;
+                        seen2++;
+                        const int64_t e = e0 + k;
+                        const uint16_t il = a.e_inslen[e * (a.mmax + 1) + j];
+                        int code = 4;
+                        if (kk < il) { code = a.e_slice[e * a.nmax + a.e_insfirst[e * (a.mmax + 1) + j] + kk]; if (code > 3) code = 4; }
+                        c[code]++;
+                    }
+                    float best = -1.f; int bi = 0;
 #pragma unroll
-                for (int b = 0; b < 5; b++) {
-                    const float f = (float)c[b] / nf;
-                    const float tf = b == 4 ? f - 0.01f : f;
-                    if (tf > best) { best = tf; bi = b; }
-                    if (cc < 128) { T[(b * 128 + cc) * 2] = f - (b == 4 ? 1.f : 0.f); T[(b * 128 + cc) * 2 + 1] = b == 4 ? 1.f : 0.f; }
+                    for (int b = 0; b < 5; b++) {
+                        const float f = (float)c[b] / nf;
+                        const float tf = b == 4 ? f - 0.01f : f;
+                        if (tf > best) { best = tf; bi = b; }
+                        if (cc < 128) { T[(b * 128 + cc) * 2] = f - (b == 4 ? 1.f : 0.f); T[(b * 128 + cc) * 2 + 1] = b == 4 ? 1.f : 0.f; }
+                    }
+                    cns_sym[cc] = (uint8_t)bi;
                 }
-                cns_sym[cc] = (uint8_t)bi;
             }
         }
         __syncwarp();
