@@ -9,6 +9,7 @@ spreads over all GPUs.  Either way chunks stay what they are on one GPU — the 
 (utils.py:72) — so every record is identical to the single-GPU run.  The one exchange is the gather of the ranks' record text to rank 0 (sizes, then padded byte tensors: NCCL on the
 GPU box, gloo in the CPU test), which merges, sorts, compresses and indexes.  (bench.py and host/shard.py shard by chunk.)"""
 import copy
+import pickle
 import os
 
 import numpy as np
@@ -140,20 +141,86 @@ def run_distributed(args, run_fn, regions, dist, device="cpu"):
         raise RuntimeError("nanocaller_b200: another rank failed; rank %d stops" % rank)
     merged = {"rank": rank, "world": world, "sharding": "chunk runs" if by_chunk else "contigs",
               "contigs_per_rank": [sorted({r[0] for r in part}) for part in shares], "regions_per_rank": shares}
+    # Record order of the reference's outputs = contig order, then position, stable (`bcftools sort`).  A rank's files are already in
+    # that order for its share, and the shares are disjoint contigs or consecutive chunk runs, so — as long as the regions of a contig
+    # come in ascending order — the merged file is "for every contig, the ranks' blocks in rank order": rank 0 concatenates bytes and
+    # builds the CSI index from the (position, REF length, line length) arrays the ranks send along, instead of splitting, sorting
+    # and re-parsing millions of lines in Python.
+    ascending = _regions_ascending(regions)
     for key, name, kind in OUTPUT_KINDS:
         have = dist_any(key in out_r, dist, world, device)
         if not have:
             continue
-        text = "".join(vcfio.read_records(out_r[key])).encode() if key in out_r else b""
-        parts = gather_bytes(text, dist, rank, world, device)
-        if rank == 0:
-            lines = [ln + "\n" for p in parts for ln in p.decode().split("\n") if ln]
-            path = os.path.join(args.output, name % args.prefix)
-            vcfio.write_vcf(path, kind, chrom_list, lines, args.sample, index=True)
-            merged[key] = path
-            merged["n_%s_records" % key] = len(lines)
+        lines = vcfio.read_records(out_r[key]) if key in out_r else []
+        if ascending:
+            payload = pickle.dumps(_contig_blocks(lines), protocol=pickle.HIGHEST_PROTOCOL)
+            parts = gather_bytes(payload, dist, rank, world, device)
+            if rank == 0:
+                path = os.path.join(args.output, name % args.prefix)
+                merged["n_%s_records" % key] = _write_blocks(path, kind, chrom_list, [pickle.loads(p) if p else {} for p in parts], args.sample)
+                merged[key] = path
+        else:
+            parts = gather_bytes("".join(lines).encode(), dist, rank, world, device)
+            if rank == 0:
+                lines = [ln + "\n" for p in parts for ln in p.decode().split("\n") if ln]
+                path = os.path.join(args.output, name % args.prefix)
+                vcfio.write_vcf(path, kind, chrom_list, lines, args.sample, index=True)
+                merged[key] = path
+                merged["n_%s_records" % key] = len(lines)
     dist.barrier()
     return merged
+
+
+def _regions_ascending(regions):
+    """True when, per contig, the regions come in ascending, non-overlapping order (then rank order = genomic order)."""
+    last = {}
+    for c, s_, e, _ in regions:
+        if c in last and s_ < last[c]:
+            return False
+        last[c] = e
+    return True
+
+
+def _contig_blocks(lines):
+    """Record lines of one rank (sorted) -> {contig: (text bytes, pos int64[n], ref allele length int32[n], line length int32[n])}."""
+    out = {}
+    cur, buf, pos, rl, ll = None, [], [], [], []
+
+    def flush():
+        if cur is not None:
+            out[cur] = ("".join(buf).encode(), np.asarray(pos, np.int64), np.asarray(rl, np.int32), np.asarray(ll, np.int32))
+    for ln in lines:
+        f = ln.split("\t", 4)
+        if f[0] != cur:
+            flush()
+            cur, buf, pos, rl, ll = f[0], [], [], [], []
+        buf.append(ln); pos.append(int(f[1])); rl.append(len(f[3])); ll.append(len(ln.encode()) if not ln.isascii() else len(ln))
+    flush()
+    return out
+
+
+def _write_blocks(path, kind, chrom_list, rank_blocks, sample):
+    """header + for every contig the ranks' blocks in rank order -> BGZF + CSI.  -> number of records."""
+    from . import vcfio
+    head = vcfio.header(kind, chrom_list, sample).encode()
+    names = list(chrom_list)
+    body, rid, beg, end, nb = [], [], [], [], []
+    seen = set(names)
+    extra = [c for blocks in rank_blocks for c in blocks if c not in seen and not seen.add(c)]
+    for ci, c in enumerate(names + extra):
+        for blocks in rank_blocks:
+            if c in blocks:
+                text, pos, rl, ll = blocks[c]
+                body.append(text)
+                rid.append(np.full(len(pos), ci, np.int64)); beg.append(pos - 1); end.append(pos - 1 + np.maximum(1, rl)); nb.append(ll.astype(np.int64))
+    data = head + b"".join(body)
+    if rid:
+        rid, beg, end, nb = np.concatenate(rid), np.concatenate(beg), np.concatenate(end), np.concatenate(nb)
+        u0 = len(head) + np.concatenate([[0], np.cumsum(nb)[:-1]])
+    else:
+        rid = beg = end = nb = u0 = np.zeros(0, np.int64)
+    vcfio.write_indexed(path, data, records=(names + extra, rid, beg, end, u0, nb))
+    return int(len(rid))
 
 
 def dist_any(flag, dist, world, device="cpu"):
