@@ -1139,13 +1139,29 @@ int nc_indel_build(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int
         // direction rows 1..n, n <= window_after; strips of 6 columns cover reference windows up to 192 columns (ONT: 161), 9 up to 288
         const int rows = (P->window_after + 2 + 1) & ~1;            // even: keeps the per-warp blocks 16-byte aligned with 2-byte words
         const bool narrow = P->window_after + 1 <= 192;
-        const int smem = kAlignWarps * align_smem_per_warp(rows, narrow ? 2 : 4);
         // function attributes are per device and one process may open contexts on several: set it on every call (cheap, no sync)
-        if (narrow) NC_CUDA(cudaFuncSetAttribute(indel_align_kernel<6, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        else NC_CUDA(cudaFuncSetAttribute(indel_align_kernel<9, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_entries, kAlignWarps), (int64_t)c->sm_count * 16);
-        if (narrow) indel_align_kernel<6, uint16_t><<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries, rows);
-        else indel_align_kernel<9, uint32_t><<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries, rows);
+        if (narrow) {
+            // two slices of a site per warp step (16-bit SIMD halves), one warp per site; as many warps as the direction words let fit
+            constexpr int kW = 11;
+            const int rs = P->window_after / 6 + 1;                   // lane strips in use: reference windows have <= window_after + 1 columns
+            int smem = kW * align2_smem_per_warp(P->window_after, rs);
+            if (smem <= 227 * 1024 - 1024) {
+                NC_CUDA(cudaFuncSetAttribute(indel_align2_kernel<6, kW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_sites, kW), (int64_t)c->sm_count);
+                indel_align2_kernel<6, kW><<<ag, kW * 32, smem, c->stream>>>(sa, rs);
+            } else {
+                constexpr int kW2 = 6;
+                smem = kW2 * align2_smem_per_warp(P->window_after, rs);
+                NC_CUDA(cudaFuncSetAttribute(indel_align2_kernel<6, kW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_sites, kW2), (int64_t)c->sm_count);
+                indel_align2_kernel<6, kW2><<<ag, kW2 * 32, smem, c->stream>>>(sa, rs);
+            }
+        } else {
+            const int smem = kAlignWarps * align_smem_per_warp(rows, 4);
+            NC_CUDA(cudaFuncSetAttribute(indel_align_kernel<9, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_entries, kAlignWarps), (int64_t)c->sm_count * 16);
+            indel_align_kernel<9, uint32_t><<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries, rows);
+        }
         NC_LAUNCH_CHECK();
     }
     NC_CUDA(cudaEventRecord(c->evi[4], c->stream));

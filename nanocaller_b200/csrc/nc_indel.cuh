@@ -732,6 +732,203 @@ __global__ void __launch_bounds__(kAlignWarps * 32) indel_align_kernel(const Sit
     }
 }
 
+// The same alignment, two slices of one site at a time in the halves of 32-bit registers (windows up to 8 columns per lane strip).
+//   * A cell value is V = 4 H + tie with tie = 2 (DIAG), 1 (UP), 0 (LEFT) in the two low bits: max(V_diag, V_up, V_left) then IS the
+//     reference's choice (DIAG if the diagonal attains the maximum, else UP, else LEFT) and its low bits are the direction — no
+//     compares.  |4 H| <= 12 (n + m) < 2^15, so a cell fits 16 bits and VIADD.16x2 / VIADDMNMX.S16x2 do two slices per instruction.
+//   * Both slices see the same reference window, so the substitution scores of a strip column are one register of four bytes
+//     (score against A, G, T, C) and the scores of the two read bases of a row are ONE byte permute with a per-row selector
+//     (sign-replicating prmt; selector 4 = the all-mismatch constant serves N and the rows past a slice's end).
+//   * One warp per site walks the site's slices pair by pair (the reference strip is set up once per site); lanes 0 and 1 trace the
+//     two paths back at the same time.
+// Per pair and strip column: prmt, add, 2 x add-max, and-mask, shift, or-and = 7 instructions for two cells (the scalar kernel: ~12
+// per cell).
+constexpr int kAlign2Aux = 2 * (272 + 32) + 2 * (272 + 2 * 272);   // row selectors (u16, 32 entries of padding in front); per half: slice (u8), traceback record per reference column (u16)
+// direction words: rows -2 .. wa (row 0 and the two rows above it are all LEFT / never read as directions), `rs` words per row = lane
+// strips in use (27 for the 161-column ONT window): 17.6 KB per pair, 11 warps per SM
+__host__ __device__ constexpr int align2_smem_per_warp(int wa, int rs) { return (((wa + 3) * rs * 4 + 15) & ~15) + kAlign2Aux; }
+__device__ __forceinline__ uint32_t pack2_s16(int32_t x) { return ((uint32_t)x & 0xFFFFu) | ((uint32_t)x << 16); }
+__device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+
+template <int CW, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) indel_align2_kernel(const SiteArgs a, int rs) {
+    static_assert(CW <= 8, "two direction bits per column and half");
+    extern __shared__ __align__(16) uint8_t s_align_all[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint8_t* s_base = s_align_all + (size_t)wib * align2_smem_per_warp(a.wa, rs);
+    uint32_t* s_dir = reinterpret_cast<uint32_t*>(s_base) + 2 * rs;              // [row -2 .. wa][rs]: half h = slice h, 2 bits per strip column, column 0 highest
+    uint16_t* s_sel = reinterpret_cast<uint16_t*>(s_base + (((a.wa + 3) * rs * 4 + 15) & ~15));   // [272]
+    uint8_t* s_half = reinterpret_cast<uint8_t*>(s_sel + 272 + 32);              // per half: slice[272], rec[272 u16]
+    constexpr int kHalfBytes = 272 + 2 * 272;
+    for (int i = lane; i < 3 * rs; i += 32) s_dir[i - 2 * rs] = 0u;             // rows <= 0 = LEFT everywhere: a path that has used up its read walks left
+    const uint32_t full = 0xffffffffu;
+    const uint32_t kMis = 0xF2F2F2F2u;                                          // 4 * (-4) + 2 in every byte
+    const uint32_t kUp = 0xFFF5FFF5u, kLeft = 0xFFF4FFF4u;                      // 4 * (-3) + 1, 4 * (-3) + 0
+#ifdef NC_ALIGN_PROFILE
+    long long prof[5] = {0, 0, 0, 0, 0}, pl = clock64(); int prof_n = 0;
+#define NC_AMARK(i) { const long long now_ = clock64(); prof[i] += now_ - pl; pl = now_; }
+#else
+#define NC_AMARK(i)
+#endif
+    for (int64_t s = (int64_t)blockIdx.x * WARPS + wib; s < a.n_sites; s += (int64_t)gridDim.x * WARPS) {
+        const int64_t e0 = __ldg(a.site_off + s), e1 = __ldg(a.site_off + s + 1);
+        const int32_t m = a.site_m[s];
+        if (e1 <= e0 || m <= 0) continue;
+        const int32_t p = a.sites[s].key - 1;
+        // scores of the strip's reference columns against read base 0..3: match 4 * 2 + 2, mismatch 4 * (-4) + 2
+        uint32_t S[CW];
+#pragma unroll
+        for (int k = 0; k < CW; k++) {
+            const int j = lane * CW + k;
+            const int rc = j < m ? ref_code_of(__ldg(a.ref + ((int64_t)p + j - a.ref_start))) : 7;
+            S[k] = rc < 4 ? (kMis ^ (0xF8u << (8 * rc))) : kMis;                // 0xF2 ^ 0xF8 = 0x0A
+        }
+        const int last_lane = (m - 1) / CW;                                     // < rs
+        for (int64_t e = e0; e < e1; e += 2) {
+            const bool two = e + 1 < e1;
+            NC_AMARK(0);
+            int32_t nh[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint8_t* sl = s_half + h * kHalfBytes;
+                int32_t n = 0;
+                if (h == 0 || two) {
+                    const int64_t ri = a.e_read[e + h];
+                    const int32_t q0 = a.e_qpn[e + h], lseq = __ldg(a.l_seq + ri);
+                    n = max(0, min(a.wa, lseq - q0));
+                    const uint8_t* sq = a.seq4 + __ldg(a.seq_off + ri);
+                    uint8_t* o_slice = a.e_slice + (e + h) * a.nmax;
+                    for (int i = lane; i < n; i += 32) {
+                        const int32_t q = q0 + i;
+                        const uint32_t b = __ldg(sq + (q >> 1));
+                        const uint32_t bn = (q & 1) ? (b & 15u) : (b >> 4);
+                        const uint8_t c = (uint8_t)((kNibToCode >> (4 * bn)) & 15u);
+                        sl[i] = c; o_slice[i] = c;
+                    }
+                }
+                nh[h] = n;
+            }
+            const int32_t nmax = max(nh[0], nh[1]);
+            __syncwarp();
+            for (int i = lane; i < nmax; i += 32) {
+                const uint32_t ra = i < nh[0] ? s_half[i] : 4u, rb = i < nh[1] ? s_half[kHalfBytes + i] : 4u;
+                s_sel[32 + i] = (uint16_t)(ra | ((ra | 8u) << 4) | (rb << 8) | ((rb | 8u) << 12));
+            }
+            __syncwarp();
+            NC_AMARK(1);
+            // wavefront: lane l works on row t - l
+            uint32_t hp[CW];
+#pragma unroll
+            for (int k = 0; k < CW; k++) hp[k] = pack2_s16(-12 * (lane * CW + k + 1));
+            uint32_t h_left_prev = pack2_s16(-12 * (lane * CW));
+            uint32_t last_out = 0;
+            const int t_end = nmax + last_lane;
+            // The row selector is loaded one step ahead (s_sel is padded by 32 entries in front: lanes that have not started yet read
+            // unused values).  (A variant with a one-instruction serial chain per column — the tie bits cleared off the chain — was
+            // slower: the kernel is bound by instruction issue, not by the chain's latency.)
+            uint32_t sel = s_sel[32 - lane];                                    // row 1 - lane ... (index i - 1 + 32)
+            for (int t = 1; t <= t_end; t++) {
+                const uint32_t from_left = __shfl_up_sync(full, last_out, 1);
+                const int i = t - lane;
+                const uint32_t sel_next = s_sel[32 + i];
+                if (i >= 1 && i <= nmax && lane <= last_lane) {
+                    const uint32_t h_left_cur = lane == 0 ? pack2_s16(-12 * i) : from_left;
+                    uint32_t diag_in = h_left_prev, left = h_left_cur, dw = 0;
+#pragma unroll
+                    for (int k = 0; k < CW; k++) {
+                        const uint32_t dg = __vadd2(diag_in, prmt_sx(S[k], kMis, sel));
+                        const uint32_t b = __viaddmax_s16x2(left, kLeft, __viaddmax_s16x2(hp[k], kUp, dg));
+                        dw = (dw << 2) | (b & 0x00030003u);
+                        diag_in = hp[k];
+                        hp[k] = left = b & 0xFFFCFFFCu;
+                    }
+                    s_dir[i * rs + lane] = dw;
+                    h_left_prev = h_left_cur;
+                    last_out = left;
+                }
+                sel = sel_next;
+            }
+            __syncwarp();
+            NC_AMARK(2);
+            // traceback from (n, m): lane h follows slice h.  The sequential loop only records, per reference column j, the row at
+            // which the path leaves it and whether it leaves diagonally; codes and insertion tables follow from that in parallel.
+            // It is branch-free (the two lanes would diverge on every branch), and the direction words of the two rows above the
+            // current one are loaded ahead, so that a step's dependent chain is shift, mask, compare, select instead of a
+            // shared-memory round trip; only a new strip (every CW-th column) reloads.
+            if (lane < 2 && (lane == 0 || two)) {
+                const int n_me = lane == 0 ? nh[0] : nh[1];
+                const uint32_t rec0 = smem_u32(s_half + lane * kHalfBytes + 272);           // rec[0]
+                const uint32_t rsb = (uint32_t)rs * 4u;
+                const int jl0 = (m - 1) / CW;
+                uint32_t ad = smem_u32(s_dir + n_me * rs + jl0);
+                uint32_t rp = rec0 + 2u * (uint32_t)m;
+                const uint32_t sh_lo = 16u * lane, sh_wrap = sh_lo + 2u * CW;
+                uint32_t sh = sh_lo + 2u * (uint32_t)(CW - 1 - ((m - 1) - jl0 * CW));
+                uint32_t i2 = (uint32_t)n_me << 1;                                          // 2 i
+                uint32_t w_cur = lds_u32(ad), w_up = lds_u32(ad - rsb), w_up2 = lds_u32(ad - 2u * rsb);
+#pragma unroll 2
+                while (rp != rec0) {
+                    const uint32_t d = (w_cur >> sh) & 3u;                                  // 2 DIAG, 1 UP, 0 LEFT
+                    const bool cm = d != 1u, rm = d != 0u;
+                    if (cm) asm volatile("st.shared.u16 [%0], %1;" :: "r"(rp), "h"((uint16_t)(i2 | (d >> 1))) : "memory");
+                    rp -= cm ? 2u : 0u;
+                    sh += cm ? 2u : 0u;
+                    i2 -= rm ? 2u : 0u;
+                    ad -= rm ? rsb : 0u;
+                    const bool wrap = sh == sh_wrap && rp != rec0;                        // (not past column 1: strip -1 does not exist)
+                    ad -= wrap ? 4u : 0u;
+                    sh = wrap ? sh_lo : sh;
+                    const uint32_t nw = lds_u32(ad - 2u * rsb);                             // in use two row moves from now
+                    w_cur = rm ? w_up : w_cur;
+                    w_up = rm ? w_up2 : w_up;
+                    w_up2 = nw;
+                    if (wrap) { w_cur = lds_u32(ad); w_up = lds_u32(ad - rsb); }
+                }
+                a.e_n[e + lane] = n_me;
+            }
+            __syncwarp();
+            NC_AMARK(3);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (h == 1 && !two) break;
+                const uint8_t* sl = s_half + h * kHalfBytes;
+                const uint16_t* rec = reinterpret_cast<const uint16_t*>(sl + 272);
+                uint8_t* o_ac = a.e_acode + (e + h) * a.mmax;
+                uint16_t* o_il = a.e_inslen + (e + h) * (a.mmax + 1);
+                uint16_t* o_if = a.e_insfirst + (e + h) * (a.mmax + 1);
+                for (int j = lane; j <= m; j += 32) {
+                    // row at which the path arrives at column j; rows above the row it leaves at are the bases inserted after column j
+                    const int32_t arrive = j == m ? nh[h] : (int32_t)(rec[j + 1] >> 1) - (int32_t)(rec[j + 1] & 1u);
+                    int32_t leave = 0;
+                    if (j > 0) {
+                        const uint32_t r = rec[j];
+                        leave = (int32_t)(r >> 1);
+                        o_ac[j - 1] = (r & 1u) ? sl[leave - 1] : (uint8_t)5;
+                    }
+                    const int32_t il = arrive - leave;
+                    o_il[j] = (uint16_t)il;
+                    o_if[j] = (uint16_t)(il > 0 ? leave : 0);
+                }
+            }
+            __syncwarp();
+            NC_AMARK(4);
+#ifdef NC_ALIGN_PROFILE
+            prof_n++;
+#endif
+        }
+    }
+#ifdef NC_ALIGN_PROFILE
+    if (blockIdx.x == 7 && threadIdx.x == 0 && prof_n > 0)
+        printf("align2 profile pairs=%d cycles/pair: other %lld setup %lld wave %lld trace %lld out %lld\n", prof_n, prof[0] / prof_n, prof[1] / prof_n, prof[2] / prof_n, prof[3] / prof_n, prof[4] / prof_n);
+#endif
+#undef NC_AMARK
+}
+
 // Star alignment step 2 + `msa` tensor assembly (:54-71): one warp per (site, group); group 0 = HP1, 1 = HP2, 2 = all reads.
 __global__ void __launch_bounds__(96) indel_msa_kernel(const SiteArgs a) {
     __shared__ uint16_t s_width[3][kRowsMax + 8];
