@@ -231,22 +231,26 @@ __global__ void __launch_bounds__(256) seq_codes_kernel(const uint4* __restrict_
 
 // ------------------------------------------------------------------------------------------------
 // K0b — aligned-row fill: one CTA per read (reads handed out dynamically, long reads dominate), a
-// warp per block of 32 output words (256 reference positions).
+// warp per block of 64 output words (512 reference positions), a lane per 16 positions.
 //   1. one linear pass over the read's ops records, per block, the op containing the block's first
 //      position (shared memory);
-//   2. the warp stages the block's ops (typically ~24 for ONT), counts for every reference-consuming
-//      op the words it touches, scans the counts and writes one entry per (op, word) SEGMENT;
-//   3. lanes take segments, not words (a word has 1..8 segments; lanes-as-words ran at 30 % lane
-//      occupancy): a match segment is a funnel shift of two words of query codes, a deletion is a
-//      constant; the partial word is AND-ed into the block's 32 words in shared memory (0xF = not
-//      covered is the identity), and the block is stored with one coalesced 128-byte write.
+//   2. the warp stages the block's reference-consuming ops in order (one 32-bit entry each: the
+//      read-relative query index that reference offset 0 would have under the op, and whether it is
+//      a match) and sets one bit per op START inside the block in a 512-bit mask: the ordinal of
+//      the op a position belongs to is then a population count of the mask up to that position;
+//   3. a lane builds its own two words: the 16 mask bits of its positions (plus a cut between the
+//      two words) split them into runs of one op each (3 on average for ONT); a match run is a
+//      funnel shift of two words of query codes, a deletion is a constant.  No atomics and no
+//      per-segment tables; all index arithmetic is 32-bit and relative to the read.
+// History in DESIGN 4.2 (lanes as words, lanes as (op, word) segments, this).
 // ------------------------------------------------------------------------------------------------
 constexpr int kFillThreads = 128;
 constexpr int kFillWarps = kFillThreads / 32;
-constexpr int kFillIdx = 1024;           // blocks indexed in shared memory (reads up to 262 kb; longer reads: per-word global search)
-constexpr int kFillOps = 96;             // ops staged per block (more: per-word global search for that block)
+constexpr int kFillIdx = 1024;           // blocks indexed in shared memory (reads up to 524 kb; longer reads: per-word global search)
+constexpr int kFillOps = 192;            // ops staged per block (more: per-word global search for that block)
 
 __device__ __forceinline__ uint32_t nib_mask(int n) { return n >= 8 ? 0xFFFFFFFFu : ((1u << (4 * n)) - 1u); }   // n low nibbles
+__device__ __forceinline__ uint32_t nib_mask_1to8(int n) { return 0xFFFFFFFFu >> (32 - 4 * n); }                 // 1 <= n <= 8
 // tensor codes of the 8 query bases starting at absolute base index Q
 __device__ __forceinline__ uint32_t fetch_codes8(const uint32_t* __restrict__ codes, int64_t Q) {
     return __funnelshift_r(__ldg(codes + (Q >> 3)), __ldg(codes + (Q >> 3) + 1), 4 * (int)(Q & 7));
@@ -293,13 +297,8 @@ __global__ void __launch_bounds__(kFillThreads) row_fill_kernel(const int32_t* _
                                                        uint32_t* __restrict__ rows, int64_t n_reads,
                                                        unsigned long long* __restrict__ next_read) {
     __shared__ int32_t s_idx[kFillIdx + 1];
-    __shared__ int32_t s_x[kFillWarps][kFillOps];            // reference start of the op (read-relative)
-    __shared__ uint32_t s_xe[kFillWarps][kFillOps];          // reference end, bit 31 set when the op is not a match (D / N)
-    __shared__ long long s_q[kFillWarps][kFillOps];          // absolute query base index of reference offset 0 under this op
-    __shared__ uint16_t s_pref[kFillWarps][kFillOps];        // first segment of the op
-    __shared__ uint8_t s_wf[kFillWarps][kFillOps];           // first word of the op inside the block
-    __shared__ uint8_t s_segop[kFillWarps][32 + kFillOps];   // segment -> staged op
-    __shared__ uint32_t s_word[kFillWarps][32];
+    __shared__ int32_t s_q[kFillWarps][kFillOps];            // per reference-consuming op of the block: (query index of reference offset 0, read-relative) << 1 | not a match
+    __shared__ uint32_t s_mark[kFillWarps][16];              // bit t: an op starts at block position t (t > 0)
     __shared__ long long s_read;
     const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
     for (;;) {
@@ -315,80 +314,96 @@ __global__ void __launch_bounds__(kFillThreads) row_fill_kernel(const int32_t* _
         const int32_t nops = (int32_t)(cigar_off[r + 1] - c0);
         const int32_t lseq = l_seq[r];
         const int64_t q_base = 2 * seq_off[r];                  // absolute index of the read's first base
+        const uint32_t* __restrict__ cbase = codes + (q_base >> 3);
+        const int32_t qb7 = (int32_t)(q_base & 7);
         uint32_t* __restrict__ out = rows + rowoff[r];
-        const int32_t nblk = (nw + 31) >> 5;
+        const int32_t nblk = (nw + 63) >> 6;
         if (nblk > kFillIdx) {                                  // longer than the shared index: every word searches all ops
             for (int32_t w = tid; w < nw; w += kFillThreads) out[w] = fill_word_global(opstart + c0, cigar + c0, nops, 8 * w - d, span, lseq, codes, q_base);
             continue;
         }
-        // ---- 1. per block b, the op containing its first position max(256 b - d, 0)
+        // ---- 1. per block b, the op containing its first position max(512 b - d, 0)
         for (int32_t k = tid; k < nops; k += kFillThreads) {
             const int32_t rl = cig_ref_len(__ldg(cigar + c0 + k));
             if (rl == 0) continue;
             const int32_t x = __ldg(&opstart[c0 + k].x);
-            const int32_t b_lo = x == 0 ? 0 : (x + d + 255) >> 8, b_hi = min((x + rl - 1 + d) >> 8, nblk - 1);
+            const int32_t b_lo = x == 0 ? 0 : (x + d + 511) >> 9, b_hi = min((x + rl - 1 + d) >> 9, nblk - 1);
             for (int32_t b = b_lo; b <= b_hi; b++) s_idx[b] = k;
         }
         __syncthreads();
         // ---- 2. a warp per block
         for (int32_t b = wi; b < nblk; b += kFillWarps) {
             const int32_t k0 = s_idx[b], k1 = b + 1 < nblk ? s_idx[b + 1] : nops - 1;
-            const int32_t n = k1 - k0 + 1, w = 32 * b + lane;
-            const int32_t o_blk = 256 * b - d;                  // read-relative offset of the block's first nibble
+            const int32_t n = k1 - k0 + 1, w0 = 64 * b + 2 * lane;
+            const int32_t o_blk = 512 * b - d;                  // read-relative offset of the block's first nibble
             if (n > kFillOps) {
-                if (w < nw) out[w] = fill_word_global(opstart + c0 + k0, cigar + c0 + k0, n, 8 * w - d, span, lseq, codes, q_base);
+                if (w0 < nw) out[w0] = fill_word_global(opstart + c0 + k0, cigar + c0 + k0, n, 8 * w0 - d, span, lseq, codes, q_base);
+                if (w0 + 1 < nw) out[w0 + 1] = fill_word_global(opstart + c0 + k0, cigar + c0 + k0, n, 8 * (w0 + 1) - d, span, lseq, codes, q_base);
                 continue;
             }
+            __syncwarp();                                       // the previous block's tables are no longer in use
+            if (lane < 16) s_mark[wi][lane] = 0u;
             __syncwarp();
-            s_word[wi][lane] = 0xFFFFFFFFu;
-            int32_t carry = 0;
+            int32_t n_ref = 0;
+            const int32_t first_cov = max(o_blk, 0);            // the op under the block's first covered position has ordinal 0: no mark
             for (int32_t j0 = 0; j0 < n; j0 += 32) {
                 const int32_t j = j0 + lane;
-                int32_t cnt = 0, wf = 0;
+                bool is_ref = false;
+                uint32_t cw = 0; int2 st = make_int2(0, 0);
                 if (j < n) {
-                    const uint32_t cw = __ldg(cigar + c0 + k0 + j);
-                    const int2 st = __ldg(opstart + c0 + k0 + j);
-                    const int32_t rl = cig_ref_len(cw);
-                    s_x[wi][j] = st.x;
-                    s_xe[wi][j] = (uint32_t)(st.x + rl) | (cig_is_match(cw) ? 0u : 0x80000000u);
-                    s_q[wi][j] = q_base + st.y - st.x;
-                    if (rl > 0) {
-                        wf = max(st.x - o_blk, 0) >> 3;
-                        const int32_t wl = min((st.x + rl - 1 - o_blk) >> 3, 31);
-                        cnt = max(wl - wf + 1, 0);             // 0 when the op lies before the block (cannot happen) or after it
-                    }
-                    s_wf[wi][j] = (uint8_t)wf;
+                    cw = __ldg(cigar + c0 + k0 + j);
+                    st = __ldg(opstart + c0 + k0 + j);
+                    is_ref = cig_ref_len(cw) > 0;
                 }
-                const int32_t inc = warp_incl_scan32(cnt, lane);
-                const int32_t first = carry + inc - cnt;
-                if (j < n) s_pref[wi][j] = (uint16_t)first;
-                for (int32_t i = 0; i < cnt; i++) s_segop[wi][first + i] = (uint8_t)j;
-                carry += __shfl_sync(0xffffffffu, inc, 31);
+                const uint32_t bal = __ballot_sync(0xffffffffu, is_ref);
+                if (is_ref) {
+                    s_q[wi][n_ref + __popc(bal & ((1u << lane) - 1u))] = (st.y - st.x) * 2 + (cig_is_match(cw) ? 0 : 1);
+                    const int32_t rel = st.x - o_blk;
+                    if (st.x > first_cov && rel < 512) atomicOr(&s_mark[wi][rel >> 5], 1u << (rel & 31));
+                }
+                n_ref += __popc(bal);
             }
             __syncwarp();
-            // ---- 3. lanes take segments
-            const int64_t q_end = q_base + lseq;
-            for (int32_t sg = lane; sg < carry; sg += 32) {
-                const int32_t j = s_segop[wi][sg];
-                const int32_t ww = (int32_t)s_wf[wi][j] + (sg - (int32_t)s_pref[wi][j]);
-                const int32_t o_w = o_blk + 8 * ww;
-                const uint32_t xe_enc = s_xe[wi][j];
-                const int32_t s0 = max(s_x[wi][j], o_w), s1 = min((int32_t)(xe_enc & 0x7FFFFFFFu), o_w + 8);
-                const int t = s0 - o_w, L = s1 - s0;           // 1 <= L <= 8
-                uint32_t vals = 0x44444444u;                    // '*': deletion, ref-skip, base beyond l_seq
-                if (!(xe_enc & 0x80000000u)) {
-                    const int64_t Q = s_q[wi][j] + s0;
-                    const int64_t left = q_end - Q;             // bases that exist from here on
-                    if (left > 0) {
-                        const uint32_t m = nib_mask((int)min((int64_t)L, left));
-                        vals = (fetch_codes8(codes, Q) & m) | (vals & ~m);
+            // ordinal of the op at the lane's first position = marks before it
+            const uint32_t mw = s_mark[wi][lane >> 1];
+            int32_t before = lane < 16 ? __popc(s_mark[wi][lane]) : 0;
+            before = warp_incl_scan32(before, lane) - before;                    // marks in the mask words before word `lane`
+            before = __shfl_sync(0xffffffffu, before, lane >> 1);
+            const int sh16 = 16 * (lane & 1);
+            const uint32_t m16 = (mw >> sh16) & 0xFFFFu;                          // op starts inside the lane's 16 positions
+            const uint32_t cuts = m16 | 0x100u;                                   // ... and the cut between its two words
+            int32_t ord = before + __popc(mw & ((1u << sh16) - 1u));
+            const int32_t o_w = o_blk + 16 * lane;                                // read-relative offset of position 0
+            const int t_lo = o_w < 0 ? -o_w : 0, t_hi = min(16, span - o_w);      // positions the read covers
+            uint32_t lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu;                          // 0xF = not covered
+            if (t_lo < t_hi) {
+                ord += __popc(m16 & ((2u << t_lo) - 1u));
+                int u = t_lo;
+                while (u < t_hi) {
+                    const uint32_t rest = cuts >> (u + 1);
+                    const int nxt = min(rest ? u + __ffs(rest) : 16, t_hi);
+                    const int L = nxt - u;                                        // 1..8 positions of one op inside one word
+                    const int32_t e = s_q[wi][ord];
+                    uint32_t vals = 0x44444444u;                                  // '*': deletion, ref-skip, base beyond l_seq
+                    if (!(e & 1)) {
+                        const int32_t q = (e >> 1) + o_w + u;                     // query index within the read
+                        const int Lv = min(L, lseq - q);                          // bases that exist
+                        if (Lv > 0) {
+                            const int32_t Q = q + qb7;
+                            const uint32_t m = nib_mask_1to8(Lv);
+                            vals = (__funnelshift_r(__ldg(cbase + (Q >> 3)), __ldg(cbase + (Q >> 3) + 1), 4 * (Q & 7)) & m) | (vals & ~m);
+                        }
                     }
+                    const int un = u & 7;
+                    const uint32_t m = nib_mask_1to8(L) << (4 * un);
+                    const uint32_t ins = (vals << (4 * un)) & m;
+                    if (u < 8) lo = (lo & ~m) | ins; else hi = (hi & ~m) | ins;
+                    ord += (int32_t)((m16 >> nxt) & 1u);                          // the cut between the words is not an op start by itself
+                    u = nxt;
                 }
-                const uint32_t m = nib_mask(L) << (4 * t);
-                atomicAnd(&s_word[wi][ww], ((vals << (4 * t)) & m) | ~m);
             }
-            __syncwarp();
-            if (w < nw) out[w] = s_word[wi][lane];
+            if (w0 < nw) out[w0] = lo;
+            if (w0 + 1 < nw) out[w0 + 1] = hi;
         }
     }
 }
