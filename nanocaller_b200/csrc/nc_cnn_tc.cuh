@@ -565,8 +565,14 @@ struct TBParams {
     const uint8_t* wimg; const float* bias;
     uint8_t* c3_out; int* err;
 };
-constexpr int TB_WGS = 3;
-constexpr int TB_THREADS = TB_WGS * 128 + 32;               // three consumer warpgroups + one TMA producer warp
+// Two consumer warpgroups, not three: a stage stays occupied from the arrival of its image until its MMAs have completed, so with
+// a ring of five (all that fits beside the weights) three consumers leave two copies in flight per SM and two consumers three —
+// the kernel is bound by bytes in flight, not by the tensor pipe (2.7 -> 2.4 ms for configs[1]).
+#ifndef NC_TB_WGS
+#define NC_TB_WGS 2
+#endif
+constexpr int TB_WGS = NC_TB_WGS;
+constexpr int TB_THREADS = TB_WGS * 128 + 32;               // consumer warpgroups + one TMA producer warp
 #ifndef NC_TB_RING
 #define NC_TB_RING 5
 #endif

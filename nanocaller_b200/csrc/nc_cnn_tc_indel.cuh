@@ -302,7 +302,10 @@ struct IBParams {
     uint8_t* c3_out;                          // [site][position][192 B]
     int* err;
 };
-constexpr int IB_WGS = 3;
+#ifndef NC_IB_WGS
+#define NC_IB_WGS 2             // as in TB: fewer consumers = more slab copies in flight out of the ring of four
+#endif
+constexpr int IB_WGS = NC_IB_WGS;
 constexpr int IB_THREADS = IB_WGS * 128 + 32;
 constexpr int IB_RING = 4;
 constexpr int IB_SMEM_RING = IB_RING * tci::SLAB_BYTES + 256;
