@@ -300,7 +300,9 @@ __global__ void indel_decide_kernel(const DecideArgs a) {
     else if (hit) atomicAdd(a.n_hits, 1ull);
 }
 
-// I1.4 greedy pass with `prev` (:249,267,273): one warp per chunk walks its columns in order.
+// I1.4 greedy pass with `prev` (:249,267,273): one warp per chunk walks its columns in order.  Hits are sparse (tens per 100 kb chunk)
+// and the walk is one dependent step per 32 columns, so the time is load latency: a lane fetches the flags of eight 32-column groups
+// at once, positions are only read for the hits (the per-chunk time does not depend on the contig, 1.65 ms before, for any size).
 __global__ void indel_greedy_kernel(const IndelChunk* __restrict__ chunks, int32_t n_chunks, const uint8_t* __restrict__ hit,
                                     const int32_t* __restrict__ em_pos, int32_t win, NcIndelVariant* __restrict__ out,
                                     unsigned long long* __restrict__ n_out) {
@@ -308,24 +310,27 @@ __global__ void indel_greedy_kernel(const IndelChunk* __restrict__ chunks, int32
     if (c >= n_chunks) return;
     const IndelChunk ch = chunks[c];
     int32_t prev = 0;
-    for (int32_t r0 = 0; r0 < ch.n_em; r0 += 32) {
-        const int32_t r = r0 + lane;
-        int h = 0; int32_t v = 0;
-        if (r < ch.n_em) { h = hit[ch.rank_off + r]; v = em_pos[ch.grank_lo + r] + 1; }
-        uint32_t m = __ballot_sync(0xffffffffu, h != 0);
-        while (m) {
-            const int l = __ffs(m) - 1;
-            m &= m - 1;
-            const int hl = __shfl_sync(0xffffffffu, h, l);
-            const int32_t vl = __shfl_sync(0xffffffffu, v, l);
-            if (vl <= prev) continue;
-            const int32_t back = hl == 1 ? win : 10;
-            prev = vl + back;
-            if (lane == 0) {
-                const unsigned long long slot = atomicAdd(n_out, 1ull);
-                NcIndelVariant nv; nv.key = max(1, vl - back); nv.type = hl == 1 ? 0 : 1; nv.chunk = c;
-                nv.src = hl == 3 ? vl : 0;             // extra_variants: the read sets come from this column (:302)
-                out[slot] = nv;
+    for (int32_t r0 = 0; r0 < ch.n_em; r0 += 256) {
+        int h[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int32_t r = r0 + 32 * k + lane; h[k] = r < ch.n_em ? (int)__ldg(hit + ch.rank_off + r) : 0; }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t m = __ballot_sync(0xffffffffu, h[k] != 0);
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const int hl = __shfl_sync(0xffffffffu, h[k], l);
+                const int32_t vl = __ldg(em_pos + ch.grank_lo + r0 + 32 * k + l) + 1;
+                if (vl <= prev) continue;
+                const int32_t back = hl == 1 ? win : 10;
+                prev = vl + back;
+                if (lane == 0) {
+                    const unsigned long long slot = atomicAdd(n_out, 1ull);
+                    NcIndelVariant nv; nv.key = max(1, vl - back); nv.type = hl == 1 ? 0 : 1; nv.chunk = c;
+                    nv.src = hl == 3 ? vl : 0;             // extra_variants: the read sets come from this column (:302)
+                    out[slot] = nv;
+                }
             }
         }
     }
