@@ -1170,7 +1170,9 @@ int nc_indel_build(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int
     {
         // I4: consensus x reference window -> allele lengths (generate_indel_pileups.py:77-127), one warp per (site, group)
         const bool narrow = P->window_after + 1 <= 192;
-        const int64_t n_warps = std::min<int64_t>(n_sites * 3, (int64_t)c->sm_count * 16);
+        // 32 resident warps per SM (64 registers): an alignment is ~230 k cycles of mostly latency (wavefront steps, then the traceback and
+        // the walk on one lane through the L2-resident scratch), so the kernel's rate is warps / latency
+        const int64_t n_warps = std::min<int64_t>(n_sites * 3, (int64_t)c->sm_count * 32);
         const int rows_cap = NC_INDEL_CNS_MAX + 1;
         NC_CUDA(c->d_ialleles.reserve((size_t)n_sites * 3 * 2 * sizeof(int32_t)));
         NC_CUDA(c->d_allele_dirs.reserve((size_t)n_warps * rows_cap * 32 * (narrow ? 4 : 8)));

@@ -1101,7 +1101,7 @@ __global__ void __launch_bounds__(128) indel_allele_kernel(const AlleleArgs a) {
     WordT* dirs = reinterpret_cast<WordT*>(a.scratch) + warp_global * (int64_t)a.rows_cap * 32;
     uint8_t* ops = a.ops_scratch + warp_global * (int64_t)(a.cmax + 272);
     const uint32_t full = 0xffffffffu;
-    const int32_t NEG = -(1 << 28);
+    const int32_t NEG = -(1 << 28);                                       // a multiple of 16 (see the flag bits below)
     for (int64_t item = warp_global; item < a.n_sites * 3; item += n_warps) {
         const int64_t s = item / 3;
         const int g = (int)(item - s * 3);
@@ -1116,33 +1116,38 @@ __global__ void __launch_bounds__(128) indel_allele_kernel(const AlleleArgs a) {
             int refc[CW];
 #pragma unroll
             for (int k = 0; k < CW; k++) { const int j = lane * CW + k; refc[k] = j < m ? ref_code_of(__ldg(a.ref + p + j)) : 7; }
-            // previous row of the strip: H[i-1][j0+k+1], F[i-1][j0+k+1]; row 0: H = E = -go - ge * (j - 1), F = NEG
-            int32_t hp[CW], fp[CW];
+            // previous row of the strip: H[i-1][j0+k+1], F[i-1][j0+k+1]; row 0: H = E = -go - ge * (j - 1), F = NEG.
+            // Values are kept as 16 * score: the four low bits of a candidate carry its rank in the reference's tie rules, so that the
+            // maximum IS the choice and the low bits of the three maxima are the cell's flags — H: diagonal 2 > F 1 > E 0 in bits 1:0
+            // (the order in which the traceback asks), F: extension 4 > opening 0 in bit 2, E: extension 8 > opening 0 in bit 3 —
+            // instead of four equality tests per cell (the kernel is bound by instruction issue: 188 -> ~125 per wavefront step).
+            const int32_t go16 = 16 * a.go, ge16 = 16 * a.ge, m16 = 16 * a.match + 2, x16 = 16 * a.mismatch + 2;
+            int32_t hp[CW], fp[CW];                                                      // clean H; F + 1 (its rank inside H's maximum)
 #pragma unroll
-            for (int k = 0; k < CW; k++) { hp[k] = -a.go - a.ge * (lane * CW + k); fp[k] = NEG; }
-            int32_t h_left_prev = lane == 0 ? 0 : -a.go - a.ge * (lane * CW - 1);         // H[i-1][j0]
+            for (int k = 0; k < CW; k++) { hp[k] = -go16 - ge16 * (lane * CW + k); fp[k] = NEG + 1; }
+            int32_t h_left_prev = lane == 0 ? 0 : -go16 - ge16 * (lane * CW - 1);        // H[i-1][j0]
             int32_t out_h = 0, out_e = 0;                                                // H / E at the strip's last column of the row just finished
             for (int t = 1; t <= n + 31; t++) {
                 const int32_t in_h = __shfl_up_sync(full, out_h, 1), in_e = __shfl_up_sync(full, out_e, 1);
                 const int i = t - lane;
                 if (i >= 1 && i <= n) {
                     const int qb = __ldg(q + i - 1);
-                    const int32_t h_left_cur = lane == 0 ? -a.go - a.ge * (i - 1) : in_h;    // H[i][j0]  (column 0: H = F = -go - ge (i - 1), E = NEG)
+                    const int32_t h_left_cur = lane == 0 ? -go16 - ge16 * (i - 1) : in_h;    // H[i][j0]  (column 0: H = F = -go - ge (i - 1), E = NEG)
                     int32_t e_left = lane == 0 ? NEG : in_e;                                 // E[i][j0]
                     int32_t diag_in = h_left_prev, left = h_left_cur;
                     WordT dw = 0;
 #pragma unroll
                     for (int k = 0; k < CW; k++) {
-                        const int32_t sc = (refc[k] == qb) ? a.match : a.mismatch;
-                        const int32_t f_ext = fp[k] - a.ge, f = max(f_ext, hp[k] - a.go);
-                        const int32_t e_ext = e_left - a.ge, e = max(e_ext, left - a.go);
-                        const int32_t dg = diag_in + sc;
-                        const int32_t best = max(dg, max(f, e));
-                        const uint32_t fl = (best == dg ? 1u : 0u) | (best == f ? 2u : 0u) | (f == f_ext ? 4u : 0u) | (e == e_ext ? 8u : 0u);
+                        const int32_t fv = max(fp[k] - ge16 + 3, hp[k] - go16);              // fp holds F + 1: extension = F - ge + 4
+                        const int32_t ev = max(e_left - ge16 + 8, left - go16);
+                        const int32_t dg = diag_in + ((refc[k] == qb) ? m16 : x16);
+                        const int32_t f1 = (fv & ~15) | 1, e = ev & ~15;
+                        const int32_t best = max(dg, max(f1, e));                            // bits 1:0: 2 diagonal, 1 F, 0 E
+                        const uint32_t fl = ((uint32_t)best & 3u) | ((uint32_t)fv & 4u) | ((uint32_t)ev & 8u);
                         dw |= (WordT)fl << (4 * k);
                         diag_in = hp[k];
-                        hp[k] = best; fp[k] = f;
-                        left = best; e_left = e;
+                        hp[k] = left = best & ~15; fp[k] = f1;
+                        e_left = e;
                     }
                     dirs[(int64_t)i * 32 + lane] = dw;
                     h_left_prev = h_left_cur;
@@ -1157,8 +1162,8 @@ __global__ void __launch_bounds__(128) indel_allele_kernel(const AlleleArgs a) {
                     uint32_t fl = 0;
                     if (i > 0 && j > 0) fl = (uint32_t)(dirs[(int64_t)i * 32 + (j - 1) / CW] >> (4 * ((j - 1) % CW))) & 15u;
                     if (state == 0) {
-                        if (i > 0 && j > 0 && (fl & 1u)) { ops[nops++] = (__ldg(q + i - 1) == ref_code_of(__ldg(a.ref + p + j - 1))) ? 7 : 8; i--; j--; }
-                        else if (i > 0 && (j == 0 || (fl & 2u))) state = 1;
+                        if (i > 0 && j > 0 && (fl & 3u) == 2u) { ops[nops++] = (__ldg(q + i - 1) == ref_code_of(__ldg(a.ref + p + j - 1))) ? 7 : 8; i--; j--; }
+                        else if (i > 0 && (j == 0 || (fl & 3u) == 1u)) state = 1;
                         else state = 2;
                     } else if (state == 1) {
                         ops[nops++] = 1;
