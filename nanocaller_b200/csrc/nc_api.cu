@@ -93,7 +93,7 @@ struct nc_ctx {
     // device-side BAM input
     struct BamContig { std::string name; int32_t length = 0; int64_t first = 0, n = 0, n_tagged = 0; };
     DevBuf d_bam_comp, d_bam_blocks, d_bam, d_bam_recoff, d_bam_rid, d_bam_pos, d_bam_flag, d_bam_lseq, d_bam_ncig, d_bam_nseq, d_bam_cigsrc, d_bam_seqsrc,
-           d_bam_hp, d_bam_ps, d_bam_err, d_bam_out;
+           d_bam_hp, d_bam_ps, d_bam_err, d_bam_out, d_bam_wst, d_bam_wcnt, d_bam_woff;
     PinBuf pin_bam;
     std::vector<BamContig> bam_contigs;
     int64_t bam_records = 0, bam_bytes = 0, bam_comp_bytes = 0;
@@ -453,7 +453,8 @@ void nc_destroy(nc_ctx* c) {
     for (auto& e : c->evi) if (e) cudaEventDestroy(e);
     c->d_iprobs.release(); c->d_ialleles.release(); c->d_allele_dirs.release(); c->d_allele_ops.release();
     for (DevBuf* b : {&c->d_bam_comp, &c->d_bam_blocks, &c->d_bam, &c->d_bam_recoff, &c->d_bam_rid, &c->d_bam_pos, &c->d_bam_flag, &c->d_bam_lseq, &c->d_bam_ncig,
-                      &c->d_bam_nseq, &c->d_bam_cigsrc, &c->d_bam_seqsrc, &c->d_bam_hp, &c->d_bam_ps, &c->d_bam_err, &c->d_bam_out}) b->release();
+                      &c->d_bam_nseq, &c->d_bam_cigsrc, &c->d_bam_seqsrc, &c->d_bam_hp, &c->d_bam_ps, &c->d_bam_err, &c->d_bam_out, &c->d_bam_wst, &c->d_bam_wcnt,
+                      &c->d_bam_woff}) b->release();
     c->pin_bam.release();
     if (c->ev_block) cudaEventDestroy(c->ev_block);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1140,7 +1141,15 @@ int nc_indel_build(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int
         const int rows = (P->window_after + 2 + 1) & ~1;            // even: keeps the per-warp blocks 16-byte aligned with 2-byte words
         const bool narrow = P->window_after + 1 <= 192;
         // function attributes are per device and one process may open contexts on several: set it on every call (cheap, no sync)
-        if (narrow) {
+        // NC_INDEL_ALIGN_SCALAR=1: the one-slice-per-warp kernel for every window (validation: tests compare the two kernels at scale)
+        const char* scalar_env = getenv("NC_INDEL_ALIGN_SCALAR");
+        const bool scalar_narrow = narrow && scalar_env && scalar_env[0] == '1';
+        if (scalar_narrow) {
+            const int smem = kAlignWarps * align_smem_per_warp(rows, 2);
+            NC_CUDA(cudaFuncSetAttribute(indel_align_kernel<6, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_entries, kAlignWarps), (int64_t)c->sm_count * 16);
+            indel_align_kernel<6, uint16_t><<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries, rows);
+        } else if (narrow) {
             // two slices of a site per warp step (16-bit SIMD halves), one warp per site; as many warps as the direction words let fit
             constexpr int kW = 11;
             const int rs = P->window_after / 6 + 1;                   // lane strips in use: reference windows have <= window_after + 1 columns
@@ -1481,7 +1490,7 @@ int nc_bam_device_close(nc_ctx* c) {
     NC_CUDA(cudaSetDevice(c->device));
     NC_CUDA(nc_stream_wait(c));
     for (DevBuf* b : {&c->d_bam_comp, &c->d_bam_blocks, &c->d_bam, &c->d_bam_recoff, &c->d_bam_rid, &c->d_bam_pos, &c->d_bam_flag, &c->d_bam_lseq, &c->d_bam_ncig,
-                      &c->d_bam_nseq, &c->d_bam_cigsrc, &c->d_bam_seqsrc, &c->d_bam_hp, &c->d_bam_ps}) b->release();
+                      &c->d_bam_nseq, &c->d_bam_cigsrc, &c->d_bam_seqsrc, &c->d_bam_hp, &c->d_bam_ps, &c->d_bam_wst, &c->d_bam_wcnt, &c->d_bam_woff}) b->release();
     c->bam_open = false; c->bam_contigs.clear(); c->bam_records = 0;
     return NC_OK;
 }
@@ -1634,7 +1643,8 @@ int nc_bam_device_open(nc_ctx* c, const char* path, int32_t* n_contigs) {
         }
         if (starts.size() >= 64) {
             const int64_t ns = (int64_t)starts.size();
-            DevBuf d_st, d_cnt, d_off;
+            // (context members: a cudaMalloc / cudaFree pair per open costs anything from microseconds to hundreds of milliseconds)
+            DevBuf& d_st = c->d_bam_wst; DevBuf& d_cnt = c->d_bam_wcnt; DevBuf& d_off = c->d_bam_woff;
             cudaError_t e_ = d_st.reserve((size_t)ns * 8);
             if (e_ == cudaSuccess) e_ = d_cnt.reserve((size_t)ns * 4);
             if (e_ == cudaSuccess) e_ = d_off.reserve((size_t)(ns + 1) * 8);
@@ -1656,7 +1666,6 @@ int nc_bam_device_open(nc_ctx* c, const char* path, int32_t* n_contigs) {
                 }
             }
             cudaStreamSynchronize(c->stream);
-            d_st.release(); d_cnt.release(); d_off.release();
             if (rcw) return rcw;
         }
     }

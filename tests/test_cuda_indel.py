@@ -146,3 +146,29 @@ def test_device_allele_prediction_equals_host_alignment(preset, seq):
     assert (host.ref_out >= 0).sum() > 50 and (host.ref_out < 0).sum() > 50
     kept = indel_pileups.kept_sites(meta, False)
     assert (dev[~kept] == -1).all()
+
+
+def test_paired_alignment_kernel_equals_one_slice_per_warp_kernel():
+    """indel_align2_kernel (two slices of a site per warp in 16-bit halves, tie bits as directions) against indel_align_kernel (one
+    slice per warp, explicit compares; the kernel the reference fixtures pinned first) on every site of a synthetic ONT contig with
+    indels up to 40 bases, reads ending inside windows and the last window cut by the contig end: identical tensors, consensus
+    strings and site records."""
+    import os
+    from nanocaller_b200.host import indel_pileups, snp_pileups
+    from nanocaller_b200.synth import make_world
+    rs = make_world(chrom="chrP", preset="ont", contig_len=400_000, seed=43, coverage=25.0, indel_every=700, indel_maxlen=40).reads
+    dct = dict(mincov=4, maxcov=160, seq="ont", del_t=0.6, ins_t=0.4, impute_indel_phase=False, supplementary=False, win_size=40, small_win_size=4)
+    chunks = [{"chrom": "chrP", "start": s, "end": min(400_000, s + 100_000), "ploidy": "diploid"} for s in range(1, 400_000, 100_000)]
+    ctx = snp_pileups.context(0)
+    out = {}
+    try:
+        for mode in ("0", "1"):
+            os.environ["NC_INDEL_ALIGN_SCALAR"] = mode
+            snp_pileups._staged.clear()
+            meta, tensors, cns = indel_pileups.scan_build(ctx, rs, dct, chunks)
+            out[mode] = (meta.copy(), np.array(tensors, copy=True), np.array(cns, copy=True), ctx.indel_fetch_alleles().copy())
+    finally:
+        os.environ.pop("NC_INDEL_ALIGN_SCALAR", None)
+    a, b = out["0"], out["1"]
+    assert len(a[0]) > 400 and indel_pileups.kept_sites(a[0], False).sum() > 300
+    assert a[0].tobytes() == b[0].tobytes() and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
