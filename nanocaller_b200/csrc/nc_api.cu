@@ -1004,13 +1004,11 @@ int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int3
     ea.grank = c->d_grank.as<int64_t>(); ea.lo_al = lo_al; ea.flag_filter = flag_filter; ea.win = P->win_size; ea.small_win = P->small_win_size; ea.haploid = P->haploid;
     ea.diff = c->d_diff.as<int32_t>(); ea.R = R;
     indel_events_kernel<<<(unsigned)div_up(c->n_reads * 32, 128), 128, 0, c->stream>>>(ea); NC_LAUNCH_CHECK();
-    NC_CUDA(c->d_uscan.reserve((size_t)(8 * R + 1) * 8));
-    if ((rc = device_scan(c, c->d_diff.as<int32_t>(), 8 * R, c->d_uscan.as<int64_t>()))) return rc;      // all eight kinds in one scan (DecideArgs::uscan)
     NC_CUDA(c->d_hit.reserve((size_t)R));
     NC_CUDA(c->d_icount.reserve(64));
     NC_CUDA(cudaMemsetAsync(c->d_icount.p, 0, 64, c->stream));
     DecideArgs dd = {};
-    dd.chunks = c->d_ichunks.as<IndelChunk>(); dd.n_chunks = n_chunks; dd.R = R; dd.uscan = c->d_uscan.as<int64_t>(); dd.em_pos = c->d_empos.as<int32_t>();
+    dd.chunks = c->d_ichunks.as<IndelChunk>(); dd.n_chunks = n_chunks; dd.R = R; dd.diff = c->d_diff.as<int32_t>(); dd.em_pos = c->d_empos.as<int32_t>();
     dd.depth = c->d_idepth.as<uint16_t>(); dd.n_al = n_al; dd.lo_al = lo_al; dd.mincov = P->mincov; dd.haploid = P->haploid; dd.ins_t = P->ins_t; dd.del_t = P->del_t;
     dd.hit = c->d_hit.as<uint8_t>(); dd.n_hits = c->d_icount.as<unsigned long long>();
     const bool impute = P->impute_indel_phase && !P->haploid;
@@ -1025,7 +1023,7 @@ int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int3
         indel_impute_count_kernel<<<(unsigned)div_up(c->n_reads, 128), 128, 0, c->stream>>>(ic); NC_LAUNCH_CHECK();
         dd.impute = 1; dd.cdel = ic.cdel; dd.cins = ic.cins;
     }
-    indel_decide_kernel<<<(unsigned)div_up(R, 256), 256, 0, c->stream>>>(dd); NC_LAUNCH_CHECK();
+    indel_decide_kernel<<<(unsigned)n_chunks, 256, 0, c->stream>>>(dd); NC_LAUNCH_CHECK();      // scans the difference arrays chunk by chunk on the way
     if (impute) {
         int64_t n_pending = 0;
         if ((rc = read_i64(c, c->d_icount.as<int64_t>() + 2, &n_pending))) return rc;
