@@ -72,7 +72,7 @@ struct nc_ctx {
     int scan_haploid = 0;
     // indel path
     bool tags_staged = false, indel_scanned = false, indel_built = false;
-    DevBuf d_hp, d_ps, d_idepth, d_em, d_grank, d_empos, d_ichunks, d_nem1, d_rankoff, d_diff, d_uscan, d_hit, d_variants, d_icount;
+    DevBuf d_hp, d_ps, d_idepth, d_em, d_grank, d_empos, d_ichunks, d_nem1, d_rankoff, d_diff, d_uscan, d_empairs, d_hit, d_variants, d_icount;
     DevBuf d_isites, d_site_m, d_site_cnt, d_site_off, d_eread, d_eqpn, d_eslice, d_eacode, d_einslen, d_einsfirst, d_en, d_itensors, d_icns, d_imeta;
     // impute_indel_phase: per-column indel marks, pending / source columns and their grouped reads
     DevBuf d_cdel, d_cins, d_imp_g, d_imp_cols, d_imp_cnt, d_imp_off, d_imp_read, d_imp_ch, d_imp_ind, d_imp_qn, d_imp_gid, d_imp_rep, d_imp_gcnt,
@@ -437,7 +437,7 @@ void nc_destroy(nc_ctx* c) {
                       &c->d_chunk_cnt, &c->d_chunk_off, &c->d_keep, &c->d_keep32, &c->d_outidx, &c->d_mat, &c->d_meta,
                       &c->d_depth_sum, &c->d_depth_cnt, &c->d_chunk_depth, &c->d_chunk_count, &c->d_probs, &c->d_scan_partial,
                       &c->d_hp, &c->d_ps, &c->d_idepth, &c->d_em, &c->d_grank, &c->d_empos, &c->d_ichunks, &c->d_nem1, &c->d_rankoff, &c->d_diff,
-                      &c->d_uscan, &c->d_hit, &c->d_variants, &c->d_icount, &c->d_isites, &c->d_site_m, &c->d_site_cnt, &c->d_site_off, &c->d_eread,
+                      &c->d_uscan, &c->d_empairs, &c->d_hit, &c->d_variants, &c->d_icount, &c->d_isites, &c->d_site_m, &c->d_site_cnt, &c->d_site_off, &c->d_eread,
                       &c->d_eqpn, &c->d_eslice, &c->d_eacode, &c->d_einslen, &c->d_einsfirst, &c->d_en, &c->d_itensors, &c->d_icns, &c->d_imeta,
                       &c->d_cdel, &c->d_cins, &c->d_imp_g, &c->d_imp_cols, &c->d_imp_cnt, &c->d_imp_off, &c->d_imp_read, &c->d_imp_ch, &c->d_imp_ind,
                       &c->d_imp_qn, &c->d_imp_gid, &c->d_imp_rep, &c->d_imp_gcnt, &c->d_imp_label, &c->d_imp_ok, &c->d_site_imp, &c->d_egrp,
@@ -1000,8 +1000,11 @@ int nc_indel_scan(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int3
     NC_CUDA(cudaMemsetAsync(c->d_diff.p, 0, (size_t)8 * R * 4, c->stream));
     EventArgs ea = {};
     ea.n_reads = c->n_reads; ea.pos = da.pos; ea.end = da.end; ea.flag = da.flag; ea.hp = da.hp; ea.cigar_off = c->d_cigar_off.as<int64_t>();
-    ea.cigar = c->d_cigar.as<uint32_t>(); ea.opstart = c->d_opstart.as<int2>(); ea.chunks = c->d_ichunks.as<IndelChunk>(); ea.n_chunks = n_chunks; ea.em = c->d_em.as<int32_t>();
-    ea.grank = c->d_grank.as<int64_t>(); ea.lo_al = lo_al; ea.flag_filter = flag_filter; ea.win = P->win_size; ea.small_win = P->small_win_size; ea.haploid = P->haploid;
+    ea.cigar = c->d_cigar.as<uint32_t>(); ea.opstart = c->d_opstart.as<int2>(); ea.chunks = c->d_ichunks.as<IndelChunk>(); ea.n_chunks = n_chunks;
+    NC_CUDA(c->d_empairs.reserve((size_t)div_up(n_al, 32) * 8));
+    indel_empairs_kernel<<<(unsigned)div_up(n_al, 256), 256, 0, c->stream>>>(c->d_em.as<int32_t>(), c->d_grank.as<int64_t>(), n_al, c->d_empairs.as<uint2>());
+    NC_LAUNCH_CHECK();
+    ea.empairs = c->d_empairs.as<uint2>(); ea.lo_al = lo_al; ea.flag_filter = flag_filter; ea.win = P->win_size; ea.small_win = P->small_win_size; ea.haploid = P->haploid;
     ea.diff = c->d_diff.as<int32_t>(); ea.R = R;
     indel_events_kernel<<<(unsigned)div_up(c->n_reads * 32, 128), 128, 0, c->stream>>>(ea); NC_LAUNCH_CHECK();
     NC_CUDA(c->d_hit.reserve((size_t)R));

@@ -142,12 +142,21 @@ __global__ void indel_chunk_off_kernel(IndelChunk* __restrict__ ch, int32_t n_ch
 // ranks r .. r+win-1; overlapping intervals of one read are merged so it is counted once (a set union).
 // kinds: key = hap*4 + {0 del 2<L<=50, 1 del L<=10, 2 ins 2<L<=50, 3 ins L<=10}.
 // ------------------------------------------------------------------------------------------------
+// emitted flags + ranks in 8 bytes per 32 positions: {bit i = position 32 b + i is emitted, rank of position 32 b}.  The event kernel
+// looks both up for every indel of every read — tens of millions of scattered reads; from the int32 flag and the int64 rank arrays
+// that was two 32-byte sectors per event, from the pairs it is one sector per ~128 positions of a read.
+__global__ void indel_empairs_kernel(const int32_t* __restrict__ em, const int64_t* __restrict__ grank, int64_t n, uint2* __restrict__ pairs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t bits = __ballot_sync(0xffffffffu, i < n && em[i] != 0);
+    if ((threadIdx.x & 31) == 0 && i < n) pairs[i >> 5] = make_uint2(bits, (uint32_t)grank[i]);
+}
+
 struct EventArgs {
     int64_t n_reads;
     const int32_t* pos; const int32_t* end; const uint16_t* flag; const int8_t* hp;
     const int64_t* cigar_off; const uint32_t* cigar; const int2* opstart;
     const IndelChunk* chunks; int32_t n_chunks;
-    const int32_t* em; const int64_t* grank; int32_t lo_al;
+    const uint2* empairs; int32_t lo_al;     // indel_empairs_kernel
     uint32_t flag_filter; int32_t win, small_win, haploid;
     int32_t* diff; int64_t R;          // [8][R]
 };
@@ -207,8 +216,9 @@ __global__ void __launch_bounds__(128) indel_events_kernel(const EventArgs a) {
                     }
                     if (tot > 0) {
                         const int64_t pi = (int64_t)plast - a.lo_al;
-                        if (__ldg(a.em + pi)) {
-                            rk = (int32_t)(__ldg(a.grank + pi) - ch.grank_lo);
+                        const uint2 pr = __ldg(a.empairs + (pi >> 5));
+                        if ((pr.x >> (pi & 31)) & 1u) {
+                            rk = (int32_t)((int64_t)pr.y + __popc(pr.x & ((1u << (pi & 31)) - 1u)) - ch.grank_lo);
                             const int base = is_del ? 0 : 2;
                             if (tot > 2 && tot <= 50) kA = base;
                             if (tot <= 10) kB = base + 1;
