@@ -109,14 +109,19 @@ struct IAParams {
     uint8_t* c2_out;                          // [site][slab][SLAB_BYTES]
     int* err;
 };
-constexpr int IA_THREADS = 128 + 32;                                   // one epilogue warpgroup + the MMA issuer warp
+constexpr int IA_THREADS = 2 * 128 + 32;                               // two epilogue warpgroups + the MMA issuer warp
+// The kernel is bound by the epilogue's instruction stream (bias, SELU, fp16 split of 584 values per thread and site with ONE warp per
+// scheduler: tensor pipe 13 % busy), so two warpgroups share every epilogue by channel groups — both read the same TMEM lanes (a warp's
+// lanes are warp % 4), follow the same barrier / mbarrier sequence, and store different 16-byte channel groups: conv1 channels 0-15 | 16-23,
+// conv2 channels 0-15 | 16-31, the input conversion by halves.  (Balancing the groups 5 : 5 changed nothing: the rest is the row
+// protocol's serial MMA -> epilogue -> barrier chain.)
 constexpr int IA_SMEM_W = tci::W1_BYTES + tci::W2_BYTES;               // 26,112
 constexpr int IA_SMEM = IA_SMEM_W + 2 * tci::IN_PLANE + 2 * tci::WIN_BYTES + 256 + 2 * 56 * 4 + 64 + 64;
 static_assert(IA_SMEM <= 232448, "IA shared memory exceeds the 227 KB per-CTA limit");
 constexpr int IA_TMEM_C1 = 64;                                         // per conv1 buffer: 48 columns used
 constexpr int IA_TMEM_C2 = 128;                                        // conv2 accumulators at column 128: 64 used
 
-__device__ __forceinline__ void ia_barrier() { asm volatile("bar.sync 1, 160;" ::: "memory"); }
+__device__ __forceinline__ void ia_barrier() { asm volatile("bar.sync 1, 288;" ::: "memory"); }
 
 __global__ void __launch_bounds__(IA_THREADS, 1) tci_trunk_a_kernel(const IAParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -146,8 +151,9 @@ __global__ void __launch_bounds__(IA_THREADS, 1) tci_trunk_a_kernel(const IAPara
     const uint32_t tmem = *s_tmem;
     const uint32_t in16 = smem_u32(s_in) >> 4, win16 = smem_u32(s_win) >> 4, w16 = smem_u32(s_w) >> 4;
 
-    if (warp == 4) {
-        // ===== MMA issuer warp: the epilogue warpgroup hands it work through the 160-thread barrier, in a fixed order
+    const int wgi = tid >> 7;                                           // epilogue warpgroup 0 / 1 (2: the issuer warp)
+    if (warp == 8) {
+        // ===== MMA issuer warp: the epilogue warpgroups hand it work through the 288-thread barrier, in a fixed order
         for (int64_t site = blockIdx.x; site < P.n_sites; site += gridDim.x) {
             ia_barrier();                                                        // input planes written
             if (elect_one()) {
@@ -187,23 +193,22 @@ __global__ void __launch_bounds__(IA_THREADS, 1) tci_trunk_a_kernel(const IAPara
     auto conv2_epilogue = [&](int64_t site, int j) {
         ok = mbar_wait(&s_bar[2], ph2) && ok; ph2 ^= 1;
         tc_fence_after();
-        float acc[32], lo_part[32];
-        tmem_ld16_nowait(tmem_lane + IA_TMEM_C2, acc);
-        tmem_ld16_nowait(tmem_lane + IA_TMEM_C2 + 16, acc + 16);
-        tmem_ld16_nowait(tmem_lane + IA_TMEM_C2 + 32, lo_part);
-        tmem_ld16_nowait(tmem_lane + IA_TMEM_C2 + 48, lo_part + 16);
+        float acc[16], lo_part[16];                                       // this warpgroup's 16 channels: columns 16 wgi .., and their w_lo partners
+        tmem_ld16_nowait(tmem_lane + IA_TMEM_C2 + 16 * wgi, acc);
+        tmem_ld16_nowait(tmem_lane + IA_TMEM_C2 + 32 + 16 * wgi, lo_part);
         tmem_ld_wait();
         tc_fence_before();
         const int h2 = 2 * j + (t >> 6), w2 = t & 63;
         if (w2 < 63 && h2 < H - 1) {
 #pragma unroll
-            for (int i = 0; i < 32; i++) acc[i] += lo_part[i];
+            for (int i = 0; i < 16; i++) acc[i] += lo_part[i];
             const int sl = h2 >> 2, r = h2 & 3;
             uint8_t* base = P.c2_out + (site * NS) * (int64_t)tci::SLAB_BYTES + ((w2 & 1) * 4) * tci::SLAB_PLANE + (w2 >> 1) * 16;
 #pragma unroll
-            for (int kg = 0; kg < 4; kg++) {
+            for (int kgl = 0; kgl < 2; kgl++) {
+                const int kg = 2 * wgi + kgl;
                 uint4 hi, lo;
-                act_split8(acc + 8 * kg, s_bias + 24 + 8 * kg, s_bl + 24 + 8 * kg, hi, lo);
+                act_split8(acc + 8 * kgl, s_bias + 24 + 8 * kg, s_bl + 24 + 8 * kg, hi, lo);
                 if (sl < NS) {
                     uint8_t* d = base + (int64_t)sl * tci::SLAB_BYTES + kg * tci::SLAB_PLANE + r * 32 * 16;
                     *reinterpret_cast<uint4*>(d) = hi;
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(IA_THREADS, 1) tci_trunk_a_kernel(const IAPara
         // ---- input image -> padded fp16 hi / lo planes; plane row (hp, wp) holds pixels wp-2 .. wp+1 of image row hp-2 (2 channels each)
         {
             const float2* x = reinterpret_cast<const float2*>(P.x + site * P.site_stride);
-            for (int idx = t; idx < H * tci::IN_COLS; idx += 128) {
+            for (int idx = t + 128 * wgi; idx < H * tci::IN_COLS; idx += 256) {
                 const int hh = idx / tci::IN_COLS, wp = idx - hh * tci::IN_COLS;
                 float2 v[4];
 #pragma unroll
@@ -243,33 +248,34 @@ __global__ void __launch_bounds__(IA_THREADS, 1) tci_trunk_a_kernel(const IAPara
         for (int h = 0; h < H; h++) {
             ok = mbar_wait(&s_bar[h & 1], ph1[h & 1]) && ok; ph1[h & 1] ^= 1;
             tc_fence_after();
-            float v[24];
+            float v[16];                                                         // channel c = column c + column 24 + c; warpgroup 0: channels 0-15, 1: 16-23
             {
-                float a[16], b[16], c[16];
-                const uint32_t col = tmem_lane + (h & 1) * IA_TMEM_C1;
-                tmem_ld16_nowait(col, a); tmem_ld16_nowait(col + 16, b); tmem_ld16_nowait(col + 32, c);
+                float a[16], b[16];
+                const uint32_t col = tmem_lane + (h & 1) * IA_TMEM_C1 + 16 * wgi;
+                tmem_ld16_nowait(col, a); tmem_ld16_nowait(col + 24, b);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; i++) v[i] = a[i] + (i < 8 ? b[8 + i] : c[i - 8]);          // column i + column 24 + i
-#pragma unroll
-                for (int i = 0; i < 8; i++) v[16 + i] = b[i] + c[8 + i];
+                for (int i = 0; i < 16; i++) v[i] = a[i] + b[i];
             }
             tc_fence_before();
             ia_barrier();                                                        // -> issuer: conv1 row h + 2 into this buffer
             if (h >= 4 && !(h & 1)) conv2_epilogue(site, (h - 4) >> 1);          // also frees the window row h is about to enter
             {
                 // c1 row h: pixel w = t, parity plane t & 1, column t >> 1; even rows enter two windows (last row of one, first of the next)
-                uint4 hi[3], lo[3];
+                const int kg0 = 2 * wgi, nkg = 2 - wgi;                          // channel groups of this warpgroup: {0, 1} | {2}
+                uint4 hi[2], lo[2];
 #pragma unroll
-                for (int kg = 0; kg < 3; kg++) act_split8(v + 8 * kg, s_bias + 8 * kg, s_bl + 8 * kg, hi[kg], lo[kg]);
+                for (int kgl = 0; kgl < 2; kgl++)
+                    if (kgl < nkg) act_split8(v + 8 * kgl, s_bias + 8 * (kg0 + kgl), s_bl + 8 * (kg0 + kgl), hi[kgl], lo[kgl]);
                 const int j = h >> 1;
                 auto put = [&](int win, int slot) {
                     uint8_t* d = s_win + win * tci::WIN_BYTES + ((t & 1) * 3) * tci::WIN_PLANE + (slot * 64 + (t >> 1)) * 16;
 #pragma unroll
-                    for (int kg = 0; kg < 3; kg++) {
-                        *reinterpret_cast<uint4*>(d + kg * tci::WIN_PLANE) = hi[kg];
-                        *reinterpret_cast<uint4*>(d + (6 + kg) * tci::WIN_PLANE) = lo[kg];
-                    }
+                    for (int kgl = 0; kgl < 2; kgl++)
+                        if (kgl < nkg) {
+                            *reinterpret_cast<uint4*>(d + (kg0 + kgl) * tci::WIN_PLANE) = hi[kgl];
+                            *reinterpret_cast<uint4*>(d + (6 + kg0 + kgl) * tci::WIN_PLANE) = lo[kgl];
+                        }
                 };
                 if (h & 1) put(j & 1, 1);
                 else {
