@@ -278,69 +278,89 @@ __global__ void __launch_bounds__(256) indel_decide_kernel(const DecideArgs a) {
     const IndelChunk ch = a.chunks[blockIdx.x];
     const int32_t n1 = ch.n_em + 1;                                   // the chunk's rank range has one slot past its last column (interval ends)
     long long carry0 = 0, carry1 = 0;
-    for (int32_t r0 = 0; r0 < n1; r0 += 256) {
-        const int32_t r = r0 + tid;
-        const int64_t g = ch.rank_off + r;
-        long long p0 = 0, p1 = 0;
-        if (r < n1) {
+    // Four tiles of 256 columns per trip: all their loads are issued first (difference arrays and positions, then the depths behind the
+    // positions), so a trip costs two memory round trips instead of eight — with one CTA per 100 kb chunk a small contig has only a few
+    // CTAs per SM and the walk is bound by exactly that latency.
+    for (int32_t r0 = 0; r0 < n1; r0 += 1024) {
+        long long q0[4], q1[4];
+        int64_t pi[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                p0 += (long long)__ldg(a.diff + (int64_t)k * a.R + g) * (1ll << (16 * k));
-                p1 += (long long)__ldg(a.diff + (int64_t)(4 + k) * a.R + g) * (1ll << (16 * k));
+        for (int u = 0; u < 4; u++) {
+            const int32_t r = r0 + 256 * u + tid;
+            const int64_t g = ch.rank_off + r;
+            q0[u] = 0; q1[u] = 0; pi[u] = -1;
+            if (r < n1) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    q0[u] += (long long)__ldg(a.diff + (int64_t)k * a.R + g) * (1ll << (16 * k));
+                    q1[u] += (long long)__ldg(a.diff + (int64_t)(4 + k) * a.R + g) * (1ll << (16 * k));
+                }
+                if (r < ch.n_em) pi[u] = (int64_t)__ldg(a.em_pos + ch.grank_lo + r) - a.lo_al;
+            }
+        }
+        int32_t l0[4], l1[4], lt[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            l0[u] = l1[u] = lt[u] = 0;
+            if (pi[u] >= 0) {
+                if (a.haploid) { l0[u] = l1[u] = a.depth[2 * a.n_al + pi[u]]; }
+                else { l0[u] = a.depth[pi[u]]; l1[u] = a.depth[a.n_al + pi[u]]; if (a.impute) lt[u] = a.depth[2 * a.n_al + pi[u]]; }
             }
         }
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const long long t0 = __shfl_up_sync(0xffffffffu, p0, d), t1 = __shfl_up_sync(0xffffffffu, p1, d);
-            if (lane >= d) { p0 += t0; p1 += t1; }
-        }
-        __syncthreads();                                              // the previous tile's totals have been read
-        if (lane == 31) { s_tot[0][wid] = p0; s_tot[1][wid] = p1; }
-        __syncthreads();
-        long long tile0 = 0, tile1 = 0;
+        for (int u = 0; u < 4; u++) {
+            const int32_t r = r0 + 256 * u + tid;
+            if (r0 + 256 * u >= n1) break;                            // uniform
+            long long p0 = q0[u], p1 = q1[u];
 #pragma unroll
-        for (int w = 0; w < 8; w++) {
-            const long long t0 = s_tot[0][w], t1 = s_tot[1][w];
-            if (w < wid) { p0 += t0; p1 += t1; }
-            tile0 += t0; tile1 += t1;
-        }
-        p0 += carry0; p1 += carry1;
-        carry0 += tile0; carry1 += tile1;
-        if (r >= n1) continue;
-        uint8_t hit = 0;
-        if (r < ch.n_em) {
-            const int32_t p = a.em_pos[ch.grank_lo + r];
-            const int64_t pi = (int64_t)p - a.lo_al;
-            const int32_t l0 = a.haploid ? a.depth[2 * a.n_al + pi] : a.depth[pi], l1 = a.haploid ? l0 : a.depth[a.n_al + pi];
-            if (a.haploid) {
-                if (l0 >= a.mincov) {                      // generate_indel_pileups_haploid.py:224-241
-                    double f[4];
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long t0 = __shfl_up_sync(0xffffffffu, p0, d), t1 = __shfl_up_sync(0xffffffffu, p1, d);
+                if (lane >= d) { p0 += t0; p1 += t1; }
+            }
+            __syncthreads();                                          // the previous tile's totals have been read
+            if (lane == 31) { s_tot[0][wid] = p0; s_tot[1][wid] = p1; }
+            __syncthreads();
+            long long tile0 = 0, tile1 = 0;
 #pragma unroll
-                    for (int k = 0; k < 4; k++) f[k] = l0 > 0 ? (double)((p0 >> (16 * k)) & 0xFFFF) / (double)l0 : 0.0;
-                    if (f[0] >= a.del_t || f[2] >= a.ins_t) hit = 1;
-                    else if (f[1] >= a.del_t || f[3] >= a.ins_t || (f[1] + f[3]) >= 0.9) hit = 2;
-                }
-            } else if (l0 >= a.mincov && l1 >= a.mincov) {
-                double f[8];
+            for (int w = 0; w < 8; w++) {
+                const long long t0 = s_tot[0][w], t1 = s_tot[1][w];
+                if (w < wid) { p0 += t0; p1 += t1; }
+                tile0 += t0; tile1 += t1;
+            }
+            p0 += carry0; p1 += carry1;
+            carry0 += tile0; carry1 += tile1;
+            if (r >= n1) continue;
+            uint8_t hit = 0;
+            if (pi[u] >= 0) {
+                if (a.haploid) {
+                    if (l0[u] >= a.mincov) {                   // generate_indel_pileups_haploid.py:224-241
+                        double f[4];
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int32_t l = k < 4 ? l0 : l1;
-                    const long long pk = k < 4 ? p0 : p1;
-                    f[k] = l > 0 ? (double)((pk >> (16 * (k & 3))) & 0xFFFF) / (double)l : 0.0;
-                }
-                if (fmax(f[0], f[4]) >= a.del_t || fmax(f[2], f[6]) >= a.ins_t) hit = 1;
-                else if (fmax(f[1], f[5]) >= a.del_t || fmax(f[3], f[7]) >= a.ins_t || (f[1] + f[3]) >= 0.9 || (f[5] + f[7]) >= 0.9) hit = 2;
-            } else if (a.impute) {
-                const int32_t lt = a.depth[2 * a.n_al + pi];
-                if (lt > 0 && lt >= 2 * a.mincov) {
-                    const double fd = (double)a.cdel[pi] / (double)lt, fi = (double)a.cins[pi] / (double)lt;
-                    if (a.del_t <= fd || a.ins_t <= fi) hit = 4;
+                        for (int k = 0; k < 4; k++) f[k] = l0[u] > 0 ? (double)((p0 >> (16 * k)) & 0xFFFF) / (double)l0[u] : 0.0;
+                        if (f[0] >= a.del_t || f[2] >= a.ins_t) hit = 1;
+                        else if (f[1] >= a.del_t || f[3] >= a.ins_t || (f[1] + f[3]) >= 0.9) hit = 2;
+                    }
+                } else if (l0[u] >= a.mincov && l1[u] >= a.mincov) {
+                    double f[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int32_t l = k < 4 ? l0[u] : l1[u];
+                        const long long pk = k < 4 ? p0 : p1;
+                        f[k] = l > 0 ? (double)((pk >> (16 * (k & 3))) & 0xFFFF) / (double)l : 0.0;
+                    }
+                    if (fmax(f[0], f[4]) >= a.del_t || fmax(f[2], f[6]) >= a.ins_t) hit = 1;
+                    else if (fmax(f[1], f[5]) >= a.del_t || fmax(f[3], f[7]) >= a.ins_t || (f[1] + f[3]) >= 0.9 || (f[5] + f[7]) >= 0.9) hit = 2;
+                } else if (a.impute) {
+                    if (lt[u] > 0 && lt[u] >= 2 * a.mincov) {
+                        const double fd = (double)a.cdel[pi[u]] / (double)lt[u], fi = (double)a.cins[pi[u]] / (double)lt[u];
+                        if (a.del_t <= fd || a.ins_t <= fi) hit = 4;
+                    }
                 }
             }
+            a.hit[ch.rank_off + r] = hit;
+            if (hit == 4) atomicAdd(a.n_hits + 2, 1ull);
+            else if (hit) atomicAdd(a.n_hits, 1ull);
         }
-        a.hit[g] = hit;
-        if (hit == 4) atomicAdd(a.n_hits + 2, 1ull);
-        else if (hit) atomicAdd(a.n_hits, 1ull);
     }
 }
 
