@@ -72,7 +72,7 @@ struct nc_ctx {
     int scan_haploid = 0;
     // indel path
     bool tags_staged = false, indel_scanned = false, indel_built = false;
-    DevBuf d_hp, d_ps, d_idepth, d_em, d_grank, d_empos, d_ichunks, d_nem1, d_rankoff, d_diff, d_uscan, d_empairs, d_hit, d_variants, d_icount;
+    DevBuf d_hp, d_ps, d_idepth, d_em, d_grank, d_empos, d_ichunks, d_nem1, d_rankoff, d_diff, d_empairs, d_hit, d_variants, d_icount;
     DevBuf d_isites, d_site_m, d_site_cnt, d_site_off, d_eread, d_eqpn, d_eslice, d_eacode, d_einslen, d_einsfirst, d_en, d_itensors, d_icns, d_imeta;
     // impute_indel_phase: per-column indel marks, pending / source columns and their grouped reads
     DevBuf d_cdel, d_cins, d_imp_g, d_imp_cols, d_imp_cnt, d_imp_off, d_imp_read, d_imp_ch, d_imp_ind, d_imp_qn, d_imp_gid, d_imp_rep, d_imp_gcnt,
@@ -437,7 +437,7 @@ void nc_destroy(nc_ctx* c) {
                       &c->d_chunk_cnt, &c->d_chunk_off, &c->d_keep, &c->d_keep32, &c->d_outidx, &c->d_mat, &c->d_meta,
                       &c->d_depth_sum, &c->d_depth_cnt, &c->d_chunk_depth, &c->d_chunk_count, &c->d_probs, &c->d_scan_partial,
                       &c->d_hp, &c->d_ps, &c->d_idepth, &c->d_em, &c->d_grank, &c->d_empos, &c->d_ichunks, &c->d_nem1, &c->d_rankoff, &c->d_diff,
-                      &c->d_uscan, &c->d_empairs, &c->d_hit, &c->d_variants, &c->d_icount, &c->d_isites, &c->d_site_m, &c->d_site_cnt, &c->d_site_off, &c->d_eread,
+                      &c->d_empairs, &c->d_hit, &c->d_variants, &c->d_icount, &c->d_isites, &c->d_site_m, &c->d_site_cnt, &c->d_site_off, &c->d_eread,
                       &c->d_eqpn, &c->d_eslice, &c->d_eacode, &c->d_einslen, &c->d_einsfirst, &c->d_en, &c->d_itensors, &c->d_icns, &c->d_imeta,
                       &c->d_cdel, &c->d_cins, &c->d_imp_g, &c->d_imp_cols, &c->d_imp_cnt, &c->d_imp_off, &c->d_imp_read, &c->d_imp_ch, &c->d_imp_ind,
                       &c->d_imp_qn, &c->d_imp_gid, &c->d_imp_rep, &c->d_imp_gcnt, &c->d_imp_label, &c->d_imp_ok, &c->d_site_imp, &c->d_egrp,
