@@ -1144,28 +1144,31 @@ int nc_indel_build(nc_ctx* c, const NcIndelParams* P, const NcChunk* chunks, int
         // function attributes are per device and one process may open contexts on several: set it on every call (cheap, no sync)
         // NC_INDEL_ALIGN_SCALAR=1: the one-slice-per-warp kernel for every window (validation: tests compare the two kernels at scale)
         const char* scalar_env = getenv("NC_INDEL_ALIGN_SCALAR");
-        const bool scalar_narrow = narrow && scalar_env && scalar_env[0] == '1';
-        if (scalar_narrow) {
+        const bool scalar = scalar_env && scalar_env[0] == '1';
+        const int rs = P->window_after / (narrow ? 6 : 9) + 1;        // lane strips in use: reference windows have <= window_after + 1 columns
+        const int smem_limit = 227 * 1024 - 1024;
+        auto launch2 = [&](auto kernel, int warps, bool wide) -> cudaError_t {
+            // two slices of a site per warp step (16-bit SIMD halves), one warp per site; as many warps as the direction words let fit
+            const int smem = warps * align2_smem_per_warp(P->window_after, rs, wide);
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_sites, warps), (int64_t)c->sm_count);
+            kernel<<<ag, warps * 32, smem, c->stream>>>(sa, rs);
+            return cudaSuccess;
+        };
+        if (!scalar && narrow && 11 * align2_smem_per_warp(P->window_after, rs, false) <= smem_limit) {
+            NC_CUDA(launch2(indel_align2_kernel<6, 11>, 11, false));
+        } else if (!scalar && narrow) {
+            NC_CUDA(launch2(indel_align2_kernel<6, 6>, 6, false));
+        } else if (!scalar && 5 * align2_smem_per_warp(P->window_after, rs, true) <= smem_limit) {
+            NC_CUDA(launch2(indel_align2_kernel<9, 5>, 5, true));
+        } else if (!scalar && 4 * align2_smem_per_warp(P->window_after, rs, true) <= smem_limit) {
+            NC_CUDA(launch2(indel_align2_kernel<9, 4>, 4, true));
+        } else if (narrow) {
             const int smem = kAlignWarps * align_smem_per_warp(rows, 2);
             NC_CUDA(cudaFuncSetAttribute(indel_align_kernel<6, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_entries, kAlignWarps), (int64_t)c->sm_count * 16);
             indel_align_kernel<6, uint16_t><<<ag, kAlignWarps * 32, smem, c->stream>>>(sa, n_entries, rows);
-        } else if (narrow) {
-            // two slices of a site per warp step (16-bit SIMD halves), one warp per site; as many warps as the direction words let fit
-            constexpr int kW = 11;
-            const int rs = P->window_after / 6 + 1;                   // lane strips in use: reference windows have <= window_after + 1 columns
-            int smem = kW * align2_smem_per_warp(P->window_after, rs);
-            if (smem <= 227 * 1024 - 1024) {
-                NC_CUDA(cudaFuncSetAttribute(indel_align2_kernel<6, kW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_sites, kW), (int64_t)c->sm_count);
-                indel_align2_kernel<6, kW><<<ag, kW * 32, smem, c->stream>>>(sa, rs);
-            } else {
-                constexpr int kW2 = 6;
-                smem = kW2 * align2_smem_per_warp(P->window_after, rs);
-                NC_CUDA(cudaFuncSetAttribute(indel_align2_kernel<6, kW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                const unsigned ag = (unsigned)std::min<int64_t>(div_up(n_sites, kW2), (int64_t)c->sm_count);
-                indel_align2_kernel<6, kW2><<<ag, kW2 * 32, smem, c->stream>>>(sa, rs);
-            }
         } else {
             const int smem = kAlignWarps * align_smem_per_warp(rows, 4);
             NC_CUDA(cudaFuncSetAttribute(indel_align_kernel<9, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -812,10 +812,16 @@ __global__ void __launch_bounds__(kAlignWarps * 32) indel_align_kernel(const Sit
 //     two paths back at the same time.
 // Per pair and strip column: prmt, add, 2 x add-max, and-mask, shift, or-and = 7 instructions for two cells (the scalar kernel: ~12
 // per cell).
-constexpr int kAlign2Aux = 2 * (272 + 32) + 2 * (272 + 2 * 272);   // row selectors (u16, 32 entries of padding in front); per half: slice (u8), traceback record per reference column (u16)
+constexpr int kAlign2Sel = 352;                                  // row selectors: rows + lane strips of the widest window, 32 entries of padding in front
+constexpr int kAlign2Aux = 2 * kAlign2Sel + 2 * (272 + 2 * 272);   // row selectors (u16); per half: slice (u8), traceback record per reference column (u16)
 // direction words: rows -2 .. wa (row 0 and the two rows above it are all LEFT / never read as directions), `rs` words per row = lane
-// strips in use (27 for the 161-column ONT window): 17.6 KB per pair, 11 warps per SM
-__host__ __device__ constexpr int align2_smem_per_warp(int wa, int rs) { return (((wa + 3) * rs * 4 + 15) & ~15) + kAlign2Aux; }
+// strips in use (27 for the 161-column ONT window): 17.6 KB per pair, 11 warps per SM.  Strips of nine columns (windows up to 288
+// columns, the HiFi preset's 261) keep the ninth column's two bits per half in a byte array beside the words: 38 KB per pair, 5 warps.
+__host__ __device__ constexpr int align2_dir_bytes(int wa, int rs) { return ((wa + 3) * rs * 4 + 15) & ~15; }
+__host__ __device__ constexpr int align2_dirb_bytes(int wa, int rs, bool wide) { return wide ? (((wa + 3) * rs + 15) & ~15) : 0; }
+__host__ __device__ constexpr int align2_smem_per_warp(int wa, int rs, bool wide = false) {
+    return align2_dir_bytes(wa, rs) + align2_dirb_bytes(wa, rs, wide) + kAlign2Aux;
+}
 __device__ __forceinline__ uint32_t pack2_s16(int32_t x) { return ((uint32_t)x & 0xFFFFu) | ((uint32_t)x << 16); }
 __device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t r;
@@ -823,18 +829,21 @@ __device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel
     return r;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 
 template <int CW, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) indel_align2_kernel(const SiteArgs a, int rs) {
-    static_assert(CW <= 8, "two direction bits per column and half");
+    static_assert(CW <= 9, "two direction bits per column and half: eight columns in the word, a ninth in the byte array");
+    constexpr bool WIDE = CW > 8;
     extern __shared__ __align__(16) uint8_t s_align_all[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint8_t* s_base = s_align_all + (size_t)wib * align2_smem_per_warp(a.wa, rs);
+    uint8_t* s_base = s_align_all + (size_t)wib * align2_smem_per_warp(a.wa, rs, WIDE);
     uint32_t* s_dir = reinterpret_cast<uint32_t*>(s_base) + 2 * rs;              // [row -2 .. wa][rs]: half h = slice h, 2 bits per strip column, column 0 highest
-    uint16_t* s_sel = reinterpret_cast<uint16_t*>(s_base + (((a.wa + 3) * rs * 4 + 15) & ~15));   // [272]
-    uint8_t* s_half = reinterpret_cast<uint8_t*>(s_sel + 272 + 32);              // per half: slice[272], rec[272 u16]
+    uint8_t* s_dirb = s_base + align2_dir_bytes(a.wa, rs) + 2 * rs;              // WIDE: column 8 of the strip, bits 1:0 slice 0, 3:2 slice 1
+    uint16_t* s_sel = reinterpret_cast<uint16_t*>(s_base + align2_dir_bytes(a.wa, rs) + align2_dirb_bytes(a.wa, rs, WIDE));   // [kAlign2Sel]
+    uint8_t* s_half = reinterpret_cast<uint8_t*>(s_sel + kAlign2Sel);            // per half: slice[272], rec[272 u16]
     constexpr int kHalfBytes = 272 + 2 * 272;
-    for (int i = lane; i < 3 * rs; i += 32) s_dir[i - 2 * rs] = 0u;             // rows <= 0 = LEFT everywhere: a path that has used up its read walks left
+    for (int i = lane; i < 3 * rs; i += 32) { s_dir[i - 2 * rs] = 0u; if (WIDE) s_dirb[i - 2 * rs] = 0; }   // rows <= 0 = LEFT everywhere: a path that has used up its read walks left
     const uint32_t full = 0xffffffffu;
     const uint32_t kMis = 0xF2F2F2F2u;                                          // 4 * (-4) + 2 in every byte
     const uint32_t kUp = 0xFFF5FFF5u, kLeft = 0xFFF4FFF4u;                      // 4 * (-3) + 1, 4 * (-3) + 0
@@ -907,16 +916,18 @@ __global__ void __launch_bounds__(WARPS * 32) indel_align2_kernel(const SiteArgs
                 const uint32_t sel_next = s_sel[32 + i];
                 if (i >= 1 && i <= nmax && lane <= last_lane) {
                     const uint32_t h_left_cur = lane == 0 ? pack2_s16(-12 * i) : from_left;
-                    uint32_t diag_in = h_left_prev, left = h_left_cur, dw = 0;
+                    uint32_t diag_in = h_left_prev, left = h_left_cur, dw = 0, dwb = 0;
 #pragma unroll
                     for (int k = 0; k < CW; k++) {
                         const uint32_t dg = __vadd2(diag_in, prmt_sx(S[k], kMis, sel));
                         const uint32_t b = __viaddmax_s16x2(left, kLeft, __viaddmax_s16x2(hp[k], kUp, dg));
-                        dw = (dw << 2) | (b & 0x00030003u);
+                        if (k < 8) dw = (dw << 2) | (b & 0x00030003u);
+                        else dwb = b & 0x00030003u;
                         diag_in = hp[k];
                         hp[k] = left = b & 0xFFFCFFFCu;
                     }
                     s_dir[i * rs + lane] = dw;
+                    if (WIDE) s_dirb[i * rs + lane] = (uint8_t)((dwb | (dwb >> 14)) & 0xFu);
                     h_left_prev = h_left_cur;
                     last_out = left;
                 }
@@ -929,7 +940,43 @@ __global__ void __launch_bounds__(WARPS * 32) indel_align2_kernel(const SiteArgs
             // It is branch-free (the two lanes would diverge on every branch), and the direction words of the two rows above the
             // current one are loaded ahead, so that a step's dependent chain is shift, mask, compare, select instead of a
             // shared-memory round trip; only a new strip (every CW-th column) reloads.
-            if (lane < 2 && (lane == 0 || two)) {
+            if (WIDE) {
+                // nine-column strips: a cell's bits come from the word (columns 0-7: bit 16 h + 2 (7 - column)) or from the byte (column
+                // 8: bit 2 h), so the three rows in flight are 64-bit values {word, byte << 32} and the shift walks 32 + 2 h, 16 h, 16 h + 2, ...
+                if (lane < 2 && (lane == 0 || two)) {
+                    const int n_me = lane == 0 ? nh[0] : nh[1];
+                    const uint32_t rec0 = smem_u32(s_half + lane * kHalfBytes + 272);       // rec[0]
+                    const uint32_t a0 = smem_u32(s_dir), b0 = smem_u32(s_dirb);
+                    auto loadw = [&](int32_t idx) { return (uint64_t)lds_u32(a0 + 4u * (uint32_t)idx) | ((uint64_t)lds_u8(b0 + (uint32_t)idx) << 32); };
+                    const int jl0 = (m - 1) / CW, kk0 = (m - 1) - jl0 * CW;
+                    int32_t idx = n_me * rs + jl0;
+                    uint32_t rp = rec0 + 2u * (uint32_t)m;
+                    const uint32_t sh_b = 32u + 2u * lane, sh_a0 = 16u * lane, sh_end = sh_a0 + 16u;
+                    uint32_t sh = kk0 == 8 ? sh_b : sh_a0 + 2u * (uint32_t)(7 - kk0);
+                    uint32_t i2 = (uint32_t)n_me << 1;
+                    uint64_t w_cur = loadw(idx), w_up = loadw(idx - rs), w_up2 = loadw(idx - 2 * rs);
+#pragma unroll 2
+                    while (rp != rec0) {
+                        const uint32_t d = (uint32_t)(w_cur >> sh) & 3u;                    // 2 DIAG, 1 UP, 0 LEFT
+                        const bool cm = d != 1u, rm = d != 0u;
+                        if (cm) asm volatile("st.shared.u16 [%0], %1;" :: "r"(rp), "h"((uint16_t)(i2 | (d >> 1))) : "memory");
+                        rp -= cm ? 2u : 0u;
+                        const uint32_t nsh = sh == sh_b ? sh_a0 : sh + 2u;
+                        sh = cm ? nsh : sh;
+                        i2 -= rm ? 2u : 0u;
+                        idx -= rm ? rs : 0;
+                        const bool wrap = sh == sh_end && rp != rec0;                       // past column 0 of the strip: the strip to the left, its column 8
+                        idx -= wrap ? 1 : 0;
+                        sh = wrap ? sh_b : sh;
+                        const uint64_t nw = loadw(idx - 2 * rs);
+                        w_cur = rm ? w_up : w_cur;
+                        w_up = rm ? w_up2 : w_up;
+                        w_up2 = nw;
+                        if (wrap) { w_cur = loadw(idx); w_up = loadw(idx - rs); }
+                    }
+                    a.e_n[e + lane] = n_me;
+                }
+            } else if (lane < 2 && (lane == 0 || two)) {
                 const int n_me = lane == 0 ? nh[0] : nh[1];
                 const uint32_t rec0 = smem_u32(s_half + lane * kHalfBytes + 272);           // rec[0]
                 const uint32_t rsb = (uint32_t)rs * 4u;

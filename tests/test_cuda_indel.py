@@ -148,16 +148,17 @@ def test_device_allele_prediction_equals_host_alignment(preset, seq):
     assert (dev[~kept] == -1).all()
 
 
-def test_paired_alignment_kernel_equals_one_slice_per_warp_kernel():
-    """indel_align2_kernel (two slices of a site per warp in 16-bit halves, tie bits as directions) against indel_align_kernel (one
-    slice per warp, explicit compares; the kernel the reference fixtures pinned first) on every site of a synthetic ONT contig with
-    indels up to 40 bases, reads ending inside windows and the last window cut by the contig end: identical tensors, consensus
-    strings and site records."""
+@pytest.mark.parametrize("preset,seq", [("ont", "ont"), ("hifi", "pacbio")])
+def test_paired_alignment_kernel_equals_one_slice_per_warp_kernel(preset, seq):
+    """indel_align2_kernel (two slices of a site per warp in 16-bit halves, tie bits as directions; six-column strips for the
+    161-column window, nine-column strips for the HiFi preset's 261) against indel_align_kernel (one slice per warp, explicit
+    compares; the kernel the reference fixtures pinned first) on every site of a synthetic contig with indels up to 40 bases, reads
+    ending inside windows and the last window cut by the contig end: identical tensors, consensus strings and site records."""
     import os
     from nanocaller_b200.host import indel_pileups, snp_pileups
     from nanocaller_b200.synth import make_world
-    rs = make_world(chrom="chrP", preset="ont", contig_len=400_000, seed=43, coverage=25.0, indel_every=700, indel_maxlen=40).reads
-    dct = dict(mincov=4, maxcov=160, seq="ont", del_t=0.6, ins_t=0.4, impute_indel_phase=False, supplementary=False, win_size=40, small_win_size=4)
+    rs = make_world(chrom="chrP", preset=preset, contig_len=400_000, seed=43, coverage=25.0, indel_every=700, indel_maxlen=40).reads
+    dct = dict(mincov=4, maxcov=160, seq=seq, del_t=0.6, ins_t=0.4, impute_indel_phase=False, supplementary=False, win_size=40, small_win_size=4)
     chunks = [{"chrom": "chrP", "start": s, "end": min(400_000, s + 100_000), "ploidy": "diploid"} for s in range(1, 400_000, 100_000)]
     ctx = snp_pileups.context(0)
     out = {}
